@@ -1,0 +1,231 @@
+/*
+ * grb200.h — C ABI of libgrb200.so: B200 (sm_100a) kernels for the two hot paths of the
+ * generative-recommender pipeline (HSTU jagged attention, candidate retrieval).
+ *
+ * Every entry point is what the reference's Python would bind for that call site
+ * (reference paths are relative to /root/reference/src/generative_recommenders_pl/):
+ * raw device pointers, explicit sizes / strides / dtype codes, a cudaStream_t.
+ * No torch types, no C++ exceptions: functions return GRB_OK (0) or a negative error
+ * code; grb_last_error_string() gives the thread-local message.  All functions are
+ * stream-ordered and never synchronise the device or read device memory on the host.
+ * The caller owns every buffer (outputs and workspaces included).
+ */
+#ifndef GRB200_H_
+#define GRB200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRB_VERSION 100
+
+typedef void* grb_stream_t; /* cudaStream_t */
+
+enum grb_status {
+  GRB_OK = 0,
+  GRB_ERR_INVALID_ARG = -1,
+  GRB_ERR_UNSUPPORTED = -2,
+  GRB_ERR_CUDA = -3,
+  GRB_ERR_WORKSPACE = -4
+};
+
+enum grb_dtype { GRB_F32 = 0, GRB_BF16 = 1 };
+
+int grb_version(void);
+const char* grb_last_error_string(void);
+/* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
+int64_t grb_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * a1  models/utils/ops.py:18-38  asynchronous_complete_cumsum  (replaces torch.ops.fbgemm.* :27)
+ *     offsets[0] = 0, offsets[i+1] = sum(lengths[0..i]);  index_bits = 32 | 64.  Bit-exact.
+ * ------------------------------------------------------------------------------------------- */
+int grb_complete_cumsum(const void* lengths, void* offsets, int64_t B, int index_bits,
+                        grb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a2  models/utils/ops.py:41-64  dense_to_jagged  (replaces torch.ops.fbgemm.dense_to_jagged :51)
+ *     dense (B, N, row_bytes) -> jagged (T, row_bytes), out[off[b]+i] = dense[b,i], i < n_b.
+ *     Rows are opaque bytes (any dtype).  n_b = off[b+1]-off[b] is clipped to N.
+ *     dense_batch_stride_bytes: distance between dense[b] and dense[b+1] (0 = N*row_bytes), so
+ *     the slices x[:, :-1] / x[:, 1:] of generative_recommenders.py:409-424 need no copy.
+ *     Also the backward of a3.
+ * ------------------------------------------------------------------------------------------- */
+int grb_dense_to_jagged(const void* dense, const void* offsets, void* jagged, int64_t B,
+                        int64_t N, int64_t row_bytes, int64_t dense_batch_stride_bytes,
+                        int index_bits, grb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a3  models/utils/ops.py:67-114  jagged_to_padded_dense  (replaces torch.ops.fbgemm.* :87)
+ *     jagged (T, row_bytes) -> dense (B, N, row_bytes); rows i >= n_b are filled with the
+ *     elem_bytes-wide pattern `pad_pattern` (1, 2, 4 or 8 bytes; host memory, copied by value).
+ *     Also the backward of a2 (pad = 0).
+ * ------------------------------------------------------------------------------------------- */
+int grb_jagged_to_padded_dense(const void* jagged, const void* offsets, void* dense, int64_t B,
+                               int64_t N, int64_t row_bytes, int64_t dense_batch_stride_bytes,
+                               const void* pad_pattern, int elem_bytes, int index_bits,
+                               grb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a10 models/utils/ops.py:171-187  get_current_embeddings: out[b] = dense[b, lengths[b]-1]
+ *     (index wraps like the reference's flattened gather: lengths[b]==0 reads row b*N-1).
+ *     scatter=1 runs the transpose (backward): dense[b, lengths[b]-1] += out[b] is NOT needed
+ *     because each b hits a distinct row; it writes instead (dense must be pre-zeroed).
+ * ------------------------------------------------------------------------------------------- */
+int grb_gather_last_rows(const void* dense, const void* lengths, void* out, int64_t B, int64_t N,
+                         int64_t row_bytes, int index_bits, int scatter, grb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a4+a5  models/sequential_encoders/hstu.py:71-128 (bias) and :134-205 (attention), fused and
+ *     jagged (no padded intermediates):  for each sequence b, head h, 0 <= j <= i < n_b
+ *        S = q_h[i].k_h[j] + pos_w[N-1+j-i] + ts_w[bucket(|ts[b,i+1] - ts[b,j]|)]
+ *        out_h[i] = sum_j SiLU(S)/N * v_h[j]
+ *     bucket(d) = #{t : thresholds[t] <= d}  (thresholds: the reference's bucketization_fn
+ *     tabulated by the host module; monotone int64 table of num_buckets entries),
+ *     ts index i+1 == N reads ts[b, N-1] (hstu.py:113-115).
+ *     q,k: (T, H*dqk) with row stride ldq/ldk elements; v: (T, H*dv) stride ldv; out (T, H*dv)
+ *     stride ldo.  dtype GRB_F32 (any dqk,dv <= 256; CUDA-core path, fp32 parity) or GRB_BF16
+ *     (dqk = dv = 64 ; tcgen05/TMEM/TMA path, fp32 accumulate).
+ *     timestamps == NULL  <=>  all_timestamps is None in the reference (no bias at all).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct grb_hstu_attn_args {
+  int64_t B;            /* sequences */
+  int64_t N;            /* padded max length: the 1/N scale and the pos_w origin (hstu.py:150,193) */
+  int64_t T;            /* total jagged rows = offsets[B] */
+  int64_t max_len;      /* upper bound of n_b known to the host (<= N); sizes the grid */
+  int32_t H, dqk, dv;
+  int32_t dtype;        /* grb_dtype of q,k,v,out,(dout,dq,dk,dv_grad) */
+  int32_t index_bits;   /* offsets: 32 | 64 */
+  int32_t num_buckets;  /* ts_w has num_buckets+1 entries; thresholds has num_buckets */
+  const void* q; const void* k; const void* v;
+  int64_t ldq, ldk, ldv;
+  const void* offsets;            /* (B+1) */
+  const int64_t* timestamps;      /* (B, N) or NULL */
+  const float* ts_w;              /* (num_buckets+1) fp32 */
+  const float* pos_w;             /* (2N-1) fp32 */
+  const int64_t* bucket_thresholds; /* (num_buckets) ascending */
+  void* out; int64_t ldo;         /* forward output (T, H*dv) */
+  /* backward only */
+  const void* dout; int64_t lddo; /* (T, H*dv) */
+  void* dq; void* dk; void* dv_grad; int64_t lddq, lddk, lddv; /* same dtype as q/k/v */
+  float* dq_accum;                /* fp32 (T, H*dqk) contiguous workspace, zero-filled by caller */
+  float* d_ts_w;                  /* fp32 (num_buckets+1), accumulated (+=) */
+  float* d_pos_w;                 /* fp32 (2N-1), accumulated (+=) */
+} grb_hstu_attn_args;
+
+int grb_hstu_attn_fwd(const grb_hstu_attn_args* a, grb_stream_t stream);
+int grb_hstu_attn_bwd(const grb_hstu_attn_args* a, grb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a6  hstu.py:258-264,402  y = gate * LayerNorm_W(x; eps, no affine)   (gate == NULL: y = LN(x))
+ *     x,gate,y: (rows, W) row strides ldx/ldg/ldy elements.  mean/rstd (rows) fp32 are saved
+ *     for backward.  Backward: dx, dgate from dy (dgate == NULL when gate == NULL).
+ * ------------------------------------------------------------------------------------------- */
+int grb_ln_gate_fwd(const void* x, int64_t ldx, const void* gate, int64_t ldg, void* y,
+                    int64_t ldy, float* mean, float* rstd, int64_t rows, int64_t W, float eps,
+                    int dtype, grb_stream_t stream);
+int grb_ln_gate_bwd(const void* x, int64_t ldx, const void* gate, int64_t ldg, const void* dy,
+                    int64_t lddy, const float* mean, const float* rstd, void* dx, int64_t lddx,
+                    void* dgate, int64_t lddg, int64_t rows, int64_t W, int dtype,
+                    grb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * b2  models/indexing/top_k.py:44-70  MIPSBruteForceTopK  (mm + topk + id gather), fused:
+ *     the (B, X) score matrix never reaches HBM.
+ *
+ *     grb_mips_topk chains, stream-ordered and without host sync:
+ *       1. scores of a strided sample of item tiles           -> ws (B, Xs) fp32
+ *       2. tau[b] = k-th largest sample score (exact)          (>= k items score >= tau[b])
+ *       3. scores of ALL items, keep (score, index) >= tau[b]  -> per-row candidate lists
+ *       4. exact top-k of each candidate list, sorted descending, ties -> lowest index,
+ *          then ids[b, r] = item_ids[index]  (item_ids == NULL: ids = index)
+ *     status[0] (device int32) is set to the largest candidate count if any row overflowed
+ *     `cand_cap`, else left 0; the host wrapper re-runs with a larger workspace in that case.
+ *
+ *     queries (B, D) row stride ldq; items (X, D) row stride ldi (the reference keeps the
+ *     transposed *view* of this contiguous table, candidate_index.py:29).
+ *     dtype GRB_BF16: tcgen05 path (D % 64 == 0, D <= 256);  GRB_F32: CUDA-core path (any D).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct grb_mips_topk_args {
+  int64_t B, X, D;
+  int32_t k;
+  int32_t dtype;
+  const void* queries; int64_t ldq;
+  const void* items; int64_t ldi;
+  const int64_t* item_ids;      /* (X) or NULL */
+  float* out_scores;            /* (B, k) fp32 */
+  int64_t* out_ids;             /* (B, k) int64 */
+  void* workspace; int64_t workspace_bytes;
+  int64_t sample_stride;        /* every sample_stride-th item tile is sampled (>=1); 0 = auto */
+  int64_t cand_cap;             /* candidate capacity per row; 0 = auto */
+  int32_t* status;              /* device int32[2]: [0] overflow count, [1] reserved */
+} grb_mips_topk_args;
+
+/* Bytes of workspace grb_mips_topk needs for these sizes (fills sample_stride/cand_cap if 0). */
+int64_t grb_mips_topk_workspace_bytes(grb_mips_topk_args* a);
+int grb_mips_topk(const grb_mips_topk_args* a, grb_stream_t stream);
+
+/* Exact top-k of per-row candidate lists (also the N3 merge of per-shard top-k after the
+ * NCCL all-gather).  cand_scores/cand_ids: (B, cap) ; counts: (B) int32 or NULL (= cap each).
+ * Sorted descending by score, ties -> lowest id.  If id_map != NULL, out_ids = id_map[cand_id].
+ * Rows with fewer than k candidates are padded with (-inf, -1). */
+int grb_topk_select(const float* cand_scores, const int64_t* cand_ids, const int32_t* counts,
+                    int64_t B, int64_t cap, int32_t k, const int64_t* id_map, float* out_scores,
+                    int64_t* out_ids, grb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * b4/b5 + b1 + b6  negatives_samples/negative_sampler.py:105-131,192-212 ; similarity/
+ *     dot_product.py:61-64 ; losses/autoregressive_losses.py:259-306 — fused sampled softmax:
+ *       e_r   = concat(table0[idx0[n,r]], table1[idx1[n,r]])        (table1 may be NULL)
+ *       neg_r = q[n].e_r / max(||e_r||, eps)   (l2_norm != 0)   |  q[n].e_r  (l2_norm == 0)
+ *       pos   = q[n].p[n]                       (p already normalised by the caller)
+ *       z     = [pos/T, where(neg_id[n,r]==pos_id[n], -5e4, neg_r/T)]   (T = temperature)
+ *       loss_row[n] = -log_softmax(z)[0]
+ *     The (N', R, D) negatives tensor is never materialised.  probs (N', R+1) fp32 = softmax(z)
+ *     is saved for backward.  Backward takes g[n] = dL/dloss_row[n] and produces dq, dp and
+ *     scatter-adds d table0 / d table1 (fp32 atomics; tables' grads must be pre-zeroed or
+ *     accumulate).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct grb_ssl_args {
+  int64_t n_rows;       /* N' */
+  int32_t R;            /* negatives per row */
+  int32_t D;            /* = d0 + d1 */
+  int32_t d0, d1;
+  int32_t l2_norm;      /* normalise gathered negatives */
+  int32_t dtype;        /* GRB_F32 (tables, q, p) */
+  float l2_eps;
+  float temperature;
+  const void* q; int64_t ldq_;          /* (N', D) */
+  const void* p; int64_t ldp;           /* (N', D) positives (normalised) */
+  const void* table0; int64_t ldt0;     /* (X0, d0) */
+  const void* table1; int64_t ldt1;     /* (X1, d1) or NULL */
+  const int64_t* idx0;                  /* (N', R) rows of table0 */
+  const int64_t* idx1;                  /* (N', R) rows of table1 or NULL */
+  const int64_t* pos_ids;               /* (N') */
+  const int64_t* neg_ids;               /* (N', R) ids compared with pos_ids */
+  float* loss_rows;                     /* (N') out */
+  float* probs;                         /* (N', R+1) out (fwd) / in (bwd) */
+  /* backward */
+  const float* g;                       /* (N') */
+  float* dq; float* dp;                 /* (N', D) fp32, written */
+  float* dtable0; float* dtable1;       /* fp32 (X0,d0)/(X1,d1) contiguous, accumulated */
+} grb_ssl_args;
+
+int grb_sampled_softmax_fwd(const grb_ssl_args* a, grb_stream_t stream);
+int grb_sampled_softmax_bwd(const grb_ssl_args* a, grb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Building-block self test (tcgen05 descriptors, TMA swizzle, TMEM layouts).  Runs tiny GEMMs
+ * in every operand mode the attention / retrieval kernels use and writes max-abs errors to
+ * host array errs[n_modes].  Returns the number of modes run, or a negative error code.
+ * This one synchronises the stream (test helper).
+ * ------------------------------------------------------------------------------------------- */
+int grb_selftest_umma(float* errs, int max_modes, grb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRB200_H_ */

@@ -1,0 +1,43 @@
+// hstu_attn_api.cu — C-ABI entry points of the fused HSTU attention; picks the tcgen05 path
+// (bf16, head dims 64) or the CUDA-core path (fp32 / other shapes).  No CPU fallback.
+#include "common.cuh"
+#include <cstdlib>
+
+namespace grb {
+int check_attn_args(const grb_hstu_attn_args* a, bool bwd);
+int hstu_attn_fwd_simt_dispatch(const grb_hstu_attn_args* a, cudaStream_t st);
+int hstu_attn_bwd_simt_dispatch(const grb_hstu_attn_args* a, cudaStream_t st);
+bool hstu_attn_fwd_sm100_supported(const grb_hstu_attn_args* a);
+bool hstu_attn_bwd_sm100_supported(const grb_hstu_attn_args* a);
+int hstu_attn_fwd_sm100(const grb_hstu_attn_args* a, cudaStream_t st);
+int hstu_attn_bwd_sm100(const grb_hstu_attn_args* a, cudaStream_t st);
+
+static bool force_cuda_core() {
+  const char* e = std::getenv("GRB_FORCE_CUDA_CORE");
+  return e && e[0] == '1';
+}
+}  // namespace grb
+
+using namespace grb;
+
+extern "C" {
+
+int grb_hstu_attn_fwd(const grb_hstu_attn_args* a, grb_stream_t stream) {
+  int rc = check_attn_args(a, false);
+  if (rc != GRB_OK) return rc;
+  GRB_REQUIRE(a->B <= 65535 && a->H <= 65535, GRB_ERR_UNSUPPORTED, "hstu_attn: B,H <= 65535");
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  if (!force_cuda_core() && hstu_attn_fwd_sm100_supported(a)) return hstu_attn_fwd_sm100(a, st);
+  return hstu_attn_fwd_simt_dispatch(a, st);
+}
+
+int grb_hstu_attn_bwd(const grb_hstu_attn_args* a, grb_stream_t stream) {
+  int rc = check_attn_args(a, true);
+  if (rc != GRB_OK) return rc;
+  GRB_REQUIRE(a->B <= 65535 && a->H <= 65535, GRB_ERR_UNSUPPORTED, "hstu_attn: B,H <= 65535");
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  if (!force_cuda_core() && hstu_attn_bwd_sm100_supported(a)) return hstu_attn_bwd_sm100(a, st);
+  return hstu_attn_bwd_simt_dispatch(a, st);
+}
+
+}

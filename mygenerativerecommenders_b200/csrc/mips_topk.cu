@@ -1,0 +1,432 @@
+// mips_topk.cu — brute-force MIPS top-k with the score matrix kept out of HBM.
+//
+// Reference: /root/reference/src/generative_recommenders_pl/models/indexing/top_k.py:44-70
+//   all_logits = mm(q, items_t) ; topk(all_logits, k, sorted) ; item_ids[idx]
+// and the caller models/indexing/candidate_index.py:107-164 (k' = k + #invalid ids).
+//
+// Exact, four stream-ordered phases (see include/grb200.h):
+//   1. score a strided sample of 128-item tiles                    -> (B, Xs) fp32
+//   2. tau[b] = k-th largest sample score (radix select)           -> >= k items score >= tau[b]
+//   3. score ALL tiles with the same code path (bit-identical scores for sampled items) and
+//      append (score, index) with score >= tau[b] to row b's candidate list
+//   4. exact select + bitonic sort of each candidate list (ties -> lowest index), id gather.
+// Expected candidates per row ~ k * stride; with Xs ~ sqrt(2 k X) the extra traffic is
+// O(B sqrt(k X)) instead of the reference's O(B X).
+//
+// This file holds the CUDA-core score kernel (fp32 tables, any D — the reference's dtype) and
+// the selection kernels.  The tcgen05 score kernel for bf16 tables is in mips_sm100.cu and
+// plugs into the same epilogue contract (ScoreEpi).
+#include "common.cuh"
+#include "mips_epilogue.cuh"
+#include <cmath>
+#include <cfloat>
+
+namespace grb {
+
+// ---------------------------------------------------------------------------------------------
+// CUDA-core score kernel: 128 queries x 128 items per CTA, BK = 16, 8x8 per thread.
+// ---------------------------------------------------------------------------------------------
+constexpr int SG_BM = 128, SG_BN = MIPS_TILE_N, SG_BK = 16, SG_LD = 132, SG_THREADS = 256;
+
+template <typename T> __device__ __forceinline__ float ld_as_f32(const T* p);
+template <> __device__ __forceinline__ float ld_as_f32<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float ld_as_f32<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat162float(*p);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SG_THREADS) mips_scores_simt(
+    const T* __restrict__ Q, int64_t ldq, const T* __restrict__ I, int64_t ldi, int64_t B,
+    int64_t X, int D, ScoreEpi epi) {
+  __shared__ __align__(16) float As[SG_BK][SG_LD];
+  __shared__ __align__(16) float Bs[SG_BK][SG_LD];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t tile = (int64_t) blockIdx.x * epi.tile_stride;
+  const int64_t n0 = tile * SG_BN;
+  const int64_t m0 = (int64_t) blockIdx.y * SG_BM;
+
+  float acc[8][8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[a][c] = 0.f;
+
+  const int lr = tid >> 1, lk = (tid & 1) * 8;
+  for (int k0 = 0; k0 < D; k0 += SG_BK) {
+    {
+      const int64_t row = m0 + lr;
+      const T* src = Q + row * ldq + k0 + lk;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        As[lk + i][lr] = (row < B && k0 + lk + i < D) ? ld_as_f32<T>(src + i) : 0.f;
+      const int64_t it = n0 + lr;
+      const T* srcb = I + it * ldi + k0 + lk;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        Bs[lk + i][lr] = (it < X && k0 + lk + i < D) ? ld_as_f32<T>(srcb + i) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < SG_BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8 + 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[a][c] = fmaf(av[a], bv[c], acc[a][c]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const int64_t row = m0 + ty * 8 + a;
+    if (row >= B) continue;
+    score_epilogue_row8(epi, row, (int64_t) blockIdx.x, n0 + tx * 8, tx * 8, X, acc[a]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phase 2: k-th largest of each row (radix select, 4 x 8 bits).  One CTA per row.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t fkey(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+constexpr int SEL_THREADS = 256;
+
+// Finds the kk-th largest (1-based) key among keys matching (key & mask) == prefix restricted to
+// digit `shift`.  hist must be 256 ints of smem; result broadcast through sh[0..2].
+__device__ __forceinline__ void pick_digit_desc(int* hist, int* sh, int kk) {
+  if (threadIdx.x == 0) {
+    int cum = 0, digit = 0, rem = kk, cnt = 0;
+    for (int b = 255; b >= 0; --b) {
+      const int h = hist[b];
+      if (cum + h >= kk) { digit = b; rem = kk - cum; cnt = h; break; }
+      cum += h;
+    }
+    sh[0] = digit; sh[1] = rem; sh[2] = cnt;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) row_kth_largest_kernel(
+    const float* __restrict__ scores, int64_t ld, int64_t L, int k, float* __restrict__ tau) {
+  __shared__ int hist[256];
+  __shared__ int sh[3];
+  const float* x = scores + (int64_t) blockIdx.x * ld;
+  uint32_t prefix = 0, mask = 0;
+  int kk = k;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += SEL_THREADS) hist[i] = 0;
+    __syncthreads();
+    for (int64_t i = threadIdx.x; i < L; i += SEL_THREADS) {
+      const uint32_t key = fkey(x[i]);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1);
+    }
+    __syncthreads();
+    pick_digit_desc(hist, sh, kk);
+    prefix |= (uint32_t) sh[0] << shift;
+    mask |= 255u << shift;
+    kk = sh[1];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) tau[blockIdx.x] = fkey_inv(prefix);
+}
+
+// Phase 3 when every tile was sampled (small corpora): filter the stored scores.
+__global__ void filter_dense_kernel(const float* __restrict__ scores, int64_t ld, int64_t X,
+                                    ScoreEpi epi) {
+  const int64_t row = blockIdx.y;
+  const int64_t col = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= X) return;
+  const float s = scores[row * ld + col];
+  if (s >= epi.tau[row]) append_candidate(epi, row, s, col);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phase 4 / shard merge: exact top-k of a candidate list, sorted, ties -> lowest id.
+// ---------------------------------------------------------------------------------------------
+constexpr int SEL_KMAX = 2048;
+
+template <typename IdT>
+__global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(
+    const float* __restrict__ cs, const IdT* __restrict__ cid, const int32_t* __restrict__ counts,
+    int64_t cap, int k, const int64_t* __restrict__ id_map, float* __restrict__ out_scores,
+    int64_t* __restrict__ out_ids, int32_t* __restrict__ status) {
+  __shared__ int hist[256];
+  __shared__ int sh[3];
+  __shared__ uint32_t skey[SEL_KMAX];
+  __shared__ long long sid[SEL_KMAX];
+  __shared__ int slot;
+  const int64_t row = blockIdx.x;
+  int64_t c = counts ? (int64_t) counts[row] : cap;
+  if (c > cap) {
+    if (threadIdx.x == 0 && status) atomicMax(status, (int) (c > 0x7fffffff ? 0x7fffffff : c));
+    c = cap;
+  }
+  const float* x = cs + row * cap;
+  const IdT* ids = cid + row * cap;
+  const int tid = threadIdx.x;
+
+  uint32_t key_k = 0;        // every key >= key_k qualifies when c <= k
+  long long id_thr = LLONG_MAX;
+  if (c > k) {
+    uint32_t prefix = 0, mask = 0;
+    int kk = k, ties = 0;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      for (int i = tid; i < 256; i += SEL_THREADS) hist[i] = 0;
+      __syncthreads();
+      for (int64_t i = tid; i < c; i += SEL_THREADS) {
+        const uint32_t key = fkey(x[i]);
+        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1);
+      }
+      __syncthreads();
+      pick_digit_desc(hist, sh, kk);
+      prefix |= (uint32_t) sh[0] << shift;
+      mask |= 255u << shift;
+      kk = sh[1];
+      ties = sh[2];
+      __syncthreads();
+    }
+    key_k = prefix;
+    if (ties > kk) {
+      // need the kk smallest ids among the `ties` entries with key == key_k:
+      // radix select (ascending) over the 64-bit ids, 8 x 8 bits.
+      unsigned long long ipre = 0, imask = 0;
+      int need = kk;
+      for (int shift = 56; shift >= 0; shift -= 8) {
+        for (int i = tid; i < 256; i += SEL_THREADS) hist[i] = 0;
+        __syncthreads();
+        for (int64_t i = tid; i < c; i += SEL_THREADS) {
+          if (fkey(x[i]) != key_k) continue;
+          const unsigned long long u = (unsigned long long) (long long) ids[i];
+          if ((u & imask) == ipre) atomicAdd(&hist[(int) ((u >> shift) & 255ull)], 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+          int cum = 0, digit = 255, rem = need;
+          for (int b = 0; b < 256; ++b) {
+            const int h = hist[b];
+            if (cum + h >= need) { digit = b; rem = need - cum; break; }
+            cum += h;
+          }
+          sh[0] = digit; sh[1] = rem;
+        }
+        __syncthreads();
+        ipre |= (unsigned long long) sh[0] << shift;
+        imask |= 255ull << shift;
+        need = sh[1];
+        __syncthreads();
+      }
+      id_thr = (long long) ipre;
+    }
+  }
+  // collect
+  if (tid == 0) slot = 0;
+  int np2 = 1;
+  while (np2 < k) np2 <<= 1;
+  for (int i = tid; i < np2; i += SEL_THREADS) { skey[i] = 0u; sid[i] = LLONG_MAX; }
+  __syncthreads();
+  for (int64_t i = tid; i < c; i += SEL_THREADS) {
+    const uint32_t key = fkey(x[i]);
+    const long long id = (long long) ids[i];
+    if (key > key_k || (key == key_k && id <= id_thr)) {
+      const int s = atomicAdd(&slot, 1);
+      if (s < k) { skey[s] = key; sid[s] = id; }
+    }
+  }
+  __syncthreads();
+  // bitonic sort, order: key descending, id ascending
+  for (int size = 2; size <= np2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < np2; i += SEL_THREADS) {
+        const int j = i ^ stride;
+        if (j > i) {
+          const bool up = (i & size) == 0;  // "up" block: best first
+          const uint32_t ki = skey[i], kj = skey[j];
+          const long long ii = sid[i], ij = sid[j];
+          const bool i_before_j = (ki > kj) || (ki == kj && ii < ij);
+          if (i_before_j != up) { skey[i] = kj; skey[j] = ki; sid[i] = ij; sid[j] = ii; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const int filled = (int) (c < k ? c : k);
+  for (int r = tid; r < k; r += SEL_THREADS) {
+    float s = -INFINITY;
+    long long id = -1;
+    if (r < filled) {
+      s = fkey_inv(skey[r]);
+      id = sid[r];
+      if (id_map) id = id_map[id];
+    }
+    out_scores[row * k + r] = s;
+    out_ids[row * k + r] = id;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Orchestration
+// ---------------------------------------------------------------------------------------------
+struct MipsPlan {
+  int64_t n_tiles, stride, n_sample_tiles, Xs, cap;
+  int64_t off_tau, off_counts, off_sample, off_cscores, off_cidx, total;
+};
+
+static int64_t align256(int64_t x) { return (x + 255) & ~255ll; }
+
+static int plan_mips(const grb_mips_topk_args* a, MipsPlan* P) {
+  GRB_REQUIRE(a && a->B >= 0 && a->X > 0 && a->D > 0 && a->k > 0, GRB_ERR_INVALID_ARG,
+              "mips_topk: bad sizes");
+  GRB_REQUIRE(a->k <= a->X, GRB_ERR_INVALID_ARG, "mips_topk: k=%d exceeds corpus size %lld",
+              a->k, (long long) a->X);
+  GRB_REQUIRE(a->k <= SEL_KMAX, GRB_ERR_UNSUPPORTED, "mips_topk: k=%d exceeds %d", a->k,
+              SEL_KMAX);
+  GRB_REQUIRE(a->X < (1ll << 31), GRB_ERR_UNSUPPORTED, "mips_topk: corpus too large");
+  P->n_tiles = ceil_div(a->X, MIPS_TILE_N);
+  int64_t stride = a->sample_stride;
+  if (stride <= 0) {
+    // sample ~ sqrt(2 k X) items, at least 4k, at most everything
+    double want = std::sqrt(2.0 * (double) a->k * (double) a->X);
+    if (want < 4.0 * a->k) want = 4.0 * a->k;
+    int64_t want_tiles = (int64_t) std::ceil(want / MIPS_TILE_N);
+    if (want_tiles < 1) want_tiles = 1;
+    stride = P->n_tiles / want_tiles;
+    if (stride < 1) stride = 1;
+  }
+  if (stride > P->n_tiles) stride = P->n_tiles;
+  P->stride = stride;
+  P->n_sample_tiles = ceil_div(P->n_tiles, stride);
+  P->Xs = P->n_sample_tiles * MIPS_TILE_N;
+  // the sample must hold at least k real items: the last sampled tile may be partial
+  const int64_t real_in_sample = (P->n_sample_tiles - 1) * MIPS_TILE_N +
+      ((P->n_sample_tiles - 1) * stride == P->n_tiles - 1
+           ? (a->X - (P->n_tiles - 1) * MIPS_TILE_N) : MIPS_TILE_N);
+  if (real_in_sample < a->k) {  // tiny corpora: sample everything
+    P->stride = 1; P->n_sample_tiles = P->n_tiles; P->Xs = P->n_tiles * MIPS_TILE_N;
+  }
+  int64_t cap = a->cand_cap;
+  if (cap <= 0) cap = 3 * (int64_t) a->k * P->stride + 1024;
+  if (cap > a->X) cap = a->X;
+  if (cap < a->k) cap = a->k;
+  P->cap = cap;
+  int64_t o = 0;
+  P->off_tau = o;     o = align256(o + a->B * 4);
+  P->off_counts = o;  o = align256(o + a->B * 4);
+  P->off_sample = o;  o = align256(o + a->B * P->Xs * 4);
+  P->off_cscores = o; o = align256(o + a->B * P->cap * 4);
+  P->off_cidx = o;    o = align256(o + a->B * P->cap * 4);
+  P->total = o;
+  return GRB_OK;
+}
+
+// implemented in mips_sm100.cu (tcgen05 score kernel, bf16 tables)
+int mips_scores_sm100(const grb_mips_topk_args* a, const ScoreEpi& epi, int64_t n_launch_tiles,
+                      cudaStream_t st);
+bool mips_sm100_supported(const grb_mips_topk_args* a);
+
+static int launch_scores(const grb_mips_topk_args* a, const ScoreEpi& epi, int64_t n_launch_tiles,
+                         cudaStream_t st) {
+  if (a->dtype == GRB_BF16 && mips_sm100_supported(a))
+    return mips_scores_sm100(a, epi, n_launch_tiles, st);
+  dim3 grid((unsigned) n_launch_tiles, (unsigned) ceil_div(a->B, SG_BM));
+  if (a->dtype == GRB_F32)
+    mips_scores_simt<float><<<grid, SG_THREADS, 0, st>>>(
+        (const float*) a->queries, a->ldq, (const float*) a->items, a->ldi, a->B, a->X,
+        (int) a->D, epi);
+  else
+    mips_scores_simt<__nv_bfloat16><<<grid, SG_THREADS, 0, st>>>(
+        (const __nv_bfloat16*) a->queries, a->ldq, (const __nv_bfloat16*) a->items, a->ldi, a->B,
+        a->X, (int) a->D, epi);
+  GRB_LAUNCH_OK();
+  return GRB_OK;
+}
+
+}  // namespace grb
+
+using namespace grb;
+
+extern "C" {
+
+int64_t grb_mips_topk_workspace_bytes(grb_mips_topk_args* a) {
+  MipsPlan P{};
+  int rc = plan_mips(a, &P);
+  if (rc != GRB_OK) return rc;
+  a->sample_stride = P.stride;
+  a->cand_cap = P.cap;
+  return P.total;
+}
+
+int grb_mips_topk(const grb_mips_topk_args* a, grb_stream_t stream) {
+  MipsPlan P{};
+  int rc = plan_mips(a, &P);
+  if (rc != GRB_OK) return rc;
+  GRB_REQUIRE(a->dtype == GRB_F32 || a->dtype == GRB_BF16, GRB_ERR_INVALID_ARG,
+              "mips_topk: dtype");
+  GRB_REQUIRE(a->queries && a->items && a->out_scores && a->out_ids && a->workspace &&
+                  a->status,
+              GRB_ERR_INVALID_ARG, "mips_topk: null pointer");
+  GRB_REQUIRE(a->workspace_bytes >= P.total, GRB_ERR_WORKSPACE,
+              "mips_topk: workspace %lld < required %lld", (long long) a->workspace_bytes,
+              (long long) P.total);
+  GRB_REQUIRE(a->B <= 65535ll * SG_BM, GRB_ERR_UNSUPPORTED, "mips_topk: too many queries");
+  if (a->B == 0) return GRB_OK;
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  auto ws = reinterpret_cast<unsigned char*>(a->workspace);
+  float* tau = reinterpret_cast<float*>(ws + P.off_tau);
+  int32_t* counts = reinterpret_cast<int32_t*>(ws + P.off_counts);
+  float* sample = reinterpret_cast<float*>(ws + P.off_sample);
+  float* cscores = reinterpret_cast<float*>(ws + P.off_cscores);
+  int32_t* cidx = reinterpret_cast<int32_t*>(ws + P.off_cidx);
+  GRB_CUDA_OK(cudaMemsetAsync(counts, 0, a->B * 4, st));
+
+  ScoreEpi epi{};
+  epi.mode = MIPS_EPI_STORE; epi.tile_stride = P.stride; epi.Xs = P.Xs; epi.out = sample;
+  epi.tau = tau; epi.counts = counts; epi.cscores = cscores; epi.cidx = cidx; epi.cap = P.cap;
+  rc = launch_scores(a, epi, P.n_sample_tiles, st);
+  if (rc != GRB_OK) return rc;
+
+  row_kth_largest_kernel<<<(unsigned) a->B, SEL_THREADS, 0, st>>>(sample, P.Xs, P.Xs, a->k, tau);
+  GRB_LAUNCH_OK();
+
+  if (P.stride == 1) {
+    dim3 grid((unsigned) ceil_div(a->X, 256), (unsigned) a->B);
+    GRB_REQUIRE(a->B <= 65535, GRB_ERR_UNSUPPORTED, "mips_topk: B > 65535 on the dense path");
+    epi.mode = MIPS_EPI_FILTER;
+    filter_dense_kernel<<<grid, 256, 0, st>>>(sample, P.Xs, a->X, epi);
+    GRB_LAUNCH_OK();
+  } else {
+    epi.mode = MIPS_EPI_FILTER; epi.tile_stride = 1;
+    rc = launch_scores(a, epi, P.n_tiles, st);
+    if (rc != GRB_OK) return rc;
+  }
+  topk_select_kernel<int32_t><<<(unsigned) a->B, SEL_THREADS, 0, st>>>(
+      cscores, cidx, counts, P.cap, a->k, a->item_ids, a->out_scores, a->out_ids, a->status);
+  GRB_LAUNCH_OK();
+  return GRB_OK;
+}
+
+int grb_topk_select(const float* cand_scores, const int64_t* cand_ids, const int32_t* counts,
+                    int64_t B, int64_t cap, int32_t k, const int64_t* id_map, float* out_scores,
+                    int64_t* out_ids, grb_stream_t stream) {
+  GRB_REQUIRE(cand_scores && cand_ids && out_scores && out_ids && B >= 0 && cap > 0 && k > 0,
+              GRB_ERR_INVALID_ARG, "topk_select: bad arguments");
+  GRB_REQUIRE(k <= SEL_KMAX, GRB_ERR_UNSUPPORTED, "topk_select: k=%d exceeds %d", k, SEL_KMAX);
+  if (B == 0) return GRB_OK;
+  topk_select_kernel<int64_t><<<(unsigned) B, SEL_THREADS, 0,
+                                reinterpret_cast<cudaStream_t>(stream)>>>(
+      cand_scores, cand_ids, counts, cap, k, id_map, out_scores, out_ids, nullptr);
+  GRB_LAUNCH_OK();
+  return GRB_OK;
+}
+
+}

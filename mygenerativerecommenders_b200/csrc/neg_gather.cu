@@ -1,0 +1,213 @@
+// neg_gather.cu — fused sampled-softmax: negative gather . dot (+L2 norm) + collision mask +
+// log-softmax, forward and backward.  The (N', R, D) negatives tensor is never materialised.
+//
+// Reference (under /root/reference/src/generative_recommenders_pl/models/):
+//   negatives_samples/negative_sampler.py:31-37   _maybe_l2_norm: x / clamp(||x||, eps)
+//   negatives_samples/negative_sampler.py:123-131 gather of sampled ids (Local sampler; this
+//        fork's embedding = concat(item_emb[id], year_emb[year_lookup[id]]), embeddings.py:94-97)
+//   negatives_samples/negative_sampler.py:208-211 gather from the in-batch cache
+//   similarity/dot_product.py:61-64               bmm((N',R,D),(N',D,1))
+//   losses/autoregressive_losses.py:279-306       /T, where(==, -5e4), -log_softmax[:,0]
+//
+// Mapping: one warp per supervised position n; lanes stride over the D embedding columns, so
+// every gathered row is read with coalesced 128-byte requests; dot and squared norm are reduced
+// with warp shuffles.  HBM/L2-bound: bytes = N'.R.(D.4 + 16) + 2.N'.D.4 + N'.(R+1).4.
+#include "common.cuh"
+
+namespace grb {
+
+constexpr int SSL_WARPS = 4;
+
+struct SslP {
+  int64_t n_rows;
+  int R, D, d0, d1, l2;
+  float eps, temp;
+  const float* q; int64_t ldq;
+  const float* p; int64_t ldp;
+  const float* t0; int64_t ldt0;
+  const float* t1; int64_t ldt1;
+  const int64_t* idx0; const int64_t* idx1;
+  const int64_t* pos_ids; const int64_t* neg_ids;
+  float* loss_rows; float* probs;
+  const float* g; float* dq; float* dp; float* dt0; float* dt1;
+};
+
+template <int NPL>
+__device__ __forceinline__ void gather_row(const SslP& P, int64_t i0, int64_t i1, int lane,
+                                           float (&e)[NPL]) {
+#pragma unroll
+  for (int u = 0; u < NPL; ++u) {
+    const int c = lane + 32 * u;
+    float v = 0.f;
+    if (c < P.d0) v = __ldg(P.t0 + i0 * P.ldt0 + c);
+    else if (c < P.D) v = __ldg(P.t1 + i1 * P.ldt1 + (c - P.d0));
+    e[u] = v;
+  }
+}
+
+template <int NPL>
+__global__ void __launch_bounds__(SSL_WARPS * 32) ssl_fwd_kernel(SslP P) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n = (int64_t) blockIdx.x * SSL_WARPS + (threadIdx.x >> 5);
+  if (n >= P.n_rows) return;
+  float qv[NPL], e[NPL];
+  float pd = 0.f;
+#pragma unroll
+  for (int u = 0; u < NPL; ++u) {
+    const int c = lane + 32 * u;
+    qv[u] = c < P.D ? P.q[n * P.ldq + c] : 0.f;
+    const float pv = c < P.D ? P.p[n * P.ldp + c] : 0.f;
+    pd = fmaf(qv[u], pv, pd);
+  }
+  const float zpos = warp_sum(pd) / P.temp;
+  const int64_t pid = P.pos_ids[n];
+  float* pr = P.probs + n * (int64_t) (P.R + 1);
+  float m = zpos;
+  for (int r = 0; r < P.R; ++r) {
+    const int64_t i0 = P.idx0[n * P.R + r];
+    const int64_t i1 = P.idx1 ? P.idx1[n * P.R + r] : 0;
+    gather_row<NPL>(P, i0, i1, lane, e);
+    float dot = 0.f, nn = 0.f;
+#pragma unroll
+    for (int u = 0; u < NPL; ++u) { dot = fmaf(qv[u], e[u], dot); nn = fmaf(e[u], e[u], nn); }
+    dot = warp_sum(dot);
+    float z;
+    if (P.l2) {
+      nn = warp_sum(nn);
+      z = dot / fmaxf(sqrtf(nn), P.eps);
+    } else {
+      z = dot;
+    }
+    z = (P.neg_ids[n * P.R + r] == pid) ? -5e4f : z / P.temp;
+    if (lane == 0) pr[r + 1] = z;  // stash logits, normalised below
+    m = fmaxf(m, z);
+  }
+  __syncwarp();
+  float se = 0.f;
+  for (int r = lane; r < P.R; r += 32) se += expf(pr[r + 1] - m);
+  se = warp_sum(se) + expf(zpos - m);
+  const float lse = logf(se);
+  for (int r = lane; r < P.R; r += 32) pr[r + 1] = expf(pr[r + 1] - m - lse);
+  if (lane == 0) {
+    pr[0] = expf(zpos - m - lse);
+    P.loss_rows[n] = -(zpos - m - lse);
+  }
+}
+
+template <int NPL>
+__global__ void __launch_bounds__(SSL_WARPS * 32) ssl_bwd_kernel(SslP P) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n = (int64_t) blockIdx.x * SSL_WARPS + (threadIdx.x >> 5);
+  if (n >= P.n_rows) return;
+  float qv[NPL], e[NPL], dqa[NPL];
+  const float g = P.g[n];
+  const float* pr = P.probs + n * (int64_t) (P.R + 1);
+  const float dzpos = g * (pr[0] - 1.0f) / P.temp;
+#pragma unroll
+  for (int u = 0; u < NPL; ++u) {
+    const int c = lane + 32 * u;
+    qv[u] = c < P.D ? P.q[n * P.ldq + c] : 0.f;
+    const float pv = c < P.D ? P.p[n * P.ldp + c] : 0.f;
+    dqa[u] = dzpos * pv;
+    if (c < P.D) P.dp[n * (int64_t) P.D + c] = dzpos * qv[u];
+  }
+  const int64_t pid = P.pos_ids[n];
+  if (g != 0.f) {
+    for (int r = 0; r < P.R; ++r) {
+      if (P.neg_ids[n * P.R + r] == pid) continue;  // constant -5e4: no gradient (warp-uniform)
+      const float dl = g * pr[r + 1] / P.temp;
+      if (dl == 0.f) continue;                       // warp-uniform
+      const int64_t i0 = P.idx0[n * P.R + r];
+      const int64_t i1 = P.idx1 ? P.idx1[n * P.R + r] : 0;
+      gather_row<NPL>(P, i0, i1, lane, e);
+      float a = 1.0f, bcoef = 0.f;  // d e = dl * (a * q - bcoef * e) ; d q += dl * a * e
+      if (P.l2) {
+        float dot = 0.f, nn = 0.f;
+#pragma unroll
+        for (int u = 0; u < NPL; ++u) { dot = fmaf(qv[u], e[u], dot); nn = fmaf(e[u], e[u], nn); }
+        dot = warp_sum(dot);
+        nn = warp_sum(nn);
+        const float nrm = sqrtf(nn);
+        if (nrm > P.eps) { a = 1.0f / nrm; bcoef = dot / (nrm * nn); }
+        else { a = 1.0f / P.eps; bcoef = 0.f; }      // clamp branch: denominator is constant
+      }
+#pragma unroll
+      for (int u = 0; u < NPL; ++u) {
+        const int c = lane + 32 * u;
+        dqa[u] = fmaf(dl * a, e[u], dqa[u]);
+        const float de = dl * (a * qv[u] - bcoef * e[u]);
+        if (c < P.d0) atomicAdd(P.dt0 + i0 * (int64_t) P.d0 + c, de);
+        else if (c < P.D) atomicAdd(P.dt1 + i1 * (int64_t) P.d1 + (c - P.d0), de);
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < NPL; ++u) {
+    const int c = lane + 32 * u;
+    if (c < P.D) P.dq[n * (int64_t) P.D + c] = dqa[u];
+  }
+}
+
+static int make(const grb_ssl_args* a, SslP* P, bool bwd) {
+  GRB_REQUIRE(a != nullptr, GRB_ERR_INVALID_ARG, "sampled_softmax: null args");
+  GRB_REQUIRE(a->dtype == GRB_F32, GRB_ERR_UNSUPPORTED, "sampled_softmax: only fp32 tables");
+  GRB_REQUIRE(a->n_rows >= 0 && a->R > 0 && a->D > 0 && a->D <= 256 && a->d0 > 0 &&
+                  a->d0 + a->d1 == a->D && a->d1 >= 0,
+              GRB_ERR_INVALID_ARG, "sampled_softmax: bad sizes (D=%d d0=%d d1=%d R=%d)", a->D,
+              a->d0, a->d1, a->R);
+  GRB_REQUIRE(a->q && a->p && a->table0 && a->idx0 && a->pos_ids && a->neg_ids && a->probs,
+              GRB_ERR_INVALID_ARG, "sampled_softmax: null tensor");
+  GRB_REQUIRE((a->d1 == 0) == (a->table1 == nullptr), GRB_ERR_INVALID_ARG,
+              "sampled_softmax: table1/d1 mismatch");
+  GRB_REQUIRE(a->d1 == 0 || a->idx1, GRB_ERR_INVALID_ARG, "sampled_softmax: idx1 is null");
+  GRB_REQUIRE(a->temperature > 0.f, GRB_ERR_INVALID_ARG, "sampled_softmax: temperature <= 0");
+  if (!bwd) GRB_REQUIRE(a->loss_rows, GRB_ERR_INVALID_ARG, "sampled_softmax_fwd: loss_rows null");
+  else
+    GRB_REQUIRE(a->g && a->dq && a->dp && a->dtable0 && (a->d1 == 0 || a->dtable1),
+                GRB_ERR_INVALID_ARG, "sampled_softmax_bwd: null gradient buffer");
+  P->n_rows = a->n_rows; P->R = a->R; P->D = a->D; P->d0 = a->d0; P->d1 = a->d1;
+  P->l2 = a->l2_norm; P->eps = a->l2_eps; P->temp = a->temperature;
+  P->q = (const float*) a->q; P->ldq = a->ldq_; P->p = (const float*) a->p; P->ldp = a->ldp;
+  P->t0 = (const float*) a->table0; P->ldt0 = a->ldt0;
+  P->t1 = (const float*) a->table1; P->ldt1 = a->ldt1;
+  P->idx0 = a->idx0; P->idx1 = a->idx1; P->pos_ids = a->pos_ids; P->neg_ids = a->neg_ids;
+  P->loss_rows = a->loss_rows; P->probs = a->probs; P->g = a->g; P->dq = a->dq; P->dp = a->dp;
+  P->dt0 = a->dtable0; P->dt1 = a->dtable1;
+  return GRB_OK;
+}
+
+}  // namespace grb
+
+using namespace grb;
+
+extern "C" {
+
+int grb_sampled_softmax_fwd(const grb_ssl_args* a, grb_stream_t stream) {
+  SslP P{};
+  int rc = make(a, &P, false);
+  if (rc != GRB_OK) return rc;
+  if (P.n_rows == 0) return GRB_OK;
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned) ceil_div(P.n_rows, SSL_WARPS);
+  if (P.D <= 64) ssl_fwd_kernel<2><<<grid, SSL_WARPS * 32, 0, st>>>(P);
+  else if (P.D <= 128) ssl_fwd_kernel<4><<<grid, SSL_WARPS * 32, 0, st>>>(P);
+  else ssl_fwd_kernel<8><<<grid, SSL_WARPS * 32, 0, st>>>(P);
+  GRB_LAUNCH_OK();
+  return GRB_OK;
+}
+
+int grb_sampled_softmax_bwd(const grb_ssl_args* a, grb_stream_t stream) {
+  SslP P{};
+  int rc = make(a, &P, true);
+  if (rc != GRB_OK) return rc;
+  if (P.n_rows == 0) return GRB_OK;
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned) ceil_div(P.n_rows, SSL_WARPS);
+  if (P.D <= 64) ssl_bwd_kernel<2><<<grid, SSL_WARPS * 32, 0, st>>>(P);
+  else if (P.D <= 128) ssl_bwd_kernel<4><<<grid, SSL_WARPS * 32, 0, st>>>(P);
+  else ssl_bwd_kernel<8><<<grid, SSL_WARPS * 32, 0, st>>>(P);
+  GRB_LAUNCH_OK();
+  return GRB_OK;
+}
+
+}
