@@ -1,0 +1,170 @@
+"""ctypes binding of libgrb200.so (the C ABI in include/grb200.h).
+
+There is deliberately no fallback of any kind: if the shared library is missing or a call
+fails, the error is raised to the caller.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import torch
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libgrb200.so"
+
+GRB_OK = 0
+GRB_ERR_INVALID_ARG = -1
+GRB_ERR_UNSUPPORTED = -2
+GRB_ERR_CUDA = -3
+GRB_ERR_WORKSPACE = -4
+GRB_F32 = 0
+GRB_BF16 = 1
+
+c_i64 = C.c_int64
+c_i32 = C.c_int32
+c_vp = C.c_void_p
+
+
+class HstuAttnArgs(C.Structure):
+    _fields_ = [
+        ("B", c_i64), ("N", c_i64), ("T", c_i64), ("max_len", c_i64),
+        ("H", c_i32), ("dqk", c_i32), ("dv", c_i32),
+        ("dtype", c_i32), ("index_bits", c_i32), ("num_buckets", c_i32),
+        ("q", c_vp), ("k", c_vp), ("v", c_vp),
+        ("ldq", c_i64), ("ldk", c_i64), ("ldv", c_i64),
+        ("offsets", c_vp), ("timestamps", c_vp), ("ts_w", c_vp), ("pos_w", c_vp),
+        ("bucket_thresholds", c_vp),
+        ("out", c_vp), ("ldo", c_i64),
+        ("dout", c_vp), ("lddo", c_i64),
+        ("dq", c_vp), ("dk", c_vp), ("dv_grad", c_vp),
+        ("lddq", c_i64), ("lddk", c_i64), ("lddv", c_i64),
+        ("dq_accum", c_vp), ("d_ts_w", c_vp), ("d_pos_w", c_vp),
+    ]
+
+
+class MipsTopkArgs(C.Structure):
+    _fields_ = [
+        ("B", c_i64), ("X", c_i64), ("D", c_i64),
+        ("k", c_i32), ("dtype", c_i32),
+        ("queries", c_vp), ("ldq", c_i64),
+        ("items", c_vp), ("ldi", c_i64),
+        ("item_ids", c_vp),
+        ("out_scores", c_vp), ("out_ids", c_vp),
+        ("workspace", c_vp), ("workspace_bytes", c_i64),
+        ("sample_stride", c_i64), ("cand_cap", c_i64),
+        ("status", c_vp),
+    ]
+
+
+class SslArgs(C.Structure):
+    _fields_ = [
+        ("n_rows", c_i64),
+        ("R", c_i32), ("D", c_i32), ("d0", c_i32), ("d1", c_i32),
+        ("l2_norm", c_i32), ("dtype", c_i32),
+        ("l2_eps", C.c_float), ("temperature", C.c_float),
+        ("q", c_vp), ("ldq_", c_i64),
+        ("p", c_vp), ("ldp", c_i64),
+        ("table0", c_vp), ("ldt0", c_i64),
+        ("table1", c_vp), ("ldt1", c_i64),
+        ("idx0", c_vp), ("idx1", c_vp), ("pos_ids", c_vp), ("neg_ids", c_vp),
+        ("loss_rows", c_vp), ("probs", c_vp),
+        ("g", c_vp), ("dq", c_vp), ("dp", c_vp), ("dtable0", c_vp), ("dtable1", c_vp),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/grb200.h declares
+SYMBOLS = {
+    "grb_version": (C.c_int, []),
+    "grb_last_error_string": (C.c_char_p, []),
+    "grb_launch_count": (c_i64, []),
+    "grb_complete_cumsum": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, c_vp]),
+    "grb_dense_to_jagged": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, C.c_int, c_vp]),
+    "grb_jagged_to_padded_dense": (
+        C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, C.c_int, C.c_int, c_vp]),
+    "grb_gather_last_rows": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, C.c_int, C.c_int, c_vp]),
+    "grb_hstu_attn_fwd": (C.c_int, [C.POINTER(HstuAttnArgs), c_vp]),
+    "grb_hstu_attn_bwd": (C.c_int, [C.POINTER(HstuAttnArgs), c_vp]),
+    "grb_ln_gate_fwd": (
+        C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, C.c_float,
+                  C.c_int, c_vp]),
+    "grb_ln_gate_bwd": (
+        C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64,
+                  c_i64, c_i64, C.c_int, c_vp]),
+    "grb_mips_topk_workspace_bytes": (c_i64, [C.POINTER(MipsTopkArgs)]),
+    "grb_mips_topk": (C.c_int, [C.POINTER(MipsTopkArgs), c_vp]),
+    "grb_topk_select": (
+        C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "grb_sampled_softmax_fwd": (C.c_int, [C.POINTER(SslArgs), c_vp]),
+    "grb_sampled_softmax_bwd": (C.c_int, [C.POINTER(SslArgs), c_vp]),
+    "grb_selftest_umma": (C.c_int, [C.POINTER(C.c_float), C.c_int, c_vp]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """The loaded library.  Raises if it has not been built (python -m ...build)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with "
+                "`python -m mygenerativerecommenders_b200.build` (needs nvcc). "
+                "This package has no CPU or PyTorch fallback."
+            )
+        handle = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(handle, name)  # AttributeError if the .so lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc == GRB_OK:
+        return
+    msg = lib().grb_last_error_string().decode("utf-8", "replace")
+    if rc == GRB_ERR_INVALID_ARG:
+        raise ValueError(f"grb200: {msg}")
+    if rc == GRB_ERR_UNSUPPORTED:
+        raise NotImplementedError(f"grb200: {msg}")
+    raise RuntimeError(f"grb200 (code {rc}): {msg}")
+
+
+def stream_ptr(device: torch.device | None = None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "grb200 ops run on CUDA tensors only (no CPU fallback); got a "
+                f"{t.device} tensor of shape {tuple(t.shape)}"
+            )
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return GRB_F32
+    if dt == torch.bfloat16:
+        return GRB_BF16
+    raise NotImplementedError(f"grb200: unsupported dtype {dt} (float32 / bfloat16 only)")
+
+
+def index_bits(t: torch.Tensor) -> int:
+    if t.dtype == torch.int32:
+        return 32
+    if t.dtype == torch.int64:
+        return 64
+    raise ValueError(f"grb200: offsets/lengths must be int32 or int64, got {t.dtype}")
+
+
+def ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def launch_count() -> int:
+    return int(lib().grb_launch_count())

@@ -1,0 +1,155 @@
+"""Candidate index — drop-in for the reference's ``models/indexing/candidate_index.py``.
+
+Same constructor, properties and ``get_top_k_outputs`` contract (candidate_index.py:9-164):
+owns the id buffer (1, X) and the transposed view of the item table, widens k by the number
+of invalid ids, asks the top-k module, drops invalid ids row-wise and returns (ids, scores).
+``ShardedCandidateIndex`` adds the corpus-sharded variant: every rank holds
+X/G items, runs the fused local top-k and the per-shard results are merged after an NCCL
+all-gather with the same exact selection kernel.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import functional as GF
+from .top_k import TopKModule
+
+
+def _drop_invalid(ids: torch.Tensor, scores: torch.Tensor, invalid_ids: torch.Tensor, k: int):
+    """Keep, in order, the first k entries of each row whose id is not in invalid_ids[row]
+    (candidate_index.py:142-158)."""
+    bad = (ids.unsqueeze(2) == invalid_ids.unsqueeze(1)).any(dim=2)
+    keep = ~bad
+    keep &= torch.cumsum(keep.to(torch.int32), dim=1) <= k
+    # stable argsort brings the kept positions to the front without reordering them
+    pos = torch.argsort((~keep).to(torch.int8), dim=1, stable=True)[:, :k]
+    return torch.gather(ids, 1, pos), torch.gather(scores, 1, pos)
+
+
+class CandidateIndex(torch.nn.Module):
+    def __init__(self, k: int, ids: torch.Tensor, top_k_module: TopKModule,
+                 embeddings: torch.Tensor = None, invalid_ids: Optional[torch.Tensor] = None,
+                 debug_path: Optional[str] = None) -> None:
+        super().__init__()
+        self.register_buffer("_ids", torch.as_tensor(ids).unsqueeze(0))
+        self._k = min(k, self._ids.shape[1])
+        self._top_k_module: TopKModule = top_k_module
+        self._invalid_ids: Optional[torch.Tensor] = invalid_ids
+        self._debug_path: Optional[str] = debug_path
+        self.update_embeddings(embeddings)
+
+    def update_embeddings(self, embeddings: Optional[torch.Tensor]) -> None:
+        """embeddings: (1, X, D).  Stored as the (D, X) transposed *view* (no copy), like
+        candidate_index.py:27-31."""
+        self._embeddings_t = None if embeddings is None else embeddings.permute(2, 1, 0).squeeze(2)
+
+    @property
+    def ids(self) -> torch.Tensor:
+        return self._ids
+
+    @property
+    def num_objects(self) -> int:
+        return self._ids.size(1)
+
+    @property
+    def embeddings(self) -> Optional[torch.Tensor]:
+        if self._embeddings_t is None:
+            return None
+        return self._embeddings_t.unsqueeze(2).permute(2, 1, 0).squeeze(2)
+
+    def get_top_k_outputs(self, query_embeddings: torch.Tensor, k: int = None,
+                          invalid_ids: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Returns (top_k_ids, top_k_scores), each (B, k) — ids first, as the reference."""
+        n_invalid = invalid_ids.size(1) if invalid_ids is not None else 0
+        if k is None:
+            k = self._k
+        k_prime = min(k + n_invalid, self.num_objects)
+        scores, ids = self._top_k_module(
+            query_embeddings=query_embeddings, item_embeddings_t=self._embeddings_t,
+            item_ids=self._ids, k=k_prime, sorted=True)
+        if invalid_ids is not None:
+            ids, scores = _drop_invalid(ids, scores, invalid_ids, k)
+        return ids, scores
+
+    def apply_object_filter(self) -> "CandidateIndex":
+        raise NotImplementedError("not implemented.")
+
+
+class ShardedCandidateIndex(CandidateIndex):
+    """Corpus-sharded index: rank r of G holds the contiguous item range r*ceil(X/G) ...
+
+    ``ids`` / ``embeddings`` passed to the constructor / ``update_embeddings`` are the FULL
+    corpus (as in the reference, where every rank holds everything); this module keeps only
+    its own slice.  Queries must be the same on every rank of ``group`` (replicated eval
+    batch); every rank returns the full merged top-k."""
+
+    def __init__(self, k: int, ids: torch.Tensor, top_k_module: TopKModule,
+                 embeddings: torch.Tensor = None, invalid_ids: Optional[torch.Tensor] = None,
+                 debug_path: Optional[str] = None, group=None) -> None:
+        self._group = group
+        self._world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._rank = dist.get_rank(group) if dist.is_initialized() else 0
+        ids = torch.as_tensor(ids)
+        self._num_total = ids.numel()
+        self._k_total = min(k, self._num_total)
+        lo, hi = self._range(self._num_total)
+        super().__init__(k=k, ids=ids[lo:hi], top_k_module=top_k_module, embeddings=None,
+                         invalid_ids=invalid_ids, debug_path=debug_path)
+        self.update_embeddings(embeddings)
+
+    def _range(self, n: int) -> Tuple[int, int]:
+        per = -(-n // self._world)
+        return min(self._rank * per, n), min((self._rank + 1) * per, n)
+
+    def update_embeddings(self, embeddings: Optional[torch.Tensor]) -> None:
+        if embeddings is not None and embeddings.size(1) == getattr(self, "_num_total", -1) \
+                and self._world > 1:
+            lo, hi = self._range(self._num_total)
+            embeddings = embeddings[:, lo:hi].contiguous()
+        super().update_embeddings(embeddings)
+
+    @property
+    def num_objects(self) -> int:
+        return self._num_total
+
+    def get_top_k_outputs(self, query_embeddings: torch.Tensor, k: int = None,
+                          invalid_ids: Optional[torch.Tensor] = None):
+        n_invalid = invalid_ids.size(1) if invalid_ids is not None else 0
+        if k is None:
+            k = self._k_total
+        k_prime = min(k + n_invalid, self._num_total)
+        k_local = min(k_prime, self._ids.size(1))
+        scores, ids = self._top_k_module(
+            query_embeddings=query_embeddings, item_embeddings_t=self._embeddings_t,
+            item_ids=self._ids, k=k_local, sorted=True)
+        if self._world > 1:
+            scores, ids = merge_sharded_topk(scores.float(), ids, k_prime, self._world, self._group)
+        if invalid_ids is not None:
+            ids, scores = _drop_invalid(ids, scores, invalid_ids, k)
+        return ids, scores
+
+
+def merge_sharded_topk(scores: torch.Tensor, ids: torch.Tensor, k: int, world: int, group=None):
+    """All-gather per-shard (B, k_local) results and select the exact global top-k.
+
+    Shards may hold fewer than k items; short shards are padded with (-inf, int64 max) so the
+    gathered tensor is rectangular.  Works with NCCL (CUDA) — the selection is a kernel."""
+    B, kl = scores.shape
+    klen = torch.tensor([kl], device=scores.device, dtype=torch.int64)
+    lens = [torch.zeros_like(klen) for _ in range(world)]
+    dist.all_gather(lens, klen, group=group)
+    kmax = int(max(int(x.item()) for x in lens))
+    if kl < kmax:
+        pad_s = torch.full((B, kmax - kl), float("-inf"), device=scores.device, dtype=scores.dtype)
+        pad_i = torch.full((B, kmax - kl), torch.iinfo(torch.int64).max, device=ids.device, dtype=ids.dtype)
+        scores, ids = torch.cat([scores, pad_s], 1), torch.cat([ids, pad_i], 1)
+    all_s = torch.empty((world, B, kmax), device=scores.device, dtype=scores.dtype)
+    all_i = torch.empty((world, B, kmax), device=ids.device, dtype=ids.dtype)
+    dist.all_gather_into_tensor(all_s, scores.contiguous(), group=group)
+    dist.all_gather_into_tensor(all_i, ids.contiguous(), group=group)
+    cand_s = all_s.permute(1, 0, 2).reshape(B, world * kmax)
+    cand_i = all_i.permute(1, 0, 2).reshape(B, world * kmax)
+    return GF.topk_merge(cand_s, cand_i, k)

@@ -1,0 +1,323 @@
+"""Autograd-aware wrappers over the C ABI for the fused hot-path kernels.
+
+Each function documents the reference lines it replaces (paths under
+/root/reference/src/generative_recommenders_pl/models/).  CUDA tensors only; errors from the
+library surface as Python exceptions (ValueError / NotImplementedError / RuntimeError).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+
+def _ld(t: torch.Tensor) -> int:
+    """Row stride (elements) of a 2-D tensor whose rows are contiguous."""
+    return t.stride(0) if t.shape[0] > 1 else t.shape[1]
+
+
+def _rows_contiguous(t: torch.Tensor) -> torch.Tensor:
+    if t.dim() != 2:
+        raise ValueError(f"expected a 2-D tensor, got shape {tuple(t.shape)}")
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        return t.contiguous()
+    if t.shape[0] > 1 and t.stride(0) < t.shape[1]:
+        return t.contiguous()
+    return t
+
+
+# --------------------------------------------------------------------------------------------
+# fused jagged HSTU attention  (sequential_encoders/hstu.py:96-128 + :134-205)
+# --------------------------------------------------------------------------------------------
+def _attn_args(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk, dv, max_len):
+    a = _lib.HstuAttnArgs()
+    a.B = offsets.numel() - 1
+    a.N = N
+    a.T = q.shape[0]
+    a.max_len = max_len
+    a.H, a.dqk, a.dv = H, dqk, dv
+    a.dtype = _lib.dtype_code(q.dtype)
+    a.index_bits = _lib.index_bits(offsets)
+    a.q, a.k, a.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
+    a.ldq, a.ldk, a.ldv = _ld(q), _ld(k), _ld(v)
+    a.offsets = offsets.data_ptr()
+    if timestamps is not None:
+        a.num_buckets = thresholds.numel()
+        a.timestamps = timestamps.data_ptr()
+        a.ts_w = ts_w.data_ptr()
+        a.pos_w = pos_w.data_ptr()
+        a.bucket_thresholds = thresholds.data_ptr()
+    return a
+
+
+class _HstuAttention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk, dv, max_len):
+        _lib.require_cuda(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds)
+        if not (q.dtype == k.dtype == v.dtype):
+            raise ValueError("hstu_attention: q, k, v must share a dtype")
+        q, k, v = _rows_contiguous(q), _rows_contiguous(k), _rows_contiguous(v)
+        offsets = offsets.contiguous()
+        if timestamps is not None:
+            if timestamps.dtype != torch.int64 or timestamps.shape != (offsets.numel() - 1, N):
+                raise ValueError("hstu_attention: timestamps must be int64 of shape (B, N)")
+            timestamps = timestamps.contiguous()
+            ts_w = ts_w.detach().float().contiguous()
+            pos_w = pos_w.detach().float().contiguous()
+            if ts_w.numel() != thresholds.numel() + 1 or pos_w.numel() < 2 * N - 1:
+                raise ValueError("hstu_attention: bias table sizes do not match N / num_buckets")
+        out = torch.empty((q.shape[0], H * dv), dtype=q.dtype, device=q.device)
+        a = _attn_args(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk, dv, max_len)
+        a.out, a.ldo = out.data_ptr(), H * dv
+        _lib.check(_lib.lib().grb_hstu_attn_fwd(C.byref(a), _lib.stream_ptr(q.device)))
+        ctx.save_for_backward(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds)
+        ctx.dims = (N, H, dqk, dv, max_len)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, offsets, timestamps, ts_w, pos_w, thresholds = ctx.saved_tensors
+        N, H, dqk, dv, max_len = ctx.dims
+        dout = _rows_contiguous(dout)
+        T = q.shape[0]
+        dq = torch.empty((T, H * dqk), dtype=q.dtype, device=q.device)
+        dk = torch.empty((T, H * dqk), dtype=q.dtype, device=q.device)
+        dvv = torch.empty((T, H * dv), dtype=q.dtype, device=q.device)
+        dq_acc = torch.zeros((T, H * dqk), dtype=torch.float32, device=q.device)
+        a = _attn_args(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk, dv, max_len)
+        a.dout, a.lddo = dout.data_ptr(), _ld(dout)
+        a.dq, a.dk, a.dv_grad = dq.data_ptr(), dk.data_ptr(), dvv.data_ptr()
+        a.lddq, a.lddk, a.lddv = H * dqk, H * dqk, H * dv
+        a.dq_accum = dq_acc.data_ptr()
+        d_ts = d_pos = None
+        if timestamps is not None:
+            d_ts = torch.zeros_like(ts_w)
+            d_pos = torch.zeros_like(pos_w)
+            a.d_ts_w, a.d_pos_w = d_ts.data_ptr(), d_pos.data_ptr()
+        _lib.check(_lib.lib().grb_hstu_attn_bwd(C.byref(a), _lib.stream_ptr(q.device)))
+        return dq, dk, dvv, None, None, d_ts, d_pos, None, None, None, None, None, None
+
+
+def hstu_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, offsets: torch.Tensor,
+                   timestamps: Optional[torch.Tensor], ts_w: Optional[torch.Tensor],
+                   pos_w: Optional[torch.Tensor], bucket_thresholds: Optional[torch.Tensor],
+                   N: int, num_heads: int, attention_dim: int, linear_dim: int,
+                   max_len: Optional[int] = None) -> torch.Tensor:
+    """Jagged pointwise-SiLU attention with relative time+position bias.
+
+    q, k: (T, H*attention_dim); v: (T, H*linear_dim); offsets (B+1); timestamps (B, N) int64 or
+    None (no bias, hstu.py:191).  Returns (T, H*linear_dim).  ``N`` is the padded length that the
+    reference uses for the 1/N scale and the bias origin (hstu.py:150,193)."""
+    if max_len is None:
+        max_len = N
+    if ts_w is not None and ts_w.dtype != torch.float32:
+        ts_w = ts_w.float()
+    if pos_w is not None and pos_w.dtype != torch.float32:
+        pos_w = pos_w.float()
+    return _HstuAttention.apply(q, k, v, offsets, timestamps, ts_w, pos_w, bucket_thresholds,
+                                N, num_heads, attention_dim, linear_dim, min(max_len, N))
+
+
+# --------------------------------------------------------------------------------------------
+# y = gate * LayerNorm(x)   (hstu.py:258-264, :300, :402)
+# --------------------------------------------------------------------------------------------
+class _LnGate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gate, eps):
+        _lib.require_cuda(x, gate)
+        x = _rows_contiguous(x)
+        if gate is not None:
+            gate = _rows_contiguous(gate)
+            if gate.dtype != x.dtype or gate.shape != x.shape:
+                raise ValueError("ln_gate: gate must match x in shape and dtype")
+        rows, W = x.shape
+        y = torch.empty((rows, W), dtype=x.dtype, device=x.device)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().grb_ln_gate_fwd(
+            x.data_ptr(), _ld(x), _lib.ptr(gate), _ld(gate) if gate is not None else 0,
+            y.data_ptr(), W, mean.data_ptr(), rstd.data_ptr(), rows, W, float(eps),
+            _lib.dtype_code(x.dtype), _lib.stream_ptr(x.device)))
+        ctx.save_for_backward(x, gate, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gate, mean, rstd = ctx.saved_tensors
+        dy = _rows_contiguous(dy)
+        rows, W = x.shape
+        dx = torch.empty((rows, W), dtype=x.dtype, device=x.device)
+        dgate = torch.empty((rows, W), dtype=x.dtype, device=x.device) if gate is not None else None
+        _lib.check(_lib.lib().grb_ln_gate_bwd(
+            x.data_ptr(), _ld(x), _lib.ptr(gate), _ld(gate) if gate is not None else 0,
+            dy.data_ptr(), _ld(dy), mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(), W,
+            _lib.ptr(dgate), W, rows, W, _lib.dtype_code(x.dtype), _lib.stream_ptr(x.device)))
+        return dx, dgate, None
+
+
+def layer_norm_gate(x: torch.Tensor, gate: Optional[torch.Tensor], eps: float) -> torch.Tensor:
+    """gate * F.layer_norm(x, [W], eps=eps) without affine; gate=None gives the plain norm."""
+    return _LnGate.apply(x, gate, eps)
+
+
+# --------------------------------------------------------------------------------------------
+# fused sampled softmax  (negative_sampler.py:31-37,123-131,208-211; dot_product.py:61-64;
+#                         autoregressive_losses.py:279-306)
+# --------------------------------------------------------------------------------------------
+class _SampledSoftmax(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, p, table0, table1, idx0, idx1, pos_ids, neg_ids, l2_norm, eps, temperature):
+        _lib.require_cuda(q, p, table0, table1, idx0, idx1, pos_ids, neg_ids)
+        for t in (q, p, table0, table1):
+            if t is not None and t.dtype != torch.float32:
+                raise NotImplementedError("sampled_softmax: float32 tensors only")
+        q, p = _rows_contiguous(q), _rows_contiguous(p)
+        table0 = _rows_contiguous(table0)
+        table1 = _rows_contiguous(table1) if table1 is not None else None
+        idx0 = idx0.contiguous()
+        idx1 = idx1.contiguous() if idx1 is not None else None
+        pos_ids, neg_ids = pos_ids.contiguous(), neg_ids.contiguous()
+        n, D = q.shape
+        R = idx0.shape[1]
+        loss_rows = torch.empty(n, dtype=torch.float32, device=q.device)
+        probs = torch.empty((n, R + 1), dtype=torch.float32, device=q.device)
+        a = _SampledSoftmax._args(q, p, table0, table1, idx0, idx1, pos_ids, neg_ids, l2_norm, eps,
+                                  temperature, probs)
+        a.loss_rows = loss_rows.data_ptr()
+        _lib.check(_lib.lib().grb_sampled_softmax_fwd(C.byref(a), _lib.stream_ptr(q.device)))
+        ctx.save_for_backward(q, p, table0, table1, idx0, idx1, pos_ids, neg_ids, probs)
+        ctx.cfg = (l2_norm, eps, temperature)
+        return loss_rows
+
+    @staticmethod
+    def _args(q, p, table0, table1, idx0, idx1, pos_ids, neg_ids, l2_norm, eps, temperature, probs):
+        a = _lib.SslArgs()
+        a.n_rows, a.D = q.shape
+        a.R = idx0.shape[1]
+        a.d0 = table0.shape[1]
+        a.d1 = table1.shape[1] if table1 is not None else 0
+        a.l2_norm = 1 if l2_norm else 0
+        a.dtype = _lib.GRB_F32
+        a.l2_eps = float(eps)
+        a.temperature = float(temperature)
+        a.q, a.ldq_ = q.data_ptr(), _ld(q)
+        a.p, a.ldp = p.data_ptr(), _ld(p)
+        a.table0, a.ldt0 = table0.data_ptr(), _ld(table0)
+        if table1 is not None:
+            a.table1, a.ldt1 = table1.data_ptr(), _ld(table1)
+            a.idx1 = idx1.data_ptr()
+        a.idx0 = idx0.data_ptr()
+        a.pos_ids, a.neg_ids = pos_ids.data_ptr(), neg_ids.data_ptr()
+        a.probs = probs.data_ptr()
+        return a
+
+    @staticmethod
+    def backward(ctx, g):
+        q, p, table0, table1, idx0, idx1, pos_ids, neg_ids, probs = ctx.saved_tensors
+        l2_norm, eps, temperature = ctx.cfg
+        g = g.contiguous().float()
+        dq = torch.empty(q.shape, dtype=torch.float32, device=q.device)
+        dp = torch.empty(p.shape, dtype=torch.float32, device=q.device)
+        dt0 = torch.zeros(table0.shape, dtype=torch.float32, device=q.device)
+        dt1 = torch.zeros(table1.shape, dtype=torch.float32, device=q.device) if table1 is not None else None
+        a = _SampledSoftmax._args(q, p, table0, table1, idx0, idx1, pos_ids, neg_ids, l2_norm, eps,
+                                  temperature, probs)
+        a.g, a.dq, a.dp = g.data_ptr(), dq.data_ptr(), dp.data_ptr()
+        a.dtable0 = dt0.data_ptr()
+        if dt1 is not None:
+            a.dtable1 = dt1.data_ptr()
+        _lib.check(_lib.lib().grb_sampled_softmax_bwd(C.byref(a), _lib.stream_ptr(q.device)))
+        return dq, dp, dt0, dt1, None, None, None, None, None, None, None
+
+
+def sampled_softmax_rows(q: torch.Tensor, p: torch.Tensor, table0: torch.Tensor,
+                         table1: Optional[torch.Tensor], idx0: torch.Tensor,
+                         idx1: Optional[torch.Tensor], pos_ids: torch.Tensor,
+                         neg_ids: torch.Tensor, l2_norm: bool, eps: float,
+                         temperature: float) -> torch.Tensor:
+    """Per-row sampled-softmax loss -log_softmax([q.p/T, masked q.e_r/T])[0], (N',) fp32.
+
+    Negatives e_r = concat(table0[idx0[n, r]], table1[idx1[n, r]]) are gathered, optionally
+    L2-normalised, dotted and reduced inside one kernel; (N', R, D) never exists."""
+    return _SampledSoftmax.apply(q, p, table0, table1, idx0, idx1, pos_ids, neg_ids, l2_norm, eps,
+                                 temperature)
+
+
+# --------------------------------------------------------------------------------------------
+# fused MIPS top-k  (indexing/top_k.py:44-70)
+# --------------------------------------------------------------------------------------------
+_WS_CACHE: dict = {}
+
+
+def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _WS_CACHE.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _WS_CACHE[key] = ws
+    return ws
+
+
+def mips_topk(queries: torch.Tensor, items: torch.Tensor, item_ids: Optional[torch.Tensor],
+              k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Exact top-k of queries @ items.T, sorted descending, ties -> lowest item index.
+
+    queries (B, D), items (X, D) row-major (same dtype, fp32 or bf16); item_ids (X,) int64 or
+    None.  Returns (scores (B, k) fp32, ids (B, k) int64)."""
+    _lib.require_cuda(queries, items, item_ids)
+    if queries.dtype != items.dtype:
+        raise ValueError("mips_topk: queries and items must share a dtype")
+    queries, items = _rows_contiguous(queries), _rows_contiguous(items)
+    B, D = queries.shape
+    X = items.shape[0]
+    if items.shape[1] != D:
+        raise ValueError("mips_topk: embedding dims differ")
+    if item_ids is not None:
+        item_ids = item_ids.contiguous()
+        if item_ids.dtype != torch.int64 or item_ids.numel() != X:
+            raise ValueError("mips_topk: item_ids must be int64 with one id per item")
+    dev = queries.device
+    out_s = torch.empty((B, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((B, k), dtype=torch.int64, device=dev)
+    status = torch.zeros(2, dtype=torch.int32, device=dev)
+    a = _lib.MipsTopkArgs()
+    a.B, a.X, a.D, a.k = B, X, D, k
+    a.dtype = _lib.dtype_code(queries.dtype)
+    a.queries, a.ldq = queries.data_ptr(), _ld(queries)
+    a.items, a.ldi = items.data_ptr(), _ld(items)
+    a.item_ids = _lib.ptr(item_ids)
+    a.out_scores, a.out_ids = out_s.data_ptr(), out_i.data_ptr()
+    a.status = status.data_ptr()
+    cap = 0
+    for _attempt in range(3):
+        a.sample_stride, a.cand_cap = 0, cap
+        need = int(_lib.lib().grb_mips_topk_workspace_bytes(C.byref(a)))
+        if need < 0:
+            _lib.check(need)
+        ws = _workspace(need, dev)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        _lib.check(_lib.lib().grb_mips_topk(C.byref(a), _lib.stream_ptr(dev)))
+        overflow = int(status[0].item())  # the caller consumes the ids on the host anyway
+        if overflow == 0:
+            return out_s, out_i
+        cap = overflow + 1024  # a row had more candidates than the workspace held: exact re-run
+        status.zero_()
+    raise RuntimeError("grb200 mips_topk: candidate workspace overflowed repeatedly")
+
+
+def topk_merge(cand_scores: torch.Tensor, cand_ids: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Exact top-k of per-row candidate lists (B, C): sorted descending, ties -> lowest id.
+    This is the merge step after the all-gather of per-shard top-k."""
+    _lib.require_cuda(cand_scores, cand_ids)
+    cand_scores = cand_scores.contiguous().float()
+    cand_ids = cand_ids.contiguous()
+    B, cap = cand_scores.shape
+    out_s = torch.empty((B, k), dtype=torch.float32, device=cand_scores.device)
+    out_i = torch.empty((B, k), dtype=torch.int64, device=cand_scores.device)
+    _lib.check(_lib.lib().grb_topk_select(
+        cand_scores.data_ptr(), cand_ids.data_ptr(), None, B, cap, k, None, out_s.data_ptr(),
+        out_i.data_ptr(), _lib.stream_ptr(cand_scores.device)))
+    return out_s, out_i

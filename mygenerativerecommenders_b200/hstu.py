@@ -1,0 +1,338 @@
+"""HSTU encoder — drop-in for the reference's ``models/sequential_encoders/hstu.py``.
+
+Same class names, constructor kwargs, forward signatures and parameter names
+(``_hstu._attention_layers.{i}._uvqk``, ``._o.weight/.bias``, ``._rel_attn_bias._ts_w/._pos_w``,
+buffer ``_attn_mask``) as /root/reference/src/generative_recommenders_pl/models/
+sequential_encoders/hstu.py (:71 bias, :208 STU layer, :426 HSTUJagged, :521 HSTU), so Hydra
+``_target_`` strings and checkpoints carry over.  The difference is below the module boundary:
+the bias (:96-128), the attention (:134-205), both LayerNorms and the U-gate (:258-264, :300,
+:402) run as fused jagged sm_100a kernels, so no padded q/k/v, no (B,H,N,N) scores and no
+(B,N,N) bucket tensor ever exist.
+
+Extension: ``HSTU(..., compute_dtype=torch.bfloat16)`` runs the layers with bf16 activations
+(fp32 master weights, fp32 accumulation; tcgen05 attention) — the reference is fp32-only
+(autocast disabled, hstu.py:592).
+"""
+from __future__ import annotations
+
+import abc
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import functional as GF
+from . import ops
+
+TIMESTAMPS_KEY = "timestamps"
+
+HSTUCacheState = Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]
+
+
+def tabulate_bucket_thresholds(bucketization_fn: Callable[[torch.Tensor], torch.Tensor],
+                               num_buckets: int) -> torch.Tensor:
+    """thresholds[t] = smallest d >= 0 with clamp(fn(d), 0, num_buckets) >= t+1  (int64, CPU).
+
+    The reference evaluates ``bucketization_fn`` on every (i, j) pair each layer
+    (hstu.py:117-123).  For a monotone fn of |d| the bucket is ``#{t: thresholds[t] <= |d|}``;
+    the table is built by bisection on the *same* fn evaluated by torch on the CPU, so the
+    kernel's integer compare reproduces the reference's float32 log/div/trunc bit for bit.
+    """
+    hi_cap = (1 << 62)
+    probe = torch.tensor([0, 1, 2, 3, 7, 100, 12345, 10 ** 9, 10 ** 12], dtype=torch.int64)
+    pos = torch.clamp(bucketization_fn(probe), 0, num_buckets)
+    neg = torch.clamp(bucketization_fn(-probe), 0, num_buckets)
+    if not torch.equal(pos, neg):
+        raise NotImplementedError("bucketization_fn must depend on |x| only")
+    if (pos[1:] < pos[:-1]).any():
+        raise NotImplementedError("bucketization_fn must be non-decreasing in |x|")
+    targets = torch.arange(1, num_buckets + 1, dtype=torch.int64)
+    lo = torch.zeros(num_buckets, dtype=torch.int64)            # fn(lo) < target (or lo == 0)
+    hi = torch.full((num_buckets,), hi_cap, dtype=torch.int64)  # fn(hi) >= target, or unreachable
+    reach = torch.clamp(bucketization_fn(hi), 0, num_buckets) >= targets
+    zero_ok = torch.clamp(bucketization_fn(lo), 0, num_buckets) >= targets
+    for _ in range(64):
+        mid = lo + (hi - lo) // 2
+        ge = torch.clamp(bucketization_fn(mid), 0, num_buckets) >= targets
+        hi = torch.where(ge, mid, hi)
+        lo = torch.where(ge, lo, mid)
+    thr = torch.where(zero_ok, torch.zeros_like(hi), hi)
+    thr = torch.where(reach, thr, torch.full_like(thr, torch.iinfo(torch.int64).max))
+    return thr
+
+
+class RelativeAttentionBiasModule(torch.nn.Module):
+    @abc.abstractmethod
+    def forward(self, all_timestamps: torch.Tensor) -> torch.Tensor:
+        """all_timestamps: (B, N) int64 -> float tensor broadcastable to (B, N, N)."""
+
+
+class RelativePositionalBias(RelativeAttentionBiasModule):
+    """bias[i, j] = w[N-1+j-i]  (reference hstu.py:50-68)."""
+
+    def __init__(self, max_seq_len: int) -> None:
+        super().__init__()
+        self._max_seq_len: int = max_seq_len
+        self._w = torch.nn.Parameter(torch.empty(2 * max_seq_len - 1).normal_(mean=0, std=0.02))
+
+    def forward(self, all_timestamps: torch.Tensor) -> torch.Tensor:
+        n = self._max_seq_len
+        ar = torch.arange(n, device=self._w.device)
+        return self._w[(n - 1) + ar.view(1, n) - ar.view(n, 1)].unsqueeze(0)
+
+
+class RelativeBucketedTimeAndPositionBasedBias(RelativeAttentionBiasModule):
+    """pos_w[N-1+j-i] + ts_w[bucket(ts[i+1] - ts[j])]  (reference hstu.py:71-128).
+
+    Inside the encoder this module is only a parameter holder: the fused attention kernel
+    reads ``_ts_w``, ``_pos_w`` and the tabulated thresholds directly.  ``forward`` still
+    returns the dense (B, N, N) bias for callers that want it."""
+
+    def __init__(self, max_seq_len: int, num_buckets: int,
+                 bucketization_fn: Callable[[torch.Tensor], torch.Tensor]) -> None:
+        super().__init__()
+        self._max_seq_len: int = max_seq_len
+        self._ts_w = torch.nn.Parameter(torch.empty(num_buckets + 1).normal_(mean=0, std=0.02))
+        self._pos_w = torch.nn.Parameter(torch.empty(2 * max_seq_len - 1).normal_(mean=0, std=0.02))
+        self._num_buckets: int = num_buckets
+        self._bucketization_fn = bucketization_fn
+        self.register_buffer("_bucket_thresholds",
+                             tabulate_bucket_thresholds(bucketization_fn, num_buckets),
+                             persistent=False)
+
+    def forward(self, all_timestamps: torch.Tensor) -> torch.Tensor:
+        N = self._max_seq_len
+        ar = torch.arange(N, device=all_timestamps.device)
+        pos = self._pos_w[(N - 1) + ar.view(1, N) - ar.view(N, 1)]
+        nxt = torch.cat([all_timestamps[:, 1:], all_timestamps[:, N - 1:N]], dim=1)
+        d = (nxt.unsqueeze(2) - all_timestamps.unsqueeze(1)).abs()
+        buckets = torch.bucketize(d, self._bucket_thresholds, right=True)
+        return pos.unsqueeze(0) + self._ts_w[buckets]
+
+
+class SequentialTransductionUnitJagged(torch.nn.Module):
+    """One HSTU layer on jagged rows (reference hstu.py:208-423)."""
+
+    def __init__(self, embedding_dim: int, linear_hidden_dim: int, attention_dim: int,
+                 dropout_ratio: float, attn_dropout_ratio: float, num_heads: int,
+                 linear_activation: str,
+                 relative_attention_bias_module: Optional[RelativeAttentionBiasModule] = None,
+                 normalization: str = "rel_bias", linear_config: str = "uvqk",
+                 concat_ua: bool = False, epsilon: float = 1e-6,
+                 max_length: Optional[int] = None) -> None:
+        super().__init__()
+        self._embedding_dim: int = embedding_dim
+        self._linear_dim: int = linear_hidden_dim
+        self._attention_dim: int = attention_dim
+        self._dropout_ratio: float = dropout_ratio
+        self._attn_dropout_ratio: float = attn_dropout_ratio  # stored, never applied (as :230)
+        self._num_heads: int = num_heads
+        self._rel_attn_bias: Optional[RelativeAttentionBiasModule] = relative_attention_bias_module
+        self._normalization: str = normalization
+        self._linear_config: str = linear_config
+        if linear_config != "uvqk":
+            raise ValueError(f"Unknown linear_config {linear_config}")
+        self._uvqk = torch.nn.Parameter(
+            torch.empty((embedding_dim,
+                         linear_hidden_dim * 2 * num_heads + attention_dim * num_heads * 2)
+                        ).normal_(mean=0, std=0.02))
+        self._linear_activation: str = linear_activation
+        self._concat_ua: bool = concat_ua
+        self._o = torch.nn.Linear(
+            in_features=linear_hidden_dim * num_heads * (3 if concat_ua else 1),
+            out_features=embedding_dim)
+        torch.nn.init.xavier_uniform_(self._o.weight)
+        self._eps: float = epsilon
+
+    def _norm_input(self, x: torch.Tensor) -> torch.Tensor:
+        return GF.layer_norm_gate(x, None, self._eps)
+
+    def _norm_attn_output(self, x: torch.Tensor) -> torch.Tensor:
+        return GF.layer_norm_gate(x, None, self._eps)
+
+    def forward(self, x: torch.Tensor, x_offsets: torch.Tensor,
+                all_timestamps: Optional[torch.Tensor], invalid_attn_mask: torch.Tensor,
+                delta_x_offsets: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+                cache: Optional[HSTUCacheState] = None,
+                return_cache_states: bool = False):
+        """x: (sum_i N_i, D); x_offsets: (B+1); all_timestamps: (B, N) int64 or None;
+        invalid_attn_mask: (N, N) — only its size is read: the kernel applies the causal
+        lower-triangular mask that HSTU registers (hstu.py:595-607,667)."""
+        if delta_x_offsets is not None or cache is not None:
+            raise NotImplementedError(
+                "incremental decoding (delta_x_offsets / cache, hstu.py:151-177) is not on the "
+                "B200 hot path yet")
+        if self._normalization not in ("rel_bias", "hstu_rel_bias"):
+            if self._normalization == "softmax_rel_bias":
+                raise NotImplementedError("softmax_rel_bias normalization is not implemented")
+            raise ValueError(f"Unknown normalization method {self._normalization}")
+        n: int = invalid_attn_mask.size(-1)
+        H, dv, dqk = self._num_heads, self._linear_dim, self._attention_dim
+
+        normed_x = self._norm_input(x)
+        w = self._uvqk if self._uvqk.dtype == x.dtype else self._uvqk.to(x.dtype)
+        mm = torch.mm(normed_x, w)
+        if self._linear_activation == "silu":
+            mm = F.silu(mm)
+        elif self._linear_activation != "none":
+            raise ValueError(f"Unknown linear_activation {self._linear_activation}")
+        u, v, q, k = torch.split(mm, [dv * H, dv * H, dqk * H, dqk * H], dim=1)
+
+        bias = self._rel_attn_bias if all_timestamps is not None else None
+        if bias is not None and not isinstance(bias, RelativeBucketedTimeAndPositionBasedBias):
+            raise NotImplementedError(
+                "the fused attention supports RelativeBucketedTimeAndPositionBasedBias only")
+        attn_output = GF.hstu_attention(
+            q, k, v, x_offsets,
+            all_timestamps if bias is not None else None,
+            bias._ts_w if bias is not None else None,
+            bias._pos_w if bias is not None else None,
+            bias._bucket_thresholds if bias is not None else None,
+            N=n, num_heads=H, attention_dim=dqk, linear_dim=dv)
+
+        if self._concat_ua:
+            a = self._norm_attn_output(attn_output)
+            o_input = torch.cat([u, a, u * a], dim=-1)
+        else:
+            o_input = GF.layer_norm_gate(attn_output, u, self._eps)
+
+        o_w = self._o.weight if self._o.weight.dtype == x.dtype else self._o.weight.to(x.dtype)
+        o_b = self._o.bias if self._o.bias.dtype == x.dtype else self._o.bias.to(x.dtype)
+        new_outputs = F.linear(
+            F.dropout(o_input, p=self._dropout_ratio, training=self.training), o_w, o_b) + x
+
+        cache_state = None
+        if return_cache_states:
+            cache_state = (
+                v.contiguous(),
+                ops.jagged_to_padded_dense(q.contiguous(), x_offsets, n, 0.0),
+                ops.jagged_to_padded_dense(k.contiguous(), x_offsets, n, 0.0),
+                new_outputs,
+            )
+        return new_outputs, cache_state
+
+
+class HSTUJagged(torch.nn.Module):
+    """Stack of STU layers over jagged rows (reference hstu.py:426-518)."""
+
+    def __init__(self, modules: List[SequentialTransductionUnitJagged],
+                 autocast_dtype: Optional[torch.dtype]) -> None:
+        super().__init__()
+        self._attention_layers = torch.nn.ModuleList(modules=modules)
+        self._autocast_dtype = autocast_dtype
+
+    def jagged_forward(self, x: torch.Tensor, x_offsets: torch.Tensor,
+                       all_timestamps: Optional[torch.Tensor], invalid_attn_mask: torch.Tensor,
+                       delta_x_offsets=None, cache=None, return_cache_states: bool = False):
+        cache_states: List[HSTUCacheState] = []
+        in_dtype = x.dtype
+        if self._autocast_dtype is not None and x.dtype != self._autocast_dtype:
+            x = x.to(self._autocast_dtype)
+        for i, layer in enumerate(self._attention_layers):
+            x, cs = layer(x=x, x_offsets=x_offsets, all_timestamps=all_timestamps,
+                          invalid_attn_mask=invalid_attn_mask, delta_x_offsets=delta_x_offsets,
+                          cache=cache[i] if cache is not None else None,
+                          return_cache_states=return_cache_states)
+            if return_cache_states:
+                cache_states.append(cs)
+        if x.dtype != in_dtype:
+            x = x.to(in_dtype)
+        return x, cache_states
+
+    def forward(self, x: torch.Tensor, x_offsets: torch.Tensor,
+                all_timestamps: Optional[torch.Tensor], invalid_attn_mask: torch.Tensor,
+                delta_x_offsets=None, cache=None, return_cache_states: bool = False,
+                total_length: Optional[int] = None):
+        """x: (B, N, D) padded or (T, D) jagged.  Returns (B, N, D), cache states."""
+        if x.dim() == 3:
+            x = ops.dense_to_jagged(x, x_offsets, total=total_length)
+        jagged_x, cache_states = self.jagged_forward(
+            x=x, x_offsets=x_offsets, all_timestamps=all_timestamps,
+            invalid_attn_mask=invalid_attn_mask, delta_x_offsets=delta_x_offsets, cache=cache,
+            return_cache_states=return_cache_states)
+        y = ops.jagged_to_padded_dense(values=jagged_x, offsets=x_offsets,
+                                       max_lengths=invalid_attn_mask.size(1), padding_value=0.0)
+        return y, cache_states
+
+
+def _default_bucketization(x: torch.Tensor) -> torch.Tensor:
+    # the reference's lambda (hstu.py:579-581), kept as a named function so modules pickle
+    return (torch.log(torch.abs(x).clamp(min=1)) / 0.301).long()
+
+
+class HSTU(torch.nn.Module):
+    """Top-level encoder the model config targets (reference hstu.py:521-672)."""
+
+    def __init__(self, max_sequence_len: int, max_output_len: int, embedding_dim: int,
+                 item_embedding_dim: int, num_blocks: int, num_heads: int, linear_dim: int,
+                 attention_dim: int, normalization: str, linear_config: str,
+                 linear_activation: str, linear_dropout_rate: float, attn_dropout_rate: float,
+                 enable_relative_attention_bias: bool = True, concat_ua: bool = False,
+                 compute_dtype: Optional[torch.dtype] = None) -> None:
+        super().__init__()
+        self._embedding_dim: int = embedding_dim
+        self._item_embedding_dim: int = item_embedding_dim
+        self._max_sequence_length: int = max_sequence_len
+        self._num_blocks: int = num_blocks
+        self._num_heads: int = num_heads
+        self._dqk: int = attention_dim
+        self._dv: int = linear_dim
+        self._linear_activation: str = linear_activation
+        self._linear_dropout_rate: float = linear_dropout_rate
+        self._attn_dropout_rate: float = attn_dropout_rate
+        self._enable_relative_attention_bias: bool = enable_relative_attention_bias
+        n = max_sequence_len + max_output_len
+        self._hstu = HSTUJagged(
+            modules=[
+                SequentialTransductionUnitJagged(
+                    embedding_dim=embedding_dim, linear_hidden_dim=linear_dim,
+                    attention_dim=attention_dim, normalization=normalization,
+                    linear_config=linear_config, linear_activation=linear_activation,
+                    num_heads=num_heads,
+                    relative_attention_bias_module=(
+                        RelativeBucketedTimeAndPositionBasedBias(
+                            max_seq_len=n, num_buckets=128,
+                            bucketization_fn=_default_bucketization)
+                        if enable_relative_attention_bias else None),
+                    dropout_ratio=linear_dropout_rate, attn_dropout_ratio=attn_dropout_rate,
+                    concat_ua=concat_ua)
+                for _ in range(num_blocks)
+            ],
+            autocast_dtype=compute_dtype,
+        )
+        self.register_buffer("_attn_mask",
+                             torch.triu(torch.ones((n, n), dtype=torch.bool), diagonal=1))
+        self.reset_params()
+
+    def reset_params(self) -> None:
+        # every encoder parameter name contains "_hstu", which the reference skips (:610-621)
+        for name, params in self.named_parameters():
+            if ("_hstu" in name) or ("_embedding_module" in name):
+                continue
+            try:
+                torch.nn.init.xavier_normal_(params.data)
+            except Exception:
+                pass
+
+    def debug_str(self) -> str:
+        s = (f"HSTU-b{self._num_blocks}-h{self._num_heads}-dqk{self._dqk}-dv{self._dv}"
+             f"-l{self._linear_activation}d{self._linear_dropout_rate}-ad{self._attn_dropout_rate}")
+        if not self._enable_relative_attention_bias:
+            s += "-norab"
+        return s
+
+    def forward(self, past_lengths: torch.Tensor, user_embeddings: torch.Tensor,
+                valid_mask: torch.Tensor, past_payloads: Dict[str, torch.Tensor],
+                delta_x_offsets=None, cache=None, return_cache_states: bool = False,
+                total_length: Optional[int] = None):
+        """past_lengths (B,) int; user_embeddings (B, N, D); valid_mask unused (as :637);
+        past_payloads["timestamps"] (B, N) int64.  Returns ((B, N, D), cache states)."""
+        # only the mask's size is read downstream: pass the bool buffer itself instead of
+        # materialising 1 - mask in the activation dtype every step (256 MB at N = 8192)
+        return self._hstu(
+            x=user_embeddings,
+            x_offsets=ops.asynchronous_complete_cumsum(past_lengths),
+            all_timestamps=past_payloads.get(TIMESTAMPS_KEY),
+            invalid_attn_mask=self._attn_mask,
+            delta_x_offsets=delta_x_offsets, cache=cache,
+            return_cache_states=return_cache_states, total_length=total_length)

@@ -1,0 +1,174 @@
+"""Negative samplers — drop-in for the reference's
+``models/negatives_samples/negative_sampler.py`` (:21 base, :65 Local, :135 InBatch).
+
+``forward(positive_ids, num_to_sample) -> (ids, embeddings)`` keeps the reference contract
+(and its RNG stream: the same ``torch.randint`` call).  In addition every sampler exposes
+``fused_sample`` which returns row indices into the source table(s) instead of the gathered
+(N', R, D) tensor; :class:`~mygenerativerecommenders_b200.losses.SampledSoftmaxLoss` feeds
+those to the fused gather.dot kernel, so the negatives tensor is never materialised.
+"""
+from __future__ import annotations
+
+import abc
+from typing import List, NamedTuple, Optional, Tuple
+
+import torch
+
+
+class FusedNegatives(NamedTuple):
+    ids: torch.Tensor                 # (N', R) item ids compared against the positives
+    table0: torch.Tensor              # (X0, d0) source table (autograd leaf or graph tensor)
+    idx0: torch.Tensor                # (N', R) rows of table0
+    table1: Optional[torch.Tensor]    # (X1, d1) second table, concatenated after table0
+    idx1: Optional[torch.Tensor]
+    l2_norm: bool                     # normalise the gathered rows inside the kernel
+    zero_grad_rows: Tuple[Optional[int], Optional[int]]  # padding_idx rows of table0 / table1
+
+
+class NegativesSampler(torch.nn.Module):
+    def __init__(self, l2_norm: bool, l2_norm_eps: float) -> None:
+        super().__init__()
+        self._l2_norm: bool = l2_norm
+        self._l2_norm_eps: float = l2_norm_eps
+
+    def normalize_embeddings(self, x: torch.Tensor) -> torch.Tensor:
+        return self._maybe_l2_norm(x)
+
+    def _maybe_l2_norm(self, x: torch.Tensor) -> torch.Tensor:
+        # x / clamp(||x||_2, min=eps)  (negative_sampler.py:31-37)
+        if self._l2_norm:
+            x = x / torch.clamp(torch.linalg.norm(x, ord=2, dim=-1, keepdim=True),
+                                min=self._l2_norm_eps)
+        return x
+
+    @abc.abstractmethod
+    def debug_str(self) -> str:
+        pass
+
+    @abc.abstractmethod
+    def process_batch(self, ids: torch.Tensor, presences: torch.Tensor,
+                      embeddings: torch.Tensor) -> None:
+        pass
+
+    @abc.abstractmethod
+    def forward(self, positive_ids: torch.Tensor, num_to_sample: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        pass
+
+    def fused_sample(self, positive_ids: torch.Tensor, num_to_sample: int) -> Optional[FusedNegatives]:
+        """Row indices for the fused kernel, or None if this sampler cannot provide them."""
+        return None
+
+
+class LocalNegativesSampler(NegativesSampler):
+    """Uniform sampling with replacement over ``all_item_ids`` (positives included)."""
+
+    def __init__(self, l2_norm: bool, l2_norm_eps: float, num_items: int = None,
+                 all_item_ids: List[int] = None) -> None:
+        super().__init__(l2_norm=l2_norm, l2_norm_eps=l2_norm_eps)
+        if all_item_ids is None and num_items is None:
+            raise ValueError("Either num_items or all_item_ids must be provided")
+        elif all_item_ids and num_items and num_items != len(all_item_ids):
+            raise ValueError("num_items and all_item_ids must have the same length")
+        elif all_item_ids:
+            num_items = len(all_item_ids)
+        elif num_items:
+            all_item_ids = list(range(num_items))
+        self._num_items: int = len(all_item_ids)
+        self.register_buffer("_all_item_ids", torch.tensor(all_item_ids))
+        self._item_emb: torch.nn.Embedding = None
+        self._embeddings_module = None  # late-bound by the caller (retrieval.py:117)
+
+    def debug_str(self) -> str:
+        return f"local{f'-l2-eps{self._l2_norm_eps}' if self._l2_norm else ''}"
+
+    def process_batch(self, ids, presences, embeddings) -> None:
+        pass
+
+    def _draw(self, positive_ids: torch.Tensor, num_to_sample: int) -> torch.Tensor:
+        shape = positive_ids.size() + (num_to_sample,)
+        offsets = torch.randint(low=0, high=self._num_items, size=shape,
+                                dtype=positive_ids.dtype, device=positive_ids.device)
+        return self._all_item_ids[offsets.view(-1)].reshape(shape)
+
+    def forward(self, positive_ids: torch.Tensor, num_to_sample: int):
+        sampled_ids = self._draw(positive_ids, num_to_sample)
+        if self._embeddings_module is not None:
+            emb = self._embeddings_module.get_item_embeddings(sampled_ids)
+        else:
+            emb = self._item_emb(sampled_ids)
+        return sampled_ids, self.normalize_embeddings(emb)
+
+    def fused_sample(self, positive_ids: torch.Tensor, num_to_sample: int) -> Optional[FusedNegatives]:
+        mod = self._embeddings_module
+        if mod is not None:
+            item = getattr(mod, "_item_emb", None)
+            year = getattr(mod, "_year_emb", None)
+            if not isinstance(item, torch.nn.Embedding):
+                return None
+            if year is not None and not (isinstance(year, torch.nn.Embedding)
+                                         and hasattr(mod, "lookup_year_ids")):
+                return None
+            # CategoricalEmbeddingModule-style id remapping is not a plain table gather
+            if hasattr(mod, "_item_id_to_category_id"):
+                return None
+            ids = self._draw(positive_ids, num_to_sample)
+            if year is None:
+                return FusedNegatives(ids, item.weight, ids, None, None, self._l2_norm,
+                                      (item.padding_idx, None))
+            # this fork: concat(item_emb[id], year_emb[year_lookup[id]])  (embeddings.py:94-97)
+            return FusedNegatives(ids, item.weight, ids, year.weight, mod.lookup_year_ids(ids),
+                                  self._l2_norm, (item.padding_idx, year.padding_idx))
+        if isinstance(self._item_emb, torch.nn.Embedding):
+            ids = self._draw(positive_ids, num_to_sample)
+            return FusedNegatives(ids, self._item_emb.weight, ids, None, None, self._l2_norm,
+                                  (self._item_emb.padding_idx, None))
+        return None
+
+
+class InBatchNegativesSampler(NegativesSampler):
+    """Uniform sampling over the ids present in the current batch (optionally de-duplicated)."""
+
+    def __init__(self, l2_norm: bool, l2_norm_eps: float, dedup_embeddings: bool) -> None:
+        super().__init__(l2_norm=l2_norm, l2_norm_eps=l2_norm_eps)
+        self._dedup_embeddings: bool = dedup_embeddings
+
+    def debug_str(self) -> str:
+        s = f"in-batch{f'-l2-eps{self._l2_norm_eps}' if self._l2_norm else ''}"
+        return s + "-dedup" if self._dedup_embeddings else s
+
+    def process_batch(self, ids: torch.Tensor, presences: torch.Tensor,
+                      embeddings: torch.Tensor) -> None:
+        """ids (N') or (B, N) int64; presences same shape, bool; embeddings (..., D)."""
+        assert ids.size() == presences.size()
+        assert ids.size() == embeddings.size()[:-1]
+        valid_ids = ids[presences]
+        valid_emb = embeddings[presences]
+        if self._dedup_embeddings:
+            # one representative occurrence per distinct id (negative_sampler.py:168-184);
+            # equal ids carry equal embeddings, so which occurrence wins does not matter
+            uniq, inverse = torch.unique(valid_ids, sorted=False, return_inverse=True)
+            rep = torch.empty(uniq.numel(), dtype=torch.int64, device=uniq.device)
+            rep[inverse] = torch.arange(valid_ids.numel(), dtype=torch.int64, device=uniq.device)
+            self._cached_embeddings = self._maybe_l2_norm(valid_emb[rep, :])
+            self._cached_ids = uniq
+        else:
+            self._cached_embeddings = self._maybe_l2_norm(valid_emb)
+            self._cached_ids = valid_ids
+
+    def get_all_ids_and_embeddings(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self._cached_ids, self._cached_embeddings
+
+    def _draw(self, positive_ids: torch.Tensor, num_to_sample: int) -> torch.Tensor:
+        return torch.randint(low=0, high=self._cached_ids.size(0),
+                             size=positive_ids.size() + (num_to_sample,),
+                             dtype=positive_ids.dtype, device=positive_ids.device)
+
+    def forward(self, positive_ids: torch.Tensor, num_to_sample: int):
+        offsets = self._draw(positive_ids, num_to_sample)
+        return self._cached_ids[offsets], self._cached_embeddings[offsets]
+
+    def fused_sample(self, positive_ids: torch.Tensor, num_to_sample: int) -> Optional[FusedNegatives]:
+        offsets = self._draw(positive_ids, num_to_sample)
+        # the cache is already normalised (process_batch), so the kernel must not re-normalise
+        return FusedNegatives(self._cached_ids[offsets], self._cached_embeddings, offsets, None,
+                              None, False, (None, None))

@@ -1,0 +1,113 @@
+"""CPU-side checks: the C-ABI library loads and exports what include/grb200.h declares, the host
+modules mirror the reference's names, and the product path refuses CPU tensors (no fallback)."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+import mygenerativerecommenders_b200 as pkg
+from mygenerativerecommenders_b200 import _lib, hstu, ops
+from conftest import hstu_case
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _declared_symbols():
+    text = (ROOT / "include" / "grb200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(grb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _declared_symbols()
+    assert len(names) >= 15
+    handle = ctypes.CDLL(str(_lib.LIB_PATH))
+    for n in names:
+        assert hasattr(handle, n), f"libgrb200.so lacks {n}"
+    assert sorted(_lib.SYMBOLS) == names, "ctypes table and header disagree"
+    assert _lib.lib().grb_version() == 100
+
+
+def test_struct_layouts_match_header():
+    # sizes implied by the header's field lists (8-byte aligned, LP64)
+    assert ctypes.sizeof(_lib.HstuAttnArgs) == 4 * 8 + 6 * 4 + 3 * 8 + 3 * 8 + 5 * 8 + 2 * 8 + 2 * 8 + 3 * 8 + 3 * 8 + 3 * 8
+    assert ctypes.sizeof(_lib.MipsTopkArgs) == 3 * 8 + 2 * 4 + 4 * 8 + 8 + 2 * 8 + 2 * 8 + 2 * 8 + 8
+    assert ctypes.sizeof(_lib.SslArgs) == 8 + 6 * 4 + 2 * 4 + 8 * 8 + 4 * 8 + 2 * 8 + 5 * 8
+
+
+def test_invalid_arguments_are_reported_without_a_gpu():
+    L = _lib.lib()
+    assert L.grb_complete_cumsum(None, None, 4, 16, None) == _lib.GRB_ERR_INVALID_ARG
+    assert b"index_bits" in L.grb_last_error_string()
+    with pytest.raises(ValueError):
+        _lib.check(L.grb_complete_cumsum(None, None, 4, 16, None))
+    a = _lib.MipsTopkArgs()
+    a.B, a.X, a.D, a.k = 4, 100, 8, 200  # k > X
+    assert L.grb_mips_topk_workspace_bytes(ctypes.byref(a)) == _lib.GRB_ERR_INVALID_ARG
+
+
+def test_no_cpu_fallback():
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.asynchronous_complete_cumsum(torch.tensor([1, 2]))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.dense_to_jagged(torch.zeros(2, 3, 1), torch.tensor([0, 1, 3]))
+    with pytest.raises(ValueError, match="max_lengths must be an integer"):
+        ops.jagged_to_padded_dense(torch.zeros(3, 1), torch.tensor([0, 1, 3]), [3], 0.0)
+
+
+def test_product_never_imports_oracle():
+    for p in (ROOT / "mygenerativerecommenders_b200").rglob("*.py"):
+        assert "oracle" not in p.read_text(), f"{p} mentions the oracle"
+
+
+def test_bucket_threshold_table_matches_reference(golden):
+    g = golden("bias")
+    thr = hstu.tabulate_bucket_thresholds(hstu._default_bucketization, 128)
+    assert thr.dtype == torch.int64 and thr.numel() == 128
+    assert (thr[1:] >= thr[:-1]).all()
+    got = torch.bucketize(g["bucket_probe"], thr, right=True)
+    assert torch.equal(got, g["bucket_value"])
+    # first edges are ceil(e^{0.301 k})
+    assert thr[:8].tolist() == [2, 2, 3, 4, 5, 7, 9, 12]
+
+
+def test_dense_bias_module_matches_reference(golden):
+    g = golden("bias")
+    N = g["bias_ts"].shape[1]
+    m = hstu.RelativeBucketedTimeAndPositionBasedBias(N, 128, hstu._default_bucketization)
+    with torch.no_grad():
+        m._ts_w.copy_(g["bias_ts_w"]); m._pos_w.copy_(g["bias_pos_w"])
+    assert torch.equal(m(g["bias_ts"]).detach(), g["bias_out"])
+
+
+@pytest.mark.parametrize("name", ["mh", "ml1m"])
+def test_module_parameter_names_match_reference(golden, name):
+    c = hstu_case(golden("hstu"), name)
+    enc = hstu.HSTU(max_sequence_len=c["max_seq"], max_output_len=c["out_len"],
+                    embedding_dim=c["D"], item_embedding_dim=c["D"], num_blocks=c["blocks"],
+                    num_heads=c["H"], linear_dim=c["dv"], attention_dim=c["dqk"],
+                    normalization="rel_bias", linear_config="uvqk", linear_activation="silu",
+                    linear_dropout_rate=0.2, attn_dropout_rate=0.0)
+    ours = {k: tuple(v.shape) for k, v in enc.state_dict().items()}
+    ref = {k: tuple(v.shape) for k, v in c["sd"].items()}
+    ref["_attn_mask"] = (c["N"], c["N"])
+    assert ours == ref
+    missing, unexpected = enc.load_state_dict(c["sd"], strict=False)
+    assert unexpected == [] and missing == ["_attn_mask"]
+
+
+def test_public_api_names():
+    for n in ["asynchronous_complete_cumsum", "dense_to_jagged", "jagged_to_padded_dense",
+              "batch_gather_embeddings", "batch_scatter_embeddings", "get_current_embeddings",
+              "jagged_or_dense_repeat_interleave_dim0", "jagged_or_dense_index_select_dim0",
+              "mask_dense_by_aux_mask"]:
+        assert callable(getattr(ops, n))
+    from mygenerativerecommenders_b200 import (candidate_index, losses, negative_sampler,
+                                                similarity, top_k)
+    assert issubclass(top_k.MIPSBruteForceTopK, top_k.TopKModule)
+    assert issubclass(negative_sampler.LocalNegativesSampler, negative_sampler.NegativesSampler)
+    assert issubclass(losses.SampledSoftmaxLoss, losses.AutoregressiveLoss)
+    assert similarity.DotProductSimilarity().debug_str() == "dp"
+    assert candidate_index.CandidateIndex is not None

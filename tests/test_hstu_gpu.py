@@ -1,0 +1,193 @@
+"""a4-a8 on the GPU: fused jagged attention, LN/gate and the HSTU modules against the reference's
+golden outputs (tests/golden/hstu.pt) and the CPU oracle.
+
+Tolerances: fp32 path  max|d| <= 1e-5 * ||ref||_inf for outputs, 2e-4 for gradients
+(fp32 atomics reorder sums); bf16 path  ||d||_inf <= 1e-2 * ||ref||_inf and ||d||_2/||ref||_2 <=
+5e-3 for outputs, 2e-2 for gradients."""
+import pytest
+import torch
+
+from mygenerativerecommenders_b200 import functional as GF
+from mygenerativerecommenders_b200 import hstu
+from oracle import reference_port as O
+from conftest import hstu_case
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _close(got, ref, tol_inf, tol_l2=None, what=""):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    scale = max(ref.abs().max().item(), 1e-12)
+    err = (got - ref).abs().max().item()
+    assert err <= tol_inf * scale, f"{what}: max|d|={err:.3e} > {tol_inf:.0e}*{scale:.3e}"
+    if tol_l2 is not None:
+        rel = ((got - ref).norm() / max(ref.norm().item(), 1e-12)).item()
+        assert rel <= tol_l2, f"{what}: rel-l2 {rel:.3e} > {tol_l2:.0e}"
+
+
+def _rand_case(seed, B, N, H, dqk, dv, lengths, with_ts=True, dtype=torch.float32):
+    gen = torch.Generator().manual_seed(seed)
+    lengths = torch.tensor(lengths, dtype=torch.int64)
+    off = O.complete_cumsum(lengths)
+    T = int(off[-1])
+    q = torch.randn(T, H * dqk, generator=gen)
+    k = torch.randn(T, H * dqk, generator=gen)
+    v = torch.randn(T, H * dv, generator=gen)
+    ts = None
+    if with_ts:
+        steps = torch.randint(1, 100000, (B, N), generator=gen)
+        ts = 978_300_000 + torch.cumsum(steps, dim=1)
+        mask = torch.arange(N).unsqueeze(0) <= lengths.unsqueeze(1)  # keep index n_b (target ts)
+        ts = ts * mask
+    ts_w = torch.randn(129, generator=gen) * 0.5
+    pos_w = torch.randn(2 * N - 1, generator=gen) * 0.5
+    return dict(off=off, T=T, q=q, k=k, v=v, ts=ts, ts_w=ts_w, pos_w=pos_w, lengths=lengths)
+
+
+THR = None
+
+
+def _thr():
+    global THR
+    if THR is None:
+        THR = hstu.tabulate_bucket_thresholds(hstu._default_bucketization, 128).to(DEV)
+    return THR
+
+
+def _run_kernel(c, N, H, dqk, dv, dtype=torch.float32, grad=False):
+    q, k, v = (c[n].to(DEV).to(dtype).requires_grad_(grad) for n in ("q", "k", "v"))
+    ts = c["ts"].to(DEV) if c["ts"] is not None else None
+    ts_w = c["ts_w"].to(DEV).requires_grad_(grad)
+    pos_w = c["pos_w"].to(DEV).requires_grad_(grad)
+    out = GF.hstu_attention(q, k, v, c["off"].to(DEV), ts, ts_w if ts is not None else None,
+                            pos_w if ts is not None else None, _thr() if ts is not None else None,
+                            N, H, dqk, dv)
+    return out, (q, k, v, ts_w, pos_w)
+
+
+@pytest.mark.parametrize("B,N,H,dqk,dv,lengths", [
+    (4, 24, 2, 8, 8, [1, 24, 7, 13]),
+    (3, 211, 1, 50, 50, [211, 37, 64]),           # ml-1m head shape, N not a tile multiple
+    (5, 70, 3, 16, 24, [0, 65, 64, 1, 70]),        # empty sequence, tile-edge lengths, dqk != dv
+    (2, 130, 2, 64, 64, [130, 129]),
+    (2, 40, 1, 200, 130, [40, 17]),                # wide heads (forward only)
+])
+def test_attention_forward_fp32_vs_oracle(B, N, H, dqk, dv, lengths):
+    c = _rand_case(B * 100 + N, B, N, H, dqk, dv, lengths)
+    out, _ = _run_kernel(c, N, H, dqk, dv)
+    ref = O.hstu_attention(c["q"], c["k"], c["v"], c["off"], c["ts"], c["ts_w"], c["pos_w"],
+                           N, H, dqk, dv)
+    _close(out, ref, 1e-5, what="attn fwd")
+
+
+def test_attention_without_timestamps_has_no_bias():
+    c = _rand_case(7, 3, 33, 2, 16, 16, [33, 5, 20], with_ts=False)
+    out, _ = _run_kernel(c, 33, 2, 16, 16)
+    ref = O.hstu_attention(c["q"], c["k"], c["v"], c["off"], None, None, None, 33, 2, 16, 16)
+    _close(out, ref, 1e-5, what="attn fwd no-ts")
+
+
+@pytest.mark.parametrize("B,N,H,dqk,dv,lengths", [
+    (4, 24, 2, 8, 8, [1, 24, 7, 13]),
+    (3, 211, 1, 50, 50, [211, 37, 64]),
+    (4, 70, 3, 16, 24, [0, 65, 64, 70]),
+    (2, 130, 2, 64, 64, [130, 129]),
+])
+def test_attention_backward_fp32_vs_oracle(B, N, H, dqk, dv, lengths):
+    c = _rand_case(B * 10 + N, B, N, H, dqk, dv, lengths)
+    gen = torch.Generator().manual_seed(1)
+    w = torch.randn(c["T"], H * dv, generator=gen)
+    out, leaves = _run_kernel(c, N, H, dqk, dv, grad=True)
+    (out * w.to(DEV)).sum().backward()
+    ref_leaves = [c[n].clone().double().requires_grad_(True) for n in ("q", "k", "v", "ts_w", "pos_w")]
+    ref = O.hstu_attention(ref_leaves[0], ref_leaves[1], ref_leaves[2], c["off"], c["ts"],
+                           ref_leaves[3], ref_leaves[4], N, H, dqk, dv)
+    (ref * w.double()).sum().backward()
+    for name, got, r in zip(("dq", "dk", "dv", "d_ts_w", "d_pos_w"), leaves, ref_leaves):
+        _close(got.grad, r.grad, 2e-4, what=name)
+
+
+def test_padded_rows_and_neighbour_sequences_do_not_leak():
+    # same sequence alone and inside a batch must give identical rows (jagged independence)
+    N, H, d = 96, 2, 32
+    c = _rand_case(11, 3, N, H, d, d, [50, 96, 3])
+    out, _ = _run_kernel(c, N, H, d, d)
+    s, e = int(c["off"][1]), int(c["off"][2])
+    solo = dict(c)
+    solo.update(off=torch.tensor([0, e - s]), q=c["q"][s:e], k=c["k"][s:e], v=c["v"][s:e],
+                ts=c["ts"][1:2], T=e - s)
+    out1, _ = _run_kernel(solo, N, H, d, d)
+    assert torch.equal(out[s:e], out1)
+
+
+@pytest.mark.parametrize("W", [50, 64, 256, 1000])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_ln_gate_vs_torch(W, dtype):
+    gen = torch.Generator().manual_seed(W)
+    x = torch.randn(37, W, generator=gen) * 3 + 1
+    u = torch.randn(37, W, generator=gen)
+    dy = torch.randn(37, W, generator=gen)
+    xg, ug = x.to(DEV).to(dtype).requires_grad_(True), u.to(DEV).to(dtype).requires_grad_(True)
+    y = GF.layer_norm_gate(xg, ug, 1e-6)
+    y.backward(dy.to(DEV).to(dtype))
+    xr, ur = xg.detach().double().cpu().requires_grad_(True), ug.detach().double().cpu().requires_grad_(True)
+    yr = ur * torch.nn.functional.layer_norm(xr, [W], eps=1e-6)
+    yr.backward(dy.to(dtype).double())
+    t = (1e-5, None) if dtype == torch.float32 else (1e-2, 5e-3)
+    _close(y, yr, *t, what="ln_gate y")
+    tg = (1e-4, None) if dtype == torch.float32 else (2e-2, 2e-2)
+    _close(xg.grad, xr.grad, *tg, what="ln_gate dx")
+    _close(ug.grad, ur.grad, *tg, what="ln_gate dgate")
+    y2 = GF.layer_norm_gate(xg.detach(), None, 1e-6)
+    _close(y2, torch.nn.functional.layer_norm(xr.detach(), [W], eps=1e-6), *t, what="ln y")
+
+
+def _build(c, compute_dtype=None):
+    enc = hstu.HSTU(max_sequence_len=c["max_seq"], max_output_len=c["out_len"],
+                    embedding_dim=c["D"], item_embedding_dim=c["D"], num_blocks=c["blocks"],
+                    num_heads=c["H"], linear_dim=c["dv"], attention_dim=c["dqk"],
+                    normalization="rel_bias", linear_config="uvqk", linear_activation="silu",
+                    linear_dropout_rate=0.2, attn_dropout_rate=0.0, compute_dtype=compute_dtype)
+    enc.load_state_dict(c["sd"], strict=False)
+    return enc.to(DEV).eval()
+
+
+@pytest.mark.parametrize("name", ["mh", "ml1m", "h64"])
+def test_hstu_module_fp32_vs_reference_golden(golden, name):
+    c = hstu_case(golden("hstu"), name)
+    enc = _build(c)
+    x = c["x"].to(DEV).requires_grad_(True)
+    y, _ = enc(past_lengths=c["lengths"].to(DEV), user_embeddings=x, valid_mask=None,
+               past_payloads={"timestamps": c["ts"].to(DEV)})
+    _close(y, c["y"], 1e-5, what=f"{name} y")
+    (y * c["w"].to(DEV)).sum().backward()
+    _close(x.grad, c["dx"], 2e-4, what=f"{name} dx")
+    for k, p in enc.named_parameters():
+        _close(p.grad, c["grads"][k], 5e-4, what=f"{name} grad {k}")
+
+
+def test_hstu_module_bf16_vs_reference_golden(golden):
+    c = hstu_case(golden("hstu"), "h64")
+    enc = _build(c, compute_dtype=torch.bfloat16)
+    x = c["x"].to(DEV).requires_grad_(True)
+    y, _ = enc(past_lengths=c["lengths"].to(DEV), user_embeddings=x, valid_mask=None,
+               past_payloads={"timestamps": c["ts"].to(DEV)})
+    assert y.dtype == torch.float32
+    _close(y, c["y"], 2e-2, 1e-2, what="bf16 y")
+    (y * c["w"].to(DEV)).sum().backward()
+    _close(x.grad, c["dx"], 5e-2, 2e-2, what="bf16 dx")
+    for k, p in enc.named_parameters():
+        _close(p.grad, c["grads"][k], 8e-2, 3e-2, what=f"bf16 grad {k}")
+
+
+def test_training_mode_dropout_only_touches_o_input(golden):
+    c = hstu_case(golden("hstu"), "mh")
+    enc = _build(c).train()
+    torch.manual_seed(0)
+    y1, _ = enc(past_lengths=c["lengths"].to(DEV), user_embeddings=c["x"].to(DEV), valid_mask=None,
+                past_payloads={"timestamps": c["ts"].to(DEV)})
+    torch.manual_seed(0)
+    y2, _ = enc(past_lengths=c["lengths"].to(DEV), user_embeddings=c["x"].to(DEV), valid_mask=None,
+                past_payloads={"timestamps": c["ts"].to(DEV)})
+    assert torch.equal(y1, y2) and not torch.allclose(y1.cpu(), c["y"], atol=1e-4)

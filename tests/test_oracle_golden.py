@@ -1,0 +1,102 @@
+"""The CPU oracle (oracle/reference_port.py) against fixtures produced by the real reference
+(oracle/make_golden.py).  CPU-only; pins the oracle before any kernel is compared with it."""
+import pytest
+import torch
+
+from oracle import reference_port as O
+from conftest import hstu_case
+
+
+def test_ops_known_answers(golden):
+    g = golden("ops")
+    # the reference's own vectors, /root/reference/tests/test_ops.py:7-53
+    assert torch.equal(O.complete_cumsum(g["kat_cumsum_in"]), g["kat_cumsum_out"])
+    assert O.complete_cumsum(g["kat_cumsum_in"]).dtype == torch.int32
+    assert torch.equal(g["kat_cumsum_out"], torch.tensor([0, 1, 3], dtype=torch.int32))
+    assert torch.equal(O.dense_to_jagged(g["kat_d2j_in"], g["kat_cumsum_out"]), g["kat_d2j_out"])
+    assert torch.equal(O.jagged_to_padded_dense(g["kat_j2d_in"], g["kat_j2d_off"], 3, 0.0),
+                       g["kat_j2d_out"])
+
+
+def test_ops_ragged(golden):
+    g = golden("ops")
+    off = O.complete_cumsum(g["r_lengths"])
+    assert torch.equal(off, g["r_offsets"])
+    jag = O.dense_to_jagged(g["r_dense"], off)
+    assert torch.equal(jag, g["r_jagged"])
+    assert torch.equal(O.jagged_to_padded_dense(jag, off, 12, 0.0), g["r_padded"])
+    assert torch.equal(O.jagged_to_padded_dense(jag, off, 12, -1.5), g["r_padded_pad"])
+    assert torch.equal(O.get_current_embeddings(g["cur_lengths"], g["r_dense"]), g["cur_out"])
+    out, nl = O.mask_dense_by_aux_mask(g["mask_dense"], g["mask_aux"], g["mask_lengths"], 4)
+    assert torch.equal(out, g["mask_out"]) and torch.equal(nl, g["mask_new_lengths"])
+
+
+def test_bucket_and_bias(golden):
+    g = golden("bias")
+    assert torch.equal(O.bucketize_ts(g["bucket_probe"]), g["bucket_value"])
+    N = g["bias_ts"].shape[1]
+    out = O.rel_bias(g["bias_ts"], g["bias_ts_w"], g["bias_pos_w"], N)
+    assert torch.equal(out, g["bias_out"])  # same ops in the same order: bit-exact
+
+
+@pytest.mark.parametrize("name", ["mh", "ml1m", "h64"])
+def test_hstu_forward_backward(golden, name):
+    c = hstu_case(golden("hstu"), name)
+    sd = {k: v.clone().requires_grad_(True) for k, v in c["sd"].items()}
+    x = c["x"].clone().requires_grad_(True)
+    y = O.hstu_forward(c["lengths"], x, c["ts"], sd, c["blocks"], c["H"], c["dqk"], c["dv"])
+    # fp32 on both sides, same algorithm: tolerance 1e-5 relative to the output scale
+    scale = c["y"].abs().max().item()
+    assert (y - c["y"]).abs().max().item() <= 1e-5 * scale
+    (y * c["w"]).sum().backward()
+    assert (x.grad - c["dx"]).abs().max().item() <= 1e-4 * c["dx"].abs().max().item()
+    for k, gref in c["grads"].items():
+        got = sd[k].grad
+        assert got is not None, k
+        assert (got - gref).abs().max().item() <= 2e-4 * max(gref.abs().max().item(), 1e-6), k
+
+
+def test_topk_and_candidate_index(golden):
+    g = golden("retrieval")
+    s, i = O.mips_topk(g["tk_q"], g["tk_table"], g["tk_ids"], 25)
+    assert torch.equal(i, g["tk_ids25"])
+    assert torch.allclose(s, g["tk_scores25"], atol=1e-6)
+    oi, os_ = O.candidate_index_topk(g["tk_q"], g["tk_table"], g["tk_ids"], 10, g["ci_invalid"])
+    assert torch.equal(oi, g["ci_ids"])
+    assert torch.allclose(os_, g["ci_scores"], atol=1e-6)
+
+
+def test_topk_tie_rule():
+    # duplicated items => equal scores; the lowest index must win, in order
+    q = torch.tensor([[1.0, 0.0]])
+    items = torch.tensor([[0.5, 0.0], [0.9, 0.0], [0.9, 0.0], [0.1, 0.0], [0.9, 0.0]])
+    s, i = O.mips_topk(q, items, None, 3)
+    assert i.tolist() == [[1, 2, 4]]
+    s, i = O.mips_topk(q, items, None, 2, chunk=2)
+    assert i.tolist() == [[1, 2]]
+
+
+def test_sampled_softmax(golden):
+    g = golden("retrieval")
+    table = g["ssl_table"].clone().requires_grad_(True)
+    out_emb = g["ssl_out_emb"].clone().requires_grad_(True)
+    neg_emb = table[g["ssl_neg_ids"]]
+    sup_emb = table[g["ssl_sup_ids"]]
+    loss, _ = O.sampled_softmax_loss(out_emb, g["ssl_sup_ids"], sup_emb, g["ssl_sup_w"],
+                                     g["ssl_neg_ids"], neg_emb, 0.05, 1e-6)
+    assert abs(loss.item() - g["ssl_loss"].item()) <= 1e-5 * abs(g["ssl_loss"].item())
+    loss.backward()
+    assert torch.allclose(out_emb.grad, g["ssl_d_out_emb"], rtol=1e-4, atol=1e-6)
+    dt = table.grad.clone()
+    dt[0] = 0  # padding_idx row of the reference's nn.Embedding
+    assert torch.allclose(dt, g["ssl_d_table"], rtol=1e-4, atol=1e-6)
+
+
+def test_inbatch_dedup(golden):
+    g = golden("retrieval")
+    ids, emb = O.inbatch_process(g["ib_ids"], g["ib_ids"] != 0, g["ib_emb"], 1e-6, True)
+    # unique(sorted=False) order is unspecified: compare as id -> embedding maps
+    ref = {int(i): e for i, e in zip(g["ib_cached_ids"], g["ib_cached_emb"])}
+    assert sorted(ref) == sorted(int(i) for i in ids)
+    for i, e in zip(ids, emb):
+        assert torch.allclose(e, ref[int(i)], atol=1e-7)

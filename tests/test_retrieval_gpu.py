@@ -1,0 +1,221 @@
+"""b1-b6 on the GPU: fused MIPS top-k, candidate index, samplers and the fused sampled-softmax
+loss against the reference's golden outputs and the CPU oracle.
+
+Scores: fp32 tables agree to 1e-5 absolute on unit-norm embeddings; index sets must be identical
+wherever adjacent score gaps exceed 2*tol, ties resolved to the lowest item index."""
+import pytest
+import torch
+
+from mygenerativerecommenders_b200 import functional as GF
+from mygenerativerecommenders_b200.candidate_index import CandidateIndex
+from mygenerativerecommenders_b200.losses import SampledSoftmaxLoss
+from mygenerativerecommenders_b200.negative_sampler import (InBatchNegativesSampler,
+                                                             LocalNegativesSampler)
+from mygenerativerecommenders_b200.similarity import DotProductSimilarity
+from mygenerativerecommenders_b200.top_k import MIPSBruteForceTopK
+from oracle import reference_port as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _check_topk(got_s, got_i, ref_s, ref_i, tol):
+    got_s, got_i = got_s.cpu().float(), got_i.cpu()
+    assert torch.allclose(got_s, ref_s, atol=tol), (got_s - ref_s).abs().max()
+    assert (got_s[:, 1:] <= got_s[:, :-1]).all(), "not sorted"
+    # identical ids wherever the neighbouring gaps are > 2*tol; elsewhere same score is enough
+    B, k = ref_i.shape
+    for b in range(B):
+        if torch.equal(got_i[b], ref_i[b]):
+            continue
+        for c in range(k):
+            if got_i[b, c] != ref_i[b, c]:
+                lo, hi = max(c - 1, 0), min(c + 1, k - 1)
+                gap = min((ref_s[b, lo] - ref_s[b, c]).abs() if lo != c else 1e9,
+                          (ref_s[b, c] - ref_s[b, hi]).abs() if hi != c else 1e9)
+                assert gap <= 2 * tol, f"row {b} col {c}: ids differ across a gap of {gap}"
+
+
+def test_golden_topk_and_candidate_index(golden):
+    g = golden("retrieval")
+    ids, table, q = g["tk_ids"].to(DEV), g["tk_table"].to(DEV), g["tk_q"].to(DEV)
+    ci = CandidateIndex(k=10, ids=ids, top_k_module=MIPSBruteForceTopK(),
+                        embeddings=table.unsqueeze(0)).to(DEV)
+    assert ci._embeddings_t.shape == (table.shape[1], table.shape[0])
+    assert ci.embeddings.shape == (1, *table.shape)
+    s, i = ci._top_k_module(q, ci._embeddings_t, ci.ids, k=25, sorted=True)
+    _check_topk(s, i, g["tk_scores25"], g["tk_ids25"], 1e-5)
+    oi, os_ = ci.get_top_k_outputs(q, invalid_ids=g["ci_invalid"].to(DEV))
+    assert torch.equal(oi.cpu(), g["ci_ids"])
+    assert torch.allclose(os_.cpu(), g["ci_scores"], atol=1e-5)
+
+
+def test_ties_resolve_to_lowest_index():
+    base = torch.nn.functional.normalize(torch.randn(40, 16, generator=torch.Generator().manual_seed(3)), dim=-1)
+    items = base.repeat(25, 1)                     # every item appears 25 times: massive ties
+    q = base[:5].clone()
+    s, i = GF.mips_topk(q.to(DEV), items.to(DEV), None, 60)
+    rs, ri = O.mips_topk(q, items, None, 60)
+    assert torch.equal(i.cpu(), ri)
+    assert torch.allclose(s.cpu(), rs, atol=1e-6)
+
+
+@pytest.mark.parametrize("B,X,D,k,dtype", [
+    (128, 3883, 50, 411, torch.float32),           # C1: ml-1m corpus, k' = 200 + 211
+    (128, 3883, 50, 411, torch.bfloat16),
+    (17, 100_000, 64, 261, torch.float32),         # C3-shaped slice, k' = 200 + 61
+    (130, 50_000, 256, 200, torch.bfloat16),       # C4-shaped slice: D = 256 bf16, 2 query tiles
+    (3, 700, 24, 700, torch.float32),              # k == X
+    (1, 129, 8, 1, torch.float32),
+])
+def test_random_corpora_vs_oracle(B, X, D, k, dtype):
+    gen = torch.Generator().manual_seed(X + k)
+    items = torch.nn.functional.normalize(torch.randn(X, D, generator=gen), dim=-1).to(dtype)
+    q = torch.nn.functional.normalize(torch.randn(B, D, generator=gen), dim=-1).to(dtype)
+    ids = torch.arange(1, X + 1) * 3
+    s, i = GF.mips_topk(q.to(DEV), items.to(DEV), ids.to(DEV), k)
+    rs, ri = O.mips_topk(q, items, ids, k)
+    _check_topk(s, i, rs, ri, 1e-5 if dtype == torch.float32 else 2e-5)
+
+
+def test_adversarial_order_forces_exact_rerun():
+    # scores increase with the item index: the strided sample under-estimates tau badly,
+    # candidate lists overflow, and the wrapper must still return the exact answer
+    X, D, B, k = 60_000, 8, 4, 50
+    items = torch.zeros(X, D)
+    items[:, 0] = torch.linspace(-1, 1, X)
+    q = torch.zeros(B, D)
+    q[:, 0] = torch.tensor([1.0, 0.5, -1.0, 2.0])
+    s, i = GF.mips_topk(q.to(DEV), items.to(DEV), None, k)
+    rs, ri = O.mips_topk(q, items, None, k)
+    assert torch.equal(i.cpu(), ri)
+
+
+def test_topk_merge_matches_global_topk():
+    gen = torch.Generator().manual_seed(8)
+    B, G, kl, k = 33, 8, 200, 200
+    s = torch.randn(B, G * kl, generator=gen)
+    s[:, 100:140] = s[:, 300:340]                 # cross-shard ties
+    ids = torch.randperm(10 ** 7, generator=gen)[:G * kl].unsqueeze(0).repeat(B, 1) + (1 << 33)
+    ms, mi = GF.topk_merge(s.to(DEV), ids.to(DEV), k)
+    order = torch.argsort(ids, dim=1, stable=True)
+    cs, ci = torch.gather(s, 1, order), torch.gather(ids, 1, order)
+    order = torch.argsort(cs, dim=1, descending=True, stable=True)[:, :k]
+    assert torch.equal(mi.cpu(), torch.gather(ci, 1, order))
+    assert torch.equal(ms.cpu(), torch.gather(cs, 1, order))
+
+
+def test_similarity_branches():
+    sim = DotProductSimilarity()
+    a = torch.randn(6, 8, device=DEV)
+    out = sim(a, torch.randn(1, 10, 8, device=DEV), None, None)
+    assert isinstance(out, tuple) and out[0].shape == (6, 10) and out[1] == {}
+    assert sim(a, torch.randn(6, 10, 8, device=DEV), None, None).shape == (6, 10)
+    assert sim(a, torch.randn(3, 10, 8, device=DEV), None, None).shape == (6, 10)
+
+
+def _ssl_setup(g):
+    table = g["ssl_table"].to(DEV)
+    emb = torch.nn.Embedding(table.shape[0], table.shape[1], padding_idx=0).to(DEV)
+    with torch.no_grad():
+        emb.weight.copy_(table)
+    smp = LocalNegativesSampler(l2_norm=True, l2_norm_eps=1e-6,
+                                all_item_ids=list(range(1, table.shape[0]))).to(DEV)
+    smp._item_emb = emb
+    return emb, smp
+
+
+def test_fused_sampled_softmax_vs_reference_golden(golden, monkeypatch):
+    g = golden("retrieval")
+    emb, smp = _ssl_setup(g)
+    neg = g["ssl_neg_ids"].to(DEV)
+    monkeypatch.setattr(smp, "_draw", lambda positive_ids, n: neg)   # the reference's CPU draw
+    out_emb = g["ssl_out_emb"].to(DEV).requires_grad_(True)
+    sup_ids = g["ssl_sup_ids"].to(DEV)
+    loss_fn = SampledSoftmaxLoss(num_to_sample=neg.shape[1], softmax_temperature=0.05)
+    loss = loss_fn.jagged_forward(output_embeddings=out_emb, supervision_ids=sup_ids,
+                                  supervision_embeddings=emb(sup_ids),
+                                  supervision_weights=g["ssl_sup_w"].to(DEV),
+                                  negatives_sampler=smp, similarity=DotProductSimilarity())
+    assert abs(loss.item() - g["ssl_loss"].item()) <= 1e-5 * abs(g["ssl_loss"].item())
+    loss.backward()
+    assert torch.allclose(out_emb.grad.cpu(), g["ssl_d_out_emb"], rtol=1e-4, atol=1e-6)
+    assert torch.allclose(emb.weight.grad.cpu(), g["ssl_d_table"], rtol=1e-4, atol=1e-6)
+    # and the unfused module path (generic sampler.forward + similarity) agrees with the fused one
+    emb.weight.grad = None
+    out2 = g["ssl_out_emb"].to(DEV).requires_grad_(True)
+    monkeypatch.setattr(smp, "fused_sample", lambda positive_ids, n: None)
+    loss2 = loss_fn.jagged_forward(output_embeddings=out2, supervision_ids=sup_ids,
+                                   supervision_embeddings=emb(sup_ids),
+                                   supervision_weights=g["ssl_sup_w"].to(DEV),
+                                   negatives_sampler=smp, similarity=DotProductSimilarity())
+    assert abs(loss2.item() - loss.item()) <= 1e-5 * abs(loss.item())
+
+
+def test_fused_two_table_concat_and_collisions():
+    # this fork's embedding: concat(item_emb[id], year_emb[year_lookup[id]]) (embeddings.py:94-97)
+    gen = torch.Generator().manual_seed(12)
+    n, R, d0, d1, V = 300, 128, 25, 25, 40          # V small => many positive/negative collisions
+    t0 = torch.randn(V + 1, d0, generator=gen) * 0.3
+    t1 = torch.randn(12, d1, generator=gen) * 0.3
+    years = torch.randint(0, 12, (V + 1,), generator=gen)
+    q = torch.nn.functional.normalize(torch.randn(n, d0 + d1, generator=gen), dim=-1)
+    pos_ids = torch.randint(1, V + 1, (n,), generator=gen)
+    neg_ids = torch.randint(1, V + 1, (n, R), generator=gen)
+    w = (torch.rand(n, generator=gen) > 0.1).float()
+    assert (neg_ids == pos_ids.unsqueeze(1)).any()
+    leaves = [x.clone().double().requires_grad_(True) for x in (q, t0, t1)]
+    table = torch.cat([leaves[1][neg_ids], leaves[2][years[neg_ids]]], dim=-1)
+    sup = torch.cat([leaves[1][pos_ids], leaves[2][years[pos_ids]]], dim=-1)
+    ref, _ = O.sampled_softmax_loss(leaves[0], pos_ids, sup, w.double(), neg_ids, table, 0.05, 1e-6)
+    ref.backward()
+    gq, g0, g1 = (x.to(DEV).requires_grad_(True) for x in (q, t0, t1))
+    sup_g = torch.cat([g0[pos_ids.to(DEV)], g1[years[pos_ids].to(DEV)]], dim=-1)
+    rows = GF.sampled_softmax_rows(gq, O.l2_normalize(sup_g, 1e-6), g0, g1, neg_ids.to(DEV),
+                                   years[neg_ids].to(DEV), pos_ids.to(DEV), neg_ids.to(DEV),
+                                   True, 1e-6, 0.05)
+    loss = (rows * w.to(DEV)).sum() / w.sum()
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    loss.backward()
+    for got, r, name in ((gq, leaves[0], "dq"), (g0, leaves[1], "dt0"), (g1, leaves[2], "dt1")):
+        scale = r.grad.abs().max().item()
+        assert (got.grad.cpu().double() - r.grad).abs().max().item() <= 2e-4 * scale, name
+
+
+def test_inbatch_sampler_fused_vs_oracle(golden, monkeypatch):
+    g = golden("retrieval")
+    ib = InBatchNegativesSampler(l2_norm=True, l2_norm_eps=1e-6, dedup_embeddings=True)
+    src = g["ib_emb"].to(DEV).requires_grad_(True)
+    ids = g["ib_ids"].to(DEV)
+    ib.process_batch(ids=ids, presences=(ids != 0), embeddings=src)
+    cid, cemb = ib.get_all_ids_and_embeddings()
+    ref = {int(i): e for i, e in zip(g["ib_cached_ids"], g["ib_cached_emb"])}
+    assert sorted(ref) == sorted(cid.cpu().tolist())
+    for i, e in zip(cid.cpu(), cemb.detach().cpu()):
+        assert torch.allclose(e, ref[int(i)], atol=1e-6)
+    gen = torch.Generator().manual_seed(5)
+    n, R = 21, 16
+    offs = torch.randint(0, cid.numel(), (n, R), generator=gen).to(DEV)
+    monkeypatch.setattr(ib, "_draw", lambda positive_ids, k: offs)
+    q = torch.nn.functional.normalize(torch.randn(n, cemb.shape[1], generator=gen), dim=-1).to(DEV).requires_grad_(True)
+    sup_ids = cid[torch.randint(0, cid.numel(), (n,), generator=gen).to(DEV)]
+    sup_emb = torch.randn(n, cemb.shape[1], generator=gen).to(DEV)
+    w = torch.ones(n, device=DEV)
+    loss = SampledSoftmaxLoss(R, 0.05).jagged_forward(q, sup_ids, sup_emb, w, ib, DotProductSimilarity())
+    loss.backward()
+    # oracle on CPU with the same offsets
+    qc = q.detach().cpu().clone().requires_grad_(True)
+    srcc = g["ib_emb"].clone().requires_grad_(True)
+    c_ids, c_emb = O.inbatch_process(g["ib_ids"], g["ib_ids"] != 0, srcc, 1e-6, True)
+    remap = {int(i): j for j, i in enumerate(c_ids)}
+    o2 = torch.tensor([[remap[int(cid[o])] for o in row] for row in offs.cpu()])
+    ref_loss, _ = O.sampled_softmax_loss(qc, sup_ids.cpu(), sup_emb.cpu(), w.cpu(), c_ids[o2],
+                                         c_emb[o2], 0.05, 1e-6, neg_already_normalized=True)
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= 1e-5 * abs(ref_loss.item())
+    assert torch.allclose(q.grad.cpu(), qc.grad, rtol=1e-4, atol=1e-6)
+    # gradient reaches the batch embeddings through the cache; per-id sums must agree
+    # (which duplicate occurrence receives it is unspecified, negative_sampler.py:174-182)
+    for item in set(g["ib_ids"].tolist()) - {0}:
+        m = g["ib_ids"] == item
+        assert torch.allclose(src.grad.cpu()[m].sum(0), srcc.grad[m].sum(0), rtol=1e-3, atol=1e-6)
