@@ -1,0 +1,465 @@
+#!/usr/bin/env python
+"""bench.py — HSTU training sequences/s (+ top-k retrieval queries/s) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One JSON line on stdout (rank 0).  Headline metric = BASELINE.json's: HSTU training sequences/s
+on configs[1] (C2: ml-20m-shaped, N=211, 4 layers, D=256, 4 heads x 64, in-batch negatives
+R=128, AdamW; bf16 activations / fp32 master weights), one full train step per "step"
+(forward + backward + optimizer), data-parallel over ranks (weak scaling: 128 sequences per
+GPU).  The same line carries a ``retrieval`` object with the second half of the metric: top-k
+queries/s on C4 (10 M x 256 bf16 items sharded over the ranks, 4096 queries, k=200).
+
+``--impl reference`` times the reference's CPU path (oracle/ref_step.py — the Python reference
+itself does not exist on the GPU box) on the host cores, on a bounded sample of the same
+workload, and prints the same JSON shape with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+from mygenerativerecommenders_b200.pipeline import (  # noqa: E402
+    RetrievalConfig, synthetic_batch, synthetic_item_ids)
+
+PER_GPU_BATCH = 128
+
+
+def c2_config(bf16: bool = True) -> RetrievalConfig:
+    return RetrievalConfig(
+        name="C2 ml-20m-shaped", num_items=131_262, max_sequence_length=200, gr_output_length=10,
+        embedding_dim=256, num_blocks=4, num_heads=4, attention_dim=64, linear_dim=64,
+        dropout=0.2, sampler="inbatch", num_negatives=128, temperature=0.05, top_k=200,
+        split_year_embedding=False, compute_dtype=torch.bfloat16 if bf16 else None)
+
+
+def peaks() -> dict:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+            "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200", "-i", str(self.idx)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        return False
+
+    def summary(self) -> dict:
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                  "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_setup(n_gpus: int):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    elif n_gpus > 1:
+        raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run")
+    else:
+        torch.cuda.set_device(0)
+    return world, rank, local
+
+
+def barrier(world: int):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x: float, world: int, dev) -> float:
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+# --------------------------------------------------------------------------------------------
+# training arm (ours)
+# --------------------------------------------------------------------------------------------
+class TrainStep(torch.nn.Module):
+    def __init__(self, model):
+        super().__init__()
+        self.model = model
+
+    def forward(self, row, total_length):
+        return self.model.training_loss(row, total_length)
+
+
+def attention_pairs(lengths: torch.Tensor) -> int:
+    n = lengths.to(torch.int64)
+    return int((n * (n + 1) // 2).sum().item())
+
+
+def run_training(args, world, rank, local):
+    from mygenerativerecommenders_b200 import _lib
+    from mygenerativerecommenders_b200.pipeline import RetrievalModel
+    dev = torch.device("cuda", local)
+    cfg = c2_config(bf16=True)
+    ids = synthetic_item_ids(26_744, cfg.num_items)
+    torch.manual_seed(42)
+    model = RetrievalModel(cfg, ids).to(dev).train()
+    step_mod = TrainStep(model)
+    if world > 1:
+        step_mod = torch.nn.parallel.DistributedDataParallel(
+            step_mod, device_ids=[local], gradient_as_bucket_view=True, broadcast_buffers=False)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, betas=(0.9, 0.98), weight_decay=1e-3,
+                            fused=True)
+    n_batches = 8
+    host = [synthetic_batch(cfg, ids, PER_GPU_BATCH, seed=1000 * rank + i) for i in range(n_batches)]
+    totals = [int(b["history_lengths"].sum()) for b in host]
+    pinned = [{k: v.pin_memory() for k, v in b.items()} for b in host]
+    resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
+
+    def step(row, total):
+        loss = step_mod(row, total)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for i in range(args.warmup):
+        step(resident[i % n_batches], totals[i % n_batches])
+    barrier(world)
+
+    # ---- timed region: inputs resident in HBM -------------------------------------------------
+    launches0 = _lib.launch_count()
+    _lib.profile_start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier(world)
+        e0.record()
+        for i in range(args.steps):
+            step(resident[i % n_batches], totals[i % n_batches])
+        e1.record()
+        barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    prof = _lib.profile_stop()
+    launches = _lib.launch_count() - launches0
+
+    # ---- end to end: pinned host batch -> device each step, loss read back each step ---------
+    h2d = sum(v.numel() * v.element_size() for v in pinned[0].values())
+    barrier(world)
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    last = 0.0
+    for i in range(args.steps):
+        row = {k: v.to(dev, non_blocking=True) for k, v in pinned[i % n_batches].items()}
+        last = step(row, totals[i % n_batches]).item()     # D2H read of the loss
+    e3.record()
+    barrier(world)
+    ms_e2e = max_over_ranks(e2.elapsed_time(e3), world, dev)
+
+    seqs = PER_GPU_BATCH * world * args.steps
+    out = {
+        "value": seqs / (ms / 1e3), "ms_per_step": ms / args.steps,
+        "e2e": {"value": seqs / (ms_e2e / 1e3), "unit": "sequences/s",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches), "clocks": clk.summary(), "final_loss": last,
+    }
+    # ---- roofline of the dominant hand-written kernel, from the live per-kernel events -------
+    pk = peaks()
+    lengths_used = [host[i % n_batches]["history_lengths"] for i in range(args.steps)]
+    pairs = sum(attention_pairs(l) for l in lengths_used) * cfg.num_blocks
+    H, dqk, dv = cfg.num_heads, cfg.attention_dim, cfg.linear_dim
+    flops = {"hstu_attn_fwd": pairs * 2 * H * (dqk + dv),
+             "hstu_attn_bwd": pairs * 2 * H * (3 * dqk + 2 * dv)}
+    kern = {}
+    for name, (n, tot_ms) in prof.items():
+        kern[name] = {"calls": n, "ms_total": round(tot_ms, 3),
+                      "share_of_step": round(tot_ms / ms, 4) if ms > 0 else None}
+    out["kernels"] = kern
+    dom = max((k for k in flops if k in prof), key=lambda k: prof[k][1], default=None)
+    if dom is not None:
+        n, tot_ms = prof[dom]
+        achieved = flops[dom] / (tot_ms / 1e3) / 1e12
+        out["roofline"] = {
+            "kernel": dom, "bound": "tensor", "achieved": achieved,
+            "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+            "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None,
+            "peak_source": pk["source"] + " (sustained bf16, kernel timed inside a long step)",
+            "algorithmic_flop_per_launch": flops[dom] / max(n, 1),
+        }
+    return out, cfg, ids, model
+
+
+# --------------------------------------------------------------------------------------------
+# retrieval arm (ours): C4, corpus sharded over the ranks
+# --------------------------------------------------------------------------------------------
+def run_retrieval(args, world, rank, local, X_total=10_000_000, B=4096, D=256, k=200):
+    from mygenerativerecommenders_b200 import _lib
+    from mygenerativerecommenders_b200 import functional as GF
+    from mygenerativerecommenders_b200.candidate_index import merge_sharded_topk
+    dev = torch.device("cuda", local)
+    per = -(-X_total // world)
+    lo, hi = min(rank * per, X_total), min((rank + 1) * per, X_total)
+    g = torch.Generator(device=dev).manual_seed(rank)
+    items = torch.nn.functional.normalize(
+        torch.randn(hi - lo, D, device=dev, generator=g), dim=-1).to(torch.bfloat16)
+    item_ids = torch.arange(lo + 1, hi + 1, device=dev, dtype=torch.int64)
+    gq = torch.Generator(device=dev).manual_seed(1234)
+    n_q = 4
+    queries = [torch.nn.functional.normalize(torch.randn(B, D, device=dev, generator=gq), dim=-1)
+               .to(torch.bfloat16) for _ in range(n_q)]
+    pinned_q = [q.cpu().pin_memory() for q in queries]
+
+    def once(q):
+        s, i = GF.mips_topk(q, items, item_ids, k)
+        if world > 1:
+            s, i = merge_sharded_topk(s, i, k, world)
+        return s, i
+
+    steps = max(2, min(args.steps, 10))
+    for i in range(2):
+        once(queries[i % n_q])
+    barrier(world)
+    _lib.profile_start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        once(queries[i % n_q])
+    e1.record()
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    prof = _lib.profile_stop()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(steps):
+        q = pinned_q[i % n_q].to(dev, non_blocking=True)
+        s, ids_ = once(q)
+        ids_host = ids_.cpu()                                  # D2H of the result
+    e3.record()
+    barrier(world)
+    ms_e2e = max_over_ranks(e2.elapsed_time(e3), world, dev)
+    pk = peaks()
+    n_calls, k_ms = prof.get("mips_topk", (steps, ms))
+    flop = 2.0 * B * (hi - lo) * D
+    byts = (hi - lo) * D * 2 + B * D * 2 + B * k * 12
+    t_kernel = k_ms / max(n_calls, 1) / 1e3
+    return {
+        "metric": "topk_retrieval_queries_per_s", "unit": "queries/s",
+        "value": B * steps / (ms / 1e3), "ms_per_step": ms / steps, "steps": steps,
+        "e2e": {"value": B * steps / (ms_e2e / 1e3), "unit": "queries/s",
+                "h2d_bytes_per_step": B * D * 2, "d2h_bytes_per_step": B * k * 8},
+        "config": {"workload": f"C4 retrieval-only MIPS top-k={k}: {X_total} x {D} bf16 items "
+                               f"sharded over {world} GPU(s), {B} queries/batch, exact, "
+                               "ties->lowest id; table (5.1 GB total) >> L2",
+                   "items_per_gpu": hi - lo},
+        "roofline": {"kernel": "grb_mips_topk (score GEMM + select)", "bound": "tensor",
+                     "achieved": flop / t_kernel / 1e12, "peak": pk["bf16_tflops"],
+                     "unit": "TFLOP/s", "frac": flop / t_kernel / 1e12 / pk["bf16_tflops"],
+                     "hbm_frac": byts / t_kernel / 1e9 / pk["hbm_gbs"], "traffic": None,
+                     "peak_source": pk["source"]},
+    }
+
+
+# --------------------------------------------------------------------------------------------
+# CPU baseline (the reference's CPU path, oracle port)
+# --------------------------------------------------------------------------------------------
+def cpu_train_baseline(cfg, ids, sample_batch: int, steps: int, warmup: int, state_dict=None):
+    from oracle.ref_step import RefRetrieval
+    from mygenerativerecommenders_b200.pipeline import RetrievalModel
+    torch.set_num_threads(os.cpu_count() or 1)
+    fp32 = RetrievalConfig(**{**cfg.__dict__, "compute_dtype": None})
+    if state_dict is None:
+        torch.manual_seed(42)
+        state_dict = RetrievalModel(fp32, ids).state_dict()
+    ref = RefRetrieval.from_state_dict(fp32, ids, state_dict).train()
+    opt = torch.optim.AdamW(ref.parameters(), lr=1e-3, betas=(0.9, 0.98), weight_decay=1e-3)
+    batches = [synthetic_batch(fp32, ids, sample_batch, seed=77 + i) for i in range(2)]
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        loss = ref.training_loss(batches[i % 2])
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": sample_batch * len(times) / total, "unit": "sequences/s",
+            "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{len(times)} full train steps (fwd+bwd+AdamW) of the C2 model at "
+                      f"batch {sample_batch} (same shapes, fp32, reference formulation: padded "
+                      f"attention, python-loop jagged ops, materialised negatives); "
+                      f"{total:.1f} s of CPU work", "ms_per_step": 1e3 * total / len(times)}
+
+
+def cpu_retrieval_baseline(D=256, k=200, Bq=256, Xs=1_000_000):
+    from oracle.ref_step import torch_topk_baseline
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(0)
+    items = torch.nn.functional.normalize(torch.randn(Xs, D, generator=g), dim=-1).to(torch.bfloat16)
+    q = torch.nn.functional.normalize(torch.randn(Bq, D, generator=g), dim=-1).to(torch.bfloat16)
+    torch_topk_baseline(q[:8], items[:50_000], k)
+    t0 = time.perf_counter()
+    torch_topk_baseline(q, items, k)
+    dt = time.perf_counter() - t0
+    scale = 10_000_000 / Xs
+    return {"value": Bq / (dt * scale), "unit": "queries/s", "cores": torch.get_num_threads(),
+            "kind": "port",
+            "sample": f"{Bq} queries x {Xs} items (fp32 mm + torch.topk, top_k.py:62-69) in "
+                      f"{dt:.2f} s, scaled linearly x{scale:.0f} to the 10 M corpus"}
+
+
+def run_reference_arm(args, world, rank):
+    if rank != 0:
+        return None
+    cfg = c2_config(bf16=False)
+    ids = synthetic_item_ids(26_744, cfg.num_items)
+    sample = 32
+    steps = max(1, min(args.steps, 4))
+    warm = 1 if args.warmup > 0 else 0
+    base = cpu_train_baseline(cfg, ids, sample, steps, warm)
+    retr = cpu_retrieval_baseline()
+    return {
+        "impl": "reference", "metric": "hstu_train_sequences_per_s", "value": base["value"],
+        "unit": "sequences/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(cfg, world),
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": "sequences/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "retrieval": {"metric": "topk_retrieval_queries_per_s", "value": retr["value"],
+                      "unit": "queries/s", "cpu_baseline": retr,
+                      "e2e": {"value": retr["value"], "unit": "queries/s",
+                              "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
+    }
+
+
+def workload_config(cfg, world):
+    return {
+        "workload": "C2 ml-20m-shaped HSTU training step (BASELINE.json configs[1]): 26,744 items "
+                    "(ids <= 131,262), max_seq_len 200 (N=211), 4 HSTU layers, D=256, 4 heads x 64, "
+                    "sampled softmax with in-batch negatives R=128 T=0.05, dropout 0.2, AdamW; "
+                    "fwd+bwd+optimizer per step; lengths U[20,200]",
+        "global_batch": PER_GPU_BATCH * world, "seq_len": cfg.N,
+        "parallelism": f"dp{world}",
+        "l2": "per-step working set (134 MB fp32 embedding table + grads + AdamW state, 8 rotating "
+              "batches) exceeds the 126 MB L2; no explicit flush",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--skip-retrieval", action="store_true")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        line = run_reference_arm(args, world, rank)
+        if line is not None:
+            print(json.dumps(line), flush=True)
+        return
+
+    world, rank, local = dist_setup(args.gpus)
+    train, cfg, ids, model = run_training(args, world, rank, local)
+    state = {k: v.detach().cpu() for k, v in model.state_dict().items()} if rank == 0 else None
+    del model
+    torch.cuda.empty_cache()
+    retrieval = None if args.skip_retrieval else run_retrieval(args, world, rank, local)
+    line = {
+        "metric": "hstu_train_sequences_per_s", "value": train["value"], "unit": "sequences/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": train["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(cfg, world),
+        "clocks": train["clocks"], "e2e": train["e2e"], "gpu_launches": train["gpu_launches"],
+        "roofline": train.get("roofline"), "kernels": train["kernels"],
+        "final_loss": train["final_loss"], "retrieval": retrieval,
+    }
+    if rank == 0:
+        if world == 1 and not args.skip_cpu_baseline:
+            fp32 = RetrievalConfig(**{**cfg.__dict__, "compute_dtype": None})
+            line["cpu_baseline"] = cpu_train_baseline(fp32, ids, 32, 2, 1, state)
+            if retrieval is not None:
+                retrieval["cpu_baseline"] = cpu_retrieval_baseline()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -168,3 +168,48 @@ def ptr(t: torch.Tensor | None) -> int | None:
 
 def launch_count() -> int:
     return int(lib().grb_launch_count())
+
+
+# --------------------------------------------------------------------------------------------
+# optional per-kernel timing (bench.py): CUDA events on the launching stream around one call
+# --------------------------------------------------------------------------------------------
+_PROFILE = None  # name -> list of (start_event, end_event)
+
+
+def profile_start() -> None:
+    global _PROFILE
+    _PROFILE = {}
+
+
+def profile_stop() -> dict:
+    """Returns name -> (launch_groups, total_ms).  Synchronises the device."""
+    global _PROFILE
+    prof, _PROFILE = _PROFILE, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, evs in (prof or {}).items():
+        out[name] = (len(evs), sum(s.elapsed_time(e) for s, e in evs))
+    return out
+
+
+class timed:
+    """``with timed("name"):`` around a C-ABI call; free when profiling is off."""
+
+    __slots__ = ("name", "start")
+
+    def __init__(self, name: str):
+        self.name = name
+        self.start = None
+
+    def __enter__(self):
+        if _PROFILE is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.start is not None and _PROFILE is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            _PROFILE.setdefault(self.name, []).append((self.start, end))
+        return False

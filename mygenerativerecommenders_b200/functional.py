@@ -72,7 +72,8 @@ class _HstuAttention(torch.autograd.Function):
         out = torch.empty((q.shape[0], H * dv), dtype=q.dtype, device=q.device)
         a = _attn_args(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk, dv, max_len)
         a.out, a.ldo = out.data_ptr(), H * dv
-        _lib.check(_lib.lib().grb_hstu_attn_fwd(C.byref(a), _lib.stream_ptr(q.device)))
+        with _lib.timed("hstu_attn_fwd"):
+            _lib.check(_lib.lib().grb_hstu_attn_fwd(C.byref(a), _lib.stream_ptr(q.device)))
         ctx.save_for_backward(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds)
         ctx.dims = (N, H, dqk, dv, max_len)
         return out
@@ -97,7 +98,8 @@ class _HstuAttention(torch.autograd.Function):
             d_ts = torch.zeros_like(ts_w)
             d_pos = torch.zeros_like(pos_w)
             a.d_ts_w, a.d_pos_w = d_ts.data_ptr(), d_pos.data_ptr()
-        _lib.check(_lib.lib().grb_hstu_attn_bwd(C.byref(a), _lib.stream_ptr(q.device)))
+        with _lib.timed("hstu_attn_bwd"):
+            _lib.check(_lib.lib().grb_hstu_attn_bwd(C.byref(a), _lib.stream_ptr(q.device)))
         return dq, dk, dvv, None, None, d_ts, d_pos, None, None, None, None, None, None
 
 
@@ -187,7 +189,8 @@ class _SampledSoftmax(torch.autograd.Function):
         a = _SampledSoftmax._args(q, p, table0, table1, idx0, idx1, pos_ids, neg_ids, l2_norm, eps,
                                   temperature, probs)
         a.loss_rows = loss_rows.data_ptr()
-        _lib.check(_lib.lib().grb_sampled_softmax_fwd(C.byref(a), _lib.stream_ptr(q.device)))
+        with _lib.timed("sampled_softmax_fwd"):
+            _lib.check(_lib.lib().grb_sampled_softmax_fwd(C.byref(a), _lib.stream_ptr(q.device)))
         ctx.save_for_backward(q, p, table0, table1, idx0, idx1, pos_ids, neg_ids, probs)
         ctx.cfg = (l2_norm, eps, temperature)
         return loss_rows
@@ -229,7 +232,8 @@ class _SampledSoftmax(torch.autograd.Function):
         a.dtable0 = dt0.data_ptr()
         if dt1 is not None:
             a.dtable1 = dt1.data_ptr()
-        _lib.check(_lib.lib().grb_sampled_softmax_bwd(C.byref(a), _lib.stream_ptr(q.device)))
+        with _lib.timed("sampled_softmax_bwd"):
+            _lib.check(_lib.lib().grb_sampled_softmax_bwd(C.byref(a), _lib.stream_ptr(q.device)))
         return dq, dp, dt0, dt1, None, None, None, None, None, None, None
 
 
@@ -299,7 +303,8 @@ def mips_topk(queries: torch.Tensor, items: torch.Tensor, item_ids: Optional[tor
             _lib.check(need)
         ws = _workspace(need, dev)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
-        _lib.check(_lib.lib().grb_mips_topk(C.byref(a), _lib.stream_ptr(dev)))
+        with _lib.timed("mips_topk"):
+            _lib.check(_lib.lib().grb_mips_topk(C.byref(a), _lib.stream_ptr(dev)))
         overflow = int(status[0].item())  # the caller consumes the ids on the host anyway
         if overflow == 0:
             return out_s, out_i

@@ -1,0 +1,244 @@
+"""Lightning-free host harness around the two hot paths: what the reference's ``Retrieval``
+LightningModule does in ``training_step`` / ``retrieve`` (models/retrieval.py:21-48, :80-146,
+:162-169; models/generative_recommenders.py:355-425), minus Lightning/Hydra, with this package's
+modules wired in where the reference's ``_target_`` strings point (configs/model/hstu.yaml).
+
+The pieces either side of the hot paths — embedding tables, the positional pre-processor, the
+L2 post-processor and ``seq_features_from_row`` — are the reference's callers; they are restated
+here on plain torch ops so bench.py and the tests can drive a whole step on a box that has no
+reference tree.  They are SURVEY §8(f) "next" rows, not B200 kernels yet.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, NamedTuple, Optional, Tuple
+
+import torch
+
+from . import ops
+from .candidate_index import CandidateIndex, ShardedCandidateIndex
+from .hstu import HSTU
+from .losses import SampledSoftmaxLoss
+from .negative_sampler import InBatchNegativesSampler, LocalNegativesSampler
+from .similarity import DotProductSimilarity
+from .top_k import MIPSBruteForceTopK
+
+
+@dataclass
+class RetrievalConfig:
+    """One row of SURVEY §8's config table."""
+    name: str = "ml-1m"
+    num_items: int = 3952            # embedding rows = num_items + 1 (id 0 = padding)
+    max_sequence_length: int = 200
+    gr_output_length: int = 10
+    embedding_dim: int = 50
+    num_blocks: int = 2
+    num_heads: int = 1
+    attention_dim: int = 50
+    linear_dim: int = 50
+    dropout: float = 0.2
+    sampler: str = "local"           # "local" | "inbatch"
+    num_negatives: int = 128
+    temperature: float = 0.05
+    l2_eps: float = 1e-6
+    top_k: int = 200
+    split_year_embedding: bool = False  # this fork's item+year concat (embeddings.py:55-97)
+    compute_dtype: Optional[torch.dtype] = None
+
+    @property
+    def N(self) -> int:
+        return self.max_sequence_length + self.gr_output_length + 1
+
+
+class SequentialFeatures(NamedTuple):
+    past_lengths: torch.Tensor
+    past_ids: torch.Tensor
+    past_embeddings: Optional[torch.Tensor]
+    past_payloads: Dict[str, torch.Tensor]
+
+
+def seq_features_from_row(row: Dict[str, torch.Tensor], device, max_output_length: int):
+    """models/utils/features.py:19-85: move to device, right-pad by ``max_output_length`` zeros,
+    write the target timestamp at index ``length``."""
+    lengths = row["history_lengths"].to(device, non_blocking=True)
+    ids = row["historical_ids"].to(device, non_blocking=True)
+    ts = row["historical_timestamps"].to(device, non_blocking=True)
+    target_ids = row["target_ids"].to(device, non_blocking=True).unsqueeze(1)
+    target_ts = row["target_timestamps"].to(device, non_blocking=True).unsqueeze(1)
+    if max_output_length > 0:
+        ids = torch.nn.functional.pad(ids, (0, max_output_length))
+        ts = torch.nn.functional.pad(ts, (0, max_output_length))
+        ts.scatter_(dim=1, index=lengths.view(-1, 1), src=target_ts.view(-1, 1))
+    return SequentialFeatures(lengths, ids, None, {"timestamps": ts}), target_ids
+
+
+class ItemEmbeddings(torch.nn.Module):
+    """models/embeddings/embeddings.py:40-101.  ``split_year``: concat(item_emb[id],
+    year_emb[year_lookup[id]]), each D/2 wide, as in this fork; else one D-wide table."""
+
+    def __init__(self, num_items: int, dim: int, split_year: bool) -> None:
+        super().__init__()
+        self._item_embedding_dim = dim
+        if split_year:
+            self._item_emb = torch.nn.Embedding(num_items + 1, dim // 2, padding_idx=0)
+            self._year_emb = torch.nn.Embedding(num_items + 1, dim - dim // 2, padding_idx=0)
+            self.register_buffer("year_lookup_table", torch.zeros(num_items + 1, dtype=torch.long))
+        else:
+            self._item_emb = torch.nn.Embedding(num_items + 1, dim, padding_idx=0)
+            self._year_emb = None
+        for p in self.parameters():
+            torch.nn.init.trunc_normal_(p, mean=0.0, std=0.02, a=-0.04, b=0.04)
+
+    def lookup_year_ids(self, item_ids: torch.Tensor) -> torch.Tensor:
+        return self.year_lookup_table[item_ids.clamp(0, self.year_lookup_table.size(0) - 1)]
+
+    def get_item_embeddings(self, item_ids: torch.Tensor) -> torch.Tensor:
+        if self._year_emb is None:
+            return self._item_emb(item_ids)
+        return torch.cat([self._item_emb(item_ids),
+                          self._year_emb(self.lookup_year_ids(item_ids))], dim=-1)
+
+
+class PositionalPreprocessor(torch.nn.Module):
+    """preprocessors/learnable_positional_embedding.py:42-58: emb*sqrt(D) + pos_emb, dropout,
+    zero the padded positions."""
+
+    def __init__(self, max_sequence_len: int, dim: int, dropout: float) -> None:
+        super().__init__()
+        self._embedding_dim = dim
+        self._pos_emb = torch.nn.Embedding(max_sequence_len, dim)
+        torch.nn.init.trunc_normal_(self._pos_emb.weight, std=math.sqrt(1.0 / dim),
+                                    a=-2 * math.sqrt(1.0 / dim), b=2 * math.sqrt(1.0 / dim))
+        self._emb_dropout = torch.nn.Dropout(p=dropout)
+
+    def forward(self, past_lengths, past_ids, past_embeddings, past_payloads):
+        N = past_ids.size(1)
+        x = past_embeddings * (self._embedding_dim ** 0.5) + self._pos_emb.weight[:N].unsqueeze(0)
+        x = self._emb_dropout(x)
+        valid = (past_ids != 0).unsqueeze(-1).float()
+        return past_lengths, x * valid, valid, None
+
+
+class L2NormPostprocessor(torch.nn.Module):
+    """postprocessors/postprocessors.py:47-55."""
+
+    def __init__(self, dim: int, eps: float = 1e-6) -> None:
+        super().__init__()
+        self._embedding_dim, self._eps = dim, eps
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        x = x[..., : self._embedding_dim]
+        return x / torch.clamp(torch.linalg.norm(x, dim=-1, keepdim=True), min=self._eps)
+
+
+class RetrievalModel(torch.nn.Module):
+    """The retrieval task without Lightning: ``training_loss`` == the body of
+    Retrieval.training_step up to the loss (retrieval.py:80-133); ``retrieve`` == :21-48."""
+
+    def __init__(self, cfg: RetrievalConfig, all_item_ids: torch.Tensor, sharded_index: bool = False):
+        super().__init__()
+        self.cfg = cfg
+        D = cfg.embedding_dim
+        self.embeddings = ItemEmbeddings(cfg.num_items, D, cfg.split_year_embedding)
+        self.preprocessor = PositionalPreprocessor(cfg.N, D, cfg.dropout)
+        self.sequence_encoder = HSTU(
+            max_sequence_len=cfg.max_sequence_length, max_output_len=cfg.gr_output_length + 1,
+            embedding_dim=D, item_embedding_dim=D, num_blocks=cfg.num_blocks,
+            num_heads=cfg.num_heads, linear_dim=cfg.linear_dim, attention_dim=cfg.attention_dim,
+            normalization="rel_bias", linear_config="uvqk", linear_activation="silu",
+            linear_dropout_rate=cfg.dropout, attn_dropout_rate=0.0,
+            compute_dtype=cfg.compute_dtype)
+        self.postprocessor = L2NormPostprocessor(D, cfg.l2_eps)
+        self.similarity = DotProductSimilarity()
+        if cfg.sampler == "local":
+            self.negatives_sampler = LocalNegativesSampler(
+                l2_norm=True, l2_norm_eps=cfg.l2_eps, all_item_ids=all_item_ids.tolist())
+        else:
+            self.negatives_sampler = InBatchNegativesSampler(
+                l2_norm=True, l2_norm_eps=cfg.l2_eps, dedup_embeddings=True)
+        self.loss = SampledSoftmaxLoss(cfg.num_negatives, cfg.temperature)
+        index_cls = ShardedCandidateIndex if sharded_index else CandidateIndex
+        self.candidate_index = index_cls(k=cfg.top_k, ids=all_item_ids,
+                                         top_k_module=MIPSBruteForceTopK())
+
+    # generative_recommenders.py:355-393
+    def forward(self, sf: SequentialFeatures, total_length: Optional[int] = None) -> torch.Tensor:
+        lengths, x, valid, _ = self.preprocessor(sf.past_lengths, sf.past_ids, sf.past_embeddings,
+                                                 sf.past_payloads)
+        x, _ = self.sequence_encoder(past_lengths=lengths, user_embeddings=x, valid_mask=valid,
+                                     past_payloads=sf.past_payloads, total_length=total_length)
+        return self.postprocessor(x)
+
+    def training_loss(self, row: Dict[str, torch.Tensor], total_length: Optional[int] = None) -> torch.Tensor:
+        dev = self.embeddings._item_emb.weight.device
+        sf, target_ids = seq_features_from_row(row, dev, self.cfg.gr_output_length + 1)
+        sf.past_ids.scatter_(dim=1, index=sf.past_lengths.view(-1, 1), src=target_ids.view(-1, 1))
+        input_emb = self.embeddings.get_item_embeddings(sf.past_ids)
+        sf = sf._replace(past_embeddings=input_emb)
+        seq_emb = self.forward(sf, total_length)
+        sup_ids = sf.past_ids
+        if isinstance(self.negatives_sampler, InBatchNegativesSampler):
+            flat = sup_ids.view(-1)
+            self.negatives_sampler.process_batch(
+                ids=flat, presences=(flat != 0),
+                embeddings=self.embeddings.get_item_embeddings(flat))
+        else:
+            self.negatives_sampler._embeddings_module = self.embeddings
+        # generative_recommenders.py:407-425 (ids go through float32 there; exact below 2^24 —
+        # here they are gathered as integers, which is exact everywhere)
+        off = ops.asynchronous_complete_cumsum(sf.past_lengths)
+        tot = total_length
+        jag = dict(
+            output_embeddings=ops.dense_to_jagged(seq_emb[:, :-1, :], off, total=tot),
+            supervision_ids=ops.dense_to_jagged(sup_ids[:, 1:], off, total=tot),
+            supervision_embeddings=ops.dense_to_jagged(input_emb[:, 1:, :], off, total=tot),
+            supervision_weights=ops.dense_to_jagged((sup_ids[:, 1:] != 0).float(), off, total=tot),
+        )
+        return self.loss.jagged_forward(negatives_sampler=self.negatives_sampler,
+                                        similarity=self.similarity, **jag)
+
+    @torch.no_grad()
+    def refresh_index(self) -> None:
+        """retrieval.py:165-169: re-embed + normalise the whole corpus."""
+        emb = self.negatives_sampler.normalize_embeddings(
+            self.embeddings.get_item_embeddings(self.candidate_index.ids))
+        self.candidate_index.update_embeddings(emb)
+
+    @torch.inference_mode()
+    def retrieve(self, row: Dict[str, torch.Tensor], filter_past_ids: bool = True):
+        dev = self.embeddings._item_emb.weight.device
+        sf, _ = seq_features_from_row(row, dev, self.cfg.gr_output_length + 1)
+        sf = sf._replace(past_embeddings=self.embeddings.get_item_embeddings(sf.past_ids))
+        cur = ops.get_current_embeddings(sf.past_lengths, self.forward(sf))
+        if self.candidate_index.embeddings is None:
+            self.refresh_index()
+        return self.candidate_index.get_top_k_outputs(
+            query_embeddings=cur, invalid_ids=(sf.past_ids if filter_past_ids else None))
+
+
+def synthetic_batch(cfg: RetrievalConfig, all_item_ids: torch.Tensor, batch_size: int, seed: int,
+                    min_len: int = 20, full: bool = False) -> Dict[str, torch.Tensor]:
+    """SURVEY §8(d) generator: the dict ``seq_features_from_row`` consumes (CPU tensors)."""
+    gen = torch.Generator().manual_seed(seed)
+    L = cfg.max_sequence_length
+    lengths = torch.full((batch_size,), L) if full else \
+        torch.randint(min_len, L + 1, (batch_size,), generator=gen)
+    pick = torch.randint(0, all_item_ids.numel(), (batch_size, L), generator=gen)
+    ids = all_item_ids[pick]
+    ts = 978_300_000 + torch.cumsum(torch.randint(1, 5000, (batch_size, L), generator=gen), dim=1)
+    valid = torch.arange(L).unsqueeze(0) < lengths.unsqueeze(1)
+    last_ts = torch.gather(ts, 1, (lengths - 1).clamp(min=0).view(-1, 1)).squeeze(1)
+    tgt = all_item_ids[torch.randint(0, all_item_ids.numel(), (batch_size,), generator=gen)]
+    return {
+        "history_lengths": lengths,
+        "historical_ids": ids * valid,
+        "historical_timestamps": ts * valid,
+        "target_ids": tgt,
+        "target_timestamps": last_ts + 100,
+    }
+
+
+def synthetic_item_ids(num_distinct: int, max_id: int, seed: int = 42) -> torch.Tensor:
+    gen = torch.Generator().manual_seed(seed)
+    return (torch.randperm(max_id, generator=gen)[:num_distinct] + 1).sort().values
