@@ -1,0 +1,405 @@
+// hstu_attn_sm100.cu — HSTU jagged attention forward on Blackwell tensor cores
+// (bf16 in, fp32 accumulate, dqk = dv = 64).
+//
+// Reference math: /root/reference/src/generative_recommenders_pl/models/sequential_encoders/
+// hstu.py:96-128 (bias) + :134-205 (attention).  One CTA owns (sequence b, 128 query rows,
+// a group of HG heads) and walks the causal key tiles j = 0..iq:
+//
+//   TMA warp   : Q_h tiles once; then per unit (key tile j, head h) a 128x64 K tile and a
+//                128x64 V tile (128-byte swizzle) into a 3-stage ring, rows addressed through
+//                the jagged offsets (row coordinate = off[b] + j0).
+//   MMA warp   : S = Q_h K_h^T   tcgen05.mma  M128 N128 K64  (both operands K-major smem)
+//                O_h += P V_h    tcgen05.mma  M128 N64  K128 (A = P from TMEM, B = V MN-major)
+//                S is double buffered in TMEM; P (bf16) aliases the first 64 columns of its S.
+//   epilogue   : 2 warpgroups (thread = query row).  Per key tile the head-independent bias
+//                tile  pos_w[N-1+j-i] + ts_w[bucket(|ts[i+1]-ts[j]|)]  is computed ONCE into
+//                shared memory (fp16, pre-halved) with integer-only bucketing (clz octave table
+//                built from the reference's tabulated thresholds), then every head of the group
+//                does  h = S/2 + bias/2 ; P = h + h*tanh(h) = SiLU(S+bias)  (one MUFU per
+//                element), causal mask on the diagonal tile, bf16 pack, tcgen05.st.
+//                The 1/N scale is applied once to O.
+//
+// TMEM: S0 [0,128) S1 [128,256) O_h [256 + 64h, +64)  -> 512 columns at HG = 4.
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+#include <cuda_fp16.h>
+
+namespace grb {
+
+using namespace ptx;
+
+constexpr int AT_BM = 128;          // query rows per CTA
+constexpr int AT_BN = 128;          // key rows per tile
+constexpr int AT_D = 64;            // head dim (dqk = dv)
+constexpr int AT_STAGES = 3;
+constexpr int AT_TILE_BYTES = AT_BN * AT_D * 2;  // 16 KiB
+constexpr int AT_THREADS = 384;     // warp 0 TMA, warp 1 MMA, warps 2-3 spare, warps 4-11 epilogue
+
+struct AttnFwdParams {
+  int64_t N, T;
+  int H, nb, index_bits, n_qt;
+  const void* offsets;
+  const int64_t* ts;
+  const float* ts_w;
+  const float* pos_w;
+  const int64_t* thr;
+  __nv_bfloat16* out;
+  int64_t ldo;
+};
+
+struct alignas(16) OctRec { uint32_t base, t1, t2, t3; };
+
+template <int HG>
+struct AttnSmem {
+  // offsets into dynamic smem (1024-byte aligned base)
+  static constexpr int q = 0;                                   // HG x 16 KiB
+  static constexpr int kv = q + HG * AT_TILE_BYTES;             // STAGES x (K 16 KiB + V 16 KiB)
+  static constexpr int bias = kv + AT_STAGES * 2 * AT_TILE_BYTES;  // 128 x 128 fp16 = 32 KiB
+  static constexpr int tsk = bias + AT_BM * AT_BN * 2;          // 128 x int64
+  static constexpr int pos = tsk + 128 * 8;                     // 256 x float
+  static constexpr int tsw = pos + 256 * 4;                     // up to 4097 floats -> cap 132
+  static constexpr int oct = tsw + 136 * 4;                     // 32 x OctRec
+  static constexpr int bars = oct + 32 * 16;                    // barriers
+  static constexpr int total = bars + 256;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ int64_t ext_ts_at(const int64_t* ts, int64_t b, int64_t N, int64_t idx) {
+  if (idx >= N) idx = N - 1;
+  return ts[b * N + idx];
+}
+
+// bucket(d) = #{t : thr[t] <= d}; fast path for d < 2^32 through the octave table
+__device__ __forceinline__ int bucket_fast(const OctRec* __restrict__ oct, int b_zero,
+                                           const int64_t* __restrict__ thr_g, int nb, bool slow,
+                                           int64_t d) {
+  // 0xffffffff doubles as the "no threshold" marker of the table, so it takes the slow path too
+  if (slow || (uint64_t) d >= 0xffffffffull) return bucket_of(thr_g, nb, d);
+  const uint32_t u = (uint32_t) d;
+  if (u == 0) return b_zero;
+  const OctRec r = oct[31 - __clz(u)];
+  return (int) r.base + (u >= r.t1) + (u >= r.t2) + (u >= r.t3);
+}
+
+template <int HG, bool HAS_BIAS>
+__global__ void __launch_bounds__(AT_THREADS, 1) hstu_attn_fwd_sm100_kernel(
+    const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+    const __grid_constant__ CUtensorMap tmV, AttnFwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // the 128-byte swizzle atoms need 1024-byte aligned tiles: align by hand (1 KiB of slack)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  using L = AttnSmem<HG>;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_hg = p.H / HG;
+  const int qt = p.n_qt - 1 - (int) (blockIdx.x / n_hg);   // heavy tiles first
+  const int h0 = (int) (blockIdx.x % n_hg) * HG;
+  const int b = blockIdx.y;
+  const int64_t off0 = load_index(p.offsets, b, p.index_bits);
+  int64_t n64 = load_index(p.offsets, b + 1, p.index_bits) - off0;
+  if (n64 > p.N) n64 = p.N;
+  const int n = (int) n64;
+  const int i0 = qt * AT_BM;
+  if (i0 >= n) return;
+  const int n_kt = qt + 1;              // causal: key tiles 0..qt
+  const int U = n_kt * HG;              // units
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bars);
+  const uint32_t bar_q = smem_u32(bars + 0);
+  const uint32_t bar_o = smem_u32(bars + 1);
+  const uint32_t bar_kv_full = smem_u32(bars + 2);                 // [STAGES]
+  const uint32_t bar_kv_empty = smem_u32(bars + 2 + AT_STAGES);    // [STAGES]
+  const uint32_t bar_s_full = smem_u32(bars + 2 + 2 * AT_STAGES);  // [2]
+  const uint32_t bar_p_full = smem_u32(bars + 4 + 2 * AT_STAGES);  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * AT_STAGES);
+  int* flags = reinterpret_cast<int*>(bars + 7 + 2 * AT_STAGES);   // [0] slow, [1] b_zero
+
+  if (tid == 0) {
+    mbar_init(bar_q, 1);
+    mbar_init(bar_o, 1);
+    for (int s = 0; s < AT_STAGES; ++s) { mbar_init(bar_kv_full + 8 * s, 1); mbar_init(bar_kv_empty + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_s_full + 8 * s, 1); mbar_init(bar_p_full + 8 * s, 4); }
+    fence_barrier_init();
+    prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (HAS_BIAS && warp == 2) {
+    // octave table: for d in [2^e, 2^(e+1)): bucket = base + (d>=t1) + (d>=t2) + (d>=t3)
+    OctRec* oct = reinterpret_cast<OctRec*>(smem + L::oct);
+    const int e = lane;
+    const int64_t lo = 1ll << e, hi = (1ll << (e + 1)) - 1;
+    const int base = bucket_of(p.thr, p.nb, lo);
+    OctRec r;
+    r.base = (uint32_t) base;
+    uint32_t t[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int idx = base + i;
+      t[i] = (idx < p.nb && p.thr[idx] <= hi) ? (uint32_t) p.thr[idx] : 0xffffffffu;
+    }
+    r.t1 = t[0]; r.t2 = t[1]; r.t3 = t[2];
+    // a 4th threshold inside the octave: the table cannot express it -> binary-search path
+    bool bad = (base + 3 < p.nb && p.thr[base + 3] <= hi);
+    oct[e] = r;
+    const unsigned any_bad = __ballot_sync(0xffffffffu, bad);
+    if (lane == 0) { flags[0] = any_bad != 0; flags[1] = bucket_of(p.thr, p.nb, 0); }
+  }
+  if (HAS_BIAS && warp == 3) {
+    float* tsw = reinterpret_cast<float*>(smem + L::tsw);
+    for (int i = lane; i <= p.nb && i < 136; i += 32) tsw[i] = 0.5f * p.ts_w[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_q, HG * AT_TILE_BYTES);
+      for (int hh = 0; hh < HG; ++hh)
+        tma_load_2d(smem_u32(smem + L::q + hh * AT_TILE_BYTES), &tmQ, (h0 + hh) * AT_D,
+                    (int) (off0 + i0), bar_q);
+      for (int u = 0; u < U; ++u) {
+        const int st = u % AT_STAGES, j = u / HG, hh = u % HG;
+        mbar_wait(bar_kv_empty + 8 * st, ((u / AT_STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(bar_kv_full + 8 * st, 2 * AT_TILE_BYTES);
+        const uint32_t dst = smem_u32(smem + L::kv + st * 2 * AT_TILE_BYTES);
+        tma_load_2d(dst, &tmK, (h0 + hh) * AT_D, (int) (off0 + j * AT_BN), bar_kv_full + 8 * st);
+        tma_load_2d(dst + AT_TILE_BYTES, &tmV, (h0 + hh) * AT_D, (int) (off0 + j * AT_BN),
+                    bar_kv_full + 8 * st);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc_qk = make_idesc_bf16(128, AT_BN, false, false);
+      const uint32_t idesc_pv = make_idesc_bf16(128, AT_D, false, true);
+      mbar_wait(bar_q, 0);
+      auto issue_qk = [&](int u) {
+        const int st = u % AT_STAGES, hh = u % HG, sb = u & 1;
+        mbar_wait(bar_kv_full + 8 * st, (u / AT_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t qa = smem_u32(smem + L::q + hh * AT_TILE_BYTES);
+        const uint32_t ka = smem_u32(smem + L::kv + st * 2 * AT_TILE_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < AT_D / 16; ++ks)
+          umma_ss(tmem + sb * 128, make_smem_desc_sw128(qa + ks * 32, 0, 1024),
+                  make_smem_desc_sw128(ka + ks * 32, 0, 1024), idesc_qk, ks > 0);
+        umma_commit(bar_s_full + 8 * sb);
+      };
+      issue_qk(0);
+      if (U > 1) issue_qk(1);
+      for (int u = 0; u < U; ++u) {
+        const int st = u % AT_STAGES, j = u / HG, hh = u % HG, sb = u & 1;
+        mbar_wait(bar_p_full + 8 * sb, (u >> 1) & 1);
+        tc_fence_after();
+        const uint32_t va = smem_u32(smem + L::kv + st * 2 * AT_TILE_BYTES + AT_TILE_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < AT_BN / 16; ++ks)
+          umma_ts(tmem + 256 + hh * AT_D, tmem + sb * 128 + ks * 8,
+                  make_smem_desc_sw128(va + ks * 2048, 0, 1024), idesc_pv, (j > 0) || (ks > 0));
+        umma_commit(bar_kv_empty + 8 * st);
+        if (u + 2 < U) issue_qk(u + 2);
+      }
+      umma_commit(bar_o);
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue warpgroups =================
+    const int g = (warp - 4) >> 2;                 // warpgroup 0 / 1 -> S buffer g, units u = g (mod 2)
+    const int r = ((warp & 3) << 5) | lane;        // query row inside the tile = TMEM lane
+    const uint32_t lane_base = (uint32_t) ((warp & 3) * 32) << 16;
+    const int i = i0 + r;
+    __half* bias_s = reinterpret_cast<__half*>(smem + L::bias);
+    int64_t* tsk_s = reinterpret_cast<int64_t*>(smem + L::tsk);
+    float* pos_s = reinterpret_cast<float*>(smem + L::pos);
+    const float* tsw_s = reinterpret_cast<const float*>(smem + L::tsw);
+    const OctRec* oct = reinterpret_cast<const OctRec*>(smem + L::oct);
+    int64_t ts_q = 0;
+    bool slow = false;
+    int b_zero = 0;
+    if (HAS_BIAS) {
+      ts_q = ext_ts_at(p.ts, b, p.N, (int64_t) i + 1);
+      slow = flags[0] != 0;
+      b_zero = flags[1];
+    }
+    auto stage_tables = [&](int j) {   // key timestamps and the pos_w window of key tile j
+      const int j0 = j * AT_BN;
+      if (g == 0) {
+        tsk_s[r] = ext_ts_at(p.ts, b, p.N, (int64_t) j0 + r);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int x = r + 128 * t;               // pos_s[x] = 0.5 * pos_w[N-1 + j0 - i0 - 127 + x]
+          const int64_t idx = p.N - 1 + j0 - i0 - 127 + x;
+          pos_s[x] = (idx >= 0 && idx < 2 * p.N - 1) ? 0.5f * p.pos_w[idx] : 0.f;
+        }
+      }
+    };
+    if (HAS_BIAS) stage_tables(0);
+    for (int j = 0; j < n_kt; ++j) {
+      if (HAS_BIAS) {
+        named_bar_sync(2, 256);                    // previous tile's bias fully consumed; tables visible
+        // this warpgroup's half of the bias tile: columns [64g, 64g+64)
+#pragma unroll 2
+        for (int c8 = 0; c8 < 8; ++c8) {
+          const int cb = 64 * g + 8 * c8;
+          __half2 hv[4];
+#pragma unroll
+          for (int e2 = 0; e2 < 4; ++e2) {
+            float v[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int c = cb + 2 * e2 + e;
+              int64_t d = ts_q - tsk_s[c];
+              d = d < 0 ? -d : d;
+              const int bk = bucket_fast(oct, b_zero, p.thr, p.nb, slow, d);
+              v[e] = pos_s[c - r + 127] + tsw_s[bk];
+            }
+            hv[e2] = __floats2half2_rn(v[0], v[1]);
+          }
+          uint4 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&hv[0]);
+          pk.y = *reinterpret_cast<uint32_t*>(&hv[1]);
+          pk.z = *reinterpret_cast<uint32_t*>(&hv[2]);
+          pk.w = *reinterpret_cast<uint32_t*>(&hv[3]);
+          *reinterpret_cast<uint4*>(bias_s + ((size_t) (cb >> 3) * 128 + r) * 8) = pk;
+        }
+        named_bar_sync(1, 256);                    // bias tile complete
+        if (j + 1 < n_kt) stage_tables(j + 1);     // tables are free again after barrier 1
+      }
+      const bool diag = (j == qt);
+      for (int hh = g; hh < HG; hh += 2) {
+        const int u = j * HG + hh;                 // u & 1 == g because HG is even
+        const uint32_t s_addr = tmem + lane_base + g * 128;
+        mbar_wait(bar_s_full + 8 * g, (u >> 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c32 = 0; c32 < 4; ++c32) {
+          uint32_t sv[32];
+          tmem_ld32(s_addr + c32 * 32, sv);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8) {
+            float hb[8];
+            if (HAS_BIAS) {
+              const uint4 raw = *reinterpret_cast<const uint4*>(
+                  bias_s + ((size_t) (c32 * 4 + c8) * 128 + r) * 8);
+              const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+              for (int e2 = 0; e2 < 4; ++e2) {
+                const float2 f = __half22float2(h2[e2]);
+                hb[2 * e2] = f.x; hb[2 * e2 + 1] = f.y;
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) hb[e] = 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+              float pv[2];
+#pragma unroll
+              for (int t = 0; t < 2; ++t) {
+                const int cc = c8 * 8 + e + t;
+                const float hx = fmaf(__uint_as_float(sv[cc]), 0.5f, hb[e + t]);
+                float v = fmaf(hx, tanh_approx(hx), hx);
+                if (diag && (c32 * 32 + cc) > r) v = 0.f;
+                pv[t] = v;
+              }
+              pk[(c8 * 8 + e) >> 1] = pack_bf16x2(pv[0], pv[1]);
+            }
+          }
+          tmem_st16(s_addr + c32 * 16, pk);        // P aliases S: columns already consumed
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p_full + 8 * g);
+      }
+    }
+    // ---- O epilogue: scale by 1/N, bf16, store this thread's row ----
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    const float inv_n = 1.0f / (float) p.N;
+    for (int hh = g; hh < HG; hh += 2) {
+      uint32_t ov[32];
+      __nv_bfloat16* dst = p.out + (off0 + i) * p.ldo + (h0 + hh) * AT_D;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        tmem_ld32(tmem + lane_base + 256 + hh * AT_D + half * 32, ov);
+        tmem_ld_wait();
+        if (i < n) {
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 0]) * inv_n, __uint_as_float(ov[v4 * 8 + 1]) * inv_n);
+            o.y = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 2]) * inv_n, __uint_as_float(ov[v4 * 8 + 3]) * inv_n);
+            o.z = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 4]) * inv_n, __uint_as_float(ov[v4 * 8 + 5]) * inv_n);
+            o.w = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 6]) * inv_n, __uint_as_float(ov[v4 * 8 + 7]) * inv_n);
+            *reinterpret_cast<uint4*>(dst + half * 32 + v4 * 8) = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+bool hstu_attn_fwd_sm100_supported(const grb_hstu_attn_args* a) {
+  if (a->dtype != GRB_BF16 || a->dqk != AT_D || a->dv != AT_D) return false;
+  if (a->H % 2 != 0) return false;
+  if (a->timestamps && a->num_buckets > 128) return false;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!al16(a->q) || !al16(a->k) || !al16(a->v) || !al16(a->out)) return false;
+  if ((a->ldq * 2) % 16 || (a->ldk * 2) % 16 || (a->ldv * 2) % 16 || (a->ldo * 2) % 16) return false;
+  if (a->T >= (1ll << 31) || a->T == 0) return false;
+  return true;
+}
+
+template <int HG>
+static int launch_fwd_sm100(const grb_hstu_attn_args* a, cudaStream_t st) {
+  CUtensorMap tmQ, tmK, tmV;
+  int rc;
+  const uint64_t W = (uint64_t) a->H * AT_D;
+  if ((rc = make_tmap_bf16_2d(&tmQ, a->q, a->T, W, a->ldq, AT_BM)) != GRB_OK) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmK, a->k, a->T, W, a->ldk, AT_BN)) != GRB_OK) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmV, a->v, a->T, W, a->ldv, AT_BN)) != GRB_OK) return rc;
+  AttnFwdParams p{};
+  p.N = a->N; p.T = a->T; p.H = a->H; p.nb = a->num_buckets; p.index_bits = a->index_bits;
+  p.n_qt = (int) ceil_div(a->max_len, AT_BM);
+  p.offsets = a->offsets; p.ts = a->timestamps; p.ts_w = a->ts_w; p.pos_w = a->pos_w;
+  p.thr = a->bucket_thresholds;
+  p.out = reinterpret_cast<__nv_bfloat16*>(a->out); p.ldo = a->ldo;
+  const size_t smem = AttnSmem<HG>::total + 1024;
+  dim3 grid((unsigned) (p.n_qt * (a->H / HG)), (unsigned) a->B);
+  if (a->timestamps) {
+    auto kern = hstu_attn_fwd_sm100_kernel<HG, true>;
+    GRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    kern<<<grid, AT_THREADS, smem, st>>>(tmQ, tmK, tmV, p);
+  } else {
+    auto kern = hstu_attn_fwd_sm100_kernel<HG, false>;
+    GRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    kern<<<grid, AT_THREADS, smem, st>>>(tmQ, tmK, tmV, p);
+  }
+  GRB_LAUNCH_OK();
+  return GRB_OK;
+}
+
+int hstu_attn_fwd_sm100(const grb_hstu_attn_args* a, cudaStream_t st) {
+  if (a->B == 0 || a->max_len == 0) return GRB_OK;
+  if (a->H % 4 == 0) return launch_fwd_sm100<4>(a, st);
+  return launch_fwd_sm100<2>(a, st);
+}
+
+}  // namespace grb

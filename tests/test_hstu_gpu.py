@@ -191,3 +191,47 @@ def test_training_mode_dropout_only_touches_o_input(golden):
     y2, _ = enc(past_lengths=c["lengths"].to(DEV), user_embeddings=c["x"].to(DEV), valid_mask=None,
                 past_payloads={"timestamps": c["ts"].to(DEV)})
     assert torch.equal(y1, y2) and not torch.allclose(y1.cpu(), c["y"], atol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------
+# tcgen05 path (bf16, head dim 64)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,N,H,lengths,with_ts", [
+    (3, 211, 2, [211, 37, 129], True),              # HG = 2, two query tiles
+    (6, 400, 4, [400, 129, 128, 1, 0, 257], True),  # HG = 4, tile-edge lengths, empty sequence
+    (2, 300, 8, [300, 77], True),                   # two head groups
+    (2, 260, 4, [260, 128], False),                 # no timestamps: no bias
+    (1, 1024, 2, [1000], True),                     # eight key tiles: ring wrap-around
+])
+def test_attention_forward_bf16_tcgen05_vs_oracle(B, N, H, lengths, with_ts):
+    d = 64
+    c = _rand_case(B * 1000 + N, B, N, H, d, d, lengths, with_ts=with_ts)
+    for nme in ("q", "k", "v"):
+        c[nme] = c[nme].to(torch.bfloat16).float() * 0.5   # values exactly representable in bf16
+    # q/k/v as strided views of one wide matrix, like torch.split of the uvqk output (hstu.py:308)
+    wide = torch.cat([c["v"], c["q"], c["k"]], dim=1).to(DEV).to(torch.bfloat16)
+    W = H * d
+    vg, qg, kg = wide[:, :W], wide[:, W:2 * W], wide[:, 2 * W:]
+    ts = c["ts"].to(DEV) if with_ts else None
+    out = GF.hstu_attention(qg, kg, vg, c["off"].to(DEV), ts,
+                            c["ts_w"].to(DEV) if with_ts else None,
+                            c["pos_w"].to(DEV) if with_ts else None,
+                            _thr() if with_ts else None, N, H, d, d)
+    assert out.dtype == torch.bfloat16
+    ref = O.hstu_attention(c["q"].double(), c["k"].double(), c["v"].double(), c["off"], c["ts"],
+                           c["ts_w"].double() if with_ts else None,
+                           c["pos_w"].double() if with_ts else None, N, H, d, d)
+    _close(out, ref, 1e-2, 5e-3, what="tcgen05 attn fwd")
+
+
+def test_bf16_tcgen05_large_time_gaps_take_the_exact_slow_path():
+    # millisecond-style timestamps: gaps beyond 2^32 use the 64-bit binary search
+    B, N, H, d = 2, 200, 2, 64
+    c = _rand_case(77, B, N, H, d, d, [200, 150])
+    c["ts"] = c["ts"] * 100_000 * (c["ts"] > 0)
+    for nme in ("q", "k", "v"):
+        c[nme] = c[nme].to(torch.bfloat16).float() * 0.5
+    out, _ = _run_kernel(c, N, H, d, d, dtype=torch.bfloat16)
+    ref = O.hstu_attention(c["q"].double(), c["k"].double(), c["v"].double(), c["off"], c["ts"],
+                           c["ts_w"].double(), c["pos_w"].double(), N, H, d, d)
+    _close(out, ref, 1e-2, 5e-3, what="tcgen05 attn fwd, 64-bit gaps")
