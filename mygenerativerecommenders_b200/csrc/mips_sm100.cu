@@ -1,0 +1,240 @@
+// mips_sm100.cu — retrieval score GEMM on Blackwell tensor cores (bf16 queries x bf16 items,
+// fp32 accumulate in TMEM), fused with the sample-store / threshold-filter epilogue of
+// mips_topk.cu, so the (B, X) logits of the reference (indexing/top_k.py:62) never reach HBM.
+//
+// Persistent kernel, one CTA per SM.  Work item = (chunk of consecutive item tiles, query block
+// of 128 rows), ordered chunk-major so the CTAs that run concurrently read the SAME item tiles
+// for different query blocks: the item table streams from HBM once and is re-used out of L2.
+//
+//   TMA warp  : Q block [128 x D] (K-major, 64-column 128-byte-swizzled slabs) when the query
+//               block changes; item slabs [128 items x 64] through an 8-stage ring.
+//   MMA warp  : tcgen05.mma M128 N128 K16 x (D/16) per tile into one of 4 TMEM accumulators.
+//   epilogue  : 4 warps, thread = query row: tcgen05.ld the 128 scores of the tile and either
+//               store them (sample pass) or append (score, index) >= tau[row] (filter pass).
+#include "common.cuh"
+#include "mips_epilogue.cuh"
+#include "sm100_ptx.cuh"
+
+namespace grb {
+
+using namespace ptx;
+
+constexpr int MS_THREADS = 192;
+constexpr int MS_STAGES = 8;
+constexpr int MS_SLAB = 128 * 64 * 2;   // 16 KiB: 128 rows x 64 bf16
+constexpr int MS_ACC = 4;
+
+struct MipsSmParams {
+  int64_t B, X;
+  int D;                 // multiple of 64, <= 256
+  int64_t n_launch_tiles;
+  int64_t chunk;         // launch tiles per work item
+  int64_t n_chunks;
+  int64_t n_qb;
+  ScoreEpi epi;
+};
+
+struct MsSmem {
+  static constexpr int q = 0;                          // 4 slabs
+  static constexpr int ring = 4 * MS_SLAB;             // MS_STAGES slabs
+  static constexpr int bars = ring + MS_STAGES * MS_SLAB;
+  static constexpr int total = bars + 512;
+};
+
+__global__ void __launch_bounds__(MS_THREADS, 1) mips_scores_sm100_kernel(
+    const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmI,
+    MipsSmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MsSmem::bars);
+  const uint32_t bar_full = smem_u32(bars);                        // [STAGES]
+  const uint32_t bar_empty = smem_u32(bars + MS_STAGES);           // [STAGES]
+  const uint32_t bar_acc_full = smem_u32(bars + 2 * MS_STAGES);    // [ACC]
+  const uint32_t bar_acc_empty = smem_u32(bars + 2 * MS_STAGES + MS_ACC);  // [ACC]
+  const uint32_t bar_q_full = smem_u32(bars + 2 * MS_STAGES + 2 * MS_ACC);
+  const uint32_t bar_q_empty = bar_q_full + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MS_STAGES + 2 * MS_ACC + 2);
+
+  if (tid == 0) {
+    for (int s = 0; s < MS_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < MS_ACC; ++s) { mbar_init(bar_acc_full + 8 * s, 1); mbar_init(bar_acc_empty + 8 * s, 4); }
+    mbar_init(bar_q_full, 1);
+    mbar_init(bar_q_empty, 1);
+    fence_barrier_init();
+    prefetch_tensormap(&tmQ); prefetch_tensormap(&tmI);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int kslabs = p.D / 64;
+  const int64_t n_items = p.n_chunks * p.n_qb;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;          // slab counter (ring position)
+      int64_t cur_qb = -1;
+      uint32_t q_loads = 0;
+      for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const int64_t chunk = w / p.n_qb, qb = w % p.n_qb;
+        if (qb != cur_qb) {
+          mbar_wait(bar_q_empty, (q_loads & 1) ^ 1);   // MMAs of the previous Q are done
+          mbar_arrive_expect_tx(bar_q_full, kslabs * MS_SLAB);
+          for (int kc = 0; kc < kslabs; ++kc)
+            tma_load_2d(smem_u32(smem + MsSmem::q + kc * MS_SLAB), &tmQ, kc * 64,
+                        (int) (qb * 128), bar_q_full);
+          cur_qb = qb;
+          ++q_loads;
+        }
+        const int64_t u0 = chunk * p.chunk;
+        const int64_t u1 = (u0 + p.chunk < p.n_launch_tiles) ? u0 + p.chunk : p.n_launch_tiles;
+        for (int64_t u = u0; u < u1; ++u) {
+          const int64_t row0 = u * p.epi.tile_stride * MIPS_TILE_N;
+          for (int kc = 0; kc < kslabs; ++kc, ++it) {
+            const uint32_t st = it % MS_STAGES;
+            mbar_wait(bar_empty + 8 * st, ((it / MS_STAGES) & 1) ^ 1);
+            mbar_arrive_expect_tx(bar_full + 8 * st, MS_SLAB);
+            tma_load_2d(smem_u32(smem + MsSmem::ring + st * MS_SLAB), &tmI, kc * 64, (int) row0,
+                        bar_full + 8 * st);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, MIPS_TILE_N, false, false);
+      uint32_t it = 0, tile = 0, q_loads = 0;
+      int64_t cur_qb = -1;
+      for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const int64_t chunk = w / p.n_qb, qb = w % p.n_qb;
+        if (qb != cur_qb) {
+          if (cur_qb >= 0) umma_commit(bar_q_empty);     // all MMAs reading the old Q are issued
+          mbar_wait(bar_q_full, q_loads & 1);
+          tc_fence_after();
+          cur_qb = qb;
+          ++q_loads;
+        }
+        const int64_t u0 = chunk * p.chunk;
+        const int64_t u1 = (u0 + p.chunk < p.n_launch_tiles) ? u0 + p.chunk : p.n_launch_tiles;
+        for (int64_t u = u0; u < u1; ++u, ++tile) {
+          const uint32_t ab = tile % MS_ACC;
+          mbar_wait(bar_acc_empty + 8 * ab, ((tile / MS_ACC) & 1) ^ 1);
+          tc_fence_after();
+          for (int kc = 0; kc < kslabs; ++kc, ++it) {
+            const uint32_t st = it % MS_STAGES;
+            mbar_wait(bar_full + 8 * st, (it / MS_STAGES) & 1);
+            tc_fence_after();
+            const uint32_t qa = smem_u32(smem + MsSmem::q + kc * MS_SLAB);
+            const uint32_t ia = smem_u32(smem + MsSmem::ring + st * MS_SLAB);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_ss(tmem + ab * MIPS_TILE_N, make_smem_desc_sw128(qa + ks * 32, 0, 1024),
+                      make_smem_desc_sw128(ia + ks * 32, 0, 1024), idesc, (kc > 0) || (ks > 0));
+            umma_commit(bar_empty + 8 * st);
+          }
+          umma_commit(bar_acc_full + 8 * ab);
+        }
+      }
+    }
+  } else {
+    // epilogue: warps 2..5, TMEM lane quadrant = warp % 4
+    const int r = ((warp & 3) << 5) | lane;
+    const uint32_t lane_base = (uint32_t) ((warp & 3) * 32) << 16;
+    uint32_t tile = 0;
+    for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+      const int64_t chunk = w / p.n_qb, qb = w % p.n_qb;
+      const int64_t row = qb * 128 + r;
+      const bool row_ok = row < p.B;
+      const float tau = (p.epi.mode == MIPS_EPI_FILTER && row_ok) ? p.epi.tau[row] : INFINITY;
+      const int64_t u0 = chunk * p.chunk;
+      const int64_t u1 = (u0 + p.chunk < p.n_launch_tiles) ? u0 + p.chunk : p.n_launch_tiles;
+      for (int64_t u = u0; u < u1; ++u, ++tile) {
+        const uint32_t ab = tile % MS_ACC;
+        mbar_wait(bar_acc_full + 8 * ab, (tile / MS_ACC) & 1);
+        tc_fence_after();
+        const int64_t item0 = u * p.epi.tile_stride * MIPS_TILE_N;
+#pragma unroll 1
+        for (int c32 = 0; c32 < 4; ++c32) {
+          uint32_t sv[32];
+          tmem_ld32(tmem + lane_base + ab * MIPS_TILE_N + c32 * 32, sv);
+          tmem_ld_wait();
+          if (!row_ok) continue;
+          if (p.epi.mode == MIPS_EPI_STORE) {
+            float* o = p.epi.out + row * p.epi.Xs + u * MIPS_TILE_N + c32 * 32;
+#pragma unroll
+            for (int v4 = 0; v4 < 8; ++v4) {
+              float4 f;
+              const int64_t ib = item0 + c32 * 32 + v4 * 4;
+              f.x = (ib + 0 < p.X) ? __uint_as_float(sv[v4 * 4 + 0]) : -INFINITY;
+              f.y = (ib + 1 < p.X) ? __uint_as_float(sv[v4 * 4 + 1]) : -INFINITY;
+              f.z = (ib + 2 < p.X) ? __uint_as_float(sv[v4 * 4 + 2]) : -INFINITY;
+              f.w = (ib + 3 < p.X) ? __uint_as_float(sv[v4 * 4 + 3]) : -INFINITY;
+              *reinterpret_cast<float4*>(o + v4 * 4) = f;
+            }
+          } else {
+            // cheap reject: most 32-score groups hold nothing above tau
+            float mx = __uint_as_float(sv[0]);
+#pragma unroll
+            for (int c = 1; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(sv[c]));
+            if (mx >= tau) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) {
+                const float s = __uint_as_float(sv[c]);
+                const int64_t item = item0 + c32 * 32 + c;
+                if (s >= tau && item < p.X) append_candidate(p.epi, row, s, item);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_acc_empty + 8 * ab);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+bool mips_sm100_supported(const grb_mips_topk_args* a) {
+  if (a->dtype != GRB_BF16) return false;
+  if (a->D % 64 != 0 || a->D > 256 || a->D <= 0) return false;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!al16(a->queries) || !al16(a->items)) return false;
+  if ((a->ldq * 2) % 16 || (a->ldi * 2) % 16) return false;
+  return true;
+}
+
+int mips_scores_sm100(const grb_mips_topk_args* a, const ScoreEpi& epi, int64_t n_launch_tiles,
+                      cudaStream_t st) {
+  CUtensorMap tmQ, tmI;
+  int rc;
+  if ((rc = make_tmap_bf16_2d(&tmQ, a->queries, a->B, a->D, a->ldq, 128)) != GRB_OK) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmI, a->items, a->X, a->D, a->ldi, 128)) != GRB_OK) return rc;
+  MipsSmParams p{};
+  p.B = a->B; p.X = a->X; p.D = (int) a->D;
+  p.n_launch_tiles = n_launch_tiles;
+  p.n_qb = ceil_div(a->B, 128);
+  const int sms = num_sms();
+  // ~8 work items per CTA for balance; at most 128 tiles (8 MiB of items) per item
+  int64_t chunk = ceil_div(n_launch_tiles * p.n_qb, (int64_t) sms * 8);
+  if (chunk < 1) chunk = 1;
+  if (chunk > 128) chunk = 128;
+  p.chunk = chunk;
+  p.n_chunks = ceil_div(n_launch_tiles, chunk);
+  p.epi = epi;
+  const int64_t n_items = p.n_chunks * p.n_qb;
+  const unsigned grid = (unsigned) (n_items < sms ? n_items : sms);
+  const size_t smem = MsSmem::total + 1024;
+  GRB_CUDA_OK(cudaFuncSetAttribute(mips_scores_sm100_kernel,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  mips_scores_sm100_kernel<<<grid, MS_THREADS, smem, st>>>(tmQ, tmI, p);
+  GRB_LAUNCH_OK();
+  return GRB_OK;
+}
+
+}  // namespace grb

@@ -4,6 +4,4 @@
 namespace grb {
 bool hstu_attn_bwd_sm100_supported(const grb_hstu_attn_args*) { return false; }
 int hstu_attn_bwd_sm100(const grb_hstu_attn_args*, cudaStream_t) { return GRB_ERR_UNSUPPORTED; }
-bool mips_sm100_supported(const grb_mips_topk_args*) { return false; }
-int mips_scores_sm100(const grb_mips_topk_args*, const ScoreEpi&, int64_t, cudaStream_t) { return GRB_ERR_UNSUPPORTED; }
 }
