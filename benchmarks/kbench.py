@@ -152,6 +152,8 @@ def main():
                    torch.randint(1024, 8193, (8,), generator=torch.Generator().manual_seed(0)))
         bench_attn("C2 128x U[20,200] N211 H4", 128, 211, 4,
                    torch.randint(20, 201, (128,), generator=torch.Generator().manual_seed(0)))
+    if "attnfwd" in which:
+        bench_attn("prof 2x8192 H8 full", 2, 8192, 8, [8192] * 2, bwd=False)
     if want("jagged"):
         bench_jagged()
     if want("ssl"):

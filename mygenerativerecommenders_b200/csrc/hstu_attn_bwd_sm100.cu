@@ -1,0 +1,472 @@
+// hstu_attn_bwd_sm100.cu — HSTU jagged attention backward on Blackwell tensor cores
+// (bf16 in, fp32 accumulate in TMEM, dqk = dv = 64).
+//
+// Math (backward of hstu.py:186-204 with the bias of :96-128), per sequence / head, j <= i < n:
+//   S = Q K^T + bias ; P = SiLU(S)/N ; dP = dO V^T ; dS = dP * SiLU'(S)/N
+//   dV = P^T dO ; dK = dS^T Q ; dQ = dS K ; d pos_w[N-1+j-i] += dS ; d ts_w[bucket] += dS
+//
+// One CTA owns (sequence b, head h, key tile j) and walks the query tiles i = j .. last.  Scores
+// are produced TRANSPOSED (thread = key row) so that P^T and dS^T land in shared memory as
+// K-major A operands; the same dS^T tile read MN-major is the A operand of dQ.
+//
+//   TMA warp : K_j, V_j once; Q_i, dO_i through a 2-stage ring (128-byte swizzle, jagged rows).
+//   MMA warp : S^T  = K_j Q_i^T   M128 N128 K64   (K-major x K-major)        -> TMEM [0,128)
+//              dP^T = V_j dO_i^T  M128 N128 K64                              -> TMEM [128,256)
+//              dV  += P^T  dO_i   M128 N64  K128  (smem K-major x MN-major)  -> TMEM [256,320)
+//              dK  += dS^T Q_i    M128 N64  K128                             -> TMEM [320,384)
+//              dQ_i = dS   K_j    M128 N64  K128  (MN-major x MN-major)      -> TMEM [384,448)
+//   epilogue : 2 warpgroups, thread = key row, each warpgroup half of the 128 query columns:
+//              bias (integer bucketing), tanh-based SiLU / SiLU', masks, bf16 P^T / dS^T into
+//              swizzled shared memory, bias-gradient partial sums; then dQ_i is read back and
+//              added to the fp32 dq accumulator with vector red.global.
+#include "hstu_attn_sm100.cuh"
+
+namespace grb {
+
+using namespace ptx;
+
+constexpr int AB_THREADS = 384;
+
+struct AttnBwdParams {
+  int64_t N, T;
+  int H, nb, index_bits, n_kt;
+  const void* offsets;
+  const int64_t* ts;
+  const float* ts_w;
+  const float* pos_w;
+  const int64_t* thr;
+  __nv_bfloat16* dk; int64_t lddk;
+  __nv_bfloat16* dv; int64_t lddv;
+  float* dq_accum;          // (T, H*64) fp32, zero-filled by the caller
+  float* d_ts_w; float* d_pos_w;
+};
+
+struct AbSmem {
+  static constexpr int k = 0;
+  static constexpr int v = k + AT_TILE_BYTES;
+  static constexpr int ring = v + AT_TILE_BYTES;                 // 2 x (Q, dO)
+  static constexpr int pT = ring + 4 * AT_TILE_BYTES;            // 2 blocks [128 k][64 q]
+  static constexpr int dsT = pT + 2 * AT_TILE_BYTES;
+  static constexpr int tsq = dsT + 2 * AT_TILE_BYTES;            // 128 x int64
+  static constexpr int tsq32 = tsq + 128 * 8;                    // 128 x uint32
+  static constexpr int red = tsq32 + 128 * 4;                    // 16 x int64
+  static constexpr int pos = red + 16 * 8;                       // 256 x float (pre-halved)
+  static constexpr int tsw = pos + 256 * 4;                      // 136 x float (pre-halved)
+  static constexpr int oct = tsw + 136 * 4;                      // 32 x OctRec
+  static constexpr int h_ts = oct + 32 * 16;                     // 136 x float
+  static constexpr int h_pos = h_ts + 136 * 4;                   // 8 warps x 256 x float
+  static constexpr int bars = h_pos + 8 * 256 * 4;
+  static constexpr int total = bars + 256;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
+               "f"(d)
+               : "memory");
+}
+
+template <bool HAS_BIAS>
+__global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
+    const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+    AttnBwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  using L = AbSmem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kt = (int) blockIdx.x;                 // key tile: early tiles have the most work
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int64_t off0 = load_index(p.offsets, b, p.index_bits);
+  int64_t n64 = load_index(p.offsets, b + 1, p.index_bits) - off0;
+  if (n64 > p.N) n64 = p.N;
+  const int n = (int) n64;
+  const int j0 = kt * AT_BN;
+  if (j0 >= n) return;
+  const int n_qt = (n + AT_BM - 1) / AT_BM;
+  const int n_it = n_qt - kt;                      // query tiles kt .. n_qt-1
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bars);
+  const uint32_t bar_kv = smem_u32(bars + 0);
+  const uint32_t bar_ring_full = smem_u32(bars + 1);    // [2]
+  const uint32_t bar_ring_empty = smem_u32(bars + 3);   // [2]
+  const uint32_t bar_s_full = smem_u32(bars + 5);
+  const uint32_t bar_s_free = smem_u32(bars + 6);
+  const uint32_t bar_pds_full = smem_u32(bars + 7);
+  const uint32_t bar_pds_free = smem_u32(bars + 8);
+  const uint32_t bar_dq_full = smem_u32(bars + 9);
+  const uint32_t bar_dq_free = smem_u32(bars + 10);
+  const uint32_t bar_dkv = smem_u32(bars + 11);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  int* flags = reinterpret_cast<int*>(bars + 13);
+
+  if (tid == 0) {
+    mbar_init(bar_kv, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_ring_full + 8 * s, 1); mbar_init(bar_ring_empty + 8 * s, 1); }
+    mbar_init(bar_s_full, 1);
+    mbar_init(bar_s_free, 8);
+    mbar_init(bar_pds_full, 8);
+    mbar_init(bar_pds_free, 1);
+    mbar_init(bar_dq_full, 1);
+    mbar_init(bar_dq_free, 8);
+    mbar_init(bar_dkv, 1);
+    fence_barrier_init();
+    prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV);
+    prefetch_tensormap(&tmdO);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (HAS_BIAS && warp == 2)
+    build_octave_table(reinterpret_cast<OctRec*>(smem + L::oct), flags, p.thr, p.nb, lane);
+  if (warp == 3) {
+    float* tsw = reinterpret_cast<float*>(smem + L::tsw);
+    float* hts = reinterpret_cast<float*>(smem + L::h_ts);
+    for (int i = lane; i < 136; i += 32) {
+      tsw[i] = (HAS_BIAS && i <= p.nb) ? 0.5f * p.ts_w[i] : 0.f;
+      hts[i] = 0.f;
+    }
+    float* hp = reinterpret_cast<float*>(smem + L::h_pos);
+    for (int i = lane; i < 8 * 256; i += 32) hp[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_kv, 2 * AT_TILE_BYTES);
+      tma_load_2d(smem_u32(smem + L::k), &tmK, h * AT_D, (int) (off0 + j0), bar_kv);
+      tma_load_2d(smem_u32(smem + L::v), &tmV, h * AT_D, (int) (off0 + j0), bar_kv);
+      for (int it = 0; it < n_it; ++it) {
+        const int st = it & 1;
+        mbar_wait_parked(bar_ring_empty + 8 * st, ((it >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(bar_ring_full + 8 * st, 2 * AT_TILE_BYTES);
+        const uint32_t dst = smem_u32(smem + L::ring + st * 2 * AT_TILE_BYTES);
+        const int row = (int) (off0 + (kt + it) * AT_BM);
+        tma_load_2d(dst, &tmQ, h * AT_D, row, bar_ring_full + 8 * st);
+        tma_load_2d(dst + AT_TILE_BYTES, &tmdO, h * AT_D, row, bar_ring_full + 8 * st);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t id_kk = make_idesc_bf16(128, 128, false, false);   // S^T, dP^T
+      const uint32_t id_kmn = make_idesc_bf16(128, AT_D, false, true);  // dV, dK
+      const uint32_t id_mnmn = make_idesc_bf16(128, AT_D, true, true);  // dQ
+      const uint32_t ka = smem_u32(smem + L::k), va = smem_u32(smem + L::v);
+      const uint32_t pa = smem_u32(smem + L::pT), da = smem_u32(smem + L::dsT);
+      auto issue_scores = [&](int it) {
+        const int st = it & 1;
+        mbar_wait_parked(bar_ring_full + 8 * st, (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t qa = smem_u32(smem + L::ring + st * 2 * AT_TILE_BYTES);
+        const uint32_t oa = qa + AT_TILE_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_ss(tmem, make_smem_desc_sw128(ka + ks * 32, 0, 1024),
+                  make_smem_desc_sw128(qa + ks * 32, 0, 1024), id_kk, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_ss(tmem + 128, make_smem_desc_sw128(va + ks * 32, 0, 1024),
+                  make_smem_desc_sw128(oa + ks * 32, 0, 1024), id_kk, ks > 0);
+        umma_commit(bar_s_full);
+      };
+      mbar_wait_parked(bar_kv, 0);
+      issue_scores(0);
+      for (int it = 0; it < n_it; ++it) {
+        const int st = it & 1;
+        mbar_wait_parked(bar_s_free, it & 1);             // epilogue has read S^T / dP^T(it)
+        if (it + 1 < n_it) issue_scores(it + 1);
+        mbar_wait_parked(bar_pds_full, it & 1);           // P^T / dS^T(it) are in shared memory
+        if (it > 0) mbar_wait_parked(bar_dq_free, (it - 1) & 1);
+        tc_fence_after();
+        const uint32_t qa = smem_u32(smem + L::ring + st * 2 * AT_TILE_BYTES);
+        const uint32_t oa = qa + AT_TILE_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)   // dV += P^T dO_i : A K-major (2 blocks), B = dO MN-major
+          umma_ss(tmem + 256, make_smem_desc_sw128(pa + (ks >> 2) * AT_TILE_BYTES + (ks & 3) * 32, 0, 1024),
+                  make_smem_desc_sw128(oa + ks * 2048, 0, 1024), id_kmn, (it > 0) || (ks > 0));
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)   // dK += dS^T Q_i
+          umma_ss(tmem + 320, make_smem_desc_sw128(da + (ks >> 2) * AT_TILE_BYTES + (ks & 3) * 32, 0, 1024),
+                  make_smem_desc_sw128(qa + ks * 2048, 0, 1024), id_kmn, (it > 0) || (ks > 0));
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)   // dQ_i = dS K_j : A = dS^T read MN-major, B = K MN-major
+          umma_ss(tmem + 384, make_smem_desc_sw128(da + ks * 2048, AT_TILE_BYTES, 1024),
+                  make_smem_desc_sw128(ka + ks * 2048, 0, 1024), id_mnmn, ks > 0);
+        umma_commit(bar_pds_free);
+        umma_commit(bar_dq_full);
+        umma_commit(bar_ring_empty + 8 * st);
+      }
+      umma_commit(bar_dkv);
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue warpgroups =================
+    const int g = (warp - 4) >> 2;                 // which half of the 128 query columns
+    const int r = ((warp & 3) << 5) | lane;        // key row inside the tile = TMEM lane
+    const int w8 = warp - 4;
+    const uint32_t lane_base = (uint32_t) ((warp & 3) * 32) << 16;
+    const int jk = j0 + r;                         // key position in the sequence
+    int64_t* tsq_s = reinterpret_cast<int64_t*>(smem + L::tsq);
+    uint32_t* tsq32_s = reinterpret_cast<uint32_t*>(smem + L::tsq32);
+    float* pos_s = reinterpret_cast<float*>(smem + L::pos);
+    const float* tsw_s = reinterpret_cast<const float*>(smem + L::tsw);
+    const OctRec* oct = reinterpret_cast<const OctRec*>(smem + L::oct);
+    float* h_ts = reinterpret_cast<float*>(smem + L::h_ts);
+    float* h_pos = reinterpret_cast<float*>(smem + L::h_pos) + w8 * 256;
+    float* h_pos_all = reinterpret_cast<float*>(smem + L::h_pos);
+    uint8_t* pT = smem + L::pT + g * AT_TILE_BYTES + r * 128;
+    uint8_t* dsT = smem + L::dsT + g * AT_TILE_BYTES + r * 128;
+    const float inv_n = 1.0f / (float) p.N;
+    int64_t ts_k = 0;
+    uint32_t tk32 = 0;
+    bool slow = false, narrow = false;
+    int64_t tmin = 0;
+    if (HAS_BIAS) {
+      ts_k = ext_ts_at(p.ts, b, p.N, (int64_t) jk);
+      slow = flags[0] != 0;
+      const int cnt = (int) (n64 + 1 < p.N ? n64 + 1 : p.N);
+      const TsRange tr = scan_ts_range(p.ts + (int64_t) b * p.N, cnt, tid - 128,
+                                       reinterpret_cast<int64_t*>(smem + L::red), 3);
+      narrow = tr.narrow && !slow;
+      tmin = tr.tmin;
+      tk32 = (uint32_t) (ts_k - tmin);
+    }
+    auto read_back_dq = [&](int it) {   // dQ of iteration `it`: lane = query row, 32 columns per warpgroup
+      mbar_wait(bar_dq_full, it & 1);
+      tc_fence_after();
+      uint32_t qv[32];
+      tmem_ld32(tmem + lane_base + 384 + 32 * g, qv);
+      tmem_ld_wait();
+      const int qi = (kt + it) * AT_BM + r;
+      if (qi < n) {
+        float* dst = p.dq_accum + (off0 + qi) * (int64_t) (p.H * AT_D) + h * AT_D + 32 * g;
+#pragma unroll
+        for (int v4 = 0; v4 < 8; ++v4)
+          red_add_v4(dst + 4 * v4, __uint_as_float(qv[4 * v4]), __uint_as_float(qv[4 * v4 + 1]),
+                     __uint_as_float(qv[4 * v4 + 2]), __uint_as_float(qv[4 * v4 + 3]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_dq_free);
+    };
+
+    for (int it = 0; it < n_it; ++it) {
+      const int i0 = (kt + it) * AT_BM;
+      if (HAS_BIAS) {
+        // stage the query-side tables of this tile: ext_ts[i0 + c + 1] and the pos_w window
+        named_bar_sync(2, 256);                    // everyone finished with the previous tables
+        if (g == 0) {
+          const int64_t tq = ext_ts_at(p.ts, b, p.N, (int64_t) i0 + r + 1);
+          tsq_s[r] = tq;
+          tsq32_s[r] = (uint32_t) (tq - tmin);
+        } else {
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const int x = r + 128 * t;             // pos_s[x] = 0.5 * pos_w[N-1 + j0 - i0 - 127 + x]
+            const int64_t idx = p.N - 1 + j0 - i0 - 127 + x;
+            pos_s[x] = (idx >= 0 && idx < 2 * p.N - 1) ? 0.5f * p.pos_w[idx] : 0.f;
+          }
+        }
+        named_bar_sync(1, 256);
+      }
+      const bool edge = (it == 0) || (i0 + AT_BM > n);   // diagonal tile or ragged last tile
+      mbar_wait(bar_s_full, it & 1);
+      tc_fence_after();
+      int cur_bk = -1;
+      float acc_ts = 0.f;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        const int cb = 64 * g + 32 * half;
+        uint32_t sv[32], dv_[32];
+        tmem_ld32(tmem + lane_base + cb, sv);
+        tmem_ld32(tmem + lane_base + 128 + cb, dv_);
+        tmem_ld_wait();
+        if (half == 0 && it > 0) mbar_wait(bar_pds_free, (it - 1) & 1);   // smem tiles reusable
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          uint32_t ppk[4], dpk[4];
+          uint32_t tq32v[8];
+          if (HAS_BIAS && narrow) {
+            const uint4 ta = *reinterpret_cast<const uint4*>(tsq32_s + cb + 8 * c8);
+            const uint4 tb = *reinterpret_cast<const uint4*>(tsq32_s + cb + 8 * c8 + 4);
+            tq32v[0] = ta.x; tq32v[1] = ta.y; tq32v[2] = ta.z; tq32v[3] = ta.w;
+            tq32v[4] = tb.x; tq32v[5] = tb.y; tq32v[6] = tb.z; tq32v[7] = tb.w;
+          }
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            float pv[2], ds[2];
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              const int cc = 8 * c8 + e + t;       // column inside this 32-chunk
+              const int c = cb + cc;               // query column inside the tile
+              float hb = 0.f;
+              int bk = 0;
+              if (HAS_BIAS) {
+                if (narrow) {
+                  bk = bucket_narrow(oct, __usad(tk32, tq32v[e + t], 0u));
+                } else {
+                  int64_t d = tsq_s[c] - ts_k;
+                  d = d < 0 ? -d : d;
+                  bk = bucket_wide(oct, p.thr, p.nb, slow, d);
+                }
+                hb = pos_s[r - c + 127] + tsw_s[bk];
+              }
+              const float hx = fmaf(__uint_as_float(sv[cc]), 0.5f, hb);
+              const float th = tanh_approx(hx);
+              float pval = fmaf(hx, th, hx) * inv_n;                       // SiLU(x)/N
+              const float u1 = fmaf(-th, th, 1.0f);                        // 1 - tanh^2
+              const float w2 = fmaf(hx, u1, 1.0f + th);                    // 2 * SiLU'(x)
+              float dsv = __uint_as_float(dv_[cc]) * w2 * (0.5f * inv_n);
+              if (edge) {
+                const bool ok = (jk <= i0 + c) && (i0 + c < n);
+                if (!ok) { pval = 0.f; dsv = 0.f; }
+              }
+              if (HAS_BIAS) {
+                h_pos[r - c + 127] += dsv;          // lanes of a warp hit distinct entries
+                if (bk != cur_bk) {                  // run-length accumulate along the row
+                  if (cur_bk >= 0) atomicAdd(&h_ts[cur_bk], acc_ts);
+                  cur_bk = bk;
+                  acc_ts = 0.f;
+                }
+                acc_ts += dsv;
+              }
+              pv[t] = pval;
+              ds[t] = dsv;
+            }
+            ppk[e >> 1] = pack_bf16x2(pv[0], pv[1]);
+            dpk[e >> 1] = pack_bf16x2(ds[0], ds[1]);
+          }
+          // 16-byte chunk (half * 4 + c8) of this thread's 128-byte row, 128-byte swizzle
+          const int chunk = ((half * 4 + c8) ^ (r & 7)) * 16;
+          *reinterpret_cast<uint4*>(pT + chunk) = make_uint4(ppk[0], ppk[1], ppk[2], ppk[3]);
+          *reinterpret_cast<uint4*>(dsT + chunk) = make_uint4(dpk[0], dpk[1], dpk[2], dpk[3]);
+        }
+      }
+      if (HAS_BIAS && cur_bk >= 0) atomicAdd(&h_ts[cur_bk], acc_ts);
+      tc_fence_before();
+      fence_proxy_async_smem();                    // st.shared -> visible to the MMA (async proxy)
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(bar_s_free); mbar_arrive(bar_pds_full); }
+      if (HAS_BIAS) {
+        // merge the 8 per-warp pos histograms of this tile and flush them
+        named_bar_sync(4, 256);
+        const int x = tid - 128;
+        if (x < 255) {
+          float sum = 0.f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) { sum += h_pos_all[w * 256 + x]; h_pos_all[w * 256 + x] = 0.f; }
+          const int64_t idx = p.N - 1 + j0 - i0 - 127 + x;
+          if (sum != 0.f && idx >= 0 && idx < 2 * p.N - 1) atomicAdd(p.d_pos_w + idx, sum);
+        }
+        // the next iteration's named barrier 2 orders these clears before the next accumulation
+      }
+      if (it > 0) read_back_dq(it - 1);
+    }
+    read_back_dq(n_it - 1);
+
+    // ---- dV / dK: thread = key row; warpgroup 0 stores dV, warpgroup 1 stores dK ----
+    mbar_wait(bar_dkv, 0);
+    tc_fence_after();
+    {
+      __nv_bfloat16* dst = (g == 0 ? p.dv + (off0 + jk) * p.lddv : p.dk + (off0 + jk) * p.lddk) + h * AT_D;
+      const uint32_t col0 = 256 + 64 * g;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t ov[32];
+        tmem_ld32(tmem + lane_base + col0 + 32 * half, ov);
+        tmem_ld_wait();
+        if (jk < n) {
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 0]), __uint_as_float(ov[v4 * 8 + 1]));
+            o.y = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 2]), __uint_as_float(ov[v4 * 8 + 3]));
+            o.z = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 4]), __uint_as_float(ov[v4 * 8 + 5]));
+            o.w = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 6]), __uint_as_float(ov[v4 * 8 + 7]));
+            *reinterpret_cast<uint4*>(dst + half * 32 + v4 * 8) = o;
+          }
+        }
+      }
+    }
+    if (HAS_BIAS) {
+      named_bar_sync(4, 256);                       // all h_ts atomics done
+      const int x = tid - 128;
+      if (x <= p.nb) {
+        const float v = h_ts[x];
+        if (v != 0.f) atomicAdd(p.d_ts_w + x, v);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// dq_accum (T, H*64) fp32 -> dq (T, lddq) bf16
+__global__ void dq_to_bf16_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq,
+                                  int64_t rows, int W, int64_t lddq) {
+  const int64_t idx = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (idx >= rows * W) return;
+  const int64_t r = idx / W;
+  const int c = (int) (idx - r * W);
+  const float4 v = *reinterpret_cast<const float4*>(acc + idx);
+  uint2 o;
+  o.x = pack_bf16x2(v.x, v.y);
+  o.y = pack_bf16x2(v.z, v.w);
+  *reinterpret_cast<uint2*>(dq + r * lddq + c) = o;
+}
+
+bool hstu_attn_bwd_sm100_supported(const grb_hstu_attn_args* a) {
+  if (a->dtype != GRB_BF16 || a->dqk != AT_D || a->dv != AT_D) return false;
+  if (a->timestamps && a->num_buckets > 128) return false;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!al16(a->q) || !al16(a->k) || !al16(a->v) || !al16(a->dout) || !al16(a->dq) ||
+      !al16(a->dk) || !al16(a->dv_grad) || !al16(a->dq_accum))
+    return false;
+  if ((a->ldq * 2) % 16 || (a->ldk * 2) % 16 || (a->ldv * 2) % 16 || (a->lddo * 2) % 16 ||
+      (a->lddq * 2) % 16 || (a->lddk * 2) % 16 || (a->lddv * 2) % 16)
+    return false;
+  if (a->T >= (1ll << 31) || a->T == 0) return false;
+  return true;
+}
+
+int hstu_attn_bwd_sm100(const grb_hstu_attn_args* a, cudaStream_t st) {
+  if (a->B == 0 || a->max_len == 0) return GRB_OK;
+  CUtensorMap tmQ, tmK, tmV, tmdO;
+  int rc;
+  const uint64_t W = (uint64_t) a->H * AT_D;
+  if ((rc = make_tmap_bf16_2d(&tmQ, a->q, a->T, W, a->ldq, AT_BM)) != GRB_OK) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmK, a->k, a->T, W, a->ldk, AT_BN)) != GRB_OK) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmV, a->v, a->T, W, a->ldv, AT_BN)) != GRB_OK) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmdO, a->dout, a->T, W, a->lddo, AT_BM)) != GRB_OK) return rc;
+  AttnBwdParams p{};
+  p.N = a->N; p.T = a->T; p.H = a->H; p.nb = a->num_buckets; p.index_bits = a->index_bits;
+  p.n_kt = (int) ceil_div(a->max_len, AT_BN);
+  p.offsets = a->offsets; p.ts = a->timestamps; p.ts_w = a->ts_w; p.pos_w = a->pos_w;
+  p.thr = a->bucket_thresholds;
+  p.dk = reinterpret_cast<__nv_bfloat16*>(a->dk); p.lddk = a->lddk;
+  p.dv = reinterpret_cast<__nv_bfloat16*>(a->dv_grad); p.lddv = a->lddv;
+  p.dq_accum = a->dq_accum; p.d_ts_w = a->d_ts_w; p.d_pos_w = a->d_pos_w;
+  const size_t smem = AbSmem::total + 1024;
+  dim3 grid((unsigned) p.n_kt, (unsigned) a->H, (unsigned) a->B);
+  if (a->timestamps) {
+    auto kern = hstu_attn_bwd_sm100_kernel<true>;
+    GRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    kern<<<grid, AB_THREADS, smem, st>>>(tmQ, tmK, tmV, tmdO, p);
+  } else {
+    auto kern = hstu_attn_bwd_sm100_kernel<false>;
+    GRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    kern<<<grid, AB_THREADS, smem, st>>>(tmQ, tmK, tmV, tmdO, p);
+  }
+  GRB_LAUNCH_OK();
+  const int Wi = a->H * AT_D;
+  const int64_t total4 = a->T * Wi / 4;
+  dq_to_bf16_kernel<<<(unsigned) ceil_div(total4, 256), 256, 0, st>>>(
+      a->dq_accum, reinterpret_cast<__nv_bfloat16*>(a->dq), a->T, Wi, a->lddq);
+  GRB_LAUNCH_OK();
+  return GRB_OK;
+}
+
+}  // namespace grb

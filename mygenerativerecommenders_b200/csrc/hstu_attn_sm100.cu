@@ -20,20 +20,14 @@
 //                The 1/N scale is applied once to O.
 //
 // TMEM: S0 [0,128) S1 [128,256) O_h [256 + 64h, +64)  -> 512 columns at HG = 4.
-#include "common.cuh"
-#include "sm100_ptx.cuh"
-#include <cuda_fp16.h>
+#include "hstu_attn_sm100.cuh"
 
 namespace grb {
 
 using namespace ptx;
 
-constexpr int AT_BM = 128;          // query rows per CTA
-constexpr int AT_BN = 128;          // key rows per tile
-constexpr int AT_D = 64;            // head dim (dqk = dv)
 constexpr int AT_STAGES = 3;
-constexpr int AT_TILE_BYTES = AT_BN * AT_D * 2;  // 16 KiB
-constexpr int AT_THREADS = 384;     // warp 0 TMA, warp 1 MMA, warps 2-3 spare, warps 4-11 epilogue
+constexpr int AT_THREADS = 384;     // warp 0 TMA, warp 1 MMA, warps 2-3 setup, warps 4-11 epilogue
 
 struct AttnFwdParams {
   int64_t N, T;
@@ -47,8 +41,6 @@ struct AttnFwdParams {
   int64_t ldo;
 };
 
-struct alignas(16) OctRec { uint32_t base, t1, t2, t3; };
-
 template <int HG>
 struct AttnSmem {
   // offsets into dynamic smem (1024-byte aligned base)
@@ -56,39 +48,14 @@ struct AttnSmem {
   static constexpr int kv = q + HG * AT_TILE_BYTES;             // STAGES x (K 16 KiB + V 16 KiB)
   static constexpr int bias = kv + AT_STAGES * 2 * AT_TILE_BYTES;  // 128 x 128 fp16 = 32 KiB
   static constexpr int tsk = bias + AT_BM * AT_BN * 2;          // 128 x int64
-  static constexpr int pos = tsk + 128 * 8;                     // 256 x float
+  static constexpr int tsk32 = tsk + 128 * 8;                   // 128 x uint32 (ts - tmin)
+  static constexpr int red = tsk32 + 128 * 4;                   // 16 x int64 scratch
+  static constexpr int pos = red + 16 * 8;                      // 256 x float
   static constexpr int tsw = pos + 256 * 4;                     // up to 4097 floats -> cap 132
   static constexpr int oct = tsw + 136 * 4;                     // 32 x OctRec
   static constexpr int bars = oct + 32 * 16;                    // barriers
   static constexpr int total = bars + 256;
 };
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-__device__ __forceinline__ float tanh_approx(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-__device__ __forceinline__ int64_t ext_ts_at(const int64_t* ts, int64_t b, int64_t N, int64_t idx) {
-  if (idx >= N) idx = N - 1;
-  return ts[b * N + idx];
-}
-
-// bucket(d) = #{t : thr[t] <= d}; fast path for d < 2^32 through the octave table
-__device__ __forceinline__ int bucket_fast(const OctRec* __restrict__ oct, int b_zero,
-                                           const int64_t* __restrict__ thr_g, int nb, bool slow,
-                                           int64_t d) {
-  // 0xffffffff doubles as the "no threshold" marker of the table, so it takes the slow path too
-  if (slow || (uint64_t) d >= 0xffffffffull) return bucket_of(thr_g, nb, d);
-  const uint32_t u = (uint32_t) d;
-  if (u == 0) return b_zero;
-  const OctRec r = oct[31 - __clz(u)];
-  return (int) r.base + (u >= r.t1) + (u >= r.t2) + (u >= r.t3);
-}
 
 template <int HG, bool HAS_BIAS>
 __global__ void __launch_bounds__(AT_THREADS, 1) hstu_attn_fwd_sm100_kernel(
@@ -132,25 +99,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) hstu_attn_fwd_sm100_kernel(
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
   if (HAS_BIAS && warp == 2) {
-    // octave table: for d in [2^e, 2^(e+1)): bucket = base + (d>=t1) + (d>=t2) + (d>=t3)
-    OctRec* oct = reinterpret_cast<OctRec*>(smem + L::oct);
-    const int e = lane;
-    const int64_t lo = 1ll << e, hi = (1ll << (e + 1)) - 1;
-    const int base = bucket_of(p.thr, p.nb, lo);
-    OctRec r;
-    r.base = (uint32_t) base;
-    uint32_t t[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const int idx = base + i;
-      t[i] = (idx < p.nb && p.thr[idx] <= hi) ? (uint32_t) p.thr[idx] : 0xffffffffu;
-    }
-    r.t1 = t[0]; r.t2 = t[1]; r.t3 = t[2];
-    // a 4th threshold inside the octave: the table cannot express it -> binary-search path
-    bool bad = (base + 3 < p.nb && p.thr[base + 3] <= hi);
-    oct[e] = r;
-    const unsigned any_bad = __ballot_sync(0xffffffffu, bad);
-    if (lane == 0) { flags[0] = any_bad != 0; flags[1] = bucket_of(p.thr, p.nb, 0); }
+    build_octave_table(reinterpret_cast<OctRec*>(smem + L::oct), flags, p.thr, p.nb, lane);
   }
   if (HAS_BIAS && warp == 3) {
     float* tsw = reinterpret_cast<float*>(smem + L::tsw);
@@ -170,7 +119,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) hstu_attn_fwd_sm100_kernel(
                     (int) (off0 + i0), bar_q);
       for (int u = 0; u < U; ++u) {
         const int st = u % AT_STAGES, j = u / HG, hh = u % HG;
-        mbar_wait(bar_kv_empty + 8 * st, ((u / AT_STAGES) & 1) ^ 1);
+        mbar_wait_parked(bar_kv_empty + 8 * st, ((u / AT_STAGES) & 1) ^ 1);
         mbar_arrive_expect_tx(bar_kv_full + 8 * st, 2 * AT_TILE_BYTES);
         const uint32_t dst = smem_u32(smem + L::kv + st * 2 * AT_TILE_BYTES);
         tma_load_2d(dst, &tmK, (h0 + hh) * AT_D, (int) (off0 + j * AT_BN), bar_kv_full + 8 * st);
@@ -183,10 +132,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) hstu_attn_fwd_sm100_kernel(
     if (lane == 0) {
       const uint32_t idesc_qk = make_idesc_bf16(128, AT_BN, false, false);
       const uint32_t idesc_pv = make_idesc_bf16(128, AT_D, false, true);
-      mbar_wait(bar_q, 0);
+      mbar_wait_parked(bar_q, 0);
       auto issue_qk = [&](int u) {
         const int st = u % AT_STAGES, hh = u % HG, sb = u & 1;
-        mbar_wait(bar_kv_full + 8 * st, (u / AT_STAGES) & 1);
+        mbar_wait_parked(bar_kv_full + 8 * st, (u / AT_STAGES) & 1);
         tc_fence_after();
         const uint32_t qa = smem_u32(smem + L::q + hh * AT_TILE_BYTES);
         const uint32_t ka = smem_u32(smem + L::kv + st * 2 * AT_TILE_BYTES);
@@ -200,7 +149,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) hstu_attn_fwd_sm100_kernel(
       if (U > 1) issue_qk(1);
       for (int u = 0; u < U; ++u) {
         const int st = u % AT_STAGES, j = u / HG, hh = u % HG, sb = u & 1;
-        mbar_wait(bar_p_full + 8 * sb, (u >> 1) & 1);
+        mbar_wait_parked(bar_p_full + 8 * sb, (u >> 1) & 1);
         tc_fence_after();
         const uint32_t va = smem_u32(smem + L::kv + st * 2 * AT_TILE_BYTES + AT_TILE_BYTES);
 #pragma unroll
@@ -223,18 +172,27 @@ __global__ void __launch_bounds__(AT_THREADS, 1) hstu_attn_fwd_sm100_kernel(
     float* pos_s = reinterpret_cast<float*>(smem + L::pos);
     const float* tsw_s = reinterpret_cast<const float*>(smem + L::tsw);
     const OctRec* oct = reinterpret_cast<const OctRec*>(smem + L::oct);
+    uint32_t* tsk32_s = reinterpret_cast<uint32_t*>(smem + L::tsk32);
     int64_t ts_q = 0;
-    bool slow = false;
-    int b_zero = 0;
+    uint32_t tq32 = 0;
+    bool slow = false, narrow = false;
+    int64_t tmin = 0;
     if (HAS_BIAS) {
       ts_q = ext_ts_at(p.ts, b, p.N, (int64_t) i + 1);
       slow = flags[0] != 0;
-      b_zero = flags[1];
+      const int cnt = (int) (n64 + 1 < p.N ? n64 + 1 : p.N);     // indices 0..min(n, N-1)
+      const TsRange tr = scan_ts_range(p.ts + (int64_t) b * p.N, cnt, tid - 128,
+                                       reinterpret_cast<int64_t*>(smem + L::red), 3);
+      narrow = tr.narrow && !slow;
+      tmin = tr.tmin;
+      tq32 = (uint32_t) (ts_q - tmin);   // garbage for rows >= n: their output is never stored
     }
     auto stage_tables = [&](int j) {   // key timestamps and the pos_w window of key tile j
       const int j0 = j * AT_BN;
       if (g == 0) {
-        tsk_s[r] = ext_ts_at(p.ts, b, p.N, (int64_t) j0 + r);
+        const int64_t tk = ext_ts_at(p.ts, b, p.N, (int64_t) j0 + r);
+        tsk_s[r] = tk;
+        tsk32_s[r] = (uint32_t) (tk - tmin);
       } else {
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
@@ -245,32 +203,33 @@ __global__ void __launch_bounds__(AT_THREADS, 1) hstu_attn_fwd_sm100_kernel(
       }
     };
     if (HAS_BIAS) stage_tables(0);
+    const uint32_t half_half = 0x38003800u;        // (0.5h, 0.5h)
     for (int j = 0; j < n_kt; ++j) {
       if (HAS_BIAS) {
         named_bar_sync(2, 256);                    // previous tile's bias fully consumed; tables visible
-        // this warpgroup's half of the bias tile: columns [64g, 64g+64)
+        // this warpgroup's half of the bias tile: columns [64g, 64g+64), stored pre-halved as fp16
 #pragma unroll 2
         for (int c8 = 0; c8 < 8; ++c8) {
           const int cb = 64 * g + 8 * c8;
-          __half2 hv[4];
+          float v[8];
+          if (narrow) {
+            const uint4 ta = *reinterpret_cast<const uint4*>(tsk32_s + cb);
+            const uint4 tb = *reinterpret_cast<const uint4*>(tsk32_s + cb + 4);
+            const uint32_t tk[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
 #pragma unroll
-          for (int e2 = 0; e2 < 4; ++e2) {
-            float v[2];
+            for (int e = 0; e < 8; ++e)
+              v[e] = pos_s[cb + e - r + 127] + tsw_s[bucket_narrow(oct, __usad(tq32, tk[e], 0u))];
+          } else {
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int c = cb + 2 * e2 + e;
-              int64_t d = ts_q - tsk_s[c];
+            for (int e = 0; e < 8; ++e) {
+              int64_t d = ts_q - tsk_s[cb + e];
               d = d < 0 ? -d : d;
-              const int bk = bucket_fast(oct, b_zero, p.thr, p.nb, slow, d);
-              v[e] = pos_s[c - r + 127] + tsw_s[bk];
+              v[e] = pos_s[cb + e - r + 127] + tsw_s[bucket_wide(oct, p.thr, p.nb, slow, d)];
             }
-            hv[e2] = __floats2half2_rn(v[0], v[1]);
           }
           uint4 pk;
-          pk.x = *reinterpret_cast<uint32_t*>(&hv[0]);
-          pk.y = *reinterpret_cast<uint32_t*>(&hv[1]);
-          pk.z = *reinterpret_cast<uint32_t*>(&hv[2]);
-          pk.w = *reinterpret_cast<uint32_t*>(&hv[3]);
+          pk.x = pack_f16x2(v[0], v[1]); pk.y = pack_f16x2(v[2], v[3]);
+          pk.z = pack_f16x2(v[4], v[5]); pk.w = pack_f16x2(v[6], v[7]);
           *reinterpret_cast<uint4*>(bias_s + ((size_t) (cb >> 3) * 128 + r) * 8) = pk;
         }
         named_bar_sync(1, 256);                    // bias tile complete
@@ -290,32 +249,25 @@ __global__ void __launch_bounds__(AT_THREADS, 1) hstu_attn_fwd_sm100_kernel(
           uint32_t pk[16];
 #pragma unroll
           for (int c8 = 0; c8 < 4; ++c8) {
-            float hb[8];
-            if (HAS_BIAS) {
-              const uint4 raw = *reinterpret_cast<const uint4*>(
-                  bias_s + ((size_t) (c32 * 4 + c8) * 128 + r) * 8);
-              const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+            uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+            if (HAS_BIAS)
+              raw = *reinterpret_cast<const uint4*>(bias_s + ((size_t) (c32 * 4 + c8) * 128 + r) * 8);
+            const uint32_t hb[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-              for (int e2 = 0; e2 < 4; ++e2) {
-                const float2 f = __half22float2(h2[e2]);
-                hb[2 * e2] = f.x; hb[2 * e2 + 1] = f.y;
+            for (int e2 = 0; e2 < 4; ++e2) {
+              const int cc = c8 * 8 + 2 * e2;
+              // h = S/2 + bias/2 ; SiLU(S + bias) = h + h * tanh(h), two elements per instruction
+              const uint32_t s2 = pack_f16x2(__uint_as_float(sv[cc]), __uint_as_float(sv[cc + 1]));
+              uint32_t h2, p2;
+              asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(h2) : "r"(s2), "r"(half_half), "r"(hb[e2]));
+              const uint32_t t2 = tanh_approx_f16x2(h2);
+              asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(p2) : "r"(h2), "r"(t2));
+              float2 pf = __half22float2(*reinterpret_cast<const __half2*>(&p2));
+              if (diag) {
+                if (c32 * 32 + cc > r) pf.x = 0.f;
+                if (c32 * 32 + cc + 1 > r) pf.y = 0.f;
               }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) hb[e] = 0.f;
-            }
-#pragma unroll
-            for (int e = 0; e < 8; e += 2) {
-              float pv[2];
-#pragma unroll
-              for (int t = 0; t < 2; ++t) {
-                const int cc = c8 * 8 + e + t;
-                const float hx = fmaf(__uint_as_float(sv[cc]), 0.5f, hb[e + t]);
-                float v = fmaf(hx, tanh_approx(hx), hx);
-                if (diag && (c32 * 32 + cc) > r) v = 0.f;
-                pv[t] = v;
-              }
-              pk[(c8 * 8 + e) >> 1] = pack_bf16x2(pv[0], pv[1]);
+              pk[cc >> 1] = pack_bf16x2(pf.x, pf.y);
             }
           }
           tmem_st16(s_addr + c32 * 16, pk);        // P aliases S: columns already consumed

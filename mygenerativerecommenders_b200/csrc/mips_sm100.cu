@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mips_scores_sm100_kernel(
         const int64_t u0 = chunk * p.chunk;
         const int64_t u1 = (u0 + p.chunk < p.n_launch_tiles) ? u0 + p.chunk : p.n_launch_tiles;
         for (int64_t u = u0; u < u1; ++u) {
-          const int64_t row0 = u * p.epi.tile_stride * MIPS_TILE_N;
+          const int64_t row0 = epi_item_tile(p.epi, u) * MIPS_TILE_N;
           for (int kc = 0; kc < kslabs; ++kc, ++it) {
             const uint32_t st = it % MS_STAGES;
             mbar_wait(bar_empty + 8 * st, ((it / MS_STAGES) & 1) ^ 1);
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mips_scores_sm100_kernel(
         const uint32_t ab = tile % MS_ACC;
         mbar_wait(bar_acc_full + 8 * ab, (tile / MS_ACC) & 1);
         tc_fence_after();
-        const int64_t item0 = u * p.epi.tile_stride * MIPS_TILE_N;
+        const int64_t item0 = epi_item_tile(p.epi, u) * MIPS_TILE_N;
 #pragma unroll 1
         for (int c32 = 0; c32 < 4; ++c32) {
           uint32_t sv[32];
@@ -180,11 +180,24 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mips_scores_sm100_kernel(
 #pragma unroll
             for (int c = 1; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(sv[c]));
             if (mx >= tau) {
+              int cnt = 0;
 #pragma unroll
-              for (int c = 0; c < 32; ++c) {
-                const float s = __uint_as_float(sv[c]);
-                const int64_t item = item0 + c32 * 32 + c;
-                if (s >= tau && item < p.X) append_candidate(p.epi, row, s, item);
+              for (int c = 0; c < 32; ++c)
+                cnt += (__uint_as_float(sv[c]) >= tau && item0 + c32 * 32 + c < p.X) ? 1 : 0;
+              if (cnt) {  // one atomic per 32 scores
+                int slot = atomicAdd(p.epi.counts + row, cnt);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                  const float s = __uint_as_float(sv[c]);
+                  const int64_t item = item0 + c32 * 32 + c;
+                  if (s >= tau && item < p.X) {
+                    if (slot < p.epi.cap) {
+                      p.epi.cscores[row * p.epi.cap + slot] = s;
+                      p.epi.cidx[row * p.epi.cap + slot] = (int32_t) item;
+                    }
+                    ++slot;
+                  }
+                }
               }
             }
           }

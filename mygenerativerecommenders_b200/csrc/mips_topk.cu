@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(SG_THREADS) mips_scores_simt(
   __shared__ __align__(16) float As[SG_BK][SG_LD];
   __shared__ __align__(16) float Bs[SG_BK][SG_LD];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int64_t tile = (int64_t) blockIdx.x * epi.tile_stride;
+  const int64_t tile = epi_item_tile(epi, (int64_t) blockIdx.x);
   const int64_t n0 = tile * SG_BN;
   const int64_t m0 = (int64_t) blockIdx.y * SG_BM;
 
@@ -118,10 +118,16 @@ __device__ __forceinline__ void pick_digit_desc(int* hist, int* sh, int kk) {
 }
 
 __global__ void __launch_bounds__(SEL_THREADS) row_kth_largest_kernel(
-    const float* __restrict__ scores, int64_t ld, int64_t L, int k, float* __restrict__ tau) {
+    const float* __restrict__ scores, int64_t ld, int64_t L, const int32_t* __restrict__ counts,
+    int k, float* __restrict__ tau) {
   __shared__ int hist[256];
   __shared__ int sh[3];
   const float* x = scores + (int64_t) blockIdx.x * ld;
+  if (counts) {  // candidate lists: only the filled prefix (capped) is valid
+    const int64_t c = counts[blockIdx.x];
+    L = c < L ? c : L;
+    if (L < k) return;  // cannot happen once phase 0 has contributed k entries; keep tau
+  }
   uint32_t prefix = 0, mask = 0;
   int kk = k;
   for (int shift = 24; shift >= 0; shift -= 8) {
@@ -142,13 +148,17 @@ __global__ void __launch_bounds__(SEL_THREADS) row_kth_largest_kernel(
 }
 
 // Phase 3 when every tile was sampled (small corpora): filter the stored scores.
-__global__ void filter_dense_kernel(const float* __restrict__ scores, int64_t ld, int64_t X,
-                                    ScoreEpi epi) {
+// Sampled scores -> candidates.  Column c of the sample is item
+// (c / 128) * sample_stride * 128 + c % 128.
+__global__ void filter_dense_kernel(const float* __restrict__ scores, int64_t ld, int64_t ncols,
+                                    int64_t sample_stride, int64_t X, ScoreEpi epi) {
   const int64_t row = blockIdx.y;
   const int64_t col = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= X) return;
+  if (col >= ncols) return;
+  const int64_t item = (col / MIPS_TILE_N) * sample_stride * MIPS_TILE_N + col % MIPS_TILE_N;
+  if (item >= X) return;
   const float s = scores[row * ld + col];
-  if (s >= epi.tau[row]) append_candidate(epi, row, s, col);
+  if (s >= epi.tau[row]) append_candidate(epi, row, s, item);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -279,6 +289,7 @@ __global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(
 // ---------------------------------------------------------------------------------------------
 struct MipsPlan {
   int64_t n_tiles, stride, n_sample_tiles, Xs, cap;
+  int levels;  // stride = 4^levels; refinement phases 1..levels
   int64_t off_tau, off_counts, off_sample, off_cscores, off_cidx, total;
 };
 
@@ -293,29 +304,33 @@ static int plan_mips(const grb_mips_topk_args* a, MipsPlan* P) {
               SEL_KMAX);
   GRB_REQUIRE(a->X < (1ll << 31), GRB_ERR_UNSUPPORTED, "mips_topk: corpus too large");
   P->n_tiles = ceil_div(a->X, MIPS_TILE_N);
-  int64_t stride = a->sample_stride;
-  if (stride <= 0) {
-    // sample ~ sqrt(2 k X) items, at least 4k, at most everything
-    double want = std::sqrt(2.0 * (double) a->k * (double) a->X);
-    if (want < 4.0 * a->k) want = 4.0 * a->k;
-    int64_t want_tiles = (int64_t) std::ceil(want / MIPS_TILE_N);
-    if (want_tiles < 1) want_tiles = 1;
-    stride = P->n_tiles / want_tiles;
-    if (stride < 1) stride = 1;
+  // Phase 0 scores every (4^levels)-th tile; phase p = 1..levels scores the tiles that are
+  // multiples of 4^(levels-p) but not of 4^(levels-p+1), tightening tau[b] in between.  Each
+  // refinement phase is expected to add ~3k candidates per row (3x the items seen so far).
+  int64_t min_tiles = ceil_div(8 * (int64_t) a->k, MIPS_TILE_N);
+  if (min_tiles < 32) min_tiles = 32;
+  int levels = 0;
+  if (a->sample_stride > 0) {
+    int64_t s4 = 1;
+    while (s4 * 4 <= a->sample_stride && levels < 8) { s4 *= 4; ++levels; }
+  } else {
+    while (levels < 6 && P->n_tiles / (4ll << (2 * levels)) >= min_tiles) ++levels;
   }
-  if (stride > P->n_tiles) stride = P->n_tiles;
-  P->stride = stride;
+  int64_t stride = 1ll << (2 * levels);
   P->n_sample_tiles = ceil_div(P->n_tiles, stride);
-  P->Xs = P->n_sample_tiles * MIPS_TILE_N;
-  // the sample must hold at least k real items: the last sampled tile may be partial
-  const int64_t real_in_sample = (P->n_sample_tiles - 1) * MIPS_TILE_N +
-      ((P->n_sample_tiles - 1) * stride == P->n_tiles - 1
-           ? (a->X - (P->n_tiles - 1) * MIPS_TILE_N) : MIPS_TILE_N);
-  if (real_in_sample < a->k) {  // tiny corpora: sample everything
-    P->stride = 1; P->n_sample_tiles = P->n_tiles; P->Xs = P->n_tiles * MIPS_TILE_N;
+  // the sample must hold at least k real items (its last tile may be partial)
+  while (levels > 0) {
+    const int64_t last = (P->n_sample_tiles - 1) * stride;
+    const int64_t real = (P->n_sample_tiles - 1) * MIPS_TILE_N +
+        (last == P->n_tiles - 1 ? a->X - last * MIPS_TILE_N : MIPS_TILE_N);
+    if (real >= a->k) break;
+    --levels; stride = 1ll << (2 * levels); P->n_sample_tiles = ceil_div(P->n_tiles, stride);
   }
+  P->levels = levels;
+  P->stride = stride;
+  P->Xs = P->n_sample_tiles * MIPS_TILE_N;
   int64_t cap = a->cand_cap;
-  if (cap <= 0) cap = 3 * (int64_t) a->k * P->stride + 1024;
+  if (cap <= 0) cap = (int64_t) a->k * (4 + 6 * levels) + 1024;
   if (cap > a->X) cap = a->X;
   if (cap < a->k) cap = a->k;
   P->cap = cap;
@@ -390,24 +405,36 @@ int grb_mips_topk(const grb_mips_topk_args* a, grb_stream_t stream) {
   GRB_CUDA_OK(cudaMemsetAsync(counts, 0, a->B * 4, st));
 
   ScoreEpi epi{};
-  epi.mode = MIPS_EPI_STORE; epi.tile_stride = P.stride; epi.Xs = P.Xs; epi.out = sample;
+  epi.mode = MIPS_EPI_STORE; epi.tile_stride = P.stride; epi.grp = 1; epi.per = 1; epi.first = 0;
+  epi.Xs = P.Xs; epi.out = sample;
   epi.tau = tau; epi.counts = counts; epi.cscores = cscores; epi.cidx = cidx; epi.cap = P.cap;
   rc = launch_scores(a, epi, P.n_sample_tiles, st);
   if (rc != GRB_OK) return rc;
 
-  row_kth_largest_kernel<<<(unsigned) a->B, SEL_THREADS, 0, st>>>(sample, P.Xs, P.Xs, a->k, tau);
+  row_kth_largest_kernel<<<(unsigned) a->B, SEL_THREADS, 0, st>>>(sample, P.Xs, P.Xs, nullptr,
+                                                                  a->k, tau);
   GRB_LAUNCH_OK();
-
-  if (P.stride == 1) {
-    dim3 grid((unsigned) ceil_div(a->X, 256), (unsigned) a->B);
-    GRB_REQUIRE(a->B <= 65535, GRB_ERR_UNSUPPORTED, "mips_topk: B > 65535 on the dense path");
+  {
+    GRB_REQUIRE(a->B <= 65535, GRB_ERR_UNSUPPORTED, "mips_topk: more than 65535 queries per call");
+    dim3 grid((unsigned) ceil_div(P.Xs, 256), (unsigned) a->B);
     epi.mode = MIPS_EPI_FILTER;
-    filter_dense_kernel<<<grid, 256, 0, st>>>(sample, P.Xs, a->X, epi);
+    filter_dense_kernel<<<grid, 256, 0, st>>>(sample, P.Xs, P.Xs, P.stride, a->X, epi);
     GRB_LAUNCH_OK();
-  } else {
-    epi.mode = MIPS_EPI_FILTER; epi.tile_stride = 1;
-    rc = launch_scores(a, epi, P.n_tiles, st);
-    if (rc != GRB_OK) return rc;
+  }
+  for (int ph = 1; ph <= P.levels; ++ph) {
+    const int64_t S = P.stride >> (2 * ph);
+    const int64_t nS = ceil_div(P.n_tiles, S);
+    const int64_t n_ph = nS - ceil_div(nS, 4);
+    if (n_ph > 0) {
+      epi.mode = MIPS_EPI_FILTER; epi.tile_stride = S; epi.grp = 4; epi.per = 3; epi.first = 1;
+      rc = launch_scores(a, epi, n_ph, st);
+      if (rc != GRB_OK) return rc;
+    }
+    if (ph < P.levels) {
+      row_kth_largest_kernel<<<(unsigned) a->B, SEL_THREADS, 0, st>>>(cscores, P.cap, P.cap,
+                                                                      counts, a->k, tau);
+      GRB_LAUNCH_OK();
+    }
   }
   topk_select_kernel<int32_t><<<(unsigned) a->B, SEL_THREADS, 0, st>>>(
       cscores, cidx, counts, P.cap, a->k, a->item_ids, a->out_scores, a->out_ids, a->status);

@@ -127,6 +127,13 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_m
          ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t) (N >> 3) << 17) |
          ((uint32_t) (M >> 4) << 24);
 }
+// Same with an fp16 A operand (A fmt = 0) against a bf16 B operand: used for P (fp16) x V (bf16).
+__host__ __device__ constexpr uint32_t make_idesc_f16a_bf16b(int M, int N, bool a_mn_major,
+                                                             bool b_mn_major) {
+  return (1u << 4) | (0u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) |
+         ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t) (N >> 3) << 17) |
+         ((uint32_t) (M >> 4) << 24);
+}
 
 // ---- tcgen05: MMA -------------------------------------------------------------------------------
 // D[tmem] (+)= A[smem desc] * B[smem desc];  issued by ONE thread.
@@ -200,6 +207,11 @@ __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));

@@ -37,7 +37,7 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return GRB_OK;
 }
 
-enum { OP_K_MAJOR = 0, OP_MN_MAJOR = 1, OP_TMEM = 2 };
+enum { OP_K_MAJOR = 0, OP_MN_MAJOR = 1, OP_TMEM = 2, OP_TMEM_F16 = 3 };
 
 // D[128][N] = A[128][K] * B[N][K]^T with the operands staged as the mode says.
 __global__ void __launch_bounds__(128) umma_probe_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(128) umma_probe_kernel(const __grid_constant__
     bytes += N * K * 2;
     mbar_arrive_expect_tx(bl, bytes);
   }
-  if (a_mode == OP_TMEM) {
+  if (a_mode == OP_TMEM || a_mode == OP_TMEM_F16) {
     // thread = row; 16 bf16 (8 packed columns) per store
     const uint32_t lane_base = (uint32_t) (warp * 32) << 16;
     for (int ks = 0; ks < K / 16; ++ks) {
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(128) umma_probe_kernel(const __grid_constant__
       for (int i = 0; i < 8; ++i) {
         const float lo = __bfloat162float(a_rowmajor[tid * K + ks * 16 + 2 * i]);
         const float hi = __bfloat162float(a_rowmajor[tid * K + ks * 16 + 2 * i + 1]);
-        v[i] = pack_bf16x2(lo, hi);
+        v[i] = a_mode == OP_TMEM_F16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
       }
       tmem_st8(tmem + lane_base + a_tmem_col + ks * 8, v);
     }
@@ -106,14 +106,16 @@ __global__ void __launch_bounds__(128) umma_probe_kernel(const __grid_constant__
     tc_fence_after();
     mbar_wait(bl, 0);
     tc_fence_after();
-    const uint32_t idesc = make_idesc_bf16(128, N, a_mode == OP_MN_MAJOR, b_mode == OP_MN_MAJOR);
+    const uint32_t idesc = a_mode == OP_TMEM_F16
+        ? make_idesc_f16a_bf16b(128, N, false, b_mode == OP_MN_MAJOR)
+        : make_idesc_bf16(128, N, a_mode == OP_MN_MAJOR, b_mode == OP_MN_MAJOR);
     for (int ks = 0; ks < K / 16; ++ks) {
       uint64_t bdesc;
       if (b_mode == OP_K_MAJOR)
         bdesc = make_smem_desc_sw128(smem_u32(sB + (ks / 4) * N * 128 + (ks % 4) * 32), 0, 1024);
       else
         bdesc = make_smem_desc_sw128(smem_u32(sB + ks * 2048), K * 128, 1024);
-      if (a_mode == OP_TMEM) {
+      if (a_mode == OP_TMEM || a_mode == OP_TMEM_F16) {
         umma_ts(tmem, tmem + a_tmem_col + ks * 8, bdesc, idesc, ks > 0);
       } else {
         uint64_t adesc;
@@ -156,6 +158,7 @@ extern "C" int grb_selftest_umma(float* errs, int max_modes, grb_stream_t stream
       {OP_MN_MAJOR, OP_MN_MAJOR, 64, 128},  // 4: dV = P^T dO (both MN-major)
       {OP_K_MAJOR, OP_K_MAJOR, 256, 256},   // 5: retrieval score tile
       {OP_MN_MAJOR, OP_K_MAJOR, 128, 64},   // 6: MN-major A with K-major B
+      {OP_TMEM_F16, OP_MN_MAJOR, 64, 128},  // 7: fp16 P in TMEM x bf16 V (mixed operand formats)
   };
   const int n_modes = (int) (sizeof(modes) / sizeof(modes[0]));
   GRB_REQUIRE(errs != nullptr && max_modes > 0, GRB_ERR_INVALID_ARG, "selftest: bad arguments");

@@ -235,3 +235,32 @@ def test_bf16_tcgen05_large_time_gaps_take_the_exact_slow_path():
     ref = O.hstu_attention(c["q"].double(), c["k"].double(), c["v"].double(), c["off"], c["ts"],
                            c["ts_w"].double(), c["pos_w"].double(), N, H, d, d)
     _close(out, ref, 1e-2, 5e-3, what="tcgen05 attn fwd, 64-bit gaps")
+
+
+@pytest.mark.parametrize("B,N,H,lengths,with_ts,scale_ts", [
+    (3, 211, 2, [211, 37, 129], True, 1),
+    (6, 400, 4, [400, 129, 128, 1, 0, 257], True, 1),
+    (2, 300, 8, [300, 77], True, 1),
+    (2, 260, 4, [260, 128], False, 1),
+    (1, 700, 2, [650], True, 1),
+    (2, 200, 2, [200, 150], True, 100_000),      # gaps beyond 2^32: exact 64-bit bucketing path
+])
+def test_attention_backward_bf16_tcgen05_vs_oracle(B, N, H, lengths, with_ts, scale_ts):
+    d = 64
+    c = _rand_case(B * 1000 + N + 1, B, N, H, d, d, lengths, with_ts=with_ts)
+    if with_ts and scale_ts != 1:
+        c["ts"] = c["ts"] * scale_ts
+    for nme in ("q", "k", "v"):
+        c[nme] = c[nme].to(torch.bfloat16).float() * 0.5
+    gen = torch.Generator().manual_seed(2)
+    w = torch.randn(c["T"], H * d, generator=gen).to(torch.bfloat16).float()
+    out, leaves = _run_kernel(c, N, H, d, d, dtype=torch.bfloat16, grad=True)
+    out.backward(w.to(DEV).to(torch.bfloat16))
+    ref_leaves = [c[n].clone().double().requires_grad_(True) for n in ("q", "k", "v", "ts_w", "pos_w")]
+    ref = O.hstu_attention(ref_leaves[0], ref_leaves[1], ref_leaves[2], c["off"], c["ts"],
+                           ref_leaves[3] if with_ts else None, ref_leaves[4] if with_ts else None,
+                           N, H, d, d)
+    (ref * w.double()).sum().backward()
+    names = ("dq", "dk", "dv") + (("d_ts_w", "d_pos_w") if with_ts else ())
+    for name, got, r in zip(names, leaves, ref_leaves):
+        _close(got.grad, r.grad, 2e-2, 2e-2, what=f"tcgen05 {name}")
