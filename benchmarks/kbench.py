@@ -154,6 +154,8 @@ def main():
                    torch.randint(20, 201, (128,), generator=torch.Generator().manual_seed(0)))
     if "attnfwd" in which:
         bench_attn("prof 2x8192 H8 full", 2, 8192, 8, [8192] * 2, bwd=False)
+    if "attnbwd" in which:
+        bench_attn("prof 1x8192 H4 full", 1, 8192, 4, [8192], bwd=True)
     if want("jagged"):
         bench_jagged()
     if want("ssl"):

@@ -113,7 +113,9 @@ typedef struct grb_hstu_attn_args {
   void* dq; void* dk; void* dv_grad; int64_t lddq, lddk, lddv; /* same dtype as q/k/v */
   float* dq_accum;                /* fp32 (T, H*dqk) contiguous workspace, zero-filled by caller */
   float* d_ts_w;                  /* fp32 (num_buckets+1), accumulated (+=) */
-  float* d_pos_w;                 /* fp32 (2N-1), accumulated (+=) */
+  float* d_pos_w;                 /* fp32 (d_pos_copies, 2N-1), accumulated (+=); the caller sums the
+                                     copies (they spread same-address atomics of short sequences) */
+  int32_t d_pos_copies;           /* >= 1 (0 is read as 1) */
 } grb_hstu_attn_args;
 
 int grb_hstu_attn_fwd(const grb_hstu_attn_args* a, grb_stream_t stream);

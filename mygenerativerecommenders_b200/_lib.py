@@ -39,7 +39,7 @@ class HstuAttnArgs(C.Structure):
         ("dout", c_vp), ("lddo", c_i64),
         ("dq", c_vp), ("dk", c_vp), ("dv_grad", c_vp),
         ("lddq", c_i64), ("lddk", c_i64), ("lddv", c_i64),
-        ("dq_accum", c_vp), ("d_ts_w", c_vp), ("d_pos_w", c_vp),
+        ("dq_accum", c_vp), ("d_ts_w", c_vp), ("d_pos_w", c_vp), ("d_pos_copies", c_i32),
     ]
 
 

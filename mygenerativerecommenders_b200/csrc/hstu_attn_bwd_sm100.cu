@@ -39,6 +39,7 @@ struct AttnBwdParams {
   __nv_bfloat16* dv; int64_t lddv;
   float* dq_accum;          // (T, H*64) fp32, zero-filled by the caller
   float* d_ts_w; float* d_pos_w;
+  int d_pos_copies;
 };
 
 struct AbSmem {
@@ -47,15 +48,16 @@ struct AbSmem {
   static constexpr int ring = v + AT_TILE_BYTES;                 // 2 x (Q, dO)
   static constexpr int pT = ring + 4 * AT_TILE_BYTES;            // 2 blocks [128 k][64 q]
   static constexpr int dsT = pT + 2 * AT_TILE_BYTES;
-  static constexpr int tsq = dsT + 2 * AT_TILE_BYTES;            // 128 x int64
-  static constexpr int tsq32 = tsq + 128 * 8;                    // 128 x uint32
-  static constexpr int red = tsq32 + 128 * 4;                    // 16 x int64
-  static constexpr int pos = red + 16 * 8;                       // 256 x float (pre-halved)
-  static constexpr int tsw = pos + 256 * 4;                      // 136 x float (pre-halved)
+  // query-side tables are double buffered by tile parity: one named barrier per tile orders
+  // staging against use
+  static constexpr int tsq = dsT + 2 * AT_TILE_BYTES;            // 2 x 128 x int64
+  static constexpr int tsq32 = tsq + 2 * 128 * 8;                // 2 x 128 x uint32
+  static constexpr int red = tsq32 + 2 * 128 * 4;                // 16 x int64
+  static constexpr int pos = red + 16 * 8;                       // 2 x 256 x float (pre-halved)
+  static constexpr int tsw = pos + 2 * 256 * 4;                  // 136 x float (pre-halved)
   static constexpr int oct = tsw + 136 * 4;                      // 32 x OctRec
-  static constexpr int h_ts = oct + 32 * 16;                     // 136 x float
-  static constexpr int h_pos = h_ts + 136 * 4;                   // 8 warps x 256 x float
-  static constexpr int bars = h_pos + 8 * 256 * 4;
+  static constexpr int h_ts = oct + 32 * 16;                     // 8 warps x 136 x float
+  static constexpr int bars = h_ts + 8 * 136 * 4;
   static constexpr int total = bars + 256;
 };
 
@@ -119,13 +121,9 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
     build_octave_table(reinterpret_cast<OctRec*>(smem + L::oct), flags, p.thr, p.nb, lane);
   if (warp == 3) {
     float* tsw = reinterpret_cast<float*>(smem + L::tsw);
-    float* hts = reinterpret_cast<float*>(smem + L::h_ts);
-    for (int i = lane; i < 136; i += 32) {
-      tsw[i] = (HAS_BIAS && i <= p.nb) ? 0.5f * p.ts_w[i] : 0.f;
-      hts[i] = 0.f;
-    }
-    float* hp = reinterpret_cast<float*>(smem + L::h_pos);
-    for (int i = lane; i < 8 * 256; i += 32) hp[i] = 0.f;
+    for (int i = lane; i < 136; i += 32) tsw[i] = (HAS_BIAS && i <= p.nb) ? 0.5f * p.ts_w[i] : 0.f;
+    float* hp = reinterpret_cast<float*>(smem + L::h_ts);
+    for (int i = lane; i < 8 * 136; i += 32) hp[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -208,17 +206,18 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
     const int w8 = warp - 4;
     const uint32_t lane_base = (uint32_t) ((warp & 3) * 32) << 16;
     const int jk = j0 + r;                         // key position in the sequence
-    int64_t* tsq_s = reinterpret_cast<int64_t*>(smem + L::tsq);
-    uint32_t* tsq32_s = reinterpret_cast<uint32_t*>(smem + L::tsq32);
-    float* pos_s = reinterpret_cast<float*>(smem + L::pos);
+    int64_t* tsq_all = reinterpret_cast<int64_t*>(smem + L::tsq);
+    uint32_t* tsq32_all = reinterpret_cast<uint32_t*>(smem + L::tsq32);
+    float* pos_all = reinterpret_cast<float*>(smem + L::pos);
     const float* tsw_s = reinterpret_cast<const float*>(smem + L::tsw);
     const OctRec* oct = reinterpret_cast<const OctRec*>(smem + L::oct);
-    float* h_ts = reinterpret_cast<float*>(smem + L::h_ts);
-    float* h_pos = reinterpret_cast<float*>(smem + L::h_pos) + w8 * 256;
-    float* h_pos_all = reinterpret_cast<float*>(smem + L::h_pos);
+    float* h_ts = reinterpret_cast<float*>(smem + L::h_ts) + w8 * 136;   // this warp's d ts_w
     uint8_t* pT = smem + L::pT + g * AT_TILE_BYTES + r * 128;
     uint8_t* dsT = smem + L::dsT + g * AT_TILE_BYTES + r * 128;
     const float inv_n = 1.0f / (float) p.N;
+    // this CTA's private copy of d pos_w (the caller sums the copies)
+    float* d_pos_mine = p.d_pos_w + (int64_t) ((blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) %
+                                               (unsigned) p.d_pos_copies) * (2 * p.N - 1);
     int64_t ts_k = 0;
     uint32_t tk32 = 0;
     bool slow = false, narrow = false;
@@ -251,31 +250,53 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_dq_free);
     };
+    // query-side tables of tile `it` (ext_ts[i0 + c + 1] and the pos_w window) into buffer it & 1
+    auto stage_tables = [&](int it) {
+      const int i0 = (kt + it) * AT_BM;
+      const int pb = it & 1;
+      if (g == 0) {
+        const int64_t tq = ext_ts_at(p.ts, b, p.N, (int64_t) i0 + r + 1);
+        tsq_all[pb * 128 + r] = tq;
+        tsq32_all[pb * 128 + r] = (uint32_t) (tq - tmin);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int x = r + 128 * t;               // pos[x] = 0.5 * pos_w[N-1 + j0 - i0 - 127 + x]
+          const int64_t idx = p.N - 1 + j0 - i0 - 127 + x;
+          pos_all[pb * 256 + x] = (idx >= 0 && idx < 2 * p.N - 1) ? 0.5f * p.pos_w[idx] : 0.f;
+        }
+      }
+    };
+    // d ts_w, warp collective (all 32 lanes call it): sum `val` per distinct bucket of the warp
+    // and let ONE lane do the read-modify-write on the warp-private histogram — shared memory has
+    // no native fp32 atomic add (atomicAdd compiles to a CAS spin loop).
+    auto warp_flush = [&](int bk, float val) {
+      unsigned todo = 0xffffffffu;
+      while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int lbk = __shfl_sync(0xffffffffu, bk, leader);
+        const bool mine = (bk == lbk);
+        const float sum = warp_sum(mine ? val : 0.f);
+        if (lane == 0 && lbk >= 0) h_ts[lbk] += sum;
+        todo &= ~__ballot_sync(0xffffffffu, mine);
+      }
+      __syncwarp();
+    };
 
+    if (HAS_BIAS) {
+      stage_tables(0);
+      named_bar_sync(2, 256);
+    }
     for (int it = 0; it < n_it; ++it) {
       const int i0 = (kt + it) * AT_BM;
-      if (HAS_BIAS) {
-        // stage the query-side tables of this tile: ext_ts[i0 + c + 1] and the pos_w window
-        named_bar_sync(2, 256);                    // everyone finished with the previous tables
-        if (g == 0) {
-          const int64_t tq = ext_ts_at(p.ts, b, p.N, (int64_t) i0 + r + 1);
-          tsq_s[r] = tq;
-          tsq32_s[r] = (uint32_t) (tq - tmin);
-        } else {
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const int x = r + 128 * t;             // pos_s[x] = 0.5 * pos_w[N-1 + j0 - i0 - 127 + x]
-            const int64_t idx = p.N - 1 + j0 - i0 - 127 + x;
-            pos_s[x] = (idx >= 0 && idx < 2 * p.N - 1) ? 0.5f * p.pos_w[idx] : 0.f;
-          }
-        }
-        named_bar_sync(1, 256);
-      }
+      const int pb = it & 1;
+      if (HAS_BIAS && it + 1 < n_it) stage_tables(it + 1);   // ordered by this tile's barrier 4
+      const int64_t* tsq_s = tsq_all + pb * 128;
+      const uint32_t* tsq32_s = tsq32_all + pb * 128;
+      const float* pos_s = pos_all + pb * 256;
       const bool edge = (it == 0) || (i0 + AT_BM > n);   // diagonal tile or ragged last tile
       mbar_wait(bar_s_full, it & 1);
       tc_fence_after();
-      int cur_bk = -1;
-      float acc_ts = 0.f;
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         const int cb = 64 * g + 32 * half;
@@ -284,83 +305,102 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
         tmem_ld32(tmem + lane_base + 128 + cb, dv_);
         tmem_ld_wait();
         if (half == 0 && it > 0) mbar_wait(bar_pds_free, (it - 1) & 1);   // smem tiles reusable
+        int run_bk = -1;          // d ts_w: run-length accumulate along the row
+        float run_acc = 0.f;
 #pragma unroll
         for (int c8 = 0; c8 < 4; ++c8) {
           uint32_t ppk[4], dpk[4];
-          uint32_t tq32v[8];
-          if (HAS_BIAS && narrow) {
-            const uint4 ta = *reinterpret_cast<const uint4*>(tsq32_s + cb + 8 * c8);
-            const uint4 tb = *reinterpret_cast<const uint4*>(tsq32_s + cb + 8 * c8 + 4);
-            tq32v[0] = ta.x; tq32v[1] = ta.y; tq32v[2] = ta.z; tq32v[3] = ta.w;
-            tq32v[4] = tb.x; tq32v[5] = tb.y; tq32v[6] = tb.z; tq32v[7] = tb.w;
-          }
+          int bk[8];
+          float hb[8];
+          if (HAS_BIAS) {
+            if (narrow) {
+              const uint4 ta = *reinterpret_cast<const uint4*>(tsq32_s + cb + 8 * c8);
+              const uint4 tb = *reinterpret_cast<const uint4*>(tsq32_s + cb + 8 * c8 + 4);
+              const uint32_t tq[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
 #pragma unroll
-          for (int e = 0; e < 8; e += 2) {
-            float pv[2], ds[2];
+              for (int e = 0; e < 8; ++e) bk[e] = bucket_narrow(oct, __usad(tk32, tq[e], 0u));
+            } else {
 #pragma unroll
-            for (int t = 0; t < 2; ++t) {
-              const int cc = 8 * c8 + e + t;       // column inside this 32-chunk
-              const int c = cb + cc;               // query column inside the tile
-              float hb = 0.f;
-              int bk = 0;
-              if (HAS_BIAS) {
-                if (narrow) {
-                  bk = bucket_narrow(oct, __usad(tk32, tq32v[e + t], 0u));
-                } else {
-                  int64_t d = tsq_s[c] - ts_k;
-                  d = d < 0 ? -d : d;
-                  bk = bucket_wide(oct, p.thr, p.nb, slow, d);
-                }
-                hb = pos_s[r - c + 127] + tsw_s[bk];
+              for (int e = 0; e < 8; ++e) {
+                int64_t d = tsq_s[cb + 8 * c8 + e] - ts_k;
+                d = d < 0 ? -d : d;
+                bk[e] = bucket_wide(oct, p.thr, p.nb, slow, d);
               }
-              const float hx = fmaf(__uint_as_float(sv[cc]), 0.5f, hb);
-              const float th = tanh_approx(hx);
-              float pval = fmaf(hx, th, hx) * inv_n;                       // SiLU(x)/N
-              const float u1 = fmaf(-th, th, 1.0f);                        // 1 - tanh^2
-              const float w2 = fmaf(hx, u1, 1.0f + th);                    // 2 * SiLU'(x)
-              float dsv = __uint_as_float(dv_[cc]) * w2 * (0.5f * inv_n);
-              if (edge) {
-                const bool ok = (jk <= i0 + c) && (i0 + c < n);
-                if (!ok) { pval = 0.f; dsv = 0.f; }
-              }
-              if (HAS_BIAS) {
-                h_pos[r - c + 127] += dsv;          // lanes of a warp hit distinct entries
-                if (bk != cur_bk) {                  // run-length accumulate along the row
-                  if (cur_bk >= 0) atomicAdd(&h_ts[cur_bk], acc_ts);
-                  cur_bk = bk;
-                  acc_ts = 0.f;
-                }
-                acc_ts += dsv;
-              }
-              pv[t] = pval;
-              ds[t] = dsv;
             }
-            ppk[e >> 1] = pack_bf16x2(pv[0], pv[1]);
-            dpk[e >> 1] = pack_bf16x2(ds[0], ds[1]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) hb[e] = pos_s[r - (cb + 8 * c8 + e) + 127] + tsw_s[bk[e]];
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { bk[e] = 0; hb[e] = 0.f; }
+          }
+          float dsv[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int cc = 8 * c8 + e;             // column inside this 32-chunk
+            const float hx = fmaf(__uint_as_float(sv[cc]), 0.5f, hb[e]);
+            const float th = tanh_approx(hx);
+            float pval = fmaf(hx, th, hx) * inv_n;                       // SiLU(x)/N
+            const float u1 = fmaf(-th, th, 1.0f);                        // 1 - tanh^2
+            const float w2 = fmaf(hx, u1, 1.0f + th);                    // 2 * SiLU'(x)
+            float dval = __uint_as_float(dv_[cc]) * w2 * (0.5f * inv_n);
+            if (edge) {
+              const int c = cb + cc;
+              const bool ok = (jk <= i0 + c) && (i0 + c < n);
+              pval = ok ? pval : 0.f;
+              dval = ok ? dval : 0.f;
+            }
+            dsv[e] = dval;
+            if (e & 1) {
+              ppk[e >> 1] = pack_bf16x2(__uint_as_float(ppk[e >> 1]), pval);
+              dpk[e >> 1] = pack_bf16x2(dsv[e - 1], dval);
+            } else {
+              ppk[e >> 1] = __float_as_uint(pval);
+            }
+          }
+          if (HAS_BIAS) {
+            // d pos_w[N-1+j-i]: for a fixed column the 32 lanes of a warp hit 32 consecutive
+            // floats, so each element is one fully coalesced fire-and-forget red.global.add
+            float* dpos = d_pos_mine + (p.N - 1 + jk - i0 - (cb + 8 * c8));
+#pragma unroll
+            for (int e = 0; e < 8; ++e) atomicAdd(dpos - e, dsv[e]);
+            // d ts_w: run-length accumulate along the row; the 8 columns almost always stay in
+            // the current bucket.  Any change anywhere in the warp takes the collective path.
+            const bool same = (bk[0] == run_bk) & (bk[1] == run_bk) & (bk[2] == run_bk) &
+                              (bk[3] == run_bk) & (bk[4] == run_bk) & (bk[5] == run_bk) &
+                              (bk[6] == run_bk) & (bk[7] == run_bk);
+            if (__all_sync(0xffffffffu, same)) {
+              run_acc += ((dsv[0] + dsv[1]) + (dsv[2] + dsv[3])) + ((dsv[4] + dsv[5]) + (dsv[6] + dsv[7]));
+            } else {
+              warp_flush(run_bk, run_acc);
+              // runs inside the group, per lane; at most 8 collective flushes
+              int gb = bk[0];
+              float ga = dsv[0];
+#pragma unroll
+              for (int e = 1; e < 8; ++e) {
+                const bool brk = bk[e] != gb;
+                if (__any_sync(0xffffffffu, brk)) {
+                  warp_flush(brk ? gb : -1, brk ? ga : 0.f);
+                  if (brk) { gb = bk[e]; ga = 0.f; }
+                }
+                ga += dsv[e];
+              }
+              run_bk = gb;
+              run_acc = ga;
+            }
           }
           // 16-byte chunk (half * 4 + c8) of this thread's 128-byte row, 128-byte swizzle
           const int chunk = ((half * 4 + c8) ^ (r & 7)) * 16;
           *reinterpret_cast<uint4*>(pT + chunk) = make_uint4(ppk[0], ppk[1], ppk[2], ppk[3]);
           *reinterpret_cast<uint4*>(dsT + chunk) = make_uint4(dpk[0], dpk[1], dpk[2], dpk[3]);
         }
+        if (HAS_BIAS) warp_flush(run_bk, run_acc);
       }
-      if (HAS_BIAS && cur_bk >= 0) atomicAdd(&h_ts[cur_bk], acc_ts);
       tc_fence_before();
       fence_proxy_async_smem();                    // st.shared -> visible to the MMA (async proxy)
       __syncwarp();
       if (lane == 0) { mbar_arrive(bar_s_free); mbar_arrive(bar_pds_full); }
       if (HAS_BIAS) {
-        // merge the 8 per-warp pos histograms of this tile and flush them
-        named_bar_sync(4, 256);
-        const int x = tid - 128;
-        if (x < 255) {
-          float sum = 0.f;
-#pragma unroll
-          for (int w = 0; w < 8; ++w) { sum += h_pos_all[w * 256 + x]; h_pos_all[w * 256 + x] = 0.f; }
-          const int64_t idx = p.N - 1 + j0 - i0 - 127 + x;
-          if (sum != 0.f && idx >= 0 && idx < 2 * p.N - 1) atomicAdd(p.d_pos_w + idx, sum);
-        }
-        // the next iteration's named barrier 2 orders these clears before the next accumulation
+        named_bar_sync(4, 256);   // tables of tile it+1 staged by everyone before their use
       }
       if (it > 0) read_back_dq(it - 1);
     }
@@ -391,10 +431,13 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
       }
     }
     if (HAS_BIAS) {
-      named_bar_sync(4, 256);                       // all h_ts atomics done
+      named_bar_sync(4, 256);                       // every warp's histogram is final
       const int x = tid - 128;
       if (x <= p.nb) {
-        const float v = h_ts[x];
+        const float* hall = reinterpret_cast<const float*>(smem + L::h_ts);
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += hall[w * 136 + x];
         if (v != 0.f) atomicAdd(p.d_ts_w + x, v);
       }
     }
@@ -449,6 +492,7 @@ int hstu_attn_bwd_sm100(const grb_hstu_attn_args* a, cudaStream_t st) {
   p.dk = reinterpret_cast<__nv_bfloat16*>(a->dk); p.lddk = a->lddk;
   p.dv = reinterpret_cast<__nv_bfloat16*>(a->dv_grad); p.lddv = a->lddv;
   p.dq_accum = a->dq_accum; p.d_ts_w = a->d_ts_w; p.d_pos_w = a->d_pos_w;
+  p.d_pos_copies = a->d_pos_copies > 0 ? a->d_pos_copies : 1;
   const size_t smem = AbSmem::total + 1024;
   dim3 grid((unsigned) p.n_kt, (unsigned) a->H, (unsigned) a->B);
   if (a->timestamps) {

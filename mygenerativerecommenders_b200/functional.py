@@ -96,10 +96,15 @@ class _HstuAttention(torch.autograd.Function):
         d_ts = d_pos = None
         if timestamps is not None:
             d_ts = torch.zeros_like(ts_w)
-            d_pos = torch.zeros_like(pos_w)
-            a.d_ts_w, a.d_pos_w = d_ts.data_ptr(), d_pos.data_ptr()
+            # short sequences funnel every CTA's d pos_w atomics into a few cache lines:
+            # spread them over private copies and sum afterwards
+            copies = max(1, min(64, 16384 // max(1, pos_w.numel())))
+            d_pos = torch.zeros((copies, pos_w.numel()), dtype=torch.float32, device=q.device)
+            a.d_ts_w, a.d_pos_w, a.d_pos_copies = d_ts.data_ptr(), d_pos.data_ptr(), copies
         with _lib.timed("hstu_attn_bwd"):
             _lib.check(_lib.lib().grb_hstu_attn_bwd(C.byref(a), _lib.stream_ptr(q.device)))
+        if d_pos is not None:
+            d_pos = d_pos.sum(0) if d_pos.shape[0] > 1 else d_pos[0]
         return dq, dk, dvv, None, None, d_ts, d_pos, None, None, None, None, None, None
 
 
