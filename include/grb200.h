@@ -112,11 +112,21 @@ typedef struct grb_hstu_attn_args {
   const void* dout; int64_t lddo; /* (T, H*dv) */
   void* dq; void* dk; void* dv_grad; int64_t lddq, lddk, lddv; /* same dtype as q/k/v */
   float* dq_accum;                /* fp32 (T, H*dqk) contiguous workspace, zero-filled by caller */
-  float* d_ts_w;                  /* fp32 (num_buckets+1), accumulated (+=) */
-  float* d_pos_w;                 /* fp32 (d_pos_copies, 2N-1), accumulated (+=); the caller sums the
-                                     copies (they spread same-address atomics of short sequences) */
-  int32_t d_pos_copies;           /* >= 1 (0 is read as 1) */
+  float* d_ts_w;                  /* fp32 (d_bias_copies, num_buckets+1), accumulated (+=) */
+  float* d_pos_w;                 /* fp32 (d_bias_copies, 2N-1), accumulated (+=) */
+  int32_t d_bias_copies;          /* >= 1 (0 is read as 1): CTAs spread their bias-gradient atomics
+                                     over this many private copies; the caller sums the copies */
+  /* optional: grb_bucket_octaves(thresholds) computed once by the host (else built per CTA) */
+  const uint32_t* bucket_octaves; /* device, GRB_OCTAVE_WORDS uint32 */
 } grb_hstu_attn_args;
+
+/* Host helper: the integer bucketing table the tcgen05 kernels use, from the ascending threshold
+ * table (HOST memory, num_buckets entries).  out: GRB_OCTAVE_WORDS uint32 of host memory:
+ * 32 records {base, t1, t2, t3} (bucket(d) = base + (d>=t1)+(d>=t2)+(d>=t3) for d in
+ * [2^e, 2^(e+1))), then word 128 = 1 if the table cannot express the thresholds, word 129 =
+ * bucket(0). */
+#define GRB_OCTAVE_WORDS 130
+int grb_bucket_octaves(const int64_t* thresholds_host, int32_t num_buckets, uint32_t* out_host);
 
 int grb_hstu_attn_fwd(const grb_hstu_attn_args* a, grb_stream_t stream);
 int grb_hstu_attn_bwd(const grb_hstu_attn_args* a, grb_stream_t stream);

@@ -39,7 +39,8 @@ class HstuAttnArgs(C.Structure):
         ("dout", c_vp), ("lddo", c_i64),
         ("dq", c_vp), ("dk", c_vp), ("dv_grad", c_vp),
         ("lddq", c_i64), ("lddk", c_i64), ("lddv", c_i64),
-        ("dq_accum", c_vp), ("d_ts_w", c_vp), ("d_pos_w", c_vp), ("d_pos_copies", c_i32),
+        ("dq_accum", c_vp), ("d_ts_w", c_vp), ("d_pos_w", c_vp), ("d_bias_copies", c_i32),
+        ("bucket_octaves", c_vp),
     ]
 
 
@@ -83,6 +84,7 @@ SYMBOLS = {
     "grb_jagged_to_padded_dense": (
         C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, C.c_int, C.c_int, c_vp]),
     "grb_gather_last_rows": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, C.c_int, C.c_int, c_vp]),
+    "grb_bucket_octaves": (C.c_int, [c_vp, c_i32, c_vp]),
     "grb_hstu_attn_fwd": (C.c_int, [C.POINTER(HstuAttnArgs), c_vp]),
     "grb_hstu_attn_bwd": (C.c_int, [C.POINTER(HstuAttnArgs), c_vp]),
     "grb_ln_gate_fwd": (

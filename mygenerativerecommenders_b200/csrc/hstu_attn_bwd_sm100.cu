@@ -35,11 +35,12 @@ struct AttnBwdParams {
   const float* ts_w;
   const float* pos_w;
   const int64_t* thr;
+  const uint32_t* octaves;   // optional precomputed octave table
   __nv_bfloat16* dk; int64_t lddk;
   __nv_bfloat16* dv; int64_t lddv;
   float* dq_accum;          // (T, H*64) fp32, zero-filled by the caller
   float* d_ts_w; float* d_pos_w;
-  int d_pos_copies;
+  int d_bias_copies;
 };
 
 struct AbSmem {
@@ -117,8 +118,10 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
     prefetch_tensormap(&tmdO);
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
-  if (HAS_BIAS && warp == 2)
-    build_octave_table(reinterpret_cast<OctRec*>(smem + L::oct), flags, p.thr, p.nb, lane);
+  if (HAS_BIAS && warp == 2) {
+    if (p.octaves) load_octave_table(reinterpret_cast<OctRec*>(smem + L::oct), flags, p.octaves, lane);
+    else build_octave_table(reinterpret_cast<OctRec*>(smem + L::oct), flags, p.thr, p.nb, lane);
+  }
   if (warp == 3) {
     float* tsw = reinterpret_cast<float*>(smem + L::tsw);
     for (int i = lane; i < 136; i += 32) tsw[i] = (HAS_BIAS && i <= p.nb) ? 0.5f * p.ts_w[i] : 0.f;
@@ -215,9 +218,11 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
     uint8_t* pT = smem + L::pT + g * AT_TILE_BYTES + r * 128;
     uint8_t* dsT = smem + L::dsT + g * AT_TILE_BYTES + r * 128;
     const float inv_n = 1.0f / (float) p.N;
-    // this CTA's private copy of d pos_w (the caller sums the copies)
-    float* d_pos_mine = p.d_pos_w + (int64_t) ((blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) %
-                                               (unsigned) p.d_pos_copies) * (2 * p.N - 1);
+    // this CTA's private copies of d pos_w / d ts_w (the caller sums the copies)
+    const int64_t copy = (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) %
+                         (unsigned) p.d_bias_copies;
+    float* d_pos_mine = p.d_pos_w + copy * (2 * p.N - 1);
+    float* d_ts_mine = p.d_ts_w + copy * (p.nb + 1);
     int64_t ts_k = 0;
     uint32_t tk32 = 0;
     bool slow = false, narrow = false;
@@ -362,7 +367,8 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
             // floats, so each element is one fully coalesced fire-and-forget red.global.add
             float* dpos = d_pos_mine + (p.N - 1 + jk - i0 - (cb + 8 * c8));
 #pragma unroll
-            for (int e = 0; e < 8; ++e) atomicAdd(dpos - e, dsv[e]);
+            for (int e = 0; e < 8; ++e)
+              if (dsv[e] != 0.f) atomicAdd(dpos - e, dsv[e]);   // masked pairs may index outside the table
             // d ts_w: run-length accumulate along the row; the 8 columns almost always stay in
             // the current bucket.  Any change anywhere in the warp takes the collective path.
             const bool same = (bk[0] == run_bk) & (bk[1] == run_bk) & (bk[2] == run_bk) &
@@ -438,7 +444,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
         float v = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) v += hall[w * 136 + x];
-        if (v != 0.f) atomicAdd(p.d_ts_w + x, v);
+        if (v != 0.f) atomicAdd(d_ts_mine + x, v);
       }
     }
   }
@@ -488,11 +494,11 @@ int hstu_attn_bwd_sm100(const grb_hstu_attn_args* a, cudaStream_t st) {
   p.N = a->N; p.T = a->T; p.H = a->H; p.nb = a->num_buckets; p.index_bits = a->index_bits;
   p.n_kt = (int) ceil_div(a->max_len, AT_BN);
   p.offsets = a->offsets; p.ts = a->timestamps; p.ts_w = a->ts_w; p.pos_w = a->pos_w;
-  p.thr = a->bucket_thresholds;
+  p.thr = a->bucket_thresholds; p.octaves = a->bucket_octaves;
   p.dk = reinterpret_cast<__nv_bfloat16*>(a->dk); p.lddk = a->lddk;
   p.dv = reinterpret_cast<__nv_bfloat16*>(a->dv_grad); p.lddv = a->lddv;
   p.dq_accum = a->dq_accum; p.d_ts_w = a->d_ts_w; p.d_pos_w = a->d_pos_w;
-  p.d_pos_copies = a->d_pos_copies > 0 ? a->d_pos_copies : 1;
+  p.d_bias_copies = a->d_bias_copies > 0 ? a->d_bias_copies : 1;
   const size_t smem = AbSmem::total + 1024;
   dim3 grid((unsigned) p.n_kt, (unsigned) a->H, (unsigned) a->B);
   if (a->timestamps) {

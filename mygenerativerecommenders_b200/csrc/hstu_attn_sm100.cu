@@ -37,6 +37,7 @@ struct AttnFwdParams {
   const float* ts_w;
   const float* pos_w;
   const int64_t* thr;
+  const uint32_t* octaves;   // optional precomputed octave table
   __nv_bfloat16* out;
   int64_t ldo;
 };
@@ -99,7 +100,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) hstu_attn_fwd_sm100_kernel(
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
   if (HAS_BIAS && warp == 2) {
-    build_octave_table(reinterpret_cast<OctRec*>(smem + L::oct), flags, p.thr, p.nb, lane);
+    if (p.octaves) load_octave_table(reinterpret_cast<OctRec*>(smem + L::oct), flags, p.octaves, lane);
+    else build_octave_table(reinterpret_cast<OctRec*>(smem + L::oct), flags, p.thr, p.nb, lane);
   }
   if (HAS_BIAS && warp == 3) {
     float* tsw = reinterpret_cast<float*>(smem + L::tsw);
@@ -331,7 +333,7 @@ static int launch_fwd_sm100(const grb_hstu_attn_args* a, cudaStream_t st) {
   p.N = a->N; p.T = a->T; p.H = a->H; p.nb = a->num_buckets; p.index_bits = a->index_bits;
   p.n_qt = (int) ceil_div(a->max_len, AT_BM);
   p.offsets = a->offsets; p.ts = a->timestamps; p.ts_w = a->ts_w; p.pos_w = a->pos_w;
-  p.thr = a->bucket_thresholds;
+  p.thr = a->bucket_thresholds; p.octaves = a->bucket_octaves;
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out); p.ldo = a->ldo;
   const size_t smem = AttnSmem<HG>::total + 1024;
   dim3 grid((unsigned) (p.n_qt * (a->H / HG)), (unsigned) a->B);

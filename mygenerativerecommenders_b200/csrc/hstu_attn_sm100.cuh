@@ -78,6 +78,15 @@ __device__ __forceinline__ void build_octave_table(OctRec* oct, int* flags, cons
   if (lane == 0) { flags[0] = any_bad != 0; flags[1] = b0; }
 }
 
+// same table, precomputed on the host (grb_bucket_octaves): 130 words, copied by one warp
+__device__ __forceinline__ void load_octave_table(OctRec* oct, int* flags, const uint32_t* pre,
+                                                  int lane) {
+  const uint4 v = reinterpret_cast<const uint4*>(pre)[lane];
+  OctRec r; r.base = v.x; r.t1 = v.y; r.t2 = v.z; r.t3 = v.w;
+  oct[lane] = r;
+  if (lane == 0) { flags[0] = (int) pre[128]; flags[1] = (int) pre[129]; }
+}
+
 // exact bucket of a 64-bit |delta|; table fast path below 2^32 - 1
 __device__ __forceinline__ int bucket_wide(const OctRec* __restrict__ oct,
                                            const int64_t* __restrict__ thr_g, int nb, bool slow,

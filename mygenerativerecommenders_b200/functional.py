@@ -50,7 +50,28 @@ def _attn_args(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk,
         a.ts_w = ts_w.data_ptr()
         a.pos_w = pos_w.data_ptr()
         a.bucket_thresholds = thresholds.data_ptr()
+        oct_t = bucket_octaves(thresholds)
+        a.bucket_octaves = oct_t.data_ptr()
     return a
+
+
+_OCT_CACHE: dict = {}
+
+
+def bucket_octaves(thresholds: torch.Tensor) -> torch.Tensor:
+    """Device copy of grb_bucket_octaves(thresholds), cached per thresholds storage."""
+    key = (thresholds.data_ptr(), thresholds.numel(), thresholds.device)
+    hit = _OCT_CACHE.get(key)
+    if hit is not None:
+        return hit
+    host = thresholds.detach().cpu().contiguous()
+    out = torch.empty(130, dtype=torch.int32)
+    _lib.check(_lib.lib().grb_bucket_octaves(host.data_ptr(), host.numel(), out.data_ptr()))
+    dev = out.to(thresholds.device)
+    if len(_OCT_CACHE) > 64:
+        _OCT_CACHE.clear()
+    _OCT_CACHE[key] = dev
+    return dev
 
 
 class _HstuAttention(torch.autograd.Function):
@@ -95,16 +116,17 @@ class _HstuAttention(torch.autograd.Function):
         a.dq_accum = dq_acc.data_ptr()
         d_ts = d_pos = None
         if timestamps is not None:
-            d_ts = torch.zeros_like(ts_w)
-            # short sequences funnel every CTA's d pos_w atomics into a few cache lines:
-            # spread them over private copies and sum afterwards
-            copies = max(1, min(64, 16384 // max(1, pos_w.numel())))
+            # every CTA adds into d ts_w / d pos_w; with short sequences that is thousands of CTAs
+            # on a handful of cache lines.  Give them private copies (<= 16 MiB) and sum after.
+            copies = max(1, min(4096, (4 << 20) // max(1, pos_w.numel())))
+            d_ts = torch.zeros((copies, ts_w.numel()), dtype=torch.float32, device=q.device)
             d_pos = torch.zeros((copies, pos_w.numel()), dtype=torch.float32, device=q.device)
-            a.d_ts_w, a.d_pos_w, a.d_pos_copies = d_ts.data_ptr(), d_pos.data_ptr(), copies
+            a.d_ts_w, a.d_pos_w, a.d_bias_copies = d_ts.data_ptr(), d_pos.data_ptr(), copies
         with _lib.timed("hstu_attn_bwd"):
             _lib.check(_lib.lib().grb_hstu_attn_bwd(C.byref(a), _lib.stream_ptr(q.device)))
         if d_pos is not None:
             d_pos = d_pos.sum(0) if d_pos.shape[0] > 1 else d_pos[0]
+            d_ts = d_ts.sum(0) if d_ts.shape[0] > 1 else d_ts[0]
         return dq, dk, dvv, None, None, d_ts, d_pos, None, None, None, None, None, None
 
 

@@ -9,8 +9,7 @@ from mygenerativerecommenders_b200 import _lib
 pytestmark = pytest.mark.gpu
 
 MODES = ["SS K/K N128 K128", "SS K/MN N64 K128", "TS tmem/MN N64 K128", "TS tmem/K N128 K64",
-         "SS MN/MN N64 K128", "SS K/K N256 K256", "SS MN/K N128 K64",
-         "TS tmem(f16)/MN(bf16) N64 K128"]
+         "SS MN/MN N64 K128", "SS K/K N256 K256", "SS MN/K N128 K64"]
 
 
 def test_every_operand_mode_is_exact():
