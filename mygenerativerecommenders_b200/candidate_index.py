@@ -146,10 +146,11 @@ def merge_sharded_topk(scores: torch.Tensor, ids: torch.Tensor, k: int, world: i
         pad_s = torch.full((B, kmax - kl), float("-inf"), device=scores.device, dtype=scores.dtype)
         pad_i = torch.full((B, kmax - kl), torch.iinfo(torch.int64).max, device=ids.device, dtype=ids.dtype)
         scores, ids = torch.cat([scores, pad_s], 1), torch.cat([ids, pad_i], 1)
-    all_s = torch.empty((world, B, kmax), device=scores.device, dtype=scores.dtype)
-    all_i = torch.empty((world, B, kmax), device=ids.device, dtype=ids.dtype)
+    # rank-major concatenation along dim 0 (the layout both NCCL and gloo accept)
+    all_s = torch.empty((world * B, kmax), device=scores.device, dtype=scores.dtype)
+    all_i = torch.empty((world * B, kmax), device=ids.device, dtype=ids.dtype)
     dist.all_gather_into_tensor(all_s, scores.contiguous(), group=group)
     dist.all_gather_into_tensor(all_i, ids.contiguous(), group=group)
-    cand_s = all_s.permute(1, 0, 2).reshape(B, world * kmax)
-    cand_i = all_i.permute(1, 0, 2).reshape(B, world * kmax)
+    cand_s = all_s.view(world, B, kmax).permute(1, 0, 2).reshape(B, world * kmax)
+    cand_i = all_i.view(world, B, kmax).permute(1, 0, 2).reshape(B, world * kmax)
     return GF.topk_merge(cand_s, cand_i, k)
