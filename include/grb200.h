@@ -148,14 +148,18 @@ int grb_ln_gate_bwd(const void* x, int64_t ldx, const void* gate, int64_t ldg, c
  * b2  models/indexing/top_k.py:44-70  MIPSBruteForceTopK  (mm + topk + id gather), fused:
  *     the (B, X) score matrix never reaches HBM.
  *
- *     grb_mips_topk chains, stream-ordered and without host sync:
- *       1. scores of a strided sample of item tiles           -> ws (B, Xs) fp32
- *       2. tau[b] = k-th largest sample score (exact)          (>= k items score >= tau[b])
- *       3. scores of ALL items, keep (score, index) >= tau[b]  -> per-row candidate lists
- *       4. exact top-k of each candidate list, sorted descending, ties -> lowest index,
+ *     grb_mips_topk chains, stream-ordered and without host sync (L = refinement levels):
+ *       0. scores of every 4^L-th 128-item tile                -> ws (B, Xs) fp32 ;
+ *          tau[b] = k-th largest sample score (exact)           (>= k items score >= tau[b]);
+ *          sample scores >= tau[b] become the first candidates
+ *       p = 1..L. scores of the tiles that are multiples of 4^(L-p) but not of 4^(L-p+1), keep
+ *          (score, index) >= tau[b] in row b's candidate list, then tighten tau[b] to the k-th
+ *          largest candidate so far
+ *       last. exact top-k of each candidate list, sorted descending, ties -> lowest index,
  *          then ids[b, r] = item_ids[index]  (item_ids == NULL: ids = index)
- *     status[0] (device int32) is set to the largest candidate count if any row overflowed
- *     `cand_cap`, else left 0; the host wrapper re-runs with a larger workspace in that case.
+ *     Every tile is scored exactly once.  status[0] (device int32) is set to the largest candidate
+ *     count if any row overflowed `cand_cap`, else left 0; the host wrapper re-runs with a larger
+ *     workspace in that case.  sample_stride: 0 = auto, else 4^L is the largest power of 4 <= it.
  *
  *     queries (B, D) row stride ldq; items (X, D) row stride ldi (the reference keeps the
  *     transposed *view* of this contiguous table, candidate_index.py:29).
