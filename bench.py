@@ -57,62 +57,84 @@ def peaks() -> dict:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock / power / throttle reasons sampled every 200 ms while the timed region runs.
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    In-process NVML (nvidia_ml_py): spawning `nvidia-smi -lms 200` next to the timed loop costs the
+    training step ~40 % (its NVML session contends with kernel launches); the same counters read
+    through one persistent handle do not.  Falls back to one nvidia-smi query if NVML is missing."""
 
     def __init__(self, gpu_index: int):
         self.idx = gpu_index
-        self.proc = None
-        self.lines: list[str] = []
+        self.samples: list[tuple[float, float, int]] = []
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+
+    def _physical_index(self) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.idx])
+            except (ValueError, IndexError):
+                pass
+        return self.idx
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "200", "-i", str(self.idx)],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._pump, daemon=True)
-            self.t.start()
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
         except Exception:
-            self.proc = None
+            self._nvml = None
         return self
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _poll(self):
+        nv = self._nvml
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0
+                rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                self.samples.append((sm, pw, rs))
+            except Exception:
+                pass
+            self._stop.wait(0.2)
 
     def __exit__(self, *exc):
-        if self.proc is not None:
-            time.sleep(0.25)
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=1.0)
         return False
 
     def summary(self) -> dict:
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
-                                  "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        nv = self._nvml
+        if nv is None or not self.samples:
+            return self._smi_once()
+        sm = sorted(s[0] for s in self.samples)
+        bits = 0
+        for s in self.samples:
+            bits |= s[2]
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        reasons = sorted(k for k, v in names.items() if bits & v)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self._max, "reasons": reasons,
+                "samples": len(sm), "power_w_max": max(s[1] for s in self.samples), "via": "nvml"}
+
+    def _smi_once(self) -> dict:
+        try:
+            out = subprocess.run(
+                ["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits",
+                 "-i", str(self._physical_index())], capture_output=True, text=True, timeout=10).stdout
+            a, b = [float(x) for x in out.strip().split(",")[:2]]
+            return {"sm_mhz": a, "sm_max_mhz": b, "reasons": [], "samples": 1, "via": "nvidia-smi (after)"}
+        except Exception:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
 
 
 def dist_setup(n_gpus: int):
@@ -429,7 +451,7 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-retrieval", action="store_true")

@@ -25,7 +25,9 @@ namespace grb {
 
 using namespace ptx;
 
-constexpr int AB_THREADS = 384;
+constexpr int AB_NWG = 4;                       // epilogue warpgroups: 32 query columns each
+constexpr int AB_EPI = AB_NWG * 128;
+constexpr int AB_THREADS = 128 + AB_EPI;
 
 struct AttnBwdParams {
   int64_t N, T;
@@ -53,12 +55,16 @@ struct AbSmem {
   // staging against use
   static constexpr int tsq = dsT + 2 * AT_TILE_BYTES;            // 2 x 128 x int64
   static constexpr int tsq32 = tsq + 2 * 128 * 8;                // 2 x 128 x uint32
-  static constexpr int red = tsq32 + 2 * 128 * 4;                // 16 x int64
-  static constexpr int pos = red + 16 * 8;                       // 2 x 256 x float (pre-halved)
+  static constexpr int red = tsq32 + 2 * 128 * 4;                // 2 x 16 x int64
+  static constexpr int pos = red + 32 * 8;                       // 2 x 256 x float (pre-halved)
   static constexpr int tsw = pos + 2 * 256 * 4;                  // 136 x float (pre-halved)
   static constexpr int oct = tsw + 136 * 4;                      // 32 x OctRec
-  static constexpr int h_ts = oct + 32 * 16;                     // 8 warps x 136 x float
-  static constexpr int bars = h_ts + 8 * 136 * 4;
+  static constexpr int h_ts = oct + 32 * 16;                     // 16 warps x 136 x float
+  // plain (unswizzled) bf16 copy of dS^T [128 key rows][128 query cols], row stride 272 B: the
+  // d pos_w diagonal sums read it after the tile barrier
+  static constexpr int ds_plain = h_ts + 16 * 136 * 4;
+  static constexpr int DS_STRIDE = 272;
+  static constexpr int bars = ds_plain + 128 * DS_STRIDE;
   static constexpr int total = bars + 256;
 };
 
@@ -107,11 +113,11 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
     mbar_init(bar_kv, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(bar_ring_full + 8 * s, 1); mbar_init(bar_ring_empty + 8 * s, 1); }
     mbar_init(bar_s_full, 1);
-    mbar_init(bar_s_free, 8);
-    mbar_init(bar_pds_full, 8);
+    mbar_init(bar_s_free, AB_EPI / 32);
+    mbar_init(bar_pds_full, AB_EPI / 32);
     mbar_init(bar_pds_free, 1);
     mbar_init(bar_dq_full, 1);
-    mbar_init(bar_dq_free, 8);
+    mbar_init(bar_dq_free, AB_EPI / 32);
     mbar_init(bar_dkv, 1);
     fence_barrier_init();
     prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV);
@@ -126,7 +132,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
     float* tsw = reinterpret_cast<float*>(smem + L::tsw);
     for (int i = lane; i < 136; i += 32) tsw[i] = (HAS_BIAS && i <= p.nb) ? 0.5f * p.ts_w[i] : 0.f;
     float* hp = reinterpret_cast<float*>(smem + L::h_ts);
-    for (int i = lane; i < 8 * 136; i += 32) hp[i] = 0.f;
+    for (int i = lane; i < 16 * 136; i += 32) hp[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -204,9 +210,10 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
     }
   } else if (warp >= 4) {
     // ================= epilogue warpgroups =================
-    const int g = (warp - 4) >> 2;                 // which half of the 128 query columns
+    const int g = (warp - 4) >> 2;                 // warpgroup: query columns [32g, 32g+32)
     const int r = ((warp & 3) << 5) | lane;        // key row inside the tile = TMEM lane
-    const int w8 = warp - 4;
+    const int wq = warp - 4;
+    const int et = tid - 128;                      // 0 .. AB_EPI-1
     const uint32_t lane_base = (uint32_t) ((warp & 3) * 32) << 16;
     const int jk = j0 + r;                         // key position in the sequence
     int64_t* tsq_all = reinterpret_cast<int64_t*>(smem + L::tsq);
@@ -214,9 +221,12 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
     float* pos_all = reinterpret_cast<float*>(smem + L::pos);
     const float* tsw_s = reinterpret_cast<const float*>(smem + L::tsw);
     const OctRec* oct = reinterpret_cast<const OctRec*>(smem + L::oct);
-    float* h_ts = reinterpret_cast<float*>(smem + L::h_ts) + w8 * 136;   // this warp's d ts_w
-    uint8_t* pT = smem + L::pT + g * AT_TILE_BYTES + r * 128;
-    uint8_t* dsT = smem + L::dsT + g * AT_TILE_BYTES + r * 128;
+    float* h_ts = reinterpret_cast<float*>(smem + L::h_ts) + wq * 136;   // this warp's d ts_w
+    // this thread's 64-byte slice (4 x 16-byte chunks) of its 128-byte row in block g / 2
+    uint8_t* pT = smem + L::pT + (g >> 1) * AT_TILE_BYTES + r * 128;
+    uint8_t* dsT = smem + L::dsT + (g >> 1) * AT_TILE_BYTES + r * 128;
+    const int chunk0 = (g & 1) * 4;
+    uint8_t* ds_plain = smem + L::ds_plain;
     const float inv_n = 1.0f / (float) p.N;
     // this CTA's private copies of d pos_w / d ts_w (the caller sums the copies)
     const int64_t copy = (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) %
@@ -231,23 +241,23 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
       ts_k = ext_ts_at(p.ts, b, p.N, (int64_t) jk);
       slow = flags[0] != 0;
       const int cnt = (int) (n64 + 1 < p.N ? n64 + 1 : p.N);
-      const TsRange tr = scan_ts_range(p.ts + (int64_t) b * p.N, cnt, tid - 128,
-                                       reinterpret_cast<int64_t*>(smem + L::red), 3);
+      const TsRange tr = scan_ts_range<AB_EPI>(p.ts + (int64_t) b * p.N, cnt, et,
+                                               reinterpret_cast<int64_t*>(smem + L::red), 3);
       narrow = tr.narrow && !slow;
       tmin = tr.tmin;
       tk32 = (uint32_t) (ts_k - tmin);
     }
-    auto read_back_dq = [&](int it) {   // dQ of iteration `it`: lane = query row, 32 columns per warpgroup
+    auto read_back_dq = [&](int it) {   // dQ of iteration `it`: lane = query row, 16 columns per warpgroup
       mbar_wait(bar_dq_full, it & 1);
       tc_fence_after();
-      uint32_t qv[32];
-      tmem_ld32(tmem + lane_base + 384 + 32 * g, qv);
+      uint32_t qv[16];
+      tmem_ld16(tmem + lane_base + 384 + 16 * g, qv);
       tmem_ld_wait();
       const int qi = (kt + it) * AT_BM + r;
       if (qi < n) {
-        float* dst = p.dq_accum + (off0 + qi) * (int64_t) (p.H * AT_D) + h * AT_D + 32 * g;
+        float* dst = p.dq_accum + (off0 + qi) * (int64_t) (p.H * AT_D) + h * AT_D + 16 * g;
 #pragma unroll
-        for (int v4 = 0; v4 < 8; ++v4)
+        for (int v4 = 0; v4 < 4; ++v4)
           red_add_v4(dst + 4 * v4, __uint_as_float(qv[4 * v4]), __uint_as_float(qv[4 * v4 + 1]),
                      __uint_as_float(qv[4 * v4 + 2]), __uint_as_float(qv[4 * v4 + 3]));
       }
@@ -263,7 +273,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
         const int64_t tq = ext_ts_at(p.ts, b, p.N, (int64_t) i0 + r + 1);
         tsq_all[pb * 128 + r] = tq;
         tsq32_all[pb * 128 + r] = (uint32_t) (tq - tmin);
-      } else {
+      } else if (g == 1) {
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           const int x = r + 128 * t;               // pos[x] = 0.5 * pos_w[N-1 + j0 - i0 - 127 + x]
@@ -290,7 +300,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
 
     if (HAS_BIAS) {
       stage_tables(0);
-      named_bar_sync(2, 256);
+      named_bar_sync(2, AB_EPI);
     }
     for (int it = 0; it < n_it; ++it) {
       const int i0 = (kt + it) * AT_BM;
@@ -302,38 +312,40 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
       const bool edge = (it == 0) || (i0 + AT_BM > n);   // diagonal tile or ragged last tile
       mbar_wait(bar_s_full, it & 1);
       tc_fence_after();
+      if (HAS_BIAS && it > 0) named_bar_sync(5, AB_EPI);   // diagonal sums of tile it-1 are done
+      int run_bk = -1;            // d ts_w: run-length accumulate along the row
+      float run_acc = 0.f;
 #pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        const int cb = 64 * g + 32 * half;
-        uint32_t sv[32], dv_[32];
-        tmem_ld32(tmem + lane_base + cb, sv);
-        tmem_ld32(tmem + lane_base + 128 + cb, dv_);
+      for (int c16 = 0; c16 < 2; ++c16) {
+        const int cb = 32 * g + 16 * c16;
+        uint32_t sv[16], dv_[16];
+        tmem_ld16(tmem + lane_base + cb, sv);
+        tmem_ld16(tmem + lane_base + 128 + cb, dv_);
         tmem_ld_wait();
-        if (half == 0 && it > 0) mbar_wait(bar_pds_free, (it - 1) & 1);   // smem tiles reusable
-        int run_bk = -1;          // d ts_w: run-length accumulate along the row
-        float run_acc = 0.f;
+        if (c16 == 0 && it > 0) mbar_wait(bar_pds_free, (it - 1) & 1);   // smem tiles reusable
 #pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
+        for (int c8 = 0; c8 < 2; ++c8) {
           uint32_t ppk[4], dpk[4];
           int bk[8];
           float hb[8];
+          const int c0 = cb + 8 * c8;              // first query column of this group
           if (HAS_BIAS) {
             if (narrow) {
-              const uint4 ta = *reinterpret_cast<const uint4*>(tsq32_s + cb + 8 * c8);
-              const uint4 tb = *reinterpret_cast<const uint4*>(tsq32_s + cb + 8 * c8 + 4);
+              const uint4 ta = *reinterpret_cast<const uint4*>(tsq32_s + c0);
+              const uint4 tb = *reinterpret_cast<const uint4*>(tsq32_s + c0 + 4);
               const uint32_t tq[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
 #pragma unroll
               for (int e = 0; e < 8; ++e) bk[e] = bucket_narrow(oct, __usad(tk32, tq[e], 0u));
             } else {
-#pragma unroll
+#pragma unroll 1
               for (int e = 0; e < 8; ++e) {
-                int64_t d = tsq_s[cb + 8 * c8 + e] - ts_k;
+                int64_t d = tsq_s[c0 + e] - ts_k;
                 d = d < 0 ? -d : d;
                 bk[e] = bucket_wide(oct, p.thr, p.nb, slow, d);
               }
             }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) hb[e] = pos_s[r - (cb + 8 * c8 + e) + 127] + tsw_s[bk[e]];
+            for (int e = 0; e < 8; ++e) hb[e] = pos_s[r - (c0 + e) + 127] + tsw_s[bk[e]];
           } else {
 #pragma unroll
             for (int e = 0; e < 8; ++e) { bk[e] = 0; hb[e] = 0.f; }
@@ -341,7 +353,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
           float dsv[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const int cc = 8 * c8 + e;             // column inside this 32-chunk
+            const int cc = 8 * c8 + e;             // column inside this 16-chunk
             const float hx = fmaf(__uint_as_float(sv[cc]), 0.5f, hb[e]);
             const float th = tanh_approx(hx);
             float pval = fmaf(hx, th, hx) * inv_n;                       // SiLU(x)/N
@@ -349,8 +361,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
             const float w2 = fmaf(hx, u1, 1.0f + th);                    // 2 * SiLU'(x)
             float dval = __uint_as_float(dv_[cc]) * w2 * (0.5f * inv_n);
             if (edge) {
-              const int c = cb + cc;
-              const bool ok = (jk <= i0 + c) && (i0 + c < n);
+              const bool ok = (jk <= i0 + c0 + e) && (i0 + c0 + e < n);
               pval = ok ? pval : 0.f;
               dval = ok ? dval : 0.f;
             }
@@ -363,12 +374,11 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
             }
           }
           if (HAS_BIAS) {
-            // d pos_w[N-1+j-i]: for a fixed column the 32 lanes of a warp hit 32 consecutive
-            // floats, so each element is one fully coalesced fire-and-forget red.global.add
-            float* dpos = d_pos_mine + (p.N - 1 + jk - i0 - (cb + 8 * c8));
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-              if (dsv[e] != 0.f) atomicAdd(dpos - e, dsv[e]);   // masked pairs may index outside the table
+            // d pos_w needs the sums of dS along the diagonals of the tile: stash a plain copy
+            // (per-element global red costs ~41 LSU cycles per warp instruction; a shared
+            // read-modify-write per element races between neighbouring lanes)
+            *reinterpret_cast<uint4*>(ds_plain + r * L::DS_STRIDE + c0 * 2) =
+                make_uint4(dpk[0], dpk[1], dpk[2], dpk[3]);
             // d ts_w: run-length accumulate along the row; the 8 columns almost always stay in
             // the current bucket.  Any change anywhere in the warp takes the collective path.
             const bool same = (bk[0] == run_bk) & (bk[1] == run_bk) & (bk[2] == run_bk) &
@@ -378,7 +388,6 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
               run_acc += ((dsv[0] + dsv[1]) + (dsv[2] + dsv[3])) + ((dsv[4] + dsv[5]) + (dsv[6] + dsv[7]));
             } else {
               warp_flush(run_bk, run_acc);
-              // runs inside the group, per lane; at most 8 collective flushes
               int gb = bk[0];
               float ga = dsv[0];
 #pragma unroll
@@ -394,57 +403,68 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
               run_acc = ga;
             }
           }
-          // 16-byte chunk (half * 4 + c8) of this thread's 128-byte row, 128-byte swizzle
-          const int chunk = ((half * 4 + c8) ^ (r & 7)) * 16;
+          // 16-byte chunk of this thread's row slice, 128-byte swizzle
+          const int chunk = ((chunk0 + 2 * c16 + c8) ^ (r & 7)) * 16;
           *reinterpret_cast<uint4*>(pT + chunk) = make_uint4(ppk[0], ppk[1], ppk[2], ppk[3]);
           *reinterpret_cast<uint4*>(dsT + chunk) = make_uint4(dpk[0], dpk[1], dpk[2], dpk[3]);
         }
-        if (HAS_BIAS) warp_flush(run_bk, run_acc);
       }
+      if (HAS_BIAS) warp_flush(run_bk, run_acc);
       tc_fence_before();
       fence_proxy_async_smem();                    // st.shared -> visible to the MMA (async proxy)
       __syncwarp();
       if (lane == 0) { mbar_arrive(bar_s_free); mbar_arrive(bar_pds_full); }
       if (HAS_BIAS) {
-        named_bar_sync(4, 256);   // tables of tile it+1 staged by everyone before their use
+        named_bar_sync(4, AB_EPI);   // dS^T copy complete; tables of tile it+1 staged
+        // d pos_w[N-1+j-i]: thread (x, half) sums diagonal x = r - c + 127 over 64 key rows
+        const int x = et & 255, hf = et >> 8;
+        if (x < 255) {
+          int r0 = hf * 64, r1 = r0 + 64;
+          const int lo = x - 127 > 0 ? x - 127 : 0;          // c = r - x + 127 >= 0
+          const int hi = x + 1 < 128 ? x + 1 : 128;          // c <= 127
+          r0 = r0 > lo ? r0 : lo;
+          r1 = r1 < hi ? r1 : hi;
+          float sum = 0.f;
+          const uint8_t* ptr = ds_plain + r0 * L::DS_STRIDE + (r0 - x + 127) * 2;
+          for (int rr = r0; rr < r1; ++rr, ptr += L::DS_STRIDE + 2)
+            sum += __uint_as_float((uint32_t) (*reinterpret_cast<const uint16_t*>(ptr)) << 16);
+          const int64_t idx = p.N - 1 + j0 - i0 - 127 + x;
+          if (sum != 0.f && idx >= 0 && idx < 2 * p.N - 1) atomicAdd(d_pos_mine + idx, sum);
+        }
       }
       if (it > 0) read_back_dq(it - 1);
     }
     read_back_dq(n_it - 1);
 
-    // ---- dV / dK: thread = key row; warpgroup 0 stores dV, warpgroup 1 stores dK ----
+    // ---- dV / dK: thread = key row; warpgroups 0,1 store dV halves, 2,3 store dK halves ----
     mbar_wait(bar_dkv, 0);
     tc_fence_after();
     {
-      __nv_bfloat16* dst = (g == 0 ? p.dv + (off0 + jk) * p.lddv : p.dk + (off0 + jk) * p.lddk) + h * AT_D;
-      const uint32_t col0 = 256 + 64 * g;
+      __nv_bfloat16* dst = (g < 2 ? p.dv + (off0 + jk) * p.lddv : p.dk + (off0 + jk) * p.lddk) +
+                           h * AT_D + 32 * (g & 1);
+      uint32_t ov[32];
+      tmem_ld32(tmem + lane_base + 256 + 32 * g, ov);
+      tmem_ld_wait();
+      if (jk < n) {
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t ov[32];
-        tmem_ld32(tmem + lane_base + col0 + 32 * half, ov);
-        tmem_ld_wait();
-        if (jk < n) {
-#pragma unroll
-          for (int v4 = 0; v4 < 4; ++v4) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 0]), __uint_as_float(ov[v4 * 8 + 1]));
-            o.y = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 2]), __uint_as_float(ov[v4 * 8 + 3]));
-            o.z = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 4]), __uint_as_float(ov[v4 * 8 + 5]));
-            o.w = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 6]), __uint_as_float(ov[v4 * 8 + 7]));
-            *reinterpret_cast<uint4*>(dst + half * 32 + v4 * 8) = o;
-          }
+        for (int v4 = 0; v4 < 4; ++v4) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 0]), __uint_as_float(ov[v4 * 8 + 1]));
+          o.y = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 2]), __uint_as_float(ov[v4 * 8 + 3]));
+          o.z = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 4]), __uint_as_float(ov[v4 * 8 + 5]));
+          o.w = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 6]), __uint_as_float(ov[v4 * 8 + 7]));
+          *reinterpret_cast<uint4*>(dst + v4 * 8) = o;
         }
       }
     }
     if (HAS_BIAS) {
-      named_bar_sync(4, 256);                       // every warp's histogram is final
-      const int x = tid - 128;
-      if (x <= p.nb) {
+      named_bar_sync(4, AB_EPI);                    // every warp's histogram is final
+      if (et <= p.nb) {
         const float* hall = reinterpret_cast<const float*>(smem + L::h_ts);
         float v = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) v += hall[w * 136 + x];
-        if (v != 0.f) atomicAdd(d_ts_mine + x, v);
+        for (int w = 0; w < AB_EPI / 32; ++w) v += hall[w * 136 + et];
+        if (v != 0.f) atomicAdd(d_ts_mine + et, v);
       }
     }
   }

@@ -87,12 +87,17 @@ __device__ __forceinline__ void load_octave_table(OctRec* oct, int* flags, const
   if (lane == 0) { flags[0] = (int) pre[128]; flags[1] = (int) pre[129]; }
 }
 
+// out-of-line exact search: keeps the (rare) 64-bit path from bloating the unrolled hot loops
+static __device__ __noinline__ int bucket_search_noinline(const int64_t* thr, int n, int64_t d) {
+  return bucket_of(thr, n, d);
+}
+
 // exact bucket of a 64-bit |delta|; table fast path below 2^32 - 1
 __device__ __forceinline__ int bucket_wide(const OctRec* __restrict__ oct,
                                            const int64_t* __restrict__ thr_g, int nb, bool slow,
                                            int64_t d) {
   // 0xffffffff doubles as the "no threshold" marker of the table, so it takes the slow path too
-  if (slow || (uint64_t) d >= 0xffffffffull) return bucket_of(thr_g, nb, d);
+  if (slow || (uint64_t) d >= 0xffffffffull) return bucket_search_noinline(thr_g, nb, d);
   const uint32_t u = (uint32_t) d;
   const OctRec r = oct[31 - __clz(u | 1u)];
   return (int) r.base + (u >= r.t1) + (u >= r.t2) + (u >= r.t3);
@@ -105,12 +110,13 @@ __device__ __forceinline__ int bucket_narrow(const OctRec* __restrict__ oct, uin
 
 // min / max of ts[b, 0..count) over the 256 epilogue threads (tid256 in [0,256)).  If the span
 // fits in 32 bits every |delta| of the sequence does, and the kernels use 32-bit arithmetic on
-// (ts - tmin).  red: 16 x int64 of shared memory.  All 256 threads must call it.
+// (ts - tmin).  red: 2 * NT/32 x int64 of shared memory.  All NT threads must call it.
 struct TsRange { int64_t tmin; bool narrow; };
+template <int NT = 256>
 __device__ __forceinline__ TsRange scan_ts_range(const int64_t* __restrict__ ts_row, int count,
                                                  int tid256, int64_t* red, int bar_id) {
   int64_t mn = INT64_MAX, mx = INT64_MIN;
-  for (int i = tid256; i < count; i += 256) {
+  for (int i = tid256; i < count; i += NT) {
     const int64_t v = ts_row[i];
     mn = v < mn ? v : mn;
     mx = v > mx ? v : mx;
@@ -123,9 +129,9 @@ __device__ __forceinline__ TsRange scan_ts_range(const int64_t* __restrict__ ts_
     mx = c > mx ? c : mx;
   }
   if ((tid256 & 31) == 0) { red[(tid256 >> 5) * 2] = mn; red[(tid256 >> 5) * 2 + 1] = mx; }
-  named_bar_sync(bar_id, 256);
+  named_bar_sync(bar_id, NT);
 #pragma unroll
-  for (int w = 0; w < 8; ++w) {
+  for (int w = 0; w < NT / 32; ++w) {
     const int64_t a = red[w * 2], c = red[w * 2 + 1];
     mn = a < mn ? a : mn;
     mx = c > mx ? c : mx;
