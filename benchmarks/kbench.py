@@ -80,14 +80,19 @@ def attn_case(B, N, H, lengths, dtype=torch.bfloat16, d=64):
 def bench_attn(tag, B, N, H, lengths, bwd=True):
     c = attn_case(B, N, H, lengths)
     H, d = c["H"], c["d"]
+    mkc = lambda: GF.hstu_bucket_cache(c["off"], c["ts"], c["thr"], c["N"])
+    cache = mkc()
+    report(f"hstu_bucket_tiles[{tag}] (once per batch, shared by all layers)", timeit(mkc, flush=False),
+           byts=cache.numel())
     run = lambda: GF.hstu_attention(c["q"], c["k"], c["v"], c["off"], c["ts"], c["ts_w"],
-                                    c["pos_w"], c["thr"], c["N"], H, d, d)
+                                    c["pos_w"], c["thr"], c["N"], H, d, d, bucket_cache=cache)
     ms = timeit(run, flush=False)
     report(f"hstu_attn_fwd[{tag}]", ms, flop=c["pairs"] * 2 * H * 2 * d, T=c["T"], pairs=c["pairs"])
     if bwd:
         q, k, v = (c[n].clone().requires_grad_(True) for n in ("q", "k", "v"))
         ts_w, pos_w = c["ts_w"].clone().requires_grad_(True), c["pos_w"].clone().requires_grad_(True)
-        out = GF.hstu_attention(q, k, v, c["off"], c["ts"], ts_w, pos_w, c["thr"], c["N"], H, d, d)
+        out = GF.hstu_attention(q, k, v, c["off"], c["ts"], ts_w, pos_w, c["thr"], c["N"], H, d, d,
+                                bucket_cache=cache)
         go = torch.randn_like(out)
         runb = lambda: torch.autograd.grad(out, (q, k, v, ts_w, pos_w), go, retain_graph=True)
         msb = timeit(runb, iters=5, warmup=2, flush=False)

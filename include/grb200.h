@@ -118,6 +118,11 @@ typedef struct grb_hstu_attn_args {
                                      over this many private copies; the caller sums the copies */
   /* optional: grb_bucket_octaves(thresholds) computed once by the host (else built per CTA) */
   const uint32_t* bucket_octaves; /* device, GRB_OCTAVE_WORDS uint32 */
+  /* optional: grb_hstu_bucket_tiles output for THIS (offsets, timestamps, thresholds): the bucket
+   * indices are layer-, head- and direction-independent, so one tabulation serves every attention
+   * launch of a step.  bucket_cache_max_len = the max_len it was built with. */
+  const uint8_t* bucket_cache;
+  int64_t bucket_cache_max_len;
 } grb_hstu_attn_args;
 
 /* Host helper: the integer bucketing table the tcgen05 kernels use, from the ascending threshold
@@ -127,6 +132,13 @@ typedef struct grb_hstu_attn_args {
  * bucket(0). */
 #define GRB_OCTAVE_WORDS 130
 int grb_bucket_octaves(const int64_t* thresholds_host, int32_t num_buckets, uint32_t* out_host);
+
+/* Bucket-index tiles, once per batch (hstu.py:113-123 hoisted out of the layers).  cache must hold
+ * grb_hstu_bucket_cache_bytes(B, max_len) bytes; layout in csrc/hstu_bucket_cache.cu. */
+int64_t grb_hstu_bucket_cache_bytes(int64_t B, int64_t max_len);
+int grb_hstu_bucket_tiles(const void* offsets, int index_bits, const int64_t* timestamps, int64_t B,
+                          int64_t N, int64_t max_len, const int64_t* thresholds, int32_t num_buckets,
+                          const uint32_t* octaves, void* cache, grb_stream_t stream);
 
 int grb_hstu_attn_fwd(const grb_hstu_attn_args* a, grb_stream_t stream);
 int grb_hstu_attn_bwd(const grb_hstu_attn_args* a, grb_stream_t stream);

@@ -38,6 +38,8 @@ struct AttnBwdParams {
   const float* pos_w;
   const int64_t* thr;
   const uint32_t* octaves;   // optional precomputed octave table
+  const uint8_t* bcache;     // optional bucket-index tiles (hstu_bucket_cache.cu)
+  int cache_nt;
   __nv_bfloat16* dk; int64_t lddk;
   __nv_bfloat16* dv; int64_t lddv;
   float* dq_accum;          // (T, H*64) fp32, zero-filled by the caller
@@ -64,7 +66,8 @@ struct AbSmem {
   // d pos_w diagonal sums read it after the tile barrier
   static constexpr int ds_plain = h_ts + 16 * 136 * 4;
   static constexpr int DS_STRIDE = 272;
-  static constexpr int bars = ds_plain + 128 * DS_STRIDE;
+  static constexpr int bkt = ds_plain + 128 * DS_STRIDE;       // 128 x 128 uint8 bucket tile
+  static constexpr int bars = bkt + 128 * 128;
   static constexpr int total = bars + 256;
 };
 
@@ -108,6 +111,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
   const uint32_t bar_dkv = smem_u32(bars + 11);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   int* flags = reinterpret_cast<int*>(bars + 13);
+  const uint32_t bar_bkt = smem_u32(bars + 14);
 
   if (tid == 0) {
     mbar_init(bar_kv, 1);
@@ -119,6 +123,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
     mbar_init(bar_dq_full, 1);
     mbar_init(bar_dq_free, AB_EPI / 32);
     mbar_init(bar_dkv, 1);
+    mbar_init(bar_bkt, 1);
     fence_barrier_init();
     prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV);
     prefetch_tensormap(&tmdO);
@@ -228,6 +233,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
     const int chunk0 = (g & 1) * 4;
     uint8_t* ds_plain = smem + L::ds_plain;
     const float inv_n = 1.0f / (float) p.N;
+    const float half_inv_n = 0.5f * inv_n;
     // this CTA's private copies of d pos_w / d ts_w (the caller sums the copies)
     const int64_t copy = (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) %
                          (unsigned) p.d_bias_copies;
@@ -258,8 +264,10 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
         float* dst = p.dq_accum + (off0 + qi) * (int64_t) (p.H * AT_D) + h * AT_D + 16 * g;
 #pragma unroll
         for (int v4 = 0; v4 < 4; ++v4)
-          red_add_v4(dst + 4 * v4, __uint_as_float(qv[4 * v4]), __uint_as_float(qv[4 * v4 + 1]),
-                     __uint_as_float(qv[4 * v4 + 2]), __uint_as_float(qv[4 * v4 + 3]));
+          red_add_v4(dst + 4 * v4, __uint_as_float(qv[4 * v4]) * half_inv_n,
+                     __uint_as_float(qv[4 * v4 + 1]) * half_inv_n,
+                     __uint_as_float(qv[4 * v4 + 2]) * half_inv_n,
+                     __uint_as_float(qv[4 * v4 + 3]) * half_inv_n);
       }
       tc_fence_before();
       __syncwarp();
@@ -282,23 +290,26 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
         }
       }
     };
-    // d ts_w, warp collective (all 32 lanes call it): sum `val` per distinct bucket of the warp
-    // and let ONE lane do the read-modify-write on the warp-private histogram — shared memory has
-    // no native fp32 atomic add (atomicAdd compiles to a CAS spin loop).
-    auto warp_flush = [&](int bk, float val) {
-      unsigned todo = 0xffffffffu;
-      while (todo) {
-        const int leader = __ffs(todo) - 1;
-        const int lbk = __shfl_sync(0xffffffffu, bk, leader);
-        const bool mine = (bk == lbk);
-        const float sum = warp_sum(mine ? val : 0.f);
-        if (lane == 0 && lbk >= 0) h_ts[lbk] += sum;
-        todo &= ~__ballot_sync(0xffffffffu, mine);
-      }
-      __syncwarp();
+    // d ts_w: each thread run-length accumulates along its row (buckets change rarely along a
+    // row) and adds a finished run to its warp's private histogram.  Shared memory has no native
+    // fp32 add (atomicAdd is a CAS loop), but a run ends only a few times per row and only lanes
+    // of one warp can collide here, so the loop almost never retries.
+    auto flush_run = [&](int bk, float val) {
+      if (bk >= 0 && val != 0.f) atomicAdd(&h_ts[bk], val * half_inv_n);
     };
 
+    // cached bucket tiles: slot (kt + it, kt) of this sequence, "K orientation" half
+    const bool cached = HAS_BIAS && p.bcache != nullptr;
+    const uint8_t* bkt_s = smem + L::bkt;
+    auto load_bkt = [&](int it) {
+      const int64_t tps = (int64_t) p.cache_nt * (p.cache_nt + 1) / 2;
+      const int64_t iq = kt + it;
+      const uint8_t* src = p.bcache + ((int64_t) b * tps + iq * (iq + 1) / 2 + kt) * 32768 + 16384;
+      mbar_arrive_expect_tx(bar_bkt, 16384);
+      bulk_load_1d(smem_u32(bkt_s), src, 16384, bar_bkt);
+    };
     if (HAS_BIAS) {
+      if (cached && et == 0) load_bkt(0);
       stage_tables(0);
       named_bar_sync(2, AB_EPI);
     }
@@ -313,6 +324,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
       mbar_wait(bar_s_full, it & 1);
       tc_fence_after();
       if (HAS_BIAS && it > 0) named_bar_sync(5, AB_EPI);   // diagonal sums of tile it-1 are done
+      if (cached) mbar_wait(bar_bkt, it & 1);
       int run_bk = -1;            // d ts_w: run-length accumulate along the row
       float run_acc = 0.f;
 #pragma unroll 1
@@ -330,7 +342,14 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
           float hb[8];
           const int c0 = cb + 8 * c8;              // first query column of this group
           if (HAS_BIAS) {
-            if (narrow) {
+            if (cached) {
+              // 8 bucket bytes of this key row: query chunk (c0 / 16), bytes (c0 % 16) .. +7
+              const uint2 raw = *reinterpret_cast<const uint2*>(
+                  bkt_s + ((size_t) (c0 >> 4) * 128 + r) * 16 + (c0 & 8));
+              const uint32_t w2[2] = {raw.x, raw.y};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) bk[e] = (int) ((w2[e >> 2] >> (8 * (e & 3))) & 0xffu);
+            } else if (narrow) {
               const uint4 ta = *reinterpret_cast<const uint4*>(tsq32_s + c0);
               const uint4 tb = *reinterpret_cast<const uint4*>(tsq32_s + c0 + 4);
               const uint32_t tq[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
@@ -356,10 +375,12 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
             const int cc = 8 * c8 + e;             // column inside this 16-chunk
             const float hx = fmaf(__uint_as_float(sv[cc]), 0.5f, hb[e]);
             const float th = tanh_approx(hx);
-            float pval = fmaf(hx, th, hx) * inv_n;                       // SiLU(x)/N
+            // unscaled: P' = SiLU(x) = N P ; dS' = dP * 2 SiLU'(x) = 2N dS.  The 1/N and 1/(2N)
+            // factors are linear and applied once to dV, dK, dQ and the bias gradients.
+            float pval = fmaf(hx, th, hx);
             const float u1 = fmaf(-th, th, 1.0f);                        // 1 - tanh^2
             const float w2 = fmaf(hx, u1, 1.0f + th);                    // 2 * SiLU'(x)
-            float dval = __uint_as_float(dv_[cc]) * w2 * (0.5f * inv_n);
+            float dval = __uint_as_float(dv_[cc]) * w2;
             if (edge) {
               const bool ok = (jk <= i0 + c0 + e) && (i0 + c0 + e < n);
               pval = ok ? pval : 0.f;
@@ -379,28 +400,22 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
             // read-modify-write per element races between neighbouring lanes)
             *reinterpret_cast<uint4*>(ds_plain + r * L::DS_STRIDE + c0 * 2) =
                 make_uint4(dpk[0], dpk[1], dpk[2], dpk[3]);
-            // d ts_w: run-length accumulate along the row; the 8 columns almost always stay in
-            // the current bucket.  Any change anywhere in the warp takes the collective path.
+            // d ts_w: run-length accumulate along the row
             const bool same = (bk[0] == run_bk) & (bk[1] == run_bk) & (bk[2] == run_bk) &
                               (bk[3] == run_bk) & (bk[4] == run_bk) & (bk[5] == run_bk) &
                               (bk[6] == run_bk) & (bk[7] == run_bk);
-            if (__all_sync(0xffffffffu, same)) {
+            if (same) {
               run_acc += ((dsv[0] + dsv[1]) + (dsv[2] + dsv[3])) + ((dsv[4] + dsv[5]) + (dsv[6] + dsv[7]));
             } else {
-              warp_flush(run_bk, run_acc);
-              int gb = bk[0];
-              float ga = dsv[0];
 #pragma unroll
-              for (int e = 1; e < 8; ++e) {
-                const bool brk = bk[e] != gb;
-                if (__any_sync(0xffffffffu, brk)) {
-                  warp_flush(brk ? gb : -1, brk ? ga : 0.f);
-                  if (brk) { gb = bk[e]; ga = 0.f; }
+              for (int e = 0; e < 8; ++e) {
+                if (bk[e] != run_bk) {
+                  flush_run(run_bk, run_acc);
+                  run_bk = bk[e];
+                  run_acc = 0.f;
                 }
-                ga += dsv[e];
+                run_acc += dsv[e];
               }
-              run_bk = gb;
-              run_acc = ga;
             }
           }
           // 16-byte chunk of this thread's row slice, 128-byte swizzle
@@ -409,13 +424,14 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
           *reinterpret_cast<uint4*>(dsT + chunk) = make_uint4(dpk[0], dpk[1], dpk[2], dpk[3]);
         }
       }
-      if (HAS_BIAS) warp_flush(run_bk, run_acc);
+      if (HAS_BIAS) flush_run(run_bk, run_acc);
       tc_fence_before();
       fence_proxy_async_smem();                    // st.shared -> visible to the MMA (async proxy)
       __syncwarp();
       if (lane == 0) { mbar_arrive(bar_s_free); mbar_arrive(bar_pds_full); }
       if (HAS_BIAS) {
         named_bar_sync(4, AB_EPI);   // dS^T copy complete; tables of tile it+1 staged
+        if (cached && et == 0 && it + 1 < n_it) load_bkt(it + 1);   // everyone is done with bkt_s
         // d pos_w[N-1+j-i]: thread (x, half) sums diagonal x = r - c + 127 over 64 key rows
         const int x = et & 255, hf = et >> 8;
         if (x < 255) {
@@ -429,7 +445,8 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
           for (int rr = r0; rr < r1; ++rr, ptr += L::DS_STRIDE + 2)
             sum += __uint_as_float((uint32_t) (*reinterpret_cast<const uint16_t*>(ptr)) << 16);
           const int64_t idx = p.N - 1 + j0 - i0 - 127 + x;
-          if (sum != 0.f && idx >= 0 && idx < 2 * p.N - 1) atomicAdd(d_pos_mine + idx, sum);
+          if (sum != 0.f && idx >= 0 && idx < 2 * p.N - 1)
+            atomicAdd(d_pos_mine + idx, sum * half_inv_n);
         }
       }
       if (it > 0) read_back_dq(it - 1);
@@ -445,14 +462,15 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
       uint32_t ov[32];
       tmem_ld32(tmem + lane_base + 256 + 32 * g, ov);
       tmem_ld_wait();
+      const float sc = g < 2 ? inv_n : half_inv_n;   // dV = P'^T dO / N ; dK = dS'^T Q / (2N)
       if (jk < n) {
 #pragma unroll
         for (int v4 = 0; v4 < 4; ++v4) {
           uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 0]), __uint_as_float(ov[v4 * 8 + 1]));
-          o.y = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 2]), __uint_as_float(ov[v4 * 8 + 3]));
-          o.z = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 4]), __uint_as_float(ov[v4 * 8 + 5]));
-          o.w = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 6]), __uint_as_float(ov[v4 * 8 + 7]));
+          o.x = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 0]) * sc, __uint_as_float(ov[v4 * 8 + 1]) * sc);
+          o.y = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 2]) * sc, __uint_as_float(ov[v4 * 8 + 3]) * sc);
+          o.z = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 4]) * sc, __uint_as_float(ov[v4 * 8 + 5]) * sc);
+          o.w = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 6]) * sc, __uint_as_float(ov[v4 * 8 + 7]) * sc);
           *reinterpret_cast<uint4*>(dst + v4 * 8) = o;
         }
       }
@@ -515,6 +533,8 @@ int hstu_attn_bwd_sm100(const grb_hstu_attn_args* a, cudaStream_t st) {
   p.n_kt = (int) ceil_div(a->max_len, AT_BN);
   p.offsets = a->offsets; p.ts = a->timestamps; p.ts_w = a->ts_w; p.pos_w = a->pos_w;
   p.thr = a->bucket_thresholds; p.octaves = a->bucket_octaves;
+  p.bcache = a->timestamps ? a->bucket_cache : nullptr;
+  p.cache_nt = (int) ceil_div(a->bucket_cache_max_len, AT_BM);
   p.dk = reinterpret_cast<__nv_bfloat16*>(a->dk); p.lddk = a->lddk;
   p.dv = reinterpret_cast<__nv_bfloat16*>(a->dv_grad); p.lddv = a->lddv;
   p.dq_accum = a->dq_accum; p.d_ts_w = a->d_ts_w; p.d_pos_w = a->d_pos_w;

@@ -38,6 +38,8 @@ struct AttnFwdParams {
   const float* pos_w;
   const int64_t* thr;
   const uint32_t* octaves;   // optional precomputed octave table
+  const uint8_t* bcache;     // optional bucket-index tiles (hstu_bucket_cache.cu)
+  int cache_nt;              // query tiles per sequence the cache was laid out for
   __nv_bfloat16* out;
   int64_t ldo;
 };
@@ -48,7 +50,8 @@ struct AttnSmem {
   static constexpr int q = 0;                                   // HG x 16 KiB
   static constexpr int kv = q + HG * AT_TILE_BYTES;             // STAGES x (K 16 KiB + V 16 KiB)
   static constexpr int bias = kv + AT_STAGES * 2 * AT_TILE_BYTES;  // 128 x 128 fp16 = 32 KiB
-  static constexpr int tsk = bias + AT_BM * AT_BN * 2;          // 128 x int64
+  static constexpr int bkt = bias + AT_BM * AT_BN * 2;          // 128 x 128 uint8 bucket tile
+  static constexpr int tsk = bkt + AT_BM * AT_BN;               // 128 x int64
   static constexpr int tsk32 = tsk + 128 * 8;                   // 128 x uint32 (ts - tmin)
   static constexpr int red = tsk32 + 128 * 4;                   // 16 x int64 scratch
   static constexpr int pos = red + 16 * 8;                      // 256 x float
@@ -89,12 +92,14 @@ __global__ void __launch_bounds__(AT_THREADS, 1) hstu_attn_fwd_sm100_kernel(
   const uint32_t bar_p_full = smem_u32(bars + 4 + 2 * AT_STAGES);  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * AT_STAGES);
   int* flags = reinterpret_cast<int*>(bars + 7 + 2 * AT_STAGES);   // [0] slow, [1] b_zero
+  const uint32_t bar_bkt = smem_u32(bars + 8 + 2 * AT_STAGES);
 
   if (tid == 0) {
     mbar_init(bar_q, 1);
     mbar_init(bar_o, 1);
     for (int s = 0; s < AT_STAGES; ++s) { mbar_init(bar_kv_full + 8 * s, 1); mbar_init(bar_kv_empty + 8 * s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(bar_s_full + 8 * s, 1); mbar_init(bar_p_full + 8 * s, 4); }
+    mbar_init(bar_bkt, 1);
     fence_barrier_init();
     prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV);
   }
@@ -206,6 +211,18 @@ __global__ void __launch_bounds__(AT_THREADS, 1) hstu_attn_fwd_sm100_kernel(
     };
     if (HAS_BIAS) stage_tables(0);
     const uint32_t half_half = 0x38003800u;        // (0.5h, 0.5h)
+    // cached bucket tiles: slot (qt, j) of this sequence, "Q orientation" half
+    const bool cached = HAS_BIAS && p.bcache != nullptr;
+    const uint8_t* bkt_s = smem + L::bkt;
+    const uint8_t* cache_seq = nullptr;
+    if (cached) {
+      const int64_t tps = (int64_t) p.cache_nt * (p.cache_nt + 1) / 2;
+      cache_seq = p.bcache + ((int64_t) b * tps + (int64_t) qt * (qt + 1) / 2) * 32768;
+      if (tid == 128) {
+        mbar_arrive_expect_tx(bar_bkt, 16384);
+        bulk_load_1d(smem_u32(bkt_s), cache_seq, 16384, bar_bkt);
+      }
+    }
     for (int j = 0; j < n_kt; ++j) {
       if (HAS_BIAS) {
         named_bar_sync(2, 256);                    // previous tile's bias fully consumed; tables visible
@@ -214,7 +231,16 @@ __global__ void __launch_bounds__(AT_THREADS, 1) hstu_attn_fwd_sm100_kernel(
         for (int c8 = 0; c8 < 8; ++c8) {
           const int cb = 64 * g + 8 * c8;
           float v[8];
-          if (narrow) {
+          if (cached) {
+            if (c8 == 0) mbar_wait(bar_bkt, j & 1);
+            // 8 bucket bytes of this row: chunk (cb / 16), bytes (cb % 16) .. +7
+            const uint2 raw = *reinterpret_cast<const uint2*>(
+                bkt_s + ((size_t) (cb >> 4) * 128 + r) * 16 + (cb & 8));
+            const uint32_t w2[2] = {raw.x, raw.y};
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              v[e] = pos_s[cb + e - r + 127] + tsw_s[(w2[e >> 2] >> (8 * (e & 3))) & 0xffu];
+          } else if (narrow) {
             const uint4 ta = *reinterpret_cast<const uint4*>(tsk32_s + cb);
             const uint4 tb = *reinterpret_cast<const uint4*>(tsk32_s + cb + 4);
             const uint32_t tk[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
@@ -236,6 +262,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) hstu_attn_fwd_sm100_kernel(
         }
         named_bar_sync(1, 256);                    // bias tile complete
         if (j + 1 < n_kt) stage_tables(j + 1);     // tables are free again after barrier 1
+        if (cached && tid == 128 && j + 1 < n_kt) {   // so is the bucket tile buffer
+          mbar_arrive_expect_tx(bar_bkt, 16384);
+          bulk_load_1d(smem_u32(bkt_s), cache_seq + (int64_t) (j + 1) * 32768, 16384, bar_bkt);
+        }
       }
       const bool diag = (j == qt);
       for (int hh = g; hh < HG; hh += 2) {
@@ -334,6 +364,8 @@ static int launch_fwd_sm100(const grb_hstu_attn_args* a, cudaStream_t st) {
   p.n_qt = (int) ceil_div(a->max_len, AT_BM);
   p.offsets = a->offsets; p.ts = a->timestamps; p.ts_w = a->ts_w; p.pos_w = a->pos_w;
   p.thr = a->bucket_thresholds; p.octaves = a->bucket_octaves;
+  p.bcache = a->timestamps ? a->bucket_cache : nullptr;
+  p.cache_nt = (int) ceil_div(a->bucket_cache_max_len, AT_BM);
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out); p.ldo = a->ldo;
   const size_t smem = AttnSmem<HG>::total + 1024;
   dim3 grid((unsigned) (p.n_qt * (a->H / HG)), (unsigned) a->B);

@@ -62,6 +62,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(x), "r"(y), "r"(bar)
       : "memory");
 }
+// 1-D bulk copy global -> shared (size multiple of 16 bytes); completes on `bar` (tx bytes)
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst_smem, const void* src, uint32_t bytes,
+                                             uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          dst_smem),
+      "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+      : "memory");
+}
 // same with an L2 cache-policy hint
 __device__ __forceinline__ void tma_load_2d_hint(uint32_t dst_smem, const CUtensorMap* tm, int x,
                                                  int y, uint32_t bar, uint64_t policy) {

@@ -32,7 +32,8 @@ def _rows_contiguous(t: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------
 # fused jagged HSTU attention  (sequential_encoders/hstu.py:96-128 + :134-205)
 # --------------------------------------------------------------------------------------------
-def _attn_args(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk, dv, max_len):
+def _attn_args(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk, dv, max_len,
+               cache=None):
     a = _lib.HstuAttnArgs()
     a.B = offsets.numel() - 1
     a.N = N
@@ -52,6 +53,9 @@ def _attn_args(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk,
         a.bucket_thresholds = thresholds.data_ptr()
         oct_t = bucket_octaves(thresholds)
         a.bucket_octaves = oct_t.data_ptr()
+        if cache is not None:
+            a.bucket_cache = cache.data_ptr()
+            a.bucket_cache_max_len = cache.grb_max_len
     return a
 
 
@@ -74,9 +78,35 @@ def bucket_octaves(thresholds: torch.Tensor) -> torch.Tensor:
     return dev
 
 
+class BucketCache(torch.Tensor):
+    """uint8 tensor holding grb_hstu_bucket_tiles output; remembers the max_len it was built for."""
+    grb_max_len: int = 0
+
+
+def hstu_bucket_cache(offsets: torch.Tensor, timestamps: torch.Tensor, thresholds: torch.Tensor,
+                      N: int, max_len: Optional[int] = None) -> torch.Tensor:
+    """Tabulate bucket(|ts[b, i+1] - ts[b, j]|) for every causal 128x128 tile of every sequence,
+    once per batch (the reference recomputes it per layer, hstu.py:117-123).  Pass the result as
+    ``bucket_cache=`` to :func:`hstu_attention` for all layers, forward and backward."""
+    _lib.require_cuda(offsets, timestamps, thresholds)
+    max_len = N if max_len is None else min(max_len, N)
+    B = offsets.numel() - 1
+    nbytes = int(_lib.lib().grb_hstu_bucket_cache_bytes(B, max_len))
+    cache = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=offsets.device).as_subclass(BucketCache)
+    cache.grb_max_len = max_len
+    timestamps = timestamps.contiguous()
+    offsets = offsets.contiguous()
+    _lib.check(_lib.lib().grb_hstu_bucket_tiles(
+        offsets.data_ptr(), _lib.index_bits(offsets), timestamps.data_ptr(), B, N, max_len,
+        thresholds.data_ptr(), thresholds.numel(), bucket_octaves(thresholds).data_ptr(),
+        cache.data_ptr(), _lib.stream_ptr(offsets.device)))
+    return cache
+
+
 class _HstuAttention(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk, dv, max_len):
+    def forward(ctx, q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk, dv, max_len,
+                cache=None):
         _lib.require_cuda(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds)
         if not (q.dtype == k.dtype == v.dtype):
             raise ValueError("hstu_attention: q, k, v must share a dtype")
@@ -91,12 +121,15 @@ class _HstuAttention(torch.autograd.Function):
             if ts_w.numel() != thresholds.numel() + 1 or pos_w.numel() < 2 * N - 1:
                 raise ValueError("hstu_attention: bias table sizes do not match N / num_buckets")
         out = torch.empty((q.shape[0], H * dv), dtype=q.dtype, device=q.device)
-        a = _attn_args(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk, dv, max_len)
+        if cache is not None and (timestamps is None or cache.grb_max_len != max_len):
+            cache = None
+        a = _attn_args(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk, dv, max_len, cache)
         a.out, a.ldo = out.data_ptr(), H * dv
         with _lib.timed("hstu_attn_fwd"):
             _lib.check(_lib.lib().grb_hstu_attn_fwd(C.byref(a), _lib.stream_ptr(q.device)))
         ctx.save_for_backward(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds)
         ctx.dims = (N, H, dqk, dv, max_len)
+        ctx.cache = cache
         return out
 
     @staticmethod
@@ -109,7 +142,8 @@ class _HstuAttention(torch.autograd.Function):
         dk = torch.empty((T, H * dqk), dtype=q.dtype, device=q.device)
         dvv = torch.empty((T, H * dv), dtype=q.dtype, device=q.device)
         dq_acc = torch.zeros((T, H * dqk), dtype=torch.float32, device=q.device)
-        a = _attn_args(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk, dv, max_len)
+        a = _attn_args(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk, dv, max_len,
+                       ctx.cache)
         a.dout, a.lddo = dout.data_ptr(), _ld(dout)
         a.dq, a.dk, a.dv_grad = dq.data_ptr(), dk.data_ptr(), dvv.data_ptr()
         a.lddq, a.lddk, a.lddv = H * dqk, H * dqk, H * dv
@@ -127,14 +161,15 @@ class _HstuAttention(torch.autograd.Function):
         if d_pos is not None:
             d_pos = d_pos.sum(0) if d_pos.shape[0] > 1 else d_pos[0]
             d_ts = d_ts.sum(0) if d_ts.shape[0] > 1 else d_ts[0]
-        return dq, dk, dvv, None, None, d_ts, d_pos, None, None, None, None, None, None
+        return dq, dk, dvv, None, None, d_ts, d_pos, None, None, None, None, None, None, None
 
 
 def hstu_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, offsets: torch.Tensor,
                    timestamps: Optional[torch.Tensor], ts_w: Optional[torch.Tensor],
                    pos_w: Optional[torch.Tensor], bucket_thresholds: Optional[torch.Tensor],
                    N: int, num_heads: int, attention_dim: int, linear_dim: int,
-                   max_len: Optional[int] = None) -> torch.Tensor:
+                   max_len: Optional[int] = None,
+                   bucket_cache: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Jagged pointwise-SiLU attention with relative time+position bias.
 
     q, k: (T, H*attention_dim); v: (T, H*linear_dim); offsets (B+1); timestamps (B, N) int64 or
@@ -147,7 +182,8 @@ def hstu_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, offsets: t
     if pos_w is not None and pos_w.dtype != torch.float32:
         pos_w = pos_w.float()
     return _HstuAttention.apply(q, k, v, offsets, timestamps, ts_w, pos_w, bucket_thresholds,
-                                N, num_heads, attention_dim, linear_dim, min(max_len, N))
+                                N, num_heads, attention_dim, linear_dim, min(max_len, N),
+                                bucket_cache)
 
 
 # --------------------------------------------------------------------------------------------

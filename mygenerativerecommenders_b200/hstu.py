@@ -154,7 +154,8 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
                 all_timestamps: Optional[torch.Tensor], invalid_attn_mask: torch.Tensor,
                 delta_x_offsets: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
                 cache: Optional[HSTUCacheState] = None,
-                return_cache_states: bool = False):
+                return_cache_states: bool = False,
+                bucket_cache: Optional[torch.Tensor] = None):
         """x: (sum_i N_i, D); x_offsets: (B+1); all_timestamps: (B, N) int64 or None;
         invalid_attn_mask: (N, N) — only its size is read: the kernel applies the causal
         lower-triangular mask that HSTU registers (hstu.py:595-607,667)."""
@@ -188,7 +189,7 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
             bias._ts_w if bias is not None else None,
             bias._pos_w if bias is not None else None,
             bias._bucket_thresholds if bias is not None else None,
-            N=n, num_heads=H, attention_dim=dqk, linear_dim=dv)
+            N=n, num_heads=H, attention_dim=dqk, linear_dim=dv, bucket_cache=bucket_cache)
 
         if self._concat_ua:
             a = self._norm_attn_output(attn_output)
@@ -228,11 +229,21 @@ class HSTUJagged(torch.nn.Module):
         in_dtype = x.dtype
         if self._autocast_dtype is not None and x.dtype != self._autocast_dtype:
             x = x.to(self._autocast_dtype)
+        # the time buckets are the same for every layer, head and direction: tabulate them once
+        # (tcgen05 path only: bf16 activations, 64-wide heads)
+        bucket_cache = None
+        first = self._attention_layers[0] if len(self._attention_layers) else None
+        if (all_timestamps is not None and first is not None and x.dtype == torch.bfloat16
+                and first._attention_dim == 64 and first._linear_dim == 64
+                and isinstance(first._rel_attn_bias, RelativeBucketedTimeAndPositionBasedBias)):
+            bucket_cache = GF.hstu_bucket_cache(x_offsets, all_timestamps,
+                                                first._rel_attn_bias._bucket_thresholds,
+                                                invalid_attn_mask.size(-1))
         for i, layer in enumerate(self._attention_layers):
             x, cs = layer(x=x, x_offsets=x_offsets, all_timestamps=all_timestamps,
                           invalid_attn_mask=invalid_attn_mask, delta_x_offsets=delta_x_offsets,
                           cache=cache[i] if cache is not None else None,
-                          return_cache_states=return_cache_states)
+                          return_cache_states=return_cache_states, bucket_cache=bucket_cache)
             if return_cache_states:
                 cache_states.append(cs)
         if x.dtype != in_dtype:

@@ -264,3 +264,49 @@ def test_attention_backward_bf16_tcgen05_vs_oracle(B, N, H, lengths, with_ts, sc
     names = ("dq", "dk", "dv") + (("d_ts_w", "d_pos_w") if with_ts else ())
     for name, got, r in zip(names, leaves, ref_leaves):
         _close(got.grad, r.grad, 2e-2, 2e-2, what=f"tcgen05 {name}")
+
+
+@pytest.mark.parametrize("B,N,H,lengths,scale_ts", [
+    (3, 400, 4, [400, 129, 257], 1),
+    (2, 300, 2, [300, 77], 100_000),           # buckets through the 64-bit path
+])
+def test_bucket_cache_gives_the_same_forward_and_backward(B, N, H, lengths, scale_ts):
+    d = 64
+    c = _rand_case(5 + N, B, N, H, d, d, lengths)
+    c["ts"] = c["ts"] * scale_ts
+    res = []
+    for use_cache in (False, True):
+        q, k, v = (c[n].to(DEV).to(torch.bfloat16).requires_grad_(True) for n in ("q", "k", "v"))
+        ts_w = c["ts_w"].to(DEV).requires_grad_(True)
+        pos_w = c["pos_w"].to(DEV).requires_grad_(True)
+        off, ts = c["off"].to(DEV), c["ts"].to(DEV)
+        cache = GF.hstu_bucket_cache(off, ts, _thr(), N) if use_cache else None
+        out = GF.hstu_attention(q, k, v, off, ts, ts_w, pos_w, _thr(), N, H, d, d, bucket_cache=cache)
+        out.backward(torch.ones_like(out))
+        res.append((out.detach(), q.grad, k.grad, v.grad, ts_w.grad, pos_w.grad))
+    assert torch.equal(res[0][0], res[1][0])                     # identical buckets -> identical P
+    for a, b_ in zip(res[0][1:4], res[1][1:4]):
+        _close(b_, a, 1e-3, what="cached bwd")                   # dq: fp32 atomics reorder
+    _close(res[1][4], res[0][4], 2e-3, what="cached d_ts_w")
+    _close(res[1][5], res[0][5], 2e-3, what="cached d_pos_w")
+
+
+def test_bucket_cache_contents_match_the_reference_bucketization():
+    B, N = 2, 300
+    c = _rand_case(9, B, N, 2, 64, 64, [300, 140])
+    off, ts = c["off"].to(DEV), c["ts"].to(DEV)
+    cache = GF.hstu_bucket_cache(off, ts, _thr(), N).cpu().view(B, -1, 2, 8, 128, 16)
+    ext = torch.cat([c["ts"], c["ts"][:, N - 1:N]], dim=1)
+    ref = O.bucketize_ts(ext[:, 1:].unsqueeze(2) - ext[:, :-1].unsqueeze(1))     # (B, N, N)
+    for b, n in enumerate([300, 140]):
+        for iq in range((n + 127) // 128):
+            for jk in range(iq + 1):
+                slot = iq * (iq + 1) // 2 + jk
+                # Q orientation: [chunk][row][16] -> (row, col)
+                tile_q = cache[b, slot, 0].permute(1, 0, 2).reshape(128, 128)
+                tile_k = cache[b, slot, 1].permute(1, 0, 2).reshape(128, 128).t()
+                rows = min(128, N - iq * 128)
+                cols = min(128, N - jk * 128)
+                exp = ref[b, iq * 128: iq * 128 + rows, jk * 128: jk * 128 + cols].to(torch.uint8)
+                assert torch.equal(tile_q[:rows, :cols], exp)
+                assert torch.equal(tile_k[:rows, :cols], exp)
