@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
 #pragma unroll
             for (int e = 0; e < 8; ++e) { bk[e] = 0; hb[e] = 0.f; }
           }
-          float dsv[8];
+          float dsv[8], pvv[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int cc = 8 * c8 + e;             // column inside this 16-chunk
@@ -377,22 +377,24 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
             const float th = tanh_approx(hx);
             // unscaled: P' = SiLU(x) = N P ; dS' = dP * 2 SiLU'(x) = 2N dS.  The 1/N and 1/(2N)
             // factors are linear and applied once to dV, dK, dQ and the bias gradients.
-            float pval = fmaf(hx, th, hx);
+            pvv[e] = fmaf(hx, th, hx);
             const float u1 = fmaf(-th, th, 1.0f);                        // 1 - tanh^2
             const float w2 = fmaf(hx, u1, 1.0f + th);                    // 2 * SiLU'(x)
-            float dval = __uint_as_float(dv_[cc]) * w2;
-            if (edge) {
-              const bool ok = (jk <= i0 + c0 + e) && (i0 + c0 + e < n);
-              pval = ok ? pval : 0.f;
-              dval = ok ? dval : 0.f;
+            dsv[e] = __uint_as_float(dv_[cc]) * w2;
+          }
+          if (edge) {   // diagonal / ragged tiles only (warp-uniform): causal and length masks
+            const int lo = jk - i0 - c0, hi = n - i0 - c0;   // valid columns: lo <= e < hi
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const bool ok = (e >= lo) && (e < hi);
+              pvv[e] = ok ? pvv[e] : 0.f;
+              dsv[e] = ok ? dsv[e] : 0.f;
             }
-            dsv[e] = dval;
-            if (e & 1) {
-              ppk[e >> 1] = pack_bf16x2(__uint_as_float(ppk[e >> 1]), pval);
-              dpk[e >> 1] = pack_bf16x2(dsv[e - 1], dval);
-            } else {
-              ppk[e >> 1] = __float_as_uint(pval);
-            }
+          }
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            ppk[e >> 1] = pack_bf16x2(pvv[e], pvv[e + 1]);
+            dpk[e >> 1] = pack_bf16x2(dsv[e], dsv[e + 1]);
           }
           if (HAS_BIAS) {
             // d pos_w needs the sums of dS along the diagonals of the tile: stash a plain copy

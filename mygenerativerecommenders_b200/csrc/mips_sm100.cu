@@ -6,23 +6,33 @@
 // of 128 rows), ordered chunk-major so the CTAs that run concurrently read the SAME item tiles
 // for different query blocks: the item table streams from HBM once and is re-used out of L2.
 //
-//   TMA warp  : Q block [128 x D] (K-major, 64-column 128-byte-swizzled slabs) when the query
-//               block changes; item slabs [128 items x 64] through an 8-stage ring.
-//   MMA warp  : tcgen05.mma M128 N128 K16 x (D/16) per tile into one of 4 TMEM accumulators.
-//   epilogue  : 4 warps, thread = query row: tcgen05.ld the 128 scores of the tile and either
-//               store them (sample pass) or append (score, index) >= tau[row] (filter pass).
+//   TMA warp  : NQB query blocks [128 x D] each (K-major, 64-column 128-byte-swizzled slabs) when
+//               the query-block group changes; item slabs [128 items x 64] through a TMA ring.
+//   MMA warp  : per slab, tcgen05.mma M128 N128 K16 x 4 for EACH of the NQB query blocks, so one
+//               L2 -> smem item slab feeds NQB x 128 queries (L2 traffic, not the tensor pipe, is
+//               the first limit at B = 4096: 32 query blocks x 5.12 GB with one block per CTA).
+//               2 TMEM accumulator sets of NQB x 128 columns.
+//   epilogue  : NQB warpgroups, thread = query row: tcgen05.ld the 128 scores of the tile and
+//               either store them (sample pass) or append (score, index) >= tau[row].
 #include "common.cuh"
 #include "mips_epilogue.cuh"
 #include "sm100_ptx.cuh"
+#include "hstu_attn_sm100.cuh"
 
 namespace grb {
 
 using namespace ptx;
 
-constexpr int MS_THREADS = 192;
-constexpr int MS_STAGES = 8;
 constexpr int MS_SLAB = 128 * 64 * 2;   // 16 KiB: 128 rows x 64 bf16
-constexpr int MS_ACC = 4;
+template <int NQB> struct MsCfg {
+  static constexpr int threads = 64 + 128 * NQB;        // TMA warp, MMA warp, NQB epilogue warpgroups
+  static constexpr int stages = NQB == 1 ? 8 : 6;
+  static constexpr int acc = 4 / NQB;                   // accumulator sets (NQB x 128 columns each)
+  static constexpr int q = 0;                           // NQB x 4 slabs
+  static constexpr int ring = NQB * 4 * MS_SLAB;
+  static constexpr int bars = ring + stages * MS_SLAB;
+  static constexpr int total = bars + 512;
+};
 
 struct MipsSmParams {
   int64_t B, X;
@@ -34,18 +44,14 @@ struct MipsSmParams {
   ScoreEpi epi;
 };
 
-struct MsSmem {
-  static constexpr int q = 0;                          // 4 slabs
-  static constexpr int ring = 4 * MS_SLAB;             // MS_STAGES slabs
-  static constexpr int bars = ring + MS_STAGES * MS_SLAB;
-  static constexpr int total = bars + 512;
-};
-
-__global__ void __launch_bounds__(MS_THREADS, 1) mips_scores_sm100_kernel(
+template <int NQB>
+__global__ void __launch_bounds__(MsCfg<NQB>::threads, 1) mips_scores_sm100_kernel(
     const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmI,
     MipsSmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  using MsSmem = MsCfg<NQB>;
+  constexpr int MS_STAGES = MsSmem::stages, MS_ACC = MsSmem::acc;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MsSmem::bars);
   const uint32_t bar_full = smem_u32(bars);                        // [STAGES]
@@ -58,7 +64,7 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mips_scores_sm100_kernel(
 
   if (tid == 0) {
     for (int s = 0; s < MS_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    for (int s = 0; s < MS_ACC; ++s) { mbar_init(bar_acc_full + 8 * s, 1); mbar_init(bar_acc_empty + 8 * s, 4); }
+    for (int s = 0; s < MS_ACC; ++s) { mbar_init(bar_acc_full + 8 * s, 1); mbar_init(bar_acc_empty + 8 * s, 4 * NQB); }
     mbar_init(bar_q_full, 1);
     mbar_init(bar_q_empty, 1);
     fence_barrier_init();
@@ -81,11 +87,12 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mips_scores_sm100_kernel(
       for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
         const int64_t chunk = w / p.n_qb, qb = w % p.n_qb;
         if (qb != cur_qb) {
-          mbar_wait(bar_q_empty, (q_loads & 1) ^ 1);   // MMAs of the previous Q are done
-          mbar_arrive_expect_tx(bar_q_full, kslabs * MS_SLAB);
-          for (int kc = 0; kc < kslabs; ++kc)
-            tma_load_2d(smem_u32(smem + MsSmem::q + kc * MS_SLAB), &tmQ, kc * 64,
-                        (int) (qb * 128), bar_q_full);
+          mbar_wait_parked(bar_q_empty, (q_loads & 1) ^ 1);   // MMAs of the previous Q are done
+          mbar_arrive_expect_tx(bar_q_full, NQB * kslabs * MS_SLAB);
+          for (int qq = 0; qq < NQB; ++qq)
+            for (int kc = 0; kc < kslabs; ++kc)
+              tma_load_2d(smem_u32(smem + MsSmem::q + (qq * 4 + kc) * MS_SLAB), &tmQ, kc * 64,
+                          (int) ((qb * NQB + qq) * 128), bar_q_full);
           cur_qb = qb;
           ++q_loads;
         }
@@ -95,7 +102,7 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mips_scores_sm100_kernel(
           const int64_t row0 = epi_item_tile(p.epi, u) * MIPS_TILE_N;
           for (int kc = 0; kc < kslabs; ++kc, ++it) {
             const uint32_t st = it % MS_STAGES;
-            mbar_wait(bar_empty + 8 * st, ((it / MS_STAGES) & 1) ^ 1);
+            mbar_wait_parked(bar_empty + 8 * st, ((it / MS_STAGES) & 1) ^ 1);
             mbar_arrive_expect_tx(bar_full + 8 * st, MS_SLAB);
             tma_load_2d(smem_u32(smem + MsSmem::ring + st * MS_SLAB), &tmI, kc * 64, (int) row0,
                         bar_full + 8 * st);
@@ -112,7 +119,7 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mips_scores_sm100_kernel(
         const int64_t chunk = w / p.n_qb, qb = w % p.n_qb;
         if (qb != cur_qb) {
           if (cur_qb >= 0) umma_commit(bar_q_empty);     // all MMAs reading the old Q are issued
-          mbar_wait(bar_q_full, q_loads & 1);
+          mbar_wait_parked(bar_q_full, q_loads & 1);
           tc_fence_after();
           cur_qb = qb;
           ++q_loads;
@@ -121,18 +128,22 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mips_scores_sm100_kernel(
         const int64_t u1 = (u0 + p.chunk < p.n_launch_tiles) ? u0 + p.chunk : p.n_launch_tiles;
         for (int64_t u = u0; u < u1; ++u, ++tile) {
           const uint32_t ab = tile % MS_ACC;
-          mbar_wait(bar_acc_empty + 8 * ab, ((tile / MS_ACC) & 1) ^ 1);
+          mbar_wait_parked(bar_acc_empty + 8 * ab, ((tile / MS_ACC) & 1) ^ 1);
           tc_fence_after();
           for (int kc = 0; kc < kslabs; ++kc, ++it) {
             const uint32_t st = it % MS_STAGES;
-            mbar_wait(bar_full + 8 * st, (it / MS_STAGES) & 1);
+            mbar_wait_parked(bar_full + 8 * st, (it / MS_STAGES) & 1);
             tc_fence_after();
-            const uint32_t qa = smem_u32(smem + MsSmem::q + kc * MS_SLAB);
             const uint32_t ia = smem_u32(smem + MsSmem::ring + st * MS_SLAB);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma_ss(tmem + ab * MIPS_TILE_N, make_smem_desc_sw128(qa + ks * 32, 0, 1024),
-                      make_smem_desc_sw128(ia + ks * 32, 0, 1024), idesc, (kc > 0) || (ks > 0));
+            for (int qq = 0; qq < NQB; ++qq) {
+              const uint32_t qa = smem_u32(smem + MsSmem::q + (qq * 4 + kc) * MS_SLAB);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                umma_ss(tmem + (ab * NQB + qq) * MIPS_TILE_N,
+                        make_smem_desc_sw128(qa + ks * 32, 0, 1024),
+                        make_smem_desc_sw128(ia + ks * 32, 0, 1024), idesc, (kc > 0) || (ks > 0));
+            }
             umma_commit(bar_empty + 8 * st);
           }
           umma_commit(bar_acc_full + 8 * ab);
@@ -140,13 +151,14 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mips_scores_sm100_kernel(
       }
     }
   } else {
-    // epilogue: warps 2..5, TMEM lane quadrant = warp % 4
+    // epilogue: warps 2 .. 2+4*NQB, TMEM lane quadrant = warp % 4, warpgroup = query block
     const int r = ((warp & 3) << 5) | lane;
+    const int qq = (warp - 2) >> 2;
     const uint32_t lane_base = (uint32_t) ((warp & 3) * 32) << 16;
     uint32_t tile = 0;
     for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
       const int64_t chunk = w / p.n_qb, qb = w % p.n_qb;
-      const int64_t row = qb * 128 + r;
+      const int64_t row = (qb * NQB + qq) * 128 + r;
       const bool row_ok = row < p.B;
       const float tau = (p.epi.mode == MIPS_EPI_FILTER && row_ok) ? p.epi.tau[row] : INFINITY;
       const int64_t u0 = chunk * p.chunk;
@@ -159,7 +171,7 @@ __global__ void __launch_bounds__(MS_THREADS, 1) mips_scores_sm100_kernel(
 #pragma unroll 1
         for (int c32 = 0; c32 < 4; ++c32) {
           uint32_t sv[32];
-          tmem_ld32(tmem + lane_base + ab * MIPS_TILE_N + c32 * 32, sv);
+          tmem_ld32(tmem + lane_base + (ab * NQB + qq) * MIPS_TILE_N + c32 * 32, sv);
           tmem_ld_wait();
           if (!row_ok) continue;
           if (p.epi.mode == MIPS_EPI_STORE) {
@@ -231,7 +243,8 @@ int mips_scores_sm100(const grb_mips_topk_args* a, const ScoreEpi& epi, int64_t 
   MipsSmParams p{};
   p.B = a->B; p.X = a->X; p.D = (int) a->D;
   p.n_launch_tiles = n_launch_tiles;
-  p.n_qb = ceil_div(a->B, 128);
+  const int nqb = a->B > 128 ? 2 : 1;     // query blocks per CTA
+  p.n_qb = ceil_div(a->B, 128 * nqb);     // query-block groups
   const int sms = num_sms();
   // ~8 work items per CTA for balance; at most 128 tiles (8 MiB of items) per item
   int64_t chunk = ceil_div(n_launch_tiles * p.n_qb, (int64_t) sms * 8);
@@ -242,10 +255,17 @@ int mips_scores_sm100(const grb_mips_topk_args* a, const ScoreEpi& epi, int64_t 
   p.epi = epi;
   const int64_t n_items = p.n_chunks * p.n_qb;
   const unsigned grid = (unsigned) (n_items < sms ? n_items : sms);
-  const size_t smem = MsSmem::total + 1024;
-  GRB_CUDA_OK(cudaFuncSetAttribute(mips_scores_sm100_kernel,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  mips_scores_sm100_kernel<<<grid, MS_THREADS, smem, st>>>(tmQ, tmI, p);
+  if (nqb == 2) {
+    const size_t smem = MsCfg<2>::total + 1024;
+    GRB_CUDA_OK(cudaFuncSetAttribute(mips_scores_sm100_kernel<2>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    mips_scores_sm100_kernel<2><<<grid, MsCfg<2>::threads, smem, st>>>(tmQ, tmI, p);
+  } else {
+    const size_t smem = MsCfg<1>::total + 1024;
+    GRB_CUDA_OK(cudaFuncSetAttribute(mips_scores_sm100_kernel<1>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    mips_scores_sm100_kernel<1><<<grid, MsCfg<1>::threads, smem, st>>>(tmQ, tmI, p);
+  }
   GRB_LAUNCH_OK();
   return GRB_OK;
 }
