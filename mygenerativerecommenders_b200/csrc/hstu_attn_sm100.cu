@@ -27,7 +27,8 @@ namespace grb {
 using namespace ptx;
 
 constexpr int AT_STAGES = 3;
-constexpr int AT_THREADS = 384;     // warp 0 TMA, warp 1 MMA, warps 2-3 setup, warps 4-11 epilogue
+constexpr int AT_EPI = 512;         // 4 epilogue warpgroups: (S buffer 0/1) x (column half 0/1)
+constexpr int AT_THREADS = 128 + AT_EPI;   // warp 0 TMA, warp 1 MMA, warps 2-3 setup
 
 struct AttnFwdParams {
   int64_t N, T;
@@ -53,8 +54,8 @@ struct AttnSmem {
   static constexpr int bkt = bias + AT_BM * AT_BN * 2;          // 128 x 128 uint8 bucket tile
   static constexpr int tsk = bkt + AT_BM * AT_BN;               // 128 x int64
   static constexpr int tsk32 = tsk + 128 * 8;                   // 128 x uint32 (ts - tmin)
-  static constexpr int red = tsk32 + 128 * 4;                   // 16 x int64 scratch
-  static constexpr int pos = red + 16 * 8;                      // 256 x float
+  static constexpr int red = tsk32 + 128 * 4;                   // 32 x int64 scratch
+  static constexpr int pos = red + 32 * 8;                      // 256 x float
   static constexpr int tsw = pos + 256 * 4;                     // up to 4097 floats -> cap 132
   static constexpr int oct = tsw + 136 * 4;                     // 32 x OctRec
   static constexpr int bars = oct + 32 * 16;                    // barriers
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) hstu_attn_fwd_sm100_kernel(
     mbar_init(bar_q, 1);
     mbar_init(bar_o, 1);
     for (int s = 0; s < AT_STAGES; ++s) { mbar_init(bar_kv_full + 8 * s, 1); mbar_init(bar_kv_empty + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(bar_s_full + 8 * s, 1); mbar_init(bar_p_full + 8 * s, 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_s_full + 8 * s, 1); mbar_init(bar_p_full + 8 * s, 8); }
     mbar_init(bar_bkt, 1);
     fence_barrier_init();
     prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV);
@@ -170,7 +171,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) hstu_attn_fwd_sm100_kernel(
     }
   } else if (warp >= 4) {
     // ================= epilogue warpgroups =================
-    const int g = (warp - 4) >> 2;                 // warpgroup 0 / 1 -> S buffer g, units u = g (mod 2)
+    const int wg = (warp - 4) >> 2;                // 0..3
+    const int g = wg & 1;                          // S buffer: this warpgroup works on units u = g (mod 2)
+    const int ch = wg >> 1;                        // which 64 of the 128 key columns of a unit
     const int r = ((warp & 3) << 5) | lane;        // query row inside the tile = TMEM lane
     const uint32_t lane_base = (uint32_t) ((warp & 3) * 32) << 16;
     const int i = i0 + r;
@@ -188,7 +191,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) hstu_attn_fwd_sm100_kernel(
       ts_q = ext_ts_at(p.ts, b, p.N, (int64_t) i + 1);
       slow = flags[0] != 0;
       const int cnt = (int) (n64 + 1 < p.N ? n64 + 1 : p.N);     // indices 0..min(n, N-1)
-      const TsRange tr = scan_ts_range(p.ts + (int64_t) b * p.N, cnt, tid - 128,
+      const TsRange tr = scan_ts_range<AT_EPI>(p.ts + (int64_t) b * p.N, cnt, tid - 128,
                                        reinterpret_cast<int64_t*>(smem + L::red), 3);
       narrow = tr.narrow && !slow;
       tmin = tr.tmin;
@@ -196,11 +199,11 @@ __global__ void __launch_bounds__(AT_THREADS, 1) hstu_attn_fwd_sm100_kernel(
     }
     auto stage_tables = [&](int j) {   // key timestamps and the pos_w window of key tile j
       const int j0 = j * AT_BN;
-      if (g == 0) {
+      if (wg == 0) {
         const int64_t tk = ext_ts_at(p.ts, b, p.N, (int64_t) j0 + r);
         tsk_s[r] = tk;
         tsk32_s[r] = (uint32_t) (tk - tmin);
-      } else {
+      } else if (wg == 1) {
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           const int x = r + 128 * t;               // pos_s[x] = 0.5 * pos_w[N-1 + j0 - i0 - 127 + x]
@@ -225,11 +228,11 @@ __global__ void __launch_bounds__(AT_THREADS, 1) hstu_attn_fwd_sm100_kernel(
     }
     for (int j = 0; j < n_kt; ++j) {
       if (HAS_BIAS) {
-        named_bar_sync(2, 256);                    // previous tile's bias fully consumed; tables visible
-        // this warpgroup's half of the bias tile: columns [64g, 64g+64), stored pre-halved as fp16
+        named_bar_sync(2, AT_EPI);                 // previous tile's bias fully consumed; tables visible
+        // this warpgroup's quarter of the bias tile: columns [32wg, 32wg+32), pre-halved fp16
 #pragma unroll 2
-        for (int c8 = 0; c8 < 8; ++c8) {
-          const int cb = 64 * g + 8 * c8;
+        for (int c8 = 0; c8 < 4; ++c8) {
+          const int cb = 32 * wg + 8 * c8;
           float v[8];
           if (cached) {
             if (c8 == 0) mbar_wait(bar_bkt, j & 1);
@@ -260,7 +263,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) hstu_attn_fwd_sm100_kernel(
           pk.z = pack_f16x2(v[4], v[5]); pk.w = pack_f16x2(v[6], v[7]);
           *reinterpret_cast<uint4*>(bias_s + ((size_t) (cb >> 3) * 128 + r) * 8) = pk;
         }
-        named_bar_sync(1, 256);                    // bias tile complete
+        named_bar_sync(1, AT_EPI);                 // bias tile complete
         if (j + 1 < n_kt) stage_tables(j + 1);     // tables are free again after barrier 1
         if (cached && tid == 128 && j + 1 < n_kt) {   // so is the bucket tile buffer
           mbar_arrive_expect_tx(bar_bkt, 16384);
@@ -273,12 +276,15 @@ __global__ void __launch_bounds__(AT_THREADS, 1) hstu_attn_fwd_sm100_kernel(
         const uint32_t s_addr = tmem + lane_base + g * 128;
         mbar_wait(bar_s_full + 8 * g, (u >> 1) & 1);
         tc_fence_after();
-#pragma unroll 1
-        for (int c32 = 0; c32 < 4; ++c32) {
+        // P (bf16, 64 TMEM columns) overlays S columns [0, 64).  P chunk c (16 columns) lands on
+        // S chunk c / 2, so: the lower-half warpgroup (S chunks 0, 1) reads chunk 1 FIRST, tells
+        // the upper-half warpgroup, and only then reads chunk 0 and writes P0, P1 (both over S
+        // chunk 0, which only it reads); the upper-half warpgroup (S chunks 2, 3, never
+        // overwritten) waits for that signal before its first P write (P2 lands on S chunk 1).
+        auto compute_chunk = [&](int c32, uint32_t (&pk)[16]) {
           uint32_t sv[32];
           tmem_ld32(s_addr + c32 * 32, sv);
           tmem_ld_wait();
-          uint32_t pk[16];
 #pragma unroll
           for (int c8 = 0; c8 < 4; ++c8) {
             uint4 raw = make_uint4(0u, 0u, 0u, 0u);
@@ -288,21 +294,38 @@ __global__ void __launch_bounds__(AT_THREADS, 1) hstu_attn_fwd_sm100_kernel(
 #pragma unroll
             for (int e2 = 0; e2 < 4; ++e2) {
               const int cc = c8 * 8 + 2 * e2;
-              // h = S/2 + bias/2 ; SiLU(S + bias) = h + h * tanh(h), two elements per instruction
+              // h = S/2 + bias/2 ; SiLU(S + bias) = h + h * tanh(h)
               const uint32_t s2 = pack_f16x2(__uint_as_float(sv[cc]), __uint_as_float(sv[cc + 1]));
               uint32_t h2, p2;
               asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(h2) : "r"(s2), "r"(half_half), "r"(hb[e2]));
               const uint32_t t2 = tanh_approx_f16x2(h2);
               asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(p2) : "r"(h2), "r"(t2));
-              float2 pf = __half22float2(*reinterpret_cast<const __half2*>(&p2));
-              if (diag) {
-                if (c32 * 32 + cc > r) pf.x = 0.f;
-                if (c32 * 32 + cc + 1 > r) pf.y = 0.f;
-              }
+              const float2 pf = __half22float2(*reinterpret_cast<const __half2*>(&p2));
               pk[cc >> 1] = pack_bf16x2(pf.x, pf.y);
             }
           }
-          tmem_st16(s_addr + c32 * 16, pk);        // P aliases S: columns already consumed
+          if (diag) {   // causal mask, diagonal tile only (warp-uniform branch): keep columns <= r
+            const int rel = r - c32 * 32;
+#pragma unroll
+            for (int w = 0; w < 16; ++w)
+              pk[w] &= (2 * w <= rel ? 0x0000ffffu : 0u) | (2 * w + 1 <= rel ? 0xffff0000u : 0u);
+          }
+        };
+        uint32_t pk0[16], pk1[16];
+        if (ch == 0) {
+          compute_chunk(1, pk1);
+          tc_fence_before();
+          asm volatile("bar.arrive %0, 256;" ::"r"(5 + g) : "memory");   // S chunk 1 is consumed
+          compute_chunk(0, pk0);
+          tmem_st16(s_addr + 0, pk0);
+          tmem_st16(s_addr + 16, pk1);
+        } else {
+          compute_chunk(2, pk0);
+          named_bar_sync(5 + g, 256);
+          tc_fence_after();
+          tmem_st16(s_addr + 32, pk0);
+          compute_chunk(3, pk1);
+          tmem_st16(s_addr + 48, pk1);
         }
         tmem_st_wait();
         tc_fence_before();
@@ -316,21 +339,18 @@ __global__ void __launch_bounds__(AT_THREADS, 1) hstu_attn_fwd_sm100_kernel(
     const float inv_n = 1.0f / (float) p.N;
     for (int hh = g; hh < HG; hh += 2) {
       uint32_t ov[32];
-      __nv_bfloat16* dst = p.out + (off0 + i) * p.ldo + (h0 + hh) * AT_D;
+      __nv_bfloat16* dst = p.out + (off0 + i) * p.ldo + (h0 + hh) * AT_D + ch * 32;
+      tmem_ld32(tmem + lane_base + 256 + hh * AT_D + ch * 32, ov);
+      tmem_ld_wait();
+      if (i < n) {
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        tmem_ld32(tmem + lane_base + 256 + hh * AT_D + half * 32, ov);
-        tmem_ld_wait();
-        if (i < n) {
-#pragma unroll
-          for (int v4 = 0; v4 < 4; ++v4) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 0]) * inv_n, __uint_as_float(ov[v4 * 8 + 1]) * inv_n);
-            o.y = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 2]) * inv_n, __uint_as_float(ov[v4 * 8 + 3]) * inv_n);
-            o.z = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 4]) * inv_n, __uint_as_float(ov[v4 * 8 + 5]) * inv_n);
-            o.w = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 6]) * inv_n, __uint_as_float(ov[v4 * 8 + 7]) * inv_n);
-            *reinterpret_cast<uint4*>(dst + half * 32 + v4 * 8) = o;
-          }
+        for (int v4 = 0; v4 < 4; ++v4) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 0]) * inv_n, __uint_as_float(ov[v4 * 8 + 1]) * inv_n);
+          o.y = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 2]) * inv_n, __uint_as_float(ov[v4 * 8 + 3]) * inv_n);
+          o.z = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 4]) * inv_n, __uint_as_float(ov[v4 * 8 + 5]) * inv_n);
+          o.w = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 6]) * inv_n, __uint_as_float(ov[v4 * 8 + 7]) * inv_n);
+          *reinterpret_cast<uint4*>(dst + v4 * 8) = o;
         }
       }
     }
