@@ -161,6 +161,20 @@ def main():
         bench_attn("prof 2x8192 H8 full", 2, 8192, 8, [8192] * 2, bwd=False)
     if "attnbwd" in which:
         bench_attn("prof 1x8192 H4 full", 1, 8192, 4, [8192], bwd=True)
+    if "attnc5" in which:
+        bench_attn("C5-slice 4x8192 H8 full", 4, 8192, 8, [8192] * 4)
+    if "attnnobias" in which:
+        c = attn_case(4, 8192, 8, [8192] * 4)
+        H, d = c["H"], c["d"]
+        q, k, v = (c[n].clone().requires_grad_(True) for n in ("q", "k", "v"))
+        out = GF.hstu_attention(q, k, v, c["off"], None, None, None, None, c["N"], H, d, d)
+        report("hstu_attn_fwd[no-bias 4x8192 H8]", timeit(lambda: GF.hstu_attention(
+            c["q"], c["k"], c["v"], c["off"], None, None, None, None, c["N"], H, d, d), flush=False),
+            flop=c["pairs"] * 2 * H * 2 * d)
+        go = torch.randn_like(out)
+        report("hstu_attn_bwd[no-bias 4x8192 H8]", timeit(lambda: torch.autograd.grad(
+            out, (q, k, v), go, retain_graph=True), iters=5, warmup=2, flush=False),
+            flop=c["pairs"] * 2 * H * 5 * d)
     if want("jagged"):
         bench_jagged()
     if want("ssl"):

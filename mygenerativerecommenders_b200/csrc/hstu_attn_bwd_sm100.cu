@@ -6,20 +6,38 @@
 //   dV = P^T dO ; dK = dS^T Q ; dQ = dS K ; d pos_w[N-1+j-i] += dS ; d ts_w[bucket] += dS
 //
 // One CTA owns (sequence b, head h, key tile j) and walks the query tiles i = j .. last.  Scores
-// are produced TRANSPOSED (thread = key row) so that P^T and dS^T land in shared memory as
-// K-major A operands; the same dS^T tile read MN-major is the A operand of dQ.
+// are produced TRANSPOSED (thread = key row): P^T goes back to TMEM as the A operand of dV, dS^T
+// lands in shared memory as the K-major A operand of dK and, read MN-major, the A operand of dQ.
 //
-//   TMA warp : K_j, V_j once; Q_i, dO_i through a 2-stage ring (128-byte swizzle, jagged rows).
-//   MMA warp : S^T  = K_j Q_i^T   M128 N128 K64   (K-major x K-major)        -> TMEM [0,128)
-//              dP^T = V_j dO_i^T  M128 N128 K64                              -> TMEM [128,256)
-//              dV  += P^T  dO_i   M128 N64  K128  (smem K-major x MN-major)  -> TMEM [256,320)
-//              dK  += dS^T Q_i    M128 N64  K128                             -> TMEM [320,384)
-//              dQ_i = dS   K_j    M128 N64  K128  (MN-major x MN-major)      -> TMEM [384,448)
-//   epilogue : 2 warpgroups, thread = key row, each warpgroup half of the 128 query columns:
-//              bias (integer bucketing), tanh-based SiLU / SiLU', masks, bf16 P^T / dS^T into
-//              swizzled shared memory, bias-gradient partial sums; then dQ_i is read back and
-//              added to the fp32 dq accumulator with vector red.global.
+//   warp 0 (TMA)  : K_j, V_j once; Q_i, dO_i through a 3-stage ring (128-byte swizzle, jagged
+//                   rows); the cached 128x128 bucket-index tile of (i, j), double buffered.
+//   warp 1 (MMA)  : S^T  = K_j Q_i^T   M128 2xN64 K64  (K-major x K-major)        -> TMEM [0,128)
+//                   dP^T = V_j dO_i^T  M128 2xN64 K64                             -> TMEM [128,256)
+//                   dV  += P^T  dO_i   M128 N64  K128  (TMEM A x MN-major)        -> TMEM [256,320)
+//                   dK  += dS^T Q_i    M128 N64  K128  (smem K-major x MN-major)  -> TMEM [320,384)
+//                   dQ_i = dS   K_j    M128 N64  K128  (MN-major x MN-major)      -> TMEM [384,448)
+//                   (P^T as packed bf16 lives in TMEM [448,512))
+//   warp 2        : stages the pos_w window of each query tile (double buffered, mbarriers)
+//   epilogue      : 4 warpgroups, thread = key row: bias, tanh-based SiLU / SiLU', masks, bf16
+//                   P^T / dS^T, bias-gradient partial sums; then dQ_i is read back and added to
+//                   the fp32 dq accumulator with vector red.global.  No CTA-wide barrier inside
+//                   the tile loop when the bucket cache is used: every hand-off is an mbarrier.
+//
+// Half-tile software pipeline: a query tile is processed as two halves of 64 query columns
+// (warpgroup g owns columns 64*hf + 16g .. +16 of half hf).  Every buffer is naturally split the
+// same way (S^T / dP^T / P^T column ranges in TMEM, the two 64-column blocks of dS^T in shared
+// memory), so while the epilogue works on half B the tensor core already runs dV/dK of half A and
+// the scores of the next tile's half A: neither side waits for a whole tile of the other.
+//
+// Bias gradients without shared-memory atomics:
+//   d ts_w : each thread run-length accumulates along its row (the bucket changes rarely along a
+//            row); a finished run is parked and reduced across the warp once per tile.
+//   d pos_w: the 32x32 block of dS^T a warp owns is summed along its diagonals with lane
+//            rotations: lane L collects diagonal r - c = L (and L - 32), 16 shuffles of packed
+//            bf16 pairs per tile, then two red.global per thread.
 #include "hstu_attn_sm100.cuh"
+#include <cstdlib>
+#include <cstdio>
 
 namespace grb {
 
@@ -28,6 +46,7 @@ using namespace ptx;
 constexpr int AB_NWG = 4;                       // epilogue warpgroups: 32 query columns each
 constexpr int AB_EPI = AB_NWG * 128;
 constexpr int AB_THREADS = 128 + AB_EPI;
+constexpr int AB_RING = 3;                      // (Q, dO) stages
 
 struct AttnBwdParams {
   int64_t N, T;
@@ -45,35 +64,40 @@ struct AttnBwdParams {
   float* dq_accum;          // (T, H*64) fp32, zero-filled by the caller
   float* d_ts_w; float* d_pos_w;
   int d_bias_copies;
+  int dbg;
+  long long* tl;            // timeline buffer (GRB_BWD_DEBUG=8)
 };
 
 struct AbSmem {
   static constexpr int k = 0;
   static constexpr int v = k + AT_TILE_BYTES;
-  static constexpr int ring = v + AT_TILE_BYTES;                 // 2 x (Q, dO)
-  static constexpr int pT = ring + 4 * AT_TILE_BYTES;            // 2 blocks [128 k][64 q]
-  static constexpr int dsT = pT + 2 * AT_TILE_BYTES;
-  // query-side tables are double buffered by tile parity: one named barrier per tile orders
-  // staging against use
-  static constexpr int tsq = dsT + 2 * AT_TILE_BYTES;            // 2 x 128 x int64
+  static constexpr int ring = v + AT_TILE_BYTES;                 // AB_RING x (Q, dO)
+  // dS^T as [128 k][64 q] blocks: block A (query columns 0..63) double buffered by tile parity,
+  // then block B.  dQ of a tile is issued late and reads both, so the next tile's half A must
+  // not land in the buffer dQ is still reading.
+  static constexpr int dsT = ring + AB_RING * 2 * AT_TILE_BYTES;
+  static constexpr int bkt = dsT + 3 * AT_TILE_BYTES;            // 2 x 128 x 128 uint8 bucket tiles
+  // query-side tables are double buffered by tile parity
+  static constexpr int tsq = bkt + 2 * 128 * 128;                // 2 x 128 x int64
   static constexpr int tsq32 = tsq + 2 * 128 * 8;                // 2 x 128 x uint32
   static constexpr int red = tsq32 + 2 * 128 * 4;                // 2 x 16 x int64
   static constexpr int pos = red + 32 * 8;                       // 2 x 256 x float (pre-halved)
   static constexpr int tsw = pos + 2 * 256 * 4;                  // 136 x float (pre-halved)
   static constexpr int oct = tsw + 136 * 4;                      // 32 x OctRec
   static constexpr int h_ts = oct + 32 * 16;                     // 16 warps x 136 x float
-  // plain (unswizzled) bf16 copy of dS^T [128 key rows][128 query cols], row stride 272 B: the
-  // d pos_w diagonal sums read it after the tile barrier
-  static constexpr int ds_plain = h_ts + 16 * 136 * 4;
-  static constexpr int DS_STRIDE = 272;
-  static constexpr int bkt = ds_plain + 128 * DS_STRIDE;       // 128 x 128 uint8 bucket tile
-  static constexpr int bars = bkt + 128 * 128;
-  static constexpr int total = bars + 256;
+  static constexpr int bars = h_ts + 16 * 136 * 4;
+  static constexpr int total = bars + 256;   // 27 barrier / scratch words
 };
+static_assert(AbSmem::total + 1024 <= 232448, "shared memory budget");
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
                "f"(d)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3])
                : "memory");
 }
 
@@ -86,9 +110,10 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   using L = AbSmem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int kt = (int) blockIdx.x;                 // key tile: early tiles have the most work
-  const int h = blockIdx.y;
-  const int b = blockIdx.z;
+  const int kt = (int) blockIdx.z;                 // key tile, slowest grid index: the tiles with the most work start first
+  const bool TLOG = (p.dbg & 8) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  const int h = blockIdx.x;
+  const int b = blockIdx.y;
   const int64_t off0 = load_index(p.offsets, b, p.index_bits);
   int64_t n64 = load_index(p.offsets, b + 1, p.index_bits) - off0;
   if (n64 > p.N) n64 = p.N;
@@ -97,33 +122,41 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
   if (j0 >= n) return;
   const int n_qt = (n + AT_BM - 1) / AT_BM;
   const int n_it = n_qt - kt;                      // query tiles kt .. n_qt-1
+  const bool cached = HAS_BIAS && p.bcache != nullptr;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bars);
   const uint32_t bar_kv = smem_u32(bars + 0);
-  const uint32_t bar_ring_full = smem_u32(bars + 1);    // [2]
-  const uint32_t bar_ring_empty = smem_u32(bars + 3);   // [2]
-  const uint32_t bar_s_full = smem_u32(bars + 5);
-  const uint32_t bar_s_free = smem_u32(bars + 6);
-  const uint32_t bar_pds_full = smem_u32(bars + 7);
-  const uint32_t bar_pds_free = smem_u32(bars + 8);
-  const uint32_t bar_dq_full = smem_u32(bars + 9);
-  const uint32_t bar_dq_free = smem_u32(bars + 10);
-  const uint32_t bar_dkv = smem_u32(bars + 11);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-  int* flags = reinterpret_cast<int*>(bars + 13);
-  const uint32_t bar_bkt = smem_u32(bars + 14);
+  const uint32_t bar_ring_full = smem_u32(bars + 1);    // [3]
+  const uint32_t bar_ring_empty = smem_u32(bars + 4);   // [3]
+  const uint32_t bar_s_full = smem_u32(bars + 7);       // [2] scores of half hf are in TMEM
+  const uint32_t bar_half_done = smem_u32(bars + 24);   // [2] half hf: S^T/dP^T read, P^T/dS^T written
+  const uint32_t bar_pds_free = smem_u32(bars + 10);    // MMAs reading P^T / dS^T of a tile are done
+  const uint32_t bar_a_free = smem_u32(bars + 26);      // dV / dK of half A (reads P^T half A) are done
+  const uint32_t bar_dq_full = smem_u32(bars + 11);
+  const uint32_t bar_dq_free = smem_u32(bars + 12);
+  const uint32_t bar_dkv = smem_u32(bars + 13);
+  const uint32_t bar_bkt_full = smem_u32(bars + 14);    // [2]
+  const uint32_t bar_bkt_free = smem_u32(bars + 16);    // [2]
+  const uint32_t bar_tab_full = smem_u32(bars + 18);    // [2]
+  const uint32_t bar_tab_free = smem_u32(bars + 20);    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  int* flags = reinterpret_cast<int*>(bars + 23);
 
   if (tid == 0) {
     mbar_init(bar_kv, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(bar_ring_full + 8 * s, 1); mbar_init(bar_ring_empty + 8 * s, 1); }
-    mbar_init(bar_s_full, 1);
-    mbar_init(bar_s_free, AB_EPI / 32);
-    mbar_init(bar_pds_full, AB_EPI / 32);
+    for (int s = 0; s < AB_RING; ++s) { mbar_init(bar_ring_full + 8 * s, 1); mbar_init(bar_ring_empty + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_s_full + 8 * s, 1); mbar_init(bar_half_done + 8 * s, AB_EPI / 32); }
     mbar_init(bar_pds_free, 1);
+    mbar_init(bar_a_free, 1);
     mbar_init(bar_dq_full, 1);
     mbar_init(bar_dq_free, AB_EPI / 32);
     mbar_init(bar_dkv, 1);
-    mbar_init(bar_bkt, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_bkt_full + 8 * s, 1);
+      mbar_init(bar_bkt_free + 8 * s, AB_EPI / 32);
+      mbar_init(bar_tab_full + 8 * s, 1);
+      mbar_init(bar_tab_free + 8 * s, AB_EPI / 32);
+    }
     fence_barrier_init();
     prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV);
     prefetch_tensormap(&tmdO);
@@ -150,9 +183,18 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
       mbar_arrive_expect_tx(bar_kv, 2 * AT_TILE_BYTES);
       tma_load_2d(smem_u32(smem + L::k), &tmK, h * AT_D, (int) (off0 + j0), bar_kv);
       tma_load_2d(smem_u32(smem + L::v), &tmV, h * AT_D, (int) (off0 + j0), bar_kv);
+      const int64_t tps = (int64_t) p.cache_nt * (p.cache_nt + 1) / 2;
       for (int it = 0; it < n_it; ++it) {
-        const int st = it & 1;
-        mbar_wait_parked(bar_ring_empty + 8 * st, ((it >> 1) & 1) ^ 1);
+        if (cached) {   // bucket tile of (query tile kt + it, key tile kt), "K orientation" half
+          const int sb = it & 1;
+          mbar_wait_parked(bar_bkt_free + 8 * sb, ((it >> 1) & 1) ^ 1);
+          const int64_t iq = kt + it;
+          const uint8_t* src = p.bcache + ((int64_t) b * tps + iq * (iq + 1) / 2 + kt) * 32768 + 16384;
+          mbar_arrive_expect_tx(bar_bkt_full + 8 * sb, 16384);
+          bulk_load_1d(smem_u32(smem + L::bkt + sb * 16384), src, 16384, bar_bkt_full + 8 * sb);
+        }
+        const int st = it % AB_RING;
+        mbar_wait_parked(bar_ring_empty + 8 * st, ((it / AB_RING) & 1) ^ 1);
         mbar_arrive_expect_tx(bar_ring_full + 8 * st, 2 * AT_TILE_BYTES);
         const uint32_t dst = smem_u32(smem + L::ring + st * 2 * AT_TILE_BYTES);
         const int row = (int) (off0 + (kt + it) * AT_BM);
@@ -162,60 +204,105 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      const uint32_t id_kk = make_idesc_bf16(128, 128, false, false);   // S^T, dP^T
+    {   // whole warp, uniform control flow; one elected lane issues (umma_*_warp)
+      const uint32_t id_kk = make_idesc_bf16(128, 64, false, false);    // S^T, dP^T halves
       const uint32_t id_kmn = make_idesc_bf16(128, AT_D, false, true);  // dV, dK
       const uint32_t id_mnmn = make_idesc_bf16(128, AT_D, true, true);  // dQ
-      const uint32_t ka = smem_u32(smem + L::k), va = smem_u32(smem + L::v);
-      const uint32_t pa = smem_u32(smem + L::pT), da = smem_u32(smem + L::dsT);
-      auto issue_scores = [&](int it) {
-        const int st = it & 1;
-        mbar_wait_parked(bar_ring_full + 8 * st, (it >> 1) & 1);
-        tc_fence_after();
-        const uint32_t qa = smem_u32(smem + L::ring + st * 2 * AT_TILE_BYTES);
-        const uint32_t oa = qa + AT_TILE_BYTES;
+      // descriptors are built once; stepping an operand is an add on the address field
+      const uint64_t k_desc = make_smem_desc_sw128(smem_u32(smem + L::k), 0, 1024);
+      const uint64_t v_desc = make_smem_desc_sw128(smem_u32(smem + L::v), 0, 1024);
+      const uint64_t ds_k_desc = make_smem_desc_sw128(smem_u32(smem + L::dsT), 0, 1024);
+      // dQ reads block A [parity] and block B as one MN-major operand: LBO = distance between them
+      const uint64_t ds_mn_desc0 = make_smem_desc_sw128(smem_u32(smem + L::dsT), 2 * AT_TILE_BYTES, 1024);
+      const uint64_t ds_mn_desc1 =
+          make_smem_desc_sw128(smem_u32(smem + L::dsT) + AT_TILE_BYTES, AT_TILE_BYTES, 1024);
+      const uint64_t ring_desc = make_smem_desc_sw128(smem_u32(smem + L::ring), 0, 1024);
+      auto adv = [](uint64_t d, uint32_t bytes) { return d + (uint64_t) (bytes >> 4); };
+      // scores of query columns 64*hf .. +64 of tile it (ring stage already resident)
+      auto issue_scores = [&](int it, int hf) {
+        const uint64_t q_desc = adv(ring_desc, (it % AB_RING) * 2 * AT_TILE_BYTES + hf * 8192);
+        const uint64_t o_desc = adv(q_desc, AT_TILE_BYTES);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
-          umma_ss(tmem, make_smem_desc_sw128(ka + ks * 32, 0, 1024),
-                  make_smem_desc_sw128(qa + ks * 32, 0, 1024), id_kk, ks > 0);
+          umma_ss_warp(tmem + 64 * hf, adv(k_desc, ks * 32), adv(q_desc, ks * 32), id_kk, ks > 0);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
-          umma_ss(tmem + 128, make_smem_desc_sw128(va + ks * 32, 0, 1024),
-                  make_smem_desc_sw128(oa + ks * 32, 0, 1024), id_kk, ks > 0);
-        umma_commit(bar_s_full);
+          umma_ss_warp(tmem + 128 + 64 * hf, adv(v_desc, ks * 32), adv(o_desc, ks * 32), id_kk, ks > 0);
+        umma_commit_warp(bar_s_full + 8 * hf);
+      };
+      // dV += P_hf^T dO_hf ; dK += dS_hf^T Q_hf  (K = the 64 query rows of half hf)
+      auto issue_dvdk = [&](int it, int hf) {
+        const uint64_t q_desc = adv(ring_desc, (it % AB_RING) * 2 * AT_TILE_BYTES);
+        const uint64_t o_desc = adv(q_desc, AT_TILE_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)   // A = packed bf16 P^T in TMEM, B = dO MN-major
+          umma_ts_warp(tmem + 256, tmem + 448 + 32 * hf + ks * 8, adv(o_desc, (4 * hf + ks) * 2048), id_kmn,
+                  (it > 0) || (hf > 0) || (ks > 0));
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)   // A = dS^T block hf K-major, B = Q MN-major
+          umma_ss_warp(tmem + 320, adv(ds_k_desc, (hf ? 2 : (it & 1)) * AT_TILE_BYTES + ks * 32),
+                  adv(q_desc, (4 * hf + ks) * 2048), id_kmn, (it > 0) || (hf > 0) || (ks > 0));
       };
       mbar_wait_parked(bar_kv, 0);
-      issue_scores(0);
+      mbar_wait_parked(bar_ring_full, 0);
+      tc_fence_after();
+      issue_scores(0, 0);
+      issue_scores(0, 1);
       for (int it = 0; it < n_it; ++it) {
-        const int st = it & 1;
-        mbar_wait_parked(bar_s_free, it & 1);             // epilogue has read S^T / dP^T(it)
-        if (it + 1 < n_it) issue_scores(it + 1);
-        mbar_wait_parked(bar_pds_full, it & 1);           // P^T / dS^T(it) are in shared memory
-        if (it > 0) mbar_wait_parked(bar_dq_free, (it - 1) & 1);
+        const int st = it % AB_RING;
+        const bool more = it + 1 < n_it;
+        mbar_wait_parked(bar_half_done, it & 1);          // half A of tile it
+        if (TLOG && lane == 0 && it < 16) p.tl[it * 16 + 0] = clock64();
         tc_fence_after();
-        const uint32_t qa = smem_u32(smem + L::ring + st * 2 * AT_TILE_BYTES);
-        const uint32_t oa = qa + AT_TILE_BYTES;
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks)   // dV += P^T dO_i : A K-major (2 blocks), B = dO MN-major
-          umma_ss(tmem + 256, make_smem_desc_sw128(pa + (ks >> 2) * AT_TILE_BYTES + (ks & 3) * 32, 0, 1024),
-                  make_smem_desc_sw128(oa + ks * 2048, 0, 1024), id_kmn, (it > 0) || (ks > 0));
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks)   // dK += dS^T Q_i
-          umma_ss(tmem + 320, make_smem_desc_sw128(da + (ks >> 2) * AT_TILE_BYTES + (ks & 3) * 32, 0, 1024),
-                  make_smem_desc_sw128(qa + ks * 2048, 0, 1024), id_kmn, (it > 0) || (ks > 0));
+        issue_dvdk(it, 0);
+        umma_commit_warp(bar_a_free);
+        if (more) {
+          mbar_wait_parked(bar_ring_full + 8 * ((it + 1) % AB_RING), ((it + 1) / AB_RING) & 1);
+          tc_fence_after();
+          issue_scores(it + 1, 0);
+        }
+        if (TLOG && lane == 0 && it < 16) p.tl[it * 16 + 1] = clock64();
+        mbar_wait_parked(bar_half_done + 8, it & 1);      // half B of tile it
+        if (TLOG && lane == 0 && it < 16) p.tl[it * 16 + 2] = clock64();
+        if (it > 0 && !(p.dbg & 4)) mbar_wait_parked(bar_dq_free, (it - 1) & 1);
+        if (TLOG && lane == 0 && it < 16) p.tl[it * 16 + 3] = clock64();
+        tc_fence_after();
+        issue_dvdk(it, 1);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)   // dQ_i = dS K_j : A = dS^T read MN-major, B = K MN-major
-          umma_ss(tmem + 384, make_smem_desc_sw128(da + ks * 2048, AT_TILE_BYTES, 1024),
-                  make_smem_desc_sw128(ka + ks * 2048, 0, 1024), id_mnmn, ks > 0);
-        umma_commit(bar_pds_free);
-        umma_commit(bar_dq_full);
-        umma_commit(bar_ring_empty + 8 * st);
+          umma_ss_warp(tmem + 384, adv((it & 1) ? ds_mn_desc1 : ds_mn_desc0, ks * 2048), adv(k_desc, ks * 2048),
+                  id_mnmn, ks > 0);
+        umma_commit_warp(bar_pds_free);
+        umma_commit_warp(bar_dq_full);
+        umma_commit_warp(bar_ring_empty + 8 * st);
+        if (more) issue_scores(it + 1, 1);
+        if (TLOG && lane == 0 && it < 16) p.tl[it * 16 + 4] = clock64();
       }
-      umma_commit(bar_dkv);
+      umma_commit_warp(bar_dkv);
+    }
+  } else if (warp == 2) {
+    // ================= pos_w window stager =================
+    if (HAS_BIAS) {
+      float* pos_all = reinterpret_cast<float*>(smem + L::pos);
+      for (int it = 0; it < n_it; ++it) {
+        const int pb = it & 1;
+        const int i0 = (kt + it) * AT_BM;
+        float vals[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {              // pos[x] = 0.5 * pos_w[N-1 + j0 - i0 - 127 + x]
+          const int64_t idx = p.N - 1 + j0 - i0 - 127 + (lane + 32 * t);
+          vals[t] = (idx >= 0 && idx < 2 * p.N - 1) ? 0.5f * p.pos_w[idx] : 0.f;
+        }
+        mbar_wait_parked(bar_tab_free + 8 * pb, ((it >> 1) & 1) ^ 1);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) pos_all[pb * 256 + lane + 32 * t] = vals[t];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tab_full + 8 * pb);
+      }
     }
   } else if (warp >= 4) {
     // ================= epilogue warpgroups =================
-    const int g = (warp - 4) >> 2;                 // warpgroup: query columns [32g, 32g+32)
+    const int g = (warp - 4) >> 2;                 // warpgroup: query columns 64*hf + [16g, 16g+16)
     const int r = ((warp & 3) << 5) | lane;        // key row inside the tile = TMEM lane
     const int wq = warp - 4;
     const int et = tid - 128;                      // 0 .. AB_EPI-1
@@ -223,15 +310,13 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
     const int jk = j0 + r;                         // key position in the sequence
     int64_t* tsq_all = reinterpret_cast<int64_t*>(smem + L::tsq);
     uint32_t* tsq32_all = reinterpret_cast<uint32_t*>(smem + L::tsq32);
-    float* pos_all = reinterpret_cast<float*>(smem + L::pos);
+    const float* pos_all = reinterpret_cast<const float*>(smem + L::pos);
     const float* tsw_s = reinterpret_cast<const float*>(smem + L::tsw);
     const OctRec* oct = reinterpret_cast<const OctRec*>(smem + L::oct);
     float* h_ts = reinterpret_cast<float*>(smem + L::h_ts) + wq * 136;   // this warp's d ts_w
-    // this thread's 64-byte slice (4 x 16-byte chunks) of its 128-byte row in block g / 2
-    uint8_t* pT = smem + L::pT + (g >> 1) * AT_TILE_BYTES + r * 128;
-    uint8_t* dsT = smem + L::dsT + (g >> 1) * AT_TILE_BYTES + r * 128;
-    const int chunk0 = (g & 1) * 4;
-    uint8_t* ds_plain = smem + L::ds_plain;
+    // this thread's 32-byte slice (2 x 16-byte chunks) of its 128-byte row, in block hf
+    uint8_t* dsT = smem + L::dsT + r * 128;
+    const int chunk0 = 2 * g;
     const float inv_n = 1.0f / (float) p.N;
     const float half_inv_n = 0.5f * inv_n;
     // this CTA's private copies of d pos_w / d ts_w (the caller sums the copies)
@@ -243,7 +328,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
     uint32_t tk32 = 0;
     bool slow = false, narrow = false;
     int64_t tmin = 0;
-    if (HAS_BIAS) {
+    if (HAS_BIAS && !cached) {
       ts_k = ext_ts_at(p.ts, b, p.N, (int64_t) jk);
       slow = flags[0] != 0;
       const int cnt = (int) (n64 + 1 < p.N ? n64 + 1 : p.N);
@@ -273,68 +358,80 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_dq_free);
     };
-    // query-side tables of tile `it` (ext_ts[i0 + c + 1] and the pos_w window) into buffer it & 1
-    auto stage_tables = [&](int it) {
-      const int i0 = (kt + it) * AT_BM;
-      const int pb = it & 1;
+    // Without the bucket cache the query-side timestamps of tile `it` (ext_ts[i0 + c + 1]) are
+    // staged by warpgroup 0 into buffer it & 1: global loads a tile ahead (stage_fetch), stores at
+    // the end of the tile (stage_commit), one named barrier per tile orders them against use.
+    int64_t st_a = 0;
+    auto stage_fetch = [&](int it) {
+      if (g == 0) st_a = ext_ts_at(p.ts, b, p.N, (int64_t) (kt + it) * AT_BM + r + 1);
+    };
+    auto stage_commit = [&](int it) {
       if (g == 0) {
-        const int64_t tq = ext_ts_at(p.ts, b, p.N, (int64_t) i0 + r + 1);
-        tsq_all[pb * 128 + r] = tq;
-        tsq32_all[pb * 128 + r] = (uint32_t) (tq - tmin);
-      } else if (g == 1) {
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const int x = r + 128 * t;               // pos[x] = 0.5 * pos_w[N-1 + j0 - i0 - 127 + x]
-          const int64_t idx = p.N - 1 + j0 - i0 - 127 + x;
-          pos_all[pb * 256 + x] = (idx >= 0 && idx < 2 * p.N - 1) ? 0.5f * p.pos_w[idx] : 0.f;
-        }
+        tsq_all[(it & 1) * 128 + r] = st_a;
+        tsq32_all[(it & 1) * 128 + r] = (uint32_t) (st_a - tmin);
       }
     };
-    // d ts_w: each thread run-length accumulates along its row (buckets change rarely along a
-    // row) and adds a finished run to its warp's private histogram.  Shared memory has no native
-    // fp32 add (atomicAdd is a CAS loop), but a run ends only a few times per row and only lanes
-    // of one warp can collide here, so the loop almost never retries.
+    // d ts_w: a finished run goes to this warp's private histogram.  Shared memory has no native
+    // fp32 add (atomicAdd is a CAS loop); this path only runs when a row crosses two bucket
+    // boundaries inside one tile.
     auto flush_run = [&](int bk, float val) {
       if (bk >= 0 && val != 0.f) atomicAdd(&h_ts[bk], val * half_inv_n);
     };
-
-    // cached bucket tiles: slot (kt + it, kt) of this sequence, "K orientation" half
-    const bool cached = HAS_BIAS && p.bcache != nullptr;
-    const uint8_t* bkt_s = smem + L::bkt;
-    auto load_bkt = [&](int it) {
-      const int64_t tps = (int64_t) p.cache_nt * (p.cache_nt + 1) / 2;
-      const int64_t iq = kt + it;
-      const uint8_t* src = p.bcache + ((int64_t) b * tps + iq * (iq + 1) / 2 + kt) * 32768 + 16384;
-      mbar_arrive_expect_tx(bar_bkt, 16384);
-      bulk_load_1d(smem_u32(bkt_s), src, 16384, bar_bkt);
+    // adds (bucket, value) of every lane to the warp-private histogram: one shuffle reduction per
+    // distinct bucket, then a plain update by lane 0.  Must be called by the whole warp.
+    auto warp_flush = [&](int bk, float val) {
+      unsigned todo = __ballot_sync(0xffffffffu, bk >= 0);
+      while (todo) {
+        const int bsel = __shfl_sync(0xffffffffu, bk, __ffs(todo) - 1);
+        const bool mine = bk == bsel;
+        const float v = warp_sum(mine ? val : 0.f);
+        if (lane == 0) h_ts[bsel] += v * half_inv_n;
+        todo &= ~__ballot_sync(0xffffffffu, mine);
+      }
+      __syncwarp();
     };
-    if (HAS_BIAS) {
-      if (cached && et == 0) load_bkt(0);
-      stage_tables(0);
+
+    if (HAS_BIAS && !cached) {
+      stage_fetch(0);
+      stage_commit(0);
       named_bar_sync(2, AB_EPI);
     }
+    // d ts_w run state: carried across query tiles (the row continues to the right, where the
+    // bucket is usually still the same), flushed once after the last tile
+    int run_bk = -1, pend_bk = -1;
+    float run_acc = 0.f, pend_acc = 0.f;
     for (int it = 0; it < n_it; ++it) {
       const int i0 = (kt + it) * AT_BM;
       const int pb = it & 1;
-      if (HAS_BIAS && it + 1 < n_it) stage_tables(it + 1);   // ordered by this tile's barrier 4
+      if (HAS_BIAS && !cached && it + 1 < n_it) stage_fetch(it + 1);
       const int64_t* tsq_s = tsq_all + pb * 128;
       const uint32_t* tsq32_s = tsq32_all + pb * 128;
       const float* pos_s = pos_all + pb * 256;
+      const uint8_t* bkt_s = smem + L::bkt + pb * 16384;
       const bool edge = (it == 0) || (i0 + AT_BM > n);   // diagonal tile or ragged last tile
-      mbar_wait(bar_s_full, it & 1);
-      tc_fence_after();
-      if (HAS_BIAS && it > 0) named_bar_sync(5, AB_EPI);   // diagonal sums of tile it-1 are done
-      if (cached) mbar_wait(bar_bkt, it & 1);
-      int run_bk = -1;            // d ts_w: run-length accumulate along the row
-      float run_acc = 0.f;
+      if (TLOG && et == 0 && it < 16) p.tl[it * 16 + 8] = clock64();
 #pragma unroll 1
-      for (int c16 = 0; c16 < 2; ++c16) {
-        const int cb = 32 * g + 16 * c16;
+      for (int hf = 0; hf < 2; ++hf) {
+        const int cb = 64 * hf + 16 * g;           // first query column of this thread's chunk
+        mbar_wait(bar_s_full + 8 * hf, it & 1);
+        tc_fence_after();
+        if (hf == 0) {
+          if (HAS_BIAS) mbar_wait(bar_tab_full + 8 * pb, (it >> 1) & 1);
+          if (cached) mbar_wait(bar_bkt_full + 8 * pb, (it >> 1) & 1);
+        }
+        if (TLOG && et == 0 && it < 16) p.tl[it * 16 + 9 + 3 * hf] = clock64();
         uint32_t sv[16], dv_[16];
         tmem_ld16(tmem + lane_base + cb, sv);
         tmem_ld16(tmem + lane_base + 128 + cb, dv_);
         tmem_ld_wait();
-        if (c16 == 0 && it > 0) mbar_wait(bar_pds_free, (it - 1) & 1);   // smem tiles reusable
+        if (it > 0) {   // the MMAs that read the buffers this half is about to overwrite
+          if (hf == 0) mbar_wait(bar_a_free, (it - 1) & 1);     // P^T half A (dV of half A, tile it-1)
+          else mbar_wait(bar_pds_free, (it - 1) & 1);           // P^T half B, dS^T block B; and block A
+        }                                                       // of this parity two tiles ago
+        if (TLOG && et == 0 && it < 16) p.tl[it * 16 + 10 + 3 * hf] = clock64();
+        // d pos_w partial sums of this warp's 32x16 block: diagonal r - c = lane (am, bm -> lane - 1)
+        // and lane - 32 (aw, bw -> lane - 33); a* take the even column of a pair, b* the odd one
+        float am = 0.f, aw = 0.f, bm = 0.f, bw = 0.f;
 #pragma unroll
         for (int c8 = 0; c8 < 2; ++c8) {
           uint32_t ppk[4], dpk[4];
@@ -345,7 +442,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
             if (cached) {
               // 8 bucket bytes of this key row: query chunk (c0 / 16), bytes (c0 % 16) .. +7
               const uint2 raw = *reinterpret_cast<const uint2*>(
-                  bkt_s + ((size_t) (c0 >> 4) * 128 + r) * 16 + (c0 & 8));
+                  bkt_s + ((size_t) (c0 >> 4) * 128 + r) * 16 + 8 * c8);
               const uint32_t w2[2] = {raw.x, raw.y};
 #pragma unroll
               for (int e = 0; e < 8; ++e) bk[e] = (int) ((w2[e >> 2] >> (8 * (e & 3))) & 0xffu);
@@ -356,8 +453,8 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
 #pragma unroll
               for (int e = 0; e < 8; ++e) bk[e] = bucket_narrow(oct, __usad(tk32, tq[e], 0u));
             } else {
-#pragma unroll 1
-              for (int e = 0; e < 8; ++e) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {   // (unrolled: a runtime index would push bk[] to local memory)
                 int64_t d = tsq_s[c0 + e] - ts_k;
                 d = d < 0 ? -d : d;
                 bk[e] = bucket_wide(oct, p.thr, p.nb, slow, d);
@@ -396,13 +493,23 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
             ppk[e >> 1] = pack_bf16x2(pvv[e], pvv[e + 1]);
             dpk[e >> 1] = pack_bf16x2(dsv[e], dsv[e + 1]);
           }
+          // P^T: packed bf16 pairs, query columns c0 .. c0+7 -> TMEM columns 448 + c0/2 .. +3
+          tmem_st4(tmem + lane_base + 448 + (c0 >> 1), ppk);
+          // dS^T: 16-byte chunk of this thread's row slice, 128-byte swizzle, block hf
+          *reinterpret_cast<uint4*>(dsT + (hf ? 2 : pb) * AT_TILE_BYTES + ((chunk0 + c8) ^ (r & 7)) * 16) =
+              make_uint4(dpk[0], dpk[1], dpk[2], dpk[3]);
           if (HAS_BIAS) {
-            // d pos_w needs the sums of dS along the diagonals of the tile: stash a plain copy
-            // (per-element global red costs ~41 LSU cycles per warp instruction; a shared
-            // read-modify-write per element races between neighbouring lanes)
-            *reinterpret_cast<uint4*>(ds_plain + r * L::DS_STRIDE + c0 * 2) =
-                make_uint4(dpk[0], dpk[1], dpk[2], dpk[3]);
+            // d pos_w: rotate each packed pair to the lane that owns its diagonal
+            if (!(p.dbg & 2))
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) {
+              const int src = lane + 8 * c8 + 2 * k2;   // source lane (mod 32) of column pair k2
+              const uint32_t got = __shfl_sync(0xffffffffu, dpk[k2], src);
+              const float lo = __uint_as_float(got << 16), hi = __uint_as_float(got & 0xffff0000u);
+              if (src < 32) { am += lo; bm += hi; } else { aw += lo; bw += hi; }
+            }
             // d ts_w: run-length accumulate along the row
+            if (!(p.dbg & 1)) {
             const bool same = (bk[0] == run_bk) & (bk[1] == run_bk) & (bk[2] == run_bk) &
                               (bk[3] == run_bk) & (bk[4] == run_bk) & (bk[5] == run_bk) &
                               (bk[6] == run_bk) & (bk[7] == run_bk);
@@ -411,49 +518,61 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
             } else {
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                if (bk[e] != run_bk) {
-                  flush_run(run_bk, run_acc);
+                if (bk[e] != run_bk) {   // the finished run parks in the pending slot
+                  if (pend_bk >= 0) flush_run(pend_bk, pend_acc);   // (second boundary in one tile: rare)
+                  pend_bk = run_bk;
+                  pend_acc = run_acc;
                   run_bk = bk[e];
                   run_acc = 0.f;
                 }
                 run_acc += dsv[e];
               }
             }
+            }
           }
-          // 16-byte chunk of this thread's row slice, 128-byte swizzle
-          const int chunk = ((chunk0 + 2 * c16 + c8) ^ (r & 7)) * 16;
-          *reinterpret_cast<uint4*>(pT + chunk) = make_uint4(ppk[0], ppk[1], ppk[2], ppk[3]);
-          *reinterpret_cast<uint4*>(dsT + chunk) = make_uint4(dpk[0], dpk[1], dpk[2], dpk[3]);
         }
+        tmem_st_wait();
+        tc_fence_before();
+        fence_proxy_async_smem();                  // st.shared -> visible to the MMA (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(bar_half_done + 8 * hf);
+          if (hf == 1) {
+            if (HAS_BIAS) mbar_arrive(bar_tab_free + 8 * pb);
+            if (cached) mbar_arrive(bar_bkt_free + 8 * pb);
+          }
+        }
+        if (TLOG && et == 0 && it < 16) p.tl[it * 16 + 11 + 3 * hf] = clock64();
+        if (HAS_BIAS) {
+          // diagonal totals: b* of lane L+1 belong to the diagonals of lane L (lane 0's bm is
+          // diagonal -1, the wrap diagonal of lane 31)
+          const float tbm = __shfl_sync(0xffffffffu, bm, lane + 1);
+          const float tbw = __shfl_sync(0xffffffffu, bw, lane + 1);
+          const float tot_m = am + (lane < 31 ? tbm : 0.f);
+          const float tot_w = aw + tbw + (lane == 31 ? tbm : 0.f);
+          // diagonal r - c = rel  ->  pos_w index N-1 + (j0 + r) - (i0 + c)
+          const int64_t idx_m = p.N - 1 + j0 - i0 + 32 * (warp & 3) - cb + lane;
+          if (tot_m != 0.f && idx_m >= 0 && idx_m < 2 * p.N - 1)
+            atomicAdd(d_pos_mine + idx_m, tot_m * half_inv_n);
+          const int64_t idx_w = idx_m - 32;
+          if (tot_w != 0.f && idx_w >= 0 && idx_w < 2 * p.N - 1)
+            atomicAdd(d_pos_mine + idx_w, tot_w * half_inv_n);
+        }
+        if (hf == 0 && it > 0 && !(p.dbg & 4)) read_back_dq(it - 1);
       }
-      if (HAS_BIAS) flush_run(run_bk, run_acc);
-      tc_fence_before();
-      fence_proxy_async_smem();                    // st.shared -> visible to the MMA (async proxy)
-      __syncwarp();
-      if (lane == 0) { mbar_arrive(bar_s_free); mbar_arrive(bar_pds_full); }
       if (HAS_BIAS) {
-        named_bar_sync(4, AB_EPI);   // dS^T copy complete; tables of tile it+1 staged
-        if (cached && et == 0 && it + 1 < n_it) load_bkt(it + 1);   // everyone is done with bkt_s
-        // d pos_w[N-1+j-i]: thread (x, half) sums diagonal x = r - c + 127 over 64 key rows
-        const int x = et & 255, hf = et >> 8;
-        if (x < 255) {
-          int r0 = hf * 64, r1 = r0 + 64;
-          const int lo = x - 127 > 0 ? x - 127 : 0;          // c = r - x + 127 >= 0
-          const int hi = x + 1 < 128 ? x + 1 : 128;          // c <= 127
-          r0 = r0 > lo ? r0 : lo;
-          r1 = r1 < hi ? r1 : hi;
-          float sum = 0.f;
-          const uint8_t* ptr = ds_plain + r0 * L::DS_STRIDE + (r0 - x + 127) * 2;
-          for (int rr = r0; rr < r1; ++rr, ptr += L::DS_STRIDE + 2)
-            sum += __uint_as_float((uint32_t) (*reinterpret_cast<const uint16_t*>(ptr)) << 16);
-          const int64_t idx = p.N - 1 + j0 - i0 - 127 + x;
-          if (sum != 0.f && idx >= 0 && idx < 2 * p.N - 1)
-            atomicAdd(d_pos_mine + idx, sum * half_inv_n);
+        // runs that ended inside this tile: neighbouring rows end the same bucket
+        warp_flush(pend_bk, pend_acc);
+        pend_bk = -1;
+        if (!cached) {
+          if (it + 1 < n_it) stage_commit(it + 1);   // other buffer: nobody reads it during tile it
+          named_bar_sync(4, AB_EPI);
         }
       }
-      if (it > 0) read_back_dq(it - 1);
+      if (TLOG && et == 0 && it < 16) p.tl[it * 16 + 15] = clock64();
     }
-    read_back_dq(n_it - 1);
+    if (!(p.dbg & 4)) read_back_dq(n_it - 1);
+    if (HAS_BIAS) warp_flush(run_bk, run_acc);   // final runs of the 32 rows of this warp
 
     // ---- dV / dK: thread = key row; warpgroups 0,1 store dV halves, 2,3 store dK halves ----
     mbar_wait(bar_dkv, 0);
@@ -518,6 +637,7 @@ bool hstu_attn_bwd_sm100_supported(const grb_hstu_attn_args* a) {
       (a->lddq * 2) % 16 || (a->lddk * 2) % 16 || (a->lddv * 2) % 16)
     return false;
   if (a->T >= (1ll << 31) || a->T == 0) return false;
+  if (a->B > 65535) return false;   // grid.y
   return true;
 }
 
@@ -541,8 +661,10 @@ int hstu_attn_bwd_sm100(const grb_hstu_attn_args* a, cudaStream_t st) {
   p.dv = reinterpret_cast<__nv_bfloat16*>(a->dv_grad); p.lddv = a->lddv;
   p.dq_accum = a->dq_accum; p.d_ts_w = a->d_ts_w; p.d_pos_w = a->d_pos_w;
   p.d_bias_copies = a->d_bias_copies > 0 ? a->d_bias_copies : 1;
+  { const char* e = std::getenv("GRB_BWD_DEBUG"); p.dbg = e ? atoi(e) : 0; }
+  if (p.dbg & 8) { static long long* tlbuf = nullptr; if (!tlbuf) cudaMalloc(&tlbuf, 256 * 8); p.tl = tlbuf; }
   const size_t smem = AbSmem::total + 1024;
-  dim3 grid((unsigned) p.n_kt, (unsigned) a->H, (unsigned) a->B);
+  dim3 grid((unsigned) a->H, (unsigned) a->B, (unsigned) p.n_kt);
   if (a->timestamps) {
     auto kern = hstu_attn_bwd_sm100_kernel<true>;
     GRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
@@ -553,6 +675,17 @@ int hstu_attn_bwd_sm100(const grb_hstu_attn_args* a, cudaStream_t st) {
     kern<<<grid, AB_THREADS, smem, st>>>(tmQ, tmK, tmV, tmdO, p);
   }
   GRB_LAUNCH_OK();
+  if (p.dbg & 8) {
+    cudaStreamSynchronize(st);
+    long long h[256];
+    cudaMemcpy(h, p.tl, sizeof(h), cudaMemcpyDeviceToHost);
+    const long long t0 = h[8];
+    for (int it = 0; it < 12; ++it) {
+      fprintf(stderr, "it %2d MMA: A_done %6lld issuedA %6lld B_done %6lld dq_free %6lld issuedB %6lld | EPI: top %6lld A: s_full %6lld go %6lld arrive %6lld  B: s_full %6lld go %6lld arrive %6lld  end %6lld\n",
+              it, h[it*16+0]-t0, h[it*16+1]-t0, h[it*16+2]-t0, h[it*16+3]-t0, h[it*16+4]-t0,
+              h[it*16+8]-t0, h[it*16+9]-t0, h[it*16+10]-t0, h[it*16+11]-t0, h[it*16+12]-t0, h[it*16+13]-t0, h[it*16+14]-t0, h[it*16+15]-t0);
+    }
+  }
   const int Wi = a->H * AT_D;
   const int64_t total4 = a->T * Wi / 4;
   dq_to_bf16_kernel<<<(unsigned) ceil_div(total4, 256), 256, 0, st>>>(

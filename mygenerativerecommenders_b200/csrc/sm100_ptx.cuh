@@ -163,6 +163,32 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t) accumulate)
       : "memory");
 }
+// Warp-collective forms: called by all 32 lanes of a converged warp, issued by one elected lane.
+// With uniform control flow around them the operands stay in uniform registers and the issue is
+// a single predicated instruction (an `if (lane == 0)` region makes the compiler wrap every MMA in
+// an elect / branch loop and move each descriptor through R2UR: ~85 cycles per MMA, measured).
+__device__ __forceinline__ void umma_ss_warp(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                             uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred e, p;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t) accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts_warp(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                             uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred e, p;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t) accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_warp(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
+      : "memory");
+}
 // all previously issued MMAs of this thread arrive on `bar` when complete (implies fence::before)
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
