@@ -43,10 +43,17 @@ namespace grb {
 
 using namespace ptx;
 
+// Build with -DGRB_BWD_TIMELINE and run with GRB_BWD_DEBUG=8 to get a clock64 timeline of CTA
+// (0,0,0) on stderr (benchmarks/probes/bwd_timeline.py).
+#ifdef GRB_BWD_TIMELINE
+#define TL_STAMP(cond, slot) do { if (TLOG && (cond)) p.tl[slot] = clock64(); } while (0)
+#else
+#define TL_STAMP(cond, slot) do { } while (0)
+#endif
+
 constexpr int AB_NWG = 4;                       // epilogue warpgroups: 32 query columns each
 constexpr int AB_EPI = AB_NWG * 128;
 constexpr int AB_THREADS = 128 + AB_EPI;
-constexpr int AB_RING = 3;                      // (Q, dO) stages
 
 struct AttnBwdParams {
   int64_t N, T;
@@ -68,32 +75,51 @@ struct AttnBwdParams {
   long long* tl;            // timeline buffer (GRB_BWD_DEBUG=8)
 };
 
+template <bool HAS_BIAS>
 struct AbSmem {
+  // (Q, dO) stages: the kernel without bias has a short epilogue, so the loads must run further
+  // ahead; with bias the bucket tiles take the space instead
+  static constexpr int RING = HAS_BIAS ? 2 : 3;
   static constexpr int k = 0;
   static constexpr int v = k + AT_TILE_BYTES;
-  static constexpr int ring = v + AT_TILE_BYTES;                 // AB_RING x (Q, dO)
+  static constexpr int ring = v + AT_TILE_BYTES;                 // RING x (Q, dO)
   // dS^T as [128 k][64 q] blocks: block A (query columns 0..63) double buffered by tile parity,
   // then block B.  dQ of a tile is issued late and reads both, so the next tile's half A must
   // not land in the buffer dQ is still reading.
-  static constexpr int dsT = ring + AB_RING * 2 * AT_TILE_BYTES;
-  static constexpr int bkt = dsT + 3 * AT_TILE_BYTES;            // 2 x 128 x 128 uint8 bucket tiles
-  // query-side tables are double buffered by tile parity
-  static constexpr int tsq = bkt + 2 * 128 * 128;                // 2 x 128 x int64
+  static constexpr int dsT = ring + RING * 2 * AT_TILE_BYTES;
+  // dQ staging for the bulk reduce-add: 16 warps x [32 rows][16 floats], 64-byte swizzle
+  static constexpr int dqs = dsT + 3 * AT_TILE_BYTES;
+  static constexpr int bkt = dqs + 16 * 2048;                    // 2 x 128 x 128 uint8 bucket tiles
+  // query-side tables are double buffered by tile parity.  The timestamp tables are only used
+  // when there is no bucket cache, so they live inside the (then unused) bucket-tile space.
+  static constexpr int tsq = bkt;                                // 2 x 128 x int64
   static constexpr int tsq32 = tsq + 2 * 128 * 8;                // 2 x 128 x uint32
-  static constexpr int red = tsq32 + 2 * 128 * 4;                // 2 x 16 x int64
-  static constexpr int pos = red + 32 * 8;                       // 2 x 256 x float (pre-halved)
-  static constexpr int tsw = pos + 2 * 256 * 4;                  // 136 x float (pre-halved)
+  static constexpr int red = bkt + (HAS_BIAS ? 2 * 128 * 128 : 0);   // 2 x 16 x int64
+  // pos_w window (pre-halved): 4 copies shifted by 0..3 floats so that every thread can fetch the
+  // 4 consecutive values it needs with one aligned 16-byte load; copy stride = 8 banks
+  static constexpr int POS_COPY = 264;                           // floats per copy
+  static constexpr int pos = red + 32 * 8;                       // 2 x 4 x POS_COPY x float
+  static constexpr int tsw = pos + 2 * 4 * POS_COPY * 4;         // 136 x float (pre-halved)
   static constexpr int oct = tsw + 136 * 4;                      // 32 x OctRec
-  static constexpr int h_ts = oct + 32 * 16;                     // 16 warps x 136 x float
-  static constexpr int bars = h_ts + 16 * 136 * 4;
-  static constexpr int total = bars + 256;   // 27 barrier / scratch words
+  static constexpr int H_TS = 132;                               // >= num_buckets + 1 (129), padded
+  static constexpr int h_ts = oct + 32 * 16;                     // 16 warps x H_TS x float
+  static constexpr int bars = h_ts + 16 * H_TS * 4;
+  static constexpr int total = bars + 224;   // 27 barrier / scratch words
 };
-static_assert(AbSmem::total + 1024 <= 232448, "shared memory budget");
+static_assert(AbSmem<true>::total + 1024 <= 232448 && AbSmem<false>::total + 1024 <= 232448,
+              "shared memory budget");
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
                "f"(d)
                : "memory");
+}
+// acc_lo += low bf16 half of `pair`, acc_hi += high half (fp32 accumulate, one FHADD each)
+__device__ __forceinline__ void add_bf16_pair(float& acc_lo, float& acc_hi, uint32_t pair) {
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tadd.rn.f32.bf16 %0, lo, %0;\n\t"
+      "add.rn.f32.bf16 %1, hi, %1;\n\t}"
+      : "+f"(acc_lo), "+f"(acc_hi)
+      : "r"(pair));
 }
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]),
@@ -105,13 +131,16 @@ template <bool HAS_BIAS>
 __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
     const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
-    AttnBwdParams p) {
+    const __grid_constant__ CUtensorMap tmDQ, AttnBwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  using L = AbSmem;
+  using L = AbSmem<HAS_BIAS>;
+  constexpr int AB_RING = L::RING;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kt = (int) blockIdx.z;                 // key tile, slowest grid index: the tiles with the most work start first
+#ifdef GRB_BWD_TIMELINE
   const bool TLOG = (p.dbg & 8) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+#endif
   const int h = blockIdx.x;
   const int b = blockIdx.y;
   const int64_t off0 = load_index(p.offsets, b, p.index_bits);
@@ -159,7 +188,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
     }
     fence_barrier_init();
     prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV);
-    prefetch_tensormap(&tmdO);
+    prefetch_tensormap(&tmdO); prefetch_tensormap(&tmDQ);
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
   if (HAS_BIAS && warp == 2) {
@@ -170,7 +199,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
     float* tsw = reinterpret_cast<float*>(smem + L::tsw);
     for (int i = lane; i < 136; i += 32) tsw[i] = (HAS_BIAS && i <= p.nb) ? 0.5f * p.ts_w[i] : 0.f;
     float* hp = reinterpret_cast<float*>(smem + L::h_ts);
-    for (int i = lane; i < 16 * 136; i += 32) hp[i] = 0.f;
+    for (int i = lane; i < 16 * L::H_TS; i += 32) hp[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -252,7 +281,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
         const int st = it % AB_RING;
         const bool more = it + 1 < n_it;
         mbar_wait_parked(bar_half_done, it & 1);          // half A of tile it
-        if (TLOG && lane == 0 && it < 16) p.tl[it * 16 + 0] = clock64();
+        TL_STAMP(lane == 0 && it < 16, it * 16 + 0);
         tc_fence_after();
         issue_dvdk(it, 0);
         umma_commit_warp(bar_a_free);
@@ -261,22 +290,22 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
           tc_fence_after();
           issue_scores(it + 1, 0);
         }
-        if (TLOG && lane == 0 && it < 16) p.tl[it * 16 + 1] = clock64();
+        TL_STAMP(lane == 0 && it < 16, it * 16 + 1);
         mbar_wait_parked(bar_half_done + 8, it & 1);      // half B of tile it
-        if (TLOG && lane == 0 && it < 16) p.tl[it * 16 + 2] = clock64();
-        if (it > 0 && !(p.dbg & 4)) mbar_wait_parked(bar_dq_free, (it - 1) & 1);
-        if (TLOG && lane == 0 && it < 16) p.tl[it * 16 + 3] = clock64();
+        TL_STAMP(lane == 0 && it < 16, it * 16 + 2);
+        if (it > 0) mbar_wait_parked(bar_dq_free, (it - 1) & 1);
+        TL_STAMP(lane == 0 && it < 16, it * 16 + 3);
         tc_fence_after();
-        issue_dvdk(it, 1);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)   // dQ_i = dS K_j : A = dS^T read MN-major, B = K MN-major
           umma_ss_warp(tmem + 384, adv((it & 1) ? ds_mn_desc1 : ds_mn_desc0, ks * 2048), adv(k_desc, ks * 2048),
                   id_mnmn, ks > 0);
+        umma_commit_warp(bar_dq_full);             // first: the epilogue reads dQ back mid-tile
+        issue_dvdk(it, 1);
         umma_commit_warp(bar_pds_free);
-        umma_commit_warp(bar_dq_full);
         umma_commit_warp(bar_ring_empty + 8 * st);
         if (more) issue_scores(it + 1, 1);
-        if (TLOG && lane == 0 && it < 16) p.tl[it * 16 + 4] = clock64();
+        TL_STAMP(lane == 0 && it < 16, it * 16 + 4);
       }
       umma_commit_warp(bar_dkv);
     }
@@ -287,15 +316,22 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
       for (int it = 0; it < n_it; ++it) {
         const int pb = it & 1;
         const int i0 = (kt + it) * AT_BM;
-        float vals[8];
+        float vals[9];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {              // pos[x] = 0.5 * pos_w[N-1 + j0 - i0 - 127 + x]
-          const int64_t idx = p.N - 1 + j0 - i0 - 127 + (lane + 32 * t);
-          vals[t] = (idx >= 0 && idx < 2 * p.N - 1) ? 0.5f * p.pos_w[idx] : 0.f;
+        for (int t = 0; t < 9; ++t) {              // pos[x] = 0.5 * pos_w[N-1 + j0 - i0 - 127 + x], x < 259
+          const int x = lane + 32 * t;
+          const int64_t idx = p.N - 1 + j0 - i0 - 127 + x;
+          vals[t] = (x < 259 && idx >= 0 && idx < 2 * p.N - 1) ? 0.5f * p.pos_w[idx] : 0.f;
         }
         mbar_wait_parked(bar_tab_free + 8 * pb, ((it >> 1) & 1) ^ 1);
+        float* dst = pos_all + pb * 4 * L::POS_COPY;
 #pragma unroll
-        for (int t = 0; t < 8; ++t) pos_all[pb * 256 + lane + 32 * t] = vals[t];
+        for (int t = 0; t < 9; ++t) {              // copy s holds pos[y + s] at index y
+          const int x = lane + 32 * t;
+#pragma unroll
+          for (int sft = 0; sft < 4; ++sft)
+            if (x - sft >= 0 && x - sft < 256) dst[sft * L::POS_COPY + x - sft] = vals[t];
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tab_full + 8 * pb);
       }
@@ -313,7 +349,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
     const float* pos_all = reinterpret_cast<const float*>(smem + L::pos);
     const float* tsw_s = reinterpret_cast<const float*>(smem + L::tsw);
     const OctRec* oct = reinterpret_cast<const OctRec*>(smem + L::oct);
-    float* h_ts = reinterpret_cast<float*>(smem + L::h_ts) + wq * 136;   // this warp's d ts_w
+    float* h_ts = reinterpret_cast<float*>(smem + L::h_ts) + wq * L::H_TS;   // this warp's d ts_w
     // this thread's 32-byte slice (2 x 16-byte chunks) of its 128-byte row, in block hf
     uint8_t* dsT = smem + L::dsT + r * 128;
     const int chunk0 = 2 * g;
@@ -338,25 +374,34 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
       tmin = tr.tmin;
       tk32 = (uint32_t) (ts_k - tmin);
     }
-    auto read_back_dq = [&](int it) {   // dQ of iteration `it`: lane = query row, 16 columns per warpgroup
+    // dQ of iteration `it` (lane = query row, 16 columns per warpgroup) is added to the fp32
+    // accumulator by a bulk reduce-add: the warp stages its [32 rows][16 floats] block in shared
+    // memory (64-byte swizzle: 16-byte chunk k of row rr sits at chunk k ^ ((rr >> 1) & 3)) and
+    // one lane hands it to the TMA unit, so no LSU time goes into 16-byte scattered atomics.
+    // Rows past the end of the sequence are exactly zero (dS is masked), rows past T are clipped.
+    uint8_t* dq_stage = smem + L::dqs + wq * 2048;
+    auto read_back_dq = [&](int it) {
       mbar_wait(bar_dq_full, it & 1);
       tc_fence_after();
       uint32_t qv[16];
       tmem_ld16(tmem + lane_base + 384 + 16 * g, qv);
       tmem_ld_wait();
-      const int qi = (kt + it) * AT_BM + r;
-      if (qi < n) {
-        float* dst = p.dq_accum + (off0 + qi) * (int64_t) (p.H * AT_D) + h * AT_D + 16 * g;
-#pragma unroll
-        for (int v4 = 0; v4 < 4; ++v4)
-          red_add_v4(dst + 4 * v4, __uint_as_float(qv[4 * v4]) * half_inv_n,
-                     __uint_as_float(qv[4 * v4 + 1]) * half_inv_n,
-                     __uint_as_float(qv[4 * v4 + 2]) * half_inv_n,
-                     __uint_as_float(qv[4 * v4 + 3]) * half_inv_n);
-      }
-      tc_fence_before();
+      if (lane == 0) bulk_wait_group_read0();      // the previous reduce has read the staging block
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_dq_free);
+#pragma unroll
+      for (int v4 = 0; v4 < 4; ++v4)
+        *reinterpret_cast<float4*>(dq_stage + lane * 64 + ((v4 ^ ((lane >> 1) & 3)) << 4)) =
+            make_float4(__uint_as_float(qv[4 * v4]) * half_inv_n, __uint_as_float(qv[4 * v4 + 1]) * half_inv_n,
+                        __uint_as_float(qv[4 * v4 + 2]) * half_inv_n, __uint_as_float(qv[4 * v4 + 3]) * half_inv_n);
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_reduce_add_2d(&tmDQ, h * AT_D + 16 * g, (int) (off0 + (kt + it) * AT_BM + 32 * (warp & 3)),
+                          smem_u32(dq_stage));
+        bulk_commit_group();
+        mbar_arrive(bar_dq_free);
+      }
     };
     // Without the bucket cache the query-side timestamps of tile `it` (ext_ts[i0 + c + 1]) are
     // staged by warpgroup 0 into buffer it & 1: global loads a tile ahead (stage_fetch), stores at
@@ -398,18 +443,23 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
     }
     // d ts_w run state: carried across query tiles (the row continues to the right, where the
     // bucket is usually still the same), flushed once after the last tile
-    int run_bk = -1, pend_bk = -1;
-    float run_acc = 0.f, pend_acc = 0.f;
+    // (run_bk4 = the run's bucket in all four bytes, 0xffffffff before the first element;
+    //  run_tsw = 0.5 * ts_w[run bucket])
+    uint32_t run_bk4 = 0xffffffffu;
+    int pend_bk = -1;
+    float run_acc = 0.f, pend_acc = 0.f, run_tsw = 0.f;
     for (int it = 0; it < n_it; ++it) {
       const int i0 = (kt + it) * AT_BM;
       const int pb = it & 1;
       if (HAS_BIAS && !cached && it + 1 < n_it) stage_fetch(it + 1);
       const int64_t* tsq_s = tsq_all + pb * 128;
       const uint32_t* tsq32_s = tsq32_all + pb * 128;
-      const float* pos_s = pos_all + pb * 256;
+      // this thread's copy (r & 3) of the pos_w window, positioned so that group c0 reads the two
+      // aligned float4 at pos4 - c0 (elements e = 7..4) and pos4 - c0 + 4 (e = 3..0)
+      const float* pos4 = pos_all + (pb * 4 + (r & 3)) * L::POS_COPY + (r + 120 - (r & 3));
       const uint8_t* bkt_s = smem + L::bkt + pb * 16384;
       const bool edge = (it == 0) || (i0 + AT_BM > n);   // diagonal tile or ragged last tile
-      if (TLOG && et == 0 && it < 16) p.tl[it * 16 + 8] = clock64();
+      TL_STAMP(et == 0 && it < 16, it * 16 + 8);
 #pragma unroll 1
       for (int hf = 0; hf < 2; ++hf) {
         const int cb = 64 * hf + 16 * g;           // first query column of this thread's chunk
@@ -419,7 +469,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
           if (HAS_BIAS) mbar_wait(bar_tab_full + 8 * pb, (it >> 1) & 1);
           if (cached) mbar_wait(bar_bkt_full + 8 * pb, (it >> 1) & 1);
         }
-        if (TLOG && et == 0 && it < 16) p.tl[it * 16 + 9 + 3 * hf] = clock64();
+        TL_STAMP(et == 0 && it < 16, it * 16 + 9 + 3 * hf);
         uint32_t sv[16], dv_[16];
         tmem_ld16(tmem + lane_base + cb, sv);
         tmem_ld16(tmem + lane_base + 128 + cb, dv_);
@@ -428,7 +478,8 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
           if (hf == 0) mbar_wait(bar_a_free, (it - 1) & 1);     // P^T half A (dV of half A, tile it-1)
           else mbar_wait(bar_pds_free, (it - 1) & 1);           // P^T half B, dS^T block B; and block A
         }                                                       // of this parity two tiles ago
-        if (TLOG && et == 0 && it < 16) p.tl[it * 16 + 10 + 3 * hf] = clock64();
+        TL_STAMP(et == 0 && it < 16, it * 16 + 10 + 3 * hf);
+        TL_STAMP(lane == 0 && it == 10, 256 + wq * 8 + 4 * hf);
         // d pos_w partial sums of this warp's 32x16 block: diagonal r - c = lane (am, bm -> lane - 1)
         // and lane - 32 (aw, bw -> lane - 33); a* take the even column of a pair, b* the odd one
         float am = 0.f, aw = 0.f, bm = 0.f, bw = 0.f;
@@ -438,30 +489,43 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
           int bk[8];
           float hb[8];
           const int c0 = cb + 8 * c8;              // first query column of this group
+          bool uni = false;   // (warp-uniform) every lane's 8 buckets continue its current run
           if (HAS_BIAS) {
+            uint2 raw = make_uint2(0u, 0u);
             if (cached) {
               // 8 bucket bytes of this key row: query chunk (c0 / 16), bytes (c0 % 16) .. +7
-              const uint2 raw = *reinterpret_cast<const uint2*>(
-                  bkt_s + ((size_t) (c0 >> 4) * 128 + r) * 16 + 8 * c8);
-              const uint32_t w2[2] = {raw.x, raw.y};
-#pragma unroll
-              for (int e = 0; e < 8; ++e) bk[e] = (int) ((w2[e >> 2] >> (8 * (e & 3))) & 0xffu);
-            } else if (narrow) {
-              const uint4 ta = *reinterpret_cast<const uint4*>(tsq32_s + c0);
-              const uint4 tb = *reinterpret_cast<const uint4*>(tsq32_s + c0 + 4);
-              const uint32_t tq[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
-#pragma unroll
-              for (int e = 0; e < 8; ++e) bk[e] = bucket_narrow(oct, __usad(tk32, tq[e], 0u));
-            } else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {   // (unrolled: a runtime index would push bk[] to local memory)
-                int64_t d = tsq_s[c0 + e] - ts_k;
-                d = d < 0 ? -d : d;
-                bk[e] = bucket_wide(oct, p.thr, p.nb, slow, d);
-              }
+              raw = *reinterpret_cast<const uint2*>(bkt_s + ((size_t) (c0 >> 4) * 128 + r) * 16 + 8 * c8);
+              uni = __all_sync(0xffffffffu, (raw.x == run_bk4) & (raw.y == run_bk4));
             }
+            // x = r - (c0 + e) + 127 ; the thread's copy makes x - 3 (e = 0) and x - 7 (e = 4) aligned
+            const float4 pa = *reinterpret_cast<const float4*>(pos4 - c0 + 4);   // e = 3, 2, 1, 0
+            const float4 pc = *reinterpret_cast<const float4*>(pos4 - c0);       // e = 7, 6, 5, 4
+            const float pz[8] = {pa.w, pa.z, pa.y, pa.x, pc.w, pc.z, pc.y, pc.x};
+            if (uni) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) hb[e] = pos_s[r - (c0 + e) + 127] + tsw_s[bk[e]];
+              for (int e = 0; e < 8; ++e) { bk[e] = 0; hb[e] = pz[e] + run_tsw; }
+            } else {
+              if (cached) {
+                const uint32_t w2[2] = {raw.x, raw.y};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) bk[e] = (int) ((w2[e >> 2] >> (8 * (e & 3))) & 0xffu);
+              } else if (narrow) {
+                const uint4 ta = *reinterpret_cast<const uint4*>(tsq32_s + c0);
+                const uint4 tb = *reinterpret_cast<const uint4*>(tsq32_s + c0 + 4);
+                const uint32_t tq[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) bk[e] = bucket_narrow(oct, __usad(tk32, tq[e], 0u));
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {   // (unrolled: a runtime index would push bk[] to local memory)
+                  int64_t d = tsq_s[c0 + e] - ts_k;
+                  d = d < 0 ? -d : d;
+                  bk[e] = bucket_wide(oct, p.thr, p.nb, slow, d);
+                }
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e) hb[e] = pz[e] + tsw_s[bk[e]];
+            }
           } else {
 #pragma unroll
             for (int e = 0; e < 8; ++e) { bk[e] = 0; hb[e] = 0.f; }
@@ -499,35 +563,39 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
           *reinterpret_cast<uint4*>(dsT + (hf ? 2 : pb) * AT_TILE_BYTES + ((chunk0 + c8) ^ (r & 7)) * 16) =
               make_uint4(dpk[0], dpk[1], dpk[2], dpk[3]);
           if (HAS_BIAS) {
-            // d pos_w: rotate each packed pair to the lane that owns its diagonal
-            if (!(p.dbg & 2))
+            // d pos_w: rotate each packed pair to the lane that owns its diagonal; the bf16 halves
+            // are added to fp32 accumulators directly (add.f32.bf16)
 #pragma unroll
             for (int k2 = 0; k2 < 4; ++k2) {
               const int src = lane + 8 * c8 + 2 * k2;   // source lane (mod 32) of column pair k2
               const uint32_t got = __shfl_sync(0xffffffffu, dpk[k2], src);
-              const float lo = __uint_as_float(got << 16), hi = __uint_as_float(got & 0xffff0000u);
-              if (src < 32) { am += lo; bm += hi; } else { aw += lo; bw += hi; }
+              if (src < 32) add_bf16_pair(am, bm, got); else add_bf16_pair(aw, bw, got);
             }
             // d ts_w: run-length accumulate along the row
-            if (!(p.dbg & 1)) {
-            const bool same = (bk[0] == run_bk) & (bk[1] == run_bk) & (bk[2] == run_bk) &
-                              (bk[3] == run_bk) & (bk[4] == run_bk) & (bk[5] == run_bk) &
-                              (bk[6] == run_bk) & (bk[7] == run_bk);
-            if (same) {
-              run_acc += ((dsv[0] + dsv[1]) + (dsv[2] + dsv[3])) + ((dsv[4] + dsv[5]) + (dsv[6] + dsv[7]));
+            const float sum8 = ((dsv[0] + dsv[1]) + (dsv[2] + dsv[3])) + ((dsv[4] + dsv[5]) + (dsv[6] + dsv[7]));
+            if (uni) {
+              run_acc += sum8;
             } else {
+              int cur = (run_bk4 == 0xffffffffu) ? -1 : (int) (run_bk4 & 0xffu);
+              const bool same = (bk[0] == cur) & (bk[1] == cur) & (bk[2] == cur) & (bk[3] == cur) &
+                                (bk[4] == cur) & (bk[5] == cur) & (bk[6] == cur) & (bk[7] == cur);
+              if (same) {
+                run_acc += sum8;
+              } else {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                if (bk[e] != run_bk) {   // the finished run parks in the pending slot
-                  if (pend_bk >= 0) flush_run(pend_bk, pend_acc);   // (second boundary in one tile: rare)
-                  pend_bk = run_bk;
-                  pend_acc = run_acc;
-                  run_bk = bk[e];
-                  run_acc = 0.f;
+                for (int e = 0; e < 8; ++e) {
+                  // a finished run parks in the pending slot (selects, no divergence); only a
+                  // second boundary inside one tile has to go to the histogram right away
+                  const bool chg = bk[e] != cur;
+                  if (chg && pend_bk >= 0) flush_run(pend_bk, pend_acc);
+                  pend_bk = chg ? cur : pend_bk;
+                  pend_acc = chg ? run_acc : pend_acc;
+                  run_acc = (chg ? 0.f : run_acc) + dsv[e];
+                  cur = bk[e];
                 }
-                run_acc += dsv[e];
+                run_bk4 = (uint32_t) cur * 0x01010101u;
+                run_tsw = tsw_s[cur];
               }
-            }
             }
           }
         }
@@ -542,7 +610,8 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
             if (cached) mbar_arrive(bar_bkt_free + 8 * pb);
           }
         }
-        if (TLOG && et == 0 && it < 16) p.tl[it * 16 + 11 + 3 * hf] = clock64();
+        TL_STAMP(et == 0 && it < 16, it * 16 + 11 + 3 * hf);
+        TL_STAMP(lane == 0 && it == 10, 256 + wq * 8 + 4 * hf + 1);
         if (HAS_BIAS) {
           // diagonal totals: b* of lane L+1 belong to the diagonals of lane L (lane 0's bm is
           // diagonal -1, the wrap diagonal of lane 31)
@@ -558,7 +627,9 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
           if (tot_w != 0.f && idx_w >= 0 && idx_w < 2 * p.N - 1)
             atomicAdd(d_pos_mine + idx_w, tot_w * half_inv_n);
         }
-        if (hf == 0 && it > 0 && !(p.dbg & 4)) read_back_dq(it - 1);
+        TL_STAMP(lane == 0 && it == 10, 256 + wq * 8 + 4 * hf + 2);
+        if (hf == 0 && it > 0) read_back_dq(it - 1);
+        TL_STAMP(lane == 0 && it == 10, 256 + wq * 8 + 4 * hf + 3);
       }
       if (HAS_BIAS) {
         // runs that ended inside this tile: neighbouring rows end the same bucket
@@ -569,10 +640,12 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
           named_bar_sync(4, AB_EPI);
         }
       }
-      if (TLOG && et == 0 && it < 16) p.tl[it * 16 + 15] = clock64();
+      TL_STAMP(et == 0 && it < 16, it * 16 + 15);
     }
-    if (!(p.dbg & 4)) read_back_dq(n_it - 1);
-    if (HAS_BIAS) warp_flush(run_bk, run_acc);   // final runs of the 32 rows of this warp
+    read_back_dq(n_it - 1);
+    if (lane == 0) bulk_wait_group0();           // shared memory must outlive the reduce
+    if (HAS_BIAS)   // final runs of the 32 rows of this warp
+      warp_flush(run_bk4 == 0xffffffffu ? -1 : (int) (run_bk4 & 0xffu), run_acc);
 
     // ---- dV / dK: thread = key row; warpgroups 0,1 store dV halves, 2,3 store dK halves ----
     mbar_wait(bar_dkv, 0);
@@ -602,7 +675,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
         const float* hall = reinterpret_cast<const float*>(smem + L::h_ts);
         float v = 0.f;
 #pragma unroll
-        for (int w = 0; w < AB_EPI / 32; ++w) v += hall[w * 136 + et];
+        for (int w = 0; w < AB_EPI / 32; ++w) v += hall[w * L::H_TS + et];
         if (v != 0.f) atomicAdd(d_ts_mine + et, v);
       }
     }
@@ -643,13 +716,14 @@ bool hstu_attn_bwd_sm100_supported(const grb_hstu_attn_args* a) {
 
 int hstu_attn_bwd_sm100(const grb_hstu_attn_args* a, cudaStream_t st) {
   if (a->B == 0 || a->max_len == 0) return GRB_OK;
-  CUtensorMap tmQ, tmK, tmV, tmdO;
+  CUtensorMap tmQ, tmK, tmV, tmdO, tmDQ;
   int rc;
   const uint64_t W = (uint64_t) a->H * AT_D;
   if ((rc = make_tmap_bf16_2d(&tmQ, a->q, a->T, W, a->ldq, AT_BM)) != GRB_OK) return rc;
   if ((rc = make_tmap_bf16_2d(&tmK, a->k, a->T, W, a->ldk, AT_BN)) != GRB_OK) return rc;
   if ((rc = make_tmap_bf16_2d(&tmV, a->v, a->T, W, a->ldv, AT_BN)) != GRB_OK) return rc;
   if ((rc = make_tmap_bf16_2d(&tmdO, a->dout, a->T, W, a->lddo, AT_BM)) != GRB_OK) return rc;
+  if ((rc = make_tmap_f32_2d_sw64(&tmDQ, a->dq_accum, a->T, W, W, 32)) != GRB_OK) return rc;
   AttnBwdParams p{};
   p.N = a->N; p.T = a->T; p.H = a->H; p.nb = a->num_buckets; p.index_bits = a->index_bits;
   p.n_kt = (int) ceil_div(a->max_len, AT_BN);
@@ -661,31 +735,39 @@ int hstu_attn_bwd_sm100(const grb_hstu_attn_args* a, cudaStream_t st) {
   p.dv = reinterpret_cast<__nv_bfloat16*>(a->dv_grad); p.lddv = a->lddv;
   p.dq_accum = a->dq_accum; p.d_ts_w = a->d_ts_w; p.d_pos_w = a->d_pos_w;
   p.d_bias_copies = a->d_bias_copies > 0 ? a->d_bias_copies : 1;
+#ifdef GRB_BWD_TIMELINE
   { const char* e = std::getenv("GRB_BWD_DEBUG"); p.dbg = e ? atoi(e) : 0; }
-  if (p.dbg & 8) { static long long* tlbuf = nullptr; if (!tlbuf) cudaMalloc(&tlbuf, 256 * 8); p.tl = tlbuf; }
-  const size_t smem = AbSmem::total + 1024;
+  if (p.dbg & 8) { static long long* tlbuf = nullptr; if (!tlbuf) cudaMalloc(&tlbuf, 512 * 8); p.tl = tlbuf; }
+#endif
   dim3 grid((unsigned) a->H, (unsigned) a->B, (unsigned) p.n_kt);
   if (a->timestamps) {
     auto kern = hstu_attn_bwd_sm100_kernel<true>;
+    const size_t smem = AbSmem<true>::total + 1024;
     GRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    kern<<<grid, AB_THREADS, smem, st>>>(tmQ, tmK, tmV, tmdO, p);
+    kern<<<grid, AB_THREADS, smem, st>>>(tmQ, tmK, tmV, tmdO, tmDQ, p);
   } else {
     auto kern = hstu_attn_bwd_sm100_kernel<false>;
+    const size_t smem = AbSmem<false>::total + 1024;
     GRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    kern<<<grid, AB_THREADS, smem, st>>>(tmQ, tmK, tmV, tmdO, p);
+    kern<<<grid, AB_THREADS, smem, st>>>(tmQ, tmK, tmV, tmdO, tmDQ, p);
   }
   GRB_LAUNCH_OK();
+#ifdef GRB_BWD_TIMELINE
   if (p.dbg & 8) {
     cudaStreamSynchronize(st);
-    long long h[256];
+    long long h[512];
     cudaMemcpy(h, p.tl, sizeof(h), cudaMemcpyDeviceToHost);
     const long long t0 = h[8];
+    for (int w = 0; w < 16; ++w)
+      fprintf(stderr, "warp %2d (wg %d, smsp %d) tile 10: A go %6lld arrive %6lld flushed %6lld dq %6lld | B go %6lld arrive %6lld flushed %6lld\n", w, w / 4, w % 4,
+              h[256+w*8]-t0, h[256+w*8+1]-t0, h[256+w*8+2]-t0, h[256+w*8+3]-t0, h[256+w*8+4]-t0, h[256+w*8+5]-t0, h[256+w*8+6]-t0);
     for (int it = 0; it < 12; ++it) {
       fprintf(stderr, "it %2d MMA: A_done %6lld issuedA %6lld B_done %6lld dq_free %6lld issuedB %6lld | EPI: top %6lld A: s_full %6lld go %6lld arrive %6lld  B: s_full %6lld go %6lld arrive %6lld  end %6lld\n",
               it, h[it*16+0]-t0, h[it*16+1]-t0, h[it*16+2]-t0, h[it*16+3]-t0, h[it*16+4]-t0,
               h[it*16+8]-t0, h[it*16+9]-t0, h[it*16+10]-t0, h[it*16+11]-t0, h[it*16+12]-t0, h[it*16+13]-t0, h[it*16+14]-t0, h[it*16+15]-t0);
     }
   }
+#endif
   const int Wi = a->H * AT_D;
   const int64_t total4 = a->T * Wi / 4;
   dq_to_bf16_kernel<<<(unsigned) ceil_div(total4, 256), 256, 0, st>>>(

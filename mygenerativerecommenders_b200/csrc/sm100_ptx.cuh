@@ -91,6 +91,26 @@ __device__ __forceinline__ uint64_t policy_evict_last() {
   return p;
 }
 
+// 2-D tile reduce-add shared -> global (element type from the tensor map); bulk async-group
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, int x, int y,
+                                                  uint32_t src_smem) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(x), "r"(y), "r"(src_smem)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// all bulk groups of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_group_read0() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// all bulk groups of this thread are complete (writes performed)
+__device__ __forceinline__ void bulk_wait_group0() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // ---- tcgen05: TMEM allocation -------------------------------------------------------------------
 // Whole warp; writes the TMEM base address to *dst_smem.  ncols: power of two in [32, 512].
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
@@ -261,5 +281,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // (cudaGetDriverEntryPoint) so the library has no link-time dependency on libcuda.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols = 64);
+// fp32 (rows, cols) matrix, box = box_rows x 16 floats, 64-byte swizzle (bulk reduce-add tiles)
+int make_tmap_f32_2d_sw64(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                          uint64_t ld_elems, uint32_t box_rows);
 
 }  // namespace grb

@@ -11,8 +11,7 @@
 
 namespace grb {
 
-int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
-                      uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols) {
+static PFN_cuTensorMapEncodeTiled_v12000 tmap_encoder() {
   static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
   static std::once_flag once;
   std::call_once(once, [] {
@@ -22,6 +21,12 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
             cudaSuccess && q == cudaDriverEntryPointSuccess)
       encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
   });
+  return encode;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                      uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols) {
+  auto encode = tmap_encoder();
   GRB_REQUIRE(encode != nullptr, GRB_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
   GRB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld_elems * 2) % 16 == 0,
               GRB_ERR_INVALID_ARG, "TMA needs a 16-byte aligned base and row stride");
@@ -34,6 +39,25 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GRB_REQUIRE(r == CUDA_SUCCESS, GRB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int) r);
+  return GRB_OK;
+}
+
+// fp32 matrix, box of box_rows x 16 floats (64-byte rows, 64-byte swizzle): the shape the
+// attention backward uses for its bulk reduce-add of dQ tiles.
+int make_tmap_f32_2d_sw64(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                          uint64_t ld_elems, uint32_t box_rows) {
+  auto encode = tmap_encoder();
+  GRB_REQUIRE(encode != nullptr, GRB_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+  GRB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld_elems * 4) % 16 == 0,
+              GRB_ERR_INVALID_ARG, "TMA needs a 16-byte aligned base and row stride");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld_elems * 4};
+  cuuint32_t box[2] = {16, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim,
+                      gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GRB_REQUIRE(r == CUDA_SUCCESS, GRB_ERR_CUDA, "cuTensorMapEncodeTiled (f32) failed (%d)", (int) r);
   return GRB_OK;
 }
 
