@@ -246,6 +246,17 @@ int grb_sampled_softmax_fwd(const grb_ssl_args* a, grb_stream_t stream);
 int grb_sampled_softmax_bwd(const grb_ssl_args* a, grb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Embedding-table gradient: table_grad[ids[i], :] += grad[i, :] for every i with ids[i] != skip_id.
+ *     Replaces aten::embedding_dense_backward under the nn.Embedding tables of
+ *     models/embeddings/embeddings.py:40-101 (padding_idx = 0 -> skip_id = 0; pass -1 to skip
+ *     nothing).  grad (n, D) fp32 with row stride ld_grad; table_grad (V, D) fp32 contiguous,
+ *     zero-filled or accumulating.  fp32 atomics: the summation order is not fixed.
+ * ------------------------------------------------------------------------------------------- */
+int grb_rows_scatter_add(const float* grad, int64_t ld_grad, const int64_t* ids, float* table_grad,
+                         int64_t n, int32_t D, int64_t num_rows, int64_t skip_id,
+                         grb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Building-block self test (tcgen05 descriptors, TMA swizzle, TMEM layouts).  Runs tiny GEMMs
  * in every operand mode the attention / retrieval kernels use and writes max-abs errors to
  * host array errs[n_modes].  Returns the number of modes run, or a negative error code.

@@ -148,6 +148,31 @@ __global__ void __launch_bounds__(SSL_WARPS * 32) ssl_bwd_kernel(SslP P) {
   }
 }
 
+// table_grad[ids[i], :] += grad[i, :]: one warp per row, 16-byte vector reductions
+template <bool VEC>
+__global__ void __launch_bounds__(256) rows_scatter_add_kernel(const float* __restrict__ grad, int64_t ld,
+                                                               const int64_t* __restrict__ ids,
+                                                               float* __restrict__ tg, int64_t n, int D,
+                                                               int64_t num_rows, int64_t skip) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t) blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const int64_t id = ids[i];
+  if (id == skip || id < 0 || id >= num_rows) return;
+  const float* src = grad + i * ld;
+  float* dst = tg + id * (int64_t) D;
+  if (VEC) {
+    for (int c = 4 * lane; c < D; c += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(src + c);
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c), "f"(v.x), "f"(v.y),
+                   "f"(v.z), "f"(v.w)
+                   : "memory");
+    }
+  } else {
+    for (int c = lane; c < D; c += 32) atomicAdd(dst + c, src[c]);
+  }
+}
+
 static int make(const grb_ssl_args* a, SslP* P, bool bwd) {
   GRB_REQUIRE(a != nullptr, GRB_ERR_INVALID_ARG, "sampled_softmax: null args");
   GRB_REQUIRE(a->dtype == GRB_F32, GRB_ERR_UNSUPPORTED, "sampled_softmax: only fp32 tables");
@@ -206,6 +231,24 @@ int grb_sampled_softmax_bwd(const grb_ssl_args* a, grb_stream_t stream) {
   if (P.D <= 64) ssl_bwd_kernel<2><<<grid, SSL_WARPS * 32, 0, st>>>(P);
   else if (P.D <= 128) ssl_bwd_kernel<4><<<grid, SSL_WARPS * 32, 0, st>>>(P);
   else ssl_bwd_kernel<8><<<grid, SSL_WARPS * 32, 0, st>>>(P);
+  GRB_LAUNCH_OK();
+  return GRB_OK;
+}
+
+int grb_rows_scatter_add(const float* grad, int64_t ld_grad, const int64_t* ids, float* table_grad,
+                         int64_t n, int32_t D, int64_t num_rows, int64_t skip_id,
+                         grb_stream_t stream) {
+  using namespace grb;
+  GRB_REQUIRE(n >= 0 && D > 0 && num_rows > 0 && ld_grad >= D, GRB_ERR_INVALID_ARG,
+              "rows_scatter_add: bad sizes");
+  if (n == 0) return GRB_OK;
+  GRB_REQUIRE(grad && ids && table_grad, GRB_ERR_INVALID_ARG, "rows_scatter_add: null tensor");
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned) ceil_div(n, 8);
+  const bool vec = (D % 4 == 0) && (ld_grad % 4 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(table_grad)) & 15) == 0;
+  if (vec) rows_scatter_add_kernel<true><<<grid, 256, 0, st>>>(grad, ld_grad, ids, table_grad, n, D, num_rows, skip_id);
+  else rows_scatter_add_kernel<false><<<grid, 256, 0, st>>>(grad, ld_grad, ids, table_grad, n, D, num_rows, skip_id);
   GRB_LAUNCH_OK();
   return GRB_OK;
 }

@@ -223,6 +223,44 @@ class _LnGate(torch.autograd.Function):
         return dx, dgate, None
 
 
+class _EmbeddingLookup(torch.autograd.Function):
+    """weight[ids] with a scatter-add backward (one launch) instead of
+    aten::embedding_dense_backward (sort + segmented reduce, ~30 launches)."""
+
+    @staticmethod
+    def forward(ctx, weight, ids, padding_idx):
+        _lib.require_cuda(weight, ids)
+        ctx.save_for_backward(ids)
+        ctx.shape = weight.shape
+        ctx.padding_idx = -1 if padding_idx is None else int(padding_idx)
+        return torch.embedding(weight, ids)
+
+    @staticmethod
+    def backward(ctx, g):
+        (ids,) = ctx.saved_tensors
+        V, D = ctx.shape
+        g2 = g.reshape(-1, D)
+        if g2.dtype != torch.float32 or g2.stride(-1) != 1:
+            g2 = g2.float().contiguous()
+        flat = ids.reshape(-1)
+        if flat.dtype != torch.int64 or not flat.is_contiguous():
+            flat = flat.to(torch.int64).contiguous()
+        dw = torch.zeros(V, D, device=g.device, dtype=torch.float32)
+        _lib.check(_lib.lib().grb_rows_scatter_add(
+            g2.data_ptr(), g2.stride(0), flat.data_ptr(), dw.data_ptr(), flat.numel(), D, V,
+            ctx.padding_idx, _lib.stream_ptr(g.device)))
+        return dw, None, None
+
+
+def embedding_lookup(weight: torch.Tensor, ids: torch.Tensor,
+                     padding_idx: Optional[int] = None) -> torch.Tensor:
+    """F.embedding(ids, weight, padding_idx) for fp32 CUDA tables (models/embeddings/
+    embeddings.py:40-101); rows whose id equals padding_idx get no gradient."""
+    if weight.dtype != torch.float32:
+        return torch.nn.functional.embedding(ids, weight, padding_idx)
+    return _EmbeddingLookup.apply(weight, ids, padding_idx)
+
+
 def layer_norm_gate(x: torch.Tensor, gate: Optional[torch.Tensor], eps: float) -> torch.Tensor:
     """gate * F.layer_norm(x, [W], eps=eps) without affine; gate=None gives the plain norm."""
     return _LnGate.apply(x, gate, eps)

@@ -141,8 +141,9 @@ class InBatchNegativesSampler(NegativesSampler):
         """ids (N') or (B, N) int64; presences same shape, bool; embeddings (..., D)."""
         assert ids.size() == presences.size()
         assert ids.size() == embeddings.size()[:-1]
-        valid_ids = ids[presences]
-        valid_emb = embeddings[presences]
+        self._cache_valid(ids[presences], embeddings[presences])
+
+    def _cache_valid(self, valid_ids: torch.Tensor, valid_emb: torch.Tensor) -> None:
         if self._dedup_embeddings:
             # one representative occurrence per distinct id (negative_sampler.py:168-184);
             # equal ids carry equal embeddings, so which occurrence wins does not matter
@@ -154,6 +155,19 @@ class InBatchNegativesSampler(NegativesSampler):
         else:
             self._cached_embeddings = self._maybe_l2_norm(valid_emb)
             self._cached_ids = valid_ids
+
+    def process_batch_prefix(self, ids: torch.Tensor, embeddings: torch.Tensor,
+                             prefix_offsets: torch.Tensor, total: int) -> None:
+        """``process_batch`` for the layout the training step has (generative_recommenders.py /
+        retrieval.py:117-123): ids (B, N) whose non-zero entries are the first
+        ``prefix_offsets[b+1] - prefix_offsets[b]`` of every row, ``total`` of them in all (known on
+        the host from the batch lengths).  ``ids[presences]`` is then exactly the jagged packing
+        of the rows, which needs no ``nonzero`` and therefore no device synchronisation; results
+        are identical to ``process_batch(ids.view(-1), ids.view(-1) != 0, embeddings.view(-1, D))``."""
+        from . import ops
+        valid_ids = ops.dense_to_jagged(ids.unsqueeze(-1), prefix_offsets, total=total).squeeze(-1)
+        valid_emb = ops.dense_to_jagged(embeddings, prefix_offsets, total=total)
+        self._cache_valid(valid_ids, valid_emb)
 
     def get_all_ids_and_embeddings(self) -> Tuple[torch.Tensor, torch.Tensor]:
         return self._cached_ids, self._cached_embeddings

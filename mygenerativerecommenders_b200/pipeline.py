@@ -16,6 +16,7 @@ from typing import Dict, NamedTuple, Optional, Tuple
 
 import torch
 
+from . import functional as GF
 from . import ops
 from .candidate_index import CandidateIndex, ShardedCandidateIndex
 from .hstu import HSTU
@@ -94,10 +95,12 @@ class ItemEmbeddings(torch.nn.Module):
         return self.year_lookup_table[item_ids.clamp(0, self.year_lookup_table.size(0) - 1)]
 
     def get_item_embeddings(self, item_ids: torch.Tensor) -> torch.Tensor:
+        look = lambda emb, ids: (GF.embedding_lookup(emb.weight, ids, emb.padding_idx)
+                                 if emb.weight.is_cuda else emb(ids))
         if self._year_emb is None:
-            return self._item_emb(item_ids)
-        return torch.cat([self._item_emb(item_ids),
-                          self._year_emb(self.lookup_year_ids(item_ids))], dim=-1)
+            return look(self._item_emb, item_ids)
+        return torch.cat([look(self._item_emb, item_ids),
+                          look(self._year_emb, self.lookup_year_ids(item_ids))], dim=-1)
 
 
 class PositionalPreprocessor(torch.nn.Module):
@@ -176,19 +179,29 @@ class RetrievalModel(torch.nn.Module):
         sf.past_ids.scatter_(dim=1, index=sf.past_lengths.view(-1, 1), src=target_ids.view(-1, 1))
         input_emb = self.embeddings.get_item_embeddings(sf.past_ids)
         sf = sf._replace(past_embeddings=input_emb)
-        seq_emb = self.forward(sf, total_length)
         sup_ids = sf.past_ids
-        if isinstance(self.negatives_sampler, InBatchNegativesSampler):
-            flat = sup_ids.view(-1)
-            self.negatives_sampler.process_batch(
-                ids=flat, presences=(flat != 0),
-                embeddings=self.embeddings.get_item_embeddings(flat))
-        else:
-            self.negatives_sampler._embeddings_module = self.embeddings
-        # generative_recommenders.py:407-425 (ids go through float32 there; exact below 2^24 —
-        # here they are gathered as integers, which is exact everywhere)
         off = ops.asynchronous_complete_cumsum(sf.past_lengths)
         tot = total_length
+        # The sampler's cache is built BEFORE the encoder runs (the reference does it after,
+        # retrieval.py:117-123; neither consumes RNG nor depends on the other): torch.unique has to
+        # report its size to the host, and here that wait happens while the GPU queue is still
+        # short instead of behind the whole encoder forward.
+        if isinstance(self.negatives_sampler, InBatchNegativesSampler):
+            if tot is not None:
+                # valid ids are the first length+1 entries of each row; the embeddings the
+                # reference looks up again (get_item_embeddings(flat)) are input_emb itself
+                self.negatives_sampler.process_batch_prefix(
+                    sup_ids, input_emb, off + torch.arange(off.numel(), device=off.device, dtype=off.dtype),
+                    tot + sup_ids.size(0))
+            else:
+                flat = sup_ids.view(-1)
+                self.negatives_sampler.process_batch(
+                    ids=flat, presences=(flat != 0), embeddings=input_emb.view(flat.numel(), -1))
+        else:
+            self.negatives_sampler._embeddings_module = self.embeddings
+        seq_emb = self.forward(sf, total_length)
+        # generative_recommenders.py:407-425 (ids go through float32 there; exact below 2^24 —
+        # here they are gathered as integers, which is exact everywhere)
         jag = dict(
             output_embeddings=ops.dense_to_jagged(seq_emb[:, :-1, :], off, total=tot),
             supervision_ids=ops.dense_to_jagged(sup_ids[:, 1:], off, total=tot),

@@ -138,3 +138,49 @@ def test_large_batch_cumsum():
     lengths = torch.randint(0, 1000, (100_003,), dtype=torch.int64)
     off = ops.asynchronous_complete_cumsum(lengths.to(DEV))
     assert torch.equal(off.cpu(), O.complete_cumsum(lengths))
+
+
+@pytest.mark.parametrize("D", [256, 50, 128])
+def test_embedding_lookup_gradient_matches_nn_embedding(D):
+    """functional.embedding_lookup == F.embedding incl. padding_idx and repeated ids
+    (models/embeddings/embeddings.py:40-101 tables); the gradient is a scatter-add."""
+    from mygenerativerecommenders_b200 import functional as GF
+    g = torch.Generator(device="cuda").manual_seed(D)
+    V = 1000
+    w = torch.randn(V, D, device="cuda", generator=g)
+    ids = torch.randint(0, 40, (7, 33), device="cuda", generator=g)   # many repeats, some zeros
+    go = torch.randn(7, 33, D, device="cuda", generator=g)
+    w1 = w.clone().requires_grad_(True)
+    out1 = GF.embedding_lookup(w1, ids, 0)
+    out1.backward(go)
+    w2 = w.clone().requires_grad_(True)
+    out2 = torch.nn.functional.embedding(ids, w2, padding_idx=0)
+    out2.backward(go)
+    assert torch.equal(out1, out2)
+    assert w1.grad[0].abs().max() == 0
+    torch.testing.assert_close(w1.grad, w2.grad, rtol=1e-5, atol=1e-5)
+
+
+def test_inbatch_prefix_cache_equals_boolean_mask_path():
+    """InBatchNegativesSampler.process_batch_prefix (no nonzero / no sync) builds the same cache as
+    the reference-shaped process_batch (negative_sampler.py:160-190)."""
+    from mygenerativerecommenders_b200 import ops
+    from mygenerativerecommenders_b200.negative_sampler import InBatchNegativesSampler
+    g = torch.Generator().manual_seed(0)
+    B, N, D = 9, 17, 24
+    lengths = torch.randint(0, N - 1, (B,), generator=g)
+    ids = torch.zeros(B, N, dtype=torch.int64)
+    for b in range(B):
+        ids[b, : lengths[b] + 1] = torch.randint(1, 30, (int(lengths[b]) + 1,), generator=g)
+    ids = ids.cuda()
+    table = torch.randn(31, D, generator=g).cuda()
+    emb = table[ids]
+    for dedup in (False, True):
+        a = InBatchNegativesSampler(True, 1e-6, dedup)
+        b_ = InBatchNegativesSampler(True, 1e-6, dedup)
+        flat = ids.view(-1)
+        a.process_batch(flat, flat != 0, emb.view(-1, D))
+        off = ops.asynchronous_complete_cumsum(lengths.cuda() + 1)
+        b_.process_batch_prefix(ids, emb, off, int(lengths.sum()) + B)
+        assert torch.equal(a._cached_ids, b_._cached_ids)
+        assert torch.equal(a._cached_embeddings, b_._cached_embeddings)
