@@ -106,7 +106,7 @@ def hstu_bucket_cache(offsets: torch.Tensor, timestamps: torch.Tensor, threshold
 class _HstuAttention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk, dv, max_len,
-                cache=None):
+                cache=None, rows_padded=False):
         _lib.require_cuda(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds)
         if not (q.dtype == k.dtype == v.dtype):
             raise ValueError("hstu_attention: q, k, v must share a dtype")
@@ -120,7 +120,10 @@ class _HstuAttention(torch.autograd.Function):
             pos_w = pos_w.detach().float().contiguous()
             if ts_w.numel() != thresholds.numel() + 1 or pos_w.numel() < 2 * N - 1:
                 raise ValueError("hstu_attention: bias table sizes do not match N / num_buckets")
-        out = torch.empty((q.shape[0], H * dv), dtype=q.dtype, device=q.device)
+        # rows_padded: q/k/v carry rows past offsets[-1] (fixed-size row buckets); the kernels
+        # never write those rows, so they must start as zeros
+        alloc = torch.zeros if rows_padded else torch.empty
+        out = alloc((q.shape[0], H * dv), dtype=q.dtype, device=q.device)
         if cache is not None and (timestamps is None or cache.grb_max_len != max_len):
             cache = None
         a = _attn_args(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk, dv, max_len, cache)
@@ -130,6 +133,7 @@ class _HstuAttention(torch.autograd.Function):
         ctx.save_for_backward(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds)
         ctx.dims = (N, H, dqk, dv, max_len)
         ctx.cache = cache
+        ctx.rows_padded = rows_padded
         return out
 
     @staticmethod
@@ -138,9 +142,10 @@ class _HstuAttention(torch.autograd.Function):
         N, H, dqk, dv, max_len = ctx.dims
         dout = _rows_contiguous(dout)
         T = q.shape[0]
-        dq = torch.empty((T, H * dqk), dtype=q.dtype, device=q.device)
-        dk = torch.empty((T, H * dqk), dtype=q.dtype, device=q.device)
-        dvv = torch.empty((T, H * dv), dtype=q.dtype, device=q.device)
+        alloc = torch.zeros if ctx.rows_padded else torch.empty
+        dq = alloc((T, H * dqk), dtype=q.dtype, device=q.device)
+        dk = alloc((T, H * dqk), dtype=q.dtype, device=q.device)
+        dvv = alloc((T, H * dv), dtype=q.dtype, device=q.device)
         dq_acc = torch.zeros((T, H * dqk), dtype=torch.float32, device=q.device)
         a = _attn_args(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk, dv, max_len,
                        ctx.cache)
@@ -161,7 +166,7 @@ class _HstuAttention(torch.autograd.Function):
         if d_pos is not None:
             d_pos = d_pos.sum(0) if d_pos.shape[0] > 1 else d_pos[0]
             d_ts = d_ts.sum(0) if d_ts.shape[0] > 1 else d_ts[0]
-        return dq, dk, dvv, None, None, d_ts, d_pos, None, None, None, None, None, None, None
+        return dq, dk, dvv, None, None, d_ts, d_pos, None, None, None, None, None, None, None, None
 
 
 def hstu_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, offsets: torch.Tensor,
@@ -169,7 +174,8 @@ def hstu_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, offsets: t
                    pos_w: Optional[torch.Tensor], bucket_thresholds: Optional[torch.Tensor],
                    N: int, num_heads: int, attention_dim: int, linear_dim: int,
                    max_len: Optional[int] = None,
-                   bucket_cache: Optional[torch.Tensor] = None) -> torch.Tensor:
+                   bucket_cache: Optional[torch.Tensor] = None,
+                   rows_padded: bool = False) -> torch.Tensor:
     """Jagged pointwise-SiLU attention with relative time+position bias.
 
     q, k: (T, H*attention_dim); v: (T, H*linear_dim); offsets (B+1); timestamps (B, N) int64 or
@@ -183,7 +189,7 @@ def hstu_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, offsets: t
         pos_w = pos_w.float()
     return _HstuAttention.apply(q, k, v, offsets, timestamps, ts_w, pos_w, bucket_thresholds,
                                 N, num_heads, attention_dim, linear_dim, min(max_len, N),
-                                bucket_cache)
+                                bucket_cache, rows_padded)
 
 
 # --------------------------------------------------------------------------------------------

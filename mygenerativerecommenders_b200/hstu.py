@@ -155,7 +155,8 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
                 delta_x_offsets: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
                 cache: Optional[HSTUCacheState] = None,
                 return_cache_states: bool = False,
-                bucket_cache: Optional[torch.Tensor] = None):
+                bucket_cache: Optional[torch.Tensor] = None,
+                rows_padded: bool = False):
         """x: (sum_i N_i, D); x_offsets: (B+1); all_timestamps: (B, N) int64 or None;
         invalid_attn_mask: (N, N) — only its size is read: the kernel applies the causal
         lower-triangular mask that HSTU registers (hstu.py:595-607,667)."""
@@ -189,7 +190,8 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
             bias._ts_w if bias is not None else None,
             bias._pos_w if bias is not None else None,
             bias._bucket_thresholds if bias is not None else None,
-            N=n, num_heads=H, attention_dim=dqk, linear_dim=dv, bucket_cache=bucket_cache)
+            N=n, num_heads=H, attention_dim=dqk, linear_dim=dv, bucket_cache=bucket_cache,
+            rows_padded=rows_padded)
 
         if self._concat_ua:
             a = self._norm_attn_output(attn_output)
@@ -221,10 +223,13 @@ class HSTUJagged(torch.nn.Module):
         super().__init__()
         self._attention_layers = torch.nn.ModuleList(modules=modules)
         self._autocast_dtype = autocast_dtype
+        self._graph_rows = 0
+        object.__setattr__(self, "_graphs", {})
 
     def jagged_forward(self, x: torch.Tensor, x_offsets: torch.Tensor,
                        all_timestamps: Optional[torch.Tensor], invalid_attn_mask: torch.Tensor,
-                       delta_x_offsets=None, cache=None, return_cache_states: bool = False):
+                       delta_x_offsets=None, cache=None, return_cache_states: bool = False,
+                       rows_padded: bool = False):
         cache_states: List[HSTUCacheState] = []
         in_dtype = x.dtype
         if self._autocast_dtype is not None and x.dtype != self._autocast_dtype:
@@ -243,7 +248,8 @@ class HSTUJagged(torch.nn.Module):
             x, cs = layer(x=x, x_offsets=x_offsets, all_timestamps=all_timestamps,
                           invalid_attn_mask=invalid_attn_mask, delta_x_offsets=delta_x_offsets,
                           cache=cache[i] if cache is not None else None,
-                          return_cache_states=return_cache_states, bucket_cache=bucket_cache)
+                          return_cache_states=return_cache_states, bucket_cache=bucket_cache,
+                          rows_padded=rows_padded)
             if return_cache_states:
                 cache_states.append(cs)
         if x.dtype != in_dtype:
@@ -255,6 +261,20 @@ class HSTUJagged(torch.nn.Module):
                 delta_x_offsets=None, cache=None, return_cache_states: bool = False,
                 total_length: Optional[int] = None):
         """x: (B, N, D) padded or (T, D) jagged.  Returns (B, N, D), cache states."""
+        n = invalid_attn_mask.size(1)
+        if (self._graph_rows and x.dim() == 3 and total_length is not None and x.is_cuda
+                and torch.is_grad_enabled() and x.requires_grad and self.training
+                and all_timestamps is not None and delta_x_offsets is None and cache is None
+                and not return_cache_states):
+            # CUDA-graph path: jagged rows padded with zero rows up to a fixed bucket, so that one
+            # captured (forward, backward) pair serves every batch of that bucket
+            t_pad = -(-max(int(total_length), 1) // self._graph_rows) * self._graph_rows
+            xj = ops.dense_to_jagged(x, x_offsets, total=t_pad, zero_tail=True)
+            run = self._graphed_stack(xj, x_offsets, all_timestamps, invalid_attn_mask)
+            yj = run(xj, x_offsets, all_timestamps)
+            y = ops.jagged_to_padded_dense(values=yj, offsets=x_offsets, max_lengths=n,
+                                           padding_value=0.0, padded_rows=True)
+            return y, []
         if x.dim() == 3:
             x = ops.dense_to_jagged(x, x_offsets, total=total_length)
         jagged_x, cache_states = self.jagged_forward(
@@ -262,8 +282,52 @@ class HSTUJagged(torch.nn.Module):
             invalid_attn_mask=invalid_attn_mask, delta_x_offsets=delta_x_offsets, cache=cache,
             return_cache_states=return_cache_states)
         y = ops.jagged_to_padded_dense(values=jagged_x, offsets=x_offsets,
-                                       max_lengths=invalid_attn_mask.size(1), padding_value=0.0)
+                                       max_lengths=n, padding_value=0.0)
         return y, cache_states
+
+    # ---- CUDA graphs (extension; the reference runs the layers eagerly, hstu.py:467-478) ----
+    def enable_cuda_graphs(self, row_granularity: int = 1024) -> None:
+        """Run the layer stack (forward and backward) as captured CUDA graphs in training.  The
+        ~40 launches per layer per direction of the eager path cost more host time than GPU time
+        at the ml-20m shape; a graph replays them with one launch.  Jagged rows are padded with
+        zero rows to a multiple of ``row_granularity`` and one graph pair is captured per padded
+        size seen (lazily, on first use).  Needs ``total_length`` from the caller."""
+        object.__setattr__(self, "_graphs", {})
+        self._graph_rows = int(row_granularity)
+
+    def disable_cuda_graphs(self) -> None:
+        self._graph_rows = 0
+        object.__setattr__(self, "_graphs", {})
+
+    def _graphed_stack(self, xj, x_offsets, timestamps, invalid_attn_mask):
+        key = (tuple(xj.shape), xj.dtype, tuple(x_offsets.shape), x_offsets.dtype,
+               tuple(timestamps.shape))
+        run = self._graphs.get(key)
+        if run is None:
+            stack = _LayerStack(self, invalid_attn_mask)
+            sample = (xj.detach().clone().requires_grad_(True), x_offsets.clone(), timestamps.clone())
+            run = torch.cuda.make_graphed_callables(stack, sample)
+            self._graphs[key] = run
+        return run
+
+
+class _LayerStack(torch.nn.Module):
+    """The callable that gets captured: all layers over padded jagged rows.  Holds the encoder
+    without registering it as a child (it must not show up in the encoder's own state_dict)."""
+
+    def __init__(self, encoder: "HSTUJagged", invalid_attn_mask: torch.Tensor) -> None:
+        super().__init__()
+        object.__setattr__(self, "_encoder", encoder)
+        object.__setattr__(self, "_mask", invalid_attn_mask)
+
+    def parameters(self, recurse: bool = True):
+        return self._encoder.parameters(recurse)
+
+    def forward(self, xj, x_offsets, timestamps):
+        y, _ = self._encoder.jagged_forward(
+            x=xj, x_offsets=x_offsets, all_timestamps=timestamps, invalid_attn_mask=self._mask,
+            rows_padded=True)
+        return y
 
 
 def _default_bucketization(x: torch.Tensor) -> torch.Tensor:

@@ -64,7 +64,8 @@ def _dense_layout(dense: torch.Tensor) -> tuple[torch.Tensor, int, int]:
     return dense, row_elems * es, bstride
 
 
-def _d2j_raw(dense: torch.Tensor, offsets: torch.Tensor, total: Optional[int]) -> torch.Tensor:
+def _d2j_raw(dense: torch.Tensor, offsets: torch.Tensor, total: Optional[int],
+             zero_tail: bool = False) -> torch.Tensor:
     _lib.require_cuda(dense, offsets)
     if dense.dim() < 2:
         raise ValueError("dense_to_jagged: dense tensor must be at least 2-D (B, N, ...)")
@@ -76,7 +77,10 @@ def _d2j_raw(dense: torch.Tensor, offsets: torch.Tensor, total: Optional[int]) -
     if total is None:
         total = int(offsets[-1].item())
     dense, row_bytes, bstride = _dense_layout(dense)
-    out = torch.empty((total, *dense.shape[2:]), dtype=dense.dtype, device=dense.device)
+    # zero_tail: `total` may exceed offsets[-1] (rows padded to a fixed bucket); the kernel only
+    # writes offsets[-1] rows
+    alloc = torch.zeros if zero_tail else torch.empty
+    out = alloc((total, *dense.shape[2:]), dtype=dense.dtype, device=dense.device)
     if total > 0:
         _lib.check(_lib.lib().grb_dense_to_jagged(
             dense.data_ptr(), offsets.data_ptr(), out.data_ptr(), B, N, row_bytes, bstride, bits,
@@ -119,28 +123,29 @@ def _j2d_raw(values: torch.Tensor, offsets: torch.Tensor, N: int, padding_value:
 
 class _DenseToJagged(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, dense, offsets, total):
+    def forward(ctx, dense, offsets, total, zero_tail=False):
         ctx.save_for_backward(offsets)
         ctx.N = dense.shape[1]
-        return _d2j_raw(dense, offsets, total)
+        return _d2j_raw(dense, offsets, total, zero_tail)
 
     @staticmethod
     def backward(ctx, grad):
         (offsets,) = ctx.saved_tensors
-        return _j2d_raw(grad, offsets, ctx.N, 0.0), None, None
+        return _j2d_raw(grad, offsets, ctx.N, 0.0), None, None, None
 
 
 class _JaggedToPaddedDense(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, values, offsets, N, padding_value):
+    def forward(ctx, values, offsets, N, padding_value, padded_rows=False):
         ctx.save_for_backward(offsets)
         ctx.total = values.shape[0]
+        ctx.padded_rows = padded_rows
         return _j2d_raw(values, offsets, N, padding_value)
 
     @staticmethod
     def backward(ctx, grad):
         (offsets,) = ctx.saved_tensors
-        return _d2j_raw(grad, offsets, ctx.total), None, None, None
+        return _d2j_raw(grad, offsets, ctx.total, ctx.padded_rows), None, None, None, None
 
 
 class _GatherLastRows(torch.autograd.Function):
@@ -182,21 +187,23 @@ def asynchronous_complete_cumsum(lengths: torch.Tensor) -> torch.Tensor:
 
 
 def dense_to_jagged(dense_tensor: torch.Tensor, offsets: torch.Tensor, *,
-                    total: Optional[int] = None) -> torch.Tensor:
-    """(B, N, ...) -> (offsets[-1], ...): drops the padding.  Reference ops.py:41-64."""
+                    total: Optional[int] = None, zero_tail: bool = False) -> torch.Tensor:
+    """(B, N, ...) -> (offsets[-1], ...): drops the padding.  Reference ops.py:41-64.
+    ``total`` (optional) spares the host read of offsets[-1]; with ``zero_tail`` it may be larger
+    than offsets[-1] and the extra rows are zero (fixed-size row buckets for CUDA graphs)."""
     if dense_tensor.requires_grad and torch.is_grad_enabled():
-        return _DenseToJagged.apply(dense_tensor, offsets, total)
-    return _d2j_raw(dense_tensor, offsets, total)
+        return _DenseToJagged.apply(dense_tensor, offsets, total, zero_tail)
+    return _d2j_raw(dense_tensor, offsets, total, zero_tail)
 
 
 def jagged_to_padded_dense(values: torch.Tensor, offsets: torch.Tensor, max_lengths: int,
-                           padding_value: float = 0.0) -> torch.Tensor:
+                           padding_value: float = 0.0, padded_rows: bool = False) -> torch.Tensor:
     """(T, ...) -> (B, max_lengths, ...) padded with ``padding_value``.  Reference ops.py:67-114
     (same ``ValueError`` for a non-int ``max_lengths``, ops.py:83-84)."""
     if not isinstance(max_lengths, int):
         raise ValueError(f"max_lengths must be an integer, but got {type(max_lengths)}")
     if values.requires_grad and torch.is_grad_enabled():
-        return _JaggedToPaddedDense.apply(values, offsets, max_lengths, padding_value)
+        return _JaggedToPaddedDense.apply(values, offsets, max_lengths, padding_value, padded_rows)
     return _j2d_raw(values, offsets, max_lengths, padding_value)
 
 

@@ -165,6 +165,14 @@ class RetrievalModel(torch.nn.Module):
         self.candidate_index = index_cls(k=cfg.top_k, ids=all_item_ids,
                                          top_k_module=MIPSBruteForceTopK())
 
+    def enable_cuda_graphs(self, row_granularity: int = 1024) -> None:
+        """Training only: run the HSTU layer stack as captured CUDA graphs (see
+        HSTUJagged.enable_cuda_graphs).  ``training_loss`` must then be given ``total_length``."""
+        self.sequence_encoder._hstu.enable_cuda_graphs(row_granularity)
+
+    def disable_cuda_graphs(self) -> None:
+        self.sequence_encoder._hstu.disable_cuda_graphs()
+
     # generative_recommenders.py:355-393
     def forward(self, sf: SequentialFeatures, total_length: Optional[int] = None) -> torch.Tensor:
         lengths, x, valid, _ = self.preprocessor(sf.past_lengths, sf.past_ids, sf.past_embeddings,
