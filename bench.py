@@ -197,17 +197,20 @@ def run_training(args, world, rank, local):
     # the HSTU layer stack runs as captured CUDA graphs (one pair per padded row count); the eager
     # path is used for the per-kernel attribution pass below.  GRB_NO_GRAPHS=1 times the eager path.
     use_graphs = os.environ.get("GRB_NO_GRAPHS") != "1"
+    n_batches = 8
+    host = [synthetic_batch(cfg, ids, PER_GPU_BATCH, seed=1000 * rank + i) for i in range(n_batches)]
+    totals = [int(b["history_lengths"].sum()) for b in host]
     if use_graphs:
-        model.enable_cuda_graphs(row_granularity=1024)
+        # under DDP the graphs have to exist before the wrapper does (see HSTUJagged.enable_cuda_graphs)
+        model.enable_cuda_graphs(row_granularity=1024, lazy=(world == 1))
+        if world > 1:
+            model.precapture_cuda_graphs(totals, PER_GPU_BATCH)
     step_mod = TrainStep(model)
     if world > 1:
         step_mod = torch.nn.parallel.DistributedDataParallel(
             step_mod, device_ids=[local], gradient_as_bucket_view=True, broadcast_buffers=False)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3, betas=(0.9, 0.98), weight_decay=1e-3,
                             fused=True)
-    n_batches = 8
-    host = [synthetic_batch(cfg, ids, PER_GPU_BATCH, seed=1000 * rank + i) for i in range(n_batches)]
-    totals = [int(b["history_lengths"].sum()) for b in host]
     pinned = [{k: v.pin_memory() for k, v in b.items()} for b in host]
     resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
 
@@ -265,7 +268,7 @@ def run_training(args, world, rank, local):
     prof = _lib.profile_stop()
     launches = (_lib.launch_count() - launches0) * args.steps // n_attr
     if use_graphs:
-        model.enable_cuda_graphs(row_granularity=1024)
+        model.enable_cuda_graphs(row_granularity=1024, lazy=(world == 1))
     barrier(world)
 
     seqs = PER_GPU_BATCH * world * args.steps

@@ -224,6 +224,7 @@ class HSTUJagged(torch.nn.Module):
         self._attention_layers = torch.nn.ModuleList(modules=modules)
         self._autocast_dtype = autocast_dtype
         self._graph_rows = 0
+        self._graph_lazy = True
         object.__setattr__(self, "_graphs", {})
 
     def jagged_forward(self, x: torch.Tensor, x_offsets: torch.Tensor,
@@ -270,8 +271,13 @@ class HSTUJagged(torch.nn.Module):
             # captured (forward, backward) pair serves every batch of that bucket
             t_pad = -(-max(int(total_length), 1) // self._graph_rows) * self._graph_rows
             xj = ops.dense_to_jagged(x, x_offsets, total=t_pad, zero_tail=True)
-            run = self._graphed_stack(xj, x_offsets, all_timestamps, invalid_attn_mask)
-            yj = run(xj, x_offsets, all_timestamps)
+            run = self._graphed_stack(xj, x_offsets, all_timestamps, invalid_attn_mask,
+                                      capture=self._graph_lazy)
+            if run is not None:
+                yj = run(xj, x_offsets, all_timestamps)
+            else:   # no graph for this bucket and lazy capture is off: same padded rows, eagerly
+                yj, _ = self.jagged_forward(x=xj, x_offsets=x_offsets, all_timestamps=all_timestamps,
+                                            invalid_attn_mask=invalid_attn_mask, rows_padded=True)
             y = ops.jagged_to_padded_dense(values=yj, offsets=x_offsets, max_lengths=n,
                                            padding_value=0.0, padded_rows=True)
             return y, []
@@ -286,24 +292,45 @@ class HSTUJagged(torch.nn.Module):
         return y, cache_states
 
     # ---- CUDA graphs (extension; the reference runs the layers eagerly, hstu.py:467-478) ----
-    def enable_cuda_graphs(self, row_granularity: int = 1024) -> None:
+    def enable_cuda_graphs(self, row_granularity: int = 1024, lazy: bool = True) -> None:
         """Run the layer stack (forward and backward) as captured CUDA graphs in training.  The
         ~40 launches per layer per direction of the eager path cost more host time than GPU time
         at the ml-20m shape; a graph replays them with one launch.  Jagged rows are padded with
         zero rows to a multiple of ``row_granularity`` and one graph pair is captured per padded
-        size seen (lazily, on first use).  Needs ``total_length`` from the caller."""
-        object.__setattr__(self, "_graphs", {})
-        self._graph_rows = int(row_granularity)
+        size seen (lazily, on first use).  Needs ``total_length`` from the caller.
 
-    def disable_cuda_graphs(self) -> None:
+        Under DistributedDataParallel graphs must be captured BEFORE the model is wrapped (the
+        wrapper pins the parameters' gradient accumulators to the stream it was built on, which a
+        later capture may not touch): call ``precapture`` first and pass ``lazy=False`` so that
+        sizes without a graph run eagerly."""
+        self._graph_rows = int(row_granularity)   # graphs are keyed by shape: old ones stay valid
+        self._graph_lazy = bool(lazy)
+
+    def precapture(self, total_lengths, batch_size: int, n: int, width: int, device,
+                   invalid_attn_mask: torch.Tensor, dtype: torch.dtype = torch.float32) -> int:
+        """Captures the graph pair of every row bucket that ``total_lengths`` fall into, with
+        synthetic inputs of the right shapes.  Returns the number of graphs held."""
+        assert self._graph_rows > 0, "enable_cuda_graphs first"
+        for t in sorted({-(-max(int(t), 1) // self._graph_rows) * self._graph_rows for t in total_lengths}):
+            per = max(1, min(n - 1, t // batch_size))
+            lengths = torch.full((batch_size,), per, dtype=torch.int64, device=device)
+            offsets = ops.asynchronous_complete_cumsum(lengths)
+            ts = torch.arange(n, device=device, dtype=torch.int64).repeat(batch_size, 1) * 1000 + 978_300_000
+            xj = torch.zeros(t, width, device=device, dtype=dtype)
+            self._graphed_stack(xj, offsets, ts, invalid_attn_mask, capture=True)
+        return len(self._graphs)
+
+    def disable_cuda_graphs(self, drop: bool = False) -> None:
+        """Back to the eager path; captured graphs are kept for a later enable unless ``drop``."""
         self._graph_rows = 0
-        object.__setattr__(self, "_graphs", {})
+        if drop:
+            object.__setattr__(self, "_graphs", {})
 
-    def _graphed_stack(self, xj, x_offsets, timestamps, invalid_attn_mask):
+    def _graphed_stack(self, xj, x_offsets, timestamps, invalid_attn_mask, capture: bool = True):
         key = (tuple(xj.shape), xj.dtype, tuple(x_offsets.shape), x_offsets.dtype,
                tuple(timestamps.shape))
         run = self._graphs.get(key)
-        if run is None:
+        if run is None and capture:
             stack = _LayerStack(self, invalid_attn_mask)
             sample = (xj.detach().clone().requires_grad_(True), x_offsets.clone(), timestamps.clone())
             run = torch.cuda.make_graphed_callables(stack, sample)

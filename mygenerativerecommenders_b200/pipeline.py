@@ -165,10 +165,18 @@ class RetrievalModel(torch.nn.Module):
         self.candidate_index = index_cls(k=cfg.top_k, ids=all_item_ids,
                                          top_k_module=MIPSBruteForceTopK())
 
-    def enable_cuda_graphs(self, row_granularity: int = 1024) -> None:
+    def enable_cuda_graphs(self, row_granularity: int = 1024, lazy: bool = True) -> None:
         """Training only: run the HSTU layer stack as captured CUDA graphs (see
         HSTUJagged.enable_cuda_graphs).  ``training_loss`` must then be given ``total_length``."""
-        self.sequence_encoder._hstu.enable_cuda_graphs(row_granularity)
+        self.sequence_encoder._hstu.enable_cuda_graphs(row_granularity, lazy)
+
+    def precapture_cuda_graphs(self, total_lengths, batch_size: int) -> int:
+        """Capture the graphs for the row buckets of ``total_lengths`` now (required before the
+        model is wrapped in DistributedDataParallel)."""
+        enc = self.sequence_encoder
+        dev = self.embeddings._item_emb.weight.device
+        return enc._hstu.precapture(total_lengths, batch_size, self.cfg.N, self.cfg.embedding_dim, dev,
+                                    enc._attn_mask, self.embeddings._item_emb.weight.dtype)
 
     def disable_cuda_graphs(self) -> None:
         self.sequence_encoder._hstu.disable_cuda_graphs()
