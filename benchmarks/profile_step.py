@@ -13,6 +13,9 @@ cfg = bench.c2_config(True)
 ids = synthetic_item_ids(26_744, cfg.num_items)
 torch.manual_seed(42)
 model = RetrievalModel(cfg, ids).to(dev).train()
+import os
+if os.environ.get("GRB_NO_GRAPHS") != "1":
+    model.enable_cuda_graphs()
 opt = torch.optim.AdamW(model.parameters(), lr=1e-3, betas=(0.9, 0.98), weight_decay=1e-3, fused=True)
 batches = [{k: v.to(dev) for k, v in synthetic_batch(cfg, ids, 128, seed=i).items()} for i in range(4)]
 totals = [int(b["history_lengths"].sum()) for b in batches]

@@ -148,6 +148,174 @@ __global__ void __launch_bounds__(SSL_WARPS * 32) ssl_bwd_kernel(SslP P) {
   }
 }
 
+// ---- vector path: one table, D = 128 * NV, 16-byte aligned rows --------------------------------
+// Lane l owns columns 128 v + 4 l .. + 3 (float4 gathers: two 512-byte requests per 1 KiB row
+// instead of eight 128-byte ones).  The forward reduces the dot products of 32 negatives together
+// with a transposing butterfly (31 shuffles for 32 sums instead of 160): afterwards lane j holds
+// the logit of negative r0 + j, which is also the layout the softmax and the stores want.
+__device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
+  acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc);
+  acc = fmaf(a.z, b.z, acc); return fmaf(a.w, b.w, acc);
+}
+// in: v[j] = this lane's partial sum for item j.  out: v[0] on lane j = sum over lanes of item j.
+__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float keep = up ? v[i + s] : v[i];
+      const float send = up ? v[i] : v[i + s];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+template <int NV, bool L2>
+__global__ void __launch_bounds__(SSL_WARPS * 32) ssl_fwd_vec_kernel(SslP P) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n = (int64_t) blockIdx.x * SSL_WARPS + (threadIdx.x >> 5);
+  if (n >= P.n_rows) return;
+  float4 q[NV];
+  float pd = 0.f;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    q[v] = *reinterpret_cast<const float4*>(P.q + n * P.ldq + 128 * v + 4 * lane);
+    pd = dot4(q[v], *reinterpret_cast<const float4*>(P.p + n * P.ldp + 128 * v + 4 * lane), pd);
+  }
+  const float zpos = warp_sum(pd) / P.temp;
+  const int64_t pid = P.pos_ids[n];
+  float* pr = P.probs + n * (int64_t) (P.R + 1);
+  const int64_t* idx = P.idx0 + n * (int64_t) P.R;
+  const int64_t* nid = P.neg_ids + n * (int64_t) P.R;
+  float m = zpos;
+  for (int r0 = 0; r0 < P.R; r0 += 32) {
+    float dots[32], nrm[L2 ? 32 : 1];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float d = 0.f, nn = 0.f;
+      if (r0 + j < P.R) {                            // warp-uniform
+        const float* row = P.t0 + idx[r0 + j] * P.ldt0 + 4 * lane;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const float4 e = __ldg(reinterpret_cast<const float4*>(row + 128 * v));
+          d = dot4(q[v], e, d);
+          if (L2) nn = dot4(e, e, nn);
+        }
+      }
+      dots[j] = d;
+      if (L2) nrm[j] = nn;
+    }
+    float z = transpose_reduce32(dots, lane);
+    if (L2) {
+      float (&nr)[32] = reinterpret_cast<float (&)[32]>(nrm);
+      z = z / fmaxf(sqrtf(transpose_reduce32(nr, lane)), P.eps);
+    }
+    const int r = r0 + lane;
+    if (r < P.R) {
+      z = (nid[r] == pid) ? -5e4f : z / P.temp;
+      pr[r + 1] = z;                                 // stash logits, normalised below
+      m = fmaxf(m, z);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __syncwarp();
+  float se = 0.f;
+  for (int r = lane; r < P.R; r += 32) se += expf(pr[r + 1] - m);
+  se = warp_sum(se) + expf(zpos - m);
+  const float lse = logf(se);
+  for (int r = lane; r < P.R; r += 32) pr[r + 1] = expf(pr[r + 1] - m - lse);
+  if (lane == 0) {
+    pr[0] = expf(zpos - m - lse);
+    P.loss_rows[n] = -(zpos - m - lse);
+  }
+}
+
+__device__ __forceinline__ void red_add4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
+               "f"(d)
+               : "memory");
+}
+
+template <int NV, bool L2>
+__global__ void __launch_bounds__(SSL_WARPS * 32) ssl_bwd_vec_kernel(SslP P) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n = (int64_t) blockIdx.x * SSL_WARPS + (threadIdx.x >> 5);
+  if (n >= P.n_rows) return;
+  const float g = P.g[n];
+  const float* pr = P.probs + n * (int64_t) (P.R + 1);
+  const float dzpos = g * (pr[0] - 1.0f) / P.temp;
+  float4 q[NV], dqa[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int c = 128 * v + 4 * lane;
+    q[v] = *reinterpret_cast<const float4*>(P.q + n * P.ldq + c);
+    const float4 pv = *reinterpret_cast<const float4*>(P.p + n * P.ldp + c);
+    dqa[v] = make_float4(dzpos * pv.x, dzpos * pv.y, dzpos * pv.z, dzpos * pv.w);
+    *reinterpret_cast<float4*>(P.dp + n * (int64_t) P.D + c) =
+        make_float4(dzpos * q[v].x, dzpos * q[v].y, dzpos * q[v].z, dzpos * q[v].w);
+  }
+  const int64_t pid = P.pos_ids[n];
+  const int64_t* idx = P.idx0 + n * (int64_t) P.R;
+  const int64_t* nid = P.neg_ids + n * (int64_t) P.R;
+  if (g != 0.f) {
+    for (int r0 = 0; r0 < P.R; r0 += 32) {
+      // this lane's negative of the batch: coefficient (0: masked collision / out of range) and row
+      const int r = r0 + lane;
+      float my_dl = 0.f;
+      int64_t my_i = 0;
+      if (r < P.R) {
+        my_i = idx[r];
+        if (nid[r] != pid) my_dl = g * pr[r + 1] / P.temp;
+      }
+#pragma unroll 4
+      for (int j = 0; j < 32; ++j) {
+        const float dl = __shfl_sync(0xffffffffu, my_dl, j);
+        if (dl == 0.f) continue;                     // warp-uniform
+        const int64_t i0 = __shfl_sync(0xffffffffu, my_i, j);
+        const float* row = P.t0 + i0 * P.ldt0 + 4 * lane;
+        float* drow = P.dt0 + i0 * (int64_t) P.d0 + 4 * lane;
+        float4 e[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) e[v] = __ldg(reinterpret_cast<const float4*>(row + 128 * v));
+        float a = 1.0f, bcoef = 0.f;  // d e = dl * (a * q - bcoef * e) ; d q += dl * a * e
+        if (L2) {
+          float dot = 0.f, nn = 0.f;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) { dot = dot4(q[v], e[v], dot); nn = dot4(e[v], e[v], nn); }
+          dot = warp_sum(dot);
+          nn = warp_sum(nn);
+          const float nrm = sqrtf(nn);
+          if (nrm > P.eps) { a = 1.0f / nrm; bcoef = dot / (nrm * nn); }
+          else { a = 1.0f / P.eps; bcoef = 0.f; }    // clamp branch: denominator is constant
+        }
+        const float da = dl * a, db = dl * bcoef;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          dqa[v].x = fmaf(da, e[v].x, dqa[v].x); dqa[v].y = fmaf(da, e[v].y, dqa[v].y);
+          dqa[v].z = fmaf(da, e[v].z, dqa[v].z); dqa[v].w = fmaf(da, e[v].w, dqa[v].w);
+          red_add4(drow + 128 * v, da * q[v].x - db * e[v].x, da * q[v].y - db * e[v].y,
+                   da * q[v].z - db * e[v].z, da * q[v].w - db * e[v].w);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+    *reinterpret_cast<float4*>(P.dq + n * (int64_t) P.D + 128 * v + 4 * lane) = dqa[v];
+}
+
+// single table, D = 128 or 256, everything 16-byte aligned
+static bool ssl_vec_ok(const SslP& P, bool bwd) {
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (P.d1 != 0 || (P.D != 128 && P.D != 256)) return false;
+  if (!al(P.q) || !al(P.p) || !al(P.t0) || P.ldq % 4 || P.ldp % 4 || P.ldt0 % 4) return false;
+  if (bwd && (!al(P.dq) || !al(P.dp) || !al(P.dt0))) return false;
+  return true;
+}
+
 // table_grad[ids[i], :] += grad[i, :]: one warp per row, 16-byte vector reductions
 template <bool VEC>
 __global__ void __launch_bounds__(256) rows_scatter_add_kernel(const float* __restrict__ grad, int64_t ld,
@@ -214,6 +382,17 @@ int grb_sampled_softmax_fwd(const grb_ssl_args* a, grb_stream_t stream) {
   if (P.n_rows == 0) return GRB_OK;
   auto st = reinterpret_cast<cudaStream_t>(stream);
   const unsigned grid = (unsigned) ceil_div(P.n_rows, SSL_WARPS);
+  if (ssl_vec_ok(P, false)) {
+    if (P.D == 128) {
+      if (P.l2) ssl_fwd_vec_kernel<1, true><<<grid, SSL_WARPS * 32, 0, st>>>(P);
+      else ssl_fwd_vec_kernel<1, false><<<grid, SSL_WARPS * 32, 0, st>>>(P);
+    } else {
+      if (P.l2) ssl_fwd_vec_kernel<2, true><<<grid, SSL_WARPS * 32, 0, st>>>(P);
+      else ssl_fwd_vec_kernel<2, false><<<grid, SSL_WARPS * 32, 0, st>>>(P);
+    }
+    GRB_LAUNCH_OK();
+    return GRB_OK;
+  }
   if (P.D <= 64) ssl_fwd_kernel<2><<<grid, SSL_WARPS * 32, 0, st>>>(P);
   else if (P.D <= 128) ssl_fwd_kernel<4><<<grid, SSL_WARPS * 32, 0, st>>>(P);
   else ssl_fwd_kernel<8><<<grid, SSL_WARPS * 32, 0, st>>>(P);
@@ -228,6 +407,17 @@ int grb_sampled_softmax_bwd(const grb_ssl_args* a, grb_stream_t stream) {
   if (P.n_rows == 0) return GRB_OK;
   auto st = reinterpret_cast<cudaStream_t>(stream);
   const unsigned grid = (unsigned) ceil_div(P.n_rows, SSL_WARPS);
+  if (ssl_vec_ok(P, true)) {
+    if (P.D == 128) {
+      if (P.l2) ssl_bwd_vec_kernel<1, true><<<grid, SSL_WARPS * 32, 0, st>>>(P);
+      else ssl_bwd_vec_kernel<1, false><<<grid, SSL_WARPS * 32, 0, st>>>(P);
+    } else {
+      if (P.l2) ssl_bwd_vec_kernel<2, true><<<grid, SSL_WARPS * 32, 0, st>>>(P);
+      else ssl_bwd_vec_kernel<2, false><<<grid, SSL_WARPS * 32, 0, st>>>(P);
+    }
+    GRB_LAUNCH_OK();
+    return GRB_OK;
+  }
   if (P.D <= 64) ssl_bwd_kernel<2><<<grid, SSL_WARPS * 32, 0, st>>>(P);
   else if (P.D <= 128) ssl_bwd_kernel<4><<<grid, SSL_WARPS * 32, 0, st>>>(P);
   else ssl_bwd_kernel<8><<<grid, SSL_WARPS * 32, 0, st>>>(P);

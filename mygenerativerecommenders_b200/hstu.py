@@ -260,8 +260,9 @@ class HSTUJagged(torch.nn.Module):
     def forward(self, x: torch.Tensor, x_offsets: torch.Tensor,
                 all_timestamps: Optional[torch.Tensor], invalid_attn_mask: torch.Tensor,
                 delta_x_offsets=None, cache=None, return_cache_states: bool = False,
-                total_length: Optional[int] = None):
-        """x: (B, N, D) padded or (T, D) jagged.  Returns (B, N, D), cache states."""
+                total_length: Optional[int] = None, jagged_output: bool = False):
+        """x: (B, N, D) padded or (T, D) jagged.  Returns (B, N, D), cache states; with
+        ``jagged_output`` the (>= T, D) jagged rows instead (rows past offsets[-1] are padding)."""
         n = invalid_attn_mask.size(1)
         if (self._graph_rows and x.dim() == 3 and total_length is not None and x.is_cuda
                 and torch.is_grad_enabled() and x.requires_grad and self.training
@@ -278,6 +279,8 @@ class HSTUJagged(torch.nn.Module):
             else:   # no graph for this bucket and lazy capture is off: same padded rows, eagerly
                 yj, _ = self.jagged_forward(x=xj, x_offsets=x_offsets, all_timestamps=all_timestamps,
                                             invalid_attn_mask=invalid_attn_mask, rows_padded=True)
+            if jagged_output:
+                return yj, []
             y = ops.jagged_to_padded_dense(values=yj, offsets=x_offsets, max_lengths=n,
                                            padding_value=0.0, padded_rows=True)
             return y, []
@@ -287,6 +290,8 @@ class HSTUJagged(torch.nn.Module):
             x=x, x_offsets=x_offsets, all_timestamps=all_timestamps,
             invalid_attn_mask=invalid_attn_mask, delta_x_offsets=delta_x_offsets, cache=cache,
             return_cache_states=return_cache_states)
+        if jagged_output:
+            return jagged_x, cache_states
         y = ops.jagged_to_padded_dense(values=jagged_x, offsets=x_offsets,
                                        max_lengths=n, padding_value=0.0)
         return y, cache_states
@@ -426,9 +431,10 @@ class HSTU(torch.nn.Module):
     def forward(self, past_lengths: torch.Tensor, user_embeddings: torch.Tensor,
                 valid_mask: torch.Tensor, past_payloads: Dict[str, torch.Tensor],
                 delta_x_offsets=None, cache=None, return_cache_states: bool = False,
-                total_length: Optional[int] = None):
+                total_length: Optional[int] = None, jagged_output: bool = False):
         """past_lengths (B,) int; user_embeddings (B, N, D); valid_mask unused (as :637);
-        past_payloads["timestamps"] (B, N) int64.  Returns ((B, N, D), cache states)."""
+        past_payloads["timestamps"] (B, N) int64.  Returns ((B, N, D), cache states);
+        ``jagged_output`` (extension) skips the final jagged -> padded copy."""
         # only the mask's size is read downstream: pass the bool buffer itself instead of
         # materialising 1 - mask in the activation dtype every step (256 MB at N = 8192)
         return self._hstu(
@@ -437,4 +443,5 @@ class HSTU(torch.nn.Module):
             all_timestamps=past_payloads.get(TIMESTAMPS_KEY),
             invalid_attn_mask=self._attn_mask,
             delta_x_offsets=delta_x_offsets, cache=cache,
-            return_cache_states=return_cache_states, total_length=total_length)
+            return_cache_states=return_cache_states, total_length=total_length,
+            jagged_output=jagged_output)

@@ -182,11 +182,17 @@ class RetrievalModel(torch.nn.Module):
         self.sequence_encoder._hstu.disable_cuda_graphs()
 
     # generative_recommenders.py:355-393
-    def forward(self, sf: SequentialFeatures, total_length: Optional[int] = None) -> torch.Tensor:
+    def forward(self, sf: SequentialFeatures, total_length: Optional[int] = None,
+                jagged_output: bool = False) -> torch.Tensor:
+        """(B, N, D) normalised encodings; ``jagged_output``: the (T, D) valid rows only (the
+        post-processor acts per row, so it can run on the jagged rows directly)."""
         lengths, x, valid, _ = self.preprocessor(sf.past_lengths, sf.past_ids, sf.past_embeddings,
                                                  sf.past_payloads)
         x, _ = self.sequence_encoder(past_lengths=lengths, user_embeddings=x, valid_mask=valid,
-                                     past_payloads=sf.past_payloads, total_length=total_length)
+                                     past_payloads=sf.past_payloads, total_length=total_length,
+                                     jagged_output=jagged_output)
+        if jagged_output and total_length is not None and x.size(0) != total_length:
+            x = x[:total_length]       # drop the zero rows of the CUDA-graph row bucket
         return self.postprocessor(x)
 
     def training_loss(self, row: Dict[str, torch.Tensor], total_length: Optional[int] = None) -> torch.Tensor:
@@ -215,11 +221,13 @@ class RetrievalModel(torch.nn.Module):
                     ids=flat, presences=(flat != 0), embeddings=input_emb.view(flat.numel(), -1))
         else:
             self.negatives_sampler._embeddings_module = self.embeddings
-        seq_emb = self.forward(sf, total_length)
         # generative_recommenders.py:407-425 (ids go through float32 there; exact below 2^24 —
-        # here they are gathered as integers, which is exact everywhere)
+        # here they are gathered as integers, which is exact everywhere).  The reference pads the
+        # encoder output to (B, N, D), normalises it and packs rows [0, length) again; those are
+        # exactly the encoder's jagged rows, so they are normalised and used as they are.
+        out_rows = self.forward(sf, total_length, jagged_output=True)
         jag = dict(
-            output_embeddings=ops.dense_to_jagged(seq_emb[:, :-1, :], off, total=tot),
+            output_embeddings=out_rows,
             supervision_ids=ops.dense_to_jagged(sup_ids[:, 1:], off, total=tot),
             supervision_embeddings=ops.dense_to_jagged(input_emb[:, 1:, :], off, total=tot),
             supervision_weights=ops.dense_to_jagged((sup_ids[:, 1:] != 0).float(), off, total=tot),

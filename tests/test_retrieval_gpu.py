@@ -219,3 +219,33 @@ def test_inbatch_sampler_fused_vs_oracle(golden, monkeypatch):
     for item in set(g["ib_ids"].tolist()) - {0}:
         m = g["ib_ids"] == item
         assert torch.allclose(src.grad.cpu()[m].sum(0), srcc.grad[m].sum(0), rtol=1e-3, atol=1e-6)
+
+
+@pytest.mark.parametrize("D,R,l2", [(256, 128, False), (256, 40, True), (128, 128, True), (128, 33, False)])
+def test_fused_sampled_softmax_vector_path(D, R, l2):
+    """Single table with D = 128 / 256 takes the float4 kernels (32 negatives reduced together);
+    same oracle as the generic path, incl. collisions and a ragged last batch of negatives."""
+    gen = torch.Generator().manual_seed(D + R)
+    n, V = 150, 60
+    t0 = torch.randn(V + 1, D, generator=gen) * 0.3
+    if not l2:   # the in-batch cache arrives normalised
+        t0 = torch.nn.functional.normalize(t0, dim=-1)
+    q = torch.nn.functional.normalize(torch.randn(n, D, generator=gen), dim=-1)
+    pos_ids = torch.randint(1, V + 1, (n,), generator=gen)
+    neg_ids = torch.randint(1, V + 1, (n, R), generator=gen)
+    w = (torch.rand(n, generator=gen) > 0.1).float()
+    assert (neg_ids == pos_ids.unsqueeze(1)).any()
+    lq, lt = (x.clone().double().requires_grad_(True) for x in (q, t0))
+    sup = torch.nn.functional.normalize(torch.randn(n, D, generator=gen), dim=-1)
+    ref, _ = O.sampled_softmax_loss(lq, pos_ids, sup.double(), w.double(), neg_ids, lt[neg_ids], 0.05,
+                                    1e-6, neg_already_normalized=not l2)
+    ref.backward()
+    gq, g0 = (x.to(DEV).requires_grad_(True) for x in (q, t0))
+    rows = GF.sampled_softmax_rows(gq, sup.to(DEV), g0, None, neg_ids.to(DEV), None, pos_ids.to(DEV),
+                                   neg_ids.to(DEV), l2, 1e-6, 0.05)
+    loss = (rows * w.to(DEV)).sum() / w.sum()
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    loss.backward()
+    for got, r, name in ((gq, lq, "dq"), (g0, lt, "dt0")):
+        scale = r.grad.abs().max().item()
+        assert (got.grad.cpu().double() - r.grad).abs().max().item() <= 2e-4 * scale, name
