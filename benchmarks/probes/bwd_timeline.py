@@ -1,10 +1,15 @@
+"""clock64 timeline of one CTA of the attention backward.  Needs a library built with
+GRB_NVCC_EXTRA=-DGRB_BWD_TIMELINE python -m mygenerativerecommenders_b200.build"""
 import sys, torch
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/benchmarks")
 import os
 import kbench
 from mygenerativerecommenders_b200 import functional as GF
 bias = sys.argv[1] == "bias"
-c = kbench.attn_case(4, 8192, 8, [8192] * 4)
+if len(sys.argv) > 2 and sys.argv[2] == "c2":
+    c = kbench.attn_case(128, 211, 4, torch.randint(150, 201, (128,), generator=torch.Generator().manual_seed(0)))
+else:
+    c = kbench.attn_case(4, 8192, 8, [8192] * 4)
 H, d = c["H"], c["d"]
 q, k, v = (c[n].clone().requires_grad_(True) for n in ("q", "k", "v"))
 if bias:

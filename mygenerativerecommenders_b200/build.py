@@ -22,7 +22,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
-]
+] + os.environ.get("GRB_NVCC_EXTRA", "").split()   # e.g. -DGRB_BWD_TIMELINE (developer probes)
 
 
 def _sources() -> list[Path]:

@@ -101,9 +101,7 @@ struct AbSmem {
   static constexpr int pos = red + 32 * 8;                       // 2 x 4 x POS_COPY x float
   static constexpr int tsw = pos + 2 * 4 * POS_COPY * 4;         // 136 x float (pre-halved)
   static constexpr int oct = tsw + 136 * 4;                      // 32 x OctRec
-  static constexpr int H_TS = 132;                               // >= num_buckets + 1 (129), padded
-  static constexpr int h_ts = oct + 32 * 16;                     // 16 warps x H_TS x float
-  static constexpr int bars = h_ts + 16 * H_TS * 4;
+  static constexpr int bars = oct + 32 * 16;
   static constexpr int total = bars + 224;   // 27 barrier / scratch words
 };
 static_assert(AbSmem<true>::total + 1024 <= 232448 && AbSmem<false>::total + 1024 <= 232448,
@@ -198,8 +196,6 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
   if (warp == 3) {
     float* tsw = reinterpret_cast<float*>(smem + L::tsw);
     for (int i = lane; i < 136; i += 32) tsw[i] = (HAS_BIAS && i <= p.nb) ? 0.5f * p.ts_w[i] : 0.f;
-    float* hp = reinterpret_cast<float*>(smem + L::h_ts);
-    for (int i = lane; i < 16 * L::H_TS; i += 32) hp[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -349,7 +345,6 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
     const float* pos_all = reinterpret_cast<const float*>(smem + L::pos);
     const float* tsw_s = reinterpret_cast<const float*>(smem + L::tsw);
     const OctRec* oct = reinterpret_cast<const OctRec*>(smem + L::oct);
-    float* h_ts = reinterpret_cast<float*>(smem + L::h_ts) + wq * L::H_TS;   // this warp's d ts_w
     // this thread's 32-byte slice (2 x 16-byte chunks) of its 128-byte row, in block hf
     uint8_t* dsT = smem + L::dsT + r * 128;
     const int chunk0 = 2 * g;
@@ -416,24 +411,10 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
         tsq32_all[(it & 1) * 128 + r] = (uint32_t) (st_a - tmin);
       }
     };
-    // d ts_w: a finished run goes to this warp's private histogram.  Shared memory has no native
-    // fp32 add (atomicAdd is a CAS loop); this path only runs when a row crosses two bucket
-    // boundaries inside one tile.
+    // d ts_w: a finished run is added to this CTA's private copy in global memory with a
+    // fire-and-forget red (shared memory has no native fp32 add: atomicAdd there is a CAS loop)
     auto flush_run = [&](int bk, float val) {
-      if (bk >= 0 && val != 0.f) atomicAdd(&h_ts[bk], val * half_inv_n);
-    };
-    // adds (bucket, value) of every lane to the warp-private histogram: one shuffle reduction per
-    // distinct bucket, then a plain update by lane 0.  Must be called by the whole warp.
-    auto warp_flush = [&](int bk, float val) {
-      unsigned todo = __ballot_sync(0xffffffffu, bk >= 0);
-      while (todo) {
-        const int bsel = __shfl_sync(0xffffffffu, bk, __ffs(todo) - 1);
-        const bool mine = bk == bsel;
-        const float v = warp_sum(mine ? val : 0.f);
-        if (lane == 0) h_ts[bsel] += v * half_inv_n;
-        todo &= ~__ballot_sync(0xffffffffu, mine);
-      }
-      __syncwarp();
+      if (bk >= 0 && val != 0.f) atomicAdd(d_ts_mine + bk, val * half_inv_n);
     };
 
     if (HAS_BIAS && !cached) {
@@ -446,8 +427,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
     // (run_bk4 = the run's bucket in all four bytes, 0xffffffff before the first element;
     //  run_tsw = 0.5 * ts_w[run bucket])
     uint32_t run_bk4 = 0xffffffffu;
-    int pend_bk = -1;
-    float run_acc = 0.f, pend_acc = 0.f, run_tsw = 0.f;
+    float run_acc = 0.f, run_tsw = 0.f;
     for (int it = 0; it < n_it; ++it) {
       const int i0 = (kt + it) * AT_BM;
       const int pb = it & 1;
@@ -584,12 +564,8 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
               } else {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                  // a finished run parks in the pending slot (selects, no divergence); only a
-                  // second boundary inside one tile has to go to the histogram right away
                   const bool chg = bk[e] != cur;
-                  if (chg && pend_bk >= 0) flush_run(pend_bk, pend_acc);
-                  pend_bk = chg ? cur : pend_bk;
-                  pend_acc = chg ? run_acc : pend_acc;
+                  if (chg) flush_run(cur, run_acc);        // one predicated red, no loop
                   run_acc = (chg ? 0.f : run_acc) + dsv[e];
                   cur = bk[e];
                 }
@@ -631,21 +607,27 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
         if (hf == 0 && it > 0) read_back_dq(it - 1);
         TL_STAMP(lane == 0 && it == 10, 256 + wq * 8 + 4 * hf + 3);
       }
-      if (HAS_BIAS) {
-        // runs that ended inside this tile: neighbouring rows end the same bucket
-        warp_flush(pend_bk, pend_acc);
-        pend_bk = -1;
-        if (!cached) {
-          if (it + 1 < n_it) stage_commit(it + 1);   // other buffer: nobody reads it during tile it
-          named_bar_sync(4, AB_EPI);
-        }
+      if (HAS_BIAS && !cached) {
+        if (it + 1 < n_it) stage_commit(it + 1);   // other buffer: nobody reads it during tile it
+        named_bar_sync(4, AB_EPI);
       }
       TL_STAMP(et == 0 && it < 16, it * 16 + 15);
     }
     read_back_dq(n_it - 1);
     if (lane == 0) bulk_wait_group0();           // shared memory must outlive the reduce
-    if (HAS_BIAS)   // final runs of the 32 rows of this warp
-      warp_flush(run_bk4 == 0xffffffffu ? -1 : (int) (run_bk4 & 0xffu), run_acc);
+    if (HAS_BIAS) {
+      // final runs of the 32 rows of this warp: mostly one bucket, so reduce per distinct bucket
+      // across the warp and let one lane issue the red
+      const int bk = run_bk4 == 0xffffffffu ? -1 : (int) (run_bk4 & 0xffu);
+      unsigned todo = __ballot_sync(0xffffffffu, bk >= 0);
+      while (todo) {
+        const int bsel = __shfl_sync(0xffffffffu, bk, __ffs(todo) - 1);
+        const bool mine = bk == bsel;
+        const float v = warp_sum(mine ? run_acc : 0.f);
+        if (lane == 0) flush_run(bsel, v);
+        todo &= ~__ballot_sync(0xffffffffu, mine);
+      }
+    }
 
     // ---- dV / dK: thread = key row; warpgroups 0,1 store dV halves, 2,3 store dK halves ----
     mbar_wait(bar_dkv, 0);
@@ -667,16 +649,6 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
           o.w = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 6]) * sc, __uint_as_float(ov[v4 * 8 + 7]) * sc);
           *reinterpret_cast<uint4*>(dst + v4 * 8) = o;
         }
-      }
-    }
-    if (HAS_BIAS) {
-      named_bar_sync(4, AB_EPI);                    // every warp's histogram is final
-      if (et <= p.nb) {
-        const float* hall = reinterpret_cast<const float*>(smem + L::h_ts);
-        float v = 0.f;
-#pragma unroll
-        for (int w = 0; w < AB_EPI / 32; ++w) v += hall[w * L::H_TS + et];
-        if (v != 0.f) atomicAdd(d_ts_mine + et, v);
       }
     }
   }
