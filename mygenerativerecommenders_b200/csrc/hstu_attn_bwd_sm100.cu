@@ -469,6 +469,18 @@ __global__ void __launch_bounds__(AB_THREADS, 1) hstu_attn_bwd_sm100_kernel(
           int bk[8];
           float hb[8];
           const int c0 = cb + 8 * c8;              // first query column of this group
+          if (edge) {
+            // diagonal / ragged tile: a group whose 8 columns are masked for all 32 rows of the
+            // warp (above the diagonal, or past the end of the sequence) only needs its zeros
+            const int lo = jk - i0 - c0, hi = n - i0 - c0;   // valid columns: lo <= e < hi
+            if (__all_sync(0xffffffffu, lo >= 8 || hi <= 0 || hi <= lo)) {
+              const uint32_t z4[4] = {0u, 0u, 0u, 0u};
+              tmem_st4(tmem + lane_base + 448 + (c0 >> 1), z4);
+              *reinterpret_cast<uint4*>(dsT + (hf ? 2 : pb) * AT_TILE_BYTES + ((chunk0 + c8) ^ (r & 7)) * 16) =
+                  make_uint4(0u, 0u, 0u, 0u);
+              continue;
+            }
+          }
           bool uni = false;   // (warp-uniform) every lane's 8 buckets continue its current run
           if (HAS_BIAS) {
             uint2 raw = make_uint2(0u, 0u);

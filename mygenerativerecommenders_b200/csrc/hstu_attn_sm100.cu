@@ -282,6 +282,11 @@ __global__ void __launch_bounds__(AT_THREADS, 1) hstu_attn_fwd_sm100_kernel(
         // chunk 0, which only it reads); the upper-half warpgroup (S chunks 2, 3, never
         // overwritten) waits for that signal before its first P write (P2 lands on S chunk 1).
         auto compute_chunk = [&](int c32, uint32_t (&pk)[16]) {
+          if (diag && (warp & 3) < c32) {   // diagonal tile: all 32 key columns lie above every
+#pragma unroll                             // row of this warp -> P is zero, nothing to compute
+            for (int w = 0; w < 16; ++w) pk[w] = 0u;
+            return;
+          }
           uint32_t sv[32];
           tmem_ld32(s_addr + c32 * 32, sv);
           tmem_ld_wait();
