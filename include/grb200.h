@@ -157,6 +157,16 @@ int grb_ln_gate_bwd(const void* x, int64_t ldx, const void* gate, int64_t ldg, c
                     grb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * b4  negatives_samples/negative_sampler.py:31-37 (_maybe_l2_norm) and postprocessors.py:47-55:
+ *     y = x / clamp(||x||_2, min=eps) per row, fp32.  inv (rows) is saved for backward:
+ *     1 / max(||x||, eps), negated when the clamp was active.  Backward: dx from dy, y, inv.
+ * ------------------------------------------------------------------------------------------- */
+int grb_l2norm_fwd(const float* x, int64_t ldx, float* y, int64_t ldy, float* inv, int64_t rows,
+                   int64_t W, float eps, grb_stream_t stream);
+int grb_l2norm_bwd(const float* y, int64_t ldy, const float* dy, int64_t lddy, const float* inv,
+                   float* dx, int64_t lddx, int64_t rows, int64_t W, grb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * b2  models/indexing/top_k.py:44-70  MIPSBruteForceTopK  (mm + topk + id gather), fused:
  *     the (B, X) score matrix never reaches HBM.
  *

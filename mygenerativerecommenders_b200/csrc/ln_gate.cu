@@ -86,7 +86,67 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_gate_bwd_kernel(
 
 using namespace grb;
 
+// y = x / max(||x||_2, eps) per row (negative_sampler.py:31-37 _maybe_l2_norm; postprocessors.py:47-55).
+// inv[row] = 1 / max(||x||, eps), negated when the clamp is active (||x|| < eps) so that the
+// backward knows which branch of clamp(min=eps) the row took.
+__global__ void __launch_bounds__(LN_WARPS * 32) l2norm_fwd_kernel(
+    const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy,
+    float* __restrict__ inv, int64_t rows, int W, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t) blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * ldx;
+  float q = 0.f;
+  for (int c = lane; c < W; c += 32) { const float v = xr[c]; q = fmaf(v, v, q); }
+  const float nrm = sqrtf(warp_sum(q));
+  const float iv = 1.0f / fmaxf(nrm, eps);
+  if (lane == 0) inv[row] = nrm >= eps ? iv : -iv;
+  float* yr = y + row * ldy;
+  for (int c = lane; c < W; c += 32) yr[c] = xr[c] * iv;
+}
+// dx = inv * (dy - y * <y, dy>) when the norm passed the clamp, inv * dy otherwise
+__global__ void __launch_bounds__(LN_WARPS * 32) l2norm_bwd_kernel(
+    const float* __restrict__ y, int64_t ldy, const float* __restrict__ dy, int64_t lddy,
+    const float* __restrict__ inv, float* __restrict__ dx, int64_t lddx, int64_t rows, int W) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t) blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* yr = y + row * ldy;
+  const float* gr = dy + row * lddy;
+  float* dr = dx + row * lddx;
+  const float iv = inv[row];
+  if (iv < 0.f) {
+    for (int c = lane; c < W; c += 32) dr[c] = -iv * gr[c];
+    return;
+  }
+  float d = 0.f;
+  for (int c = lane; c < W; c += 32) d = fmaf(yr[c], gr[c], d);
+  d = warp_sum(d);
+  for (int c = lane; c < W; c += 32) dr[c] = iv * (gr[c] - yr[c] * d);
+}
+
 extern "C" {
+
+int grb_l2norm_fwd(const float* x, int64_t ldx, float* y, int64_t ldy, float* inv, int64_t rows,
+                   int64_t W, float eps, grb_stream_t stream) {
+  GRB_REQUIRE(x && y && inv && rows >= 0 && W > 0 && W < (1 << 30) && eps > 0.f, GRB_ERR_INVALID_ARG,
+              "l2norm_fwd: bad arguments");
+  if (rows == 0) return GRB_OK;
+  l2norm_fwd_kernel<<<(unsigned) ceil_div(rows, LN_WARPS), LN_WARPS * 32, 0,
+                      reinterpret_cast<cudaStream_t>(stream)>>>(x, ldx, y, ldy, inv, rows, (int) W, eps);
+  GRB_LAUNCH_OK();
+  return GRB_OK;
+}
+
+int grb_l2norm_bwd(const float* y, int64_t ldy, const float* dy, int64_t lddy, const float* inv,
+                   float* dx, int64_t lddx, int64_t rows, int64_t W, grb_stream_t stream) {
+  GRB_REQUIRE(y && dy && inv && dx && rows >= 0 && W > 0, GRB_ERR_INVALID_ARG, "l2norm_bwd: bad arguments");
+  if (rows == 0) return GRB_OK;
+  l2norm_bwd_kernel<<<(unsigned) ceil_div(rows, LN_WARPS), LN_WARPS * 32, 0,
+                      reinterpret_cast<cudaStream_t>(stream)>>>(y, ldy, dy, lddy, inv, dx, lddx, rows, (int) W);
+  GRB_LAUNCH_OK();
+  return GRB_OK;
+}
 
 int grb_ln_gate_fwd(const void* x, int64_t ldx, const void* gate, int64_t ldg, void* y,
                     int64_t ldy, float* mean, float* rstd, int64_t rows, int64_t W, float eps,

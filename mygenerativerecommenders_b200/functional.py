@@ -229,6 +229,42 @@ class _LnGate(torch.autograd.Function):
         return dx, dgate, None
 
 
+class _L2Norm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, eps):
+        shape = x.shape
+        x2 = _rows_contiguous(x.reshape(-1, shape[-1]))
+        rows, W = x2.shape
+        y = torch.empty((rows, W), dtype=torch.float32, device=x.device)
+        inv = torch.empty(rows, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().grb_l2norm_fwd(x2.data_ptr(), _ld(x2), y.data_ptr(), W, inv.data_ptr(),
+                                             rows, W, float(eps), _lib.stream_ptr(x.device)))
+        ctx.save_for_backward(y, inv)
+        ctx.shape = shape
+        return y.view(shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, inv = ctx.saved_tensors
+        rows, W = y.shape
+        dy2 = dy.reshape(rows, W)
+        if dy2.dtype != torch.float32:
+            dy2 = dy2.float()
+        dy2 = _rows_contiguous(dy2)
+        dx = torch.empty((rows, W), dtype=torch.float32, device=y.device)
+        _lib.check(_lib.lib().grb_l2norm_bwd(y.data_ptr(), W, dy2.data_ptr(), _ld(dy2), inv.data_ptr(),
+                                             dx.data_ptr(), W, rows, W, _lib.stream_ptr(y.device)))
+        return dx.view(ctx.shape), None
+
+
+def l2_normalize(x: torch.Tensor, eps: float) -> torch.Tensor:
+    """x / clamp(||x||_2 over the last dim, min=eps): negative_sampler.py:31-37, postprocessors.py:47-55.
+    One kernel forward, one backward (fp32 CUDA); other inputs take the reference's composite."""
+    if x.is_cuda and x.dtype == torch.float32 and x.numel() > 0:
+        return _L2Norm.apply(x, eps)
+    return x / torch.clamp(torch.linalg.norm(x, ord=None, dim=-1, keepdim=True), min=eps)
+
+
 class _EmbeddingLookup(torch.autograd.Function):
     """weight[ids] with a scatter-add backward (one launch) instead of
     aten::embedding_dense_backward (sort + segmented reduce, ~30 launches)."""

@@ -37,8 +37,8 @@ class NegativesSampler(torch.nn.Module):
     def _maybe_l2_norm(self, x: torch.Tensor) -> torch.Tensor:
         # x / clamp(||x||_2, min=eps)  (negative_sampler.py:31-37)
         if self._l2_norm:
-            x = x / torch.clamp(torch.linalg.norm(x, ord=2, dim=-1, keepdim=True),
-                                min=self._l2_norm_eps)
+            from . import functional as GF
+            x = GF.l2_normalize(x, self._l2_norm_eps)
         return x
 
     @abc.abstractmethod
@@ -144,6 +144,7 @@ class InBatchNegativesSampler(NegativesSampler):
         self._cache_valid(ids[presences], embeddings[presences])
 
     def _cache_valid(self, valid_ids: torch.Tensor, valid_emb: torch.Tensor) -> None:
+        self._cached_count = None
         if self._dedup_embeddings:
             # one representative occurrence per distinct id (negative_sampler.py:168-184);
             # equal ids carry equal embeddings, so which occurrence wins does not matter
@@ -157,7 +158,8 @@ class InBatchNegativesSampler(NegativesSampler):
             self._cached_ids = valid_ids
 
     def process_batch_prefix(self, ids: torch.Tensor, embeddings: torch.Tensor,
-                             prefix_offsets: torch.Tensor, total: int) -> None:
+                             prefix_offsets: torch.Tensor, total: int,
+                             static_shapes: bool = False) -> None:
         """``process_batch`` for the layout the training step has (generative_recommenders.py /
         retrieval.py:117-123): ids (B, N) whose non-zero entries are the first
         ``prefix_offsets[b+1] - prefix_offsets[b]`` of every row, ``total`` of them in all (known on
@@ -167,14 +169,45 @@ class InBatchNegativesSampler(NegativesSampler):
         from . import ops
         valid_ids = ops.dense_to_jagged(ids.unsqueeze(-1), prefix_offsets, total=total).squeeze(-1)
         valid_emb = ops.dense_to_jagged(embeddings, prefix_offsets, total=total)
-        self._cache_valid(valid_ids, valid_emb)
+        if static_shapes and self._dedup_embeddings and total > 0:
+            self._cache_valid_static(valid_ids, valid_emb)
+        else:
+            self._cache_valid(valid_ids, valid_emb)
+
+    def _cache_valid_static(self, valid_ids: torch.Tensor, valid_emb: torch.Tensor) -> None:
+        """De-duplication without data-dependent shapes, hence without a device sync: the cache is
+        padded to the number of valid ids and the number of distinct ids stays on the device
+        (``_cached_count``).  Same order as ``torch.unique`` (ascending ids).  ``_draw`` then maps
+        random bits onto [0, count) on the device."""
+        n = valid_ids.numel()
+        sorted_ids, order = torch.sort(valid_ids)
+        new = torch.ones(n, dtype=torch.bool, device=valid_ids.device)
+        new[1:] = sorted_ids[1:] != sorted_ids[:-1]
+        rank = torch.cumsum(new, 0) - 1
+        uniq = torch.zeros(n, dtype=torch.int64, device=valid_ids.device).scatter_(0, rank, sorted_ids)
+        # (slots past the count keep distinct positions; nothing samples them, their gradient is 0)
+        rep = torch.arange(n, dtype=torch.int64, device=valid_ids.device).scatter_(0, rank, order)
+        from . import functional as GF
+        self._cached_embeddings = self._maybe_l2_norm(GF.embedding_lookup(valid_emb, rep, None))
+        self._cached_ids = uniq
+        self._cached_count = rank[-1] + 1
 
     def get_all_ids_and_embeddings(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        if getattr(self, "_cached_count", None) is not None:     # padded cache: trim (host sync)
+            c = int(self._cached_count.item())
+            return self._cached_ids[:c], self._cached_embeddings[:c]
         return self._cached_ids, self._cached_embeddings
 
     def _draw(self, positive_ids: torch.Tensor, num_to_sample: int) -> torch.Tensor:
-        return torch.randint(low=0, high=self._cached_ids.size(0),
-                             size=positive_ids.size() + (num_to_sample,),
+        size = positive_ids.size() + (num_to_sample,)
+        if getattr(self, "_cached_count", None) is not None:
+            # uniform over [0, count) without reading count on the host: 62 random bits modulo
+            # count (bias < count / 2^62).  Same distribution as torch.randint(0, count), not the
+            # same Philox stream (ATen folds the range into the draw on the host side).
+            raw = torch.randint(low=0, high=2 ** 62, size=size, dtype=torch.int64,
+                                device=positive_ids.device)
+            return (raw % self._cached_count).to(positive_ids.dtype)
+        return torch.randint(low=0, high=self._cached_ids.size(0), size=size,
                              dtype=positive_ids.dtype, device=positive_ids.device)
 
     def forward(self, positive_ids: torch.Tensor, num_to_sample: int):

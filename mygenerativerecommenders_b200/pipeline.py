@@ -132,7 +132,7 @@ class L2NormPostprocessor(torch.nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         x = x[..., : self._embedding_dim]
-        return x / torch.clamp(torch.linalg.norm(x, dim=-1, keepdim=True), min=self._eps)
+        return GF.l2_normalize(x, self._eps)
 
 
 class RetrievalModel(torch.nn.Module):
@@ -204,17 +204,17 @@ class RetrievalModel(torch.nn.Module):
         sup_ids = sf.past_ids
         off = ops.asynchronous_complete_cumsum(sf.past_lengths)
         tot = total_length
-        # The sampler's cache is built BEFORE the encoder runs (the reference does it after,
-        # retrieval.py:117-123; neither consumes RNG nor depends on the other): torch.unique has to
-        # report its size to the host, and here that wait happens while the GPU queue is still
-        # short instead of behind the whole encoder forward.
+        # The sampler's cache is built before the encoder runs (the reference does it after,
+        # retrieval.py:117-123; neither consumes RNG nor depends on the other) and with static
+        # shapes: the step then contains no device synchronisation at all, so the host can
+        # enqueue step k+1 while the GPU still runs step k.
         if isinstance(self.negatives_sampler, InBatchNegativesSampler):
             if tot is not None:
                 # valid ids are the first length+1 entries of each row; the embeddings the
                 # reference looks up again (get_item_embeddings(flat)) are input_emb itself
                 self.negatives_sampler.process_batch_prefix(
                     sup_ids, input_emb, off + torch.arange(off.numel(), device=off.device, dtype=off.dtype),
-                    tot + sup_ids.size(0))
+                    tot + sup_ids.size(0), static_shapes=True)
             else:
                 flat = sup_ids.view(-1)
                 self.negatives_sampler.process_batch(

@@ -184,3 +184,24 @@ def test_inbatch_prefix_cache_equals_boolean_mask_path():
         b_.process_batch_prefix(ids, emb, off, int(lengths.sum()) + B)
         assert torch.equal(a._cached_ids, b_._cached_ids)
         assert torch.equal(a._cached_embeddings, b_._cached_embeddings)
+
+
+@pytest.mark.parametrize("W", [256, 50])
+def test_l2_normalize_matches_reference_composite(W):
+    """functional.l2_normalize == x / clamp(norm(x), min=eps) (negative_sampler.py:31-37), forward and
+    backward, including rows below the clamp and a strided input."""
+    from mygenerativerecommenders_b200 import functional as GF
+    g = torch.Generator(device="cuda").manual_seed(W)
+    base = torch.randn(37, W + 6, device="cuda", generator=g)
+    base[3] = 0.0
+    base[5] *= 1e-9                      # norm below eps: the clamp branch
+    go = torch.randn(37, W, device="cuda", generator=g)
+    a = base.clone().requires_grad_(True)
+    b = base.clone().requires_grad_(True)
+    ya = GF.l2_normalize(a[:, 3:3 + W], 1e-6)
+    xb = b[:, 3:3 + W]
+    yb = xb / torch.clamp(torch.linalg.norm(xb, ord=2, dim=-1, keepdim=True), min=1e-6)
+    torch.testing.assert_close(ya, yb, rtol=1e-6, atol=1e-7)
+    ya.backward(go)
+    yb.backward(go)
+    torch.testing.assert_close(a.grad, b.grad, rtol=2e-5, atol=1e-6)

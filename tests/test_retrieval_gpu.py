@@ -249,3 +249,36 @@ def test_fused_sampled_softmax_vector_path(D, R, l2):
     for got, r, name in ((gq, lq, "dq"), (g0, lt, "dt0")):
         scale = r.grad.abs().max().item()
         assert (got.grad.cpu().double() - r.grad).abs().max().item() <= 2e-4 * scale, name
+
+
+def test_inbatch_static_cache_matches_unique_cache():
+    """The sync-free in-batch cache (padded, count on the device) holds the same ids / embeddings as
+    the torch.unique one, and its draws are uniform over [0, count)."""
+    from mygenerativerecommenders_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    B, N, D = 11, 23, 16
+    lengths = torch.randint(0, N - 1, (B,), generator=g)
+    ids = torch.zeros(B, N, dtype=torch.int64)
+    for b in range(B):
+        ids[b, : lengths[b] + 1] = torch.randint(1, 40, (int(lengths[b]) + 1,), generator=g)
+    ids = ids.to(DEV)
+    table = torch.randn(41, D, generator=g).to(DEV)
+    emb = table[ids]
+    off = ops.asynchronous_complete_cumsum(lengths.to(DEV) + 1)
+    total = int(lengths.sum()) + B
+    dyn = InBatchNegativesSampler(True, 1e-6, True)
+    sta = InBatchNegativesSampler(True, 1e-6, True)
+    dyn.process_batch_prefix(ids, emb, off, total)
+    sta.process_batch_prefix(ids, emb, off, total, static_shapes=True)
+    c = int(sta._cached_count.item())
+    assert c == dyn._cached_ids.numel() and sta._cached_ids.numel() == total
+    a_ids, a_emb = sta.get_all_ids_and_embeddings()
+    assert torch.equal(a_ids, dyn._cached_ids)
+    assert torch.allclose(a_emb, dyn._cached_embeddings, atol=1e-7)
+    pos = torch.zeros(4000, dtype=torch.int64, device=DEV)
+    torch.manual_seed(77)
+    d = sta._draw(pos, 128)
+    assert d.min().item() >= 0 and d.max().item() == c - 1
+    hist = torch.bincount(d.view(-1), minlength=c).float()
+    expect = d.numel() / c
+    assert (hist - expect).abs().max().item() < 6 * expect ** 0.5      # every bin within 6 sigma
