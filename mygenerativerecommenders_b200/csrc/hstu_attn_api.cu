@@ -10,6 +10,8 @@ int hstu_attn_bwd_simt_dispatch(const grb_hstu_attn_args* a, cudaStream_t st);
 bool hstu_attn_fwd_sm100_supported(const grb_hstu_attn_args* a);
 bool hstu_attn_bwd_sm100_supported(const grb_hstu_attn_args* a);
 int hstu_attn_fwd_sm100(const grb_hstu_attn_args* a, cudaStream_t st);
+bool hstu_attn_fwd2_sm100_usable(const grb_hstu_attn_args* a);
+int hstu_attn_fwd2_sm100(const grb_hstu_attn_args* a, cudaStream_t st);
 int hstu_attn_bwd_sm100(const grb_hstu_attn_args* a, cudaStream_t st);
 
 static bool force_cuda_core() {
@@ -27,7 +29,13 @@ int grb_hstu_attn_fwd(const grb_hstu_attn_args* a, grb_stream_t stream) {
   if (rc != GRB_OK) return rc;
   GRB_REQUIRE(a->B <= 65535 && a->H <= 65535, GRB_ERR_UNSUPPORTED, "hstu_attn: B,H <= 65535");
   auto st = reinterpret_cast<cudaStream_t>(stream);
-  if (!force_cuda_core() && hstu_attn_fwd_sm100_supported(a)) return hstu_attn_fwd_sm100(a, st);
+  if (!force_cuda_core() && hstu_attn_fwd_sm100_supported(a)) {
+    // second-generation kernel when the buckets come from the per-batch cache (or no bias);
+    // GRB_FWD_V1=1 keeps the first one (developer switch)
+    const char* v1 = std::getenv("GRB_FWD_V1");
+    if (!(v1 && v1[0] == '1') && hstu_attn_fwd2_sm100_usable(a)) return hstu_attn_fwd2_sm100(a, st);
+    return hstu_attn_fwd_sm100(a, st);
+  }
   return hstu_attn_fwd_simt_dispatch(a, st);
 }
 
