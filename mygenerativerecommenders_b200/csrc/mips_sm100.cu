@@ -111,14 +111,18 @@ __global__ void __launch_bounds__(MsCfg<NQB>::threads, 1) mips_scores_sm100_kern
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp, uniform control flow; one elected lane issues (umma_*_warp): an
+        // `if (lane == 0)` region costs ~85 cycles of issue per MMA, more than its 64 cycles of work
       const uint32_t idesc = make_idesc_bf16(128, MIPS_TILE_N, false, false);
+      const uint64_t q_desc = make_smem_desc_sw128(smem_u32(smem + MsSmem::q), 0, 1024);
+      const uint64_t ring_desc = make_smem_desc_sw128(smem_u32(smem + MsSmem::ring), 0, 1024);
+      auto adv = [](uint64_t d, uint32_t bytes) { return d + (uint64_t) (bytes >> 4); };
       uint32_t it = 0, tile = 0, q_loads = 0;
       int64_t cur_qb = -1;
       for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
         const int64_t chunk = w / p.n_qb, qb = w % p.n_qb;
         if (qb != cur_qb) {
-          if (cur_qb >= 0) umma_commit(bar_q_empty);     // all MMAs reading the old Q are issued
+          if (cur_qb >= 0) umma_commit_warp(bar_q_empty);     // all MMAs reading the old Q are issued
           mbar_wait_parked(bar_q_full, q_loads & 1);
           tc_fence_after();
           cur_qb = qb;
@@ -134,19 +138,18 @@ __global__ void __launch_bounds__(MsCfg<NQB>::threads, 1) mips_scores_sm100_kern
             const uint32_t st = it % MS_STAGES;
             mbar_wait_parked(bar_full + 8 * st, (it / MS_STAGES) & 1);
             tc_fence_after();
-            const uint32_t ia = smem_u32(smem + MsSmem::ring + st * MS_SLAB);
+            const uint64_t i_desc = adv(ring_desc, st * MS_SLAB);
 #pragma unroll
             for (int qq = 0; qq < NQB; ++qq) {
-              const uint32_t qa = smem_u32(smem + MsSmem::q + (qq * 4 + kc) * MS_SLAB);
+              const uint64_t qd = adv(q_desc, (qq * 4 + kc) * MS_SLAB);
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                umma_ss(tmem + (ab * NQB + qq) * MIPS_TILE_N,
-                        make_smem_desc_sw128(qa + ks * 32, 0, 1024),
-                        make_smem_desc_sw128(ia + ks * 32, 0, 1024), idesc, (kc > 0) || (ks > 0));
+                umma_ss_warp(tmem + (ab * NQB + qq) * MIPS_TILE_N, adv(qd, ks * 32), adv(i_desc, ks * 32),
+                             idesc, (kc > 0) || (ks > 0));
             }
-            umma_commit(bar_empty + 8 * st);
+            umma_commit_warp(bar_empty + 8 * st);
           }
-          umma_commit(bar_acc_full + 8 * ab);
+          umma_commit_warp(bar_acc_full + 8 * ab);
         }
       }
     }
