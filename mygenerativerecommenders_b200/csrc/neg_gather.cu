@@ -270,34 +270,47 @@ __global__ void __launch_bounds__(SSL_WARPS * 32) ssl_bwd_vec_kernel(SslP P) {
         my_i = idx[r];
         if (nid[r] != pid) my_dl = g * pr[r + 1] / P.temp;
       }
-#pragma unroll 4
-      for (int j = 0; j < 32; ++j) {
-        const float dl = __shfl_sync(0xffffffffu, my_dl, j);
-        if (dl == 0.f) continue;                     // warp-uniform
-        const int64_t i0 = __shfl_sync(0xffffffffu, my_i, j);
-        const float* row = P.t0 + i0 * P.ldt0 + 4 * lane;
-        float* drow = P.dt0 + i0 * (int64_t) P.d0 + 4 * lane;
-        float4 e[NV];
+      // four negatives at a time: all eight 16-byte gathers are issued before any is consumed
+#pragma unroll 2
+      for (int j4 = 0; j4 < 32; j4 += 4) {
+        float dl[4];
+        int64_t i0[4];
+        float4 e[4][NV];
 #pragma unroll
-        for (int v = 0; v < NV; ++v) e[v] = __ldg(reinterpret_cast<const float4*>(row + 128 * v));
-        float a = 1.0f, bcoef = 0.f;  // d e = dl * (a * q - bcoef * e) ; d q += dl * a * e
-        if (L2) {
-          float dot = 0.f, nn = 0.f;
-#pragma unroll
-          for (int v = 0; v < NV; ++v) { dot = dot4(q[v], e[v], dot); nn = dot4(e[v], e[v], nn); }
-          dot = warp_sum(dot);
-          nn = warp_sum(nn);
-          const float nrm = sqrtf(nn);
-          if (nrm > P.eps) { a = 1.0f / nrm; bcoef = dot / (nrm * nn); }
-          else { a = 1.0f / P.eps; bcoef = 0.f; }    // clamp branch: denominator is constant
+        for (int t = 0; t < 4; ++t) {
+          dl[t] = __shfl_sync(0xffffffffu, my_dl, j4 + t);
+          i0[t] = __shfl_sync(0xffffffffu, my_i, j4 + t);
         }
-        const float da = dl * a, db = dl * bcoef;
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          dqa[v].x = fmaf(da, e[v].x, dqa[v].x); dqa[v].y = fmaf(da, e[v].y, dqa[v].y);
-          dqa[v].z = fmaf(da, e[v].z, dqa[v].z); dqa[v].w = fmaf(da, e[v].w, dqa[v].w);
-          red_add4(drow + 128 * v, da * q[v].x - db * e[v].x, da * q[v].y - db * e[v].y,
-                   da * q[v].z - db * e[v].z, da * q[v].w - db * e[v].w);
+        for (int t = 0; t < 4; ++t) {
+          const float* row = P.t0 + i0[t] * P.ldt0 + 4 * lane;    // (masked slots point at row 0)
+#pragma unroll
+          for (int v = 0; v < NV; ++v) e[t][v] = __ldg(reinterpret_cast<const float4*>(row + 128 * v));
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if (dl[t] == 0.f) continue;                  // warp-uniform
+          float* drow = P.dt0 + i0[t] * (int64_t) P.d0 + 4 * lane;
+          float a = 1.0f, bcoef = 0.f;  // d e = dl * (a * q - bcoef * e) ; d q += dl * a * e
+          if (L2) {
+            float dot = 0.f, nn = 0.f;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) { dot = dot4(q[v], e[t][v], dot); nn = dot4(e[t][v], e[t][v], nn); }
+            dot = warp_sum(dot);
+            nn = warp_sum(nn);
+            const float nrm = sqrtf(nn);
+            if (nrm > P.eps) { a = 1.0f / nrm; bcoef = dot / (nrm * nn); }
+            else { a = 1.0f / P.eps; bcoef = 0.f; }    // clamp branch: denominator is constant
+          }
+          const float da = dl[t] * a, db = dl[t] * bcoef;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            const float4 ev = e[t][v];
+            dqa[v].x = fmaf(da, ev.x, dqa[v].x); dqa[v].y = fmaf(da, ev.y, dqa[v].y);
+            dqa[v].z = fmaf(da, ev.z, dqa[v].z); dqa[v].w = fmaf(da, ev.w, dqa[v].w);
+            red_add4(drow + 128 * v, da * q[v].x - db * ev.x, da * q[v].y - db * ev.y,
+                     da * q[v].z - db * ev.z, da * q[v].w - db * ev.w);
+          }
         }
       }
     }
