@@ -58,7 +58,7 @@ def peaks() -> dict:
 
 
 class ClockSampler:
-    """SM clock / power / throttle reasons sampled every 200 ms while the timed region runs.
+    """SM clock / power / throttle reasons sampled every 50 ms while the timed region runs.
 
     In-process NVML (nvidia_ml_py): spawning `nvidia-smi -lms 200` next to the timed loop costs the
     training step ~40 % (its NVML session contends with kernel launches); the same counters read
@@ -103,7 +103,7 @@ class ClockSampler:
                 self.samples.append((sm, pw, rs))
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.05)
 
     def __exit__(self, *exc):
         self._stop.set()
@@ -531,8 +531,10 @@ def main():
         "ms_per_step": train["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": workload_config(cfg, world),
+        "cuda_graphs": os.environ.get("GRB_NO_GRAPHS") != "1",
         "clocks": train["clocks"], "e2e": train["e2e"], "gpu_launches": train["gpu_launches"],
-        "roofline": train.get("roofline"), "kernels": train["kernels"],
+        "roofline": train.get("roofline"), "roofline_others": train.get("roofline_others"),
+        "kernels": train["kernels"], "kernels_timed_in": train.get("kernels_timed_in"),
         "final_loss": train["final_loss"], "retrieval": retrieval,
     }
     if rank == 0:
