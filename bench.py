@@ -201,10 +201,11 @@ def run_training(args, world, rank, local):
     host = [synthetic_batch(cfg, ids, PER_GPU_BATCH, seed=1000 * rank + i) for i in range(n_batches)]
     totals = [int(b["history_lengths"].sum()) for b in host]
     if use_graphs:
-        # under DDP the graphs have to exist before the wrapper does (see HSTUJagged.enable_cuda_graphs)
-        model.enable_cuda_graphs(row_granularity=1024, lazy=(world == 1))
+        # the whole loss computation and its backward replay as one CUDA-graph pair per padded row
+        # count; under DDP the graphs have to exist before the wrapper does (RetrievalModel.enable_step_graphs)
+        model.enable_step_graphs(row_granularity=1024, lazy=(world == 1))
         if world > 1:
-            model.precapture_cuda_graphs(totals, PER_GPU_BATCH)
+            model.precapture_step_graphs([{k: v.to(dev) for k, v in b.items()} for b in host], totals)
     step_mod = TrainStep(model)
     if world > 1:
         step_mod = torch.nn.parallel.DistributedDataParallel(
@@ -268,7 +269,7 @@ def run_training(args, world, rank, local):
     prof = _lib.profile_stop()
     launches = (_lib.launch_count() - launches0) * args.steps // n_attr
     if use_graphs:
-        model.enable_cuda_graphs(row_granularity=1024, lazy=(world == 1))
+        model.enable_step_graphs(row_granularity=1024, lazy=(world == 1))
     barrier(world)
 
     seqs = PER_GPU_BATCH * world * args.steps

@@ -159,7 +159,7 @@ class InBatchNegativesSampler(NegativesSampler):
 
     def process_batch_prefix(self, ids: torch.Tensor, embeddings: torch.Tensor,
                              prefix_offsets: torch.Tensor, total: int,
-                             static_shapes: bool = False) -> None:
+                             static_shapes: bool = False, padded: bool = False) -> None:
         """``process_batch`` for the layout the training step has (generative_recommenders.py /
         retrieval.py:117-123): ids (B, N) whose non-zero entries are the first
         ``prefix_offsets[b+1] - prefix_offsets[b]`` of every row, ``total`` of them in all (known on
@@ -167,19 +167,28 @@ class InBatchNegativesSampler(NegativesSampler):
         of the rows, which needs no ``nonzero`` and therefore no device synchronisation; results
         are identical to ``process_batch(ids.view(-1), ids.view(-1) != 0, embeddings.view(-1, D))``."""
         from . import ops
-        valid_ids = ops.dense_to_jagged(ids.unsqueeze(-1), prefix_offsets, total=total).squeeze(-1)
-        valid_emb = ops.dense_to_jagged(embeddings, prefix_offsets, total=total)
+        # padded: ``total`` is an upper bound (fixed row bucket); the real count is prefix_offsets[-1]
+        valid_ids = ops.dense_to_jagged(ids.unsqueeze(-1), prefix_offsets, total=total,
+                                        zero_tail=padded).squeeze(-1)
+        valid_emb = ops.dense_to_jagged(embeddings, prefix_offsets, total=total, zero_tail=padded)
         if static_shapes and self._dedup_embeddings and total > 0:
-            self._cache_valid_static(valid_ids, valid_emb)
+            self._cache_valid_static(valid_ids, valid_emb, prefix_offsets[-1] if padded else None)
         else:
             self._cache_valid(valid_ids, valid_emb)
 
-    def _cache_valid_static(self, valid_ids: torch.Tensor, valid_emb: torch.Tensor) -> None:
+    def _cache_valid_static(self, valid_ids: torch.Tensor, valid_emb: torch.Tensor,
+                            n_valid: Optional[torch.Tensor] = None) -> None:
         """De-duplication without data-dependent shapes, hence without a device sync: the cache is
         padded to the number of valid ids and the number of distinct ids stays on the device
         (``_cached_count``).  Same order as ``torch.unique`` (ascending ids).  ``_draw`` then maps
         random bits onto [0, count) on the device."""
         n = valid_ids.numel()
+        if n_valid is not None:
+            # rows past n_valid (a device scalar) are padding: give them an id that sorts last and
+            # leave them out of the count
+            pos = torch.arange(n, device=valid_ids.device)
+            valid_ids = torch.where(pos < n_valid, valid_ids,
+                                    torch.full_like(valid_ids, torch.iinfo(torch.int64).max))
         sorted_ids, order = torch.sort(valid_ids)
         new = torch.ones(n, dtype=torch.bool, device=valid_ids.device)
         new[1:] = sorted_ids[1:] != sorted_ids[:-1]
@@ -190,7 +199,11 @@ class InBatchNegativesSampler(NegativesSampler):
         from . import functional as GF
         self._cached_embeddings = self._maybe_l2_norm(GF.embedding_lookup(valid_emb, rep, None))
         self._cached_ids = uniq
-        self._cached_count = rank[-1] + 1
+        if n_valid is None:
+            self._cached_count = rank[-1] + 1
+        else:
+            # (index_select, not rank[i]: indexing with a 0-dim tensor reads it on the host)
+            self._cached_count = rank.index_select(0, (n_valid - 1).clamp(min=0).view(1)).view(()) + 1
 
     def get_all_ids_and_embeddings(self) -> Tuple[torch.Tensor, torch.Tensor]:
         if getattr(self, "_cached_count", None) is not None:     # padded cache: trim (host sync)

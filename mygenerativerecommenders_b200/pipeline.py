@@ -67,6 +67,10 @@ def seq_features_from_row(row: Dict[str, torch.Tensor], device, max_output_lengt
     ts = row["historical_timestamps"].to(device, non_blocking=True)
     target_ids = row["target_ids"].to(device, non_blocking=True).unsqueeze(1)
     target_ts = row["target_timestamps"].to(device, non_blocking=True).unsqueeze(1)
+    return _features_on_device(lengths, ids, ts, target_ids, target_ts, max_output_length)
+
+
+def _features_on_device(lengths, ids, ts, target_ids, target_ts, max_output_length: int):
     if max_output_length > 0:
         ids = torch.nn.functional.pad(ids, (0, max_output_length))
         ts = torch.nn.functional.pad(ts, (0, max_output_length))
@@ -135,6 +139,23 @@ class L2NormPostprocessor(torch.nn.Module):
         return GF.l2_normalize(x, self._eps)
 
 
+class _StepStack(torch.nn.Module):
+    """What ``enable_step_graphs`` captures: device inputs -> loss, at a fixed row bucket.  Holds
+    the model without registering it as a child."""
+
+    def __init__(self, model: "RetrievalModel", t_pad: int) -> None:
+        super().__init__()
+        object.__setattr__(self, "_model", model)
+        self._t_pad = t_pad
+
+    def parameters(self, recurse: bool = True):
+        return self._model.parameters(recurse)
+
+    def forward(self, lengths, ids, ts, target_ids, target_ts):
+        return self._model._loss_impl(lengths, ids, ts, target_ids, target_ts,
+                                      total_length=self._t_pad, padded=True)
+
+
 class RetrievalModel(torch.nn.Module):
     """The retrieval task without Lightning: ``training_loss`` == the body of
     Retrieval.training_step up to the loss (retrieval.py:80-133); ``retrieve`` == :21-48."""
@@ -164,6 +185,9 @@ class RetrievalModel(torch.nn.Module):
         index_cls = ShardedCandidateIndex if sharded_index else CandidateIndex
         self.candidate_index = index_cls(k=cfg.top_k, ids=all_item_ids,
                                          top_k_module=MIPSBruteForceTopK())
+        self._step_graph_rows = 0
+        self._step_graph_lazy = True
+        object.__setattr__(self, "_step_graphs", {})
 
     def enable_cuda_graphs(self, row_granularity: int = 1024, lazy: bool = True) -> None:
         """Training only: run the HSTU layer stack as captured CUDA graphs (see
@@ -180,6 +204,50 @@ class RetrievalModel(torch.nn.Module):
 
     def disable_cuda_graphs(self) -> None:
         self.sequence_encoder._hstu.disable_cuda_graphs()
+        self._step_graph_rows = 0
+
+    def enable_step_graphs(self, row_granularity: int = 1024, lazy: bool = True) -> None:
+        """Training only: capture the WHOLE loss computation (embedding lookup, sampler cache,
+        pre-processor, HSTU stack, post-processor, sampled-softmax loss) and its backward as one
+        pair of CUDA graphs per padded row count.  Every jagged tensor is padded with zero rows to
+        the bucket, the in-batch cache is padded and masked by device-side counts, so nothing in the
+        step has a data-dependent shape.  The host side of a step is then two graph launches, the
+        optimizer and the input copies.  ``training_loss`` must be given ``total_length``.
+        Under DistributedDataParallel capture with ``precapture_step_graphs`` before wrapping."""
+        hstu = self.sequence_encoder._hstu
+        hstu.disable_cuda_graphs(drop=True)               # the stack is captured as part of the step
+        hstu.enable_cuda_graphs(row_granularity, lazy=False)
+        self._step_graph_rows = int(row_granularity)
+        self._step_graph_lazy = bool(lazy)
+
+    def precapture_step_graphs(self, rows, total_lengths) -> int:
+        for row, tot in zip(rows, total_lengths):
+            self._step_graph(self._device_inputs(row), int(tot), capture=True)
+        return len(self._step_graphs)
+
+    def _device_inputs(self, row):
+        dev = self.embeddings._item_emb.weight.device
+        return (row["history_lengths"].to(dev, non_blocking=True),
+                row["historical_ids"].to(dev, non_blocking=True),
+                row["historical_timestamps"].to(dev, non_blocking=True),
+                row["target_ids"].to(dev, non_blocking=True).view(-1, 1),
+                row["target_timestamps"].to(dev, non_blocking=True).view(-1, 1))
+
+    def _step_graph(self, inputs, total_length: int, capture: bool):
+        t_pad = -(-max(total_length, 1) // self._step_graph_rows) * self._step_graph_rows
+        key = (t_pad,) + tuple((tuple(t.shape), t.dtype) for t in inputs)
+        run = self._step_graphs.get(key)
+        if run is None and capture:
+            # a live autograd graph from an earlier eager step (the sampler's cache holds one) keeps
+            # the parameters' gradient accumulators bound to the stream they were made on, and a
+            # capture may not touch the default stream: drop it first
+            for name in ("_cached_embeddings", "_cached_ids", "_cached_count"):
+                if hasattr(self.negatives_sampler, name):
+                    setattr(self.negatives_sampler, name, None)
+            stack = _StepStack(self, t_pad)
+            run = torch.cuda.make_graphed_callables(stack, tuple(t.clone() for t in inputs))
+            self._step_graphs[key] = run
+        return run, t_pad
 
     # generative_recommenders.py:355-393
     def forward(self, sf: SequentialFeatures, total_length: Optional[int] = None,
@@ -196,8 +264,21 @@ class RetrievalModel(torch.nn.Module):
         return self.postprocessor(x)
 
     def training_loss(self, row: Dict[str, torch.Tensor], total_length: Optional[int] = None) -> torch.Tensor:
-        dev = self.embeddings._item_emb.weight.device
-        sf, target_ids = seq_features_from_row(row, dev, self.cfg.gr_output_length + 1)
+        inputs = self._device_inputs(row)
+        if (self._step_graph_rows and total_length is not None and self.training
+                and torch.is_grad_enabled() and inputs[0].is_cuda):
+            run, t_pad = self._step_graph(inputs, int(total_length), capture=self._step_graph_lazy)
+            if run is not None:
+                return run(*inputs)
+            return self._loss_impl(*inputs, total_length=t_pad, padded=True)
+        return self._loss_impl(*inputs, total_length=total_length, padded=False)
+
+    def _loss_impl(self, lengths, ids, ts, target_ids, target_ts, total_length: Optional[int],
+                   padded: bool) -> torch.Tensor:
+        """``padded``: ``total_length`` is a row bucket >= sum(lengths); every jagged tensor has that
+        many rows, the ones past the real total being zero (and weighing zero in the loss)."""
+        sf, target_ids = _features_on_device(lengths, ids, ts, target_ids, target_ts,
+                                             self.cfg.gr_output_length + 1)
         sf.past_ids.scatter_(dim=1, index=sf.past_lengths.view(-1, 1), src=target_ids.view(-1, 1))
         input_emb = self.embeddings.get_item_embeddings(sf.past_ids)
         sf = sf._replace(past_embeddings=input_emb)
@@ -214,7 +295,7 @@ class RetrievalModel(torch.nn.Module):
                 # reference looks up again (get_item_embeddings(flat)) are input_emb itself
                 self.negatives_sampler.process_batch_prefix(
                     sup_ids, input_emb, off + torch.arange(off.numel(), device=off.device, dtype=off.dtype),
-                    tot + sup_ids.size(0), static_shapes=True)
+                    tot + sup_ids.size(0), static_shapes=True, padded=padded)
             else:
                 flat = sup_ids.view(-1)
                 self.negatives_sampler.process_batch(
@@ -228,9 +309,10 @@ class RetrievalModel(torch.nn.Module):
         out_rows = self.forward(sf, total_length, jagged_output=True)
         jag = dict(
             output_embeddings=out_rows,
-            supervision_ids=ops.dense_to_jagged(sup_ids[:, 1:], off, total=tot),
-            supervision_embeddings=ops.dense_to_jagged(input_emb[:, 1:, :], off, total=tot),
-            supervision_weights=ops.dense_to_jagged((sup_ids[:, 1:] != 0).float(), off, total=tot),
+            supervision_ids=ops.dense_to_jagged(sup_ids[:, 1:], off, total=tot, zero_tail=padded),
+            supervision_embeddings=ops.dense_to_jagged(input_emb[:, 1:, :], off, total=tot, zero_tail=padded),
+            supervision_weights=ops.dense_to_jagged((sup_ids[:, 1:] != 0).float(), off, total=tot,
+                                                    zero_tail=padded),
         )
         return self.loss.jagged_forward(negatives_sampler=self.negatives_sampler,
                                         similarity=self.similarity, **jag)

@@ -132,3 +132,51 @@ def test_cuda_graph_layer_stack_matches_eager():
             scale = max(ge[k].abs().max().item(), 1e-8)
             # identical kernels; only the fp32 atomics (bias / embedding gradients) reorder
             assert (ge[k] - gg[k]).abs().max().item() <= 2e-3 * scale, k
+
+
+def test_whole_step_cuda_graph_matches_eager():
+    """enable_step_graphs: embedding lookup, in-batch cache, encoder, loss and their backward as one
+    captured graph pair over zero-padded rows == the eager, unpadded step (same draws)."""
+    cfg = RetrievalConfig(name="g", num_items=500, max_sequence_length=40, gr_output_length=5,
+                          embedding_dim=128, num_blocks=2, num_heads=2, attention_dim=64,
+                          linear_dim=64, dropout=0.0, sampler="inbatch", num_negatives=16, top_k=20,
+                          split_year_embedding=False, compute_dtype=torch.bfloat16)
+    ids = synthetic_item_ids(300, cfg.num_items, seed=1)
+    torch.manual_seed(0)
+    m = RetrievalModel(cfg, ids).to(DEV).train()
+    with torch.no_grad():
+        for p in m.embeddings.parameters():
+            p.mul_(10.0)
+    rows = [synthetic_batch(cfg, ids, 6, seed=s, min_len=2) for s in (3, 4, 5)]
+    fixed_raw = torch.randint(0, 2 ** 40, (1024, cfg.num_negatives), device=DEV)
+    smp = m.negatives_sampler
+
+    def draw(positive_ids, n):
+        count = smp._cached_count if smp._cached_count is not None else smp._cached_ids.size(0)
+        return fixed_raw[: positive_ids.size(0)] % count
+    smp._draw = draw
+
+    def run(graphs: bool):
+        if graphs:
+            m.enable_step_graphs(row_granularity=256)
+        else:
+            m.disable_cuda_graphs()
+        out = []
+        for row in rows:
+            n_rows = int(row["history_lengths"].sum())
+            m.zero_grad(set_to_none=True)
+            loss = m.training_loss({k: v.clone() for k, v in row.items()}, total_length=n_rows)
+            loss.backward()
+            out.append((loss.item(), {k: p.grad.clone() for k, p in m.named_parameters()
+                                      if p.grad is not None}))
+        return out
+
+    eager = run(False)
+    graphed = run(True)
+    assert len(m._step_graphs) == 1                  # one bucket serves all three batches
+    for (le, ge), (lg, gg) in zip(eager, graphed):
+        assert abs(le - lg) <= 1e-5 * abs(le)
+        assert ge.keys() == gg.keys()
+        for k in ge:
+            scale = max(ge[k].abs().max().item(), 1e-8)
+            assert (ge[k] - gg[k]).abs().max().item() <= 2e-3 * scale, k
