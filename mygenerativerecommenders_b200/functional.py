@@ -156,8 +156,8 @@ class _HstuAttention(torch.autograd.Function):
         d_ts = d_pos = None
         if timestamps is not None:
             # every CTA adds into d ts_w / d pos_w; with short sequences that is thousands of CTAs
-            # on a handful of cache lines.  Give them private copies (<= 16 MiB) and sum after.
-            copies = max(1, min(4096, (4 << 20) // max(1, pos_w.numel())))
+            # on a handful of cache lines.  Give them private copies (<= 256) and sum after.
+            copies = max(1, min(256, (4 << 20) // max(1, pos_w.numel())))
             d_ts = torch.zeros((copies, ts_w.numel()), dtype=torch.float32, device=q.device)
             d_pos = torch.zeros((copies, pos_w.numel()), dtype=torch.float32, device=q.device)
             a.d_ts_w, a.d_pos_w, a.d_bias_copies = d_ts.data_ptr(), d_pos.data_ptr(), copies

@@ -183,27 +183,44 @@ class InBatchNegativesSampler(NegativesSampler):
         (``_cached_count``).  Same order as ``torch.unique`` (ascending ids).  ``_draw`` then maps
         random bits onto [0, count) on the device."""
         n = valid_ids.numel()
-        if n_valid is not None:
-            # rows past n_valid (a device scalar) are padding: give them an id that sorts last and
-            # leave them out of the count
-            pos = torch.arange(n, device=valid_ids.device)
-            valid_ids = torch.where(pos < n_valid, valid_ids,
-                                    torch.full_like(valid_ids, torch.iinfo(torch.int64).max))
-        sorted_ids, order = torch.sort(valid_ids)
-        new = torch.ones(n, dtype=torch.bool, device=valid_ids.device)
-        new[1:] = sorted_ids[1:] != sorted_ids[:-1]
-        rank = torch.cumsum(new, 0) - 1
-        uniq = torch.zeros(n, dtype=torch.int64, device=valid_ids.device).scatter_(0, rank, sorted_ids)
-        # (slots past the count keep distinct positions; nothing samples them, their gradient is 0)
-        rep = torch.arange(n, dtype=torch.int64, device=valid_ids.device).scatter_(0, rank, order)
+        dev = valid_ids.device
+        pos = torch.arange(n, device=dev)
+        live = pos < n_valid if n_valid is not None else None     # rows past n_valid are padding
+        max_id = getattr(self, "max_item_id", None)
+        if max_id is not None and max_id < (1 << 22):
+            # small id space: direct addressing instead of a sort.  flags[id] = 1 for every id seen,
+            # rank = exclusive prefix sum, the distinct ids in ascending order are the set positions
+            key = valid_ids if live is None else torch.where(live, valid_ids, torch.zeros_like(valid_ids))
+            flags = torch.zeros(max_id + 2, dtype=torch.int64, device=dev)
+            flags.scatter_(0, key, torch.ones_like(key))
+            flags[0:1].zero_()                                     # id 0 is padding, never a member
+            rank_of_id = torch.cumsum(flags, 0) - flags            # exclusive prefix sum
+            count = flags.sum()
+            uniq = torch.nonzero_static(flags, size=n, fill_value=0).view(-1)
+            # one representative row per distinct id; rows that are no members (padding) all go to
+            # the last slot, which is free whenever such rows exist (count <= members < n)
+            slot = torch.where(key != 0, rank_of_id[key], torch.full_like(key, n - 1))
+            rep = torch.zeros(n, dtype=torch.int64, device=dev).scatter_(0, slot, pos)
+        else:
+            if live is not None:
+                valid_ids = torch.where(live, valid_ids,
+                                        torch.full_like(valid_ids, torch.iinfo(torch.int64).max))
+            sorted_ids, order = torch.sort(valid_ids)
+            new = torch.ones(n, dtype=torch.bool, device=dev)
+            new[1:] = sorted_ids[1:] != sorted_ids[:-1]
+            rank = torch.cumsum(new, 0) - 1
+            uniq = torch.zeros(n, dtype=torch.int64, device=dev).scatter_(0, rank, sorted_ids)
+            # (slots past the count keep distinct positions; nothing samples them, their gradient is 0)
+            rep = pos.clone().scatter_(0, rank, order)
+            if n_valid is None:
+                count = rank[-1] + 1
+            else:
+                # (index_select, not rank[i]: indexing with a 0-dim tensor reads it on the host)
+                count = rank.index_select(0, (n_valid - 1).clamp(min=0).view(1)).view(()) + 1
         from . import functional as GF
         self._cached_embeddings = self._maybe_l2_norm(GF.embedding_lookup(valid_emb, rep, None))
         self._cached_ids = uniq
-        if n_valid is None:
-            self._cached_count = rank[-1] + 1
-        else:
-            # (index_select, not rank[i]: indexing with a 0-dim tensor reads it on the host)
-            self._cached_count = rank.index_select(0, (n_valid - 1).clamp(min=0).view(1)).view(()) + 1
+        self._cached_count = count
 
     def get_all_ids_and_embeddings(self) -> Tuple[torch.Tensor, torch.Tensor]:
         if getattr(self, "_cached_count", None) is not None:     # padded cache: trim (host sync)

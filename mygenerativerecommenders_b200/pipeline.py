@@ -181,6 +181,7 @@ class RetrievalModel(torch.nn.Module):
         else:
             self.negatives_sampler = InBatchNegativesSampler(
                 l2_norm=True, l2_norm_eps=cfg.l2_eps, dedup_embeddings=True)
+            self.negatives_sampler.max_item_id = cfg.num_items     # enables the sort-free cache build
         self.loss = SampledSoftmaxLoss(cfg.num_negatives, cfg.temperature)
         index_cls = ShardedCandidateIndex if sharded_index else CandidateIndex
         self.candidate_index = index_cls(k=cfg.top_k, ids=all_item_ids,

@@ -251,7 +251,8 @@ def test_fused_sampled_softmax_vector_path(D, R, l2):
         assert (got.grad.cpu().double() - r.grad).abs().max().item() <= 2e-4 * scale, name
 
 
-def test_inbatch_static_cache_matches_unique_cache():
+@pytest.mark.parametrize("direct", [False, True])
+def test_inbatch_static_cache_matches_unique_cache(direct):
     """The sync-free in-batch cache (padded, count on the device) holds the same ids / embeddings as
     the torch.unique one, and its draws are uniform over [0, count)."""
     from mygenerativerecommenders_b200 import ops
@@ -268,10 +269,20 @@ def test_inbatch_static_cache_matches_unique_cache():
     total = int(lengths.sum()) + B
     dyn = InBatchNegativesSampler(True, 1e-6, True)
     sta = InBatchNegativesSampler(True, 1e-6, True)
+    if direct:
+        sta.max_item_id = 40            # direct-address build instead of the sort
     dyn.process_batch_prefix(ids, emb, off, total)
     sta.process_batch_prefix(ids, emb, off, total, static_shapes=True)
     c = int(sta._cached_count.item())
     assert c == dyn._cached_ids.numel() and sta._cached_ids.numel() == total
+    # the same with rows padded to a bucket (what the CUDA-graph step does)
+    pad = InBatchNegativesSampler(True, 1e-6, True)
+    if direct:
+        pad.max_item_id = 40
+    pad.process_batch_prefix(ids, emb, off, total + 37, static_shapes=True, padded=True)
+    p_ids, p_emb = pad.get_all_ids_and_embeddings()
+    assert torch.equal(p_ids, dyn._cached_ids)
+    assert torch.allclose(p_emb, dyn._cached_embeddings, atol=1e-7)
     a_ids, a_emb = sta.get_all_ids_and_embeddings()
     assert torch.equal(a_ids, dyn._cached_ids)
     assert torch.allclose(a_emb, dyn._cached_embeddings, atol=1e-7)
