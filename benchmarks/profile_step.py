@@ -15,7 +15,7 @@ torch.manual_seed(42)
 model = RetrievalModel(cfg, ids).to(dev).train()
 import os
 if os.environ.get("GRB_NO_GRAPHS") != "1":
-    model.enable_cuda_graphs()
+    model.enable_step_graphs()
 opt = torch.optim.AdamW(model.parameters(), lr=1e-3, betas=(0.9, 0.98), weight_decay=1e-3, fused=True)
 batches = [{k: v.to(dev) for k, v in synthetic_batch(cfg, ids, 128, seed=i).items()} for i in range(4)]
 totals = [int(b["history_lengths"].sum()) for b in batches]
@@ -41,4 +41,4 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
         step(i)
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=28, max_name_column_width=60))
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=22, max_name_column_width=60))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=90))
