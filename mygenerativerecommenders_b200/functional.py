@@ -229,6 +229,32 @@ class _LnGate(torch.autograd.Function):
         return dx, dgate, None
 
 
+class _LinearBias(torch.autograd.Function):
+    """F.linear(x, w, b) for 2-D x whose bias gradient is a (1, T) x (T, out) GEMM instead of
+    ATen's column reduction (25 us for a 14k x 256 bf16 gradient, 4 per step at the C2 shape)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        return torch.addmm(b, x, w.t())
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        g = g.contiguous()
+        dx = torch.mm(g, w) if ctx.needs_input_grad[0] else None
+        dw = torch.mm(g.t(), x) if ctx.needs_input_grad[1] else None
+        db = torch.mm(g.new_ones(1, g.shape[0]), g).view(-1) if ctx.needs_input_grad[2] else None
+        return dx, dw, db
+
+
+def linear_bias(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """x @ w.T + b (hstu.py:404-413 output projection)."""
+    if x.dim() == 2 and x.is_cuda and b is not None:
+        return _LinearBias.apply(x, w, b)
+    return torch.nn.functional.linear(x, w, b)
+
+
 class _L2Norm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, eps):

@@ -201,7 +201,7 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
 
         o_w = self._o.weight if self._o.weight.dtype == x.dtype else self._o.weight.to(x.dtype)
         o_b = self._o.bias if self._o.bias.dtype == x.dtype else self._o.bias.to(x.dtype)
-        new_outputs = F.linear(
+        new_outputs = GF.linear_bias(
             F.dropout(o_input, p=self._dropout_ratio, training=self.training), o_w, o_b) + x
 
         cache_state = None

@@ -134,12 +134,13 @@ def test_cuda_graph_layer_stack_matches_eager():
             assert (ge[k] - gg[k]).abs().max().item() <= 2e-3 * scale, k
 
 
-def test_whole_step_cuda_graph_matches_eager():
-    """enable_step_graphs: embedding lookup, in-batch cache, encoder, loss and their backward as one
+@pytest.mark.parametrize("sampler", ["inbatch", "local"])
+def test_whole_step_cuda_graph_matches_eager(sampler):
+    """enable_step_graphs: embedding lookup, sampler, encoder, loss and their backward as one
     captured graph pair over zero-padded rows == the eager, unpadded step (same draws)."""
     cfg = RetrievalConfig(name="g", num_items=500, max_sequence_length=40, gr_output_length=5,
                           embedding_dim=128, num_blocks=2, num_heads=2, attention_dim=64,
-                          linear_dim=64, dropout=0.0, sampler="inbatch", num_negatives=16, top_k=20,
+                          linear_dim=64, dropout=0.0, sampler=sampler, num_negatives=16, top_k=20,
                           split_year_embedding=False, compute_dtype=torch.bfloat16)
     ids = synthetic_item_ids(300, cfg.num_items, seed=1)
     torch.manual_seed(0)
@@ -152,6 +153,8 @@ def test_whole_step_cuda_graph_matches_eager():
     smp = m.negatives_sampler
 
     def draw(positive_ids, n):
+        if sampler == "local":
+            return smp._all_item_ids[fixed_raw[: positive_ids.size(0)] % smp._all_item_ids.numel()]
         count = smp._cached_count if smp._cached_count is not None else smp._cached_ids.size(0)
         return fixed_raw[: positive_ids.size(0)] % count
     smp._draw = draw
