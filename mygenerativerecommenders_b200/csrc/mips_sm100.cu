@@ -177,40 +177,63 @@ __global__ void __launch_bounds__(MsCfg<NQB>::threads, 1) mips_scores_sm100_kern
           tmem_ld32(tmem + lane_base + (ab * NQB + qq) * MIPS_TILE_N + c32 * 32, sv);
           tmem_ld_wait();
           if (!row_ok) continue;
+          // only the last item tile can run past X: everywhere else the per-score bound checks
+          // (64-bit compares) are skipped
+          const bool full = item0 + MIPS_TILE_N <= p.X;
           if (p.epi.mode == MIPS_EPI_STORE) {
             float* o = p.epi.out + row * p.epi.Xs + u * MIPS_TILE_N + c32 * 32;
+            if (full) {
 #pragma unroll
-            for (int v4 = 0; v4 < 8; ++v4) {
-              float4 f;
-              const int64_t ib = item0 + c32 * 32 + v4 * 4;
-              f.x = (ib + 0 < p.X) ? __uint_as_float(sv[v4 * 4 + 0]) : -INFINITY;
-              f.y = (ib + 1 < p.X) ? __uint_as_float(sv[v4 * 4 + 1]) : -INFINITY;
-              f.z = (ib + 2 < p.X) ? __uint_as_float(sv[v4 * 4 + 2]) : -INFINITY;
-              f.w = (ib + 3 < p.X) ? __uint_as_float(sv[v4 * 4 + 3]) : -INFINITY;
-              *reinterpret_cast<float4*>(o + v4 * 4) = f;
+              for (int v4 = 0; v4 < 8; ++v4)
+                *reinterpret_cast<uint4*>(o + v4 * 4) =
+                    make_uint4(sv[v4 * 4 + 0], sv[v4 * 4 + 1], sv[v4 * 4 + 2], sv[v4 * 4 + 3]);
+            } else {
+#pragma unroll
+              for (int v4 = 0; v4 < 8; ++v4) {
+                float4 f;
+                const int64_t ib = item0 + c32 * 32 + v4 * 4;
+                f.x = (ib + 0 < p.X) ? __uint_as_float(sv[v4 * 4 + 0]) : -INFINITY;
+                f.y = (ib + 1 < p.X) ? __uint_as_float(sv[v4 * 4 + 1]) : -INFINITY;
+                f.z = (ib + 2 < p.X) ? __uint_as_float(sv[v4 * 4 + 2]) : -INFINITY;
+                f.w = (ib + 3 < p.X) ? __uint_as_float(sv[v4 * 4 + 3]) : -INFINITY;
+                *reinterpret_cast<float4*>(o + v4 * 4) = f;
+              }
             }
           } else {
-            // cheap reject: most 32-score groups hold nothing above tau
-            float mx = __uint_as_float(sv[0]);
+            // cheap reject at two levels: most 32-score groups hold nothing above tau, and when one
+            // does, only the 8-score sub-group that holds it is walked (the walk is executed by the
+            // whole warp as soon as ONE of its 32 rows needs it, so it has to be short)
+            float m8[4];
 #pragma unroll
-            for (int c = 1; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(sv[c]));
-            if (mx >= tau) {
-              int cnt = 0;
+            for (int k = 0; k < 4; ++k) {
+              float m = __uint_as_float(sv[8 * k]);
 #pragma unroll
-              for (int c = 0; c < 32; ++c)
-                cnt += (__uint_as_float(sv[c]) >= tau && item0 + c32 * 32 + c < p.X) ? 1 : 0;
-              if (cnt) {  // one atomic per 32 scores
-                int slot = atomicAdd(p.epi.counts + row, cnt);
+              for (int c = 1; c < 8; ++c) m = fmaxf(m, __uint_as_float(sv[8 * k + c]));
+              m8[k] = m;
+            }
+            if (fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])) >= tau) {
+              const int lim = full ? 32 : (int) (p.X - (item0 + c32 * 32));   // valid scores in this group
+              const int32_t ibase = (int32_t) (item0 + c32 * 32);
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                  const float s = __uint_as_float(sv[c]);
-                  const int64_t item = item0 + c32 * 32 + c;
-                  if (s >= tau && item < p.X) {
-                    if (slot < p.epi.cap) {
-                      p.epi.cscores[row * p.epi.cap + slot] = s;
-                      p.epi.cidx[row * p.epi.cap + slot] = (int32_t) item;
+              for (int k = 0; k < 4; ++k) {
+                if (m8[k] >= tau) {
+                  int cnt = 0;
+#pragma unroll
+                  for (int c = 8 * k; c < 8 * k + 8; ++c)
+                    cnt += (__uint_as_float(sv[c]) >= tau && c < lim) ? 1 : 0;
+                  if (cnt) {  // one atomic per sub-group
+                    int slot = atomicAdd(p.epi.counts + row, cnt);
+#pragma unroll
+                    for (int c = 8 * k; c < 8 * k + 8; ++c) {
+                      const float sc = __uint_as_float(sv[c]);
+                      if (sc >= tau && c < lim) {
+                        if (slot < p.epi.cap) {
+                          p.epi.cscores[row * p.epi.cap + slot] = sc;
+                          p.epi.cidx[row * p.epi.cap + slot] = ibase + c;
+                        }
+                        ++slot;
+                      }
                     }
-                    ++slot;
                   }
                 }
               }
