@@ -163,6 +163,9 @@ def main():
         bench_attn("prof 1x8192 H4 full", 1, 8192, 4, [8192], bwd=True)
     if "mipsc4" in which:
         bench_mips("C4 B4096 X10M D256 k200 bf16", 4096, 10_000_000, 256, 200, torch.bfloat16)
+    if "attnc2" in which:
+        bench_attn("C2 128x U[20,200] N211 H4", 128, 211, 4,
+                   torch.randint(20, 201, (128,), generator=torch.Generator().manual_seed(0)))
     if "attnc5" in which:
         bench_attn("C5-slice 4x8192 H8 full", 4, 8192, 8, [8192] * 4)
     if "attnnobias" in which:
