@@ -142,11 +142,25 @@ class _HstuAttention(torch.autograd.Function):
         N, H, dqk, dv, max_len = ctx.dims
         dout = _rows_contiguous(dout)
         T = q.shape[0]
+        # one allocation (and, with padded rows, one fill) for the three gradients; one zero-filled
+        # fp32 workspace for the dQ accumulator and the privatised bias-gradient copies
         alloc = torch.zeros if ctx.rows_padded else torch.empty
-        dq = alloc((T, H * dqk), dtype=q.dtype, device=q.device)
-        dk = alloc((T, H * dqk), dtype=q.dtype, device=q.device)
-        dvv = alloc((T, H * dv), dtype=q.dtype, device=q.device)
-        dq_acc = torch.zeros((T, H * dqk), dtype=torch.float32, device=q.device)
+        if dqk == dv:
+            g3 = alloc((3, T, H * dqk), dtype=q.dtype, device=q.device)
+            dq, dk, dvv = g3[0], g3[1], g3[2]
+        else:
+            dq = alloc((T, H * dqk), dtype=q.dtype, device=q.device)
+            dk = alloc((T, H * dqk), dtype=q.dtype, device=q.device)
+            dvv = alloc((T, H * dv), dtype=q.dtype, device=q.device)
+        n_acc = T * H * dqk
+        copies = n_ts = n_pos = 0
+        if timestamps is not None:
+            # every CTA adds into d ts_w / d pos_w; with short sequences that is thousands of CTAs
+            # on a handful of cache lines.  Give them private copies (<= 256) and sum after.
+            copies = max(1, min(256, (4 << 20) // max(1, pos_w.numel())))
+            n_ts, n_pos = ts_w.numel(), pos_w.numel()
+        ws = torch.zeros(n_acc + copies * (n_ts + n_pos), dtype=torch.float32, device=q.device)
+        dq_acc = ws[:n_acc]
         a = _attn_args(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk, dv, max_len,
                        ctx.cache)
         a.dout, a.lddo = dout.data_ptr(), _ld(dout)
@@ -155,11 +169,8 @@ class _HstuAttention(torch.autograd.Function):
         a.dq_accum = dq_acc.data_ptr()
         d_ts = d_pos = None
         if timestamps is not None:
-            # every CTA adds into d ts_w / d pos_w; with short sequences that is thousands of CTAs
-            # on a handful of cache lines.  Give them private copies (<= 256) and sum after.
-            copies = max(1, min(256, (4 << 20) // max(1, pos_w.numel())))
-            d_ts = torch.zeros((copies, ts_w.numel()), dtype=torch.float32, device=q.device)
-            d_pos = torch.zeros((copies, pos_w.numel()), dtype=torch.float32, device=q.device)
+            d_ts = ws[n_acc:n_acc + copies * n_ts].view(copies, n_ts)
+            d_pos = ws[n_acc + copies * n_ts:].view(copies, n_pos)
             a.d_ts_w, a.d_pos_w, a.d_bias_copies = d_ts.data_ptr(), d_pos.data_ptr(), copies
         with _lib.timed("hstu_attn_bwd"):
             _lib.check(_lib.lib().grb_hstu_attn_bwd(C.byref(a), _lib.stream_ptr(q.device)))
