@@ -3,6 +3,7 @@
 // (o_input = u * norm(attn_output)).  gate == NULL gives the plain LayerNorm of :300.
 // HBM-bound: fwd reads x (+gate) once from HBM (re-reads hit L1), writes y.
 #include "common.cuh"
+#include <initializer_list>
 
 namespace grb {
 
@@ -82,6 +83,108 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_gate_bwd_kernel(
   }
 }
 
+// ---- bf16 rows of 256 / 512 / 1024 elements: every lane owns NCH chunks of 8 consecutive
+// elements (one 16-byte access each), the row lives in registers, each tensor is touched once ----
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[i]) : "f"(f[2 * i + 1]), "f"(f[2 * i]));
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <int NCH, bool GATE>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_gate_fwd_bf16v_kernel(
+    const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ gate,
+    int64_t ldg, __nv_bfloat16* __restrict__ y, int64_t ldy, float* __restrict__ mean,
+    float* __restrict__ rstd, int64_t rows, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t) blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  constexpr int W = 256 * NCH;
+  float xv[NCH][8], gv[GATE ? NCH : 1][8];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    unpack8(*reinterpret_cast<const uint4*>(x + row * ldx + 256 * k + 8 * lane), xv[k]);
+    if (GATE) unpack8(*reinterpret_cast<const uint4*>(gate + row * ldg + 256 * k + 8 * lane), gv[k]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s += xv[k][e];
+  }
+  const float mu = warp_sum(s) / (float) W;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < NCH; ++k)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { const float d = xv[k][e] - mu; q = fmaf(d, d, q); }
+  const float rs = rsqrtf(warp_sum(q) / (float) W + eps);
+  if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = (GATE ? gv[k][e] : 1.0f) * ((xv[k][e] - mu) * rs);
+    *reinterpret_cast<uint4*>(y + row * ldy + 256 * k + 8 * lane) = pack8(o);
+  }
+}
+
+template <int NCH, bool GATE>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_gate_bwd_bf16v_kernel(
+    const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ gate,
+    int64_t ldg, const __nv_bfloat16* __restrict__ dy, int64_t lddy, const float* __restrict__ mean,
+    const float* __restrict__ rstd, __nv_bfloat16* __restrict__ dx, int64_t lddx,
+    __nv_bfloat16* __restrict__ dgate, int64_t lddg, int64_t rows) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t) blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  constexpr int W = 256 * NCH;
+  const float mu = mean[row], rs = rstd[row];
+  float xh[NCH][8], dyv[NCH][8], dxh[NCH][8];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    float xv[8], gv[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + row * ldx + 256 * k + 8 * lane), xv);
+    unpack8(*reinterpret_cast<const uint4*>(dy + row * lddy + 256 * k + 8 * lane), dyv[k]);
+    if (GATE) unpack8(*reinterpret_cast<const uint4*>(gate + row * ldg + 256 * k + 8 * lane), gv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      xh[k][e] = (xv[e] - mu) * rs;
+      dxh[k][e] = dyv[k][e] * (GATE ? gv[e] : 1.0f);
+      s1 += dxh[k][e];
+      s2 = fmaf(dxh[k][e], xh[k][e], s2);
+    }
+  }
+  const float m1 = warp_sum(s1) / (float) W;
+  const float m2 = warp_sum(s2) / (float) W;
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    float o[8], og[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      o[e] = rs * (dxh[k][e] - m1 - xh[k][e] * m2);
+      og[e] = dyv[k][e] * xh[k][e];
+    }
+    *reinterpret_cast<uint4*>(dx + row * lddx + 256 * k + 8 * lane) = pack8(o);
+    if (GATE) *reinterpret_cast<uint4*>(dgate + row * lddg + 256 * k + 8 * lane) = pack8(og);
+  }
+}
+
+static bool ln_vec_ok(int64_t W, std::initializer_list<const void*> ptrs, std::initializer_list<int64_t> lds) {
+  if (W != 256 && W != 512 && W != 1024) return false;
+  for (const void* p : ptrs) if (p && (reinterpret_cast<uintptr_t>(p) & 15)) return false;
+  for (int64_t l : lds) if (l % 8) return false;
+  return true;
+}
+
 }  // namespace grb
 
 using namespace grb;
@@ -157,6 +260,16 @@ int grb_ln_gate_fwd(const void* x, int64_t ldx, const void* gate, int64_t ldg, v
   if (rows == 0) return GRB_OK;
   auto st = reinterpret_cast<cudaStream_t>(stream);
   const unsigned grid = (unsigned) ceil_div(rows, LN_WARPS);
+  if (dtype == GRB_BF16 && ln_vec_ok(W, {x, gate, y}, {ldx, gate ? ldg : 0, ldy})) {
+    auto X = (const __nv_bfloat16*) x; auto G = (const __nv_bfloat16*) gate; auto Y = (__nv_bfloat16*) y;
+#define GRB_LN_FWD(NCH)                                                                              \
+    if (gate) ln_gate_fwd_bf16v_kernel<NCH, true><<<grid, LN_WARPS * 32, 0, st>>>(X, ldx, G, ldg, Y, ldy, mean, rstd, rows, eps); \
+    else ln_gate_fwd_bf16v_kernel<NCH, false><<<grid, LN_WARPS * 32, 0, st>>>(X, ldx, G, ldg, Y, ldy, mean, rstd, rows, eps)
+    if (W == 256) { GRB_LN_FWD(1); } else if (W == 512) { GRB_LN_FWD(2); } else { GRB_LN_FWD(4); }
+#undef GRB_LN_FWD
+    GRB_LAUNCH_OK();
+    return GRB_OK;
+  }
   if (dtype == GRB_F32)
     ln_gate_fwd_kernel<float><<<grid, LN_WARPS * 32, 0, st>>>(
         (const float*) x, ldx, (const float*) gate, ldg, (float*) y, ldy, mean, rstd, rows,
@@ -181,6 +294,17 @@ int grb_ln_gate_bwd(const void* x, int64_t ldx, const void* gate, int64_t ldg, c
   if (rows == 0) return GRB_OK;
   auto st = reinterpret_cast<cudaStream_t>(stream);
   const unsigned grid = (unsigned) ceil_div(rows, LN_WARPS);
+  if (dtype == GRB_BF16 && ln_vec_ok(W, {x, gate, dy, dx, dgate}, {ldx, gate ? ldg : 0, lddy, lddx, dgate ? lddg : 0})) {
+    auto X = (const __nv_bfloat16*) x; auto G = (const __nv_bfloat16*) gate; auto DY = (const __nv_bfloat16*) dy;
+    auto DX = (__nv_bfloat16*) dx; auto DG = (__nv_bfloat16*) dgate;
+#define GRB_LN_BWD(NCH)                                                                              \
+    if (gate) ln_gate_bwd_bf16v_kernel<NCH, true><<<grid, LN_WARPS * 32, 0, st>>>(X, ldx, G, ldg, DY, lddy, mean, rstd, DX, lddx, DG, lddg, rows); \
+    else ln_gate_bwd_bf16v_kernel<NCH, false><<<grid, LN_WARPS * 32, 0, st>>>(X, ldx, G, ldg, DY, lddy, mean, rstd, DX, lddx, DG, lddg, rows)
+    if (W == 256) { GRB_LN_BWD(1); } else if (W == 512) { GRB_LN_BWD(2); } else { GRB_LN_BWD(4); }
+#undef GRB_LN_BWD
+    GRB_LAUNCH_OK();
+    return GRB_OK;
+  }
   if (dtype == GRB_F32)
     ln_gate_bwd_kernel<float><<<grid, LN_WARPS * 32, 0, st>>>(
         (const float*) x, ldx, (const float*) gate, ldg, (const float*) dy, lddy, mean, rstd,

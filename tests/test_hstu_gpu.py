@@ -121,7 +121,7 @@ def test_padded_rows_and_neighbour_sequences_do_not_leak():
     assert torch.equal(out[s:e], out1)
 
 
-@pytest.mark.parametrize("W", [50, 64, 256, 1000])
+@pytest.mark.parametrize("W", [50, 64, 256, 512, 1000, 1024])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_ln_gate_vs_torch(W, dtype):
     gen = torch.Generator().manual_seed(W)
