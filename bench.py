@@ -379,7 +379,7 @@ def run_retrieval(args, world, rank, local, X_total=10_000_000, B=4096, D=256, k
     def once(q):
         s, i = GF.mips_topk(q, items, item_ids, k)
         if world > 1:
-            s, i = merge_sharded_topk(s, i, k, world)
+            s, i = merge_sharded_topk(s, i, k, world, k_locals=[k] * world)   # peer-memory exchange
         return s, i
 
     steps = max(2, min(args.steps, 10))

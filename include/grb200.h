@@ -215,6 +215,18 @@ int grb_topk_select(const float* cand_scores, const int64_t* cand_ids, const int
                     int64_t* out_ids, grb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * N3 exchange (new; the reference keeps the whole corpus on every rank): each rank stores its
+ *     (rows, row_bytes) block of local top-k results into the same column block of EVERY peer's
+ *     gather buffer with peer-to-peer stores over NVLink / NVSwitch, so that after one cross-rank
+ *     barrier every rank holds the (rows, world * k) candidate matrix grb_topk_select merges.
+ *     dst: host array of n_dst device pointers (the peers' buffers, from a symmetric-memory
+ *     rendezvous; may include the local one).  row_bytes, strides and offsets multiples of 4.
+ * ------------------------------------------------------------------------------------------- */
+int grb_p2p_put_rows(const void* src, int64_t src_row_stride_bytes, void* const* dst, int32_t n_dst,
+                     int64_t dst_row_stride_bytes, int64_t dst_col_offset_bytes, int64_t rows,
+                     int64_t row_bytes, grb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * b4/b5 + b1 + b6  negatives_samples/negative_sampler.py:105-131,192-212 ; similarity/
  *     dot_product.py:61-64 ; losses/autoregressive_losses.py:259-306 — fused sampled softmax:
  *       e_r   = concat(table0[idx0[n,r]], table1[idx1[n,r]])        (table1 may be NULL)

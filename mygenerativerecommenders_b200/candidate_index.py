@@ -126,18 +126,88 @@ class ShardedCandidateIndex(CandidateIndex):
             query_embeddings=query_embeddings, item_embeddings_t=self._embeddings_t,
             item_ids=self._ids, k=k_local, sorted=True)
         if self._world > 1:
-            scores, ids = merge_sharded_topk(scores.float(), ids, k_prime, self._world, self._group)
+            per = -(-self._num_total // self._world)
+            k_locals = [min(k_prime, max(0, min((r + 1) * per, self._num_total) - min(r * per, self._num_total)))
+                        for r in range(self._world)]
+            scores, ids = merge_sharded_topk(scores.float(), ids, k_prime, self._world, self._group,
+                                             k_locals=k_locals)
         if invalid_ids is not None:
             ids, scores = _drop_invalid(ids, scores, invalid_ids, k)
         return ids, scores
 
 
-def merge_sharded_topk(scores: torch.Tensor, ids: torch.Tensor, k: int, world: int, group=None):
-    """All-gather per-shard (B, k_local) results and select the exact global top-k.
+class _PeerExchange:
+    """The exchange step of the sharded top-k over peer memory: every rank owns a symmetric
+    (rows, world * k) gather buffer for scores and one for ids; ``put`` stores the local (B, k)
+    block into its column block of every rank's buffer with peer-to-peer stores
+    (``grb_p2p_put_rows``), a cross-rank barrier on the stream makes them visible, and the merge
+    kernel reads the local buffer in place: no NCCL call, no host synchronisation, no transposing
+    copy.  One instance per (group, rows, k); ``GRB_NO_P2P=1`` or an unavailable symmetric-memory
+    backend falls back to the NCCL all-gather."""
 
-    Shards may hold fewer than k items; short shards are padded with (-inf, int64 max) so the
-    gathered tensor is rectangular.  Works with NCCL (CUDA) — the selection is a kernel."""
+    _cache: dict = {}
+    _broken = False
+
+    @classmethod
+    def get(cls, group, rows: int, k: int, world: int, device):
+        import os
+        if cls._broken or os.environ.get("GRB_NO_P2P") == "1" or device.type != "cuda" \
+                or dist.get_backend(group) != "nccl":
+            return None
+        key = (id(group), rows, k, world, device.index)
+        st = cls._cache.get(key)
+        if st is None:
+            try:
+                st = cls(group, rows, k, world, device)
+            except Exception as e:   # no symmetric memory on this platform: keep the NCCL path
+                cls._broken = True
+                import warnings
+                warnings.warn(f"grb200: peer-memory exchange unavailable ({e!r}); using NCCL all-gather")
+                return None
+            cls._cache[key] = st
+        return st
+
+    def __init__(self, group, rows: int, k: int, world: int, device) -> None:
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        pg = group if group is not None else dist.group.WORLD
+        self.rows, self.k, self.world = rows, k, world
+        self.rank = dist.get_rank(group)
+        self.scores = symm.empty((rows, world * k), dtype=torch.float32, device=device)
+        self.ids = symm.empty((rows, world * k), dtype=torch.int64, device=device)
+        self.h_scores = symm.rendezvous(self.scores, pg)
+        self.h_ids = symm.rendezvous(self.ids, pg)
+        mk = lambda ptrs: (C.c_void_p * world)(*[int(p) for p in ptrs])
+        self.dst_scores, self.dst_ids = mk(self.h_scores.buffer_ptrs), mk(self.h_ids.buffer_ptrs)
+
+    def exchange(self, scores: torch.Tensor, ids: torch.Tensor):
+        from . import _lib
+        B, k = scores.shape
+        scores, ids = scores.contiguous(), ids.contiguous()
+        stream = _lib.stream_ptr(scores.device)
+        self.h_scores.barrier(channel=0)      # every rank is done reading the previous round
+        for src, dst, es in ((scores, self.dst_scores, 4), (ids, self.dst_ids, 8)):
+            _lib.check(_lib.lib().grb_p2p_put_rows(
+                src.data_ptr(), k * es, dst, self.world, self.world * self.k * es,
+                self.rank * self.k * es, B, k * es, stream))
+        self.h_scores.barrier(channel=1)      # all blocks have landed everywhere
+        return self.scores[:B], self.ids[:B]
+
+
+def merge_sharded_topk(scores: torch.Tensor, ids: torch.Tensor, k: int, world: int, group=None,
+                       k_locals=None):
+    """Exchange per-shard (B, k_local) results and select the exact global top-k.
+
+    ``k_locals`` (every rank's k_local, known from the shard sizes without communication): when
+    they are all equal the exchange runs over peer memory (``_PeerExchange``); otherwise — shards
+    holding fewer than k items — short shards are padded with (-inf, int64 max) and the blocks go
+    through an NCCL all-gather.  The selection is a kernel either way."""
     B, kl = scores.shape
+    if k_locals is not None and len(set(k_locals)) == 1 and scores.is_cuda:
+        px = _PeerExchange.get(group, max(B, 1), kl, world, scores.device)
+        if px is not None:
+            cand_s, cand_i = px.exchange(scores, ids)
+            return GF.topk_merge(cand_s, cand_i, k)
     klen = torch.tensor([kl], device=scores.device, dtype=torch.int64)
     lens = [torch.zeros_like(klen) for _ in range(world)]
     dist.all_gather(lens, klen, group=group)

@@ -185,6 +185,22 @@ __global__ void gather_last_rows_kernel(const unsigned char* __restrict__ dense,
   }
 }
 
+// every rank's block of local results -> the same column block of each peer's gather buffer
+// (peer-to-peer stores; blockIdx.y = destination)
+constexpr int P2P_MAX_DST = 16;
+struct P2pDst { uint32_t* p[P2P_MAX_DST]; };
+__global__ void __launch_bounds__(256) p2p_put_rows_kernel(const uint32_t* __restrict__ src, int64_t src_ld,
+                                                           P2pDst dst, int64_t dst_ld, int64_t rows,
+                                                           int64_t words) {
+  uint32_t* out = dst.p[blockIdx.y];
+  const int64_t total = rows * words;
+  for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t) gridDim.x * blockDim.x) {
+    const int64_t r = i / words, c = i - r * words;
+    out[r * dst_ld + c] = src[r * src_ld + c];
+  }
+}
+
 }  // namespace grb
 
 using namespace grb;
@@ -252,6 +268,31 @@ int grb_gather_last_rows(const void* dense, const void* lengths, void* out, int6
   gather_last_rows_kernel<<<(unsigned) B, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const unsigned char*>(dense), lengths,
       reinterpret_cast<unsigned char*>(out), B, N, row_bytes, index_bits, vec, scatter);
+  GRB_LAUNCH_OK();
+  return GRB_OK;
+}
+
+int grb_p2p_put_rows(const void* src, int64_t src_row_stride_bytes, void* const* dst, int32_t n_dst,
+                     int64_t dst_row_stride_bytes, int64_t dst_col_offset_bytes, int64_t rows,
+                     int64_t row_bytes, grb_stream_t stream) {
+  using namespace grb;
+  GRB_REQUIRE(src && dst && n_dst > 0 && n_dst <= P2P_MAX_DST && rows >= 0 && row_bytes > 0,
+              GRB_ERR_INVALID_ARG, "p2p_put_rows: bad arguments");
+  GRB_REQUIRE(row_bytes % 4 == 0 && src_row_stride_bytes % 4 == 0 && dst_row_stride_bytes % 4 == 0 &&
+                  dst_col_offset_bytes % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0,
+              GRB_ERR_INVALID_ARG, "p2p_put_rows: sizes and strides must be multiples of 4 bytes");
+  if (rows == 0) return GRB_OK;
+  P2pDst d{};
+  for (int i = 0; i < n_dst; ++i) {
+    GRB_REQUIRE(dst[i] != nullptr, GRB_ERR_INVALID_ARG, "p2p_put_rows: null destination");
+    d.p[i] = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(dst[i]) + dst_col_offset_bytes);
+  }
+  const int64_t words = row_bytes / 4;
+  const int64_t total = rows * words;
+  const unsigned bx = (unsigned) (ceil_div(total, 256) < 4096 ? ceil_div(total, 256) : 4096);
+  p2p_put_rows_kernel<<<dim3(bx, (unsigned) n_dst), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint32_t*>(src), src_row_stride_bytes / 4, d, dst_row_stride_bytes / 4, rows,
+      words);
   GRB_LAUNCH_OK();
   return GRB_OK;
 }

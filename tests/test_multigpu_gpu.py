@@ -1,5 +1,5 @@
-"""N > 1 on real GPUs (skipped with fewer than 2 devices): corpus-sharded top-k with the NCCL
-all-gather + merge kernel must equal the single-GPU result bit for bit (ids) on every rank."""
+"""N > 1 on real GPUs (skipped with fewer than 2 devices): corpus-sharded top-k with the
+peer-memory exchange + merge kernel must equal the single-GPU result bit for bit on every rank."""
 import os
 
 import pytest
@@ -31,6 +31,15 @@ def _worker(rank, world, port, tmp):
     fi, fs = full.get_top_k_outputs(q, invalid_ids=invalid)
     assert torch.equal(si, fi), (si != fi).sum()
     assert torch.equal(ss, fs)
+    # the exchange went over peer memory (symmetric buffers + P2P stores), not NCCL ...
+    from mygenerativerecommenders_b200.candidate_index import _PeerExchange
+    assert _PeerExchange._cache and not _PeerExchange._broken
+    # ... and the buffers are reusable round after round (barrier on both sides of the puts)
+    for rep in range(3):
+        q2 = torch.roll(q, rep + 1, 0)
+        si2, ss2 = sharded.get_top_k_outputs(q2, invalid_ids=invalid)
+        fi2, fs2 = full.get_top_k_outputs(q2, invalid_ids=invalid)
+        assert torch.equal(si2, fi2) and torch.equal(ss2, fs2)
     torch.save(si.cpu(), f"{tmp}/ids_{rank}.pt")
     dist.barrier()
     dist.destroy_process_group()
