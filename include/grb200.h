@@ -279,6 +279,26 @@ int grb_rows_scatter_add(const float* grad, int64_t ld_grad, const int64_t* ids,
                          grb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Cross-rank barrier on the stream, over peer memory: every rank adds 1 to word `slot` of each
+ *     rank's signal array (system-scope release after its earlier stores / reds), then waits until
+ *     its own word reaches n_ranks * epoch.  signals: host array of n_ranks device pointers to
+ *     symmetric uint64 arrays (zero-initialised once); epoch counts this slot's barriers from 1.
+ * ------------------------------------------------------------------------------------------- */
+int grb_p2p_barrier(void* const* signals, int32_t n_ranks, int32_t rank, int32_t slot, int64_t epoch,
+                    grb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Data-parallel exchange of an embedding-table gradient over peer memory (new; the reference
+ *     all-reduces the dense table, configs/trainer/ddp.yaml): for every i with ids[i] != skip_id,
+ *     dst[r][ids[i], :] += scale * grad_table[ids[i], :] for each of the n_dst destinations (the
+ *     ranks' symmetric gradient buffers; red.global over NVLink / NVSwitch for the remote ones).
+ *     ids must be distinct (apart from skip_id).  grad_table, dst[r]: (V, D) fp32 contiguous.
+ * ------------------------------------------------------------------------------------------- */
+int grb_p2p_rows_add(const float* grad_table, const int64_t* ids, int64_t n, int32_t D,
+                     int64_t num_rows, int64_t skip_id, float scale, void* const* dst, int32_t n_dst,
+                     grb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Building-block self test (tcgen05 descriptors, TMA swizzle, TMEM layouts).  Runs tiny GEMMs
  * in every operand mode the attention / retrieval kernels use and writes max-abs errors to
  * host array errs[n_modes].  Returns the number of modes run, or a negative error code.

@@ -168,29 +168,24 @@ class _PeerExchange:
         return st
 
     def __init__(self, group, rows: int, k: int, world: int, device) -> None:
-        import ctypes as C
-        import torch.distributed._symmetric_memory as symm
-        pg = group if group is not None else dist.group.WORLD
+        from .peer import PeerBarrier, symmetric_empty
         self.rows, self.k, self.world = rows, k, world
         self.rank = dist.get_rank(group)
-        self.scores = symm.empty((rows, world * k), dtype=torch.float32, device=device)
-        self.ids = symm.empty((rows, world * k), dtype=torch.int64, device=device)
-        self.h_scores = symm.rendezvous(self.scores, pg)
-        self.h_ids = symm.rendezvous(self.ids, pg)
-        mk = lambda ptrs: (C.c_void_p * world)(*[int(p) for p in ptrs])
-        self.dst_scores, self.dst_ids = mk(self.h_scores.buffer_ptrs), mk(self.h_ids.buffer_ptrs)
+        self.scores, self._hs, self.dst_scores = symmetric_empty((rows, world * k), torch.float32, device, group)
+        self.ids, self._hi, self.dst_ids = symmetric_empty((rows, world * k), torch.int64, device, group)
+        self.sync = PeerBarrier(group, device)
 
     def exchange(self, scores: torch.Tensor, ids: torch.Tensor):
         from . import _lib
         B, k = scores.shape
         scores, ids = scores.contiguous(), ids.contiguous()
         stream = _lib.stream_ptr(scores.device)
-        self.h_scores.barrier(channel=0)      # every rank is done reading the previous round
+        self.sync.barrier(0, scores.device)   # every rank is done reading the previous round
         for src, dst, es in ((scores, self.dst_scores, 4), (ids, self.dst_ids, 8)):
             _lib.check(_lib.lib().grb_p2p_put_rows(
                 src.data_ptr(), k * es, dst, self.world, self.world * self.k * es,
                 self.rank * self.k * es, B, k * es, stream))
-        self.h_scores.barrier(channel=1)      # all blocks have landed everywhere
+        self.sync.barrier(1, scores.device)   # all blocks have landed everywhere
         return self.scores[:B], self.ids[:B]
 
 

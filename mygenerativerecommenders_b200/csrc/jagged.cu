@@ -201,6 +201,20 @@ __global__ void __launch_bounds__(256) p2p_put_rows_kernel(const uint32_t* __res
   }
 }
 
+// stream barrier across ranks: see grb_p2p_barrier
+struct P2pSig { unsigned long long* p[P2P_MAX_DST]; };
+__global__ void __launch_bounds__(32) p2p_barrier_kernel(P2pSig sig, int n_ranks, int rank, int slot,
+                                                         unsigned long long target) {
+  __threadfence_system();                       // earlier peer stores / reds of this stream first
+  if ((int) threadIdx.x < n_ranks)
+    atomicAdd_system(sig.p[threadIdx.x] + slot, 1ull);
+  if (threadIdx.x == 0) {
+    volatile unsigned long long* mine = sig.p[rank] + slot;
+    while (*mine < target) __nanosleep(40);
+    __threadfence_system();
+  }
+}
+
 }  // namespace grb
 
 using namespace grb;
@@ -293,6 +307,23 @@ int grb_p2p_put_rows(const void* src, int64_t src_row_stride_bytes, void* const*
   p2p_put_rows_kernel<<<dim3(bx, (unsigned) n_dst), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const uint32_t*>(src), src_row_stride_bytes / 4, d, dst_row_stride_bytes / 4, rows,
       words);
+  GRB_LAUNCH_OK();
+  return GRB_OK;
+}
+
+int grb_p2p_barrier(void* const* signals, int32_t n_ranks, int32_t rank, int32_t slot, int64_t epoch,
+                    grb_stream_t stream) {
+  using namespace grb;
+  GRB_REQUIRE(signals && n_ranks > 0 && n_ranks <= P2P_MAX_DST && rank >= 0 && rank < n_ranks &&
+                  slot >= 0 && epoch > 0,
+              GRB_ERR_INVALID_ARG, "p2p_barrier: bad arguments");
+  P2pSig s{};
+  for (int i = 0; i < n_ranks; ++i) {
+    GRB_REQUIRE(signals[i] != nullptr, GRB_ERR_INVALID_ARG, "p2p_barrier: null signal array");
+    s.p[i] = reinterpret_cast<unsigned long long*>(signals[i]);
+  }
+  p2p_barrier_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      s, n_ranks, rank, slot, (unsigned long long) n_ranks * (unsigned long long) epoch);
   GRB_LAUNCH_OK();
   return GRB_OK;
 }

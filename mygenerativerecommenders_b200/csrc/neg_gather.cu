@@ -354,6 +354,27 @@ __global__ void __launch_bounds__(256) rows_scatter_add_kernel(const float* __re
   }
 }
 
+// dst[r][ids[i], :] += scale * src[ids[i], :] for every destination r: one warp per (row, destination)
+struct RowsDst { float* p[16]; };
+__global__ void __launch_bounds__(256) p2p_rows_add_kernel(const float* __restrict__ src,
+                                                           const int64_t* __restrict__ ids, int64_t n,
+                                                           int D, int64_t num_rows, int64_t skip, float scale,
+                                                           RowsDst dst) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t) blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const int64_t id = ids[i];
+  if (id == skip || id < 0 || id >= num_rows) return;
+  const float* row = src + id * (int64_t) D;
+  float* out = dst.p[blockIdx.y] + id * (int64_t) D;
+  for (int c = 4 * lane; c < D; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(row + c);
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + c), "f"(v.x * scale),
+                 "f"(v.y * scale), "f"(v.z * scale), "f"(v.w * scale)
+                 : "memory");
+  }
+}
+
 static int make(const grb_ssl_args* a, SslP* P, bool bwd) {
   GRB_REQUIRE(a != nullptr, GRB_ERR_INVALID_ARG, "sampled_softmax: null args");
   GRB_REQUIRE(a->dtype == GRB_F32, GRB_ERR_UNSUPPORTED, "sampled_softmax: only fp32 tables");
@@ -452,6 +473,27 @@ int grb_rows_scatter_add(const float* grad, int64_t ld_grad, const int64_t* ids,
                    ((reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(table_grad)) & 15) == 0;
   if (vec) rows_scatter_add_kernel<true><<<grid, 256, 0, st>>>(grad, ld_grad, ids, table_grad, n, D, num_rows, skip_id);
   else rows_scatter_add_kernel<false><<<grid, 256, 0, st>>>(grad, ld_grad, ids, table_grad, n, D, num_rows, skip_id);
+  GRB_LAUNCH_OK();
+  return GRB_OK;
+}
+
+int grb_p2p_rows_add(const float* grad_table, const int64_t* ids, int64_t n, int32_t D,
+                     int64_t num_rows, int64_t skip_id, float scale, void* const* dst, int32_t n_dst,
+                     grb_stream_t stream) {
+  using namespace grb;
+  GRB_REQUIRE(grad_table && ids && dst && n >= 0 && D > 0 && D % 4 == 0 && num_rows > 0 && n_dst > 0 &&
+                  n_dst <= 16,
+              GRB_ERR_INVALID_ARG, "p2p_rows_add: bad arguments (D must be a multiple of 4)");
+  if (n == 0) return GRB_OK;
+  RowsDst d{};
+  for (int i = 0; i < n_dst; ++i) {
+    GRB_REQUIRE(dst[i] != nullptr && (reinterpret_cast<uintptr_t>(dst[i]) & 15) == 0, GRB_ERR_INVALID_ARG,
+                "p2p_rows_add: destinations must be 16-byte aligned");
+    d.p[i] = reinterpret_cast<float*>(dst[i]);
+  }
+  p2p_rows_add_kernel<<<dim3((unsigned) ceil_div(n, 8), (unsigned) n_dst), 256, 0,
+                        reinterpret_cast<cudaStream_t>(stream)>>>(grad_table, ids, n, D, num_rows, skip_id,
+                                                                  scale, d);
   GRB_LAUNCH_OK();
   return GRB_OK;
 }

@@ -139,6 +139,61 @@ class L2NormPostprocessor(torch.nn.Module):
         return GF.l2_normalize(x, self._eps)
 
 
+class PeerTableGrads:
+    """Data-parallel exchange of the item-table gradient over peer memory instead of a dense
+    all-reduce (the reference all-reduces the whole (V, D) table under Lightning DDP; at the ml-20m
+    shape that is 134 MB per step although a batch touches ~11 k rows).
+
+    Every rank owns a symmetric (V, D) fp32 buffer.  After backward, each rank adds
+    ``local_grad[row] / world`` for the rows its batch touched into EVERY rank's buffer
+    (``grb_p2p_rows_add``: red.global over NVLink for the remote ones), between two cross-rank
+    stream barriers; the buffer then is the averaged gradient and replaces ``weight.grad``.
+    Traffic per rank: touched_rows x D x 4 bytes per peer.  Exclude the parameter from DDP
+    (``ddp_ignore_names``) — this object does its reduction."""
+
+    def __init__(self, weight: torch.nn.Parameter, group=None) -> None:
+        import torch.distributed as dist
+        from .peer import PeerBarrier, symmetric_empty
+        self.weight = weight
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.buf, self._h, self.dst = symmetric_empty(weight.shape, torch.float32, weight.device, group)
+        self.sync = PeerBarrier(group, weight.device)
+        self.touched: Optional[torch.Tensor] = None
+        dist.broadcast(weight.data, src=dist.get_global_rank(self.group, 0), group=group)
+        weight.register_post_accumulate_grad_hook(self._hook)
+
+    @torch.no_grad()
+    def note_ids(self, *id_tensors: torch.Tensor) -> None:
+        """Record the table rows this step's batch reads (distinct ids, padded with 0 = skipped).
+        Static shapes, no host synchronisation."""
+        V = self.weight.shape[0]
+        flags = torch.zeros(V, dtype=torch.bool, device=self.weight.device)
+        n = 0
+        for t in id_tensors:
+            flags.index_fill_(0, t.reshape(-1), True)
+            n += t.numel()
+        flags[0:1].zero_()
+        self.touched = torch.nonzero_static(flags, size=n, fill_value=0).view(-1)
+
+    def _hook(self, param: torch.nn.Parameter) -> None:
+        from . import _lib
+        if self.touched is None or param.grad is None:
+            raise RuntimeError("PeerTableGrads: note_ids() was not called for this step")
+        g = param.grad
+        if g.dtype != torch.float32 or not g.is_contiguous():
+            g = g.float().contiguous()
+        V, D = g.shape
+        self.buf.zero_()
+        self.sync.barrier(0, g.device)     # every buffer is zeroed, nobody still reads the last one
+        _lib.check(_lib.lib().grb_p2p_rows_add(
+            g.data_ptr(), self.touched.data_ptr(), self.touched.numel(), D, V, 0, 1.0 / self.world,
+            self.dst, self.world, _lib.stream_ptr(g.device)))
+        self.sync.barrier(1, g.device)     # every rank's rows have landed everywhere
+        param.grad = self.buf
+        self.touched = None
+
+
 class _StepStack(torch.nn.Module):
     """What ``enable_step_graphs`` captures: device inputs -> loss, at a fixed row bucket.  Holds
     the model without registering it as a child."""
@@ -189,6 +244,7 @@ class RetrievalModel(torch.nn.Module):
         self._step_graph_rows = 0
         self._step_graph_lazy = True
         object.__setattr__(self, "_step_graphs", {})
+        object.__setattr__(self, "_peer_grads", None)
 
     def enable_cuda_graphs(self, row_granularity: int = 1024, lazy: bool = True) -> None:
         """Training only: run the HSTU layer stack as captured CUDA graphs (see
@@ -220,6 +276,18 @@ class RetrievalModel(torch.nn.Module):
         hstu.enable_cuda_graphs(row_granularity, lazy=False)
         self._step_graph_rows = int(row_granularity)
         self._step_graph_lazy = bool(lazy)
+
+    def enable_peer_table_grads(self, group=None):
+        """Multi-GPU training: reduce the item-table gradient over peer memory (PeerTableGrads)
+        instead of DDP's dense all-reduce.  Call after the model is on its device and BEFORE
+        wrapping in DistributedDataParallel; returns the parameter names (relative to this module)
+        that DDP must be told to ignore."""
+        if not isinstance(self.negatives_sampler, InBatchNegativesSampler):
+            # LocalNegativesSampler reads (and back-propagates into) random rows of the whole table:
+            # the rows a step touches are then not the batch's ids and the sparse exchange is moot
+            raise NotImplementedError("enable_peer_table_grads needs the in-batch negatives sampler")
+        object.__setattr__(self, "_peer_grads", PeerTableGrads(self.embeddings._item_emb.weight, group))
+        return ["embeddings._item_emb.weight"]
 
     def precapture_step_graphs(self, rows, total_lengths) -> int:
         for row, tot in zip(rows, total_lengths):
@@ -266,6 +334,8 @@ class RetrievalModel(torch.nn.Module):
 
     def training_loss(self, row: Dict[str, torch.Tensor], total_length: Optional[int] = None) -> torch.Tensor:
         inputs = self._device_inputs(row)
+        if self._peer_grads is not None and self.training and torch.is_grad_enabled():
+            self._peer_grads.note_ids(inputs[1], inputs[3])      # history ids, target ids
         if (self._step_graph_rows and total_length is not None and self.training
                 and torch.is_grad_enabled() and inputs[0].is_cuda):
             run, t_pad = self._step_graph(inputs, int(total_length), capture=self._step_graph_lazy)
