@@ -210,9 +210,13 @@ def run_training(args, world, rank, local):
     if world > 1:
         if os.environ.get("GRB_NO_P2P") != "1":
             # the 134 MB item-table gradient is exchanged over peer memory (touched rows only)
-            ignore = ["model." + n for n in model.enable_peer_table_grads()]
-            torch.nn.parallel.DistributedDataParallel._set_params_and_buffers_to_ignore_for_model(
-                step_mod, ignore)
+            try:
+                ignore = ["model." + n for n in model.enable_peer_table_grads()]
+                torch.nn.parallel.DistributedDataParallel._set_params_and_buffers_to_ignore_for_model(
+                    step_mod, ignore)
+            except Exception as e:   # no symmetric memory between these GPUs: dense all-reduce by DDP
+                print(f"[bench] peer-memory table gradients unavailable ({e!r}); using DDP all-reduce",
+                      file=sys.stderr)
         step_mod = torch.nn.parallel.DistributedDataParallel(
             step_mod, device_ids=[local], gradient_as_bucket_view=True, broadcast_buffers=False)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3, betas=(0.9, 0.98), weight_decay=1e-3,
