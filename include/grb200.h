@@ -289,14 +289,17 @@ int grb_p2p_barrier(void* const* signals, int32_t n_ranks, int32_t rank, int32_t
 
 /* ---------------------------------------------------------------------------------------------
  * Data-parallel exchange of an embedding-table gradient over peer memory (new; the reference
- *     all-reduces the dense table, configs/trainer/ddp.yaml): for every i with ids[i] != skip_id,
- *     dst[r][ids[i], :] += scale * grad_table[ids[i], :] for each of the n_dst destinations (the
- *     ranks' symmetric gradient buffers; red.global over NVLink / NVSwitch for the remote ones).
- *     ids must be distinct (apart from skip_id).  grad_table, dst[r]: (V, D) fp32 contiguous.
+ *     all-reduces the dense table, configs/trainer/ddp.yaml).  Sender side: for i < n, slot
+ *     s = slot_offset + i of every destination r gets  dst_ids[r][s] = ids[i]  and, when ids[i] is a
+ *     real row (!= skip_id, in range),  dst_rows[r][s, :] = scale * grad_table[ids[i], :]  — plain
+ *     16-byte stores over NVLink / NVSwitch.  After a barrier the receiver scatter-adds its staging
+ *     buffer into its dense gradient with grb_rows_scatter_add (local atomics only).
+ *     grad_table (V, D) fp32 contiguous; dst_rows[r] (slots, D) fp32; dst_ids[r] (slots) int64.
  * ------------------------------------------------------------------------------------------- */
-int grb_p2p_rows_add(const float* grad_table, const int64_t* ids, int64_t n, int32_t D,
-                     int64_t num_rows, int64_t skip_id, float scale, void* const* dst, int32_t n_dst,
-                     grb_stream_t stream);
+int grb_p2p_put_table_rows(const float* grad_table, const int64_t* ids, int64_t n, int32_t D,
+                           int64_t num_rows, int64_t skip_id, float scale, void* const* dst_rows,
+                           void* const* dst_ids, int32_t n_dst, int64_t slot_offset,
+                           grb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Building-block self test (tcgen05 descriptors, TMA swizzle, TMEM layouts).  Runs tiny GEMMs

@@ -354,24 +354,24 @@ __global__ void __launch_bounds__(256) rows_scatter_add_kernel(const float* __re
   }
 }
 
-// dst[r][ids[i], :] += scale * src[ids[i], :] for every destination r: one warp per (row, destination)
-struct RowsDst { float* p[16]; };
-__global__ void __launch_bounds__(256) p2p_rows_add_kernel(const float* __restrict__ src,
-                                                           const int64_t* __restrict__ ids, int64_t n,
-                                                           int D, int64_t num_rows, int64_t skip, float scale,
-                                                           RowsDst dst) {
+// sender side of the table-gradient exchange: one warp per (slot, destination), 16-byte stores
+struct RowsDst { float* rows[16]; int64_t* ids[16]; };
+__global__ void __launch_bounds__(256) p2p_put_table_rows_kernel(const float* __restrict__ src,
+                                                                 const int64_t* __restrict__ ids, int64_t n,
+                                                                 int D, int64_t num_rows, int64_t skip,
+                                                                 float scale, RowsDst dst, int64_t slot0) {
   const int lane = threadIdx.x & 31;
   const int64_t i = (int64_t) blockIdx.x * 8 + (threadIdx.x >> 5);
   if (i >= n) return;
   const int64_t id = ids[i];
-  if (id == skip || id < 0 || id >= num_rows) return;
+  const bool real = id != skip && id >= 0 && id < num_rows;
+  if (lane == 0) dst.ids[blockIdx.y][slot0 + i] = real ? id : skip;
+  if (!real) return;
   const float* row = src + id * (int64_t) D;
-  float* out = dst.p[blockIdx.y] + id * (int64_t) D;
+  float* out = dst.rows[blockIdx.y] + (slot0 + i) * (int64_t) D;
   for (int c = 4 * lane; c < D; c += 128) {
     const float4 v = *reinterpret_cast<const float4*>(row + c);
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + c), "f"(v.x * scale),
-                 "f"(v.y * scale), "f"(v.z * scale), "f"(v.w * scale)
-                 : "memory");
+    *reinterpret_cast<float4*>(out + c) = make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale);
   }
 }
 
@@ -477,23 +477,26 @@ int grb_rows_scatter_add(const float* grad, int64_t ld_grad, const int64_t* ids,
   return GRB_OK;
 }
 
-int grb_p2p_rows_add(const float* grad_table, const int64_t* ids, int64_t n, int32_t D,
-                     int64_t num_rows, int64_t skip_id, float scale, void* const* dst, int32_t n_dst,
-                     grb_stream_t stream) {
+int grb_p2p_put_table_rows(const float* grad_table, const int64_t* ids, int64_t n, int32_t D,
+                           int64_t num_rows, int64_t skip_id, float scale, void* const* dst_rows,
+                           void* const* dst_ids, int32_t n_dst, int64_t slot_offset,
+                           grb_stream_t stream) {
   using namespace grb;
-  GRB_REQUIRE(grad_table && ids && dst && n >= 0 && D > 0 && D % 4 == 0 && num_rows > 0 && n_dst > 0 &&
-                  n_dst <= 16,
-              GRB_ERR_INVALID_ARG, "p2p_rows_add: bad arguments (D must be a multiple of 4)");
+  GRB_REQUIRE(grad_table && ids && dst_rows && dst_ids && n >= 0 && D > 0 && D % 4 == 0 && num_rows > 0 &&
+                  n_dst > 0 && n_dst <= 16 && slot_offset >= 0,
+              GRB_ERR_INVALID_ARG, "p2p_put_table_rows: bad arguments (D must be a multiple of 4)");
   if (n == 0) return GRB_OK;
   RowsDst d{};
   for (int i = 0; i < n_dst; ++i) {
-    GRB_REQUIRE(dst[i] != nullptr && (reinterpret_cast<uintptr_t>(dst[i]) & 15) == 0, GRB_ERR_INVALID_ARG,
-                "p2p_rows_add: destinations must be 16-byte aligned");
-    d.p[i] = reinterpret_cast<float*>(dst[i]);
+    GRB_REQUIRE(dst_rows[i] != nullptr && dst_ids[i] != nullptr &&
+                    (reinterpret_cast<uintptr_t>(dst_rows[i]) & 15) == 0,
+                GRB_ERR_INVALID_ARG, "p2p_put_table_rows: bad destination");
+    d.rows[i] = reinterpret_cast<float*>(dst_rows[i]);
+    d.ids[i] = reinterpret_cast<int64_t*>(dst_ids[i]);
   }
-  p2p_rows_add_kernel<<<dim3((unsigned) ceil_div(n, 8), (unsigned) n_dst), 256, 0,
-                        reinterpret_cast<cudaStream_t>(stream)>>>(grad_table, ids, n, D, num_rows, skip_id,
-                                                                  scale, d);
+  p2p_put_table_rows_kernel<<<dim3((unsigned) ceil_div(n, 8), (unsigned) n_dst), 256, 0,
+                              reinterpret_cast<cudaStream_t>(stream)>>>(grad_table, ids, n, D, num_rows,
+                                                                        skip_id, scale, d, slot_offset);
   GRB_LAUNCH_OK();
   return GRB_OK;
 }

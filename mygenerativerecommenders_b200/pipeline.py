@@ -144,12 +144,13 @@ class PeerTableGrads:
     all-reduce (the reference all-reduces the whole (V, D) table under Lightning DDP; at the ml-20m
     shape that is 134 MB per step although a batch touches ~11 k rows).
 
-    Every rank owns a symmetric (V, D) fp32 buffer.  After backward, each rank adds
-    ``local_grad[row] / world`` for the rows its batch touched into EVERY rank's buffer
-    (``grb_p2p_rows_add``: red.global over NVLink for the remote ones), between two cross-rank
-    stream barriers; the buffer then is the averaged gradient and replaces ``weight.grad``.
-    Traffic per rank: touched_rows x D x 4 bytes per peer.  Exclude the parameter from DDP
-    (``ddp_ignore_names``) — this object does its reduction."""
+    Every rank owns a symmetric staging buffer with one (cap, D) block of rows + ids per source
+    rank.  After backward each rank stores ``local_grad[row] / world`` for the rows its batch
+    touched into its block on EVERY rank (``grb_p2p_put_table_rows``: plain 16-byte stores over
+    NVLink / NVSwitch — remote atomics are several times slower), a stream barrier, then each
+    rank scatter-adds its staging buffer into a zeroed dense gradient with local atomics
+    (``grb_rows_scatter_add``); that becomes ``weight.grad``.  Traffic per rank: touched_rows x D x 4
+    bytes per peer.  Exclude the parameter from DDP — this object does its reduction."""
 
     def __init__(self, weight: torch.nn.Parameter, group=None) -> None:
         import torch.distributed as dist
@@ -157,8 +158,9 @@ class PeerTableGrads:
         self.weight = weight
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.buf, self._h, self.dst = symmetric_empty(weight.shape, torch.float32, weight.device, group)
+        self.buf = torch.zeros_like(weight, dtype=torch.float32)   # the reduced gradient (local)
         self.sync = PeerBarrier(group, weight.device)
+        self.cap = 0                       # staging rows per source rank, fixed by the first batch
         self.touched: Optional[torch.Tensor] = None
         dist.broadcast(weight.data, src=dist.get_global_rank(self.group, 0), group=group)
         weight.register_post_accumulate_grad_hook(self._hook)
@@ -184,12 +186,26 @@ class PeerTableGrads:
         if g.dtype != torch.float32 or not g.is_contiguous():
             g = g.float().contiguous()
         V, D = g.shape
+        n = self.touched.numel()
+        if self.cap == 0:
+            from .peer import symmetric_empty
+            self.cap = n
+            self.rows, self._hr, self.dst_rows = symmetric_empty((self.world * n, D), torch.float32,
+                                                                  g.device, self.group)
+            self.ids, self._hi, self.dst_ids = symmetric_empty((self.world * n,), torch.int64,
+                                                                g.device, self.group)
+        elif n != self.cap:
+            raise RuntimeError(f"PeerTableGrads: batch shape changed ({n} id slots, staged for {self.cap})")
+        stream = _lib.stream_ptr(g.device)
+        self.sync.barrier(0, g.device)     # every rank has consumed its staging buffer of the last step
+        _lib.check(_lib.lib().grb_p2p_put_table_rows(
+            g.data_ptr(), self.touched.data_ptr(), n, D, V, 0, 1.0 / self.world, self.dst_rows,
+            self.dst_ids, self.world, self.rank * n, stream))
         self.buf.zero_()
-        self.sync.barrier(0, g.device)     # every buffer is zeroed, nobody still reads the last one
-        _lib.check(_lib.lib().grb_p2p_rows_add(
-            g.data_ptr(), self.touched.data_ptr(), self.touched.numel(), D, V, 0, 1.0 / self.world,
-            self.dst, self.world, _lib.stream_ptr(g.device)))
-        self.sync.barrier(1, g.device)     # every rank's rows have landed everywhere
+        self.sync.barrier(1, g.device)     # every rank's block has landed everywhere
+        _lib.check(_lib.lib().grb_rows_scatter_add(
+            self.rows.data_ptr(), D, self.ids.data_ptr(), self.buf.data_ptr(), self.world * n, D, V, 0,
+            stream))
         param.grad = self.buf
         self.touched = None
 
