@@ -171,16 +171,17 @@ __global__ void __launch_bounds__(MsCfg<NQB>::threads, 1) mips_scores_sm100_kern
         mbar_wait(bar_acc_full + 8 * ab, (tile / MS_ACC) & 1);
         tc_fence_after();
         const int64_t item0 = epi_item_tile(p.epi, u) * MIPS_TILE_N;
+        // only the last item tile can run past X: everywhere else the per-score bound checks
+        // (64-bit compares) are skipped
+        const bool full = item0 + MIPS_TILE_N <= p.X;
+        const uint32_t acc_addr = tmem + lane_base + (ab * NQB + qq) * MIPS_TILE_N;
+        if (p.epi.mode == MIPS_EPI_STORE) {
 #pragma unroll 1
-        for (int c32 = 0; c32 < 4; ++c32) {
-          uint32_t sv[32];
-          tmem_ld32(tmem + lane_base + (ab * NQB + qq) * MIPS_TILE_N + c32 * 32, sv);
-          tmem_ld_wait();
-          if (!row_ok) continue;
-          // only the last item tile can run past X: everywhere else the per-score bound checks
-          // (64-bit compares) are skipped
-          const bool full = item0 + MIPS_TILE_N <= p.X;
-          if (p.epi.mode == MIPS_EPI_STORE) {
+          for (int c32 = 0; c32 < 4; ++c32) {
+            uint32_t sv[32];
+            tmem_ld32(acc_addr + c32 * 32, sv);
+            tmem_ld_wait();
+            if (!row_ok) continue;
             float* o = p.epi.out + row * p.epi.Xs + u * MIPS_TILE_N + c32 * 32;
             if (full) {
 #pragma unroll
@@ -199,10 +200,21 @@ __global__ void __launch_bounds__(MsCfg<NQB>::threads, 1) mips_scores_sm100_kern
                 *reinterpret_cast<float4*>(o + v4 * 4) = f;
               }
             }
-          } else {
-            // cheap reject at two levels: most 32-score groups hold nothing above tau, and when one
-            // does, only the 8-score sub-group that holds it is walked (the walk is executed by the
-            // whole warp as soon as ONE of its 32 rows needs it, so it has to be short)
+          }
+        } else {
+          // FILTER, two passes over the 128 scores of this row so that a tile costs ONE atomic (its
+          // ~700-cycle round trip, paid per 8-score sub-group, was what held the dense early phases
+          // back).  Pass 1: cheap reject at two levels (max of 32, max of 8) and a hit bitmask per
+          // 32-score chunk; the compare walk of a sub-group is executed by the whole warp as soon
+          // as ONE of its 32 rows needs it, so it is kept to 8 scores.
+          // (the chunk loops stay rolled — unrolled, the code no longer fits the instruction cache
+          //  and the kernel runs 2x slower — so the four masks live in scalars, not in an array)
+          uint32_t h0 = 0u, h1 = 0u, h2 = 0u, h3 = 0u;
+#pragma unroll 1
+          for (int c32 = 0; c32 < 4; ++c32) {
+            uint32_t sv[32];
+            tmem_ld32(acc_addr + c32 * 32, sv);
+            tmem_ld_wait();
             float m8[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -211,28 +223,44 @@ __global__ void __launch_bounds__(MsCfg<NQB>::threads, 1) mips_scores_sm100_kern
               for (int c = 1; c < 8; ++c) m = fmaxf(m, __uint_as_float(sv[8 * k + c]));
               m8[k] = m;
             }
-            if (fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])) >= tau) {
-              const int lim = full ? 32 : (int) (p.X - (item0 + c32 * 32));   // valid scores in this group
-              const int32_t ibase = (int32_t) (item0 + c32 * 32);
+            uint32_t h = 0u;
+            if (row_ok && fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])) >= tau) {
+              const int lim = full ? 32 : (int) (p.X - (item0 + c32 * 32));   // valid scores in this chunk
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 if (m8[k] >= tau) {
-                  int cnt = 0;
 #pragma unroll
                   for (int c = 8 * k; c < 8 * k + 8; ++c)
-                    cnt += (__uint_as_float(sv[c]) >= tau && c < lim) ? 1 : 0;
-                  if (cnt) {  // one atomic per sub-group
-                    int slot = atomicAdd(p.epi.counts + row, cnt);
+                    h |= (__uint_as_float(sv[c]) >= tau && c < lim) ? (1u << c) : 0u;
+                }
+              }
+            }
+            h0 = c32 == 0 ? h : h0; h1 = c32 == 1 ? h : h1;
+            h2 = c32 == 2 ? h : h2; h3 = c32 == 3 ? h : h3;
+          }
+          const int cnt = __popc(h0) + __popc(h1) + __popc(h2) + __popc(h3);
+          if (__any_sync(0xffffffffu, cnt > 0)) {
+            int slot = cnt ? atomicAdd(p.epi.counts + row, cnt) : 0;   // one atomic per (row, tile)
+            // pass 2: only chunks / sub-groups with hits are read again and walked
+#pragma unroll 1
+            for (int c32 = 0; c32 < 4; ++c32) {
+              const uint32_t h = c32 == 0 ? h0 : c32 == 1 ? h1 : c32 == 2 ? h2 : h3;
+              if (!__any_sync(0xffffffffu, h != 0u)) continue;
+              uint32_t sv[32];
+              tmem_ld32(acc_addr + c32 * 32, sv);
+              tmem_ld_wait();
+              const int32_t ibase = (int32_t) (item0 + c32 * 32);
 #pragma unroll
-                    for (int c = 8 * k; c < 8 * k + 8; ++c) {
-                      const float sc = __uint_as_float(sv[c]);
-                      if (sc >= tau && c < lim) {
-                        if (slot < p.epi.cap) {
-                          p.epi.cscores[row * p.epi.cap + slot] = sc;
-                          p.epi.cidx[row * p.epi.cap + slot] = ibase + c;
-                        }
-                        ++slot;
+              for (int k = 0; k < 4; ++k) {
+                if ((h >> (8 * k)) & 0xffu) {
+#pragma unroll
+                  for (int c = 8 * k; c < 8 * k + 8; ++c) {
+                    if ((h >> c) & 1u) {
+                      if (slot < p.epi.cap) {
+                        p.epi.cscores[row * p.epi.cap + slot] = __uint_as_float(sv[c]);
+                        p.epi.cidx[row * p.epi.cap + slot] = ibase + c;
                       }
+                      ++slot;
                     }
                   }
                 }
