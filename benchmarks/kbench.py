@@ -161,6 +161,12 @@ def main():
         bench_attn("prof 2x8192 H8 full", 2, 8192, 8, [8192] * 2, bwd=False)
     if "attnbwd" in which:
         bench_attn("prof 1x8192 H4 full", 1, 8192, 4, [8192], bwd=True)
+    if "mipsshards" in which:    # what one rank of a 2- / 4- / 8-way sharded C4 index computes
+        for g in (2, 4, 8):
+            bench_mips(f"C4 shard 1/{g}: B4096 X{10_000_000 // g} D256 k200 bf16", 4096, 10_000_000 // g, 256,
+                       200, torch.bfloat16)
+    if "mipsshard4" in which:
+        bench_mips("C4 shard 1/4: B4096 X2500000 D256 k200 bf16", 4096, 2_500_000, 256, 200, torch.bfloat16)
     if "mipsc4" in which:
         bench_mips("C4 B4096 X10M D256 k200 bf16", 4096, 10_000_000, 256, 200, torch.bfloat16)
     if "attnc2" in which:

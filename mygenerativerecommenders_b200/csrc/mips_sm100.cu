@@ -25,7 +25,10 @@ using namespace ptx;
 
 constexpr int MS_SLAB = 128 * 64 * 2;   // 16 KiB: 128 rows x 64 bf16
 template <int NQB> struct MsCfg {
-  static constexpr int threads = 64 + 128 * NQB;        // TMA warp, MMA warp, NQB epilogue warpgroups
+  // TMA warp, MMA warp, and per query block TWO epilogue warpgroups (64 of the 128 score columns
+  // each): with one, a tile's epilogue (TMEM loads, reject tree, the atomic's round trip) takes
+  // longer than its 1024 MMA cycles as soon as candidates are dense (small shards, early phases)
+  static constexpr int threads = 64 + 256 * NQB;
   static constexpr int stages = NQB == 1 ? 8 : 6;
   static constexpr int acc = 4 / NQB;                   // accumulator sets (NQB x 128 columns each)
   static constexpr int q = 0;                           // NQB x 4 slabs
@@ -64,7 +67,7 @@ __global__ void __launch_bounds__(MsCfg<NQB>::threads, 1) mips_scores_sm100_kern
 
   if (tid == 0) {
     for (int s = 0; s < MS_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    for (int s = 0; s < MS_ACC; ++s) { mbar_init(bar_acc_full + 8 * s, 1); mbar_init(bar_acc_empty + 8 * s, 4 * NQB); }
+    for (int s = 0; s < MS_ACC; ++s) { mbar_init(bar_acc_full + 8 * s, 1); mbar_init(bar_acc_empty + 8 * s, 8 * NQB); }
     mbar_init(bar_q_full, 1);
     mbar_init(bar_q_empty, 1);
     fence_barrier_init();
@@ -154,9 +157,11 @@ __global__ void __launch_bounds__(MsCfg<NQB>::threads, 1) mips_scores_sm100_kern
       }
     }
   } else {
-    // epilogue: warps 2 .. 2+4*NQB, TMEM lane quadrant = warp % 4, warpgroup = query block
+    // epilogue: warps 2 .. 2+8*NQB, TMEM lane quadrant = warp % 4; four consecutive warps form a
+    // group (query block qq, column half)
     const int r = ((warp & 3) << 5) | lane;
-    const int qq = (warp - 2) >> 2;
+    const int qq = (warp - 2) >> 3;
+    const int half = ((warp - 2) >> 2) & 1;
     const uint32_t lane_base = (uint32_t) ((warp & 3) * 32) << 16;
     uint32_t tile = 0;
     for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
@@ -177,7 +182,7 @@ __global__ void __launch_bounds__(MsCfg<NQB>::threads, 1) mips_scores_sm100_kern
         const uint32_t acc_addr = tmem + lane_base + (ab * NQB + qq) * MIPS_TILE_N;
         if (p.epi.mode == MIPS_EPI_STORE) {
 #pragma unroll 1
-          for (int c32 = 0; c32 < 4; ++c32) {
+          for (int c32 = 2 * half; c32 < 2 * half + 2; ++c32) {
             uint32_t sv[32];
             tmem_ld32(acc_addr + c32 * 32, sv);
             tmem_ld_wait();
@@ -208,10 +213,10 @@ __global__ void __launch_bounds__(MsCfg<NQB>::threads, 1) mips_scores_sm100_kern
           // 32-score chunk; the compare walk of a sub-group is executed by the whole warp as soon
           // as ONE of its 32 rows needs it, so it is kept to 8 scores.
           // (the chunk loops stay rolled — unrolled, the code no longer fits the instruction cache
-          //  and the kernel runs 2x slower — so the four masks live in scalars, not in an array)
-          uint32_t h0 = 0u, h1 = 0u, h2 = 0u, h3 = 0u;
+          //  and the kernel runs 2x slower — so the hit masks live in scalars, not in an array)
+          uint32_t h0 = 0u, h1 = 0u;
 #pragma unroll 1
-          for (int c32 = 0; c32 < 4; ++c32) {
+          for (int c32 = 2 * half; c32 < 2 * half + 2; ++c32) {
             uint32_t sv[32];
             tmem_ld32(acc_addr + c32 * 32, sv);
             tmem_ld_wait();
@@ -235,16 +240,16 @@ __global__ void __launch_bounds__(MsCfg<NQB>::threads, 1) mips_scores_sm100_kern
                 }
               }
             }
-            h0 = c32 == 0 ? h : h0; h1 = c32 == 1 ? h : h1;
-            h2 = c32 == 2 ? h : h2; h3 = c32 == 3 ? h : h3;
+            h0 = (c32 & 1) == 0 ? h : h0;
+            h1 = (c32 & 1) == 1 ? h : h1;
           }
-          const int cnt = __popc(h0) + __popc(h1) + __popc(h2) + __popc(h3);
+          const int cnt = __popc(h0) + __popc(h1);
           if (__any_sync(0xffffffffu, cnt > 0)) {
-            int slot = cnt ? atomicAdd(p.epi.counts + row, cnt) : 0;   // one atomic per (row, tile)
+            int slot = cnt ? atomicAdd(p.epi.counts + row, cnt) : 0;   // one atomic per (row, tile half)
             // pass 2: only chunks / sub-groups with hits are read again and walked
 #pragma unroll 1
-            for (int c32 = 0; c32 < 4; ++c32) {
-              const uint32_t h = c32 == 0 ? h0 : c32 == 1 ? h1 : c32 == 2 ? h2 : h3;
+            for (int c32 = 2 * half; c32 < 2 * half + 2; ++c32) {
+              const uint32_t h = (c32 & 1) == 0 ? h0 : h1;
               if (!__any_sync(0xffffffffu, h != 0u)) continue;
               uint32_t sv[32];
               tmem_ld32(acc_addr + c32 * 32, sv);
