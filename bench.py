@@ -31,6 +31,7 @@ import torch
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+from mygenerativerecommenders_b200.optim import FusedAdamW  # noqa: E402
 from mygenerativerecommenders_b200.pipeline import (  # noqa: E402
     RetrievalConfig, synthetic_batch, synthetic_item_ids)
 
@@ -219,8 +220,7 @@ def run_training(args, world, rank, local):
                       file=sys.stderr)
         step_mod = torch.nn.parallel.DistributedDataParallel(
             step_mod, device_ids=[local], gradient_as_bucket_view=True, broadcast_buffers=False)
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, betas=(0.9, 0.98), weight_decay=1e-3,
-                            fused=True)
+    opt = FusedAdamW(model.parameters(), lr=1e-3, betas=(0.9, 0.98), weight_decay=1e-3)
     pinned = [{k: v.pin_memory() for k, v in b.items()} for b in host]
     resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
 
@@ -304,6 +304,8 @@ def run_training(args, world, rank, local):
         "hstu_attn_bwd": ("tensor", pairs * 2 * H * (3 * dqk + 2 * dv)),
         "sampled_softmax_fwd": ("hbm", ssl_bytes),
         "sampled_softmax_bwd": ("hbm", ssl_bytes + rows * R * D * 4),
+        # 4 loads + 3 stores of fp32 per parameter element (include/grb200.h grb_adamw_step)
+        "adamw_step": ("hbm", 28 * sum(p.numel() for p in model.parameters()) * n_attr),
     }
     step_ms = ms / args.steps
     kern = {}

@@ -279,6 +279,21 @@ int grb_rows_scatter_add(const float* grad, int64_t ld_grad, const int64_t* ids,
                          grb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * AdamW step over a list of fp32 tensors, one launch per 64 tensors (the optimizer of the train
+ *     step: torch.optim.AdamW as the reference configures it, configs/model/hstu.yaml +
+ *     models/generative_recommenders.py:254-322 configure_optimizers).  Per element, in fp32:
+ *         p *= 1 - lr * weight_decay
+ *         m  = m + (g - m) * (1 - beta1)           v = beta2 * v + (1 - beta2) * g * g
+ *         p -= (lr / bias_correction1) * m / (sqrt(v) / sqrt(bias_correction2) + eps)
+ *     with bias_correction{1,2} = 1 - beta{1,2}^step computed by the caller.  p, g, m, v, numel are
+ *     HOST arrays of n device pointers / element counts.  28 bytes of HBM traffic per element.
+ * ------------------------------------------------------------------------------------------- */
+int grb_adamw_step(int n, float* const* p, const float* const* g, float* const* m, float* const* v,
+                   const int64_t* numel, double lr, double beta1, double beta2, double eps,
+                   double weight_decay, double bias_correction1, double bias_correction2,
+                   grb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Cross-rank barrier on the stream, over peer memory: every rank adds 1 to word `slot` of each
  *     rank's signal array (system-scope release after its earlier stores / reds), then waits until
  *     its own word reaches n_ranks * epoch.  signals: host array of n_ranks device pointers to
