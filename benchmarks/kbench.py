@@ -148,6 +148,20 @@ def bench_mips(tag, B, X, D, k, dtype):
            qps=round(B / ms * 1e3, 1))
 
 
+def bench_decode(tag, B, N, H, lengths, d=64):
+    """Incremental path: the last position of every sequence against its K / V caches."""
+    c = attn_case(B, N, H, lengths)
+    off, lengths = c["off"], torch.as_tensor(lengths, dtype=torch.int64).to(DEV)
+    kc = ops.jagged_to_padded_dense(c["k"], off, N, 0.0)
+    pos = lengths - 1
+    qn = c["q"][off[:-1] + pos]
+    run = lambda: GF.hstu_attention_decode(qn, kc, c["v"], off, pos, c["ts"], c["ts_w"], c["pos_w"], c["thr"],
+                                           N, H, d, d)
+    byts = int(lengths.sum()) * H * 2 * d * 2 + B * H * 2 * d * 2 + int(lengths.sum()) * 8
+    with torch.no_grad():
+        report(f"hstu_attn_decode[{tag}]", timeit(run), byts=byts)
+
+
 def bench_adamw():
     from mygenerativerecommenders_b200.optim import FusedAdamW
     p = torch.nn.Parameter(torch.randn(131_263, 256, device=DEV))
@@ -198,6 +212,11 @@ def main():
         report("hstu_attn_bwd[no-bias 4x8192 H8]", timeit(lambda: torch.autograd.grad(
             out, (q, k, v), go, retain_graph=True), iters=5, warmup=2, flush=False),
             flop=c["pairs"] * 2 * H * 5 * d)
+    if want("decode"):
+        g = torch.Generator().manual_seed(0)
+        bench_decode("C2 128x U[20,200] N211 H4", 128, 211, 4, torch.randint(20, 201, (128,), generator=g))
+        bench_decode("serving 4096x U[20,200] N211 H4", 4096, 211, 4, torch.randint(20, 201, (4096,), generator=g))
+        bench_decode("C5 128x U[1024,8192] N8192 H8", 128, 8192, 8, torch.randint(1024, 8193, (128,), generator=g))
     if want("adamw"):
         bench_adamw()
     if want("jagged"):

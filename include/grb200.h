@@ -144,6 +144,37 @@ int grb_hstu_attn_fwd(const grb_hstu_attn_args* a, grb_stream_t stream);
 int grb_hstu_attn_bwd(const grb_hstu_attn_args* a, grb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * a5/a6 incremental form  hstu.py:151-177 (+ :293-298, :321-322, :397-401, :415-418): the
+ *     delta_x_offsets + cache path.  The reference index_copy_'s the new q / k rows into the cached
+ *     padded tensors, recomputes the whole (B, H, N, N) attention and keeps one row per sequence;
+ *     this computes that row only (it depends on keys / values 0..p_b alone, causal mask :667):
+ *        out[b, h] = sum_{j <= p_b} SiLU(q[b,h].k_cache[b,j,h] + pos_w[N-1+j-p_b]
+ *                                         + ts_w[bucket(|ts[b,p_b+1] - ts[b,j]|)]) / N * v[off_b+j, h]
+ *     q (B, H*dqk) row stride ldq: the new query rows; k_cache (B, N, H*dqk) padded, row stride ldk
+ *     (already holding the new key at [b, p_b]); v (T, H*dv) jagged, stride ldv (new value at
+ *     off_b + p_b); positions (B) = delta_x_offsets[1] (int32 | int64, pos_bits); out (B, H*dv)
+ *     stride ldo.  A position outside [0, n_b) yields a zero row (the reference's padded row).
+ *     Forward only (inference).  HBM-bound: (p_b+1) * H * (dqk+dv) elements per sequence.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct grb_hstu_attn_decode_args {
+  int64_t B, N;
+  int32_t H, dqk, dv;
+  int32_t dtype;        /* grb_dtype of q, k_cache, v, out */
+  int32_t index_bits;   /* offsets: 32 | 64 */
+  int32_t pos_bits;     /* positions: 32 | 64 */
+  int32_t num_buckets;
+  const void* q; int64_t ldq;
+  const void* k_cache; int64_t ldk;
+  const void* v; int64_t ldv;
+  const void* offsets;            /* (B+1) */
+  const void* positions;          /* (B) */
+  const int64_t* timestamps;      /* (B, N) or NULL */
+  const float* ts_w; const float* pos_w; const int64_t* bucket_thresholds;
+  void* out; int64_t ldo;
+} grb_hstu_attn_decode_args;
+int grb_hstu_attn_decode(const grb_hstu_attn_decode_args* a, grb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * a6  hstu.py:258-264,402  y = gate * LayerNorm_W(x; eps, no affine)   (gate == NULL: y = LN(x))
  *     x,gate,y: (rows, W) row strides ldx/ldg/ldy elements.  mean/rstd (rows) fp32 are saved
  *     for backward.  Backward: dx, dgate from dy (dgate == NULL when gate == NULL).

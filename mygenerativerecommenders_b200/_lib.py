@@ -44,6 +44,17 @@ class HstuAttnArgs(C.Structure):
     ]
 
 
+class HstuAttnDecodeArgs(C.Structure):
+    _fields_ = [
+        ("B", c_i64), ("N", c_i64), ("H", c_i32), ("dqk", c_i32), ("dv", c_i32),
+        ("dtype", c_i32), ("index_bits", c_i32), ("pos_bits", c_i32), ("num_buckets", c_i32),
+        ("q", c_vp), ("ldq", c_i64), ("k_cache", c_vp), ("ldk", c_i64), ("v", c_vp), ("ldv", c_i64),
+        ("offsets", c_vp), ("positions", c_vp), ("timestamps", c_vp),
+        ("ts_w", c_vp), ("pos_w", c_vp), ("bucket_thresholds", c_vp),
+        ("out", c_vp), ("ldo", c_i64),
+    ]
+
+
 class MipsTopkArgs(C.Structure):
     _fields_ = [
         ("B", c_i64), ("X", c_i64), ("D", c_i64),
@@ -107,6 +118,7 @@ SYMBOLS = {
     "grb_p2p_barrier": (C.c_int, [C.POINTER(c_vp), c_i32, c_i32, c_i32, c_i64, c_vp]),
     "grb_p2p_put_table_rows": (C.c_int, [c_vp, c_vp, c_i64, c_i32, c_i64, c_i64, C.c_float, C.POINTER(c_vp),
                                          C.POINTER(c_vp), c_i32, c_i64, c_vp]),
+    "grb_hstu_attn_decode": (C.c_int, [C.POINTER(HstuAttnDecodeArgs), c_vp]),
     "grb_adamw_step": (C.c_int, [C.c_int, C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp),
                                  C.POINTER(c_i64)] + [C.c_double] * 7 + [c_vp]),
     "grb_rows_scatter_add": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_i64, c_i64, c_vp]),

@@ -203,6 +203,51 @@ def hstu_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, offsets: t
                                 bucket_cache, rows_padded)
 
 
+def hstu_attention_decode(q: torch.Tensor, k_cache: torch.Tensor, v: torch.Tensor,
+                          offsets: torch.Tensor, positions: torch.Tensor,
+                          timestamps: Optional[torch.Tensor], ts_w: Optional[torch.Tensor],
+                          pos_w: Optional[torch.Tensor], bucket_thresholds: Optional[torch.Tensor],
+                          N: int, num_heads: int, attention_dim: int, linear_dim: int) -> torch.Tensor:
+    """The attention row of ONE position per sequence, from the caches of the incremental path
+    (hstu.py:151-177 + :179-204 + :397-401: the reference recomputes the whole padded attention and
+    keeps rows ``delta_x_offsets[0]``; row p only depends on keys / values 0..p).
+
+    q (B, H*attention_dim): the new query rows; k_cache (B, N, H*attention_dim): padded keys, already
+    holding the new key at [b, positions[b]]; v (T, H*linear_dim): jagged values, new row included;
+    positions (B) int32 | int64 = delta_x_offsets[1].  Returns (B, H*linear_dim).  Inference only."""
+    _lib.require_cuda(q, k_cache, v, offsets, positions, timestamps)
+    if torch.is_grad_enabled() and (q.requires_grad or k_cache.requires_grad or v.requires_grad):
+        raise NotImplementedError(
+            "hstu_attention_decode is forward-only (the incremental path serves inference); "
+            "run it under torch.no_grad() / inference_mode()")
+    B = offsets.numel() - 1
+    if q.dtype != k_cache.dtype or q.dtype != v.dtype:
+        raise ValueError("hstu_attention_decode: q, k_cache and v must share a dtype")
+    q = _rows_contiguous(q)
+    v = _rows_contiguous(v)
+    kc = k_cache.reshape(B * N, -1) if k_cache.is_contiguous() else k_cache.contiguous().view(B * N, -1)
+    positions = positions.contiguous()
+    out = torch.empty((B, num_heads * linear_dim), dtype=q.dtype, device=q.device)
+    a = _lib.HstuAttnDecodeArgs()
+    a.B, a.N, a.H, a.dqk, a.dv = B, N, num_heads, attention_dim, linear_dim
+    a.dtype = _lib.dtype_code(q.dtype)
+    a.index_bits, a.pos_bits = _lib.index_bits(offsets), _lib.index_bits(positions)
+    a.q, a.ldq = q.data_ptr(), _ld(q)
+    a.k_cache, a.ldk = kc.data_ptr(), kc.stride(0)
+    a.v, a.ldv = v.data_ptr(), _ld(v)
+    a.offsets, a.positions = offsets.data_ptr(), positions.data_ptr()
+    if timestamps is not None:
+        ts_w = ts_w if ts_w.dtype == torch.float32 else ts_w.float()
+        pos_w = pos_w if pos_w.dtype == torch.float32 else pos_w.float()
+        a.num_buckets = bucket_thresholds.numel()
+        a.timestamps, a.ts_w, a.pos_w = timestamps.data_ptr(), ts_w.data_ptr(), pos_w.data_ptr()
+        a.bucket_thresholds = bucket_thresholds.data_ptr()
+    a.out, a.ldo = out.data_ptr(), out.stride(0)
+    with _lib.timed("hstu_attn_decode"):
+        _lib.check(_lib.lib().grb_hstu_attn_decode(C.byref(a), _lib.stream_ptr(q.device)))
+    return out
+
+
 # --------------------------------------------------------------------------------------------
 # y = gate * LayerNorm(x)   (hstu.py:258-264, :300, :402)
 # --------------------------------------------------------------------------------------------

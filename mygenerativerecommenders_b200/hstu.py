@@ -160,10 +160,17 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
         """x: (sum_i N_i, D); x_offsets: (B+1); all_timestamps: (B, N) int64 or None;
         invalid_attn_mask: (N, N) — only its size is read: the kernel applies the causal
         lower-triangular mask that HSTU registers (hstu.py:595-607,667)."""
-        if delta_x_offsets is not None or cache is not None:
-            raise NotImplementedError(
-                "incremental decoding (delta_x_offsets / cache, hstu.py:151-177) is not on the "
-                "B200 hot path yet")
+        # Incremental path (hstu.py:293-298): x, u, v, q, k are restricted to the rows
+        # delta_x_offsets[0] (one new position per sequence); the caches of the earlier positions
+        # come from a previous call with return_cache_states=True.  A cache without
+        # delta_x_offsets is ignored, as in the reference.
+        incremental = delta_x_offsets is not None
+        if incremental:
+            if cache is None:
+                raise ValueError("delta_x_offsets needs this layer's cache state (hstu.py:295)")
+            rows = delta_x_offsets[0].long()
+            x = x[rows, :]
+            cached_v, cached_q, cached_k, cached_outputs = cache
         if self._normalization not in ("rel_bias", "hstu_rel_bias"):
             if self._normalization == "softmax_rel_bias":
                 raise NotImplementedError("softmax_rel_bias normalization is not implemented")
@@ -184,14 +191,27 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
         if bias is not None and not isinstance(bias, RelativeBucketedTimeAndPositionBasedBias):
             raise NotImplementedError(
                 "the fused attention supports RelativeBucketedTimeAndPositionBasedBias only")
-        attn_output = GF.hstu_attention(
-            q, k, v, x_offsets,
-            all_timestamps if bias is not None else None,
-            bias._ts_w if bias is not None else None,
-            bias._pos_w if bias is not None else None,
-            bias._bucket_thresholds if bias is not None else None,
-            N=n, num_heads=H, attention_dim=dqk, linear_dim=dv, bucket_cache=bucket_cache,
-            rows_padded=rows_padded)
+        bias_args = (all_timestamps if bias is not None else None,
+                     bias._ts_w if bias is not None else None,
+                     bias._pos_w if bias is not None else None,
+                     bias._bucket_thresholds if bias is not None else None)
+        if incremental:
+            # hstu.py:321-322 and :151-177: the new rows go into the caches in place ...
+            B = x_offsets.numel() - 1
+            v = cached_v.index_copy_(0, rows, v)
+            flat = delta_x_offsets[1].long() + torch.arange(0, B * n, n, device=x.device)
+            padded_q = cached_q.view(B * n, -1).index_copy_(0, flat, q).view(B, n, -1)
+            padded_k = cached_k.view(B * n, -1).index_copy_(0, flat, k).view(B, n, -1)
+            # ... and where the reference recomputes the whole (B, H, N, N) attention to keep the
+            # rows delta_x_offsets[0] (:179-204, :397-401), one row per sequence is computed
+            attn_output = GF.hstu_attention_decode(
+                q, padded_k, v, x_offsets, delta_x_offsets[1], *bias_args,
+                N=n, num_heads=H, attention_dim=dqk, linear_dim=dv)
+        else:
+            attn_output = GF.hstu_attention(
+                q, k, v, x_offsets, *bias_args,
+                N=n, num_heads=H, attention_dim=dqk, linear_dim=dv, bucket_cache=bucket_cache,
+                rows_padded=rows_padded)
 
         if self._concat_ua:
             a = self._norm_attn_output(attn_output)
@@ -205,7 +225,10 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
             F.dropout(o_input, p=self._dropout_ratio, training=self.training), o_w, o_b) + x
 
         cache_state = None
-        if return_cache_states:
+        if incremental:
+            new_outputs = cached_outputs.index_copy_(0, rows, new_outputs)   # hstu.py:415-418
+            cache_state = (v, padded_q, padded_k, new_outputs)
+        elif return_cache_states:
             cache_state = (
                 v.contiguous(),
                 ops.jagged_to_padded_dense(q.contiguous(), x_offsets, n, 0.0),
@@ -240,6 +263,7 @@ class HSTUJagged(torch.nn.Module):
         bucket_cache = None
         first = self._attention_layers[0] if len(self._attention_layers) else None
         if (all_timestamps is not None and first is not None and x.dtype == torch.bfloat16
+                and delta_x_offsets is None
                 and first._attention_dim == 64 and first._linear_dim == 64
                 and isinstance(first._rel_attn_bias, RelativeBucketedTimeAndPositionBasedBias)):
             bucket_cache = GF.hstu_bucket_cache(x_offsets, all_timestamps,

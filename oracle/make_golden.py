@@ -154,6 +154,60 @@ def golden_hstu(R):
     return g
 
 
+def _hstu_incremental_case(R, name, B, max_seq, out_len, D, H, dqk, dv, blocks, lengths, seed,
+                           keep_updated_cache=True):
+    """Incremental path: a full pass with return_cache_states=True, then the LAST token of every
+    sequence is replaced and recomputed through delta_x_offsets + cache (hstu.py:293-298,
+    :151-177, :415-418).  The reference updates the caches in place, so copies go into the fixture."""
+    hstu = R["hstu"]
+    N = max_seq + out_len
+    torch.manual_seed(seed)
+    enc = hstu.HSTU(max_sequence_len=max_seq, max_output_len=out_len, embedding_dim=D,
+                    item_embedding_dim=D, num_blocks=blocks, num_heads=H, linear_dim=dv,
+                    attention_dim=dqk, normalization="rel_bias", linear_config="uvqk",
+                    linear_activation="silu", linear_dropout_rate=0.2, attn_dropout_rate=0.0)
+    enc.eval()
+    gen = torch.Generator().manual_seed(seed + 1)
+    lengths = torch.tensor(lengths, dtype=torch.int64)
+    ts = synth_timestamps(B, N, lengths, gen)
+    valid = (torch.arange(N).unsqueeze(0) < lengths.unsqueeze(1)).float().unsqueeze(-1)
+    x = torch.randn(B, N, D, generator=gen) * valid
+    kw = dict(past_lengths=lengths, valid_mask=valid, past_payloads={"timestamps": ts})
+    with torch.no_grad():
+        y0, cache = enc(user_embeddings=x, return_cache_states=True, **kw)
+        cache0 = [tuple(t.detach().clone() for t in st) for st in cache]
+        x2 = x.clone()
+        x2[torch.arange(B), lengths - 1] = torch.randn(B, D, generator=gen)
+        off = torch.zeros(B + 1, dtype=torch.int64)
+        off[1:] = torch.cumsum(lengths, 0)
+        delta = (off[1:] - 1, lengths - 1)   # int64: index_copy_ in this torch rejects the int32 the docstring names
+        y_inc, cache1 = enc(user_embeddings=x2, delta_x_offsets=delta, cache=cache,
+                            return_cache_states=True, **kw)
+        y_full, _ = enc(user_embeddings=x2, **kw)
+    assert torch.allclose(y_inc, y_full, rtol=1e-4, atol=1e-5), (y_inc - y_full).abs().max()
+    g = {f"{name}.cfg": torch.tensor([B, max_seq, out_len, D, H, dqk, dv, blocks]),
+         f"{name}.lengths": lengths, f"{name}.ts": ts, f"{name}.x": x, f"{name}.x2": x2,
+         f"{name}.delta0": delta[0], f"{name}.delta1": delta[1],
+         f"{name}.y0": y0.clone(), f"{name}.y_inc": y_inc.clone(),
+         **{f"{name}.sd.{k}": v.detach().clone() for k, v in enc.state_dict().items() if k != "_attn_mask"}}
+    for i in range(blocks):
+        for j, nm in enumerate(("v", "padded_q", "padded_k", "out")):
+            g[f"{name}.cache0.{i}.{nm}"] = cache0[i][j]
+            if keep_updated_cache:
+                g[f"{name}.cache1.{i}.{nm}"] = cache1[i][j].detach().clone()
+    return g
+
+
+def golden_hstu_incremental(R):
+    g = {}
+    g.update(_hstu_incremental_case(R, "mh", B=5, max_seq=20, out_len=4, D=16, H=2, dqk=8, dv=8,
+                                    blocks=2, lengths=[1, 24, 7, 13, 2], seed=50))
+    g.update(_hstu_incremental_case(R, "h64", B=3, max_seq=150, out_len=11, D=64, H=2, dqk=64,
+                                    dv=64, blocks=2, lengths=[161, 130, 5], seed=60,
+                                    keep_updated_cache=False))     # (fixture size)
+    return g
+
+
 def golden_retrieval(R):
     g = {}
     gen = torch.Generator().manual_seed(40)
@@ -208,8 +262,11 @@ def golden_retrieval(R):
 def main():
     R = _import_reference()
     OUT.mkdir(parents=True, exist_ok=True)
+    only = set(sys.argv[1:])                    # e.g. `make_golden.py hstu_incremental`; default: all
     for name, fn in [("ops", golden_ops), ("bias", golden_bias), ("hstu", golden_hstu),
-                     ("retrieval", golden_retrieval)]:
+                     ("hstu_incremental", golden_hstu_incremental), ("retrieval", golden_retrieval)]:
+        if only and name not in only:
+            continue
         data = fn(R)
         torch.save(data, OUT / f"{name}.pt")
         size = (OUT / f"{name}.pt").stat().st_size

@@ -136,6 +136,75 @@ def stu_layer(x, offsets, ts, sd: Dict[str, torch.Tensor], prefix: str, N, H, dq
     return F.linear(o_in, sd[prefix + "_o.weight"].to(x.dtype), sd[prefix + "_o.bias"].to(x.dtype)) + x
 
 
+def stu_layer_cache_state(x, offsets, ts, sd, prefix, N, H, dqk, dv, eps: float = 1e-6):
+    """The 4-tuple a layer returns with return_cache_states=True (hstu.py:420-423):
+    (v jagged, padded_q (B,N,H*dqk), padded_k, layer output jagged).  Eval mode."""
+    D = x.shape[1]
+    mm = F.silu(F.layer_norm(x, [D], eps=eps) @ sd[prefix + "_uvqk"].to(x.dtype))
+    _, v, q, k = torch.split(mm, [H * dv, H * dv, H * dqk, H * dqk], dim=1)
+    out = stu_layer(x, offsets, ts, sd, prefix, N, H, dqk, dv, eps=eps)
+    return (v.contiguous(), jagged_to_padded_dense(q, offsets, N, 0.0),
+            jagged_to_padded_dense(k, offsets, N, 0.0), out)
+
+
+def stu_layer_incremental(x, offsets, ts, sd, prefix, N, H, dqk, dv, delta, cache, eps: float = 1e-6):
+    """The delta_x_offsets branch of SequentialTransductionUnitJagged.forward, as the reference
+    computes it (hstu.py:293-298, :321-322, :151-177, :179-204, :397-401, :415-418): the new rows
+    are written into the caches, the WHOLE padded attention is recomputed from them, and the rows
+    delta[0] are kept.  Returns (layer output with the new rows, updated cache 4-tuple); the
+    caches are cloned, not modified in place."""
+    rows, pos = delta[0].long(), delta[1].long()
+    cached_v, cached_q, cached_k, cached_out = (t.clone() for t in cache)
+    B, D = offsets.numel() - 1, x.shape[1]
+    xr = x[rows]
+    mm = F.silu(F.layer_norm(xr, [D], eps=eps) @ sd[prefix + "_uvqk"].to(x.dtype))
+    u, v, q, k = torch.split(mm, [H * dv, H * dv, H * dqk, H * dqk], dim=1)
+    v_all = cached_v.index_copy_(0, rows, v)
+    flat = pos + torch.arange(0, B * N, N)
+    pq = cached_q.view(B * N, -1).index_copy_(0, flat, q).view(B, N, H, dqk)
+    pk = cached_k.view(B * N, -1).index_copy_(0, flat, k).view(B, N, H, dqk)
+    s = torch.einsum("bnhd,bmhd->bhnm", pq, pk)
+    has_bias = (prefix + "_rel_attn_bias._ts_w") in sd and ts is not None
+    if has_bias:
+        ts_w, pos_w = sd[prefix + "_rel_attn_bias._ts_w"], sd[prefix + "_rel_attn_bias._pos_w"]
+        s = s + rel_bias(ts, ts_w, pos_w, N, ts_w.numel() - 1).unsqueeze(1).to(s.dtype)
+    p = F.silu(s) / N * torch.tril(torch.ones(N, N, dtype=s.dtype))
+    pv = jagged_to_padded_dense(v_all, offsets, N).view(B, N, H, dv)
+    a = dense_to_jagged(torch.einsum("bhnm,bmhd->bnhd", p, pv).reshape(B, N, H * dv), offsets)[rows]
+    o_in = u * F.layer_norm(a, [H * dv], eps=eps)
+    new = F.linear(o_in, sd[prefix + "_o.weight"].to(x.dtype), sd[prefix + "_o.bias"].to(x.dtype)) + xr
+    out = cached_out.index_copy_(0, rows, new)
+    return out, (v_all, pq.reshape(B, N, H * dqk), pk.reshape(B, N, H * dqk), out)
+
+
+def hstu_forward_incremental(past_lengths, user_embeddings, timestamps, sd, num_blocks, H, dqk, dv,
+                             delta, cache):
+    """HSTU.forward with delta_x_offsets + cache (hstu.py:633-672 -> :439-478): every layer
+    recomputes only the rows delta[0]; returns ((B, N, D), list of updated cache states)."""
+    B, N, D = user_embeddings.shape
+    off = complete_cumsum(past_lengths)
+    x = dense_to_jagged(user_embeddings, off)
+    states = []
+    for i in range(num_blocks):
+        x, st = stu_layer_incremental(x, off, timestamps, sd, f"_hstu._attention_layers.{i}.", N, H,
+                                      dqk, dv, delta, cache[i])
+        states.append(st)
+    return jagged_to_padded_dense(x, off, N, 0.0), states
+
+
+def hstu_cache_states(past_lengths, user_embeddings, timestamps, sd, num_blocks, H, dqk, dv):
+    """The cache list HSTU.forward(return_cache_states=True) returns."""
+    B, N, D = user_embeddings.shape
+    off = complete_cumsum(past_lengths)
+    x = dense_to_jagged(user_embeddings, off)
+    states = []
+    for i in range(num_blocks):
+        st = stu_layer_cache_state(x, off, timestamps, sd, f"_hstu._attention_layers.{i}.", N, H, dqk, dv)
+        states.append(st)
+        x = st[3]
+    return states
+
+
 def hstu_forward(past_lengths, user_embeddings, timestamps, sd, num_blocks, H, dqk, dv,
                  dropout_p: float = 0.0, training: bool = False, **kw):
     """HSTU.forward (hstu.py:633-672): (B, N, D) -> (B, N, D)."""

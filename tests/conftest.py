@@ -40,3 +40,18 @@ def hstu_case(g, name):
                 dv=dv, blocks=blocks, sd=sd, grads=grads, lengths=g[f"{name}.lengths"],
                 ts=g[f"{name}.ts"], x=g[f"{name}.x"], w=g[f"{name}.w"], y=g[f"{name}.y"],
                 dx=g[f"{name}.dx"])
+
+
+def hstu_incremental_case(g, name):
+    """Unpack one case of tests/golden/hstu_incremental.pt (oracle/make_golden.py)."""
+    B, max_seq, out_len, D, H, dqk, dv, blocks = [int(v) for v in g[f"{name}.cfg"]]
+    sd = {k[len(name) + 4:]: v for k, v in g.items() if k.startswith(f"{name}.sd.")}
+    names = ("v", "padded_q", "padded_k", "out")
+    cache0 = [tuple(g[f"{name}.cache0.{i}.{nm}"] for nm in names) for i in range(blocks)]
+    cache1 = None
+    if f"{name}.cache1.0.v" in g:
+        cache1 = [tuple(g[f"{name}.cache1.{i}.{nm}"] for nm in names) for i in range(blocks)]
+    return dict(B=B, max_seq=max_seq, out_len=out_len, N=max_seq + out_len, D=D, H=H, dqk=dqk,
+                dv=dv, blocks=blocks, sd=sd, lengths=g[f"{name}.lengths"], ts=g[f"{name}.ts"],
+                x=g[f"{name}.x"], x2=g[f"{name}.x2"], delta=(g[f"{name}.delta0"], g[f"{name}.delta1"]),
+                y0=g[f"{name}.y0"], y_inc=g[f"{name}.y_inc"], cache0=cache0, cache1=cache1)

@@ -10,7 +10,7 @@ import torch
 from mygenerativerecommenders_b200 import functional as GF
 from mygenerativerecommenders_b200 import hstu
 from oracle import reference_port as O
-from conftest import hstu_case
+from conftest import hstu_case, hstu_incremental_case
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -351,3 +351,105 @@ def test_tcgen05_stress_deterministic_and_matches_cuda_core_path(monkeypatch):
         _close(first[0], ref[0], 2e-2, 1e-2, what=f"trial {trial} out")
         for name, a, b_ in zip(("dq", "dk", "dv", "d_ts_w", "d_pos_w"), first[1:], ref[1:]):
             _close(a, b_, 3e-2, 2e-2, what=f"trial {trial} {name}")
+
+
+# ---------------------------------------------------------------------------------------------
+# incremental path: delta_x_offsets + cache (hstu.py:151-177, :293-298, :321-322, :397-401, :415-418)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,H,d,with_ts", [
+    (torch.float32, 2, 8, True), (torch.float32, 1, 50, True), (torch.float32, 2, 64, False),
+    (torch.bfloat16, 2, 64, True), (torch.bfloat16, 4, 64, False), (torch.bfloat16, 1, 24, True),
+])
+def test_attention_decode_equals_row_of_full_attention(dtype, H, d, with_ts):
+    """grb_hstu_attn_decode against the oracle's padded attention (all rows computed, one kept),
+    at the last position and at positions in the middle of the sequences."""
+    B, N = 5, 211
+    lengths = [211, 1, 130, 37, 64]
+    c = _rand_case(7, B, N, H, d, d, lengths, with_ts=with_ts)
+    q, k, v = (c[n].to(dtype).float() for n in ("q", "k", "v"))      # the values the kernel sees
+    ref = O.hstu_attention(q, k, v, c["off"], c["ts"], c["ts_w"], c["pos_w"], N, H, d, d)
+    for positions in (c["lengths"] - 1, torch.tensor([100, 0, 0, 36, 31]), (c["lengths"] - 1).to(torch.int32)):
+        rows = c["off"][:-1] + positions.long()
+        kc = O.jagged_to_padded_dense(k, c["off"], N, 0.0)
+        got = GF.hstu_attention_decode(
+            q[rows].to(DEV).to(dtype), kc.to(DEV).to(dtype), v.to(DEV).to(dtype), c["off"].to(DEV),
+            positions.to(DEV), c["ts"].to(DEV) if with_ts else None,
+            c["ts_w"].to(DEV) if with_ts else None, c["pos_w"].to(DEV) if with_ts else None,
+            _thr() if with_ts else None, N, H, d, d)
+        assert got.shape == (B, H * d) and got.dtype == dtype
+        if dtype == torch.float32:
+            _close(got, ref[rows], 1e-5, what="decode fp32")
+        else:   # inputs identical, fp32 accumulation: only the bf16 rounding of the output differs
+            _close(got, ref[rows], 1e-2, 5e-3, what="decode bf16")
+
+
+def test_attention_decode_rejects_autograd_and_cpu():
+    q = torch.zeros(1, 8, device=DEV, requires_grad=True)
+    kc = torch.zeros(1, 4, 8, device=DEV)
+    v = torch.zeros(2, 8, device=DEV)
+    off = torch.tensor([0, 2], device=DEV)
+    pos = torch.tensor([1], device=DEV)
+    with pytest.raises(NotImplementedError):
+        GF.hstu_attention_decode(q, kc, v, off, pos, None, None, None, None, 4, 1, 8, 8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        GF.hstu_attention_decode(q.detach().cpu(), kc, v, off, pos, None, None, None, None, 4, 1, 8, 8)
+
+
+def _inc_build(c, compute_dtype=None):
+    return _build(dict(c, sd=c["sd"]), compute_dtype=compute_dtype)
+
+
+@pytest.mark.parametrize("name", ["mh", "h64"])
+def test_hstu_incremental_fp32_vs_reference_golden(golden, name):
+    c = hstu_incremental_case(golden("hstu_incremental"), name)
+    enc = _inc_build(c)
+    kw = dict(past_lengths=c["lengths"].to(DEV), valid_mask=None,
+              past_payloads={"timestamps": c["ts"].to(DEV)})
+    with torch.no_grad():
+        y0, cache = enc(user_embeddings=c["x"].to(DEV), return_cache_states=True, **kw)
+        _close(y0, c["y0"], 1e-5, what=f"{name} y0")
+        assert len(cache) == c["blocks"]
+        for got, ref in zip(cache, c["cache0"]):
+            for a, b, nm in zip(got, ref, ("v", "padded_q", "padded_k", "out")):
+                assert a.shape == b.shape
+                _close(a, b, 1e-5, what=f"{name} cache {nm}")
+        # (1) from the reference's own cache states, (2) from ours; delta indices int64 and int32
+        for states, cast in (([tuple(t.to(DEV).clone() for t in st) for st in c["cache0"]], torch.int64),
+                             (cache, torch.int32)):
+            delta = tuple(t.to(DEV).to(cast) for t in c["delta"])
+            y, new_states = enc(user_embeddings=c["x2"].to(DEV), delta_x_offsets=delta, cache=states,
+                                return_cache_states=True, **kw)
+            _close(y, c["y_inc"], 1e-5, what=f"{name} y_inc")
+            assert len(new_states) == c["blocks"]
+            # in place, like the reference (index_copy_): the caller's tensors now hold the new rows
+            assert new_states[0][0].data_ptr() == states[0][0].data_ptr()
+            if c["cache1"] is not None:
+                for got, ref in zip(new_states, c["cache1"]):
+                    for a, b, nm in zip(got, ref, ("v", "padded_q", "padded_k", "out")):
+                        _close(a, b, 1e-5, what=f"{name} updated cache {nm}")
+
+
+def test_hstu_incremental_bf16_matches_full_pass(golden):
+    """bf16 / tcgen05 configuration: recomputing the last token through the caches equals a full
+    pass over the modified sequence (and the reference's fp32 result within the bf16 tolerance)."""
+    c = hstu_incremental_case(golden("hstu_incremental"), "h64")
+    enc = _inc_build(c, compute_dtype=torch.bfloat16)
+    kw = dict(past_lengths=c["lengths"].to(DEV), valid_mask=None,
+              past_payloads={"timestamps": c["ts"].to(DEV)})
+    with torch.no_grad():
+        _, cache = enc(user_embeddings=c["x"].to(DEV), return_cache_states=True, **kw)
+        assert cache[0][1].dtype == torch.bfloat16
+        delta = tuple(t.to(DEV) for t in c["delta"])
+        y_inc, _ = enc(user_embeddings=c["x2"].to(DEV), delta_x_offsets=delta, cache=cache, **kw)
+        y_full, _ = enc(user_embeddings=c["x2"].to(DEV), **kw)
+    _close(y_inc, y_full, 1e-2, 5e-3, what="bf16 incremental vs full")
+    _close(y_inc, c["y_inc"], 2e-2, 1e-2, what="bf16 incremental vs reference")
+
+
+def test_hstu_incremental_needs_cache(golden):
+    c = hstu_incremental_case(golden("hstu_incremental"), "mh")
+    enc = _inc_build(c)
+    with pytest.raises(ValueError, match="cache"), torch.no_grad():
+        enc(past_lengths=c["lengths"].to(DEV), user_embeddings=c["x2"].to(DEV), valid_mask=None,
+            past_payloads={"timestamps": c["ts"].to(DEV)},
+            delta_x_offsets=tuple(t.to(DEV) for t in c["delta"]))

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import reference_port as O
-from conftest import hstu_case
+from conftest import hstu_case, hstu_incremental_case
 
 
 def test_ops_known_answers(golden):
@@ -100,3 +100,27 @@ def test_inbatch_dedup(golden):
     assert sorted(ref) == sorted(int(i) for i in ids)
     for i, e in zip(ids, emb):
         assert torch.allclose(e, ref[int(i)], atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["mh", "h64"])
+def test_hstu_incremental_path(golden, name):
+    """delta_x_offsets + cache (hstu.py:293-298, :151-177, :415-418): cache states of a full pass,
+    then the last token of every sequence recomputed from them, against the real reference."""
+    c = hstu_incremental_case(golden("hstu_incremental"), name)
+    args = (c["sd"], c["blocks"], c["H"], c["dqk"], c["dv"])
+    states = O.hstu_cache_states(c["lengths"], c["x"], c["ts"], *args)
+    for got, ref in zip(states, c["cache0"]):
+        for a, b in zip(got, ref):
+            assert a.shape == b.shape
+            assert (a - b).abs().max().item() <= 1e-5 * max(b.abs().max().item(), 1e-6)
+    y, new_states = O.hstu_forward_incremental(c["lengths"], c["x2"], c["ts"], *args, c["delta"], c["cache0"])
+    assert (y - c["y_inc"]).abs().max().item() <= 1e-5 * c["y_inc"].abs().max().item()
+    # only the recomputed rows differ from the first pass
+    changed = ((y - c["y0"]).abs().sum(-1) > 0)
+    last = torch.zeros_like(changed)
+    last[torch.arange(c["B"]), c["lengths"] - 1] = True
+    assert torch.equal(changed & ~last, torch.zeros_like(changed))
+    if c["cache1"] is not None:
+        for got, ref in zip(new_states, c["cache1"]):
+            for a, b in zip(got, ref):
+                assert (a - b).abs().max().item() <= 1e-5 * max(b.abs().max().item(), 1e-6)
