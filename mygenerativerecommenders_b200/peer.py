@@ -1,7 +1,7 @@
 """Peer-memory plumbing for the multi-GPU paths: symmetric buffers (torch symmetric memory gives
 every rank the device pointers of all ranks' copies) and a stream barrier built on them.
 
-The exchanges themselves are this package's kernels (``grb_p2p_put_rows``, ``grb_p2p_rows_add``):
+The exchanges themselves are this package's kernels (``grb_p2p_put_rows``, ``grb_p2p_put_table_rows``):
 plain stores / ``red.global`` into the peers' buffers over NVLink / NVSwitch, ordered by
 ``grb_p2p_barrier`` — no NCCL call and no host synchronisation on the data path."""
 from __future__ import annotations
