@@ -220,7 +220,10 @@ def run_training(args, world, rank, local):
                       file=sys.stderr)
         step_mod = torch.nn.parallel.DistributedDataParallel(
             step_mod, device_ids=[local], gradient_as_bucket_view=True, broadcast_buffers=False)
-    opt = FusedAdamW(model.parameters(), lr=1e-3, betas=(0.9, 0.98), weight_decay=1e-3)
+    if os.environ.get("GRB_TORCH_ADAMW") == "1":     # A/B switch: the library optimizer
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, betas=(0.9, 0.98), weight_decay=1e-3, fused=True)
+    else:
+        opt = FusedAdamW(model.parameters(), lr=1e-3, betas=(0.9, 0.98), weight_decay=1e-3)
     pinned = [{k: v.pin_memory() for k, v in b.items()} for b in host]
     resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
 

@@ -281,6 +281,110 @@ __global__ void __launch_bounds__(DECV_THREADS) hstu_attn_decode_vec_kernel(Deco
   }
 }
 
+// ---- short sequences: CTA = sequence, one warp per head, no block barrier after the bias ----------
+// With a few hundred keys the block-wide kernel above is a chain of short loops separated by
+// __syncthreads (13 per sequence at H = 4) and runs at a third of the HBM rate.  Here the head-independent
+// bias is computed once by the whole CTA; after that every warp owns one (sequence, head): scores into
+// its private slice of shared memory, __syncwarp, value pass, and the lanes of key group 0 store the
+// output row as 16-byte chunks.  Latency is hidden by the number of independent warps per SM.
+template <typename T> __device__ __forceinline__ void store_chunk(T* dst, const float* f);
+template <> __device__ __forceinline__ void store_chunk<float>(float* dst, const float* f) {
+  *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
+}
+template <> __device__ __forceinline__ void store_chunk<__nv_bfloat16>(__nv_bfloat16* dst, const float* f) {
+  uint4 o;
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+  __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
+  o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+  o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+  *reinterpret_cast<uint4*>(dst) = o;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512) hstu_attn_decode_warp_kernel(DecodeParams p, int GQ, int GV) {
+  extern __shared__ __align__(16) float dsm[];
+  constexpr int E = Chunk<T>::E;
+  constexpr int U = 2;                                // independent loads per lane and trip
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, h = tid >> 5, lane = tid & 31;   // blockDim.x = 32 * H
+  const int64_t off0 = load_index(p.offsets, b, p.index_bits);
+  const int64_t n = load_index(p.offsets, b + 1, p.index_bits) - off0;
+  const int64_t pos = load_index(p.pos, b, p.pos_bits);
+  T* out = reinterpret_cast<T*>(p.out) + (int64_t) b * p.ldo + (int64_t) h * p.dv;
+  if (pos < 0 || pos >= p.N || pos >= n) {
+    for (int c = lane; c < p.dv; c += 32) st_f32(out + c, 0.f);
+    return;
+  }
+  const int nk = (int) pos + 1;
+  const int nk4 = (nk + 3) & ~3;
+  float* bias_s = dsm;
+  float* ps = dsm + nk4 * (1 + h);                    // this warp's probabilities
+  if (p.ts != nullptr) {
+    int64_t qi = pos + 1;                             // ext_ts[b, pos + 1]; index N reads ts[b, N-1]
+    if (qi >= p.N) qi = p.N - 1;
+    const int64_t tq = p.ts[(int64_t) b * p.N + qi];
+    for (int j = tid; j < nk; j += blockDim.x) {
+      int64_t d = tq - p.ts[(int64_t) b * p.N + j];
+      d = d < 0 ? -d : d;
+      bias_s[j] = p.pos_w[p.N - 1 + j - pos] + p.ts_w[bucket_of(p.thr, p.nb, d)];
+    }
+  } else {
+    for (int j = tid; j < nk; j += blockDim.x) bias_s[j] = 0.f;
+  }
+  __syncthreads();
+  const float inv_n = 1.0f / (float) p.N;
+  {
+    const int sub = lane & (GQ - 1), grp = lane / GQ, per = 32 / GQ;
+    float qf[E];
+    Chunk<T>::load(reinterpret_cast<const T*>(p.q) + (int64_t) b * p.ldq + (int64_t) h * p.dqk + sub * E, qf);
+    const T* kbase = reinterpret_cast<const T*>(p.kc) + ((int64_t) b * p.N) * p.ldk + (int64_t) h * p.dqk + sub * E;
+    for (int j0 = 0; j0 < nk; j0 += U * per) {
+      float kf[U][E];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = j0 + u * per + grp;
+        if (j < nk) Chunk<T>::load(kbase + (int64_t) j * p.ldk, kf[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = j0 + u * per + grp;
+        float acc = 0.f;
+        if (j < nk) {
+#pragma unroll
+          for (int e = 0; e < E; ++e) acc = fmaf(qf[e], kf[u][e], acc);
+        }
+        for (int o = GQ >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (sub == 0 && j < nk) ps[j] = silu_f32(acc + bias_s[j]) * inv_n;
+      }
+    }
+  }
+  __syncwarp();
+  {
+    const int sub = lane & (GV - 1), grp = lane / GV, per = 32 / GV;
+    const T* vbase = reinterpret_cast<const T*>(p.v) + off0 * p.ldv + (int64_t) h * p.dv + sub * E;
+    float acc[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) acc[e] = 0.f;
+    for (int j0 = grp; j0 < nk; j0 += U * per) {
+      float vf[U][E];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (j0 + u * per < nk) Chunk<T>::load(vbase + (int64_t) (j0 + u * per) * p.ldv, vf[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (j0 + u * per < nk) {
+          const float pj = ps[j0 + u * per];
+#pragma unroll
+          for (int e = 0; e < E; ++e) acc[e] = fmaf(pj, vf[u][e], acc[e]);
+        }
+    }
+    for (int o = GV; o < 32; o <<= 1)
+#pragma unroll
+      for (int e = 0; e < E; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
+    if (grp == 0) store_chunk<T>(out + sub * E, acc);
+  }
+}
+
 }  // namespace
 }  // namespace grb
 
@@ -323,7 +427,20 @@ extern "C" int grb_hstu_attn_decode(const grb_hstu_attn_decode_args* a, grb_stre
       return reinterpret_cast<uintptr_t>(ptr) % 16 == 0 && (ld * (int64_t) es) % 16 == 0;
     };
     const int gq = pow2_lanes(a->dqk), gv = pow2_lanes(a->dv);
-    if (gq && gv && al16(a->q, a->ldq) && al16(a->k_cache, a->ldk) && al16(a->v, a->ldv)) {
+    const bool aligned = gq && gv && al16(a->q, a->ldq) && al16(a->k_cache, a->ldk) && al16(a->v, a->ldv);
+    const size_t smemw = sizeof(float) * (size_t) (a->H + 1) * ((a->N + 3) & ~3);
+    if (aligned && a->H <= 16 && smemw <= 48 * 1024 && al16(a->out, a->ldo) &&
+        ((size_t) a->dv * es) % 16 == 0) {
+      // short sequences: one warp per (sequence, head)
+      dim3 gridw((unsigned) a->B);
+      if (a->dtype == GRB_F32)
+        hstu_attn_decode_warp_kernel<float><<<gridw, 32 * a->H, smemw, st>>>(p, gq, gv);
+      else
+        hstu_attn_decode_warp_kernel<__nv_bfloat16><<<gridw, 32 * a->H, smemw, st>>>(p, gq, gv);
+      GRB_LAUNCH_OK();
+      return GRB_OK;
+    }
+    if (aligned) {
       const size_t nwdv = (size_t) (DECV_THREADS / 32) * a->dv;
       const size_t smemv = sizeof(float) * (2 * ((a->N + 3) & ~3) + nwdv + (nwdv & 1)) + 8 * 256;
       // the bias is the same for every head: a CTA takes all heads of a sequence once there are
