@@ -494,8 +494,8 @@ def run_reference_arm(args, world, rank):
         return None
     cfg = c2_config(bf16=False)
     ids = synthetic_item_ids(26_744, cfg.num_items)
-    sample = 32
-    steps = max(1, min(args.steps, 4))
+    sample = PER_GPU_BATCH
+    steps = max(1, min(args.steps, 6))
     warm = 1 if args.warmup > 0 else 0
     base = cpu_train_baseline(cfg, ids, sample, steps, warm)
     retr = cpu_retrieval_baseline()
@@ -577,7 +577,7 @@ def main():
     if rank == 0:
         if world == 1 and not args.skip_cpu_baseline:
             fp32 = RetrievalConfig(**{**cfg.__dict__, "compute_dtype": None})
-            line["cpu_baseline"] = cpu_train_baseline(fp32, ids, 32, 2, 1, state)
+            line["cpu_baseline"] = cpu_train_baseline(fp32, ids, PER_GPU_BATCH, 6, 1, state)   # ~10 s of CPU work
             if retrieval is not None:
                 retrieval["cpu_baseline"] = cpu_retrieval_baseline()
         _emit(line, out_fd)

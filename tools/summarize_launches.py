@@ -18,7 +18,8 @@ def main():
     for r in rows[hdr + 1:]:
         if len(r) <= mv:
             continue
-        name = re.sub(r"\(.*", "", re.sub(r"<.*", "", r[kn])).replace("void ", "").strip()[:70]
+        raw = r[kn].replace("(anonymous namespace)::", "").replace("<unnamed>::", "").replace("void ", "")
+        name = re.sub(r"\(.*", "", re.sub(r"<.*", "", raw)).strip()[:70]
         v = float(r[mv].replace(",", ""))
         v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(r[mu].replace("second", "s").replace("n", "n"), 1e-3) if r[mu] in ("ns", "us", "ms") else 1e-3
         cnt[name] += 1
