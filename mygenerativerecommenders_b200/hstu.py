@@ -16,6 +16,7 @@ Extension: ``HSTU(..., compute_dtype=torch.bfloat16)`` runs the layers with bf16
 from __future__ import annotations
 
 import abc
+import math
 from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
@@ -147,6 +148,36 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
     def _norm_input(self, x: torch.Tensor) -> torch.Tensor:
         return GF.layer_norm_gate(x, None, self._eps)
 
+    def _softmax_branch(self, x, u, v, q, k, x_offsets, all_timestamps, invalid_attn_mask,
+                        return_cache_states):
+        """normalization="softmax_rel_bias" (hstu.py:337-384): ONE softmax attention over the full
+        H*dqk width (no head split), bias added before the softmax, causal mask applied AFTER it, so a
+        row's weights do not sum to one.  Not a hot path of any shipped config: composed from the jagged
+        kernels, cuBLAS bmm and ATen softmax in the reference's padded formulation, O(B N^2) memory."""
+        n = invalid_attn_mask.size(-1)
+        padded_q = ops.jagged_to_padded_dense(q.contiguous(), x_offsets, n, 0.0)
+        padded_k = ops.jagged_to_padded_dense(k.contiguous(), x_offsets, n, 0.0)
+        qk = torch.bmm(padded_q, padded_k.transpose(1, 2))
+        if self._rel_attn_bias is not None:
+            qk = qk + self._rel_attn_bias(all_timestamps).to(qk.dtype)
+        # as on the fused path only the size of invalid_attn_mask is read: the mask is the causal
+        # lower triangle HSTU registers (hstu.py:595-607, :667)
+        causal = torch.ones(n, n, dtype=qk.dtype, device=qk.device).tril_()
+        qk = F.softmax(qk / math.sqrt(self._attention_dim), dim=-1) * causal
+        attn_output = ops.dense_to_jagged(
+            torch.bmm(qk, ops.jagged_to_padded_dense(v.contiguous(), x_offsets, n, 0.0)), x_offsets)
+        if self._concat_ua:
+            a = self._norm_attn_output(attn_output)
+            o_input = torch.cat([u, a, u * a], dim=-1)
+        else:
+            o_input = GF.layer_norm_gate(attn_output, u.contiguous(), self._eps)
+        o_w = self._o.weight if self._o.weight.dtype == x.dtype else self._o.weight.to(x.dtype)
+        o_b = self._o.bias if self._o.bias.dtype == x.dtype else self._o.bias.to(x.dtype)
+        new_outputs = GF.linear_bias(
+            F.dropout(o_input, p=self._dropout_ratio, training=self.training), o_w, o_b) + x
+        cache_state = (v.contiguous(), padded_q, padded_k, new_outputs) if return_cache_states else None
+        return new_outputs, cache_state
+
     def _norm_attn_output(self, x: torch.Tensor) -> torch.Tensor:
         return GF.layer_norm_gate(x, None, self._eps)
 
@@ -171,10 +202,14 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
             rows = delta_x_offsets[0].long()
             x = x[rows, :]
             cached_v, cached_q, cached_k, cached_outputs = cache
-        if self._normalization not in ("rel_bias", "hstu_rel_bias"):
-            if self._normalization == "softmax_rel_bias":
-                raise NotImplementedError("softmax_rel_bias normalization is not implemented")
+        if self._normalization not in ("rel_bias", "hstu_rel_bias", "softmax_rel_bias"):
             raise ValueError(f"Unknown normalization method {self._normalization}")
+        softmax = self._normalization == "softmax_rel_bias"
+        if softmax and incremental:
+            # the reference's own branch cannot run: `B = x_offsets.size() - 1` (hstu.py:339) is a
+            # torch.Size minus an int
+            raise NotImplementedError("softmax_rel_bias has no incremental path (nor does the reference: "
+                                      "hstu.py:339 raises TypeError)")
         n: int = invalid_attn_mask.size(-1)
         H, dv, dqk = self._num_heads, self._linear_dim, self._attention_dim
 
@@ -187,6 +222,9 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
             raise ValueError(f"Unknown linear_activation {self._linear_activation}")
         u, v, q, k = torch.split(mm, [dv * H, dv * H, dqk * H, dqk * H], dim=1)
 
+        if softmax:
+            return self._softmax_branch(x, u, v, q, k, x_offsets, all_timestamps, invalid_attn_mask,
+                                        return_cache_states)
         bias = self._rel_attn_bias if all_timestamps is not None else None
         if bias is not None and not isinstance(bias, RelativeBucketedTimeAndPositionBasedBias):
             raise NotImplementedError(

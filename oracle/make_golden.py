@@ -112,13 +112,14 @@ def golden_bias(R):
     return g
 
 
-def _hstu_case(R, name, B, max_seq, out_len, D, H, dqk, dv, blocks, lengths, seed):
+def _hstu_case(R, name, B, max_seq, out_len, D, H, dqk, dv, blocks, lengths, seed,
+               normalization="rel_bias"):
     hstu = R["hstu"]
     N = max_seq + out_len
     torch.manual_seed(seed)
     enc = hstu.HSTU(max_sequence_len=max_seq, max_output_len=out_len, embedding_dim=D,
                     item_embedding_dim=D, num_blocks=blocks, num_heads=H, linear_dim=dv,
-                    attention_dim=dqk, normalization="rel_bias", linear_config="uvqk",
+                    attention_dim=dqk, normalization=normalization, linear_config="uvqk",
                     linear_activation="silu", linear_dropout_rate=0.2, attn_dropout_rate=0.0)
     enc.eval()
     gen = torch.Generator().manual_seed(seed + 1)
@@ -151,6 +152,16 @@ def golden_hstu(R):
     # tensor-core shaped heads (dqk = dv = 64), spans more than one 128-row tile
     g.update(_hstu_case(R, "h64", B=3, max_seq=150, out_len=11, D=128, H=2, dqk=64, dv=64,
                         blocks=1, lengths=[161, 130, 5], seed=30))
+    return g
+
+
+def golden_hstu_softmax(R):
+    """normalization="softmax_rel_bias" (hstu.py:337-384), forward and backward."""
+    g = {}
+    g.update(_hstu_case(R, "mh", B=5, max_seq=20, out_len=4, D=16, H=2, dqk=8, dv=8, blocks=2,
+                        lengths=[1, 24, 7, 13, 2], seed=70, normalization="softmax_rel_bias"))
+    g.update(_hstu_case(R, "h64", B=3, max_seq=60, out_len=4, D=64, H=2, dqk=64, dv=64, blocks=1,
+                        lengths=[64, 30, 5], seed=80, normalization="softmax_rel_bias"))
     return g
 
 
@@ -264,7 +275,8 @@ def main():
     OUT.mkdir(parents=True, exist_ok=True)
     only = set(sys.argv[1:])                    # e.g. `make_golden.py hstu_incremental`; default: all
     for name, fn in [("ops", golden_ops), ("bias", golden_bias), ("hstu", golden_hstu),
-                     ("hstu_incremental", golden_hstu_incremental), ("retrieval", golden_retrieval)]:
+                     ("hstu_incremental", golden_hstu_incremental), ("hstu_softmax", golden_hstu_softmax),
+                     ("retrieval", golden_retrieval)]:
         if only and name not in only:
             continue
         data = fn(R)

@@ -117,9 +117,22 @@ def hstu_attention(q, k, v, offsets, ts, ts_w, pos_w, N: int, H: int, dqk: int, 
 # a6-a8: hstu.py:266-423, :439-518, :633-672.  Parameters come as a state dict with the
 # reference's names (``_hstu._attention_layers.{i}._uvqk`` ...).
 # ------------------------------------------------------------------------------------------
+def hstu_attention_softmax(q, k, v, offsets, bias, N: int, dqk: int):
+    """normalization="softmax_rel_bias" (hstu.py:370-384): one attention over the full H*dqk width,
+    softmax over ALL N columns of the padded row, causal mask applied after the softmax."""
+    pq = jagged_to_padded_dense(q, offsets, N)
+    pk = jagged_to_padded_dense(k, offsets, N)
+    s = torch.einsum("bnd,bmd->bnm", pq, pk)
+    if bias is not None:
+        s = s + bias.to(s.dtype)
+    p = F.softmax(s / math.sqrt(dqk), dim=-1) * torch.tril(torch.ones(N, N, dtype=s.dtype))
+    return dense_to_jagged(torch.bmm(p, jagged_to_padded_dense(v, offsets, N)), offsets)
+
+
 def stu_layer(x, offsets, ts, sd: Dict[str, torch.Tensor], prefix: str, N, H, dqk, dv,
               eps: float = 1e-6, dropout_p: float = 0.0, training: bool = False,
-              linear_activation: str = "silu", concat_ua: bool = False):
+              linear_activation: str = "silu", concat_ua: bool = False,
+              normalization: str = "rel_bias"):
     D = x.shape[1]
     xn = F.layer_norm(x, [D], eps=eps)
     mm = xn @ sd[prefix + "_uvqk"].to(x.dtype)
@@ -127,9 +140,14 @@ def stu_layer(x, offsets, ts, sd: Dict[str, torch.Tensor], prefix: str, N, H, dq
         mm = F.silu(mm)
     u, v, q, k = torch.split(mm, [H * dv, H * dv, H * dqk, H * dqk], dim=1)
     has_bias = (prefix + "_rel_attn_bias._ts_w") in sd and ts is not None
-    a = hstu_attention(q, k, v, offsets, ts if has_bias else None,
-                       sd.get(prefix + "_rel_attn_bias._ts_w"),
-                       sd.get(prefix + "_rel_attn_bias._pos_w"), N, H, dqk, dv)
+    if normalization == "softmax_rel_bias":
+        ts_w, pos_w = sd.get(prefix + "_rel_attn_bias._ts_w"), sd.get(prefix + "_rel_attn_bias._pos_w")
+        bias = rel_bias(ts, ts_w, pos_w, N, ts_w.numel() - 1) if has_bias else None
+        a = hstu_attention_softmax(q, k, v, offsets, bias, N, dqk)
+    else:
+        a = hstu_attention(q, k, v, offsets, ts if has_bias else None,
+                           sd.get(prefix + "_rel_attn_bias._ts_w"),
+                           sd.get(prefix + "_rel_attn_bias._pos_w"), N, H, dqk, dv)
     an = F.layer_norm(a, [H * dv], eps=eps)
     o_in = torch.cat([u, an, u * an], dim=-1) if concat_ua else u * an
     o_in = F.dropout(o_in, p=dropout_p, training=training)

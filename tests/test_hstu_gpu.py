@@ -143,11 +143,11 @@ def test_ln_gate_vs_torch(W, dtype):
     _close(y2, torch.nn.functional.layer_norm(xr.detach(), [W], eps=1e-6), *t, what="ln y")
 
 
-def _build(c, compute_dtype=None):
+def _build(c, compute_dtype=None, normalization="rel_bias"):
     enc = hstu.HSTU(max_sequence_len=c["max_seq"], max_output_len=c["out_len"],
                     embedding_dim=c["D"], item_embedding_dim=c["D"], num_blocks=c["blocks"],
                     num_heads=c["H"], linear_dim=c["dv"], attention_dim=c["dqk"],
-                    normalization="rel_bias", linear_config="uvqk", linear_activation="silu",
+                    normalization=normalization, linear_config="uvqk", linear_activation="silu",
                     linear_dropout_rate=0.2, attn_dropout_rate=0.0, compute_dtype=compute_dtype)
     enc.load_state_dict(c["sd"], strict=False)
     return enc.to(DEV).eval()
@@ -453,3 +453,27 @@ def test_hstu_incremental_needs_cache(golden):
         enc(past_lengths=c["lengths"].to(DEV), user_embeddings=c["x2"].to(DEV), valid_mask=None,
             past_payloads={"timestamps": c["ts"].to(DEV)},
             delta_x_offsets=tuple(t.to(DEV) for t in c["delta"]))
+
+
+# ---------------------------------------------------------------------------------------------
+# normalization="softmax_rel_bias" (hstu.py:337-384): composite of the jagged kernels, cuBLAS, ATen
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["mh", "h64"])
+def test_hstu_softmax_rel_bias_vs_reference_golden(golden, name):
+    c = hstu_case(golden("hstu_softmax"), name)
+    enc = _build(c, normalization="softmax_rel_bias")
+    x = c["x"].to(DEV).requires_grad_(True)
+    y, _ = enc(past_lengths=c["lengths"].to(DEV), user_embeddings=x, valid_mask=None,
+               past_payloads={"timestamps": c["ts"].to(DEV)})
+    _close(y, c["y"], 1e-5, what=f"softmax {name} y")
+    (y * c["w"].to(DEV)).sum().backward()
+    _close(x.grad, c["dx"], 2e-4, what=f"softmax {name} dx")
+    for k, p in enc.named_parameters():
+        _close(p.grad, c["grads"][k], 5e-4, what=f"softmax {name} grad {k}")
+    with pytest.raises(NotImplementedError, match="incremental"), torch.no_grad():
+        _, cache = enc(past_lengths=c["lengths"].to(DEV), user_embeddings=x.detach(), valid_mask=None,
+                       past_payloads={"timestamps": c["ts"].to(DEV)}, return_cache_states=True)
+        off = O.complete_cumsum(c["lengths"])
+        enc(past_lengths=c["lengths"].to(DEV), user_embeddings=x.detach(), valid_mask=None,
+            past_payloads={"timestamps": c["ts"].to(DEV)}, cache=cache,
+            delta_x_offsets=((off[1:] - 1).to(DEV), (c["lengths"] - 1).to(DEV)))

@@ -124,3 +124,18 @@ def test_hstu_incremental_path(golden, name):
         for got, ref in zip(new_states, c["cache1"]):
             for a, b in zip(got, ref):
                 assert (a - b).abs().max().item() <= 1e-5 * max(b.abs().max().item(), 1e-6)
+
+
+@pytest.mark.parametrize("name", ["mh", "h64"])
+def test_hstu_softmax_rel_bias(golden, name):
+    """normalization="softmax_rel_bias" (hstu.py:337-384) against the real reference."""
+    c = hstu_case(golden("hstu_softmax"), name)
+    sd = {k: v.clone().requires_grad_(True) for k, v in c["sd"].items()}
+    x = c["x"].clone().requires_grad_(True)
+    y = O.hstu_forward(c["lengths"], x, c["ts"], sd, c["blocks"], c["H"], c["dqk"], c["dv"],
+                       normalization="softmax_rel_bias")
+    assert (y - c["y"]).abs().max().item() <= 1e-5 * c["y"].abs().max().item()
+    (y * c["w"]).sum().backward()
+    assert (x.grad - c["dx"]).abs().max().item() <= 1e-4 * c["dx"].abs().max().item()
+    for k, gref in c["grads"].items():
+        assert (sd[k].grad - gref).abs().max().item() <= 2e-4 * max(gref.abs().max().item(), 1e-6), k
