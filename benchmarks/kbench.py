@@ -162,6 +162,21 @@ def bench_decode(tag, B, N, H, lengths, d=64):
         report(f"hstu_attn_decode[{tag}]", timeit(run), byts=byts)
 
 
+def bench_silu():
+    T, sizes = 14_336, [256, 256, 256, 256]
+    x = torch.randn(T, 1024, device=DEV).to(torch.bfloat16).requires_grad_(True)
+    byts = T * 1024 * 2
+    with torch.no_grad():
+        report("silu_fwd[C2 14336x1024 bf16]", timeit(lambda: GF.silu_split(x, sizes)), byts=2 * byts)
+        report("aten silu (library, for comparison)", timeit(lambda: torch.nn.functional.silu(x)), byts=2 * byts)
+    parts = GF.silu_split(x, sizes)
+    gs = [torch.randn_like(p) for p in parts]
+    report("silu_split_bwd[C2]", timeit(lambda: torch.autograd.grad(parts, x, gs, retain_graph=True)), byts=3 * byts)
+    ref = torch.split(torch.nn.functional.silu(x), sizes, dim=1)
+    report("aten cat + silu_backward (library, for comparison)",
+           timeit(lambda: torch.autograd.grad(ref, x, gs, retain_graph=True)), byts=3 * byts)
+
+
 def bench_adamw():
     from mygenerativerecommenders_b200.optim import FusedAdamW
     p = torch.nn.Parameter(torch.randn(131_263, 256, device=DEV))
@@ -217,6 +232,8 @@ def main():
         bench_decode("C2 128x U[20,200] N211 H4", 128, 211, 4, torch.randint(20, 201, (128,), generator=g))
         bench_decode("serving 4096x U[20,200] N211 H4", 4096, 211, 4, torch.randint(20, 201, (4096,), generator=g))
         bench_decode("C5 128x U[1024,8192] N8192 H8", 128, 8192, 8, torch.randint(1024, 8193, (128,), generator=g))
+    if want("silu"):
+        bench_silu()
     if want("adamw"):
         bench_adamw()
     if want("jagged"):

@@ -175,6 +175,22 @@ typedef struct grb_hstu_attn_decode_args {
 int grb_hstu_attn_decode(const grb_hstu_attn_decode_args* a, grb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * a6  hstu.py:304-320  the activation between the UVQK projection and its consumers:
+ *     F.silu(batched_mm_output) followed by torch.split into u, v, q, k.
+ *     grb_silu_fwd: y = x / (1 + exp(-x)), (rows, W), fp32 math.
+ *     grb_silu_split_bwd: the consumers return n_blocks (<= 4) separate gradients grads[i] of shape
+ *     (rows, widths[i]) (row stride ld_grads[i]; NULL = zero), the column blocks of the activation in
+ *     order; dx (rows, sum widths) = cat(grads) * silu'(x) in ONE pass (autograd: cat, then
+ *     silu_backward).  grads / ld_grads / widths are HOST arrays.  Rows 16-byte aligned, widths
+ *     multiples of 16 bytes.
+ * ------------------------------------------------------------------------------------------- */
+int grb_silu_fwd(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t rows, int32_t W,
+                 int32_t dtype, grb_stream_t stream);
+int grb_silu_split_bwd(const void* x, int64_t ldx, int32_t n_blocks, const void* const* grads,
+                       const int64_t* ld_grads, const int32_t* widths, void* dx, int64_t lddx,
+                       int64_t rows, int32_t dtype, grb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * a6  hstu.py:258-264,402  y = gate * LayerNorm_W(x; eps, no affine)   (gate == NULL: y = LN(x))
  *     x,gate,y: (rows, W) row strides ldx/ldg/ldy elements.  mean/rstd (rows) fp32 are saved
  *     for backward.  Backward: dx, dgate from dy (dgate == NULL when gate == NULL).

@@ -119,6 +119,9 @@ SYMBOLS = {
     "grb_p2p_put_table_rows": (C.c_int, [c_vp, c_vp, c_i64, c_i32, c_i64, c_i64, C.c_float, C.POINTER(c_vp),
                                          C.POINTER(c_vp), c_i32, c_i64, c_vp]),
     "grb_hstu_attn_decode": (C.c_int, [C.POINTER(HstuAttnDecodeArgs), c_vp]),
+    "grb_silu_fwd": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i32, c_i32, c_vp]),
+    "grb_silu_split_bwd": (C.c_int, [c_vp, c_i64, c_i32, C.POINTER(c_vp), C.POINTER(c_i64), C.POINTER(c_i32),
+                                     c_vp, c_i64, c_i64, c_i32, c_vp]),
     "grb_adamw_step": (C.c_int, [C.c_int, C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp),
                                  C.POINTER(c_i64)] + [C.c_double] * 7 + [c_vp]),
     "grb_rows_scatter_add": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_i64, c_i64, c_vp]),

@@ -285,6 +285,60 @@ class _LnGate(torch.autograd.Function):
         return dx, dgate, None
 
 
+class _SiluSplit(torch.autograd.Function):
+    """torch.split(F.silu(x), sizes, dim=1) (hstu.py:304-320).  Backward: the pieces' gradients come
+    back separately; one kernel reads them in place and applies silu' (autograd: cat + silu_backward,
+    two full passes)."""
+
+    @staticmethod
+    def forward(ctx, x, *sizes):
+        _lib.require_cuda(x)
+        x = _rows_contiguous(x)
+        rows, W = x.shape
+        y = torch.empty((rows, W), dtype=x.dtype, device=x.device)
+        _lib.check(_lib.lib().grb_silu_fwd(x.data_ptr(), _ld(x), y.data_ptr(), W, rows, W,
+                                           _lib.dtype_code(x.dtype), _lib.stream_ptr(x.device)))
+        ctx.save_for_backward(x)
+        ctx.sizes = sizes
+        return tuple(y.split(list(sizes), dim=1))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        (x,) = ctx.saved_tensors
+        rows, W = x.shape
+        n = len(ctx.sizes)
+        es = x.element_size()
+
+        def prep(g):
+            if g is None:
+                return None
+            g = _rows_contiguous(g if g.dtype == x.dtype else g.to(x.dtype))
+            if g.data_ptr() % 16 or (_ld(g) * es) % 16:      # the kernel reads 16-byte chunks
+                g = g.clone(memory_format=torch.contiguous_format)
+            return g
+
+        keep = [prep(g) for g in grads]
+        dx = torch.empty((rows, W), dtype=x.dtype, device=x.device)
+        ptrs = (C.c_void_p * n)(*[None if g is None else g.data_ptr() for g in keep])
+        lds = (C.c_int64 * n)(*[0 if g is None else _ld(g) for g in keep])
+        widths = (C.c_int32 * n)(*ctx.sizes)
+        _lib.check(_lib.lib().grb_silu_split_bwd(
+            x.data_ptr(), _ld(x), n, ptrs, lds, widths, dx.data_ptr(), W, rows,
+            _lib.dtype_code(x.dtype), _lib.stream_ptr(x.device)))
+        return (dx,) + (None,) * n
+
+
+def silu_split(x: torch.Tensor, sizes) -> Tuple[torch.Tensor, ...]:
+    """``torch.split(F.silu(x), sizes, dim=1)`` for a 2-D activation with up to four column blocks
+    whose widths are multiples of 16 bytes (the u, v, q, k blocks of the HSTU layer)."""
+    sizes = [int(v) for v in sizes]
+    per = 16 // x.element_size()
+    if (x.is_cuda and x.dim() == 2 and x.dtype in (torch.float32, torch.bfloat16) and 1 <= len(sizes) <= 4
+            and sum(sizes) == x.shape[1] and all(v > 0 and v % per == 0 for v in sizes)):
+        return _SiluSplit.apply(x, *sizes)
+    return torch.split(torch.nn.functional.silu(x), sizes, dim=1)
+
+
 class _LinearBias(torch.autograd.Function):
     """F.linear(x, w, b) for 2-D x whose bias gradient is a (1, T) x (T, out) GEMM instead of
     ATen's column reduction (25 us for a 14k x 256 bf16 gradient, 4 per step at the C2 shape)."""

@@ -216,11 +216,13 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
         normed_x = self._norm_input(x)
         w = self._uvqk if self._uvqk.dtype == x.dtype else self._uvqk.to(x.dtype)
         mm = torch.mm(normed_x, w)
+        sizes = [dv * H, dv * H, dqk * H, dqk * H]
         if self._linear_activation == "silu":
-            mm = F.silu(mm)
-        elif self._linear_activation != "none":
+            u, v, q, k = GF.silu_split(mm, sizes)      # F.silu + torch.split, one backward pass
+        elif self._linear_activation == "none":
+            u, v, q, k = torch.split(mm, sizes, dim=1)
+        else:
             raise ValueError(f"Unknown linear_activation {self._linear_activation}")
-        u, v, q, k = torch.split(mm, [dv * H, dv * H, dqk * H, dqk * H], dim=1)
 
         if softmax:
             return self._softmax_branch(x, u, v, q, k, x_offsets, all_timestamps, invalid_attn_mask,

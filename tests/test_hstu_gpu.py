@@ -477,3 +477,26 @@ def test_hstu_softmax_rel_bias_vs_reference_golden(golden, name):
         enc(past_lengths=c["lengths"].to(DEV), user_embeddings=x.detach(), valid_mask=None,
             past_payloads={"timestamps": c["ts"].to(DEV)}, cache=cache,
             delta_x_offsets=((off[1:] - 1).to(DEV), (c["lengths"] - 1).to(DEV)))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_silu_split_matches_torch(dtype):
+    """grb_silu_fwd / grb_silu_split_bwd against F.silu + torch.split (hstu.py:304-320); one of the
+    pieces gets no gradient, one arrives as a strided view."""
+    gen = torch.Generator().manual_seed(3)
+    rows, sizes = 1037, [64, 64, 32, 96]
+    x = (torch.randn(rows, sum(sizes), generator=gen) * 3).to(DEV).to(dtype)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    pa = GF.silu_split(xa, sizes)
+    pb = torch.split(torch.nn.functional.silu(xb), sizes, dim=1)
+    for a, b in zip(pa, pb):
+        assert a.shape == b.shape
+        torch.testing.assert_close(a, b, rtol=1e-6 if dtype == torch.float32 else 1e-2, atol=1e-6)
+    big = torch.randn(rows, 2 * sizes[3], generator=gen).to(DEV).to(dtype)
+    w0 = torch.randn(rows, sizes[0], generator=gen).to(DEV).to(dtype)
+    w2 = torch.randn(rows, sizes[2], generator=gen).to(DEV).to(dtype)
+    for p, xx in ((pa, xa), (pb, xb)):      # piece 1 unused, piece 3 multiplied by a strided view
+        ((p[0] * w0).sum() + (p[2] * w2).sum() + (p[3] * big[:, ::2]).sum()).backward()
+    tol = dict(rtol=1e-5, atol=1e-6) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(xa.grad, xb.grad, **tol)
+    assert xa.grad[:, sizes[0]:sizes[0] + sizes[1]].abs().max().item() == 0.0
