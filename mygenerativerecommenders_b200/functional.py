@@ -358,6 +358,60 @@ class _LinearBias(torch.autograd.Function):
         return dx, dw, db
 
 
+def _mm_out(a: torch.Tensor, b: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
+    """a @ b with the result written in out_dtype by the GEMM itself (cuBLAS fp32 epilogue)."""
+    if out_dtype == a.dtype:
+        return torch.mm(a, b)
+    return torch.mm(a, b, out_dtype=out_dtype)
+
+
+class _MasterLinear(torch.autograd.Function):
+    """Projection of low-precision activations by fp32 master parameters (the two projections of
+    the HSTU layer, hstu.py:302-304 and :404-413, under bf16 compute).  The parameters are cast to
+    the activation dtype inside; backward lets the GEMMs write the weight and bias gradients in
+    the parameters' dtype directly, instead of a bf16 gradient that autograd then casts (one
+    elementwise launch per parameter and step, and a rounding that the fp32 accumulator did not need).
+
+    ``w_in_out``: w is (in, out) and y = x @ w (``_uvqk``); else w is (out, in) and
+    y = x @ w.T + b (``nn.Linear``)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, w_in_out):
+        wc = w if w.dtype == x.dtype else w.to(x.dtype)
+        ctx.save_for_backward(x, wc)
+        ctx.w_in_out = w_in_out
+        ctx.w_dtype = w.dtype
+        ctx.b_dtype = b.dtype if b is not None else None
+        if w_in_out:
+            return torch.mm(x, wc)
+        bc = b if b.dtype == x.dtype else b.to(x.dtype)
+        return torch.addmm(bc, x, wc.t())
+
+    @staticmethod
+    def backward(ctx, g):
+        x, wc = ctx.saved_tensors
+        g = g.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.mm(g, wc.t() if ctx.w_in_out else wc)
+        if ctx.needs_input_grad[1]:
+            dw = _mm_out(x.t(), g, ctx.w_dtype) if ctx.w_in_out else _mm_out(g.t(), x, ctx.w_dtype)
+        if ctx.b_dtype is not None and ctx.needs_input_grad[2]:
+            db = _mm_out(g.new_ones(1, g.shape[0]), g, ctx.b_dtype).view(-1)
+        return dx, dw, db, None
+
+
+def master_linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor] = None,
+                  w_in_out: bool = False) -> torch.Tensor:
+    """x @ w (``w_in_out``) or F.linear(x, w, b), with w / b possibly fp32 masters of a bf16 x."""
+    if x.is_cuda and x.dim() == 2:
+        return _MasterLinear.apply(x, w, b, w_in_out)
+    wc = w.to(x.dtype)
+    if w_in_out:
+        return torch.mm(x, wc)
+    return torch.nn.functional.linear(x, wc, None if b is None else b.to(x.dtype))
+
+
 def linear_bias(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """x @ w.T + b (hstu.py:404-413 output projection)."""
     if x.dim() == 2 and x.is_cuda and b is not None:

@@ -171,10 +171,9 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
             o_input = torch.cat([u, a, u * a], dim=-1)
         else:
             o_input = GF.layer_norm_gate(attn_output, u.contiguous(), self._eps)
-        o_w = self._o.weight if self._o.weight.dtype == x.dtype else self._o.weight.to(x.dtype)
-        o_b = self._o.bias if self._o.bias.dtype == x.dtype else self._o.bias.to(x.dtype)
-        new_outputs = GF.linear_bias(
-            F.dropout(o_input, p=self._dropout_ratio, training=self.training), o_w, o_b) + x
+        new_outputs = GF.master_linear(
+            F.dropout(o_input, p=self._dropout_ratio, training=self.training),
+            self._o.weight, self._o.bias) + x
         cache_state = (v.contiguous(), padded_q, padded_k, new_outputs) if return_cache_states else None
         return new_outputs, cache_state
 
@@ -214,8 +213,7 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
         H, dv, dqk = self._num_heads, self._linear_dim, self._attention_dim
 
         normed_x = self._norm_input(x)
-        w = self._uvqk if self._uvqk.dtype == x.dtype else self._uvqk.to(x.dtype)
-        mm = torch.mm(normed_x, w)
+        mm = GF.master_linear(normed_x, self._uvqk, None, w_in_out=True)
         sizes = [dv * H, dv * H, dqk * H, dqk * H]
         if self._linear_activation == "silu":
             u, v, q, k = GF.silu_split(mm, sizes)      # F.silu + torch.split, one backward pass
@@ -259,10 +257,9 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
         else:
             o_input = GF.layer_norm_gate(attn_output, u, self._eps)
 
-        o_w = self._o.weight if self._o.weight.dtype == x.dtype else self._o.weight.to(x.dtype)
-        o_b = self._o.bias if self._o.bias.dtype == x.dtype else self._o.bias.to(x.dtype)
-        new_outputs = GF.linear_bias(
-            F.dropout(o_input, p=self._dropout_ratio, training=self.training), o_w, o_b) + x
+        new_outputs = GF.master_linear(
+            F.dropout(o_input, p=self._dropout_ratio, training=self.training),
+            self._o.weight, self._o.bias) + x
 
         cache_state = None
         if incremental:
