@@ -472,7 +472,7 @@ def cpu_train_baseline(cfg, ids, sample_batch: int, steps: int, warmup: int, sta
                       f"{total:.1f} s of CPU work", "ms_per_step": 1e3 * total / len(times)}
 
 
-def cpu_retrieval_baseline(D=256, k=200, Bq=256, Xs=1_000_000):
+def cpu_retrieval_baseline(D=256, k=200, Bq=4096, Xs=2_000_000):   # the real query batch, 1/5 of the corpus
     from oracle.ref_step import torch_topk_baseline
     torch.set_num_threads(os.cpu_count() or 1)
     g = torch.Generator().manual_seed(0)
