@@ -256,12 +256,24 @@ def run_training(args, world, rank, local):
     # ---- end to end: pinned host batch -> device each step, loss read back each step ---------
     h2d = sum(v.numel() * v.element_size() for v in pinned[0].values())
     barrier(world)
+    # The loss of every step is copied to pinned host memory as part of the step and read by the
+    # host one step later (what a logging callback does): a blocking .item() right after launching
+    # the step would only measure how long the host takes to enqueue the next one.
+    last = 0.0
+    loss_host = torch.empty(2, dtype=torch.float32).pin_memory()
+    copied = [torch.cuda.Event(), torch.cuda.Event()]
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    last = 0.0
     for i in range(args.steps):
         row = {k: v.to(dev, non_blocking=True) for k, v in pinned[i % n_batches].items()}
-        last = step(row, totals[i % n_batches]).item()     # D2H read of the loss
+        loss = step(row, totals[i % n_batches])
+        loss_host[i % 2].copy_(loss.detach(), non_blocking=True)       # D2H read of the loss
+        copied[i % 2].record()
+        if i > 0:
+            copied[(i - 1) % 2].synchronize()
+            last = float(loss_host[(i - 1) % 2])
+    copied[(args.steps - 1) % 2].synchronize()
+    last = float(loss_host[(args.steps - 1) % 2])
     e3.record()
     barrier(world)
     ms_e2e = max_over_ranks(e2.elapsed_time(e3), world, dev)
@@ -292,7 +304,8 @@ def run_training(args, world, rank, local):
     out = {
         "value": seqs / (ms / 1e3), "ms_per_step": ms / args.steps,
         "e2e": {"value": seqs / (ms_e2e / 1e3), "unit": "sequences/s",
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "d2h": "loss of every step copied to pinned host memory, consumed by the host one step later"},
         "gpu_launches": int(launches), "clocks": clk.summary(), "final_loss": last,
     }
     # ---- roofline of the dominant hand-written kernel, from the live per-kernel events -------
@@ -409,12 +422,24 @@ def run_retrieval(args, world, rank, local, X_total=10_000_000, B=4096, D=256, k
     barrier(world)
     ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
     prof = _lib.profile_stop()
+    # results land in pinned host buffers (two, alternating) and are consumed one step later, so the
+    # copy of step i overlaps the host work of step i + 1 instead of blocking it
+    ids_host = [torch.empty((B, k), dtype=torch.int64).pin_memory() for _ in range(2)]
+    copied = [torch.cuda.Event(), torch.cuda.Event()]
+    checksum = 0
+    torch.cuda.synchronize()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for i in range(steps):
         q = pinned_q[i % n_q].to(dev, non_blocking=True)
         s, ids_ = once(q)
-        ids_host = ids_.cpu()                                  # D2H of the result
+        ids_host[i % 2].copy_(ids_, non_blocking=True)         # D2H of the result
+        copied[i % 2].record()
+        if i > 0:
+            copied[(i - 1) % 2].synchronize()
+            checksum += int(ids_host[(i - 1) % 2][0, 0])       # the host touches every result
+    copied[(steps - 1) % 2].synchronize()
+    checksum += int(ids_host[(steps - 1) % 2][0, 0])
     e3.record()
     barrier(world)
     ms_e2e = max_over_ranks(e2.elapsed_time(e3), world, dev)
@@ -427,7 +452,8 @@ def run_retrieval(args, world, rank, local, X_total=10_000_000, B=4096, D=256, k
         "metric": "topk_retrieval_queries_per_s", "unit": "queries/s",
         "value": B * steps / (ms / 1e3), "ms_per_step": ms / steps, "steps": steps,
         "e2e": {"value": B * steps / (ms_e2e / 1e3), "unit": "queries/s",
-                "h2d_bytes_per_step": B * D * 2, "d2h_bytes_per_step": B * k * 8},
+                "h2d_bytes_per_step": B * D * 2, "d2h_bytes_per_step": B * k * 8,
+                "d2h": "top-k ids of every step copied to pinned host memory, consumed one step later"},
         "config": {"workload": f"C4 retrieval-only MIPS top-k={k}: {X_total} x {D} bf16 items "
                                f"sharded over {world} GPU(s), {B} queries/batch, exact, "
                                "ties->lowest id; table (5.1 GB total) >> L2",
