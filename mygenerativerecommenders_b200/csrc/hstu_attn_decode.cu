@@ -140,10 +140,10 @@ __global__ void __launch_bounds__(DEC_THREADS) hstu_attn_decode_kernel(DecodePar
 // lane stays in registers; partial dot products meet through shuffles.  The value pass keeps the same
 // lane <-> chunk mapping, every lane accumulating its 16 bytes of columns over the keys of its group.
 constexpr int DECV_THREADS = 256;
-// independent 16-byte loads per lane and loop trip.  Measured (B200, bf16, d = 64): 4 costs more in
-// registers (128 per thread, half the resident warps) than it gains in loads in flight (serving shape
-// 0.23 -> 0.35 ms), so it stays at 1.
-constexpr int DEC_UNROLL = 1;
+// independent 16-byte loads per lane and loop trip.  Measured on the 8 k-token shape (B200, bf16, d = 64):
+// 1 -> 0.74 ms (64 registers, 4 CTAs / SM), 2 -> 0.67 ms (79 registers, 3 CTAs / SM), 4 -> slower
+// (128 registers: the lost occupancy outweighs the loads in flight).
+constexpr int DEC_UNROLL = 2;
 
 template <typename T> struct Chunk;           // 16 bytes of T as floats
 template <> struct Chunk<float> {
