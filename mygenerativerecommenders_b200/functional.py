@@ -331,9 +331,10 @@ class _SiluSplit(torch.autograd.Function):
 def silu_split(x: torch.Tensor, sizes) -> Tuple[torch.Tensor, ...]:
     """``torch.split(F.silu(x), sizes, dim=1)`` for a 2-D activation with up to four column blocks
     whose widths are multiples of 16 bytes (the u, v, q, k blocks of the HSTU layer)."""
+    _lib.require_cuda(x)
     sizes = [int(v) for v in sizes]
     per = 16 // x.element_size()
-    if (x.is_cuda and x.dim() == 2 and x.dtype in (torch.float32, torch.bfloat16) and 1 <= len(sizes) <= 4
+    if (x.dim() == 2 and x.dtype in (torch.float32, torch.bfloat16) and 1 <= len(sizes) <= 4
             and sum(sizes) == x.shape[1] and all(v > 0 and v % per == 0 for v in sizes)):
         return _SiluSplit.apply(x, *sizes)
     return torch.split(torch.nn.functional.silu(x), sizes, dim=1)
@@ -404,7 +405,8 @@ class _MasterLinear(torch.autograd.Function):
 def master_linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor] = None,
                   w_in_out: bool = False) -> torch.Tensor:
     """x @ w (``w_in_out``) or F.linear(x, w, b), with w / b possibly fp32 masters of a bf16 x."""
-    if x.is_cuda and x.dim() == 2:
+    _lib.require_cuda(x, w, b)
+    if x.dim() == 2:
         return _MasterLinear.apply(x, w, b, w_in_out)
     wc = w.to(x.dtype)
     if w_in_out:
@@ -414,7 +416,8 @@ def master_linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor] = 
 
 def linear_bias(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """x @ w.T + b (hstu.py:404-413 output projection)."""
-    if x.dim() == 2 and x.is_cuda and b is not None:
+    _lib.require_cuda(x, w, b)
+    if x.dim() == 2 and b is not None:
         return _LinearBias.apply(x, w, b)
     return torch.nn.functional.linear(x, w, b)
 
@@ -450,7 +453,8 @@ class _L2Norm(torch.autograd.Function):
 def l2_normalize(x: torch.Tensor, eps: float) -> torch.Tensor:
     """x / clamp(||x||_2 over the last dim, min=eps): negative_sampler.py:31-37, postprocessors.py:47-55.
     One kernel forward, one backward (fp32 CUDA); other inputs take the reference's composite."""
-    if x.is_cuda and x.dtype == torch.float32 and x.numel() > 0:
+    _lib.require_cuda(x)
+    if x.dtype == torch.float32 and x.numel() > 0:
         return _L2Norm.apply(x, eps)
     return x / torch.clamp(torch.linalg.norm(x, ord=None, dim=-1, keepdim=True), min=eps)
 

@@ -99,8 +99,7 @@ class ItemEmbeddings(torch.nn.Module):
         return self.year_lookup_table[item_ids.clamp(0, self.year_lookup_table.size(0) - 1)]
 
     def get_item_embeddings(self, item_ids: torch.Tensor) -> torch.Tensor:
-        look = lambda emb, ids: (GF.embedding_lookup(emb.weight, ids, emb.padding_idx)
-                                 if emb.weight.is_cuda else emb(ids))
+        look = lambda emb, ids: GF.embedding_lookup(emb.weight, ids, emb.padding_idx)   # CUDA only
         if self._year_emb is None:
             return look(self._item_emb, item_ids)
         return torch.cat([look(self._item_emb, item_ids),
