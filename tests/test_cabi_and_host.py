@@ -55,6 +55,28 @@ def test_no_cpu_fallback():
         ops.dense_to_jagged(torch.zeros(2, 3, 1), torch.tensor([0, 1, 3]))
     with pytest.raises(ValueError, match="max_lengths must be an integer"):
         ops.jagged_to_padded_dense(torch.zeros(3, 1), torch.tensor([0, 1, 3]), [3], 0.0)
+    # every functional entry point, including the ones whose body is a library composite
+    from mygenerativerecommenders_b200 import functional as GF
+    from mygenerativerecommenders_b200.optim import FusedAdamW
+    z = torch.zeros(4, 8)
+    off, pos = torch.tensor([0, 4]), torch.tensor([3])
+    for call in (
+        lambda: GF.silu_split(z, [4, 4]),
+        lambda: GF.master_linear(z, torch.zeros(8, 8), None, w_in_out=True),
+        lambda: GF.linear_bias(z, torch.zeros(8, 8), torch.zeros(8)),
+        lambda: GF.l2_normalize(z, 1e-6),
+        lambda: GF.layer_norm_gate(z, None, 1e-6),
+        lambda: GF.embedding_lookup(torch.zeros(5, 8), torch.tensor([1, 2]), 0),
+        lambda: GF.hstu_attention(z, z, z, off, None, None, None, None, 4, 1, 8, 8),
+        lambda: GF.hstu_attention_decode(z[:1], z.view(1, 4, 8), z, off, pos, None, None, None, None, 4, 1, 8, 8),
+        lambda: GF.mips_topk(z, z, None, 2),
+    ):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            call()
+    p = torch.nn.Parameter(torch.zeros(3))
+    p.grad = torch.ones(3)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        FusedAdamW([p]).step()
 
 
 def test_product_never_imports_oracle():
