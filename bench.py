@@ -350,11 +350,13 @@ def run_training(args, world, rank, local):
              "algorithmic_work_per_launch": amount / max(n, 1), "avg_launch_ms": tot_ms / max(n, 1)}
         if name.startswith("hstu_attn"):
             # at the C2 shape a launch is 128 x 4 sequences of <= 211 tokens: 1-2 tiles per CTA, ~6 % of
-            # the executed 128x128 tile area is useful (causal, short), so the launch is bound by per-CTA
-            # latency, not by the tensor pipe.  The long-sequence figure of the same kernel
+            # the executed 128x128 tile area is useful (causal, short) and every tile pays the whole
+            # epilogue, so the launch is bound by epilogue instruction issue, not by the tensor pipe.  The long-sequence figure of the same kernel
             # (benchmarks/kbench.py, profiles/r1_kbench.jsonl) is attached for context.
-            r["note"] = ("C2 sequences are <= 211 tokens (1-2 tiles per CTA, ~6 % useful tile area): "
-                         "per-CTA latency bound at this shape; see long_sequence")
+            r["note"] = ("C2 sequences are <= 211 tokens: every 128x128 tile is a diagonal or ragged tile "
+                         "(~6 % useful area) that still costs a full epilogue pass (10-12 k cycles per tile "
+                         "on the clock64 timeline; a persistent-CTA variant measured no gain, DESIGN.md 4); "
+                         "see long_sequence")
             kb = ROOT / "profiles" / "r1_kbench.jsonl"
             if kb.exists():
                 for ln in kb.read_text().splitlines():
