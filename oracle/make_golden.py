@@ -113,14 +113,15 @@ def golden_bias(R):
 
 
 def _hstu_case(R, name, B, max_seq, out_len, D, H, dqk, dv, blocks, lengths, seed,
-               normalization="rel_bias"):
+               normalization="rel_bias", linear_activation="silu", with_ts=True, **enc_kw):
     hstu = R["hstu"]
     N = max_seq + out_len
     torch.manual_seed(seed)
     enc = hstu.HSTU(max_sequence_len=max_seq, max_output_len=out_len, embedding_dim=D,
                     item_embedding_dim=D, num_blocks=blocks, num_heads=H, linear_dim=dv,
                     attention_dim=dqk, normalization=normalization, linear_config="uvqk",
-                    linear_activation="silu", linear_dropout_rate=0.2, attn_dropout_rate=0.0)
+                    linear_activation=linear_activation, linear_dropout_rate=0.2, attn_dropout_rate=0.0,
+                    **enc_kw)
     enc.eval()
     gen = torch.Generator().manual_seed(seed + 1)
     lengths = torch.tensor(lengths, dtype=torch.int64)
@@ -129,7 +130,7 @@ def _hstu_case(R, name, B, max_seq, out_len, D, H, dqk, dv, blocks, lengths, see
     valid = (torch.arange(N).unsqueeze(0) < lengths.unsqueeze(1)).float().unsqueeze(-1)
     x = (x * valid).requires_grad_(True)
     y, _ = enc(past_lengths=lengths, user_embeddings=x, valid_mask=valid,
-               past_payloads={"timestamps": ts})
+               past_payloads={"timestamps": ts} if with_ts else {})
     w = torch.randn(B, N, D, generator=gen)
     (y * w).sum().backward()
     sd = {k: v.detach().clone() for k, v in enc.state_dict().items() if k != "_attn_mask"}
@@ -152,6 +153,20 @@ def golden_hstu(R):
     # tensor-core shaped heads (dqk = dv = 64), spans more than one 128-row tile
     g.update(_hstu_case(R, "h64", B=3, max_seq=150, out_len=11, D=128, H=2, dqk=64, dv=64,
                         blocks=1, lengths=[161, 130, 5], seed=30))
+    return g
+
+
+def golden_hstu_options(R):
+    """The layer options of SequentialTransductionUnitJagged that no shipped config switches on
+    (hstu.py:304-307 linear_activation="none", :398-402 concat_ua, :586-592 no relative bias)."""
+    g = {}
+    dims = dict(B=5, max_seq=20, out_len=4, D=16, H=2, dqk=8, dv=8, blocks=2, lengths=[1, 24, 7, 13, 2])
+    g.update(_hstu_case(R, "ua", seed=90, concat_ua=True, **dims))
+    g.update(_hstu_case(R, "noact", seed=91, linear_activation="none", **dims))
+    # (without the bias module the reference only runs when no timestamps are passed: hstu.py:191-192)
+    g.update(_hstu_case(R, "norab", seed=92, enable_relative_attention_bias=False, with_ts=False, **dims))
+    g.update(_hstu_case(R, "ua64", B=3, max_seq=150, out_len=11, D=64, H=2, dqk=64, dv=64, blocks=1,
+                        lengths=[161, 130, 5], seed=93, concat_ua=True))
     return g
 
 
@@ -275,7 +290,7 @@ def main():
     OUT.mkdir(parents=True, exist_ok=True)
     only = set(sys.argv[1:])                    # e.g. `make_golden.py hstu_incremental`; default: all
     for name, fn in [("ops", golden_ops), ("bias", golden_bias), ("hstu", golden_hstu),
-                     ("hstu_incremental", golden_hstu_incremental), ("hstu_softmax", golden_hstu_softmax),
+                     ("hstu_incremental", golden_hstu_incremental), ("hstu_softmax", golden_hstu_softmax), ("hstu_options", golden_hstu_options),
                      ("retrieval", golden_retrieval)]:
         if only and name not in only:
             continue

@@ -143,11 +143,11 @@ def test_ln_gate_vs_torch(W, dtype):
     _close(y2, torch.nn.functional.layer_norm(xr.detach(), [W], eps=1e-6), *t, what="ln y")
 
 
-def _build(c, compute_dtype=None, normalization="rel_bias"):
+def _build(c, compute_dtype=None, normalization="rel_bias", linear_activation="silu", **kw):
     enc = hstu.HSTU(max_sequence_len=c["max_seq"], max_output_len=c["out_len"],
                     embedding_dim=c["D"], item_embedding_dim=c["D"], num_blocks=c["blocks"],
                     num_heads=c["H"], linear_dim=c["dv"], attention_dim=c["dqk"],
-                    normalization=normalization, linear_config="uvqk", linear_activation="silu",
+                    normalization=normalization, linear_config="uvqk", linear_activation=linear_activation, **kw,
                     linear_dropout_rate=0.2, attn_dropout_rate=0.0, compute_dtype=compute_dtype)
     enc.load_state_dict(c["sd"], strict=False)
     return enc.to(DEV).eval()
@@ -500,3 +500,30 @@ def test_silu_split_matches_torch(dtype):
     tol = dict(rtol=1e-5, atol=1e-6) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
     torch.testing.assert_close(xa.grad, xb.grad, **tol)
     assert xa.grad[:, sizes[0]:sizes[0] + sizes[1]].abs().max().item() == 0.0
+
+
+# ---------------------------------------------------------------------------------------------
+# layer options no shipped config switches on: concat_ua (hstu.py:398-402),
+# linear_activation="none" (:304-307), no relative attention bias
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,kw,with_ts", [
+    ("ua", dict(concat_ua=True), True), ("ua64", dict(concat_ua=True), True),
+    ("noact", dict(linear_activation="none"), True),
+    ("norab", dict(enable_relative_attention_bias=False), False),
+])
+def test_hstu_layer_options_vs_reference_golden(golden, name, kw, with_ts):
+    c = hstu_case(golden("hstu_options"), name)
+    enc = _build(c, **kw)
+    x = c["x"].to(DEV).requires_grad_(True)
+    y, _ = enc(past_lengths=c["lengths"].to(DEV), user_embeddings=x, valid_mask=None,
+               past_payloads={"timestamps": c["ts"].to(DEV)} if with_ts else {})
+    _close(y, c["y"], 1e-5, what=f"{name} y")
+    (y * c["w"].to(DEV)).sum().backward()
+    _close(x.grad, c["dx"], 2e-4, what=f"{name} dx")
+    for k, p in enc.named_parameters():
+        _close(p.grad, c["grads"][k], 5e-4, what=f"{name} grad {k}")
+    if name == "ua64":      # bf16 / tcgen05 configuration of the same case
+        enc16 = _build(c, compute_dtype=torch.bfloat16, **kw)
+        y16, _ = enc16(past_lengths=c["lengths"].to(DEV), user_embeddings=c["x"].to(DEV), valid_mask=None,
+                       past_payloads={"timestamps": c["ts"].to(DEV)})
+        _close(y16, c["y"], 2e-2, 1e-2, what="ua64 bf16 y")

@@ -139,3 +139,25 @@ def test_hstu_softmax_rel_bias(golden, name):
     assert (x.grad - c["dx"]).abs().max().item() <= 1e-4 * c["dx"].abs().max().item()
     for k, gref in c["grads"].items():
         assert (sd[k].grad - gref).abs().max().item() <= 2e-4 * max(gref.abs().max().item(), 1e-6), k
+
+
+OPTION_CASES = {   # name -> (oracle kwargs, timestamps passed?)
+    "ua": (dict(concat_ua=True), True), "ua64": (dict(concat_ua=True), True),
+    "noact": (dict(linear_activation="none"), True), "norab": ({}, False),
+}
+
+
+@pytest.mark.parametrize("name", sorted(OPTION_CASES))
+def test_hstu_layer_options(golden, name):
+    """concat_ua (hstu.py:398-402), linear_activation="none" (:304-307), no relative bias."""
+    c = hstu_case(golden("hstu_options"), name)
+    kw, with_ts = OPTION_CASES[name]
+    sd = {k: v.clone().requires_grad_(True) for k, v in c["sd"].items()}
+    x = c["x"].clone().requires_grad_(True)
+    y = O.hstu_forward(c["lengths"], x, c["ts"] if with_ts else None, sd, c["blocks"], c["H"], c["dqk"],
+                       c["dv"], **kw)
+    assert (y - c["y"]).abs().max().item() <= 1e-5 * c["y"].abs().max().item()
+    (y * c["w"]).sum().backward()
+    assert (x.grad - c["dx"]).abs().max().item() <= 1e-4 * c["dx"].abs().max().item()
+    for k, gref in c["grads"].items():
+        assert (sd[k].grad - gref).abs().max().item() <= 2e-4 * max(gref.abs().max().item(), 1e-6), k
