@@ -133,3 +133,22 @@ def test_public_api_names():
     assert issubclass(losses.SampledSoftmaxLoss, losses.AutoregressiveLoss)
     assert similarity.DotProductSimilarity().debug_str() == "dp"
     assert candidate_index.CandidateIndex is not None
+
+
+def test_layer_argument_errors_come_before_any_kernel():
+    """Host-side checks of SequentialTransductionUnitJagged.forward (hstu.py:266-423 options): they are
+    raised from Python, before any CUDA call, so they can be checked on CPU tensors."""
+    mk = lambda **kw: hstu.SequentialTransductionUnitJagged(
+        embedding_dim=16, linear_hidden_dim=8, attention_dim=8, dropout_ratio=0.0, attn_dropout_ratio=0.0,
+        num_heads=2, linear_activation="silu", **kw)
+    x, off, mask = torch.zeros(3, 16), torch.tensor([0, 3]), torch.zeros(4, 4)
+    delta = (torch.tensor([2]), torch.tensor([2]))
+    with pytest.raises(ValueError, match="cache"):                     # hstu.py:295 `assert cache is not None`
+        mk()(x, off, None, mask, delta_x_offsets=delta)
+    with pytest.raises(ValueError, match="Unknown normalization"):     # hstu.py:385
+        mk(normalization="nope")(x, off, None, mask)
+    cache = (torch.zeros(3, 16), torch.zeros(1, 4, 16), torch.zeros(1, 4, 16), torch.zeros(3, 16))
+    with pytest.raises(NotImplementedError, match="incremental"):      # the reference raises TypeError, :339
+        mk(normalization="softmax_rel_bias")(x, off, None, mask, delta_x_offsets=delta, cache=cache)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):         # a valid call reaches the kernels
+        mk()(x, off, None, mask)
