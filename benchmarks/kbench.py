@@ -99,6 +99,44 @@ def bench_attn(tag, B, N, H, lengths, bwd=True):
         report(f"hstu_attn_bwd[{tag}]", msb, flop=c["pairs"] * 2 * H * 5 * d)
 
 
+def bench_attn_queued(tag, B, N, H, lengths):
+    """Short shapes: device time per C-ABI call with the host kept ahead of the GPU (the regime
+    inside the captured train step), for the short-sequence kernels and, with GRB_NO_SHORT=1, the
+    long-sequence kernels on the same inputs."""
+    import os
+    from mygenerativerecommenders_b200 import _lib
+    c = attn_case(B, N, H, lengths)
+    H, d = c["H"], c["d"]
+    cache = GF.hstu_bucket_cache(c["off"], c["ts"], c["thr"], c["N"])
+    for mode in ("short", "long"):
+        if mode == "long":
+            os.environ["GRB_NO_SHORT"] = "1"
+        q, k, v = (c[n].clone().requires_grad_(True) for n in ("q", "k", "v"))
+        ts_w, pos_w = c["ts_w"].clone().requires_grad_(True), c["pos_w"].clone().requires_grad_(True)
+
+        def step():
+            out = GF.hstu_attention(q, k, v, c["off"], c["ts"], ts_w, pos_w, c["thr"], c["N"], H, d, d,
+                                    bucket_cache=cache)
+            torch.autograd.grad(out, (q, k, v, ts_w, pos_w), out)
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        _lib.profile_start()
+        n_it = 10
+        torch.cuda._sleep(20_000_000)
+        for _ in range(n_it):
+            step()
+        prof = _lib.profile_stop()
+        os.environ.pop("GRB_NO_SHORT", None)
+        for name, (cnt, tot) in sorted(prof.items()):
+            flop = None
+            if name == "hstu_attn_fwd":
+                flop = c["pairs"] * 2 * H * 2 * d
+            if name == "hstu_attn_bwd":
+                flop = c["pairs"] * 2 * H * 5 * d
+            report(f"{name}[{tag}; {mode} kernels; queued]", tot / cnt, flop=flop, calls=cnt)
+
+
 def bench_jagged():
     B, N, W = 128, 8192, 512
     lengths = torch.randint(1024, N + 1, (B,), generator=torch.Generator().manual_seed(0))
@@ -234,6 +272,11 @@ def main():
     if "attnc2" in which:
         bench_attn("C2 128x U[20,200] N211 H4", 128, 211, 4,
                    torch.randint(20, 201, (128,), generator=torch.Generator().manual_seed(0)))
+    if "attnc2q" in which:
+        bench_attn_queued("C2 128x U[20,200] N211 H4", 128, 211, 4,
+                          torch.randint(20, 201, (128,), generator=torch.Generator().manual_seed(0)))
+        bench_attn_queued("C3 128x U[5,50] N61 H1", 128, 61, 1,
+                          torch.randint(5, 51, (128,), generator=torch.Generator().manual_seed(0)))
     if "attnc5" in which:
         bench_attn("C5-slice 4x8192 H8 full", 4, 8192, 8, [8192] * 4)
     if "attnnobias" in which:

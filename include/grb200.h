@@ -123,6 +123,13 @@ typedef struct grb_hstu_attn_args {
    * launch of a step.  bucket_cache_max_len = the max_len it was built with. */
   const uint8_t* bucket_cache;
   int64_t bucket_cache_max_len;
+  /* optional, short sequences (max_len <= 256): grb_hstu_bias_tiles output for THIS layer's ts_w /
+   * pos_w (fp16 bias/2 with the causal and length masks folded in).  When set (together with
+   * bucket_cache if there are timestamps) the launch takes the short-sequence kernels
+   * (csrc/hstu_attn_short.cu): two CTAs per SM, one CTA per (sequence, head).  Backward with
+   * max_len > 128 also needs dq_accum (T, H*dqk) fp32 as plain scratch (no zero fill). */
+  const void* bias_tiles;
+  int64_t bias_tiles_max_len;
 } grb_hstu_attn_args;
 
 /* Host helper: the integer bucketing table the tcgen05 kernels use, from the ascending threshold
@@ -139,6 +146,16 @@ int64_t grb_hstu_bucket_cache_bytes(int64_t B, int64_t max_len);
 int grb_hstu_bucket_tiles(const void* offsets, int index_bits, const int64_t* timestamps, int64_t B,
                           int64_t N, int64_t max_len, const int64_t* thresholds, int32_t num_buckets,
                           const uint32_t* octaves, void* cache, grb_stream_t stream);
+
+/* Bias tiles of one layer for the short-sequence attention (hstu.py:96-128 evaluated once per
+ * layer instead of once per head and direction): for every causal 128x128 tile of every sequence,
+ * fp16 (pos_w[N-1+j-i] + ts_w[bucket(i,j)]) / 2 in a query-major and a key-major copy, masked pairs
+ * (j > i or i >= n_b) = -15000.  bucket_cache == NULL: no relative bias (masks only).
+ * tiles must hold grb_hstu_bias_tiles_bytes(B, max_len) bytes; max_len <= 256. */
+int64_t grb_hstu_bias_tiles_bytes(int64_t B, int64_t max_len);
+int grb_hstu_bias_tiles(const void* offsets, int index_bits, int64_t B, int64_t N, int64_t max_len,
+                        const uint8_t* bucket_cache, int64_t bucket_cache_max_len, const float* ts_w,
+                        int32_t num_buckets, const float* pos_w, void* tiles, grb_stream_t stream);
 
 int grb_hstu_attn_fwd(const grb_hstu_attn_args* a, grb_stream_t stream);
 int grb_hstu_attn_bwd(const grb_hstu_attn_args* a, grb_stream_t stream);

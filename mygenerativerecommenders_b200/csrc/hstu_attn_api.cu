@@ -13,6 +13,9 @@ int hstu_attn_fwd_sm100(const grb_hstu_attn_args* a, cudaStream_t st);
 bool hstu_attn_fwd2_sm100_usable(const grb_hstu_attn_args* a);
 int hstu_attn_fwd2_sm100(const grb_hstu_attn_args* a, cudaStream_t st);
 int hstu_attn_bwd_sm100(const grb_hstu_attn_args* a, cudaStream_t st);
+bool hstu_attn_short_usable(const grb_hstu_attn_args* a, bool bwd);
+int hstu_attn_short_fwd(const grb_hstu_attn_args* a, cudaStream_t st);
+int hstu_attn_short_bwd(const grb_hstu_attn_args* a, cudaStream_t st);
 
 static bool force_cuda_core() {
   const char* e = std::getenv("GRB_FORCE_CUDA_CORE");
@@ -29,6 +32,12 @@ int grb_hstu_attn_fwd(const grb_hstu_attn_args* a, grb_stream_t stream) {
   if (rc != GRB_OK) return rc;
   GRB_REQUIRE(a->B <= 65535 && a->H <= 65535, GRB_ERR_UNSUPPORTED, "hstu_attn: B,H <= 65535");
   auto st = reinterpret_cast<cudaStream_t>(stream);
+  if (a->bias_tiles) {   // the caller asked for the short-sequence kernels: take them or say why not
+    GRB_REQUIRE(hstu_attn_short_usable(a, false), GRB_ERR_UNSUPPORTED,
+                "hstu_attn_fwd: bias_tiles given but the short-sequence path does not apply (bf16, head "
+                "dims 64, max_len <= 256 = the tiles' max_len, 16-byte aligned rows, bucket_cache with timestamps)");
+    return hstu_attn_short_fwd(a, st);
+  }
   if (!force_cuda_core() && hstu_attn_fwd_sm100_supported(a)) {
     // second-generation kernel when the buckets come from the per-batch cache (or no bias);
     // GRB_FWD_V1=1 keeps the first one (developer switch)
@@ -44,6 +53,13 @@ int grb_hstu_attn_bwd(const grb_hstu_attn_args* a, grb_stream_t stream) {
   if (rc != GRB_OK) return rc;
   GRB_REQUIRE(a->B <= 65535 && a->H <= 65535, GRB_ERR_UNSUPPORTED, "hstu_attn: B,H <= 65535");
   auto st = reinterpret_cast<cudaStream_t>(stream);
+  if (a->bias_tiles) {
+    GRB_REQUIRE(hstu_attn_short_usable(a, true), GRB_ERR_UNSUPPORTED,
+                "hstu_attn_bwd: bias_tiles given but the short-sequence path does not apply (bf16, head "
+                "dims 64, max_len <= 256 = the tiles' max_len, 16-byte aligned rows, bucket_cache with "
+                "timestamps, dq_accum scratch when max_len > 128)");
+    return hstu_attn_short_bwd(a, st);
+  }
   if (!force_cuda_core() && hstu_attn_bwd_sm100_supported(a)) return hstu_attn_bwd_sm100(a, st);
   return hstu_attn_bwd_simt_dispatch(a, st);
 }

@@ -1,0 +1,872 @@
+// hstu_attn_short.cu — HSTU jagged attention for SHORT sequences (n <= 256 tokens: the ml-1m /
+// ml-20m / amazon-books shapes), forward and backward, bf16, head dim 64.
+//
+// Reference math: /root/reference/src/generative_recommenders_pl/models/sequential_encoders/
+// hstu.py:96-128 (bias) + :134-205 (attention) and its backward.
+//
+// Why a second pair of kernels: at these lengths every 128x128 tile is a diagonal or ragged tile,
+// a (sequence, head) is 1-3 tiles of work, and the long-sequence kernels (one CTA per SM: 512 TMEM
+// columns, 224 KiB of shared memory, a pipeline that needs many tiles to fill) spend their time in
+// prologue / load / drain latency: 1.9 % of the tensor peak, 29 % issue-slot utilisation (ncu,
+// profiles/r1_hstu_attn_bwd_sm100_c2shape_ncu.txt).  Here a CTA is small enough that TWO are
+// resident per SM (256 TMEM columns, < 100 KiB of shared memory, 320 threads), so one CTA's
+// epilogue overlaps the other's loads and MMAs, and the per-element work is cut:
+//
+//   * bias tiles: bias/2 = (pos_w[N-1+j-i] + ts_w[bucket(i,j)]) / 2 is tabulated ONCE per layer
+//     and (sequence, tile) as fp16 (grb_hstu_bias_tiles, from the per-batch bucket tiles), in both
+//     orientations, laid out so that a thread fetches 8 consecutive values with one coalesced
+//     16-byte load.  Every head, forward and backward, reads it instead of re-deriving it
+//     (bucket byte -> ts_w lookup -> pos window -> add: ~5 instructions per score element).
+//   * the causal and length masks live IN the bias tile: masked pairs hold -15000, and
+//     tanh.approx saturates to exactly -1 there (benchmarks/probes/tanh_sat_probe.cu: exact for
+//     every x <= -8, f32 and f16x2), so P = h + h tanh(h) and dS = dP (1+t + h (1-t^2)) are exactly
+//     0 without a single compare or select in the epilogue.
+//   * backward: one CTA owns a whole (sequence, head): dQ of a query tile is complete inside the
+//     CTA, so there is no fp32 dQ accumulator to zero, no bulk reduce-add and no conversion pass
+//     (for 128 < n <= 256 the partial dQ of query tile 1 makes one plain fp32 round trip through
+//     the caller's dq_accum scratch, written and read back by the same thread).
+//
+// Work decomposition: CTA = (sequence b, head h); units = causal 128x128 tiles: one for n <= 128,
+// three for n <= 256.  The grid is two phases of B*H CTAs: the first only takes sequences with
+// three units, the second the others, so the heavy items start first.
+#include "hstu_attn_sm100.cuh"
+
+namespace grb {
+
+using namespace ptx;
+
+namespace {
+
+constexpr int SH_THREADS = 320;                 // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int SH_EPI_WARPS = 8;
+constexpr int SH_TILE_SLOT = 65536;             // bias tile slot: 32 KiB per orientation
+constexpr float SH_MASK = -15000.f;             // pre-halved bias of a masked pair
+
+// bounded mbarrier wait: a protocol bug traps (the launch fails with an error) instead of hanging
+// the GPU.  ~2^22 polls of up to ~10 us each is far beyond any legitimate wait here.
+__device__ __forceinline__ void mbar_wait_g(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(20000u)
+        : "memory");
+    if (ok) return;
+    if (spin > (1u << 22)) {
+      printf("grb200 hstu_attn_short: barrier timeout (block %d thread %d bar %u parity %u)\n",
+             (int) blockIdx.x, (int) threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3])
+               : "memory");
+}
+// acc_lo += low bf16 half of `pair`, acc_hi += high half (fp32 accumulate)
+__device__ __forceinline__ void add_bf16_pair(float& acc_lo, float& acc_hi, uint32_t pair) {
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tadd.rn.f32.bf16 %0, lo, %0;\n\t"
+      "add.rn.f32.bf16 %1, hi, %1;\n\t}"
+      : "+f"(acc_lo), "+f"(acc_hi)
+      : "r"(pair));
+}
+
+// ------------------------------------------------------------------------------------------------
+// bias tiles
+// ------------------------------------------------------------------------------------------------
+// Slot t(iq, jk) = iq (iq + 1) / 2 + jk of sequence b (TPS slots per sequence), 64 KiB:
+//   [0, 32K)   Q orientation: fp16 at byte ((c / 8) * 128 + r) * 16 + (c % 8) * 2   r = query row
+//   [32K, 64K) K orientation: fp16 at byte ((r / 8) * 128 + c) * 16 + (r % 8) * 2   c = key row
+// value = 0.5 * (pos_w[N-1+j-i] + ts_w[bucket(i, j)]) for j <= i < n, SH_MASK otherwise.
+template <bool HAS_TS>
+__global__ void __launch_bounds__(256) hstu_bias_tiles_kernel(
+    const void* __restrict__ offsets, int index_bits, int64_t N, int NT,
+    const uint8_t* __restrict__ bcache, int cache_nt, const float* __restrict__ ts_w, int nb,
+    const float* __restrict__ pos_w, uint8_t* __restrict__ tiles) {
+  __shared__ float tsw[256];
+  const int b = blockIdx.y, slot = blockIdx.x;
+  const int iq = slot == 0 ? 0 : 1, jk = slot == 2 ? 1 : 0;     // NT <= 2: slots (0,0) (1,0) (1,1)
+  const int64_t off0 = load_index(offsets, b, index_bits);
+  int64_t n64 = load_index(offsets, b + 1, index_bits) - off0;
+  if (n64 > N) n64 = N;
+  const int n = (int) n64;
+  if (iq * 128 >= n) return;
+  const int tid = threadIdx.x;
+  if (HAS_TS) {
+    tsw[tid] = tid <= nb ? 0.5f * ts_w[tid] : 0.f;
+    __syncthreads();
+  }
+  const int TPS = NT * (NT + 1) / 2;
+  uint8_t* tile = tiles + ((int64_t) b * TPS + slot) * SH_TILE_SLOT;
+  const uint8_t* bkt = nullptr;
+  if (HAS_TS) {
+    const int64_t ctps = (int64_t) cache_nt * (cache_nt + 1) / 2;
+    bkt = bcache + ((int64_t) b * ctps + (int64_t) iq * (iq + 1) / 2 + jk) * 32768;
+  }
+  const int orient = tid >> 7;          // 0: thread = query row, 1: thread = key row
+  const int rr = tid & 127;
+  const __half hmask = __float2half_rn(SH_MASK);
+  for (int ch = 0; ch < 8; ++ch) {      // 16 entries of the other dimension per step
+    uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+    if (HAS_TS) raw = *reinterpret_cast<const uint4*>(bkt + orient * 16384 + ((size_t) ch * 128 + rr) * 16);
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+    __align__(16) __half vals[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const int oth = ch * 16 + e;
+      const int i = iq * 128 + (orient == 0 ? rr : oth);     // query position
+      const int j = jk * 128 + (orient == 0 ? oth : rr);     // key position
+      float v = SH_MASK;
+      if (j <= i && i < n) {
+        v = 0.f;
+        if (HAS_TS) {
+          const int bk = (int) ((w[e >> 2] >> (8 * (e & 3))) & 0xffu);
+          v = 0.5f * pos_w[N - 1 + j - i] + tsw[bk];
+        }
+      }
+      vals[e] = (j <= i && i < n) ? __float2half_rn(v) : hmask;
+    }
+    uint8_t* dst = tile + orient * 32768;
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2)
+      *reinterpret_cast<uint4*>(dst + ((size_t) (ch * 2 + h2) * 128 + rr) * 16) =
+          *reinterpret_cast<const uint4*>(&vals[8 * h2]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+//   warp 0 (TMA) : per unit Q(qt), K(kt), V(kt) 128x64 tiles into a 2-slot ring (128-byte swizzle)
+//   warp 1 (MMA) : S = Q K^T  M128 N128 K64 -> TMEM [0,128) ; O (+)= P V  M128 N64 K128, A = P in
+//                  TMEM [128,192), B = V MN-major -> TMEM [192,256)
+//   warps 2..9   : thread = query row, warpgroup g owns key columns [64g, 64g+64): h = S/2 + bias/2
+//                  (fp16 pairs), P = h + h tanh(h), bf16 P -> TMEM; 16-column blocks that are masked
+//                  for all 32 rows of the warp only write zeros.  O of a finished query tile is read
+//                  back, scaled by 1/N and stored.
+struct ShortFwdParams {
+  int64_t N;
+  int B, H, index_bits, tps;
+  int single_phase;         // max_len <= 128: no 3-unit sequences, grid = B*H
+  const void* offsets;
+  const uint8_t* tiles;
+  __nv_bfloat16* out;
+  int64_t ldo;
+};
+
+struct SfSmem {
+  static constexpr int ring = 0;                                   // 2 x (Q, K, V)
+  static constexpr int bars = ring + 2 * 3 * AT_TILE_BYTES;
+  static constexpr int total = bars + 128;
+};
+
+__global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_fwd_kernel(
+    const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+    const __grid_constant__ CUtensorMap tmV, ShortFwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  using L = SfSmem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int items = p.B * p.H;
+  const int phase = p.single_phase ? 1 : (int) (blockIdx.x / items);
+  const int item = (int) (blockIdx.x % items);
+  const int b = item / p.H, h = item % p.H;
+  const int64_t off0 = load_index(p.offsets, b, p.index_bits);
+  int64_t n64 = load_index(p.offsets, b + 1, p.index_bits) - off0;
+  if (n64 > p.N) n64 = p.N;
+  const int n = (int) n64;
+  if (n <= 0) return;
+  const int nu = n > 128 ? 3 : 1;
+  if ((phase == 0) != (nu == 3)) return;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bars);
+  const uint32_t bar_kv_full = smem_u32(bars + 0);     // [2]
+  const uint32_t bar_slot_free = smem_u32(bars + 2);   // [2]
+  const uint32_t bar_s_full = smem_u32(bars + 4);
+  const uint32_t bar_p_full = smem_u32(bars + 5);
+  const uint32_t bar_o_full = smem_u32(bars + 6);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_kv_full + 8 * s, 1); mbar_init(bar_slot_free + 8 * s, 1); }
+    mbar_init(bar_s_full, 1);
+    mbar_init(bar_p_full, SH_EPI_WARPS);
+    mbar_init(bar_o_full, 1);
+    fence_barrier_init();
+    prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int u = 0; u < nu; ++u) {
+        const int sl = u & 1, qt = u >= 1, kt = u == 2;
+        mbar_wait_g(bar_slot_free + 8 * sl, ((u >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(bar_kv_full + 8 * sl, 3 * AT_TILE_BYTES);
+        const uint32_t dst = smem_u32(smem + L::ring + sl * 3 * AT_TILE_BYTES);
+        tma_load_2d(dst, &tmQ, h * AT_D, (int) (off0 + qt * AT_BM), bar_kv_full + 8 * sl);
+        tma_load_2d(dst + AT_TILE_BYTES, &tmK, h * AT_D, (int) (off0 + kt * AT_BN), bar_kv_full + 8 * sl);
+        tma_load_2d(dst + 2 * AT_TILE_BYTES, &tmV, h * AT_D, (int) (off0 + kt * AT_BN), bar_kv_full + 8 * sl);
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc_qk = make_idesc_bf16(128, AT_BN, false, false);
+    const uint32_t idesc_pv = make_idesc_bf16(128, AT_D, false, true);
+    const uint64_t ring_desc = make_smem_desc_sw128(smem_u32(smem + L::ring), 0, 1024);
+    auto adv = [](uint64_t d, uint32_t bytes) { return d + (uint64_t) (bytes >> 4); };
+    auto issue_qk = [&](int u) {
+      const int sl = u & 1;
+      mbar_wait_g(bar_kv_full + 8 * sl, (u >> 1) & 1);
+      tc_fence_after();
+      const uint64_t q_desc = adv(ring_desc, sl * 3 * AT_TILE_BYTES);
+#pragma unroll
+      for (int ks = 0; ks < AT_D / 16; ++ks)
+        umma_ss_warp(tmem, adv(q_desc, ks * 32), adv(q_desc, AT_TILE_BYTES + ks * 32), idesc_qk, ks > 0);
+      umma_commit_warp(bar_s_full);
+    };
+    issue_qk(0);
+    for (int u = 0; u < nu; ++u) {
+      const int sl = u & 1;
+      mbar_wait_g(bar_p_full, u & 1);                 // P_u written, S read
+      tc_fence_after();
+      const uint64_t v_desc = adv(ring_desc, sl * 3 * AT_TILE_BYTES + 2 * AT_TILE_BYTES);
+#pragma unroll
+      for (int ks = 0; ks < AT_BN / 16; ++ks)
+        umma_ts_warp(tmem + 192, tmem + 128 + ks * 8, adv(v_desc, ks * 2048), idesc_pv, (u == 2) || (ks > 0));
+      umma_commit_warp(bar_slot_free + 8 * sl);
+      if (u + 1 < nu) issue_qk(u + 1);                // its commit also covers P V of unit u
+    }
+    umma_commit_warp(bar_o_full);
+  } else {
+    const int wq = warp & 3;                          // TMEM lane quarter = rows 32 wq .. +31
+    const int g = (warp - 2) >> 2;                    // key columns [64 g, 64 g + 64)
+    const int r = (wq << 5) | lane;
+    const uint32_t lane_base = (uint32_t) (wq * 32) << 16;
+    const uint32_t half_half = 0x38003800u;           // (0.5h, 0.5h)
+    const float inv_n = 1.0f / (float) p.N;
+    auto store_o = [&](int qt) {                      // O of query tile qt -> out rows, 32 columns
+      uint32_t ov[32];
+      tmem_ld32(tmem + lane_base + 192 + 32 * g, ov);
+      tmem_ld_wait();
+      const int i = qt * AT_BM + r;
+      if (i < n) {
+        __nv_bfloat16* dst = p.out + (off0 + i) * p.ldo + h * AT_D + 32 * g;
+#pragma unroll
+        for (int v4 = 0; v4 < 4; ++v4) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 0]) * inv_n, __uint_as_float(ov[v4 * 8 + 1]) * inv_n);
+          o.y = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 2]) * inv_n, __uint_as_float(ov[v4 * 8 + 3]) * inv_n);
+          o.z = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 4]) * inv_n, __uint_as_float(ov[v4 * 8 + 5]) * inv_n);
+          o.w = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 6]) * inv_n, __uint_as_float(ov[v4 * 8 + 7]) * inv_n);
+          *reinterpret_cast<uint4*>(dst + v4 * 8) = o;
+        }
+      }
+    };
+    for (int u = 0; u < nu; ++u) {
+      const int qt = u >= 1, kt = u == 2;
+      const int rows_valid = n - qt * AT_BM;          // > 0
+      const int cols_valid = n - kt * AT_BN;          // > 0 (may exceed 128)
+      const uint8_t* tile = p.tiles + ((int64_t) b * p.tps + u) * SH_TILE_SLOT;   // slot index == u
+      // which of this thread's four 16-column blocks have any unmasked pair in the warp's 32 rows
+      bool live[4];
+      uint4 hb[4][2];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int c0 = 64 * g + 16 * c;
+        live[c] = (32 * wq < rows_valid) && (c0 < cols_valid) && (qt != kt || c0 <= 32 * wq + 31);
+        if (live[c]) {   // bias/2 of columns c0 .. c0+15 of this row: two 16-byte chunks
+          hb[c][0] = ldg_nc_v4(tile + ((size_t) (c0 >> 3) * 128 + r) * 16);
+          hb[c][1] = ldg_nc_v4(tile + ((size_t) ((c0 >> 3) + 1) * 128 + r) * 16);
+        }
+      }
+      mbar_wait_g(bar_s_full, u & 1);
+      tc_fence_after();
+      if (u == 1) store_o(0);                         // s_full(1) also covers P V of unit 0
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int c0 = 64 * g + 16 * c;
+        uint32_t pk[8];
+        if (!live[c]) {
+#pragma unroll
+          for (int w = 0; w < 8; ++w) pk[w] = 0u;
+        } else {
+          uint32_t sv[16];
+          tmem_ld16(tmem + lane_base + c0, sv);
+          tmem_ld_wait();
+          const uint32_t hbw[8] = {hb[c][0].x, hb[c][0].y, hb[c][0].z, hb[c][0].w,
+                                   hb[c][1].x, hb[c][1].y, hb[c][1].z, hb[c][1].w};
+#pragma unroll
+          for (int e2 = 0; e2 < 8; ++e2) {
+            const uint32_t s2 = pack_f16x2(__uint_as_float(sv[2 * e2]), __uint_as_float(sv[2 * e2 + 1]));
+            uint32_t h2, p2;
+            asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(h2) : "r"(s2), "r"(half_half), "r"(hbw[e2]));
+            const uint32_t t2 = tanh_approx_f16x2(h2);
+            asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(p2) : "r"(h2), "r"(t2));
+            const float2 pf = __half22float2(*reinterpret_cast<const __half2*>(&p2));
+            pk[e2] = pack_bf16x2(pf.x, pf.y);
+          }
+        }
+        tmem_st8(tmem + lane_base + 128 + (c0 >> 1), pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p_full);
+    }
+    mbar_wait_g(bar_o_full, 0);
+    tc_fence_after();
+    store_o(nu == 3 ? 1 : 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+// Scores are produced TRANSPOSED (thread = key row), a query tile as two halves of 64 columns:
+//   S^T_hf  = K Q_hf^T   M128 N64 K64 -> TMEM [0,64)      dP^T_hf = V dO_hf^T -> TMEM [64,128)
+//   dV     += P^T_hf dO_hf   (A = bf16 P^T in TMEM, written over the S^T columns its thread owns)
+//   dK     += dS^T_hf Q_hf   (A = dS^T block hf in shared memory, K-major)
+//   dQ      = dS K           (A = both dS^T blocks read MN-major)            -> TMEM [64,128)
+//   dV -> TMEM [128,192), dK -> TMEM [192,256).
+// Units: (kt, qt) = (0,0) [, (0,1), (1,1)].  K/V are loaded once per key tile, Q/dO once per query
+// tile (unit 2 reuses the Q/dO of unit 1).
+struct ShortBwdParams {
+  int64_t N;
+  int B, H, index_bits, tps, nb, cache_nt;
+  int single_phase;
+  const void* offsets;
+  const uint8_t* tiles;
+  const uint8_t* bcache;
+  __nv_bfloat16* dq; int64_t lddq;
+  __nv_bfloat16* dk; int64_t lddk;
+  __nv_bfloat16* dv; int64_t lddv;
+  float* dq_accum;          // (T, H*64) fp32 scratch (no zero fill needed)
+  float* d_ts_w; float* d_pos_w;
+  int d_bias_copies;
+};
+
+struct SbSmem {
+  static constexpr int k = 0;
+  static constexpr int v = k + AT_TILE_BYTES;
+  static constexpr int q = v + AT_TILE_BYTES;
+  static constexpr int dout = q + AT_TILE_BYTES;
+  static constexpr int dsT = dout + AT_TILE_BYTES;                 // blocks A, B: [128 k][64 q] bf16
+  static constexpr int bars = dsT + 2 * AT_TILE_BYTES;
+  static constexpr int total = bars + 128;
+};
+
+template <bool HAS_BIAS>
+__global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_bwd_kernel(
+    const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+    ShortBwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  using L = SbSmem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int items = p.B * p.H;
+  const int phase = p.single_phase ? 1 : (int) (blockIdx.x / items);
+  const int item = (int) (blockIdx.x % items);
+  const int b = item / p.H, h = item % p.H;
+  const int64_t off0 = load_index(p.offsets, b, p.index_bits);
+  int64_t n64 = load_index(p.offsets, b + 1, p.index_bits) - off0;
+  if (n64 > p.N) n64 = p.N;
+  const int n = (int) n64;
+  if (n <= 0) return;
+  const int nu = n > 128 ? 3 : 1;
+  if ((phase == 0) != (nu == 3)) return;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bars);
+  const uint32_t bar_kv_full = smem_u32(bars + 0);
+  const uint32_t bar_qdo_full = smem_u32(bars + 1);
+  const uint32_t bar_s_full = smem_u32(bars + 2);      // [2]
+  const uint32_t bar_half_done = smem_u32(bars + 4);   // [2]
+  const uint32_t bar_pa_free = smem_u32(bars + 6);
+  const uint32_t bar_dq_full = smem_u32(bars + 7);
+  const uint32_t bar_dq_read = smem_u32(bars + 8);
+  const uint32_t bar_dkv_full = smem_u32(bars + 9);
+  const uint32_t bar_dkv_read = smem_u32(bars + 10);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+  if (tid == 0) {
+    mbar_init(bar_kv_full, 1);
+    mbar_init(bar_qdo_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_s_full + 8 * s, 1); mbar_init(bar_half_done + 8 * s, SH_EPI_WARPS); }
+    mbar_init(bar_pa_free, 1);
+    mbar_init(bar_dq_full, 1);
+    mbar_init(bar_dq_read, SH_EPI_WARPS);
+    mbar_init(bar_dkv_full, 1);
+    mbar_init(bar_dkv_read, SH_EPI_WARPS);
+    fence_barrier_init();
+    prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV); prefetch_tensormap(&tmdO);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_kv_full, 2 * AT_TILE_BYTES);
+      tma_load_2d(smem_u32(smem + L::k), &tmK, h * AT_D, (int) off0, bar_kv_full);
+      tma_load_2d(smem_u32(smem + L::v), &tmV, h * AT_D, (int) off0, bar_kv_full);
+      mbar_arrive_expect_tx(bar_qdo_full, 2 * AT_TILE_BYTES);
+      tma_load_2d(smem_u32(smem + L::q), &tmQ, h * AT_D, (int) off0, bar_qdo_full);
+      tma_load_2d(smem_u32(smem + L::dout), &tmdO, h * AT_D, (int) off0, bar_qdo_full);
+      if (nu == 3) {
+        mbar_wait_g(bar_dq_full, 0);                   // every MMA of unit 0 has completed
+        mbar_arrive_expect_tx(bar_qdo_full, 2 * AT_TILE_BYTES);
+        tma_load_2d(smem_u32(smem + L::q), &tmQ, h * AT_D, (int) (off0 + AT_BM), bar_qdo_full);
+        tma_load_2d(smem_u32(smem + L::dout), &tmdO, h * AT_D, (int) (off0 + AT_BM), bar_qdo_full);
+        mbar_wait_g(bar_dq_full, 1);                   // every MMA of unit 1 has completed
+        mbar_arrive_expect_tx(bar_kv_full, 2 * AT_TILE_BYTES);
+        tma_load_2d(smem_u32(smem + L::k), &tmK, h * AT_D, (int) (off0 + AT_BN), bar_kv_full);
+        tma_load_2d(smem_u32(smem + L::v), &tmV, h * AT_D, (int) (off0 + AT_BN), bar_kv_full);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (whole warp, one elected lane issues) =================
+    const uint32_t id_kk = make_idesc_bf16(128, 64, false, false);    // S^T, dP^T halves
+    const uint32_t id_kmn = make_idesc_bf16(128, AT_D, false, true);  // dV, dK
+    const uint32_t id_mnmn = make_idesc_bf16(128, AT_D, true, true);  // dQ
+    const uint64_t k_desc = make_smem_desc_sw128(smem_u32(smem + L::k), 0, 1024);
+    const uint64_t v_desc = make_smem_desc_sw128(smem_u32(smem + L::v), 0, 1024);
+    const uint64_t q_desc = make_smem_desc_sw128(smem_u32(smem + L::q), 0, 1024);
+    const uint64_t o_desc = make_smem_desc_sw128(smem_u32(smem + L::dout), 0, 1024);
+    const uint64_t ds_k_desc = make_smem_desc_sw128(smem_u32(smem + L::dsT), 0, 1024);
+    const uint64_t ds_mn_desc = make_smem_desc_sw128(smem_u32(smem + L::dsT), AT_TILE_BYTES, 1024);
+    auto adv = [](uint64_t d, uint32_t bytes) { return d + (uint64_t) (bytes >> 4); };
+    for (int u = 0; u < nu; ++u) {
+      const bool first_of_kt = (u != 1);
+      const bool last_of_kt = (nu == 1) || (u >= 1);
+      if (u == 0) { mbar_wait_g(bar_kv_full, 0); mbar_wait_g(bar_qdo_full, 0); }
+      if (u == 1) mbar_wait_g(bar_qdo_full, 1);
+      if (u == 2) mbar_wait_g(bar_kv_full, 1);
+      if (u > 0) mbar_wait_g(bar_dq_read, (u - 1) & 1);      // dQ of unit u-1 has left TMEM [64,128)
+      tc_fence_after();
+      // ---- half A scores ----
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        umma_ss_warp(tmem, adv(k_desc, ks * 32), adv(q_desc, ks * 32), id_kk, ks > 0);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        umma_ss_warp(tmem + 64, adv(v_desc, ks * 32), adv(o_desc, ks * 32), id_kk, ks > 0);
+      umma_commit_warp(bar_s_full);
+      mbar_wait_g(bar_half_done, u & 1);
+      if (u == 2) mbar_wait_g(bar_dkv_read, 0);              // dV / dK of key tile 0 have been stored
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)     // dV += P^T_A dO_A : P^T of queries 16 ks .. at TMEM col 32 (ks/2) + 8 (ks%2)
+        umma_ts_warp(tmem + 128, tmem + 32 * (ks >> 1) + 8 * (ks & 1), adv(o_desc, ks * 2048), id_kmn,
+                     !first_of_kt || ks > 0);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)     // dK += dS^T_A Q_A
+        umma_ss_warp(tmem + 192, adv(ds_k_desc, ks * 32), adv(q_desc, ks * 2048), id_kmn,
+                     !first_of_kt || ks > 0);
+      umma_commit_warp(bar_pa_free);
+      // ---- half B scores: dP^T first (its TMEM columns are free), S^T once P^T_A has been consumed ----
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        umma_ss_warp(tmem + 64, adv(v_desc, ks * 32), adv(o_desc, 8192 + ks * 32), id_kk, ks > 0);
+      mbar_wait_g(bar_pa_free, u & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        umma_ss_warp(tmem, adv(k_desc, ks * 32), adv(q_desc, 8192 + ks * 32), id_kk, ks > 0);
+      umma_commit_warp(bar_s_full + 8);
+      mbar_wait_g(bar_half_done + 8, u & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        umma_ts_warp(tmem + 128, tmem + 32 * (ks >> 1) + 8 * (ks & 1), adv(o_desc, (4 + ks) * 2048), id_kmn, true);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        umma_ss_warp(tmem + 192, adv(ds_k_desc, AT_TILE_BYTES + ks * 32), adv(q_desc, (4 + ks) * 2048), id_kmn, true);
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)     // dQ = dS K : A = dS^T (both blocks) MN-major, B = K MN-major
+        umma_ss_warp(tmem + 64, adv(ds_mn_desc, ks * 2048), adv(k_desc, ks * 2048), id_mnmn, ks > 0);
+      umma_commit_warp(bar_dq_full);
+      if (last_of_kt) umma_commit_warp(bar_dkv_full);
+    }
+  } else {
+    // ================= epilogue: thread = key row =================
+    const int wq = warp & 3;
+    const int g = (warp - 2) >> 2;                    // query columns [32 g, 32 g + 32) of each half
+    const int r = (wq << 5) | lane;
+    const uint32_t lane_base = (uint32_t) (wq * 32) << 16;
+    const float inv_n = 1.0f / (float) p.N;
+    const float half_inv_n = 0.5f * inv_n;
+    uint8_t* dsT_row = smem + L::dsT + r * 128;
+    const int64_t copy = blockIdx.x % (unsigned) p.d_bias_copies;
+    float* d_pos_mine = HAS_BIAS ? p.d_pos_w + copy * (2 * p.N - 1) : nullptr;
+    float* d_ts_mine = HAS_BIAS ? p.d_ts_w + copy * (p.nb + 1) : nullptr;
+    const int64_t ctps = (int64_t) p.cache_nt * (p.cache_nt + 1) / 2;
+    auto flush_run = [&](int bk, float val) {
+      if (bk >= 0 && val != 0.f) atomicAdd(d_ts_mine + bk, val * half_inv_n);
+    };
+    int run_bk = -1;
+    float run_acc = 0.f;
+    for (int u = 0; u < nu; ++u) {
+      const int qt = u >= 1, kt = u == 2;
+      const int i0 = qt * AT_BM, j0 = kt * AT_BN;
+      const int jk = j0 + r;
+      const bool last_of_kt = (nu == 1) || (u >= 1);
+      const uint8_t* tile = p.tiles + ((int64_t) b * p.tps + u) * SH_TILE_SLOT + 32768;   // K orientation
+      const uint8_t* bkt = HAS_BIAS ? p.bcache + ((int64_t) b * ctps + u) * 32768 + 16384 : nullptr;
+#pragma unroll 1
+      for (int hf = 0; hf < 2; ++hf) {
+        const int cb = 64 * hf + 32 * g;               // first query column (in the tile) of this thread
+        // prefetch bias/2 (32 fp16) and the bucket bytes (32) of this half before the scores arrive
+        uint4 hbv[4], bq[2];
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8)
+          hbv[c8] = ldg_nc_v4(tile + ((size_t) ((cb >> 3) + c8) * 128 + r) * 16);
+        if (HAS_BIAS) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s)
+            bq[s] = ldg_nc_v4(bkt + ((size_t) ((cb >> 4) + s) * 128 + r) * 16);
+        }
+        mbar_wait_g(bar_s_full + 8 * hf, u & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int sc = 0; sc < 2; ++sc) {               // 16-column sub-chunks
+          const int c16 = cb + 16 * sc;
+          const int tcol = 32 * g + 16 * sc;           // column inside the half's TMEM region
+          // valid columns of this row in the sub-chunk: lo <= e < hi (warp-uniform test: nothing to do?)
+          const int lo = jk - i0 - c16, hi = n - i0 - c16;
+          const bool dead = __all_sync(0xffffffffu, lo >= 16 || hi <= 0 || hi <= lo);
+          float am = 0.f, aw = 0.f, bm = 0.f, bw = 0.f;
+          if (dead) {
+            const uint32_t z4[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int c8 = 0; c8 < 2; ++c8) {
+              tmem_st4(tmem + lane_base + 32 * g + 8 * sc + 4 * c8, z4);
+              *reinterpret_cast<uint4*>(dsT_row + hf * AT_TILE_BYTES + ((4 * g + 2 * sc + c8) ^ (r & 7)) * 16) =
+                  make_uint4(0u, 0u, 0u, 0u);
+            }
+            continue;
+          }
+          uint32_t sv[16], dv_[16];
+          tmem_ld16(tmem + lane_base + tcol, sv);
+          tmem_ld16(tmem + lane_base + 64 + tcol, dv_);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c8 = 0; c8 < 2; ++c8) {
+            const uint4 hq = hbv[2 * sc + c8];
+            const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w};
+            float dsv[8];
+            uint32_t ppk[4], dpk[4];
+#pragma unroll
+            for (int e2 = 0; e2 < 4; ++e2) {
+              const float2 hb2 = __half22float2(*reinterpret_cast<const __half2*>(&hw[e2]));
+              float pv2[2];
+#pragma unroll
+              for (int t = 0; t < 2; ++t) {
+                const int cc = 8 * c8 + 2 * e2 + t;
+                const float hx = fmaf(__uint_as_float(sv[cc]), 0.5f, t ? hb2.y : hb2.x);
+                const float th = tanh_approx(hx);
+                // unscaled: P' = SiLU(x) = N P ; dS' = dP * 2 SiLU'(x) = 2N dS (factors applied at the end)
+                pv2[t] = fmaf(hx, th, hx);
+                const float u1 = fmaf(-th, th, 1.0f);
+                const float w2 = fmaf(hx, u1, 1.0f + th);
+                dsv[2 * e2 + t] = __uint_as_float(dv_[cc]) * w2;
+              }
+              ppk[e2] = pack_bf16x2(pv2[0], pv2[1]);
+              dpk[e2] = pack_bf16x2(dsv[2 * e2], dsv[2 * e2 + 1]);
+            }
+            // P^T: queries c16 + 8 c8 .. +7 of this key row -> TMEM columns 32 g + 8 sc + 4 c8 .. +3
+            tmem_st4(tmem + lane_base + 32 * g + 8 * sc + 4 * c8, ppk);
+            // dS^T: 16-byte chunk (4 g + 2 sc + c8) of this key row, 128-byte swizzle, block hf
+            *reinterpret_cast<uint4*>(dsT_row + hf * AT_TILE_BYTES + ((4 * g + 2 * sc + c8) ^ (r & 7)) * 16) =
+                make_uint4(dpk[0], dpk[1], dpk[2], dpk[3]);
+            if (HAS_BIAS) {
+              // d pos_w: rotate each packed pair to the lane that owns its diagonal
+#pragma unroll
+              for (int k2 = 0; k2 < 4; ++k2) {
+                const int src = lane + 8 * c8 + 2 * k2;
+                const uint32_t got = __shfl_sync(0xffffffffu, dpk[k2], src);
+                if (src < 32) add_bf16_pair(am, bm, got); else add_bf16_pair(aw, bw, got);
+              }
+              // d ts_w: run-length accumulate along the row
+              const uint4 braw = bq[sc];
+              const uint32_t bw2[2] = {c8 ? braw.z : braw.x, c8 ? braw.w : braw.y};
+              const uint32_t cur4 = (uint32_t) (run_bk & 0xff) * 0x01010101u;
+              if (run_bk >= 0 && bw2[0] == cur4 && bw2[1] == cur4) {
+                run_acc += ((dsv[0] + dsv[1]) + (dsv[2] + dsv[3])) + ((dsv[4] + dsv[5]) + (dsv[6] + dsv[7]));
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const int bk = (int) ((bw2[e >> 2] >> (8 * (e & 3))) & 0xffu);
+                  const bool chg = bk != run_bk;
+                  if (chg) flush_run(run_bk, run_acc);
+                  run_acc = (chg ? 0.f : run_acc) + dsv[e];
+                  run_bk = bk;
+                }
+              }
+            }
+          }
+          if (HAS_BIAS) {
+            // diagonal r - c = lane (am, bm -> lane - 1) and lane - 32 (aw, bw -> lane - 33)
+            const float tbm = __shfl_sync(0xffffffffu, bm, lane + 1);
+            const float tbw = __shfl_sync(0xffffffffu, bw, lane + 1);
+            const float tot_m = am + (lane < 31 ? tbm : 0.f);
+            const float tot_w = aw + tbw + (lane == 31 ? tbm : 0.f);
+            const int64_t idx_m = p.N - 1 + j0 - i0 + 32 * wq - c16 + lane;
+            if (tot_m != 0.f && idx_m >= 0 && idx_m < 2 * p.N - 1)
+              atomicAdd(d_pos_mine + idx_m, tot_m * half_inv_n);
+            const int64_t idx_w = idx_m - 32;
+            if (tot_w != 0.f && idx_w >= 0 && idx_w < 2 * p.N - 1)
+              atomicAdd(d_pos_mine + idx_w, tot_w * half_inv_n);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        fence_proxy_async_smem();                  // st.shared -> visible to the MMA (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_half_done + 8 * hf);
+      }
+      // ---- dQ of this unit: thread = query row r of tile qt, columns 32 g .. +31 ----
+      mbar_wait_g(bar_dq_full, u & 1);
+      tc_fence_after();
+      {
+        uint32_t qv[32];
+        tmem_ld32(tmem + lane_base + 64 + 32 * g, qv);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_dq_read);
+        const int i = i0 + r;
+        if (i < n) {
+          float* part = p.dq_accum + (off0 + i) * ((int64_t) p.H * AT_D) + h * AT_D + 32 * g;
+          if (u == 1) {                              // partial of query tile 1 (key tile 0)
+#pragma unroll
+            for (int v4 = 0; v4 < 8; ++v4)
+              *reinterpret_cast<float4*>(part + 4 * v4) =
+                  make_float4(__uint_as_float(qv[4 * v4]), __uint_as_float(qv[4 * v4 + 1]),
+                              __uint_as_float(qv[4 * v4 + 2]), __uint_as_float(qv[4 * v4 + 3]));
+          } else {
+            if (u == 2) {
+#pragma unroll
+              for (int v4 = 0; v4 < 8; ++v4) {
+                const float4 a = *reinterpret_cast<const float4*>(part + 4 * v4);
+                qv[4 * v4] = __float_as_uint(__uint_as_float(qv[4 * v4]) + a.x);
+                qv[4 * v4 + 1] = __float_as_uint(__uint_as_float(qv[4 * v4 + 1]) + a.y);
+                qv[4 * v4 + 2] = __float_as_uint(__uint_as_float(qv[4 * v4 + 2]) + a.z);
+                qv[4 * v4 + 3] = __float_as_uint(__uint_as_float(qv[4 * v4 + 3]) + a.w);
+              }
+            }
+            __nv_bfloat16* dst = p.dq + (off0 + i) * p.lddq + h * AT_D + 32 * g;
+#pragma unroll
+            for (int v4 = 0; v4 < 4; ++v4) {
+              uint4 o;
+              o.x = pack_bf16x2(__uint_as_float(qv[v4 * 8 + 0]) * half_inv_n, __uint_as_float(qv[v4 * 8 + 1]) * half_inv_n);
+              o.y = pack_bf16x2(__uint_as_float(qv[v4 * 8 + 2]) * half_inv_n, __uint_as_float(qv[v4 * 8 + 3]) * half_inv_n);
+              o.z = pack_bf16x2(__uint_as_float(qv[v4 * 8 + 4]) * half_inv_n, __uint_as_float(qv[v4 * 8 + 5]) * half_inv_n);
+              o.w = pack_bf16x2(__uint_as_float(qv[v4 * 8 + 6]) * half_inv_n, __uint_as_float(qv[v4 * 8 + 7]) * half_inv_n);
+              *reinterpret_cast<uint4*>(dst + v4 * 8) = o;
+            }
+          }
+        }
+      }
+      // ---- dV / dK of a finished key tile: thread = key row, columns 32 g .. +31 of each ----
+      if (last_of_kt) {
+        mbar_wait_g(bar_dkv_full, kt);
+        tc_fence_after();
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+          uint32_t ov[32];
+          tmem_ld32(tmem + lane_base + 128 + 64 * which + 32 * g, ov);
+          tmem_ld_wait();
+          const float sc = which == 0 ? inv_n : half_inv_n;   // dV = P'^T dO / N ; dK = dS'^T Q / (2N)
+          if (jk < n) {
+            __nv_bfloat16* dst = (which == 0 ? p.dv + (off0 + jk) * p.lddv : p.dk + (off0 + jk) * p.lddk) +
+                                 h * AT_D + 32 * g;
+#pragma unroll
+            for (int v4 = 0; v4 < 4; ++v4) {
+              uint4 o;
+              o.x = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 0]) * sc, __uint_as_float(ov[v4 * 8 + 1]) * sc);
+              o.y = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 2]) * sc, __uint_as_float(ov[v4 * 8 + 3]) * sc);
+              o.z = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 4]) * sc, __uint_as_float(ov[v4 * 8 + 5]) * sc);
+              o.w = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 6]) * sc, __uint_as_float(ov[v4 * 8 + 7]) * sc);
+              *reinterpret_cast<uint4*>(dst + v4 * 8) = o;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_dkv_read);
+      }
+    }
+    if (HAS_BIAS) {
+      // final runs of the 32 rows of this warp: reduce per distinct bucket across the warp
+      unsigned todo = __ballot_sync(0xffffffffu, run_bk >= 0);
+      while (todo) {
+        const int bsel = __shfl_sync(0xffffffffu, run_bk, __ffs(todo) - 1);
+        const bool mine = run_bk == bsel;
+        const float v = warp_sum(mine ? run_acc : 0.f);
+        if (lane == 0) flush_run(bsel, v);
+        todo &= ~__ballot_sync(0xffffffffu, mine);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+}  // namespace
+
+// ---- host side ------------------------------------------------------------------------------
+// Self-contained: any head count (the long-sequence forward wants an even one).
+bool hstu_attn_short_usable(const grb_hstu_attn_args* a, bool bwd) {
+  if (a->bias_tiles == nullptr || a->max_len > 256 || a->bias_tiles_max_len != a->max_len) return false;
+  if (a->dtype != GRB_BF16 || a->dqk != AT_D || a->dv != AT_D) return false;
+  if (a->timestamps && (a->bucket_cache == nullptr || a->bucket_cache_max_len != a->max_len ||
+                        a->num_buckets > 255))
+    return false;
+  if ((int64_t) a->B * a->H * 2 >= (1ll << 31) || a->T >= (1ll << 31) || a->T == 0) return false;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!al16(a->q) || !al16(a->k) || !al16(a->v) || !al16(a->bias_tiles) || !al16(a->bucket_cache)) return false;
+  if ((a->ldq * 2) % 16 || (a->ldk * 2) % 16 || (a->ldv * 2) % 16) return false;
+  if (!bwd) {
+    if (!al16(a->out) || (a->ldo * 2) % 16) return false;
+  } else {
+    if (!al16(a->dout) || !al16(a->dq) || !al16(a->dk) || !al16(a->dv_grad) || !al16(a->dq_accum)) return false;
+    if ((a->lddo * 2) % 16 || (a->lddq * 2) % 16 || (a->lddk * 2) % 16 || (a->lddv * 2) % 16) return false;
+    if (a->max_len > 128 && a->dq_accum == nullptr) return false;
+  }
+  return true;
+}
+
+int hstu_attn_short_fwd(const grb_hstu_attn_args* a, cudaStream_t st) {
+  if (a->B == 0 || a->max_len == 0) return GRB_OK;
+  CUtensorMap tmQ, tmK, tmV;
+  int rc;
+  const uint64_t W = (uint64_t) a->H * AT_D;
+  if ((rc = make_tmap_bf16_2d(&tmQ, a->q, a->T, W, a->ldq, AT_BM)) != GRB_OK) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmK, a->k, a->T, W, a->ldk, AT_BN)) != GRB_OK) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmV, a->v, a->T, W, a->ldv, AT_BN)) != GRB_OK) return rc;
+  ShortFwdParams p{};
+  p.N = a->N; p.B = (int) a->B; p.H = a->H; p.index_bits = a->index_bits;
+  const int NT = (int) ceil_div(a->max_len, AT_BM);
+  p.tps = NT * (NT + 1) / 2;
+  p.offsets = a->offsets;
+  p.tiles = reinterpret_cast<const uint8_t*>(a->bias_tiles);
+  p.out = reinterpret_cast<__nv_bfloat16*>(a->out); p.ldo = a->ldo;
+  const size_t smem = SfSmem::total + 1024;
+  // two phases of B*H CTAs: the first takes the 3-unit sequences (n > 128) so that the heavy items
+  // start first; with max_len <= 128 there are none and one phase suffices
+  p.single_phase = a->max_len <= 128;
+  auto kern = hstu_attn_short_fwd_kernel;
+  GRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  GRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   (int) cudaSharedmemCarveoutMaxShared));   // two CTAs per SM
+  const unsigned items = (unsigned) (a->B * a->H);
+  kern<<<p.single_phase ? items : 2 * items, SH_THREADS, smem, st>>>(tmQ, tmK, tmV, p);
+  GRB_LAUNCH_OK();
+  return GRB_OK;
+}
+
+int hstu_attn_short_bwd(const grb_hstu_attn_args* a, cudaStream_t st) {
+  if (a->B == 0 || a->max_len == 0) return GRB_OK;
+  CUtensorMap tmQ, tmK, tmV, tmdO;
+  int rc;
+  const uint64_t W = (uint64_t) a->H * AT_D;
+  if ((rc = make_tmap_bf16_2d(&tmQ, a->q, a->T, W, a->ldq, AT_BM)) != GRB_OK) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmK, a->k, a->T, W, a->ldk, AT_BN)) != GRB_OK) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmV, a->v, a->T, W, a->ldv, AT_BN)) != GRB_OK) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmdO, a->dout, a->T, W, a->lddo, AT_BM)) != GRB_OK) return rc;
+  ShortBwdParams p{};
+  p.N = a->N; p.B = (int) a->B; p.H = a->H; p.index_bits = a->index_bits; p.nb = a->num_buckets;
+  const int NT = (int) ceil_div(a->max_len, AT_BM);
+  p.tps = NT * (NT + 1) / 2;
+  p.cache_nt = NT;
+  p.offsets = a->offsets;
+  p.tiles = reinterpret_cast<const uint8_t*>(a->bias_tiles);
+  p.bcache = a->timestamps ? a->bucket_cache : nullptr;
+  p.dq = reinterpret_cast<__nv_bfloat16*>(a->dq); p.lddq = a->lddq;
+  p.dk = reinterpret_cast<__nv_bfloat16*>(a->dk); p.lddk = a->lddk;
+  p.dv = reinterpret_cast<__nv_bfloat16*>(a->dv_grad); p.lddv = a->lddv;
+  p.dq_accum = a->dq_accum; p.d_ts_w = a->d_ts_w; p.d_pos_w = a->d_pos_w;
+  p.d_bias_copies = a->d_bias_copies > 0 ? a->d_bias_copies : 1;
+  const size_t smem = SbSmem::total + 1024;
+  p.single_phase = a->max_len <= 128;
+  const unsigned items = (unsigned) (a->B * a->H) * (p.single_phase ? 1u : 2u);
+  if (a->timestamps) {
+    auto kern = hstu_attn_short_bwd_kernel<true>;
+    GRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    GRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     (int) cudaSharedmemCarveoutMaxShared));
+    kern<<<items, SH_THREADS, smem, st>>>(tmQ, tmK, tmV, tmdO, p);
+  } else {
+    auto kern = hstu_attn_short_bwd_kernel<false>;
+    GRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    GRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     (int) cudaSharedmemCarveoutMaxShared));
+    kern<<<items, SH_THREADS, smem, st>>>(tmQ, tmK, tmV, tmdO, p);
+  }
+  GRB_LAUNCH_OK();
+  return GRB_OK;
+}
+
+}  // namespace grb
+
+using namespace grb;
+
+extern "C" {
+
+int64_t grb_hstu_bias_tiles_bytes(int64_t B, int64_t max_len) {
+  const int64_t NT = (max_len + 127) / 128;
+  return B * (NT * (NT + 1) / 2) * SH_TILE_SLOT;
+}
+
+int grb_hstu_bias_tiles(const void* offsets, int index_bits, int64_t B, int64_t N, int64_t max_len,
+                        const uint8_t* bucket_cache, int64_t bucket_cache_max_len, const float* ts_w,
+                        int32_t num_buckets, const float* pos_w, void* tiles, grb_stream_t stream) {
+  GRB_REQUIRE(index_bits == 32 || index_bits == 64, GRB_ERR_INVALID_ARG,
+              "bias_tiles: index_bits must be 32 or 64");
+  GRB_REQUIRE(offsets && tiles && B >= 0 && N > 0 && max_len >= 0 && max_len <= N, GRB_ERR_INVALID_ARG,
+              "bias_tiles: bad arguments");
+  GRB_REQUIRE(max_len <= 256, GRB_ERR_UNSUPPORTED, "bias_tiles: the short-sequence path takes max_len <= 256");
+  GRB_REQUIRE(B <= 65535, GRB_ERR_UNSUPPORTED, "bias_tiles: B <= 65535");
+  const int NT = (int) ((max_len + 127) / 128);
+  if (B == 0 || NT == 0) return GRB_OK;
+  dim3 grid((unsigned) (NT * (NT + 1) / 2), (unsigned) B);
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  if (bucket_cache) {
+    GRB_REQUIRE(ts_w && pos_w && num_buckets > 0 && num_buckets <= 255, GRB_ERR_INVALID_ARG,
+                "bias_tiles: ts_w / pos_w / num_buckets");
+    GRB_REQUIRE(bucket_cache_max_len == max_len, GRB_ERR_INVALID_ARG,
+                "bias_tiles: the bucket cache was built for another max_len");
+    hstu_bias_tiles_kernel<true><<<grid, 256, 0, st>>>(offsets, index_bits, N, NT, bucket_cache, NT, ts_w,
+                                                       num_buckets, pos_w, reinterpret_cast<uint8_t*>(tiles));
+  } else {
+    hstu_bias_tiles_kernel<false><<<grid, 256, 0, st>>>(offsets, index_bits, N, NT, nullptr, NT, nullptr, 0,
+                                                        nullptr, reinterpret_cast<uint8_t*>(tiles));
+  }
+  GRB_LAUNCH_OK();
+  return GRB_OK;
+}
+
+}

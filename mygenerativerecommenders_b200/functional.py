@@ -33,7 +33,7 @@ def _rows_contiguous(t: torch.Tensor) -> torch.Tensor:
 # fused jagged HSTU attention  (sequential_encoders/hstu.py:96-128 + :134-205)
 # --------------------------------------------------------------------------------------------
 def _attn_args(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk, dv, max_len,
-               cache=None):
+               cache=None, tiles=None):
     a = _lib.HstuAttnArgs()
     a.B = offsets.numel() - 1
     a.N = N
@@ -56,6 +56,9 @@ def _attn_args(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk,
         if cache is not None:
             a.bucket_cache = cache.data_ptr()
             a.bucket_cache_max_len = cache.grb_max_len
+    if tiles is not None:
+        a.bias_tiles = tiles.data_ptr()
+        a.bias_tiles_max_len = max_len
     return a
 
 
@@ -103,6 +106,35 @@ def hstu_bucket_cache(offsets: torch.Tensor, timestamps: torch.Tensor, threshold
     return cache
 
 
+SHORT_MAX_LEN = 256
+
+
+def short_path_applies(q: torch.Tensor, dqk: int, dv: int, max_len: int) -> bool:
+    """The short-sequence tcgen05 kernels (csrc/hstu_attn_short.cu): bf16, 64-wide heads,
+    every sequence <= 256 tokens.  GRB_NO_SHORT=1 keeps the long-sequence kernels (A/B switch)."""
+    import os
+    return (q.dtype == torch.bfloat16 and dqk == 64 and dv == 64 and 0 < max_len <= SHORT_MAX_LEN
+            and os.environ.get("GRB_NO_SHORT") != "1")
+
+
+def hstu_bias_tiles(offsets: torch.Tensor, N: int, max_len: int, cache: Optional[torch.Tensor],
+                    ts_w: Optional[torch.Tensor], pos_w: Optional[torch.Tensor],
+                    num_buckets: int) -> torch.Tensor:
+    """One layer's relative bias (hstu.py:96-128) for every causal 128x128 tile of every sequence,
+    fp16, pre-halved, causal / length masks folded in as -15000 (grb_hstu_bias_tiles).  Built once
+    per layer and step; every head reads it in forward and backward.  ``cache`` None: no bias."""
+    B = offsets.numel() - 1
+    nbytes = int(_lib.lib().grb_hstu_bias_tiles_bytes(B, max_len))
+    tiles = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=offsets.device)
+    with _lib.timed("hstu_bias_tiles"):
+        _lib.check(_lib.lib().grb_hstu_bias_tiles(
+            offsets.data_ptr(), _lib.index_bits(offsets), B, N, max_len,
+            _lib.ptr(cache), cache.grb_max_len if cache is not None else 0,
+            _lib.ptr(ts_w), num_buckets, _lib.ptr(pos_w), tiles.data_ptr(),
+            _lib.stream_ptr(offsets.device)))
+    return tiles
+
+
 class _HstuAttention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk, dv, max_len,
@@ -126,13 +158,21 @@ class _HstuAttention(torch.autograd.Function):
         out = alloc((q.shape[0], H * dv), dtype=q.dtype, device=q.device)
         if cache is not None and (timestamps is None or cache.grb_max_len != max_len):
             cache = None
-        a = _attn_args(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk, dv, max_len, cache)
+        tiles = None
+        if short_path_applies(q, dqk, dv, max_len) and (timestamps is None or thresholds.numel() <= 255):
+            if timestamps is not None and cache is None:
+                cache = hstu_bucket_cache(offsets, timestamps, thresholds, N, max_len)
+            tiles = hstu_bias_tiles(offsets, N, max_len, cache, ts_w, pos_w,
+                                    thresholds.numel() if timestamps is not None else 0)
+        a = _attn_args(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk, dv, max_len, cache,
+                       tiles)
         a.out, a.ldo = out.data_ptr(), H * dv
         with _lib.timed("hstu_attn_fwd"):
             _lib.check(_lib.lib().grb_hstu_attn_fwd(C.byref(a), _lib.stream_ptr(q.device)))
         ctx.save_for_backward(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds)
         ctx.dims = (N, H, dqk, dv, max_len)
         ctx.cache = cache
+        ctx.tiles = tiles
         ctx.rows_padded = rows_padded
         return out
 
@@ -152,21 +192,28 @@ class _HstuAttention(torch.autograd.Function):
             dq = alloc((T, H * dqk), dtype=q.dtype, device=q.device)
             dk = alloc((T, H * dqk), dtype=q.dtype, device=q.device)
             dvv = alloc((T, H * dv), dtype=q.dtype, device=q.device)
-        n_acc = T * H * dqk
+        short = ctx.tiles is not None
+        # long-sequence kernels: fp32 dQ accumulator (zero-filled).  Short kernels: plain scratch for
+        # the partial dQ of the second query tile, only when a sequence can have one.
+        n_acc = T * H * dqk if (not short or max_len > 128) else 0
         copies = n_ts = n_pos = 0
         if timestamps is not None:
             # every CTA adds into d ts_w / d pos_w; with short sequences that is thousands of CTAs
             # on a handful of cache lines.  Give them private copies (<= 256) and sum after.
             copies = max(1, min(256, (4 << 20) // max(1, pos_w.numel())))
             n_ts, n_pos = ts_w.numel(), pos_w.numel()
-        ws = torch.zeros(n_acc + copies * (n_ts + n_pos), dtype=torch.float32, device=q.device)
+        if short:
+            ws = torch.empty(n_acc + copies * (n_ts + n_pos), dtype=torch.float32, device=q.device)
+            ws[n_acc:].zero_()
+        else:
+            ws = torch.zeros(n_acc + copies * (n_ts + n_pos), dtype=torch.float32, device=q.device)
         dq_acc = ws[:n_acc]
         a = _attn_args(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk, dv, max_len,
-                       ctx.cache)
+                       ctx.cache, ctx.tiles)
         a.dout, a.lddo = dout.data_ptr(), _ld(dout)
         a.dq, a.dk, a.dv_grad = dq.data_ptr(), dk.data_ptr(), dvv.data_ptr()
         a.lddq, a.lddk, a.lddv = H * dqk, H * dqk, H * dv
-        a.dq_accum = dq_acc.data_ptr()
+        a.dq_accum = dq_acc.data_ptr() if n_acc else None
         d_ts = d_pos = None
         if timestamps is not None:
             d_ts = ws[n_acc:n_acc + copies * n_ts].view(copies, n_ts)
