@@ -130,6 +130,10 @@ typedef struct grb_hstu_attn_args {
    * max_len > 128 also needs dq_accum (T, H*dqk) fp32 as plain scratch (no zero fill). */
   const void* bias_tiles;
   int64_t bias_tiles_max_len;
+  /* short-sequence backward with timestamps: grb_hstu_bias_tiles_bytes(B, max_len) / 2 bytes,
+   * ZERO-FILLED by the caller: the kernel sums every head's bf16 dS^T tiles into it (bulk
+   * reduce-add) and bins them into d_ts_w / d_pos_w with one small kernel afterwards. */
+  void* dbias_acc;
 } grb_hstu_attn_args;
 
 /* Host helper: the integer bucketing table the tcgen05 kernels use, from the ascending threshold

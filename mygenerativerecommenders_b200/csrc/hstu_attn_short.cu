@@ -43,19 +43,22 @@ constexpr int SH_TILE_SLOT = 65536;             // bias tile slot: 32 KiB per or
 constexpr float SH_MASK = -15000.f;             // pre-halved bias of a masked pair
 
 // bounded mbarrier wait: a protocol bug traps (the launch fails with an error) instead of hanging
-// the GPU.  ~2^22 polls of up to ~10 us each is far beyond any legitimate wait here.
+// the GPU.  Plain try_wait: the hardware suspends the thread until the phase completes or an
+// internal time limit expires, so the loop body runs rarely (the form with a suspend-time hint
+// compiles to a TRYWAIT + NANOSLEEP loop that re-issued every ~80 cycles: 47 % of all executed
+// instructions of the first version of these kernels, ncu).
 __device__ __forceinline__ void mbar_wait_g(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   for (uint32_t spin = 0;; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity), "r"(20000u)
+        : "r"(bar), "r"(parity)
         : "memory");
     if (ok) return;
-    if (spin > (1u << 22)) {
+    if (spin > (1u << 24)) {
       printf("grb200 hstu_attn_short: barrier timeout (block %d thread %d bar %u parity %u)\n",
              (int) blockIdx.x, (int) threadIdx.x, bar, parity);
       __trap();
@@ -63,6 +66,12 @@ __device__ __forceinline__ void mbar_wait_g(uint32_t bar, uint32_t parity) {
   }
 }
 
+// shared -> global element-wise bf16 add of `bytes` (multiple of 16), bulk async-group
+__device__ __forceinline__ void bulk_reduce_add_bf16(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.noftz.bf16 [%0], [%1], %2;" ::"l"(dst),
+               "r"(src_smem), "r"(bytes)
+               : "memory");
+}
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   uint4 v;
   asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -90,59 +99,153 @@ __device__ __forceinline__ void add_bf16_pair(float& acc_lo, float& acc_hi, uint
 //   [0, 32K)   Q orientation: fp16 at byte ((c / 8) * 128 + r) * 16 + (c % 8) * 2   r = query row
 //   [32K, 64K) K orientation: fp16 at byte ((r / 8) * 128 + c) * 16 + (r % 8) * 2   c = key row
 // value = 0.5 * (pos_w[N-1+j-i] + ts_w[bucket(i, j)]) for j <= i < n, SH_MASK otherwise.
+// One CTA of 128 threads per (orientation, slot, sequence): thread = row of its orientation, 128
+// entries each, 8 per 16-byte store.  pos_w (pre-halved, the 255 diagonals of this tile) and ts_w
+// are staged in shared memory; the valid range of a row is an interval, so masking is two compares.
 template <bool HAS_TS>
-__global__ void __launch_bounds__(256) hstu_bias_tiles_kernel(
+__global__ void __launch_bounds__(128) hstu_bias_tiles_kernel(
     const void* __restrict__ offsets, int index_bits, int64_t N, int NT,
     const uint8_t* __restrict__ bcache, int cache_nt, const float* __restrict__ ts_w, int nb,
     const float* __restrict__ pos_w, uint8_t* __restrict__ tiles) {
   __shared__ float tsw[256];
-  const int b = blockIdx.y, slot = blockIdx.x;
+  __shared__ float posd[256];            // posd[x] = 0.5 * pos_w[N-1 + (j0 - i0) + x - 127], x = c_key - r_query + 127
+  const int b = blockIdx.y, slot = blockIdx.x >> 1, orient = blockIdx.x & 1;
   const int iq = slot == 0 ? 0 : 1, jk = slot == 2 ? 1 : 0;     // NT <= 2: slots (0,0) (1,0) (1,1)
   const int64_t off0 = load_index(offsets, b, index_bits);
   int64_t n64 = load_index(offsets, b + 1, index_bits) - off0;
   if (n64 > N) n64 = N;
   const int n = (int) n64;
   if (iq * 128 >= n) return;
-  const int tid = threadIdx.x;
+  const int rr = threadIdx.x;
   if (HAS_TS) {
-    tsw[tid] = tid <= nb ? 0.5f * ts_w[tid] : 0.f;
+    for (int x = rr; x < 256; x += 128) {
+      tsw[x] = x <= nb ? 0.5f * ts_w[x] : 0.f;
+      const int64_t idx = N - 1 + (int64_t) (jk - iq) * 128 + x - 127;
+      posd[x] = (idx >= 0 && idx < 2 * N - 1) ? 0.5f * pos_w[idx] : 0.f;
+    }
     __syncthreads();
   }
   const int TPS = NT * (NT + 1) / 2;
-  uint8_t* tile = tiles + ((int64_t) b * TPS + slot) * SH_TILE_SLOT;
+  uint8_t* dst = tiles + ((int64_t) b * TPS + slot) * SH_TILE_SLOT + orient * 32768;
   const uint8_t* bkt = nullptr;
   if (HAS_TS) {
     const int64_t ctps = (int64_t) cache_nt * (cache_nt + 1) / 2;
-    bkt = bcache + ((int64_t) b * ctps + (int64_t) iq * (iq + 1) / 2 + jk) * 32768;
+    bkt = bcache + ((int64_t) b * ctps + slot) * 32768 + orient * 16384;
   }
-  const int orient = tid >> 7;          // 0: thread = query row, 1: thread = key row
-  const int rr = tid & 127;
-  const __half hmask = __float2half_rn(SH_MASK);
-  for (int ch = 0; ch < 8; ++ch) {      // 16 entries of the other dimension per step
+  // valid entries e (index along the other dimension) of this row: lo <= e < hi
+  //   orient 0 (row = query i = i0 + rr): keys j = j0 + e <= i, i < n
+  //   orient 1 (row = key   j = j0 + rr): queries i = i0 + e >= j, i < n
+  const int i0 = iq * 128, j0 = jk * 128;
+  int lo, hi;
+  if (orient == 0) { lo = 0; hi = (i0 + rr < n) ? (i0 + rr - j0 + 1) : 0; }
+  else { lo = j0 + rr - i0; hi = n - i0; }
+  lo = lo < 0 ? 0 : lo;
+  hi = hi > 128 ? 128 : hi;
+  // diagonal index x = c_key - r_query + 127: orient 0: e - rr + 127 ; orient 1: rr - e + 127
+  const int xs = orient == 0 ? 1 : -1;
+  const int x0 = orient == 0 ? 127 - rr : 127 + rr;
+  const uint32_t hmask = 0xF353u;                    // fp16(-15000)
+#pragma unroll 2
+  for (int ch = 0; ch < 8; ++ch) {      // 16 entries per step
     uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-    if (HAS_TS) raw = *reinterpret_cast<const uint4*>(bkt + orient * 16384 + ((size_t) ch * 128 + rr) * 16);
+    if (HAS_TS) raw = *reinterpret_cast<const uint4*>(bkt + ((size_t) ch * 128 + rr) * 16);
     const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-    __align__(16) __half vals[16];
+    uint32_t outw[8];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      const int oth = ch * 16 + e;
-      const int i = iq * 128 + (orient == 0 ? rr : oth);     // query position
-      const int j = jk * 128 + (orient == 0 ? oth : rr);     // key position
-      float v = SH_MASK;
-      if (j <= i && i < n) {
-        v = 0.f;
+    for (int e2 = 0; e2 < 8; ++e2) {
+      uint32_t pair = 0u;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int e = ch * 16 + 2 * e2 + t;
+        float v = 0.f;
         if (HAS_TS) {
-          const int bk = (int) ((w[e >> 2] >> (8 * (e & 3))) & 0xffu);
-          v = 0.5f * pos_w[N - 1 + j - i] + tsw[bk];
+          const uint32_t bk = (w[(2 * e2 + t) >> 2] >> (8 * ((2 * e2 + t) & 3))) & 0xffu;
+          v = posd[x0 + xs * e] + tsw[bk];
         }
+        const uint32_t hv = (e >= lo && e < hi) ? (uint32_t) __half_as_ushort(__float2half_rn(v)) : hmask;
+        pair |= hv << (16 * t);
       }
-      vals[e] = (j <= i && i < n) ? __float2half_rn(v) : hmask;
+      outw[e2] = pair;
     }
-    uint8_t* dst = tile + orient * 32768;
+    *reinterpret_cast<uint4*>(dst + ((size_t) (ch * 2) * 128 + rr) * 16) = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+    *reinterpret_cast<uint4*>(dst + ((size_t) (ch * 2 + 1) * 128 + rr) * 16) = make_uint4(outw[4], outw[5], outw[6], outw[7]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bias gradients from the head-summed dS^T tiles
+// ------------------------------------------------------------------------------------------------
+// The backward kernel adds every (sequence, head)'s bf16 dS'^T blocks into one accumulation tile per
+// (sequence, tile) with a bulk reduce-add (the block is already in shared memory as an MMA operand:
+// no epilogue instruction is spent on it).  This kernel then bins each tile once:
+//   d pos_w[N-1+j-i] += sum along the diagonals ; d ts_w[bucket(i,j)] += run-length sums along the
+// key rows (the bucket is a step function of the query position for a fixed key).
+// Tile layout (what the backward wrote): [hf 0..1][key row 128][64 queries] bf16, 16-byte chunk c of
+// a row stored at chunk c ^ (row & 7).
+__device__ __forceinline__ void red_add_f32_pred(float* addr, float v, bool p) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q red.global.add.f32 [%0], %1;\n\t}" ::"l"(addr),
+               "f"(v), "r"((int) p)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(256) hstu_bias_grad_kernel(
+    const void* __restrict__ offsets, int index_bits, int64_t N, int NT, const uint8_t* __restrict__ bcache,
+    const uint8_t* __restrict__ dbias, int nb, float* __restrict__ d_ts_w, float* __restrict__ d_pos_w,
+    int copies, float scale) {
+  constexpr int PITCH = 130;                                  // bf16 elements per staged row
+  __shared__ __align__(16) __nv_bfloat16 tile[128 * PITCH];
+  const int b = blockIdx.y, slot = blockIdx.x;
+  const int iq = slot == 0 ? 0 : 1, jk = slot == 2 ? 1 : 0;
+  const int64_t off0 = load_index(offsets, b, index_bits);
+  int64_t n64 = load_index(offsets, b + 1, index_bits) - off0;
+  if (n64 > N) n64 = N;
+  const int n = (int) n64;
+  if (iq * 128 >= n) return;
+  const int tid = threadIdx.x;
+  const int TPS = NT * (NT + 1) / 2;
+  const uint8_t* src = dbias + ((int64_t) b * TPS + slot) * 32768;
+  // stage the tile un-swizzled: smem[key row][query 0..127]
+  for (int g = tid; g < 2048; g += 256) {
+    const int hf = g >> 10, row = (g >> 3) & 127, pos = g & 7;
+    const int chunk = pos ^ (row & 7);
+    const uint4 v = *reinterpret_cast<const uint4*>(src + (size_t) g * 16);
+    uint32_t* d = reinterpret_cast<uint32_t*>(tile + row * PITCH + hf * 64 + chunk * 8);
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  __syncthreads();
+  const int64_t copy = (blockIdx.x + gridDim.x * blockIdx.y) % (unsigned) copies;
+  float* d_pos_mine = d_pos_w + copy * (2 * N - 1);
+  float* d_ts_mine = d_ts_w + copy * (nb + 1);
+  // diagonals: thread t sums x = c - r + 127 = t  (c = query column, r = key row)
+  if (tid < 255) {
+    float acc = 0.f;
+    const int rlo = tid < 127 ? 127 - tid : 0, rhi = tid < 127 ? 128 : 255 - tid;
+    for (int r = rlo; r < rhi; ++r) acc += __bfloat162float(tile[r * PITCH + (tid - 127 + r)]);
+    // pos_w index N-1 + j - i = N-1 + (j0 + r) - (i0 + c) = N-1 + j0 - i0 - (tid - 127)
+    const int64_t idx = N - 1 + (int64_t) (jk - iq) * 128 - (tid - 127);
+    if (acc != 0.f && idx >= 0 && idx < 2 * N - 1) atomicAdd(d_pos_mine + idx, acc * scale);
+  }
+  // time buckets: thread = key row, walk the query columns
+  if (tid < 128) {
+    const int64_t ctps = (int64_t) NT * (NT + 1) / 2;
+    const uint8_t* bkt = bcache + ((int64_t) b * ctps + slot) * 32768 + 16384;   // K orientation
+    int run_bk = -1;
+    float run_acc = 0.f;
+#pragma unroll 1
+    for (int ch = 0; ch < 8; ++ch) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(bkt + ((size_t) ch * 128 + tid) * 16);
+      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-    for (int h2 = 0; h2 < 2; ++h2)
-      *reinterpret_cast<uint4*>(dst + ((size_t) (ch * 2 + h2) * 128 + rr) * 16) =
-          *reinterpret_cast<const uint4*>(&vals[8 * h2]);
+      for (int e = 0; e < 16; ++e) {
+        const int bk = (int) ((w[e >> 2] >> (8 * (e & 3))) & 0xffu);
+        const float v = __bfloat162float(tile[tid * PITCH + ch * 16 + e]);
+        const bool chg = bk != run_bk;
+        red_add_f32_pred(d_ts_mine + (run_bk < 0 ? 0 : run_bk), run_acc * scale, chg && run_bk >= 0 && run_acc != 0.f);
+        run_acc = (chg ? 0.f : run_acc) + v;
+        run_bk = bk;
+      }
+    }
+    red_add_f32_pred(d_ts_mine + (run_bk < 0 ? 0 : run_bk), run_acc * scale, run_bk >= 0 && run_acc != 0.f);
   }
 }
 
@@ -360,8 +463,7 @@ struct ShortBwdParams {
   __nv_bfloat16* dk; int64_t lddk;
   __nv_bfloat16* dv; int64_t lddv;
   float* dq_accum;          // (T, H*64) fp32 scratch (no zero fill needed)
-  float* d_ts_w; float* d_pos_w;
-  int d_bias_copies;
+  uint8_t* dbias;           // (B, tps, 32 KiB) bf16 head-summed dS'^T tiles, zero-filled by the caller
 };
 
 struct SbSmem {
@@ -464,6 +566,8 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_bwd_kernel(
       if (u == 1) mbar_wait_g(bar_qdo_full, 1);
       if (u == 2) mbar_wait_g(bar_kv_full, 1);
       if (u > 0) mbar_wait_g(bar_dq_read, (u - 1) & 1);      // dQ of unit u-1 has left TMEM [64,128)
+      if (HAS_BIAS && u > 0 && lane == 0) bulk_wait_group_read0();   // the dS^T blocks have been read
+      __syncwarp();
       tc_fence_after();
       // ---- half A scores ----
 #pragma unroll
@@ -476,6 +580,12 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_bwd_kernel(
       mbar_wait_g(bar_half_done, u & 1);
       if (u == 2) mbar_wait_g(bar_dkv_read, 0);              // dV / dK of key tile 0 have been stored
       tc_fence_after();
+      if (HAS_BIAS && lane == 0) {   // head-summed dS'^T for the bias gradients: block A -> global, bf16 add
+        bulk_reduce_add_bf16(p.dbias + (((int64_t) b * p.tps + u) * 2 + 0) * AT_TILE_BYTES,
+                             smem_u32(smem + L::dsT), AT_TILE_BYTES);
+        bulk_commit_group();
+      }
+      __syncwarp();
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)     // dV += P^T_A dO_A : P^T of queries 16 ks .. at TMEM col 32 (ks/2) + 8 (ks%2)
         umma_ts_warp(tmem + 128, tmem + 32 * (ks >> 1) + 8 * (ks & 1), adv(o_desc, ks * 2048), id_kmn,
@@ -497,6 +607,12 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_bwd_kernel(
       umma_commit_warp(bar_s_full + 8);
       mbar_wait_g(bar_half_done + 8, u & 1);
       tc_fence_after();
+      if (HAS_BIAS && lane == 0) {
+        bulk_reduce_add_bf16(p.dbias + (((int64_t) b * p.tps + u) * 2 + 1) * AT_TILE_BYTES,
+                             smem_u32(smem + L::dsT) + AT_TILE_BYTES, AT_TILE_BYTES);
+        bulk_commit_group();
+      }
+      __syncwarp();
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)
         umma_ts_warp(tmem + 128, tmem + 32 * (ks >> 1) + 8 * (ks & 1), adv(o_desc, (4 + ks) * 2048), id_kmn, true);
@@ -509,6 +625,8 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_bwd_kernel(
       umma_commit_warp(bar_dq_full);
       if (last_of_kt) umma_commit_warp(bar_dkv_full);
     }
+    if (HAS_BIAS && lane == 0) bulk_wait_group0();          // shared memory must outlive the reduces
+    __syncwarp();
   } else {
     // ================= epilogue: thread = key row =================
     const int wq = warp & 3;
@@ -518,35 +636,20 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_bwd_kernel(
     const float inv_n = 1.0f / (float) p.N;
     const float half_inv_n = 0.5f * inv_n;
     uint8_t* dsT_row = smem + L::dsT + r * 128;
-    const int64_t copy = blockIdx.x % (unsigned) p.d_bias_copies;
-    float* d_pos_mine = HAS_BIAS ? p.d_pos_w + copy * (2 * p.N - 1) : nullptr;
-    float* d_ts_mine = HAS_BIAS ? p.d_ts_w + copy * (p.nb + 1) : nullptr;
-    const int64_t ctps = (int64_t) p.cache_nt * (p.cache_nt + 1) / 2;
-    auto flush_run = [&](int bk, float val) {
-      if (bk >= 0 && val != 0.f) atomicAdd(d_ts_mine + bk, val * half_inv_n);
-    };
-    int run_bk = -1;
-    float run_acc = 0.f;
     for (int u = 0; u < nu; ++u) {
       const int qt = u >= 1, kt = u == 2;
       const int i0 = qt * AT_BM, j0 = kt * AT_BN;
       const int jk = j0 + r;
       const bool last_of_kt = (nu == 1) || (u >= 1);
       const uint8_t* tile = p.tiles + ((int64_t) b * p.tps + u) * SH_TILE_SLOT + 32768;   // K orientation
-      const uint8_t* bkt = HAS_BIAS ? p.bcache + ((int64_t) b * ctps + u) * 32768 + 16384 : nullptr;
 #pragma unroll 1
       for (int hf = 0; hf < 2; ++hf) {
         const int cb = 64 * hf + 32 * g;               // first query column (in the tile) of this thread
-        // prefetch bias/2 (32 fp16) and the bucket bytes (32) of this half before the scores arrive
-        uint4 hbv[4], bq[2];
+        // prefetch bias/2 (32 fp16) of this half before the scores arrive
+        uint4 hbv[4];
 #pragma unroll
         for (int c8 = 0; c8 < 4; ++c8)
           hbv[c8] = ldg_nc_v4(tile + ((size_t) ((cb >> 3) + c8) * 128 + r) * 16);
-        if (HAS_BIAS) {
-#pragma unroll
-          for (int s = 0; s < 2; ++s)
-            bq[s] = ldg_nc_v4(bkt + ((size_t) ((cb >> 4) + s) * 128 + r) * 16);
-        }
         mbar_wait_g(bar_s_full + 8 * hf, u & 1);
         tc_fence_after();
 #pragma unroll
@@ -556,7 +659,6 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_bwd_kernel(
           // valid columns of this row in the sub-chunk: lo <= e < hi (warp-uniform test: nothing to do?)
           const int lo = jk - i0 - c16, hi = n - i0 - c16;
           const bool dead = __all_sync(0xffffffffu, lo >= 16 || hi <= 0 || hi <= lo);
-          float am = 0.f, aw = 0.f, bm = 0.f, bw = 0.f;
           if (dead) {
             const uint32_t z4[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
@@ -600,44 +702,6 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_bwd_kernel(
             // dS^T: 16-byte chunk (4 g + 2 sc + c8) of this key row, 128-byte swizzle, block hf
             *reinterpret_cast<uint4*>(dsT_row + hf * AT_TILE_BYTES + ((4 * g + 2 * sc + c8) ^ (r & 7)) * 16) =
                 make_uint4(dpk[0], dpk[1], dpk[2], dpk[3]);
-            if (HAS_BIAS) {
-              // d pos_w: rotate each packed pair to the lane that owns its diagonal
-#pragma unroll
-              for (int k2 = 0; k2 < 4; ++k2) {
-                const int src = lane + 8 * c8 + 2 * k2;
-                const uint32_t got = __shfl_sync(0xffffffffu, dpk[k2], src);
-                if (src < 32) add_bf16_pair(am, bm, got); else add_bf16_pair(aw, bw, got);
-              }
-              // d ts_w: run-length accumulate along the row
-              const uint4 braw = bq[sc];
-              const uint32_t bw2[2] = {c8 ? braw.z : braw.x, c8 ? braw.w : braw.y};
-              const uint32_t cur4 = (uint32_t) (run_bk & 0xff) * 0x01010101u;
-              if (run_bk >= 0 && bw2[0] == cur4 && bw2[1] == cur4) {
-                run_acc += ((dsv[0] + dsv[1]) + (dsv[2] + dsv[3])) + ((dsv[4] + dsv[5]) + (dsv[6] + dsv[7]));
-              } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const int bk = (int) ((bw2[e >> 2] >> (8 * (e & 3))) & 0xffu);
-                  const bool chg = bk != run_bk;
-                  if (chg) flush_run(run_bk, run_acc);
-                  run_acc = (chg ? 0.f : run_acc) + dsv[e];
-                  run_bk = bk;
-                }
-              }
-            }
-          }
-          if (HAS_BIAS) {
-            // diagonal r - c = lane (am, bm -> lane - 1) and lane - 32 (aw, bw -> lane - 33)
-            const float tbm = __shfl_sync(0xffffffffu, bm, lane + 1);
-            const float tbw = __shfl_sync(0xffffffffu, bw, lane + 1);
-            const float tot_m = am + (lane < 31 ? tbm : 0.f);
-            const float tot_w = aw + tbw + (lane == 31 ? tbm : 0.f);
-            const int64_t idx_m = p.N - 1 + j0 - i0 + 32 * wq - c16 + lane;
-            if (tot_m != 0.f && idx_m >= 0 && idx_m < 2 * p.N - 1)
-              atomicAdd(d_pos_mine + idx_m, tot_m * half_inv_n);
-            const int64_t idx_w = idx_m - 32;
-            if (tot_w != 0.f && idx_w >= 0 && idx_w < 2 * p.N - 1)
-              atomicAdd(d_pos_mine + idx_w, tot_w * half_inv_n);
           }
         }
         tmem_st_wait();
@@ -718,17 +782,6 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_bwd_kernel(
         if (lane == 0) mbar_arrive(bar_dkv_read);
       }
     }
-    if (HAS_BIAS) {
-      // final runs of the 32 rows of this warp: reduce per distinct bucket across the warp
-      unsigned todo = __ballot_sync(0xffffffffu, run_bk >= 0);
-      while (todo) {
-        const int bsel = __shfl_sync(0xffffffffu, run_bk, __ffs(todo) - 1);
-        const bool mine = run_bk == bsel;
-        const float v = warp_sum(mine ? run_acc : 0.f);
-        if (lane == 0) flush_run(bsel, v);
-        todo &= ~__ballot_sync(0xffffffffu, mine);
-      }
-    }
   }
   tc_fence_before();
   __syncthreads();
@@ -755,6 +808,7 @@ bool hstu_attn_short_usable(const grb_hstu_attn_args* a, bool bwd) {
     if (!al16(a->dout) || !al16(a->dq) || !al16(a->dk) || !al16(a->dv_grad) || !al16(a->dq_accum)) return false;
     if ((a->lddo * 2) % 16 || (a->lddq * 2) % 16 || (a->lddk * 2) % 16 || (a->lddv * 2) % 16) return false;
     if (a->max_len > 128 && a->dq_accum == nullptr) return false;
+    if (a->timestamps && (a->dbias_acc == nullptr || !al16(a->dbias_acc))) return false;
   }
   return true;
 }
@@ -808,8 +862,8 @@ int hstu_attn_short_bwd(const grb_hstu_attn_args* a, cudaStream_t st) {
   p.dq = reinterpret_cast<__nv_bfloat16*>(a->dq); p.lddq = a->lddq;
   p.dk = reinterpret_cast<__nv_bfloat16*>(a->dk); p.lddk = a->lddk;
   p.dv = reinterpret_cast<__nv_bfloat16*>(a->dv_grad); p.lddv = a->lddv;
-  p.dq_accum = a->dq_accum; p.d_ts_w = a->d_ts_w; p.d_pos_w = a->d_pos_w;
-  p.d_bias_copies = a->d_bias_copies > 0 ? a->d_bias_copies : 1;
+  p.dq_accum = a->dq_accum;
+  p.dbias = reinterpret_cast<uint8_t*>(a->dbias_acc);
   const size_t smem = SbSmem::total + 1024;
   p.single_phase = a->max_len <= 128;
   const unsigned items = (unsigned) (a->B * a->H) * (p.single_phase ? 1u : 2u);
@@ -819,6 +873,13 @@ int hstu_attn_short_bwd(const grb_hstu_attn_args* a, cudaStream_t st) {
     GRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      (int) cudaSharedmemCarveoutMaxShared));
     kern<<<items, SH_THREADS, smem, st>>>(tmQ, tmK, tmV, tmdO, p);
+    GRB_LAUNCH_OK();
+    // bias gradients from the head-summed dS'^T tiles (dS' = 2N dS)
+    const int copies = a->d_bias_copies > 0 ? a->d_bias_copies : 1;
+    dim3 grid((unsigned) p.tps, (unsigned) a->B);
+    hstu_bias_grad_kernel<<<grid, 256, 0, st>>>(a->offsets, a->index_bits, a->N, NT, a->bucket_cache, p.dbias,
+                                                a->num_buckets, a->d_ts_w, a->d_pos_w, copies,
+                                                0.5f / (float) a->N);
   } else {
     auto kern = hstu_attn_short_bwd_kernel<false>;
     GRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
@@ -852,17 +913,17 @@ int grb_hstu_bias_tiles(const void* offsets, int index_bits, int64_t B, int64_t 
   GRB_REQUIRE(B <= 65535, GRB_ERR_UNSUPPORTED, "bias_tiles: B <= 65535");
   const int NT = (int) ((max_len + 127) / 128);
   if (B == 0 || NT == 0) return GRB_OK;
-  dim3 grid((unsigned) (NT * (NT + 1) / 2), (unsigned) B);
+  dim3 grid((unsigned) (NT * (NT + 1)), (unsigned) B);   // (slot, orientation) x sequence
   auto st = reinterpret_cast<cudaStream_t>(stream);
   if (bucket_cache) {
     GRB_REQUIRE(ts_w && pos_w && num_buckets > 0 && num_buckets <= 255, GRB_ERR_INVALID_ARG,
                 "bias_tiles: ts_w / pos_w / num_buckets");
     GRB_REQUIRE(bucket_cache_max_len == max_len, GRB_ERR_INVALID_ARG,
                 "bias_tiles: the bucket cache was built for another max_len");
-    hstu_bias_tiles_kernel<true><<<grid, 256, 0, st>>>(offsets, index_bits, N, NT, bucket_cache, NT, ts_w,
+    hstu_bias_tiles_kernel<true><<<grid, 128, 0, st>>>(offsets, index_bits, N, NT, bucket_cache, NT, ts_w,
                                                        num_buckets, pos_w, reinterpret_cast<uint8_t*>(tiles));
   } else {
-    hstu_bias_tiles_kernel<false><<<grid, 256, 0, st>>>(offsets, index_bits, N, NT, nullptr, NT, nullptr, 0,
+    hstu_bias_tiles_kernel<false><<<grid, 128, 0, st>>>(offsets, index_bits, N, NT, nullptr, NT, nullptr, 0,
                                                         nullptr, reinterpret_cast<uint8_t*>(tiles));
   }
   GRB_LAUNCH_OK();

@@ -214,6 +214,12 @@ class _HstuAttention(torch.autograd.Function):
         a.dq, a.dk, a.dv_grad = dq.data_ptr(), dk.data_ptr(), dvv.data_ptr()
         a.lddq, a.lddk, a.lddv = H * dqk, H * dqk, H * dv
         a.dq_accum = dq_acc.data_ptr() if n_acc else None
+        dbias = None
+        if short and timestamps is not None:
+            # head-summed bf16 dS^T tiles (bulk reduce-add target), binned into d ts_w / d pos_w by a
+            # small kernel inside the same C-ABI call
+            dbias = torch.zeros(ctx.tiles.numel() // 2, dtype=torch.uint8, device=q.device)
+            a.dbias_acc = dbias.data_ptr()
         d_ts = d_pos = None
         if timestamps is not None:
             d_ts = ws[n_acc:n_acc + copies * n_ts].view(copies, n_ts)
