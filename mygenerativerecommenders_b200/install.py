@@ -51,9 +51,21 @@ def install_ops() -> None:
 
 
 def install_modules() -> None:
+    import sys
     for mod_name, mapping in _MODULE_MAP.items():
         for attr, cls in mapping.items():
             _rebind(mod_name, attr, cls)
+    # modules that did ``from ... import InBatchNegativesSampler`` before this call hold their own
+    # binding (models/retrieval.py:104 isinstance-checks against it): rebind those too, without
+    # importing them (they pull in lightning / hydra)
+    flat = {attr: cls for mapping in _MODULE_MAP.values() for attr, cls in mapping.items()}
+    for name in (f"{_REF}.retrieval", f"{_REF}.ranking", f"{_REF}.generative_recommenders"):
+        mod = sys.modules.get(name)
+        if mod is None:
+            continue
+        for attr, cls in flat.items():
+            if hasattr(mod, attr):
+                _rebind(name, attr, cls)
 
 
 def install() -> None:

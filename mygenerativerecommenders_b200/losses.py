@@ -66,7 +66,9 @@ class SampledSoftmaxLoss(AutoregressiveLoss):
         if (_is_plain_dot(similarity) and output_embeddings.is_cuda
                 and output_embeddings.dtype == torch.float32 and output_embeddings.dim() == 2
                 and output_embeddings.size(1) <= 256 and supervision_ids.size(0) > 1):
-            fused = negatives_sampler.fused_sample(supervision_ids, self._num_to_sample)
+                # a reference sampler (no fused_sample) paired with this loss takes the composite below
+            fused_sample = getattr(negatives_sampler, "fused_sample", None)
+            fused = fused_sample(supervision_ids, self._num_to_sample) if fused_sample is not None else None
             if fused is not None and fused.table0.dtype != torch.float32:
                 raise NotImplementedError("fused sampled softmax needs float32 tables")
         positive_embeddings = negatives_sampler.normalize_embeddings(supervision_embeddings)

@@ -25,9 +25,24 @@ class FusedNegatives(NamedTuple):
     zero_grad_rows: Tuple[Optional[int], Optional[int]]  # padding_idx rows of table0 / table1
 
 
-class NegativesSampler(torch.nn.Module):
+def _reference_bases():
+    """The reference's own sampler classes when its package is importable.  The reference trainer
+    decides how to feed a sampler with ``isinstance(self.negatives_sampler, InBatchNegativesSampler)``
+    against ITS class (models/retrieval.py:104); deriving from it keeps that check true when these
+    classes are selected through the ``_target_`` override configs."""
+    try:
+        from generative_recommenders_pl.models.negatives_samples import negative_sampler as ref
+        return ref.NegativesSampler, ref.LocalNegativesSampler, ref.InBatchNegativesSampler
+    except Exception:       # no reference checkout on the path (the GPU box): plain modules
+        return torch.nn.Module, None, None
+
+
+_RefBase, _RefLocal, _RefInBatch = _reference_bases()
+
+
+class NegativesSampler(_RefBase):
     def __init__(self, l2_norm: bool, l2_norm_eps: float) -> None:
-        super().__init__()
+        torch.nn.Module.__init__(self)      # not the reference's __init__ chain: same attributes below
         self._l2_norm: bool = l2_norm
         self._l2_norm_eps: float = l2_norm_eps
 
@@ -59,12 +74,12 @@ class NegativesSampler(torch.nn.Module):
         return None
 
 
-class LocalNegativesSampler(NegativesSampler):
+class LocalNegativesSampler(*((NegativesSampler, _RefLocal) if _RefLocal else (NegativesSampler,))):
     """Uniform sampling with replacement over ``all_item_ids`` (positives included)."""
 
     def __init__(self, l2_norm: bool, l2_norm_eps: float, num_items: int = None,
                  all_item_ids: List[int] = None) -> None:
-        super().__init__(l2_norm=l2_norm, l2_norm_eps=l2_norm_eps)
+        NegativesSampler.__init__(self, l2_norm=l2_norm, l2_norm_eps=l2_norm_eps)
         if all_item_ids is None and num_items is None:
             raise ValueError("Either num_items or all_item_ids must be provided")
         elif all_item_ids and num_items and num_items != len(all_item_ids):
@@ -125,11 +140,11 @@ class LocalNegativesSampler(NegativesSampler):
         return None
 
 
-class InBatchNegativesSampler(NegativesSampler):
+class InBatchNegativesSampler(*((NegativesSampler, _RefInBatch) if _RefInBatch else (NegativesSampler,))):
     """Uniform sampling over the ids present in the current batch (optionally de-duplicated)."""
 
     def __init__(self, l2_norm: bool, l2_norm_eps: float, dedup_embeddings: bool) -> None:
-        super().__init__(l2_norm=l2_norm, l2_norm_eps=l2_norm_eps)
+        NegativesSampler.__init__(self, l2_norm=l2_norm, l2_norm_eps=l2_norm_eps)
         self._dedup_embeddings: bool = dedup_embeddings
 
     def debug_str(self) -> str:
@@ -236,7 +251,7 @@ class InBatchNegativesSampler(NegativesSampler):
             # same Philox stream (ATen folds the range into the draw on the host side).
             raw = torch.randint(low=0, high=2 ** 62, size=size, dtype=torch.int64,
                                 device=positive_ids.device)
-            return (raw % self._cached_count).to(positive_ids.dtype)
+            return (raw % self._cached_count.clamp(min=1)).to(positive_ids.dtype)
         return torch.randint(low=0, high=self._cached_ids.size(0), size=size,
                              dtype=positive_ids.dtype, device=positive_ids.device)
 

@@ -103,8 +103,12 @@ def test_short_kernels_agree_with_the_long_sequence_kernels(N, H, lengths, monke
     monkeypatch.delenv("GRB_NO_SHORT")
     # same bf16 inputs, same fp16 SiLU in the forward; the bias is rounded to fp16 here
     _close(out_s, out_l, 8e-3, 2e-3, "fwd short vs long")
-    for name, a, b_ in zip(("dq", "dk", "dv", "d_ts_w", "d_pos_w"), leaves_s, leaves_l):
+    for name, a, b_ in zip(("dq", "dk", "dv"), leaves_s, leaves_l):
         _close(a.grad, b_.grad, 1e-2, 5e-3, f"{name} short vs long")
+    # bias gradients: the short path sums the heads' bf16 dS in bf16 before binning, the long path
+    # bins bf16 dS per head in fp32; both are checked against the fp64 oracle at 2e-2 above
+    for name, a, b_ in zip(("d_ts_w", "d_pos_w"), leaves_s[3:], leaves_l[3:]):
+        _close(a.grad, b_.grad, 2e-2, 1e-2, f"{name} short vs long")
 
 
 def test_short_kernels_are_deterministic_in_q_k_v_and_stable_under_repeats():

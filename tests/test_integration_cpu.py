@@ -121,3 +121,29 @@ def test_sharded_topk_merge_world_size_2_gloo(tmp_path):
     mp.spawn(_merge_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     a, b = torch.load(tmp_path / "merged_0.pt"), torch.load(tmp_path / "merged_1.pt")
     assert torch.equal(a, b)  # every rank ends with the same merged top-k
+
+
+def test_samplers_pass_the_reference_trainers_isinstance_check():
+    """models/retrieval.py:104 picks process_batch vs. the late-bound embeddings module with
+    isinstance(..., InBatchNegativesSampler) against the REFERENCE class; the drop-in samplers
+    derive from the reference classes whenever its package is importable."""
+    import importlib
+    import sys
+    ref_src = "/root/reference/src"
+    import os
+    if not os.path.isdir(ref_src):
+        pytest.skip("no reference checkout in this environment")
+    sys.path.insert(0, ref_src)
+    try:
+        ref = importlib.import_module("generative_recommenders_pl.models.negatives_samples.negative_sampler")
+        import mygenerativerecommenders_b200.negative_sampler as ours
+        ours = importlib.reload(ours)        # pick up the reference bases now that it is importable
+        ib = ours.InBatchNegativesSampler(l2_norm=True, l2_norm_eps=1e-6, dedup_embeddings=True)
+        lo = ours.LocalNegativesSampler(l2_norm=True, l2_norm_eps=1e-6, all_item_ids=[1, 2, 3])
+        assert isinstance(ib, ref.InBatchNegativesSampler) and isinstance(ib, ref.NegativesSampler)
+        assert isinstance(lo, ref.LocalNegativesSampler) and not isinstance(lo, ref.InBatchNegativesSampler)
+        assert ib._dedup_embeddings and lo._num_items == 3 and hasattr(ib, "fused_sample")
+    finally:
+        sys.path.remove(ref_src)
+        import mygenerativerecommenders_b200.negative_sampler as ours2
+        importlib.reload(ours2)
