@@ -30,6 +30,8 @@
 // three for n <= 256.  The grid is two phases of B*H CTAs: the first only takes sequences with
 // three units, the second the others, so the heavy items start first.
 #include "hstu_attn_sm100.cuh"
+#include <cstdlib>
+#include <cstdio>
 
 namespace grb {
 
@@ -41,6 +43,15 @@ constexpr int SH_THREADS = 320;                 // warp 0 TMA, warp 1 MMA, warps
 constexpr int SH_EPI_WARPS = 8;
 constexpr int SH_TILE_SLOT = 65536;             // bias tile slot: 32 KiB per orientation
 constexpr float SH_MASK = -15000.f;             // pre-halved bias of a masked pair
+
+// developer probe: globaltimer stamps (ns) of the first SH_TL_CTAS CTAs that do work, 32 slots each
+constexpr int SH_TL_CTAS = 64, SH_TL_SLOTS = 32;
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define SH_STAMP(cond, slot) do { if (p.tl && (cond) && tl_id < SH_TL_CTAS) p.tl[tl_id * SH_TL_SLOTS + (slot)] = gtime(); } while (0)
 
 // bounded mbarrier wait: a protocol bug traps (the launch fails with an error) instead of hanging
 // the GPU.  Plain try_wait: the hardware suspends the thread until the phase completes or an
@@ -250,21 +261,85 @@ __global__ void __launch_bounds__(256) hstu_bias_grad_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------
+// work items
+// ------------------------------------------------------------------------------------------------
+// Both kernels are PERSISTENT: the grid is two CTAs per SM and every CTA walks a list of
+// (sequence, head) items.  (A first version launched one CTA per item: launching 1 024 CTAs of
+// 100 KiB / 320 threads took 8 us of the forward's 23 us before the last ones even started,
+// profiles/r2_short_attn_timeline_v1.txt.)  The item order comes from a per-batch schedule written
+// behind the bias tiles (hstu_short_schedule_kernel): sequences of three units first, then those of
+// one; CTA c takes items c, 2G-1-c, 2G+c, ... (snake order), so the heavy items are spread evenly.
+struct ItemIter {
+  int r, G, c, n_items;
+  __device__ ItemIter(int G_, int c_, int n_items_) : r(-1), G(G_), c(c_), n_items(n_items_) {}
+  __device__ int next() {
+    for (;;) {
+      ++r;
+      if ((int64_t) r * G >= n_items) return -1;
+      const int idx = r * G + ((r & 1) ? G - 1 - c : c);
+      if (idx < n_items) return idx;
+    }
+  }
+};
+
+struct Item { int seq, h, n, nu; int64_t off0; };
+
+__device__ __forceinline__ Item decode_item(int idx, int H, const int* __restrict__ order,
+                                            const void* __restrict__ offsets, int index_bits, int64_t N) {
+  Item it;
+  it.seq = order[idx / H];
+  it.h = idx % H;
+  it.off0 = load_index(offsets, it.seq, index_bits);
+  int64_t n64 = load_index(offsets, it.seq + 1, index_bits) - it.off0;
+  if (n64 > N) n64 = N;
+  it.n = (int) n64;
+  it.nu = it.n > 128 ? 3 : 1;
+  return it;
+}
+
+// sched[0] = sequences with n > 0, sched[1] = of those with n > 128, sched[2 ..] = their indices,
+// the n > 128 ones first.  One CTA.
+__global__ void __launch_bounds__(1024) hstu_short_schedule_kernel(const void* __restrict__ offsets,
+                                                                   int index_bits, int B, int64_t N,
+                                                                   int* __restrict__ sched) {
+  __shared__ int n_heavy, n_light, c_heavy, c_light;
+  if (threadIdx.x == 0) { n_heavy = 0; n_light = 0; c_heavy = 0; c_light = 0; }
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    int64_t n = load_index(offsets, b + 1, index_bits) - load_index(offsets, b, index_bits);
+    if (n > N) n = N;
+    if (n > 128) atomicAdd(&n_heavy, 1);
+    else if (n > 0) atomicAdd(&n_light, 1);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    int64_t n = load_index(offsets, b + 1, index_bits) - load_index(offsets, b, index_bits);
+    if (n > N) n = N;
+    if (n > 128) sched[2 + atomicAdd(&c_heavy, 1)] = b;
+    else if (n > 0) sched[2 + n_heavy + atomicAdd(&c_light, 1)] = b;
+  }
+  if (threadIdx.x == 0) { sched[0] = n_heavy + n_light; sched[1] = n_heavy; }
+}
+
+// ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-//   warp 0 (TMA) : per unit Q(qt), K(kt), V(kt) 128x64 tiles into a 2-slot ring (128-byte swizzle)
+//   warp 0 (TMA) : per unit Q(qt), K(kt), V(kt) 128x64 tiles into a 2-slot ring (128-byte swizzle);
+//                  runs ahead across items, so the next item's tiles arrive during this one's math
 //   warp 1 (MMA) : S = Q K^T  M128 N128 K64 -> TMEM [0,128) ; O (+)= P V  M128 N64 K128, A = P in
 //                  TMEM [128,192), B = V MN-major -> TMEM [192,256)
 //   warps 2..9   : thread = query row, warpgroup g owns key columns [64g, 64g+64): h = S/2 + bias/2
 //                  (fp16 pairs), P = h + h tanh(h), bf16 P -> TMEM; 16-column blocks that are masked
 //                  for all 32 rows of the warp only write zeros.  O of a finished query tile is read
-//                  back, scaled by 1/N and stored.
+//                  back at the start of the next unit (its scores' commit covers the last P V),
+//                  scaled by 1/N and stored.
 struct ShortFwdParams {
   int64_t N;
   int B, H, index_bits, tps;
-  int single_phase;         // max_len <= 128: no 3-unit sequences, grid = B*H
+  long long* tl;            // developer probe (GRB_SHORT_TIMELINE=1)
   const void* offsets;
   const uint8_t* tiles;
+  const int* sched;
   __nv_bfloat16* out;
   int64_t ldo;
 };
@@ -282,17 +357,12 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_fwd_kernel(
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   using L = SfSmem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int items = p.B * p.H;
-  const int phase = p.single_phase ? 1 : (int) (blockIdx.x / items);
-  const int item = (int) (blockIdx.x % items);
-  const int b = item / p.H, h = item % p.H;
-  const int64_t off0 = load_index(p.offsets, b, p.index_bits);
-  int64_t n64 = load_index(p.offsets, b + 1, p.index_bits) - off0;
-  if (n64 > p.N) n64 = p.N;
-  const int n = (int) n64;
-  if (n <= 0) return;
-  const int nu = n > 128 ? 3 : 1;
-  if ((phase == 0) != (nu == 3)) return;
+  const int n_items = p.sched[0] * p.H;
+  const int G = (int) gridDim.x, cta = (int) blockIdx.x;
+  if (cta >= n_items) return;
+  const int* order = p.sched + 2;
+  const int tl_id = cta < SH_TL_CTAS ? cta : 1 << 20;
+  SH_STAMP(tid == 0, 0);
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bars);
   const uint32_t bar_kv_full = smem_u32(bars + 0);     // [2]
@@ -317,25 +387,32 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_fwd_kernel(
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
+    // ================= TMA producer =================
     if (lane == 0) {
-      for (int u = 0; u < nu; ++u) {
-        const int sl = u & 1, qt = u >= 1, kt = u == 2;
-        mbar_wait_g(bar_slot_free + 8 * sl, ((u >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(bar_kv_full + 8 * sl, 3 * AT_TILE_BYTES);
-        const uint32_t dst = smem_u32(smem + L::ring + sl * 3 * AT_TILE_BYTES);
-        tma_load_2d(dst, &tmQ, h * AT_D, (int) (off0 + qt * AT_BM), bar_kv_full + 8 * sl);
-        tma_load_2d(dst + AT_TILE_BYTES, &tmK, h * AT_D, (int) (off0 + kt * AT_BN), bar_kv_full + 8 * sl);
-        tma_load_2d(dst + 2 * AT_TILE_BYTES, &tmV, h * AT_D, (int) (off0 + kt * AT_BN), bar_kv_full + 8 * sl);
+      ItemIter iter(G, cta, n_items);
+      uint32_t gu = 0;
+      for (int idx = iter.next(); idx >= 0; idx = iter.next()) {
+        const Item it = decode_item(idx, p.H, order, p.offsets, p.index_bits, p.N);
+        for (int u = 0; u < it.nu; ++u, ++gu) {
+          const int sl = gu & 1, qt = u >= 1, kt = u == 2;
+          mbar_wait_g(bar_slot_free + 8 * sl, ((gu >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(bar_kv_full + 8 * sl, 3 * AT_TILE_BYTES);
+          const uint32_t dst = smem_u32(smem + L::ring + sl * 3 * AT_TILE_BYTES);
+          tma_load_2d(dst, &tmQ, it.h * AT_D, (int) (it.off0 + qt * AT_BM), bar_kv_full + 8 * sl);
+          tma_load_2d(dst + AT_TILE_BYTES, &tmK, it.h * AT_D, (int) (it.off0 + kt * AT_BN), bar_kv_full + 8 * sl);
+          tma_load_2d(dst + 2 * AT_TILE_BYTES, &tmV, it.h * AT_D, (int) (it.off0 + kt * AT_BN), bar_kv_full + 8 * sl);
+        }
       }
     }
   } else if (warp == 1) {
+    // ================= MMA issuer (whole warp, one elected lane issues) =================
     const uint32_t idesc_qk = make_idesc_bf16(128, AT_BN, false, false);
     const uint32_t idesc_pv = make_idesc_bf16(128, AT_D, false, true);
     const uint64_t ring_desc = make_smem_desc_sw128(smem_u32(smem + L::ring), 0, 1024);
     auto adv = [](uint64_t d, uint32_t bytes) { return d + (uint64_t) (bytes >> 4); };
-    auto issue_qk = [&](int u) {
-      const int sl = u & 1;
-      mbar_wait_g(bar_kv_full + 8 * sl, (u >> 1) & 1);
+    auto issue_qk = [&](uint32_t gu) {
+      const int sl = gu & 1;
+      mbar_wait_g(bar_kv_full + 8 * sl, (gu >> 1) & 1);
       tc_fence_after();
       const uint64_t q_desc = adv(ring_desc, sl * 3 * AT_TILE_BYTES);
 #pragma unroll
@@ -343,33 +420,48 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_fwd_kernel(
         umma_ss_warp(tmem, adv(q_desc, ks * 32), adv(q_desc, AT_TILE_BYTES + ks * 32), idesc_qk, ks > 0);
       umma_commit_warp(bar_s_full);
     };
+    ItemIter iter(G, cta, n_items);
+    int idx = iter.next();
+    int nu = decode_item(idx, p.H, order, p.offsets, p.index_bits, p.N).nu;
+    int u = 0;
+    uint32_t gu = 0;
     issue_qk(0);
-    for (int u = 0; u < nu; ++u) {
-      const int sl = u & 1;
-      mbar_wait_g(bar_p_full, u & 1);                 // P_u written, S read
+    for (;;) {
+      const int sl = gu & 1;
+      mbar_wait_g(bar_p_full, gu & 1);                // P of this unit written, S read
       tc_fence_after();
       const uint64_t v_desc = adv(ring_desc, sl * 3 * AT_TILE_BYTES + 2 * AT_TILE_BYTES);
 #pragma unroll
       for (int ks = 0; ks < AT_BN / 16; ++ks)
         umma_ts_warp(tmem + 192, tmem + 128 + ks * 8, adv(v_desc, ks * 2048), idesc_pv, (u == 2) || (ks > 0));
       umma_commit_warp(bar_slot_free + 8 * sl);
-      if (u + 1 < nu) issue_qk(u + 1);                // its commit also covers P V of unit u
+      if (++u == nu) {
+        idx = iter.next();
+        if (idx < 0) break;
+        nu = decode_item(idx, p.H, order, p.offsets, p.index_bits, p.N).nu;
+        u = 0;
+      }
+      ++gu;
+      issue_qk(gu);                                   // its commit also covers the P V just issued
     }
     umma_commit_warp(bar_o_full);
   } else {
+    // ================= epilogue =================
     const int wq = warp & 3;                          // TMEM lane quarter = rows 32 wq .. +31
     const int g = (warp - 2) >> 2;                    // key columns [64 g, 64 g + 64)
     const int r = (wq << 5) | lane;
     const uint32_t lane_base = (uint32_t) (wq * 32) << 16;
     const uint32_t half_half = 0x38003800u;           // (0.5h, 0.5h)
     const float inv_n = 1.0f / (float) p.N;
-    auto store_o = [&](int qt) {                      // O of query tile qt -> out rows, 32 columns
+    // O of a finished query tile, stored at the start of the next unit
+    bool pend = false;
+    int pend_valid = 0;
+    __nv_bfloat16* pend_dst = nullptr;
+    auto store_o = [&]() {
       uint32_t ov[32];
       tmem_ld32(tmem + lane_base + 192 + 32 * g, ov);
       tmem_ld_wait();
-      const int i = qt * AT_BM + r;
-      if (i < n) {
-        __nv_bfloat16* dst = p.out + (off0 + i) * p.ldo + h * AT_D + 32 * g;
+      if (r < pend_valid) {
 #pragma unroll
         for (int v4 = 0; v4 < 4; ++v4) {
           uint4 o;
@@ -377,64 +469,78 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_fwd_kernel(
           o.y = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 2]) * inv_n, __uint_as_float(ov[v4 * 8 + 3]) * inv_n);
           o.z = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 4]) * inv_n, __uint_as_float(ov[v4 * 8 + 5]) * inv_n);
           o.w = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 6]) * inv_n, __uint_as_float(ov[v4 * 8 + 7]) * inv_n);
-          *reinterpret_cast<uint4*>(dst + v4 * 8) = o;
+          *reinterpret_cast<uint4*>(pend_dst + v4 * 8) = o;
         }
       }
+      pend = false;
     };
-    for (int u = 0; u < nu; ++u) {
-      const int qt = u >= 1, kt = u == 2;
-      const int rows_valid = n - qt * AT_BM;          // > 0
-      const int cols_valid = n - kt * AT_BN;          // > 0 (may exceed 128)
-      const uint8_t* tile = p.tiles + ((int64_t) b * p.tps + u) * SH_TILE_SLOT;   // slot index == u
-      // which of this thread's four 16-column blocks have any unmasked pair in the warp's 32 rows
-      bool live[4];
-      uint4 hb[4][2];
+    ItemIter iter(G, cta, n_items);
+    uint32_t gu = 0;
+    int k_item = 0;
+    for (int idx = iter.next(); idx >= 0; idx = iter.next(), ++k_item) {
+      const Item it = decode_item(idx, p.H, order, p.offsets, p.index_bits, p.N);
+      SH_STAMP(tid == 64 && k_item < 7, 1 + 2 * k_item);
+      for (int u = 0; u < it.nu; ++u, ++gu) {
+        const int qt = u >= 1, kt = u == 2;
+        const int rows_valid = it.n - qt * AT_BM;        // > 0
+        const int cols_valid = it.n - kt * AT_BN;        // > 0 (may exceed 128)
+        const uint8_t* tile = p.tiles + ((int64_t) it.seq * p.tps + u) * SH_TILE_SLOT;   // slot index == u
+        // which of this thread's four 16-column blocks have any unmasked pair in the warp's 32 rows
+        bool live[4];
+        uint4 hb[4][2];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int c0 = 64 * g + 16 * c;
-        live[c] = (32 * wq < rows_valid) && (c0 < cols_valid) && (qt != kt || c0 <= 32 * wq + 31);
-        if (live[c]) {   // bias/2 of columns c0 .. c0+15 of this row: two 16-byte chunks
-          hb[c][0] = ldg_nc_v4(tile + ((size_t) (c0 >> 3) * 128 + r) * 16);
-          hb[c][1] = ldg_nc_v4(tile + ((size_t) ((c0 >> 3) + 1) * 128 + r) * 16);
-        }
-      }
-      mbar_wait_g(bar_s_full, u & 1);
-      tc_fence_after();
-      if (u == 1) store_o(0);                         // s_full(1) also covers P V of unit 0
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int c0 = 64 * g + 16 * c;
-        uint32_t pk[8];
-        if (!live[c]) {
-#pragma unroll
-          for (int w = 0; w < 8; ++w) pk[w] = 0u;
-        } else {
-          uint32_t sv[16];
-          tmem_ld16(tmem + lane_base + c0, sv);
-          tmem_ld_wait();
-          const uint32_t hbw[8] = {hb[c][0].x, hb[c][0].y, hb[c][0].z, hb[c][0].w,
-                                   hb[c][1].x, hb[c][1].y, hb[c][1].z, hb[c][1].w};
-#pragma unroll
-          for (int e2 = 0; e2 < 8; ++e2) {
-            const uint32_t s2 = pack_f16x2(__uint_as_float(sv[2 * e2]), __uint_as_float(sv[2 * e2 + 1]));
-            uint32_t h2, p2;
-            asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(h2) : "r"(s2), "r"(half_half), "r"(hbw[e2]));
-            const uint32_t t2 = tanh_approx_f16x2(h2);
-            asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(p2) : "r"(h2), "r"(t2));
-            const float2 pf = __half22float2(*reinterpret_cast<const __half2*>(&p2));
-            pk[e2] = pack_bf16x2(pf.x, pf.y);
+        for (int c = 0; c < 4; ++c) {
+          const int c0 = 64 * g + 16 * c;
+          live[c] = (32 * wq < rows_valid) && (c0 < cols_valid) && (qt != kt || c0 <= 32 * wq + 31);
+          if (live[c]) {   // bias/2 of columns c0 .. c0+15 of this row: two 16-byte chunks
+            hb[c][0] = ldg_nc_v4(tile + ((size_t) (c0 >> 3) * 128 + r) * 16);
+            hb[c][1] = ldg_nc_v4(tile + ((size_t) ((c0 >> 3) + 1) * 128 + r) * 16);
           }
         }
-        tmem_st8(tmem + lane_base + 128 + (c0 >> 1), pk);
+        mbar_wait_g(bar_s_full, gu & 1);
+        tc_fence_after();
+        if (pend) store_o();                            // this commit also covers the previous P V
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int c0 = 64 * g + 16 * c;
+          uint32_t pk[8];
+          if (!live[c]) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) pk[w] = 0u;
+          } else {
+            uint32_t sv[16];
+            tmem_ld16(tmem + lane_base + c0, sv);
+            tmem_ld_wait();
+            const uint32_t hbw[8] = {hb[c][0].x, hb[c][0].y, hb[c][0].z, hb[c][0].w,
+                                     hb[c][1].x, hb[c][1].y, hb[c][1].z, hb[c][1].w};
+#pragma unroll
+            for (int e2 = 0; e2 < 8; ++e2) {
+              const uint32_t s2 = pack_f16x2(__uint_as_float(sv[2 * e2]), __uint_as_float(sv[2 * e2 + 1]));
+              uint32_t h2, p2;
+              asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(h2) : "r"(s2), "r"(half_half), "r"(hbw[e2]));
+              const uint32_t t2 = tanh_approx_f16x2(h2);
+              asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(p2) : "r"(h2), "r"(t2));
+              const float2 pf = __half22float2(*reinterpret_cast<const __half2*>(&p2));
+              pk[e2] = pack_bf16x2(pf.x, pf.y);
+            }
+          }
+          tmem_st8(tmem + lane_base + 128 + (c0 >> 1), pk);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p_full);
+        if (u == 0 || u == 2) {                         // last unit of its query tile
+          pend = true;
+          pend_valid = rows_valid;
+          pend_dst = p.out + (it.off0 + qt * AT_BM + r) * p.ldo + it.h * AT_D + 32 * g;
+        }
       }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_p_full);
+      SH_STAMP(tid == 64 && k_item < 7, 2 + 2 * k_item);
     }
     mbar_wait_g(bar_o_full, 0);
     tc_fence_after();
-    store_o(nu == 3 ? 1 : 0);
+    if (pend) store_o();
   }
   tc_fence_before();
   __syncthreads();
@@ -450,15 +556,16 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_fwd_kernel(
 //   dK     += dS^T_hf Q_hf   (A = dS^T block hf in shared memory, K-major)
 //   dQ      = dS K           (A = both dS^T blocks read MN-major)            -> TMEM [64,128)
 //   dV -> TMEM [128,192), dK -> TMEM [192,256).
-// Units: (kt, qt) = (0,0) [, (0,1), (1,1)].  K/V are loaded once per key tile, Q/dO once per query
-// tile (unit 2 reuses the Q/dO of unit 1).
+// Units of an item: (kt, qt) = (0,0) [, (0,1), (1,1)].  K/V are loaded once per key tile, Q/dO once
+// per query tile (unit 2 reuses the Q/dO of unit 1); the loads of the next item start as soon as the
+// last MMA of this one has completed, i.e. while the epilogue still drains dQ / dV / dK.
 struct ShortBwdParams {
   int64_t N;
-  int B, H, index_bits, tps, nb, cache_nt;
-  int single_phase;
+  int B, H, index_bits, tps;
+  long long* tl;
   const void* offsets;
   const uint8_t* tiles;
-  const uint8_t* bcache;
+  const int* sched;
   __nv_bfloat16* dq; int64_t lddq;
   __nv_bfloat16* dk; int64_t lddk;
   __nv_bfloat16* dv; int64_t lddv;
@@ -485,17 +592,12 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_bwd_kernel(
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   using L = SbSmem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int items = p.B * p.H;
-  const int phase = p.single_phase ? 1 : (int) (blockIdx.x / items);
-  const int item = (int) (blockIdx.x % items);
-  const int b = item / p.H, h = item % p.H;
-  const int64_t off0 = load_index(p.offsets, b, p.index_bits);
-  int64_t n64 = load_index(p.offsets, b + 1, p.index_bits) - off0;
-  if (n64 > p.N) n64 = p.N;
-  const int n = (int) n64;
-  if (n <= 0) return;
-  const int nu = n > 128 ? 3 : 1;
-  if ((phase == 0) != (nu == 3)) return;
+  const int n_items = p.sched[0] * p.H;
+  const int G = (int) gridDim.x, cta = (int) blockIdx.x;
+  if (cta >= n_items) return;
+  const int* order = p.sched + 2;
+  const int tl_id = cta < SH_TL_CTAS ? cta : 1 << 20;
+  SH_STAMP(tid == 0, 0);
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bars);
   const uint32_t bar_kv_full = smem_u32(bars + 0);
@@ -530,21 +632,29 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_bwd_kernel(
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      mbar_arrive_expect_tx(bar_kv_full, 2 * AT_TILE_BYTES);
-      tma_load_2d(smem_u32(smem + L::k), &tmK, h * AT_D, (int) off0, bar_kv_full);
-      tma_load_2d(smem_u32(smem + L::v), &tmV, h * AT_D, (int) off0, bar_kv_full);
-      mbar_arrive_expect_tx(bar_qdo_full, 2 * AT_TILE_BYTES);
-      tma_load_2d(smem_u32(smem + L::q), &tmQ, h * AT_D, (int) off0, bar_qdo_full);
-      tma_load_2d(smem_u32(smem + L::dout), &tmdO, h * AT_D, (int) off0, bar_qdo_full);
-      if (nu == 3) {
-        mbar_wait_g(bar_dq_full, 0);                   // every MMA of unit 0 has completed
-        mbar_arrive_expect_tx(bar_qdo_full, 2 * AT_TILE_BYTES);
-        tma_load_2d(smem_u32(smem + L::q), &tmQ, h * AT_D, (int) (off0 + AT_BM), bar_qdo_full);
-        tma_load_2d(smem_u32(smem + L::dout), &tmdO, h * AT_D, (int) (off0 + AT_BM), bar_qdo_full);
-        mbar_wait_g(bar_dq_full, 1);                   // every MMA of unit 1 has completed
+      ItemIter iter(G, cta, n_items);
+      uint32_t gu = 0;                                 // units before this item
+      for (int idx = iter.next(); idx >= 0; idx = iter.next()) {
+        const Item it = decode_item(idx, p.H, order, p.offsets, p.index_bits, p.N);
+        // every MMA of the previous unit has completed: the operand tiles may be overwritten
+        if (gu > 0) mbar_wait_g(bar_dq_full, (gu - 1) & 1);
         mbar_arrive_expect_tx(bar_kv_full, 2 * AT_TILE_BYTES);
-        tma_load_2d(smem_u32(smem + L::k), &tmK, h * AT_D, (int) (off0 + AT_BN), bar_kv_full);
-        tma_load_2d(smem_u32(smem + L::v), &tmV, h * AT_D, (int) (off0 + AT_BN), bar_kv_full);
+        tma_load_2d(smem_u32(smem + L::k), &tmK, it.h * AT_D, (int) it.off0, bar_kv_full);
+        tma_load_2d(smem_u32(smem + L::v), &tmV, it.h * AT_D, (int) it.off0, bar_kv_full);
+        mbar_arrive_expect_tx(bar_qdo_full, 2 * AT_TILE_BYTES);
+        tma_load_2d(smem_u32(smem + L::q), &tmQ, it.h * AT_D, (int) it.off0, bar_qdo_full);
+        tma_load_2d(smem_u32(smem + L::dout), &tmdO, it.h * AT_D, (int) it.off0, bar_qdo_full);
+        if (it.nu == 3) {
+          mbar_wait_g(bar_dq_full, gu & 1);            // unit 0 done
+          mbar_arrive_expect_tx(bar_qdo_full, 2 * AT_TILE_BYTES);
+          tma_load_2d(smem_u32(smem + L::q), &tmQ, it.h * AT_D, (int) (it.off0 + AT_BM), bar_qdo_full);
+          tma_load_2d(smem_u32(smem + L::dout), &tmdO, it.h * AT_D, (int) (it.off0 + AT_BM), bar_qdo_full);
+          mbar_wait_g(bar_dq_full, (gu + 1) & 1);      // unit 1 done
+          mbar_arrive_expect_tx(bar_kv_full, 2 * AT_TILE_BYTES);
+          tma_load_2d(smem_u32(smem + L::k), &tmK, it.h * AT_D, (int) (it.off0 + AT_BN), bar_kv_full);
+          tma_load_2d(smem_u32(smem + L::v), &tmV, it.h * AT_D, (int) (it.off0 + AT_BN), bar_kv_full);
+        }
+        gu += it.nu;
       }
     }
   } else if (warp == 1) {
@@ -559,71 +669,75 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_bwd_kernel(
     const uint64_t ds_k_desc = make_smem_desc_sw128(smem_u32(smem + L::dsT), 0, 1024);
     const uint64_t ds_mn_desc = make_smem_desc_sw128(smem_u32(smem + L::dsT), AT_TILE_BYTES, 1024);
     auto adv = [](uint64_t d, uint32_t bytes) { return d + (uint64_t) (bytes >> 4); };
-    for (int u = 0; u < nu; ++u) {
-      const bool first_of_kt = (u != 1);
-      const bool last_of_kt = (nu == 1) || (u >= 1);
-      if (u == 0) { mbar_wait_g(bar_kv_full, 0); mbar_wait_g(bar_qdo_full, 0); }
-      if (u == 1) mbar_wait_g(bar_qdo_full, 1);
-      if (u == 2) mbar_wait_g(bar_kv_full, 1);
-      if (u > 0) mbar_wait_g(bar_dq_read, (u - 1) & 1);      // dQ of unit u-1 has left TMEM [64,128)
-      if (HAS_BIAS && u > 0 && lane == 0) bulk_wait_group_read0();   // the dS^T blocks have been read
-      __syncwarp();
-      tc_fence_after();
-      // ---- half A scores ----
+    ItemIter iter(G, cta, n_items);
+    uint32_t gu = 0, gk = 0, c_kv = 0, c_qdo = 0;
+    for (int idx = iter.next(); idx >= 0; idx = iter.next()) {
+      const Item it = decode_item(idx, p.H, order, p.offsets, p.index_bits, p.N);
+      for (int u = 0; u < it.nu; ++u, ++gu) {
+        const bool first_of_kt = (u != 1);
+        const bool last_of_kt = (it.nu == 1) || (u >= 1);
+        if (u != 1) { mbar_wait_g(bar_kv_full, c_kv & 1); ++c_kv; }
+        if (u != 2) { mbar_wait_g(bar_qdo_full, c_qdo & 1); ++c_qdo; }
+        if (gu > 0) mbar_wait_g(bar_dq_read, (gu - 1) & 1);    // dQ of the previous unit has left TMEM [64,128)
+        if (HAS_BIAS && gu > 0 && lane == 0) bulk_wait_group_read0();   // the dS^T blocks have been read
+        __syncwarp();
+        tc_fence_after();
+        // ---- half A scores ----
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        umma_ss_warp(tmem, adv(k_desc, ks * 32), adv(q_desc, ks * 32), id_kk, ks > 0);
+        for (int ks = 0; ks < 4; ++ks)
+          umma_ss_warp(tmem, adv(k_desc, ks * 32), adv(q_desc, ks * 32), id_kk, ks > 0);
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        umma_ss_warp(tmem + 64, adv(v_desc, ks * 32), adv(o_desc, ks * 32), id_kk, ks > 0);
-      umma_commit_warp(bar_s_full);
-      mbar_wait_g(bar_half_done, u & 1);
-      if (u == 2) mbar_wait_g(bar_dkv_read, 0);              // dV / dK of key tile 0 have been stored
-      tc_fence_after();
-      if (HAS_BIAS && lane == 0) {   // head-summed dS'^T for the bias gradients: block A -> global, bf16 add
-        bulk_reduce_add_bf16(p.dbias + (((int64_t) b * p.tps + u) * 2 + 0) * AT_TILE_BYTES,
-                             smem_u32(smem + L::dsT), AT_TILE_BYTES);
-        bulk_commit_group();
+        for (int ks = 0; ks < 4; ++ks)
+          umma_ss_warp(tmem + 64, adv(v_desc, ks * 32), adv(o_desc, ks * 32), id_kk, ks > 0);
+        umma_commit_warp(bar_s_full);
+        mbar_wait_g(bar_half_done, gu & 1);
+        if (first_of_kt && gk > 0) mbar_wait_g(bar_dkv_read, (gk - 1) & 1);   // dV / dK of the previous key tile stored
+        tc_fence_after();
+        if (HAS_BIAS && lane == 0) {   // head-summed dS'^T for the bias gradients: block A -> global, bf16 add
+          bulk_reduce_add_bf16(p.dbias + (((int64_t) it.seq * p.tps + u) * 2 + 0) * AT_TILE_BYTES,
+                               smem_u32(smem + L::dsT), AT_TILE_BYTES);
+          bulk_commit_group();
+        }
+        __syncwarp();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)     // dV += P^T_A dO_A : P^T of queries 16 ks .. at TMEM col 32 (ks/2) + 8 (ks%2)
+          umma_ts_warp(tmem + 128, tmem + 32 * (ks >> 1) + 8 * (ks & 1), adv(o_desc, ks * 2048), id_kmn,
+                       !first_of_kt || ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)     // dK += dS^T_A Q_A
+          umma_ss_warp(tmem + 192, adv(ds_k_desc, ks * 32), adv(q_desc, ks * 2048), id_kmn,
+                       !first_of_kt || ks > 0);
+        umma_commit_warp(bar_pa_free);
+        // ---- half B scores: dP^T first (its TMEM columns are free), S^T once P^T_A has been consumed ----
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_ss_warp(tmem + 64, adv(v_desc, ks * 32), adv(o_desc, 8192 + ks * 32), id_kk, ks > 0);
+        mbar_wait_g(bar_pa_free, gu & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_ss_warp(tmem, adv(k_desc, ks * 32), adv(q_desc, 8192 + ks * 32), id_kk, ks > 0);
+        umma_commit_warp(bar_s_full + 8);
+        mbar_wait_g(bar_half_done + 8, gu & 1);
+        tc_fence_after();
+        if (HAS_BIAS && lane == 0) {
+          bulk_reduce_add_bf16(p.dbias + (((int64_t) it.seq * p.tps + u) * 2 + 1) * AT_TILE_BYTES,
+                               smem_u32(smem + L::dsT) + AT_TILE_BYTES, AT_TILE_BYTES);
+          bulk_commit_group();
+        }
+        __syncwarp();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_ts_warp(tmem + 128, tmem + 32 * (ks >> 1) + 8 * (ks & 1), adv(o_desc, (4 + ks) * 2048), id_kmn, true);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_ss_warp(tmem + 192, adv(ds_k_desc, AT_TILE_BYTES + ks * 32), adv(q_desc, (4 + ks) * 2048), id_kmn, true);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)     // dQ = dS K : A = dS^T (both blocks) MN-major, B = K MN-major
+          umma_ss_warp(tmem + 64, adv(ds_mn_desc, ks * 2048), adv(k_desc, ks * 2048), id_mnmn, ks > 0);
+        umma_commit_warp(bar_dq_full);
+        if (last_of_kt) { umma_commit_warp(bar_dkv_full); ++gk; }
       }
-      __syncwarp();
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks)     // dV += P^T_A dO_A : P^T of queries 16 ks .. at TMEM col 32 (ks/2) + 8 (ks%2)
-        umma_ts_warp(tmem + 128, tmem + 32 * (ks >> 1) + 8 * (ks & 1), adv(o_desc, ks * 2048), id_kmn,
-                     !first_of_kt || ks > 0);
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks)     // dK += dS^T_A Q_A
-        umma_ss_warp(tmem + 192, adv(ds_k_desc, ks * 32), adv(q_desc, ks * 2048), id_kmn,
-                     !first_of_kt || ks > 0);
-      umma_commit_warp(bar_pa_free);
-      // ---- half B scores: dP^T first (its TMEM columns are free), S^T once P^T_A has been consumed ----
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        umma_ss_warp(tmem + 64, adv(v_desc, ks * 32), adv(o_desc, 8192 + ks * 32), id_kk, ks > 0);
-      mbar_wait_g(bar_pa_free, u & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        umma_ss_warp(tmem, adv(k_desc, ks * 32), adv(q_desc, 8192 + ks * 32), id_kk, ks > 0);
-      umma_commit_warp(bar_s_full + 8);
-      mbar_wait_g(bar_half_done + 8, u & 1);
-      tc_fence_after();
-      if (HAS_BIAS && lane == 0) {
-        bulk_reduce_add_bf16(p.dbias + (((int64_t) b * p.tps + u) * 2 + 1) * AT_TILE_BYTES,
-                             smem_u32(smem + L::dsT) + AT_TILE_BYTES, AT_TILE_BYTES);
-        bulk_commit_group();
-      }
-      __syncwarp();
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        umma_ts_warp(tmem + 128, tmem + 32 * (ks >> 1) + 8 * (ks & 1), adv(o_desc, (4 + ks) * 2048), id_kmn, true);
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        umma_ss_warp(tmem + 192, adv(ds_k_desc, AT_TILE_BYTES + ks * 32), adv(q_desc, (4 + ks) * 2048), id_kmn, true);
-#pragma unroll
-      for (int ks = 0; ks < 8; ++ks)     // dQ = dS K : A = dS^T (both blocks) MN-major, B = K MN-major
-        umma_ss_warp(tmem + 64, adv(ds_mn_desc, ks * 2048), adv(k_desc, ks * 2048), id_mnmn, ks > 0);
-      umma_commit_warp(bar_dq_full);
-      if (last_of_kt) umma_commit_warp(bar_dkv_full);
     }
     if (HAS_BIAS && lane == 0) bulk_wait_group0();          // shared memory must outlive the reduces
     __syncwarp();
@@ -636,151 +750,161 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_bwd_kernel(
     const float inv_n = 1.0f / (float) p.N;
     const float half_inv_n = 0.5f * inv_n;
     uint8_t* dsT_row = smem + L::dsT + r * 128;
-    for (int u = 0; u < nu; ++u) {
-      const int qt = u >= 1, kt = u == 2;
-      const int i0 = qt * AT_BM, j0 = kt * AT_BN;
-      const int jk = j0 + r;
-      const bool last_of_kt = (nu == 1) || (u >= 1);
-      const uint8_t* tile = p.tiles + ((int64_t) b * p.tps + u) * SH_TILE_SLOT + 32768;   // K orientation
+    ItemIter iter(G, cta, n_items);
+    uint32_t gu = 0, gk = 0;
+    int k_item = 0;
+    for (int idx = iter.next(); idx >= 0; idx = iter.next(), ++k_item) {
+      const Item it = decode_item(idx, p.H, order, p.offsets, p.index_bits, p.N);
+      const int n = it.n, h = it.h;
+      const int64_t off0 = it.off0;
+      SH_STAMP(tid == 64 && k_item < 7, 1 + 2 * k_item);
+      for (int u = 0; u < it.nu; ++u, ++gu) {
+        const int qt = u >= 1, kt = u == 2;
+        const int i0 = qt * AT_BM, j0 = kt * AT_BN;
+        const int jk = j0 + r;
+        const bool last_of_kt = (it.nu == 1) || (u >= 1);
+        const uint8_t* tile = p.tiles + ((int64_t) it.seq * p.tps + u) * SH_TILE_SLOT + 32768;   // K orientation
 #pragma unroll 1
-      for (int hf = 0; hf < 2; ++hf) {
-        const int cb = 64 * hf + 32 * g;               // first query column (in the tile) of this thread
-        // prefetch bias/2 (32 fp16) of this half before the scores arrive
-        uint4 hbv[4];
+        for (int hf = 0; hf < 2; ++hf) {
+          const int cb = 64 * hf + 32 * g;               // first query column (in the tile) of this thread
+          // prefetch bias/2 (32 fp16) of this half before the scores arrive
+          uint4 hbv[4];
 #pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8)
-          hbv[c8] = ldg_nc_v4(tile + ((size_t) ((cb >> 3) + c8) * 128 + r) * 16);
-        mbar_wait_g(bar_s_full + 8 * hf, u & 1);
-        tc_fence_after();
+          for (int c8 = 0; c8 < 4; ++c8)
+            hbv[c8] = ldg_nc_v4(tile + ((size_t) ((cb >> 3) + c8) * 128 + r) * 16);
+          mbar_wait_g(bar_s_full + 8 * hf, gu & 1);
+          tc_fence_after();
 #pragma unroll
-        for (int sc = 0; sc < 2; ++sc) {               // 16-column sub-chunks
-          const int c16 = cb + 16 * sc;
-          const int tcol = 32 * g + 16 * sc;           // column inside the half's TMEM region
-          // valid columns of this row in the sub-chunk: lo <= e < hi (warp-uniform test: nothing to do?)
-          const int lo = jk - i0 - c16, hi = n - i0 - c16;
-          const bool dead = __all_sync(0xffffffffu, lo >= 16 || hi <= 0 || hi <= lo);
-          if (dead) {
-            const uint32_t z4[4] = {0u, 0u, 0u, 0u};
+          for (int sc = 0; sc < 2; ++sc) {               // 16-column sub-chunks
+            const int c16 = cb + 16 * sc;
+            const int tcol = 32 * g + 16 * sc;           // column inside the half's TMEM region
+            // valid columns of this row in the sub-chunk: lo <= e < hi; nothing to do for the warp?
+            const int lo = jk - i0 - c16, hi = n - i0 - c16;
+            const bool dead = __all_sync(0xffffffffu, lo >= 16 || hi <= 0 || hi <= lo);
+            if (dead) {
+              const uint32_t z4[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+              for (int c8 = 0; c8 < 2; ++c8) {
+                tmem_st4(tmem + lane_base + 32 * g + 8 * sc + 4 * c8, z4);
+                *reinterpret_cast<uint4*>(dsT_row + hf * AT_TILE_BYTES + ((4 * g + 2 * sc + c8) ^ (r & 7)) * 16) =
+                    make_uint4(0u, 0u, 0u, 0u);
+              }
+              continue;
+            }
+            uint32_t sv[16], dv_[16];
+            tmem_ld16(tmem + lane_base + tcol, sv);
+            tmem_ld16(tmem + lane_base + 64 + tcol, dv_);
+            tmem_ld_wait();
 #pragma unroll
             for (int c8 = 0; c8 < 2; ++c8) {
-              tmem_st4(tmem + lane_base + 32 * g + 8 * sc + 4 * c8, z4);
+              const uint4 hq = hbv[2 * sc + c8];
+              const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w};
+              uint32_t ppk[4], dpk[4];
+#pragma unroll
+              for (int e2 = 0; e2 < 4; ++e2) {
+                const float2 hb2 = __half22float2(*reinterpret_cast<const __half2*>(&hw[e2]));
+                float pv2[2], ds2[2];
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                  const int cc = 8 * c8 + 2 * e2 + t;
+                  const float hx = fmaf(__uint_as_float(sv[cc]), 0.5f, t ? hb2.y : hb2.x);
+                  const float th = tanh_approx(hx);
+                  // unscaled: P' = SiLU(x) = N P ; dS' = dP * 2 SiLU'(x) = 2N dS (factors applied at the end)
+                  pv2[t] = fmaf(hx, th, hx);
+                  const float u1 = fmaf(-th, th, 1.0f);
+                  const float w2 = fmaf(hx, u1, 1.0f + th);
+                  ds2[t] = __uint_as_float(dv_[cc]) * w2;
+                }
+                ppk[e2] = pack_bf16x2(pv2[0], pv2[1]);
+                dpk[e2] = pack_bf16x2(ds2[0], ds2[1]);
+              }
+              // P^T: queries c16 + 8 c8 .. +7 of this key row -> TMEM columns 32 g + 8 sc + 4 c8 .. +3
+              tmem_st4(tmem + lane_base + 32 * g + 8 * sc + 4 * c8, ppk);
+              // dS^T: 16-byte chunk (4 g + 2 sc + c8) of this key row, 128-byte swizzle, block hf
               *reinterpret_cast<uint4*>(dsT_row + hf * AT_TILE_BYTES + ((4 * g + 2 * sc + c8) ^ (r & 7)) * 16) =
-                  make_uint4(0u, 0u, 0u, 0u);
+                  make_uint4(dpk[0], dpk[1], dpk[2], dpk[3]);
             }
-            continue;
           }
-          uint32_t sv[16], dv_[16];
-          tmem_ld16(tmem + lane_base + tcol, sv);
-          tmem_ld16(tmem + lane_base + 64 + tcol, dv_);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c8 = 0; c8 < 2; ++c8) {
-            const uint4 hq = hbv[2 * sc + c8];
-            const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w};
-            float dsv[8];
-            uint32_t ppk[4], dpk[4];
-#pragma unroll
-            for (int e2 = 0; e2 < 4; ++e2) {
-              const float2 hb2 = __half22float2(*reinterpret_cast<const __half2*>(&hw[e2]));
-              float pv2[2];
-#pragma unroll
-              for (int t = 0; t < 2; ++t) {
-                const int cc = 8 * c8 + 2 * e2 + t;
-                const float hx = fmaf(__uint_as_float(sv[cc]), 0.5f, t ? hb2.y : hb2.x);
-                const float th = tanh_approx(hx);
-                // unscaled: P' = SiLU(x) = N P ; dS' = dP * 2 SiLU'(x) = 2N dS (factors applied at the end)
-                pv2[t] = fmaf(hx, th, hx);
-                const float u1 = fmaf(-th, th, 1.0f);
-                const float w2 = fmaf(hx, u1, 1.0f + th);
-                dsv[2 * e2 + t] = __uint_as_float(dv_[cc]) * w2;
-              }
-              ppk[e2] = pack_bf16x2(pv2[0], pv2[1]);
-              dpk[e2] = pack_bf16x2(dsv[2 * e2], dsv[2 * e2 + 1]);
-            }
-            // P^T: queries c16 + 8 c8 .. +7 of this key row -> TMEM columns 32 g + 8 sc + 4 c8 .. +3
-            tmem_st4(tmem + lane_base + 32 * g + 8 * sc + 4 * c8, ppk);
-            // dS^T: 16-byte chunk (4 g + 2 sc + c8) of this key row, 128-byte swizzle, block hf
-            *reinterpret_cast<uint4*>(dsT_row + hf * AT_TILE_BYTES + ((4 * g + 2 * sc + c8) ^ (r & 7)) * 16) =
-                make_uint4(dpk[0], dpk[1], dpk[2], dpk[3]);
-          }
+          tmem_st_wait();
+          tc_fence_before();
+          fence_proxy_async_smem();                  // st.shared -> visible to the MMA / bulk reduce (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_half_done + 8 * hf);
         }
-        tmem_st_wait();
-        tc_fence_before();
-        fence_proxy_async_smem();                  // st.shared -> visible to the MMA (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_half_done + 8 * hf);
-      }
-      // ---- dQ of this unit: thread = query row r of tile qt, columns 32 g .. +31 ----
-      mbar_wait_g(bar_dq_full, u & 1);
-      tc_fence_after();
-      {
-        uint32_t qv[32];
-        tmem_ld32(tmem + lane_base + 64 + 32 * g, qv);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_dq_read);
-        const int i = i0 + r;
-        if (i < n) {
-          float* part = p.dq_accum + (off0 + i) * ((int64_t) p.H * AT_D) + h * AT_D + 32 * g;
-          if (u == 1) {                              // partial of query tile 1 (key tile 0)
-#pragma unroll
-            for (int v4 = 0; v4 < 8; ++v4)
-              *reinterpret_cast<float4*>(part + 4 * v4) =
-                  make_float4(__uint_as_float(qv[4 * v4]), __uint_as_float(qv[4 * v4 + 1]),
-                              __uint_as_float(qv[4 * v4 + 2]), __uint_as_float(qv[4 * v4 + 3]));
-          } else {
-            if (u == 2) {
-#pragma unroll
-              for (int v4 = 0; v4 < 8; ++v4) {
-                const float4 a = *reinterpret_cast<const float4*>(part + 4 * v4);
-                qv[4 * v4] = __float_as_uint(__uint_as_float(qv[4 * v4]) + a.x);
-                qv[4 * v4 + 1] = __float_as_uint(__uint_as_float(qv[4 * v4 + 1]) + a.y);
-                qv[4 * v4 + 2] = __float_as_uint(__uint_as_float(qv[4 * v4 + 2]) + a.z);
-                qv[4 * v4 + 3] = __float_as_uint(__uint_as_float(qv[4 * v4 + 3]) + a.w);
-              }
-            }
-            __nv_bfloat16* dst = p.dq + (off0 + i) * p.lddq + h * AT_D + 32 * g;
-#pragma unroll
-            for (int v4 = 0; v4 < 4; ++v4) {
-              uint4 o;
-              o.x = pack_bf16x2(__uint_as_float(qv[v4 * 8 + 0]) * half_inv_n, __uint_as_float(qv[v4 * 8 + 1]) * half_inv_n);
-              o.y = pack_bf16x2(__uint_as_float(qv[v4 * 8 + 2]) * half_inv_n, __uint_as_float(qv[v4 * 8 + 3]) * half_inv_n);
-              o.z = pack_bf16x2(__uint_as_float(qv[v4 * 8 + 4]) * half_inv_n, __uint_as_float(qv[v4 * 8 + 5]) * half_inv_n);
-              o.w = pack_bf16x2(__uint_as_float(qv[v4 * 8 + 6]) * half_inv_n, __uint_as_float(qv[v4 * 8 + 7]) * half_inv_n);
-              *reinterpret_cast<uint4*>(dst + v4 * 8) = o;
-            }
-          }
-        }
-      }
-      // ---- dV / dK of a finished key tile: thread = key row, columns 32 g .. +31 of each ----
-      if (last_of_kt) {
-        mbar_wait_g(bar_dkv_full, kt);
+        // ---- dQ of this unit: thread = query row r of tile qt, columns 32 g .. +31 ----
+        mbar_wait_g(bar_dq_full, gu & 1);
         tc_fence_after();
-#pragma unroll
-        for (int which = 0; which < 2; ++which) {
-          uint32_t ov[32];
-          tmem_ld32(tmem + lane_base + 128 + 64 * which + 32 * g, ov);
+        {
+          uint32_t qv[32];
+          tmem_ld32(tmem + lane_base + 64 + 32 * g, qv);
           tmem_ld_wait();
-          const float sc = which == 0 ? inv_n : half_inv_n;   // dV = P'^T dO / N ; dK = dS'^T Q / (2N)
-          if (jk < n) {
-            __nv_bfloat16* dst = (which == 0 ? p.dv + (off0 + jk) * p.lddv : p.dk + (off0 + jk) * p.lddk) +
-                                 h * AT_D + 32 * g;
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_dq_read);
+          const int i = i0 + r;
+          if (i < n) {
+            float* part = p.dq_accum + (off0 + i) * ((int64_t) p.H * AT_D) + h * AT_D + 32 * g;
+            if (u == 1) {                              // partial of query tile 1 (key tile 0)
 #pragma unroll
-            for (int v4 = 0; v4 < 4; ++v4) {
-              uint4 o;
-              o.x = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 0]) * sc, __uint_as_float(ov[v4 * 8 + 1]) * sc);
-              o.y = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 2]) * sc, __uint_as_float(ov[v4 * 8 + 3]) * sc);
-              o.z = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 4]) * sc, __uint_as_float(ov[v4 * 8 + 5]) * sc);
-              o.w = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 6]) * sc, __uint_as_float(ov[v4 * 8 + 7]) * sc);
-              *reinterpret_cast<uint4*>(dst + v4 * 8) = o;
+              for (int v4 = 0; v4 < 8; ++v4)
+                *reinterpret_cast<float4*>(part + 4 * v4) =
+                    make_float4(__uint_as_float(qv[4 * v4]), __uint_as_float(qv[4 * v4 + 1]),
+                                __uint_as_float(qv[4 * v4 + 2]), __uint_as_float(qv[4 * v4 + 3]));
+            } else {
+              if (u == 2) {
+#pragma unroll
+                for (int v4 = 0; v4 < 8; ++v4) {
+                  const float4 a = *reinterpret_cast<const float4*>(part + 4 * v4);
+                  qv[4 * v4] = __float_as_uint(__uint_as_float(qv[4 * v4]) + a.x);
+                  qv[4 * v4 + 1] = __float_as_uint(__uint_as_float(qv[4 * v4 + 1]) + a.y);
+                  qv[4 * v4 + 2] = __float_as_uint(__uint_as_float(qv[4 * v4 + 2]) + a.z);
+                  qv[4 * v4 + 3] = __float_as_uint(__uint_as_float(qv[4 * v4 + 3]) + a.w);
+                }
+              }
+              __nv_bfloat16* dst = p.dq + (off0 + i) * p.lddq + h * AT_D + 32 * g;
+#pragma unroll
+              for (int v4 = 0; v4 < 4; ++v4) {
+                uint4 o;
+                o.x = pack_bf16x2(__uint_as_float(qv[v4 * 8 + 0]) * half_inv_n, __uint_as_float(qv[v4 * 8 + 1]) * half_inv_n);
+                o.y = pack_bf16x2(__uint_as_float(qv[v4 * 8 + 2]) * half_inv_n, __uint_as_float(qv[v4 * 8 + 3]) * half_inv_n);
+                o.z = pack_bf16x2(__uint_as_float(qv[v4 * 8 + 4]) * half_inv_n, __uint_as_float(qv[v4 * 8 + 5]) * half_inv_n);
+                o.w = pack_bf16x2(__uint_as_float(qv[v4 * 8 + 6]) * half_inv_n, __uint_as_float(qv[v4 * 8 + 7]) * half_inv_n);
+                *reinterpret_cast<uint4*>(dst + v4 * 8) = o;
+              }
             }
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_dkv_read);
+        // ---- dV / dK of a finished key tile: thread = key row, columns 32 g .. +31 of each ----
+        if (last_of_kt) {
+          mbar_wait_g(bar_dkv_full, gk & 1);
+          ++gk;
+          tc_fence_after();
+#pragma unroll
+          for (int which = 0; which < 2; ++which) {
+            uint32_t ov[32];
+            tmem_ld32(tmem + lane_base + 128 + 64 * which + 32 * g, ov);
+            tmem_ld_wait();
+            const float sc = which == 0 ? inv_n : half_inv_n;   // dV = P'^T dO / N ; dK = dS'^T Q / (2N)
+            if (jk < n) {
+              __nv_bfloat16* dst = (which == 0 ? p.dv + (off0 + jk) * p.lddv : p.dk + (off0 + jk) * p.lddk) +
+                                   h * AT_D + 32 * g;
+#pragma unroll
+              for (int v4 = 0; v4 < 4; ++v4) {
+                uint4 o;
+                o.x = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 0]) * sc, __uint_as_float(ov[v4 * 8 + 1]) * sc);
+                o.y = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 2]) * sc, __uint_as_float(ov[v4 * 8 + 3]) * sc);
+                o.z = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 4]) * sc, __uint_as_float(ov[v4 * 8 + 5]) * sc);
+                o.w = pack_bf16x2(__uint_as_float(ov[v4 * 8 + 6]) * sc, __uint_as_float(ov[v4 * 8 + 7]) * sc);
+                *reinterpret_cast<uint4*>(dst + v4 * 8) = o;
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_dkv_read);
+        }
       }
+      SH_STAMP(tid == 64 && k_item < 7, 2 + 2 * k_item);
     }
   }
   tc_fence_before();
@@ -813,6 +937,42 @@ bool hstu_attn_short_usable(const grb_hstu_attn_args* a, bool bwd) {
   return true;
 }
 
+// GRB_SHORT_TIMELINE=1: dump the stamps of the probed CTAs to stderr after the launch (synchronises)
+static long long* timeline_buffer() {
+  static long long* buf = nullptr;
+  const char* e = std::getenv("GRB_SHORT_TIMELINE");
+  if (!(e && e[0] == '1')) return nullptr;
+  if (!buf) cudaMalloc(&buf, SH_TL_CTAS * SH_TL_SLOTS * sizeof(long long));
+  cudaMemset(buf, 0, SH_TL_CTAS * SH_TL_SLOTS * sizeof(long long));
+  return buf;
+}
+static void timeline_dump(const char* what, long long* buf, cudaStream_t st) {
+  if (!buf) return;
+  cudaStreamSynchronize(st);
+  static long long h[SH_TL_CTAS * SH_TL_SLOTS];
+  cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost);
+  long long t0 = 0;
+  for (int c = 0; c < SH_TL_CTAS; ++c) if (h[c * SH_TL_SLOTS] && (!t0 || h[c * SH_TL_SLOTS] < t0)) t0 = h[c * SH_TL_SLOTS];
+  for (int c = 0; c < SH_TL_CTAS; ++c) {
+    const long long* r = h + c * SH_TL_SLOTS;
+    if (!r[0]) continue;
+    fprintf(stderr, "%s cta %2d nu %lld:", what, c, r[15]);
+    for (int s2 = 0; s2 < 15; ++s2) fprintf(stderr, " %d:%lld", s2, r[s2] ? r[s2] - t0 : -1);
+    fprintf(stderr, "\n");
+  }
+}
+
+// persistent grid: two CTAs per SM (the kernels' resource limits), never more than there are items
+static unsigned short_grid(const grb_hstu_attn_args* a) {
+  const int64_t items = a->B * a->H;
+  const int64_t slots = 2 * (int64_t) num_sms();
+  return (unsigned) (items < slots ? items : slots);
+}
+static const int* short_schedule(const grb_hstu_attn_args* a, int tps) {
+  return reinterpret_cast<const int*>(reinterpret_cast<const uint8_t*>(a->bias_tiles) +
+                                      (int64_t) a->B * tps * SH_TILE_SLOT);
+}
+
 int hstu_attn_short_fwd(const grb_hstu_attn_args* a, cudaStream_t st) {
   if (a->B == 0 || a->max_len == 0) return GRB_OK;
   CUtensorMap tmQ, tmK, tmV;
@@ -827,17 +987,16 @@ int hstu_attn_short_fwd(const grb_hstu_attn_args* a, cudaStream_t st) {
   p.tps = NT * (NT + 1) / 2;
   p.offsets = a->offsets;
   p.tiles = reinterpret_cast<const uint8_t*>(a->bias_tiles);
+  p.sched = short_schedule(a, p.tps);
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out); p.ldo = a->ldo;
   const size_t smem = SfSmem::total + 1024;
-  // two phases of B*H CTAs: the first takes the 3-unit sequences (n > 128) so that the heavy items
-  // start first; with max_len <= 128 there are none and one phase suffices
-  p.single_phase = a->max_len <= 128;
   auto kern = hstu_attn_short_fwd_kernel;
   GRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   GRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                    (int) cudaSharedmemCarveoutMaxShared));   // two CTAs per SM
-  const unsigned items = (unsigned) (a->B * a->H);
-  kern<<<p.single_phase ? items : 2 * items, SH_THREADS, smem, st>>>(tmQ, tmK, tmV, p);
+  p.tl = timeline_buffer();
+  kern<<<short_grid(a), SH_THREADS, smem, st>>>(tmQ, tmK, tmV, p);
+  timeline_dump("fwd", p.tl, st);
   GRB_LAUNCH_OK();
   return GRB_OK;
 }
@@ -852,21 +1011,20 @@ int hstu_attn_short_bwd(const grb_hstu_attn_args* a, cudaStream_t st) {
   if ((rc = make_tmap_bf16_2d(&tmV, a->v, a->T, W, a->ldv, AT_BN)) != GRB_OK) return rc;
   if ((rc = make_tmap_bf16_2d(&tmdO, a->dout, a->T, W, a->lddo, AT_BM)) != GRB_OK) return rc;
   ShortBwdParams p{};
-  p.N = a->N; p.B = (int) a->B; p.H = a->H; p.index_bits = a->index_bits; p.nb = a->num_buckets;
+  p.N = a->N; p.B = (int) a->B; p.H = a->H; p.index_bits = a->index_bits;
   const int NT = (int) ceil_div(a->max_len, AT_BM);
   p.tps = NT * (NT + 1) / 2;
-  p.cache_nt = NT;
   p.offsets = a->offsets;
   p.tiles = reinterpret_cast<const uint8_t*>(a->bias_tiles);
-  p.bcache = a->timestamps ? a->bucket_cache : nullptr;
+  p.sched = short_schedule(a, p.tps);
   p.dq = reinterpret_cast<__nv_bfloat16*>(a->dq); p.lddq = a->lddq;
   p.dk = reinterpret_cast<__nv_bfloat16*>(a->dk); p.lddk = a->lddk;
   p.dv = reinterpret_cast<__nv_bfloat16*>(a->dv_grad); p.lddv = a->lddv;
   p.dq_accum = a->dq_accum;
   p.dbias = reinterpret_cast<uint8_t*>(a->dbias_acc);
   const size_t smem = SbSmem::total + 1024;
-  p.single_phase = a->max_len <= 128;
-  const unsigned items = (unsigned) (a->B * a->H) * (p.single_phase ? 1u : 2u);
+  p.tl = timeline_buffer();
+  const unsigned items = short_grid(a);
   if (a->timestamps) {
     auto kern = hstu_attn_short_bwd_kernel<true>;
     GRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
@@ -874,6 +1032,7 @@ int hstu_attn_short_bwd(const grb_hstu_attn_args* a, cudaStream_t st) {
                                      (int) cudaSharedmemCarveoutMaxShared));
     kern<<<items, SH_THREADS, smem, st>>>(tmQ, tmK, tmV, tmdO, p);
     GRB_LAUNCH_OK();
+    timeline_dump("bwd", p.tl, st);
     // bias gradients from the head-summed dS'^T tiles (dS' = 2N dS)
     const int copies = a->d_bias_copies > 0 ? a->d_bias_copies : 1;
     dim3 grid((unsigned) p.tps, (unsigned) a->B);
@@ -897,9 +1056,10 @@ using namespace grb;
 
 extern "C" {
 
+// tiles, then the item schedule of the persistent kernels ((B + 2) int32, padded to 16 bytes)
 int64_t grb_hstu_bias_tiles_bytes(int64_t B, int64_t max_len) {
   const int64_t NT = (max_len + 127) / 128;
-  return B * (NT * (NT + 1) / 2) * SH_TILE_SLOT;
+  return B * (NT * (NT + 1) / 2) * SH_TILE_SLOT + ((B + 2) * 4 + 15) / 16 * 16;
 }
 
 int grb_hstu_bias_tiles(const void* offsets, int index_bits, int64_t B, int64_t N, int64_t max_len,
@@ -915,6 +1075,10 @@ int grb_hstu_bias_tiles(const void* offsets, int index_bits, int64_t B, int64_t 
   if (B == 0 || NT == 0) return GRB_OK;
   dim3 grid((unsigned) (NT * (NT + 1)), (unsigned) B);   // (slot, orientation) x sequence
   auto st = reinterpret_cast<cudaStream_t>(stream);
+  hstu_short_schedule_kernel<<<1, 1024, 0, st>>>(
+      offsets, index_bits, (int) B, N,
+      reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(tiles) + B * (NT * (NT + 1) / 2) * SH_TILE_SLOT));
+  GRB_LAUNCH_OK();
   if (bucket_cache) {
     GRB_REQUIRE(ts_w && pos_w && num_buckets > 0 && num_buckets <= 255, GRB_ERR_INVALID_ARG,
                 "bias_tiles: ts_w / pos_w / num_buckets");

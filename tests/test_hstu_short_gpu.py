@@ -155,7 +155,10 @@ def test_bias_tiles_match_the_reference_bias():
     off, ts = c["off"].to(DEV), c["ts"].to(DEV)
     cache = GF.hstu_bucket_cache(off, ts, _thr(), N)
     tiles = GF.hstu_bias_tiles(off, N, N, cache, c["ts_w"].to(DEV), c["pos_w"].to(DEV), 128)
-    t = tiles.cpu().view(torch.float16).view(len(lengths), 3, 2, 16, 128, 8).float()
+    n_tile_bytes = len(lengths) * 3 * 65536          # the item schedule of the kernels follows the tiles
+    t = tiles[:n_tile_bytes].cpu().view(torch.float16).view(len(lengths), 3, 2, 16, 128, 8).float()
+    sched = tiles[n_tile_bytes:n_tile_bytes + 4 * (len(lengths) + 2)].cpu().view(torch.int32)
+    assert sched[0] == 4 and sched[1] == 2 and sorted(sched[2:4].tolist()) == [0, 1] and sorted(sched[4:6].tolist()) == [2, 3]
     bias = O.rel_bias(c["ts"], c["ts_w"], c["pos_w"], N, 128)           # (B, N, N)
     for b, n in enumerate(lengths):
         for slot, (iq, jk) in enumerate([(0, 0), (1, 0), (1, 1)]):
