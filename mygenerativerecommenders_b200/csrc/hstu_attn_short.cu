@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_fwd_kernel(
   const int G = (int) gridDim.x, cta = (int) blockIdx.x;
   if (cta >= n_items) return;
   const int* order = p.sched + 2;
-  const int tl_id = cta < SH_TL_CTAS ? cta : 1 << 20;
+  const int tl_id = cta < 32 ? cta : (cta >= G - 32 ? 32 + cta - (G - 32) : 1 << 20);   // first and last 32 CTAs
   SH_STAMP(tid == 0, 0);
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bars);
@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_bwd_kernel(
   const int G = (int) gridDim.x, cta = (int) blockIdx.x;
   if (cta >= n_items) return;
   const int* order = p.sched + 2;
-  const int tl_id = cta < SH_TL_CTAS ? cta : 1 << 20;
+  const int tl_id = cta < 32 ? cta : (cta >= G - 32 ? 32 + cta - (G - 32) : 1 << 20);   // first and last 32 CTAs
   SH_STAMP(tid == 0, 0);
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bars);

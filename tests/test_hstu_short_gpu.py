@@ -113,7 +113,8 @@ def test_short_kernels_agree_with_the_long_sequence_kernels(N, H, lengths, monke
 
 def test_short_kernels_are_deterministic_in_q_k_v_and_stable_under_repeats():
     """Race hunting without a sanitizer: dq/dk/dv/out have no atomics, so repeated launches over
-    ragged random batches must be bit-identical; the bias gradients (fp32 atomics) within 1e-3."""
+    ragged random batches must be bit-identical; the bias gradients (heads summed in bf16 by bulk
+    reduce-adds in arrival order, then fp32 atomics) within 5e-3."""
     gen = torch.Generator().manual_seed(5)
     for trial in range(10):
         H = [1, 2, 4][trial % 3]
@@ -130,7 +131,7 @@ def test_short_kernels_are_deterministic_in_q_k_v_and_stable_under_repeats():
             for idx in range(4):
                 assert torch.equal(runs[0][idx], other[idx]), (trial, idx)
             for idx in (4, 5):
-                _close(other[idx], runs[0][idx], 1e-3, 1e-3, "bias grads repeat")
+                _close(other[idx], runs[0][idx], 5e-3, 5e-3, "bias grads repeat")
         assert all(torch.isfinite(t).all() for t in runs[0])
 
 
