@@ -123,16 +123,17 @@ typedef struct grb_hstu_attn_args {
    * launch of a step.  bucket_cache_max_len = the max_len it was built with. */
   const uint8_t* bucket_cache;
   int64_t bucket_cache_max_len;
-  /* optional, short sequences (max_len <= 256): grb_hstu_bias_tiles output for THIS layer's ts_w /
-   * pos_w (fp16 bias/2 with the causal and length masks folded in).  When set (together with
-   * bucket_cache if there are timestamps) the launch takes the short-sequence kernels
-   * (csrc/hstu_attn_short.cu): two CTAs per SM, one CTA per (sequence, head).  Backward with
-   * max_len > 128 also needs dq_accum (T, H*dqk) fp32 as plain scratch (no zero fill). */
-  const void* bias_tiles;
-  int64_t bias_tiles_max_len;
-  /* short-sequence backward with timestamps: grb_hstu_bias_tiles_bytes(B, max_len) / 2 bytes,
-   * ZERO-FILLED by the caller: the kernel sums every head's bf16 dS^T tiles into it (bulk
-   * reduce-add) and bins them into d_ts_w / d_pos_w with one small kernel afterwards. */
+  /* optional, short sequences (max_len <= 256): the item schedule of this batch
+   * (grb_hstu_short_schedule).  When set, together with a MASKED bucket cache
+   * (grb_hstu_bucket_tiles_masked; needed with or without timestamps), the launch takes the
+   * short-sequence kernels (csrc/hstu_attn_short.cu): persistent, two CTAs per SM, one work item per
+   * (sequence, head).  Backward with max_len > 128 also needs dq_accum (T, H*dqk) fp32 as plain
+   * scratch (no zero fill). */
+  const int32_t* short_schedule;
+  int32_t bucket_cache_masked;    /* bucket_cache came from grb_hstu_bucket_tiles_masked */
+  /* short-sequence backward with timestamps: grb_hstu_bucket_cache_bytes(B, max_len) bytes, ZERO on
+   * entry and zero again on return: the kernel sums every head's bf16 dS^T tiles into it (bulk
+   * reduce-add), a second kernel bins them into copy 0 of d_ts_w / d_pos_w and clears them. */
   void* dbias_acc;
 } grb_hstu_attn_args;
 
@@ -151,15 +152,18 @@ int grb_hstu_bucket_tiles(const void* offsets, int index_bits, const int64_t* ti
                           int64_t N, int64_t max_len, const int64_t* thresholds, int32_t num_buckets,
                           const uint32_t* octaves, void* cache, grb_stream_t stream);
 
-/* Bias tiles of one layer for the short-sequence attention (hstu.py:96-128 evaluated once per
- * layer instead of once per head and direction): for every causal 128x128 tile of every sequence,
- * fp16 (pos_w[N-1+j-i] + ts_w[bucket(i,j)]) / 2 in a query-major and a key-major copy, masked pairs
- * (j > i or i >= n_b) = -15000.  bucket_cache == NULL: no relative bias (masks only).
- * tiles must hold grb_hstu_bias_tiles_bytes(B, max_len) bytes; max_len <= 256. */
-int64_t grb_hstu_bias_tiles_bytes(int64_t B, int64_t max_len);
-int grb_hstu_bias_tiles(const void* offsets, int index_bits, int64_t B, int64_t N, int64_t max_len,
-                        const uint8_t* bucket_cache, int64_t bucket_cache_max_len, const float* ts_w,
-                        int32_t num_buckets, const float* pos_w, void* tiles, grb_stream_t stream);
+/* Short-sequence attention (max_len <= 256), per batch:
+ *   grb_hstu_bucket_tiles_masked: as grb_hstu_bucket_tiles, but pairs outside the causal triangle or
+ *     past the end of the sequence hold 255 (the kernels map it to a bias of -15000, where the
+ *     approximate tanh saturates, so masked scores contribute exact zeros); timestamps == NULL gives
+ *     mask-only tiles (valid pairs 0).  num_buckets <= 254.
+ *   grb_hstu_short_schedule: schedule (B + 2) int32: [0] = sequences with n > 0, [1] = of those with
+ *     n > 128, [2..] their indices, the n > 128 ones first: the item order of the persistent kernels. */
+int grb_hstu_bucket_tiles_masked(const void* offsets, int index_bits, const int64_t* timestamps, int64_t B,
+                                 int64_t N, int64_t max_len, const int64_t* thresholds, int32_t num_buckets,
+                                 const uint32_t* octaves, void* cache, grb_stream_t stream);
+int grb_hstu_short_schedule(const void* offsets, int index_bits, int64_t B, int64_t N, int32_t* schedule,
+                            grb_stream_t stream);
 
 int grb_hstu_attn_fwd(const grb_hstu_attn_args* a, grb_stream_t stream);
 int grb_hstu_attn_bwd(const grb_hstu_attn_args* a, grb_stream_t stream);

@@ -41,7 +41,7 @@ class HstuAttnArgs(C.Structure):
         ("lddq", c_i64), ("lddk", c_i64), ("lddv", c_i64),
         ("dq_accum", c_vp), ("d_ts_w", c_vp), ("d_pos_w", c_vp), ("d_bias_copies", c_i32),
         ("bucket_octaves", c_vp), ("bucket_cache", c_vp), ("bucket_cache_max_len", c_i64),
-        ("bias_tiles", c_vp), ("bias_tiles_max_len", c_i64), ("dbias_acc", c_vp),
+        ("short_schedule", c_vp), ("bucket_cache_masked", c_i32), ("dbias_acc", c_vp),
     ]
 
 
@@ -98,8 +98,8 @@ SYMBOLS = {
     "grb_gather_last_rows": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, C.c_int, C.c_int, c_vp]),
     "grb_bucket_octaves": (C.c_int, [c_vp, c_i32, c_vp]),
     "grb_hstu_bucket_cache_bytes": (c_i64, [c_i64, c_i64]),
-    "grb_hstu_bias_tiles_bytes": (c_i64, [c_i64, c_i64]),
-    "grb_hstu_bias_tiles": (C.c_int, [c_vp, C.c_int, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp]),
+    "grb_hstu_bucket_tiles_masked": (C.c_int, [c_vp, C.c_int, c_vp, c_i64, c_i64, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp]),
+    "grb_hstu_short_schedule": (C.c_int, [c_vp, C.c_int, c_i64, c_i64, c_vp, c_vp]),
     "grb_hstu_bucket_tiles": (C.c_int, [c_vp, C.c_int, c_vp, c_i64, c_i64, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp]),
     "grb_hstu_attn_fwd": (C.c_int, [C.POINTER(HstuAttnArgs), c_vp]),
     "grb_hstu_attn_bwd": (C.c_int, [C.POINTER(HstuAttnArgs), c_vp]),

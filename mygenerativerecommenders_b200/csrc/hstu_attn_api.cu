@@ -31,11 +31,13 @@ int grb_hstu_attn_fwd(const grb_hstu_attn_args* a, grb_stream_t stream) {
   int rc = check_attn_args(a, false);
   if (rc != GRB_OK) return rc;
   GRB_REQUIRE(a->B <= 65535 && a->H <= 65535, GRB_ERR_UNSUPPORTED, "hstu_attn: B,H <= 65535");
+  GRB_REQUIRE(a->short_schedule || !a->bucket_cache_masked, GRB_ERR_INVALID_ARG,
+              "hstu_attn: a masked bucket cache only serves the short-sequence kernels (short_schedule is null)");
   auto st = reinterpret_cast<cudaStream_t>(stream);
-  if (a->bias_tiles) {   // the caller asked for the short-sequence kernels: take them or say why not
+  if (a->short_schedule) {   // the caller asked for the short-sequence kernels: take them or say why not
     GRB_REQUIRE(hstu_attn_short_usable(a, false), GRB_ERR_UNSUPPORTED,
-                "hstu_attn_fwd: bias_tiles given but the short-sequence path does not apply (bf16, head "
-                "dims 64, max_len <= 256 = the tiles' max_len, 16-byte aligned rows, bucket_cache with timestamps)");
+                "hstu_attn_fwd: short_schedule given but the short-sequence path does not apply (bf16, head "
+                "dims 64, max_len <= 256, 16-byte aligned rows, masked bucket_cache built for max_len)");
     return hstu_attn_short_fwd(a, st);
   }
   if (!force_cuda_core() && hstu_attn_fwd_sm100_supported(a)) {
@@ -53,11 +55,11 @@ int grb_hstu_attn_bwd(const grb_hstu_attn_args* a, grb_stream_t stream) {
   if (rc != GRB_OK) return rc;
   GRB_REQUIRE(a->B <= 65535 && a->H <= 65535, GRB_ERR_UNSUPPORTED, "hstu_attn: B,H <= 65535");
   auto st = reinterpret_cast<cudaStream_t>(stream);
-  if (a->bias_tiles) {
+  if (a->short_schedule) {
     GRB_REQUIRE(hstu_attn_short_usable(a, true), GRB_ERR_UNSUPPORTED,
-                "hstu_attn_bwd: bias_tiles given but the short-sequence path does not apply (bf16, head "
-                "dims 64, max_len <= 256 = the tiles' max_len, 16-byte aligned rows, bucket_cache with "
-                "timestamps, dq_accum scratch when max_len > 128)");
+                "hstu_attn_bwd: short_schedule given but the short-sequence path does not apply (bf16, head "
+                "dims 64, max_len <= 256, 16-byte aligned rows, masked bucket_cache built for max_len, dbias_acc "
+                "with timestamps, dq_accum scratch when max_len > 128)");
     return hstu_attn_short_bwd(a, st);
   }
   if (!force_cuda_core() && hstu_attn_bwd_sm100_supported(a)) return hstu_attn_bwd_sm100(a, st);

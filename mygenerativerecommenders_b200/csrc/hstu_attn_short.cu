@@ -12,15 +12,14 @@
 // resident per SM (256 TMEM columns, < 100 KiB of shared memory, 320 threads), so one CTA's
 // epilogue overlaps the other's loads and MMAs, and the per-element work is cut:
 //
-//   * bias tiles: bias/2 = (pos_w[N-1+j-i] + ts_w[bucket(i,j)]) / 2 is tabulated ONCE per layer
-//     and (sequence, tile) as fp16 (grb_hstu_bias_tiles, from the per-batch bucket tiles), in both
-//     orientations, laid out so that a thread fetches 8 consecutive values with one coalesced
-//     16-byte load.  Every head, forward and backward, reads it instead of re-deriving it
-//     (bucket byte -> ts_w lookup -> pos window -> add: ~5 instructions per score element).
-//   * the causal and length masks live IN the bias tile: masked pairs hold -15000, and
+//   * the causal and length masks live IN the per-batch bucket tiles (grb_hstu_bucket_tiles_masked):
+//     a masked pair holds bucket 255, which the kernels' ts_w table maps to a bias of -15000;
 //     tanh.approx saturates to exactly -1 there (benchmarks/probes/tanh_sat_probe.cu: exact for
 //     every x <= -8, f32 and f16x2), so P = h + h tanh(h) and dS = dP (1+t + h (1-t^2)) are exactly
-//     0 without a single compare or select in the epilogue.
+//     0 without a single compare or select in the epilogue.  The bias itself is two shared-memory
+//     lookups per element (ts_w[bucket], pos_w by distance; tables staged once per persistent CTA).
+//     (A first version tabulated fp16 bias tiles per layer with an extra kernel: 26 us per layer
+//     for the kernel and 25 MB of tiles, more than it saved in the epilogues.)
 //   * backward: one CTA owns a whole (sequence, head): dQ of a query tile is complete inside the
 //     CTA, so there is no fp32 dQ accumulator to zero, no bulk reduce-add and no conversion pass
 //     (for 128 < n <= 256 the partial dQ of query tile 1 makes one plain fp32 round trip through
@@ -41,7 +40,6 @@ namespace {
 
 constexpr int SH_THREADS = 320;                 // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int SH_EPI_WARPS = 8;
-constexpr int SH_TILE_SLOT = 65536;             // bias tile slot: 32 KiB per orientation
 constexpr float SH_MASK = -15000.f;             // pre-halved bias of a masked pair
 
 // developer probe: globaltimer stamps (ns) of the first SH_TL_CTAS CTAs that do work, 32 slots each
@@ -104,86 +102,6 @@ __device__ __forceinline__ void add_bf16_pair(float& acc_lo, float& acc_hi, uint
 }
 
 // ------------------------------------------------------------------------------------------------
-// bias tiles
-// ------------------------------------------------------------------------------------------------
-// Slot t(iq, jk) = iq (iq + 1) / 2 + jk of sequence b (TPS slots per sequence), 64 KiB:
-//   [0, 32K)   Q orientation: fp16 at byte ((c / 8) * 128 + r) * 16 + (c % 8) * 2   r = query row
-//   [32K, 64K) K orientation: fp16 at byte ((r / 8) * 128 + c) * 16 + (r % 8) * 2   c = key row
-// value = 0.5 * (pos_w[N-1+j-i] + ts_w[bucket(i, j)]) for j <= i < n, SH_MASK otherwise.
-// One CTA of 128 threads per (orientation, slot, sequence): thread = row of its orientation, 128
-// entries each, 8 per 16-byte store.  pos_w (pre-halved, the 255 diagonals of this tile) and ts_w
-// are staged in shared memory; the valid range of a row is an interval, so masking is two compares.
-template <bool HAS_TS>
-__global__ void __launch_bounds__(128) hstu_bias_tiles_kernel(
-    const void* __restrict__ offsets, int index_bits, int64_t N, int NT,
-    const uint8_t* __restrict__ bcache, int cache_nt, const float* __restrict__ ts_w, int nb,
-    const float* __restrict__ pos_w, uint8_t* __restrict__ tiles) {
-  __shared__ float tsw[256];
-  __shared__ float posd[256];            // posd[x] = 0.5 * pos_w[N-1 + (j0 - i0) + x - 127], x = c_key - r_query + 127
-  const int b = blockIdx.y, slot = blockIdx.x >> 1, orient = blockIdx.x & 1;
-  const int iq = slot == 0 ? 0 : 1, jk = slot == 2 ? 1 : 0;     // NT <= 2: slots (0,0) (1,0) (1,1)
-  const int64_t off0 = load_index(offsets, b, index_bits);
-  int64_t n64 = load_index(offsets, b + 1, index_bits) - off0;
-  if (n64 > N) n64 = N;
-  const int n = (int) n64;
-  if (iq * 128 >= n) return;
-  const int rr = threadIdx.x;
-  if (HAS_TS) {
-    for (int x = rr; x < 256; x += 128) {
-      tsw[x] = x <= nb ? 0.5f * ts_w[x] : 0.f;
-      const int64_t idx = N - 1 + (int64_t) (jk - iq) * 128 + x - 127;
-      posd[x] = (idx >= 0 && idx < 2 * N - 1) ? 0.5f * pos_w[idx] : 0.f;
-    }
-    __syncthreads();
-  }
-  const int TPS = NT * (NT + 1) / 2;
-  uint8_t* dst = tiles + ((int64_t) b * TPS + slot) * SH_TILE_SLOT + orient * 32768;
-  const uint8_t* bkt = nullptr;
-  if (HAS_TS) {
-    const int64_t ctps = (int64_t) cache_nt * (cache_nt + 1) / 2;
-    bkt = bcache + ((int64_t) b * ctps + slot) * 32768 + orient * 16384;
-  }
-  // valid entries e (index along the other dimension) of this row: lo <= e < hi
-  //   orient 0 (row = query i = i0 + rr): keys j = j0 + e <= i, i < n
-  //   orient 1 (row = key   j = j0 + rr): queries i = i0 + e >= j, i < n
-  const int i0 = iq * 128, j0 = jk * 128;
-  int lo, hi;
-  if (orient == 0) { lo = 0; hi = (i0 + rr < n) ? (i0 + rr - j0 + 1) : 0; }
-  else { lo = j0 + rr - i0; hi = n - i0; }
-  lo = lo < 0 ? 0 : lo;
-  hi = hi > 128 ? 128 : hi;
-  // diagonal index x = c_key - r_query + 127: orient 0: e - rr + 127 ; orient 1: rr - e + 127
-  const int xs = orient == 0 ? 1 : -1;
-  const int x0 = orient == 0 ? 127 - rr : 127 + rr;
-  const uint32_t hmask = 0xF353u;                    // fp16(-15000)
-#pragma unroll 2
-  for (int ch = 0; ch < 8; ++ch) {      // 16 entries per step
-    uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-    if (HAS_TS) raw = *reinterpret_cast<const uint4*>(bkt + ((size_t) ch * 128 + rr) * 16);
-    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-    uint32_t outw[8];
-#pragma unroll
-    for (int e2 = 0; e2 < 8; ++e2) {
-      uint32_t pair = 0u;
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int e = ch * 16 + 2 * e2 + t;
-        float v = 0.f;
-        if (HAS_TS) {
-          const uint32_t bk = (w[(2 * e2 + t) >> 2] >> (8 * ((2 * e2 + t) & 3))) & 0xffu;
-          v = posd[x0 + xs * e] + tsw[bk];
-        }
-        const uint32_t hv = (e >= lo && e < hi) ? (uint32_t) __half_as_ushort(__float2half_rn(v)) : hmask;
-        pair |= hv << (16 * t);
-      }
-      outw[e2] = pair;
-    }
-    *reinterpret_cast<uint4*>(dst + ((size_t) (ch * 2) * 128 + rr) * 16) = make_uint4(outw[0], outw[1], outw[2], outw[3]);
-    *reinterpret_cast<uint4*>(dst + ((size_t) (ch * 2 + 1) * 128 + rr) * 16) = make_uint4(outw[4], outw[5], outw[6], outw[7]);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // bias gradients from the head-summed dS^T tiles
 // ------------------------------------------------------------------------------------------------
 // The backward kernel adds every (sequence, head)'s bf16 dS'^T blocks into one accumulation tile per
@@ -193,18 +111,12 @@ __global__ void __launch_bounds__(128) hstu_bias_tiles_kernel(
 // key rows (the bucket is a step function of the query position for a fixed key).
 // Tile layout (what the backward wrote): [hf 0..1][key row 128][64 queries] bf16, 16-byte chunk c of
 // a row stored at chunk c ^ (row & 7).
-__device__ __forceinline__ void red_add_f32_pred(float* addr, float v, bool p) {
-  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q red.global.add.f32 [%0], %1;\n\t}" ::"l"(addr),
-               "f"(v), "r"((int) p)
-               : "memory");
-}
-
 __global__ void __launch_bounds__(256) hstu_bias_grad_kernel(
     const void* __restrict__ offsets, int index_bits, int64_t N, int NT, const uint8_t* __restrict__ bcache,
-    const uint8_t* __restrict__ dbias, int nb, float* __restrict__ d_ts_w, float* __restrict__ d_pos_w,
-    int copies, float scale) {
+    uint8_t* __restrict__ dbias, int nb, float* __restrict__ d_ts_w, float* __restrict__ d_pos_w, float scale) {
   constexpr int PITCH = 130;                                  // bf16 elements per staged row
   __shared__ __align__(16) __nv_bfloat16 tile[128 * PITCH];
+  __shared__ float hist[256];
   const int b = blockIdx.y, slot = blockIdx.x;
   const int iq = slot == 0 ? 0 : 1, jk = slot == 2 ? 1 : 0;
   const int64_t off0 = load_index(offsets, b, index_bits);
@@ -214,19 +126,19 @@ __global__ void __launch_bounds__(256) hstu_bias_grad_kernel(
   if (iq * 128 >= n) return;
   const int tid = threadIdx.x;
   const int TPS = NT * (NT + 1) / 2;
-  const uint8_t* src = dbias + ((int64_t) b * TPS + slot) * 32768;
-  // stage the tile un-swizzled: smem[key row][query 0..127]
+  uint8_t* src = dbias + ((int64_t) b * TPS + slot) * 32768;
+  hist[tid] = 0.f;
+  // stage the tile un-swizzled: smem[key row][query 0..127]; the accumulation tile is handed back
+  // zeroed (the caller allocates it once, zero-filled, and every launch leaves it that way)
   for (int g = tid; g < 2048; g += 256) {
     const int hf = g >> 10, row = (g >> 3) & 127, pos = g & 7;
     const int chunk = pos ^ (row & 7);
     const uint4 v = *reinterpret_cast<const uint4*>(src + (size_t) g * 16);
+    *reinterpret_cast<uint4*>(src + (size_t) g * 16) = make_uint4(0u, 0u, 0u, 0u);
     uint32_t* d = reinterpret_cast<uint32_t*>(tile + row * PITCH + hf * 64 + chunk * 8);
     d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
   }
   __syncthreads();
-  const int64_t copy = (blockIdx.x + gridDim.x * blockIdx.y) % (unsigned) copies;
-  float* d_pos_mine = d_pos_w + copy * (2 * N - 1);
-  float* d_ts_mine = d_ts_w + copy * (nb + 1);
   // diagonals: thread t sums x = c - r + 127 = t  (c = query column, r = key row)
   if (tid < 255) {
     float acc = 0.f;
@@ -234,13 +146,12 @@ __global__ void __launch_bounds__(256) hstu_bias_grad_kernel(
     for (int r = rlo; r < rhi; ++r) acc += __bfloat162float(tile[r * PITCH + (tid - 127 + r)]);
     // pos_w index N-1 + j - i = N-1 + (j0 + r) - (i0 + c) = N-1 + j0 - i0 - (tid - 127)
     const int64_t idx = N - 1 + (int64_t) (jk - iq) * 128 - (tid - 127);
-    if (acc != 0.f && idx >= 0 && idx < 2 * N - 1) atomicAdd(d_pos_mine + idx, acc * scale);
+    if (acc != 0.f && idx >= 0 && idx < 2 * N - 1) atomicAdd(d_pos_w + idx, acc * scale);
   }
-  // time buckets: thread = key row, walk the query columns
+  // time buckets: thread = key row, walk the query columns; bucket 255 = masked pair (value 0)
   if (tid < 128) {
-    const int64_t ctps = (int64_t) NT * (NT + 1) / 2;
-    const uint8_t* bkt = bcache + ((int64_t) b * ctps + slot) * 32768 + 16384;   // K orientation
-    int run_bk = -1;
+    const uint8_t* bkt = bcache + ((int64_t) b * TPS + slot) * 32768 + 16384;   // K orientation
+    int run_bk = 255;
     float run_acc = 0.f;
 #pragma unroll 1
     for (int ch = 0; ch < 8; ++ch) {
@@ -250,14 +161,18 @@ __global__ void __launch_bounds__(256) hstu_bias_grad_kernel(
       for (int e = 0; e < 16; ++e) {
         const int bk = (int) ((w[e >> 2] >> (8 * (e & 3))) & 0xffu);
         const float v = __bfloat162float(tile[tid * PITCH + ch * 16 + e]);
-        const bool chg = bk != run_bk;
-        red_add_f32_pred(d_ts_mine + (run_bk < 0 ? 0 : run_bk), run_acc * scale, chg && run_bk >= 0 && run_acc != 0.f);
-        run_acc = (chg ? 0.f : run_acc) + v;
-        run_bk = bk;
+        if (bk != run_bk) {
+          if (run_bk != 255 && run_acc != 0.f) atomicAdd(&hist[run_bk], run_acc);
+          run_acc = 0.f;
+          run_bk = bk;
+        }
+        run_acc += v;
       }
     }
-    red_add_f32_pred(d_ts_mine + (run_bk < 0 ? 0 : run_bk), run_acc * scale, run_bk >= 0 && run_acc != 0.f);
+    if (run_bk != 255 && run_acc != 0.f) atomicAdd(&hist[run_bk], run_acc);
   }
+  __syncthreads();
+  if (tid <= nb && hist[tid] != 0.f) atomicAdd(d_ts_w + tid, hist[tid] * scale);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -269,6 +184,19 @@ __global__ void __launch_bounds__(256) hstu_bias_grad_kernel(
 // profiles/r2_short_attn_timeline_v1.txt.)  The item order comes from a per-batch schedule written
 // behind the bias tiles (hstu_short_schedule_kernel): sequences of three units first, then those of
 // one; CTA c takes items c, 2G-1-c, 2G+c, ... (snake order), so the heavy items are spread evenly.
+// bias tables of one layer, staged once per (persistent) CTA.  tsw[b] = ts_w[b] / 2, tsw[255] = the
+// mask; pos[256 + d] = pos_w[N-1-d] / 2 for the causal distances d = i - j in [0, N), 0 elsewhere.
+__device__ __forceinline__ void stage_bias_tables(float* tsw, float* pos, const float* __restrict__ ts_w,
+                                                  const float* __restrict__ pos_w, int nb, int64_t N,
+                                                  int tid, int nthreads) {
+  for (int i = tid; i < 256; i += nthreads)
+    tsw[i] = i == 255 ? SH_MASK : ((ts_w && i <= nb) ? 0.5f * ts_w[i] : 0.f);
+  for (int x = tid; x < 512; x += nthreads) {
+    const int d = x - 256;
+    pos[x] = (pos_w && d >= 0 && d < N) ? 0.5f * pos_w[N - 1 - d] : 0.f;
+  }
+}
+
 struct ItemIter {
   int r, G, c, n_items;
   __device__ ItemIter(int G_, int c_, int n_items_) : r(-1), G(G_), c(c_), n_items(n_items_) {}
@@ -338,15 +266,20 @@ struct ShortFwdParams {
   int B, H, index_bits, tps;
   long long* tl;            // developer probe (GRB_SHORT_TIMELINE=1)
   const void* offsets;
-  const uint8_t* tiles;
+  const uint8_t* bcache;    // masked bucket tiles (grb_hstu_bucket_tiles_masked), 32 KiB per slot
   const int* sched;
+  const float* ts_w;        // (nb + 1) or nullptr (no relative bias)
+  const float* pos_w;       // (2N - 1) or nullptr
+  int nb;
   __nv_bfloat16* out;
   int64_t ldo;
 };
 
 struct SfSmem {
   static constexpr int ring = 0;                                   // 2 x (Q, K, V)
-  static constexpr int bars = ring + 2 * 3 * AT_TILE_BYTES;
+  static constexpr int tsw = ring + 2 * 3 * AT_TILE_BYTES;         // 256 floats: ts_w / 2, [255] = mask
+  static constexpr int pos = tsw + 256 * 4;                        // 512 floats: pos[256 + (i - j)] = pos_w[N-1-(i-j)] / 2
+  static constexpr int bars = pos + 512 * 4;
   static constexpr int total = bars + 128;
 };
 
@@ -381,6 +314,9 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_fwd_kernel(
     prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV);
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 256);
+  if (warp >= 2)
+    stage_bias_tables(reinterpret_cast<float*>(smem + L::tsw), reinterpret_cast<float*>(smem + L::pos), p.ts_w,
+                      p.pos_w, p.nb, p.N, tid - 64, SH_THREADS - 64);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -453,6 +389,8 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_fwd_kernel(
     const uint32_t lane_base = (uint32_t) (wq * 32) << 16;
     const uint32_t half_half = 0x38003800u;           // (0.5h, 0.5h)
     const float inv_n = 1.0f / (float) p.N;
+    const float* tsw_s = reinterpret_cast<const float*>(smem + L::tsw);
+    const float* pos_s = reinterpret_cast<const float*>(smem + L::pos);
     // O of a finished query tile, stored at the start of the next unit
     bool pend = false;
     int pend_valid = 0;
@@ -484,18 +422,18 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_fwd_kernel(
         const int qt = u >= 1, kt = u == 2;
         const int rows_valid = it.n - qt * AT_BM;        // > 0
         const int cols_valid = it.n - kt * AT_BN;        // > 0 (may exceed 128)
-        const uint8_t* tile = p.tiles + ((int64_t) it.seq * p.tps + u) * SH_TILE_SLOT;   // slot index == u
+        const uint8_t* bkt = p.bcache + ((int64_t) it.seq * p.tps + u) * 32768;   // slot index == u, Q orientation
+        // distance i - j of (this row, column c) = dist0 - c
+        const float* pos_r = pos_s + 256 + (qt - kt) * AT_BM + r;
         // which of this thread's four 16-column blocks have any unmasked pair in the warp's 32 rows
         bool live[4];
-        uint4 hb[4][2];
+        uint4 bq[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int c0 = 64 * g + 16 * c;
           live[c] = (32 * wq < rows_valid) && (c0 < cols_valid) && (qt != kt || c0 <= 32 * wq + 31);
-          if (live[c]) {   // bias/2 of columns c0 .. c0+15 of this row: two 16-byte chunks
-            hb[c][0] = ldg_nc_v4(tile + ((size_t) (c0 >> 3) * 128 + r) * 16);
-            hb[c][1] = ldg_nc_v4(tile + ((size_t) ((c0 >> 3) + 1) * 128 + r) * 16);
-          }
+          if (live[c])   // bucket bytes of columns c0 .. c0+15 of this row (255 = masked pair)
+            bq[c] = ldg_nc_v4(bkt + ((size_t) (c0 >> 4) * 128 + r) * 16);
         }
         mbar_wait_g(bar_s_full, gu & 1);
         tc_fence_after();
@@ -511,13 +449,16 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_fwd_kernel(
             uint32_t sv[16];
             tmem_ld16(tmem + lane_base + c0, sv);
             tmem_ld_wait();
-            const uint32_t hbw[8] = {hb[c][0].x, hb[c][0].y, hb[c][0].z, hb[c][0].w,
-                                     hb[c][1].x, hb[c][1].y, hb[c][1].z, hb[c][1].w};
+            const uint32_t bw[4] = {bq[c].x, bq[c].y, bq[c].z, bq[c].w};
 #pragma unroll
             for (int e2 = 0; e2 < 8; ++e2) {
+              // bias / 2 of the pair: ts_w[bucket] / 2 + pos_w[N-1+j-i] / 2
+              const float b0 = tsw_s[(bw[e2 >> 1] >> (16 * (e2 & 1))) & 0xffu] + pos_r[-(c0 + 2 * e2)];
+              const float b1 = tsw_s[(bw[e2 >> 1] >> (16 * (e2 & 1) + 8)) & 0xffu] + pos_r[-(c0 + 2 * e2 + 1)];
+              const uint32_t hb2 = pack_f16x2(b0, b1);
               const uint32_t s2 = pack_f16x2(__uint_as_float(sv[2 * e2]), __uint_as_float(sv[2 * e2 + 1]));
               uint32_t h2, p2;
-              asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(h2) : "r"(s2), "r"(half_half), "r"(hbw[e2]));
+              asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(h2) : "r"(s2), "r"(half_half), "r"(hb2));
               const uint32_t t2 = tanh_approx_f16x2(h2);
               asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(p2) : "r"(h2), "r"(t2));
               const float2 pf = __half22float2(*reinterpret_cast<const __half2*>(&p2));
@@ -564,8 +505,11 @@ struct ShortBwdParams {
   int B, H, index_bits, tps;
   long long* tl;
   const void* offsets;
-  const uint8_t* tiles;
+  const uint8_t* bcache;
   const int* sched;
+  const float* ts_w;
+  const float* pos_w;
+  int nb;
   __nv_bfloat16* dq; int64_t lddq;
   __nv_bfloat16* dk; int64_t lddk;
   __nv_bfloat16* dv; int64_t lddv;
@@ -579,7 +523,9 @@ struct SbSmem {
   static constexpr int q = v + AT_TILE_BYTES;
   static constexpr int dout = q + AT_TILE_BYTES;
   static constexpr int dsT = dout + AT_TILE_BYTES;                 // blocks A, B: [128 k][64 q] bf16
-  static constexpr int bars = dsT + 2 * AT_TILE_BYTES;
+  static constexpr int tsw = dsT + 2 * AT_TILE_BYTES;              // as in the forward
+  static constexpr int pos = tsw + 256 * 4;
+  static constexpr int bars = pos + 512 * 4;
   static constexpr int total = bars + 128;
 };
 
@@ -624,6 +570,9 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_bwd_kernel(
     prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV); prefetch_tensormap(&tmdO);
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 256);
+  if (warp >= 2)
+    stage_bias_tables(reinterpret_cast<float*>(smem + L::tsw), reinterpret_cast<float*>(smem + L::pos), p.ts_w,
+                      p.pos_w, p.nb, p.N, tid - 64, SH_THREADS - 64);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -749,6 +698,8 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_bwd_kernel(
     const uint32_t lane_base = (uint32_t) (wq * 32) << 16;
     const float inv_n = 1.0f / (float) p.N;
     const float half_inv_n = 0.5f * inv_n;
+    const float* tsw_s = reinterpret_cast<const float*>(smem + L::tsw);
+    const float* pos_s = reinterpret_cast<const float*>(smem + L::pos);
     uint8_t* dsT_row = smem + L::dsT + r * 128;
     ItemIter iter(G, cta, n_items);
     uint32_t gu = 0, gk = 0;
@@ -763,15 +714,17 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_bwd_kernel(
         const int i0 = qt * AT_BM, j0 = kt * AT_BN;
         const int jk = j0 + r;
         const bool last_of_kt = (it.nu == 1) || (u >= 1);
-        const uint8_t* tile = p.tiles + ((int64_t) it.seq * p.tps + u) * SH_TILE_SLOT + 32768;   // K orientation
+        const uint8_t* bkt = p.bcache + ((int64_t) it.seq * p.tps + u) * 32768 + 16384;   // K orientation
+        // distance i - j of (query column c, this key row) = c + dist0
+        const float* pos_r = pos_s + 256 + (qt - kt) * AT_BM - r;
 #pragma unroll 1
         for (int hf = 0; hf < 2; ++hf) {
           const int cb = 64 * hf + 32 * g;               // first query column (in the tile) of this thread
-          // prefetch bias/2 (32 fp16) of this half before the scores arrive
-          uint4 hbv[4];
+          // prefetch the bucket bytes (32) of this half before the scores arrive
+          uint4 bqv[2];
 #pragma unroll
-          for (int c8 = 0; c8 < 4; ++c8)
-            hbv[c8] = ldg_nc_v4(tile + ((size_t) ((cb >> 3) + c8) * 128 + r) * 16);
+          for (int sc = 0; sc < 2; ++sc)
+            bqv[sc] = ldg_nc_v4(bkt + ((size_t) ((cb >> 4) + sc) * 128 + r) * 16);
           mbar_wait_g(bar_s_full + 8 * hf, gu & 1);
           tc_fence_after();
 #pragma unroll
@@ -797,17 +750,17 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_bwd_kernel(
             tmem_ld_wait();
 #pragma unroll
             for (int c8 = 0; c8 < 2; ++c8) {
-              const uint4 hq = hbv[2 * sc + c8];
-              const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w};
+              const uint32_t bw2[2] = {c8 ? bqv[sc].z : bqv[sc].x, c8 ? bqv[sc].w : bqv[sc].y};
               uint32_t ppk[4], dpk[4];
 #pragma unroll
               for (int e2 = 0; e2 < 4; ++e2) {
-                const float2 hb2 = __half22float2(*reinterpret_cast<const __half2*>(&hw[e2]));
                 float pv2[2], ds2[2];
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
                   const int cc = 8 * c8 + 2 * e2 + t;
-                  const float hx = fmaf(__uint_as_float(sv[cc]), 0.5f, t ? hb2.y : hb2.x);
+                  // bias / 2 = ts_w[bucket] / 2 + pos_w[N-1+j-i] / 2 ; bucket 255 (masked) -> -15000
+                  const float hb = tsw_s[(bw2[e2 >> 1] >> (16 * (e2 & 1) + 8 * t)) & 0xffu] + pos_r[c16 + cc];
+                  const float hx = fmaf(__uint_as_float(sv[cc]), 0.5f, hb);
                   const float th = tanh_approx(hx);
                   // unscaled: P' = SiLU(x) = N P ; dS' = dP * 2 SiLU'(x) = 2N dS (factors applied at the end)
                   pv2[t] = fmaf(hx, th, hx);
@@ -917,14 +870,13 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_bwd_kernel(
 // ---- host side ------------------------------------------------------------------------------
 // Self-contained: any head count (the long-sequence forward wants an even one).
 bool hstu_attn_short_usable(const grb_hstu_attn_args* a, bool bwd) {
-  if (a->bias_tiles == nullptr || a->max_len > 256 || a->bias_tiles_max_len != a->max_len) return false;
+  if (a->short_schedule == nullptr || a->max_len > 256) return false;
   if (a->dtype != GRB_BF16 || a->dqk != AT_D || a->dv != AT_D) return false;
-  if (a->timestamps && (a->bucket_cache == nullptr || a->bucket_cache_max_len != a->max_len ||
-                        a->num_buckets > 255))
-    return false;
-  if ((int64_t) a->B * a->H * 2 >= (1ll << 31) || a->T >= (1ll << 31) || a->T == 0) return false;
+  if (a->bucket_cache == nullptr || !a->bucket_cache_masked || a->bucket_cache_max_len != a->max_len) return false;
+  if (a->timestamps && a->num_buckets > 254) return false;
+  if (a->T >= (1ll << 31) || a->T == 0) return false;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  if (!al16(a->q) || !al16(a->k) || !al16(a->v) || !al16(a->bias_tiles) || !al16(a->bucket_cache)) return false;
+  if (!al16(a->q) || !al16(a->k) || !al16(a->v) || !al16(a->bucket_cache)) return false;
   if ((a->ldq * 2) % 16 || (a->ldk * 2) % 16 || (a->ldv * 2) % 16) return false;
   if (!bwd) {
     if (!al16(a->out) || (a->ldo * 2) % 16) return false;
@@ -968,10 +920,6 @@ static unsigned short_grid(const grb_hstu_attn_args* a) {
   const int64_t slots = 2 * (int64_t) num_sms();
   return (unsigned) (items < slots ? items : slots);
 }
-static const int* short_schedule(const grb_hstu_attn_args* a, int tps) {
-  return reinterpret_cast<const int*>(reinterpret_cast<const uint8_t*>(a->bias_tiles) +
-                                      (int64_t) a->B * tps * SH_TILE_SLOT);
-}
 
 int hstu_attn_short_fwd(const grb_hstu_attn_args* a, cudaStream_t st) {
   if (a->B == 0 || a->max_len == 0) return GRB_OK;
@@ -986,8 +934,10 @@ int hstu_attn_short_fwd(const grb_hstu_attn_args* a, cudaStream_t st) {
   const int NT = (int) ceil_div(a->max_len, AT_BM);
   p.tps = NT * (NT + 1) / 2;
   p.offsets = a->offsets;
-  p.tiles = reinterpret_cast<const uint8_t*>(a->bias_tiles);
-  p.sched = short_schedule(a, p.tps);
+  p.bcache = a->bucket_cache;
+  p.sched = a->short_schedule;
+  p.ts_w = a->timestamps ? a->ts_w : nullptr; p.pos_w = a->timestamps ? a->pos_w : nullptr;
+  p.nb = a->timestamps ? a->num_buckets : 0;
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out); p.ldo = a->ldo;
   const size_t smem = SfSmem::total + 1024;
   auto kern = hstu_attn_short_fwd_kernel;
@@ -1015,8 +965,10 @@ int hstu_attn_short_bwd(const grb_hstu_attn_args* a, cudaStream_t st) {
   const int NT = (int) ceil_div(a->max_len, AT_BM);
   p.tps = NT * (NT + 1) / 2;
   p.offsets = a->offsets;
-  p.tiles = reinterpret_cast<const uint8_t*>(a->bias_tiles);
-  p.sched = short_schedule(a, p.tps);
+  p.bcache = a->bucket_cache;
+  p.sched = a->short_schedule;
+  p.ts_w = a->timestamps ? a->ts_w : nullptr; p.pos_w = a->timestamps ? a->pos_w : nullptr;
+  p.nb = a->timestamps ? a->num_buckets : 0;
   p.dq = reinterpret_cast<__nv_bfloat16*>(a->dq); p.lddq = a->lddq;
   p.dk = reinterpret_cast<__nv_bfloat16*>(a->dk); p.lddk = a->lddk;
   p.dv = reinterpret_cast<__nv_bfloat16*>(a->dv_grad); p.lddv = a->lddv;
@@ -1033,12 +985,10 @@ int hstu_attn_short_bwd(const grb_hstu_attn_args* a, cudaStream_t st) {
     kern<<<items, SH_THREADS, smem, st>>>(tmQ, tmK, tmV, tmdO, p);
     GRB_LAUNCH_OK();
     timeline_dump("bwd", p.tl, st);
-    // bias gradients from the head-summed dS'^T tiles (dS' = 2N dS)
-    const int copies = a->d_bias_copies > 0 ? a->d_bias_copies : 1;
+    // bias gradients from the head-summed dS'^T tiles (dS' = 2N dS), added into copy 0 of d_ts_w / d_pos_w
     dim3 grid((unsigned) p.tps, (unsigned) a->B);
     hstu_bias_grad_kernel<<<grid, 256, 0, st>>>(a->offsets, a->index_bits, a->N, NT, a->bucket_cache, p.dbias,
-                                                a->num_buckets, a->d_ts_w, a->d_pos_w, copies,
-                                                0.5f / (float) a->N);
+                                                a->num_buckets, a->d_ts_w, a->d_pos_w, 0.5f / (float) a->N);
   } else {
     auto kern = hstu_attn_short_bwd_kernel<false>;
     GRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
@@ -1056,40 +1006,14 @@ using namespace grb;
 
 extern "C" {
 
-// tiles, then the item schedule of the persistent kernels ((B + 2) int32, padded to 16 bytes)
-int64_t grb_hstu_bias_tiles_bytes(int64_t B, int64_t max_len) {
-  const int64_t NT = (max_len + 127) / 128;
-  return B * (NT * (NT + 1) / 2) * SH_TILE_SLOT + ((B + 2) * 4 + 15) / 16 * 16;
-}
-
-int grb_hstu_bias_tiles(const void* offsets, int index_bits, int64_t B, int64_t N, int64_t max_len,
-                        const uint8_t* bucket_cache, int64_t bucket_cache_max_len, const float* ts_w,
-                        int32_t num_buckets, const float* pos_w, void* tiles, grb_stream_t stream) {
+int grb_hstu_short_schedule(const void* offsets, int index_bits, int64_t B, int64_t N, int32_t* schedule,
+                            grb_stream_t stream) {
   GRB_REQUIRE(index_bits == 32 || index_bits == 64, GRB_ERR_INVALID_ARG,
-              "bias_tiles: index_bits must be 32 or 64");
-  GRB_REQUIRE(offsets && tiles && B >= 0 && N > 0 && max_len >= 0 && max_len <= N, GRB_ERR_INVALID_ARG,
-              "bias_tiles: bad arguments");
-  GRB_REQUIRE(max_len <= 256, GRB_ERR_UNSUPPORTED, "bias_tiles: the short-sequence path takes max_len <= 256");
-  GRB_REQUIRE(B <= 65535, GRB_ERR_UNSUPPORTED, "bias_tiles: B <= 65535");
-  const int NT = (int) ((max_len + 127) / 128);
-  if (B == 0 || NT == 0) return GRB_OK;
-  dim3 grid((unsigned) (NT * (NT + 1)), (unsigned) B);   // (slot, orientation) x sequence
-  auto st = reinterpret_cast<cudaStream_t>(stream);
-  hstu_short_schedule_kernel<<<1, 1024, 0, st>>>(
-      offsets, index_bits, (int) B, N,
-      reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(tiles) + B * (NT * (NT + 1) / 2) * SH_TILE_SLOT));
-  GRB_LAUNCH_OK();
-  if (bucket_cache) {
-    GRB_REQUIRE(ts_w && pos_w && num_buckets > 0 && num_buckets <= 255, GRB_ERR_INVALID_ARG,
-                "bias_tiles: ts_w / pos_w / num_buckets");
-    GRB_REQUIRE(bucket_cache_max_len == max_len, GRB_ERR_INVALID_ARG,
-                "bias_tiles: the bucket cache was built for another max_len");
-    hstu_bias_tiles_kernel<true><<<grid, 128, 0, st>>>(offsets, index_bits, N, NT, bucket_cache, NT, ts_w,
-                                                       num_buckets, pos_w, reinterpret_cast<uint8_t*>(tiles));
-  } else {
-    hstu_bias_tiles_kernel<false><<<grid, 128, 0, st>>>(offsets, index_bits, N, NT, nullptr, NT, nullptr, 0,
-                                                        nullptr, reinterpret_cast<uint8_t*>(tiles));
-  }
+              "short_schedule: index_bits must be 32 or 64");
+  GRB_REQUIRE(offsets && schedule && B >= 0 && N > 0, GRB_ERR_INVALID_ARG, "short_schedule: bad arguments");
+  GRB_REQUIRE(B <= 65535, GRB_ERR_UNSUPPORTED, "short_schedule: B <= 65535");
+  hstu_short_schedule_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(offsets, index_bits, (int) B, N,
+                                                                                     schedule);
   GRB_LAUNCH_OK();
   return GRB_OK;
 }

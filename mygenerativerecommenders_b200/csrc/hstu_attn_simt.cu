@@ -457,7 +457,7 @@ int check_attn_args(const grb_hstu_attn_args* a, bool bwd) {
   } else {
     GRB_REQUIRE(a->dout && a->dq && a->dk && a->dv_grad, GRB_ERR_INVALID_ARG,
                 "hstu_attn_bwd: dout/dq/dk/dv_grad must be non-null");
-    GRB_REQUIRE(a->dq_accum || (a->bias_tiles && a->max_len <= 128), GRB_ERR_INVALID_ARG,
+    GRB_REQUIRE(a->dq_accum || (a->short_schedule && a->max_len <= 128), GRB_ERR_INVALID_ARG,
                 "hstu_attn_bwd: dq_accum workspace is null");
     if (a->timestamps)
       GRB_REQUIRE(a->d_ts_w && a->d_pos_w, GRB_ERR_INVALID_ARG,

@@ -15,6 +15,11 @@
 
 namespace grb {
 
+// MASKED (the short-sequence attention kernels): pairs outside the causal triangle or past the end
+// of the sequence (j > i or i >= n) hold 255; those kernels map bucket 255 to a bias of -15000, where
+// tanh.approx saturates to exactly -1, so P and dS come out as exact zeros without any compare.
+// With MASKED and ts == nullptr (no relative bias) the valid pairs hold 0.
+template <bool MASKED>
 __global__ void __launch_bounds__(256) hstu_bucket_tiles_kernel(
     const void* __restrict__ offsets, int index_bits, const int64_t* __restrict__ ts, int64_t N,
     const int64_t* __restrict__ thr, int nb, const uint32_t* __restrict__ octaves, int NT,
@@ -34,21 +39,31 @@ __global__ void __launch_bounds__(256) hstu_bucket_tiles_kernel(
   if (n > N) n = N;
   if ((int64_t) iq * 128 >= n) return;
   const int tid = threadIdx.x;
-  if (tid < 32) {
-    if (octaves) load_octave_table(oct, flags, octaves, tid);
-    else build_octave_table(oct, flags, thr, nb, tid);
+  const bool has_ts = ts != nullptr;
+  if (has_ts) {
+    if (tid < 32) {
+      if (octaves) load_octave_table(oct, flags, octaves, tid);
+      else build_octave_table(oct, flags, thr, nb, tid);
+    }
+    if (tid >= 128) tsq[tid - 128] = ext_ts_at(ts, b, N, (int64_t) iq * 128 + (tid - 128) + 1);
+    else tsk[tid] = ext_ts_at(ts, b, N, (int64_t) jk * 128 + tid);
   }
-  if (tid >= 128) tsq[tid - 128] = ext_ts_at(ts, b, N, (int64_t) iq * 128 + (tid - 128) + 1);
-  else tsk[tid] = ext_ts_at(ts, b, N, (int64_t) jk * 128 + tid);
   __syncthreads();
-  const bool slow = flags[0] != 0;
+  const bool slow = has_ts && flags[0] != 0;
   const int TPS = NT * (NT + 1) / 2;
   uint8_t* tile = cache + ((int64_t) b * TPS + slot) * 32768;
   const int orient = tid >> 7;          // 0: thread = query row, 1: thread = key row
   const int rr = tid & 127;
-  const int64_t mine = orient == 0 ? tsq[rr] : tsk[rr];
+  const int64_t mine = has_ts ? (orient == 0 ? tsq[rr] : tsk[rr]) : 0;
   const int64_t* other = orient == 0 ? tsk : tsq;
   uint8_t* dst = tile + orient * 16384;
+  // valid entries of this row (index e along the other dimension): lo <= e < hi
+  int lo = 0, hi = 128;
+  if (MASKED) {
+    const int i0 = iq * 128, j0 = jk * 128;
+    if (orient == 0) { lo = 0; hi = (i0 + rr < (int) n) ? (i0 + rr - j0 + 1) : 0; }   // row = query, e = key
+    else { lo = j0 + rr - i0; hi = (int) n - i0; }                                     // row = key, e = query
+  }
   for (int ch = 0; ch < 8; ++ch) {
     uint32_t w[4];
 #pragma unroll
@@ -56,9 +71,15 @@ __global__ void __launch_bounds__(256) hstu_bucket_tiles_kernel(
       uint32_t word = 0;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        int64_t d = mine - other[ch * 16 + q4 * 4 + e];
-        d = d < 0 ? -d : d;
-        word |= (uint32_t) bucket_wide(oct, thr, nb, slow, d) << (8 * e);
+        const int idx = ch * 16 + q4 * 4 + e;
+        uint32_t bk = 0;
+        if (has_ts) {
+          int64_t d = mine - other[idx];
+          d = d < 0 ? -d : d;
+          bk = (uint32_t) bucket_wide(oct, thr, nb, slow, d);
+        }
+        if (MASKED && !(idx >= lo && idx < hi)) bk = 255u;
+        word |= bk << (8 * e);
       }
       w[q4] = word;
     }
@@ -77,23 +98,44 @@ int64_t grb_hstu_bucket_cache_bytes(int64_t B, int64_t max_len) {
   return B * (NT * (NT + 1) / 2) * 32768;
 }
 
-int grb_hstu_bucket_tiles(const void* offsets, int index_bits, const int64_t* timestamps, int64_t B,
-                          int64_t N, int64_t max_len, const int64_t* thresholds, int32_t num_buckets,
-                          const uint32_t* octaves, void* cache, grb_stream_t stream) {
+static int bucket_tiles_impl(const void* offsets, int index_bits, const int64_t* timestamps, int64_t B,
+                             int64_t N, int64_t max_len, const int64_t* thresholds, int32_t num_buckets,
+                             const uint32_t* octaves, void* cache, bool masked, grb_stream_t stream) {
   GRB_REQUIRE(index_bits == 32 || index_bits == 64, GRB_ERR_INVALID_ARG,
               "bucket_tiles: index_bits must be 32 or 64");
-  GRB_REQUIRE(offsets && timestamps && thresholds && cache && B >= 0 && N > 0 && max_len >= 0 &&
-                  max_len <= N && num_buckets > 0 && num_buckets <= 255,
-              GRB_ERR_INVALID_ARG, "bucket_tiles: bad arguments");
+  GRB_REQUIRE(offsets && cache && B >= 0 && N > 0 && max_len >= 0 && max_len <= N, GRB_ERR_INVALID_ARG,
+              "bucket_tiles: bad arguments");
+  GRB_REQUIRE(masked || timestamps, GRB_ERR_INVALID_ARG, "bucket_tiles: timestamps are null");
+  if (timestamps)
+    GRB_REQUIRE(thresholds && num_buckets > 0 && num_buckets <= (masked ? 254 : 255), GRB_ERR_INVALID_ARG,
+                "bucket_tiles: thresholds / num_buckets");
   GRB_REQUIRE(B <= 65535, GRB_ERR_UNSUPPORTED, "bucket_tiles: B <= 65535");
   const int NT = (int) ((max_len + 127) / 128);
   if (B == 0 || NT == 0) return GRB_OK;
   dim3 grid((unsigned) (NT * (NT + 1) / 2), (unsigned) B);
-  hstu_bucket_tiles_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      offsets, index_bits, timestamps, N, thresholds, num_buckets, octaves, NT,
-      reinterpret_cast<uint8_t*>(cache));
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  if (masked)
+    hstu_bucket_tiles_kernel<true><<<grid, 256, 0, st>>>(offsets, index_bits, timestamps, N, thresholds,
+                                                         num_buckets, octaves, NT, reinterpret_cast<uint8_t*>(cache));
+  else
+    hstu_bucket_tiles_kernel<false><<<grid, 256, 0, st>>>(offsets, index_bits, timestamps, N, thresholds,
+                                                          num_buckets, octaves, NT, reinterpret_cast<uint8_t*>(cache));
   GRB_LAUNCH_OK();
   return GRB_OK;
+}
+
+int grb_hstu_bucket_tiles(const void* offsets, int index_bits, const int64_t* timestamps, int64_t B,
+                          int64_t N, int64_t max_len, const int64_t* thresholds, int32_t num_buckets,
+                          const uint32_t* octaves, void* cache, grb_stream_t stream) {
+  return bucket_tiles_impl(offsets, index_bits, timestamps, B, N, max_len, thresholds, num_buckets, octaves,
+                           cache, false, stream);
+}
+
+int grb_hstu_bucket_tiles_masked(const void* offsets, int index_bits, const int64_t* timestamps, int64_t B,
+                                 int64_t N, int64_t max_len, const int64_t* thresholds, int32_t num_buckets,
+                                 const uint32_t* octaves, void* cache, grb_stream_t stream) {
+  return bucket_tiles_impl(offsets, index_bits, timestamps, B, N, max_len, thresholds, num_buckets, octaves,
+                           cache, true, stream);
 }
 
 }

@@ -33,7 +33,7 @@ def _rows_contiguous(t: torch.Tensor) -> torch.Tensor:
 # fused jagged HSTU attention  (sequential_encoders/hstu.py:96-128 + :134-205)
 # --------------------------------------------------------------------------------------------
 def _attn_args(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk, dv, max_len,
-               cache=None, tiles=None):
+               cache=None, short=False):
     a = _lib.HstuAttnArgs()
     a.B = offsets.numel() - 1
     a.N = N
@@ -53,12 +53,14 @@ def _attn_args(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk,
         a.bucket_thresholds = thresholds.data_ptr()
         oct_t = bucket_octaves(thresholds)
         a.bucket_octaves = oct_t.data_ptr()
-        if cache is not None:
+        if cache is not None and not short:
             a.bucket_cache = cache.data_ptr()
             a.bucket_cache_max_len = cache.grb_max_len
-    if tiles is not None:
-        a.bias_tiles = tiles.data_ptr()
-        a.bias_tiles_max_len = max_len
+    if short:     # masked bucket tiles + item schedule: the short-sequence kernels (with or without bias)
+        a.bucket_cache = cache.data_ptr()
+        a.bucket_cache_max_len = cache.grb_max_len
+        a.bucket_cache_masked = 1
+        a.short_schedule = cache.grb_sched.data_ptr()
     return a
 
 
@@ -82,27 +84,49 @@ def bucket_octaves(thresholds: torch.Tensor) -> torch.Tensor:
 
 
 class BucketCache(torch.Tensor):
-    """uint8 tensor holding grb_hstu_bucket_tiles output; remembers the max_len it was built for."""
+    """uint8 tensor holding grb_hstu_bucket_tiles output; remembers the max_len it was built for.
+    ``grb_masked``: built by grb_hstu_bucket_tiles_masked for the short-sequence kernels (masked pairs
+    hold 255), with the item schedule of the batch in ``grb_sched``."""
     grb_max_len: int = 0
+    grb_masked: bool = False
+    grb_sched: Optional[torch.Tensor] = None
 
 
-def hstu_bucket_cache(offsets: torch.Tensor, timestamps: torch.Tensor, thresholds: torch.Tensor,
-                      N: int, max_len: Optional[int] = None) -> torch.Tensor:
+def hstu_bucket_cache(offsets: torch.Tensor, timestamps: Optional[torch.Tensor],
+                      thresholds: Optional[torch.Tensor], N: int, max_len: Optional[int] = None,
+                      masked: bool = False) -> torch.Tensor:
     """Tabulate bucket(|ts[b, i+1] - ts[b, j]|) for every causal 128x128 tile of every sequence,
     once per batch (the reference recomputes it per layer, hstu.py:117-123).  Pass the result as
-    ``bucket_cache=`` to :func:`hstu_attention` for all layers, forward and backward."""
+    ``bucket_cache=`` to :func:`hstu_attention` for all layers, forward and backward.
+
+    ``masked`` (short sequences, max_len <= 256): the tiles also carry the causal / length masks
+    (bucket 255) and the batch's item schedule is attached; ``timestamps`` may then be None (no
+    relative bias: masks only)."""
     _lib.require_cuda(offsets, timestamps, thresholds)
     max_len = N if max_len is None else min(max_len, N)
     B = offsets.numel() - 1
     nbytes = int(_lib.lib().grb_hstu_bucket_cache_bytes(B, max_len))
     cache = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=offsets.device).as_subclass(BucketCache)
     cache.grb_max_len = max_len
-    timestamps = timestamps.contiguous()
+    cache.grb_masked = bool(masked)
     offsets = offsets.contiguous()
-    _lib.check(_lib.lib().grb_hstu_bucket_tiles(
-        offsets.data_ptr(), _lib.index_bits(offsets), timestamps.data_ptr(), B, N, max_len,
-        thresholds.data_ptr(), thresholds.numel(), bucket_octaves(thresholds).data_ptr(),
-        cache.data_ptr(), _lib.stream_ptr(offsets.device)))
+    stream = _lib.stream_ptr(offsets.device)
+    if timestamps is not None:
+        timestamps = timestamps.contiguous()
+        ts_args = (timestamps.data_ptr(), B, N, max_len, thresholds.data_ptr(), thresholds.numel(),
+                   bucket_octaves(thresholds).data_ptr())
+    else:
+        if not masked:
+            raise ValueError("hstu_bucket_cache: timestamps are required unless masked=True")
+        ts_args = (None, B, N, max_len, None, 0, None)
+    fn = _lib.lib().grb_hstu_bucket_tiles_masked if masked else _lib.lib().grb_hstu_bucket_tiles
+    with _lib.timed("hstu_bucket_tiles"):
+        _lib.check(fn(offsets.data_ptr(), _lib.index_bits(offsets), *ts_args, cache.data_ptr(), stream))
+    if masked:
+        sched = torch.empty(B + 2, dtype=torch.int32, device=offsets.device)
+        _lib.check(_lib.lib().grb_hstu_short_schedule(offsets.data_ptr(), _lib.index_bits(offsets), B, N,
+                                                      sched.data_ptr(), stream))
+        cache.grb_sched = sched
     return cache
 
 
@@ -117,22 +141,20 @@ def short_path_applies(q: torch.Tensor, dqk: int, dv: int, max_len: int) -> bool
             and os.environ.get("GRB_NO_SHORT") != "1")
 
 
-def hstu_bias_tiles(offsets: torch.Tensor, N: int, max_len: int, cache: Optional[torch.Tensor],
-                    ts_w: Optional[torch.Tensor], pos_w: Optional[torch.Tensor],
-                    num_buckets: int) -> torch.Tensor:
-    """One layer's relative bias (hstu.py:96-128) for every causal 128x128 tile of every sequence,
-    fp16, pre-halved, causal / length masks folded in as -15000 (grb_hstu_bias_tiles).  Built once
-    per layer and step; every head reads it in forward and backward.  ``cache`` None: no bias."""
-    B = offsets.numel() - 1
-    nbytes = int(_lib.lib().grb_hstu_bias_tiles_bytes(B, max_len))
-    tiles = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=offsets.device)
-    with _lib.timed("hstu_bias_tiles"):
-        _lib.check(_lib.lib().grb_hstu_bias_tiles(
-            offsets.data_ptr(), _lib.index_bits(offsets), B, N, max_len,
-            _lib.ptr(cache), cache.grb_max_len if cache is not None else 0,
-            _lib.ptr(ts_w), num_buckets, _lib.ptr(pos_w), tiles.data_ptr(),
-            _lib.stream_ptr(offsets.device)))
-    return tiles
+_DBIAS_WS: dict = {}
+
+
+def _dbias_workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    """Accumulation tiles of the short-sequence backward (head-summed bf16 dS^T).  Allocated once
+    per (device, size) and zero-filled then: every backward call finds it zero and leaves it zero
+    (grb_hstu_attn_bwd clears each tile after binning it), so no per-call memset is needed.  One
+    buffer per stream: calls on the same stream are ordered."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, nbytes)
+    ws = _DBIAS_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        _DBIAS_WS[key] = ws
+    return ws
 
 
 class _HstuAttention(torch.autograd.Function):
@@ -156,23 +178,23 @@ class _HstuAttention(torch.autograd.Function):
         # never write those rows, so they must start as zeros
         alloc = torch.zeros if rows_padded else torch.empty
         out = alloc((q.shape[0], H * dv), dtype=q.dtype, device=q.device)
-        if cache is not None and (timestamps is None or cache.grb_max_len != max_len):
+        if cache is not None and ((timestamps is None and not cache.grb_masked) or cache.grb_max_len != max_len):
             cache = None
-        tiles = None
-        if short_path_applies(q, dqk, dv, max_len) and (timestamps is None or thresholds.numel() <= 255):
-            if timestamps is not None and cache is None:
-                cache = hstu_bucket_cache(offsets, timestamps, thresholds, N, max_len)
-            tiles = hstu_bias_tiles(offsets, N, max_len, cache, ts_w, pos_w,
-                                    thresholds.numel() if timestamps is not None else 0)
+        short = short_path_applies(q, dqk, dv, max_len) and (timestamps is None or thresholds.numel() <= 254)
+        if short:
+            if cache is None or not cache.grb_masked:
+                cache = hstu_bucket_cache(offsets, timestamps, thresholds, N, max_len, masked=True)
+        elif cache is not None and cache.grb_masked:
+            cache = None            # masked tiles only serve the short-sequence kernels
         a = _attn_args(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk, dv, max_len, cache,
-                       tiles)
+                       short)
         a.out, a.ldo = out.data_ptr(), H * dv
         with _lib.timed("hstu_attn_fwd"):
             _lib.check(_lib.lib().grb_hstu_attn_fwd(C.byref(a), _lib.stream_ptr(q.device)))
         ctx.save_for_backward(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds)
         ctx.dims = (N, H, dqk, dv, max_len)
         ctx.cache = cache
-        ctx.tiles = tiles
+        ctx.short = short
         ctx.rows_padded = rows_padded
         return out
 
@@ -192,7 +214,7 @@ class _HstuAttention(torch.autograd.Function):
             dq = alloc((T, H * dqk), dtype=q.dtype, device=q.device)
             dk = alloc((T, H * dqk), dtype=q.dtype, device=q.device)
             dvv = alloc((T, H * dv), dtype=q.dtype, device=q.device)
-        short = ctx.tiles is not None
+        short = ctx.short
         # long-sequence kernels: fp32 dQ accumulator (zero-filled).  Short kernels: plain scratch for
         # the partial dQ of the second query tile, only when a sequence can have one.
         n_acc = T * H * dqk if (not short or max_len > 128) else 0
@@ -200,7 +222,8 @@ class _HstuAttention(torch.autograd.Function):
         if timestamps is not None:
             # every CTA adds into d ts_w / d pos_w; with short sequences that is thousands of CTAs
             # on a handful of cache lines.  Give them private copies (<= 256) and sum after.
-            copies = max(1, min(256, (4 << 20) // max(1, pos_w.numel())))
+            # (The short-sequence path bins per tile in shared memory first: one copy.)
+            copies = 1 if short else max(1, min(256, (4 << 20) // max(1, pos_w.numel())))
             n_ts, n_pos = ts_w.numel(), pos_w.numel()
         if short:
             ws = torch.empty(n_acc + copies * (n_ts + n_pos), dtype=torch.float32, device=q.device)
@@ -209,7 +232,7 @@ class _HstuAttention(torch.autograd.Function):
             ws = torch.zeros(n_acc + copies * (n_ts + n_pos), dtype=torch.float32, device=q.device)
         dq_acc = ws[:n_acc]
         a = _attn_args(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk, dv, max_len,
-                       ctx.cache, ctx.tiles)
+                       ctx.cache, short)
         a.dout, a.lddo = dout.data_ptr(), _ld(dout)
         a.dq, a.dk, a.dv_grad = dq.data_ptr(), dk.data_ptr(), dvv.data_ptr()
         a.lddq, a.lddk, a.lddv = H * dqk, H * dqk, H * dv
@@ -217,8 +240,8 @@ class _HstuAttention(torch.autograd.Function):
         dbias = None
         if short and timestamps is not None:
             # head-summed bf16 dS^T tiles (bulk reduce-add target), binned into d ts_w / d pos_w by a
-            # small kernel inside the same C-ABI call
-            dbias = torch.zeros(ctx.tiles.numel() // 2, dtype=torch.uint8, device=q.device)
+            # small kernel inside the same C-ABI call, which also clears them again
+            dbias = _dbias_workspace(ctx.cache.numel(), q.device)
             a.dbias_acc = dbias.data_ptr()
         d_ts = d_pos = None
         if timestamps is not None:

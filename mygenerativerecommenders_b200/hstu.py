@@ -299,13 +299,19 @@ class HSTUJagged(torch.nn.Module):
         # (tcgen05 path only: bf16 activations, 64-wide heads)
         bucket_cache = None
         first = self._attention_layers[0] if len(self._attention_layers) else None
-        if (all_timestamps is not None and first is not None and x.dtype == torch.bfloat16
-                and delta_x_offsets is None
+        if (first is not None and x.dtype == torch.bfloat16 and delta_x_offsets is None
                 and first._attention_dim == 64 and first._linear_dim == 64
-                and isinstance(first._rel_attn_bias, RelativeBucketedTimeAndPositionBasedBias)):
-            bucket_cache = GF.hstu_bucket_cache(x_offsets, all_timestamps,
-                                                first._rel_attn_bias._bucket_thresholds,
-                                                invalid_attn_mask.size(-1))
+                and first._normalization != "softmax_rel_bias"):
+            n_pad = invalid_attn_mask.size(-1)
+            has_bias = (all_timestamps is not None
+                        and isinstance(first._rel_attn_bias, RelativeBucketedTimeAndPositionBasedBias))
+            # short sequences (N <= 256): masked tiles + item schedule for the persistent kernels,
+            # needed with or without a relative bias
+            short = GF.short_path_applies(x, 64, 64, n_pad)
+            if has_bias or short:
+                bucket_cache = GF.hstu_bucket_cache(
+                    x_offsets, all_timestamps if has_bias else None,
+                    first._rel_attn_bias._bucket_thresholds if has_bias else None, n_pad, masked=short)
         for i, layer in enumerate(self._attention_layers):
             x, cs = layer(x=x, x_offsets=x_offsets, all_timestamps=all_timestamps,
                           invalid_attn_mask=invalid_attn_mask, delta_x_offsets=delta_x_offsets,

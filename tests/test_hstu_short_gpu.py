@@ -149,27 +149,33 @@ def test_short_path_full_c2_shape_batch():
         _close(got.grad, r.grad, 2e-2, 2e-2, f"C2 {name}")
 
 
-def test_bias_tiles_match_the_reference_bias():
-    """grb_hstu_bias_tiles against rel_bias of the oracle (hstu.py:96-128), both orientations."""
-    N, lengths = 211, [211, 140, 128, 5]
+def test_masked_bucket_tiles_and_item_schedule():
+    """grb_hstu_bucket_tiles_masked: the reference's bucket (hstu.py:113-123) for j <= i < n, 255
+    elsewhere, both orientations; grb_hstu_short_schedule: non-empty sequences, n > 128 first."""
+    N, lengths = 211, [211, 140, 128, 5, 0]
     c = _case(3, N, 1, lengths)
     off, ts = c["off"].to(DEV), c["ts"].to(DEV)
-    cache = GF.hstu_bucket_cache(off, ts, _thr(), N)
-    tiles = GF.hstu_bias_tiles(off, N, N, cache, c["ts_w"].to(DEV), c["pos_w"].to(DEV), 128)
-    n_tile_bytes = len(lengths) * 3 * 65536          # the item schedule of the kernels follows the tiles
-    t = tiles[:n_tile_bytes].cpu().view(torch.float16).view(len(lengths), 3, 2, 16, 128, 8).float()
-    sched = tiles[n_tile_bytes:n_tile_bytes + 4 * (len(lengths) + 2)].cpu().view(torch.int32)
-    assert sched[0] == 4 and sched[1] == 2 and sorted(sched[2:4].tolist()) == [0, 1] and sorted(sched[4:6].tolist()) == [2, 3]
-    bias = O.rel_bias(c["ts"], c["ts_w"], c["pos_w"], N, 128)           # (B, N, N)
+    cache = GF.hstu_bucket_cache(off, ts, _thr(), N, masked=True)
+    sched = cache.grb_sched.cpu()
+    assert sched[0] == 4 and sched[1] == 2
+    assert sorted(sched[2:4].tolist()) == [0, 1] and sorted(sched[4:6].tolist()) == [2, 3]
+    t = cache.cpu().view(len(lengths), 3, 2, 8, 128, 16)
+    ext = torch.cat([c["ts"], c["ts"][:, N - 1:N]], dim=1)
+    ref = O.bucketize_ts(ext[:, 1:].unsqueeze(2) - ext[:, :-1].unsqueeze(1))     # (B, N, N)
     for b, n in enumerate(lengths):
         for slot, (iq, jk) in enumerate([(0, 0), (1, 0), (1, 1)]):
             if iq * 128 >= n:
                 continue
-            tq = t[b, slot, 0].permute(1, 0, 2).reshape(128, 128)          # [row][col]
+            tq = t[b, slot, 0].permute(1, 0, 2).reshape(128, 128)          # [query row][key col]
             tk = t[b, slot, 1].permute(1, 0, 2).reshape(128, 128).t()      # stored [key][query]
-            for r in range(0, 128, 7):
-                for col in range(0, 128, 5):
-                    i, j = iq * 128 + r, jk * 128 + col
-                    want = 0.5 * bias[b, i, j].item() if (j <= i < n) else -15000.0
-                    for got in (tq[r, col].item(), tk[r, col].item()):
-                        assert abs(got - want) <= 1e-3 * max(1.0, abs(want)), (b, slot, r, col, got, want)
+            i = iq * 128 + torch.arange(128).view(-1, 1)
+            j = jk * 128 + torch.arange(128).view(1, -1)
+            valid = (j <= i) & (i < n)
+            want = torch.full((128, 128), 255, dtype=torch.uint8)
+            ii, jj = i.expand(128, 128)[valid], j.expand(128, 128)[valid]
+            want[valid] = ref[b, ii, jj].to(torch.uint8)
+            assert torch.equal(tq, want) and torch.equal(tk, want), (b, slot)
+    # mask-only tiles (no timestamps): valid pairs hold 0
+    only = GF.hstu_bucket_cache(off, None, None, N, masked=True).cpu().view(len(lengths), 3, 2, 8, 128, 16)
+    tq = only[1, 1, 0].permute(1, 0, 2).reshape(128, 128)                  # sequence of 140, slot (1, 0)
+    assert (tq[:12] == 0).all() and (tq[12:] == 255).all()
