@@ -111,12 +111,16 @@ __device__ __forceinline__ void add_bf16_pair(float& acc_lo, float& acc_hi, uint
 // key rows (the bucket is a step function of the query position for a fixed key).
 // Tile layout (what the backward wrote): [hf 0..1][key row 128][64 queries] bf16, 16-byte chunk c of
 // a row stored at chunk c ^ (row & 7).
+__device__ __forceinline__ void red_add_f32(float* addr, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+
 __global__ void __launch_bounds__(256) hstu_bias_grad_kernel(
     const void* __restrict__ offsets, int index_bits, int64_t N, int NT, const uint8_t* __restrict__ bcache,
-    uint8_t* __restrict__ dbias, int nb, float* __restrict__ d_ts_w, float* __restrict__ d_pos_w, float scale) {
-  constexpr int PITCH = 130;                                  // bf16 elements per staged row
+    uint8_t* __restrict__ dbias, int nb, float* __restrict__ d_ts_w, float* __restrict__ d_pos_w, int copies,
+    float scale) {
+  constexpr int PITCH = 132;                                  // bf16 elements per staged row (8-byte aligned rows)
   __shared__ __align__(16) __nv_bfloat16 tile[128 * PITCH];
-  __shared__ float hist[256];
   const int b = blockIdx.y, slot = blockIdx.x;
   const int iq = slot == 0 ? 0 : 1, jk = slot == 2 ? 1 : 0;
   const int64_t off0 = load_index(offsets, b, index_bits);
@@ -124,10 +128,9 @@ __global__ void __launch_bounds__(256) hstu_bias_grad_kernel(
   if (n64 > N) n64 = N;
   const int n = (int) n64;
   if (iq * 128 >= n) return;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int TPS = NT * (NT + 1) / 2;
   uint8_t* src = dbias + ((int64_t) b * TPS + slot) * 32768;
-  hist[tid] = 0.f;
   // stage the tile un-swizzled: smem[key row][query 0..127]; the accumulation tile is handed back
   // zeroed (the caller allocates it once, zero-filled, and every launch leaves it that way)
   for (int g = tid; g < 2048; g += 256) {
@@ -135,44 +138,54 @@ __global__ void __launch_bounds__(256) hstu_bias_grad_kernel(
     const int chunk = pos ^ (row & 7);
     const uint4 v = *reinterpret_cast<const uint4*>(src + (size_t) g * 16);
     *reinterpret_cast<uint4*>(src + (size_t) g * 16) = make_uint4(0u, 0u, 0u, 0u);
-    uint32_t* d = reinterpret_cast<uint32_t*>(tile + row * PITCH + hf * 64 + chunk * 8);
-    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    uint2* d = reinterpret_cast<uint2*>(tile + row * PITCH + hf * 64 + chunk * 8);
+    d[0] = make_uint2(v.x, v.y);
+    d[1] = make_uint2(v.z, v.w);
   }
   __syncthreads();
-  // diagonals: thread t sums x = c - r + 127 = t  (c = query column, r = key row)
+  // ---- d pos_w: thread t sums the diagonal x = c - r + 127 = t  (c = query column, r = key row) ----
   if (tid < 255) {
     float acc = 0.f;
     const int rlo = tid < 127 ? 127 - tid : 0, rhi = tid < 127 ? 128 : 255 - tid;
     for (int r = rlo; r < rhi; ++r) acc += __bfloat162float(tile[r * PITCH + (tid - 127 + r)]);
     // pos_w index N-1 + j - i = N-1 + (j0 + r) - (i0 + c) = N-1 + j0 - i0 - (tid - 127)
     const int64_t idx = N - 1 + (int64_t) (jk - iq) * 128 - (tid - 127);
-    if (acc != 0.f && idx >= 0 && idx < 2 * N - 1) atomicAdd(d_pos_w + idx, acc * scale);
+    if (acc != 0.f && idx >= 0 && idx < 2 * N - 1) red_add_f32(d_pos_w + idx, acc * scale);
   }
-  // time buckets: thread = key row, walk the query columns; bucket 255 = masked pair (value 0)
-  if (tid < 128) {
-    const uint8_t* bkt = bcache + ((int64_t) b * TPS + slot) * 32768 + 16384;   // K orientation
-    int run_bk = 255;
-    float run_acc = 0.f;
-#pragma unroll 1
-    for (int ch = 0; ch < 8; ++ch) {
-      const uint4 raw = *reinterpret_cast<const uint4*>(bkt + ((size_t) ch * 128 + tid) * 16);
-      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+  // ---- d ts_w: along a key row the bucket is a step function of the query position, so the sum of
+  // a run is a difference of row prefix sums: every position where the bucket changes adds the
+  // prefix to the bucket on its left and subtracts it from the bucket on its right (the row end
+  // closes the last run).  A warp takes a row at a time, a lane 4 consecutive columns: no serial
+  // walk, no divergence.  Bucket 255 marks masked pairs (their values are exactly 0).
+  float* d_ts_mine = d_ts_w + (int64_t) ((blockIdx.x + gridDim.x * blockIdx.y) % (unsigned) copies) * (nb + 1);
+  const uint8_t* bkt = bcache + ((int64_t) b * TPS + slot) * 32768 + 16384;   // K orientation
+#pragma unroll 2
+  for (int r = warp; r < 128; r += 8) {
+    const uint2 raw = *reinterpret_cast<const uint2*>(tile + r * PITCH + 4 * lane);
+    const uint32_t bk4 = *reinterpret_cast<const uint32_t*>(bkt + ((size_t) (lane >> 2) * 128 + r) * 16 + 4 * (lane & 3));
+    float v[4];
+    v[0] = __uint_as_float(raw.x << 16); v[1] = __uint_as_float(raw.x & 0xffff0000u);
+    v[2] = __uint_as_float(raw.y << 16); v[3] = __uint_as_float(raw.y & 0xffff0000u);
+    v[1] += v[0]; v[2] += v[1]; v[3] += v[2];               // inclusive prefix inside the lane
+    float tot = v[3];
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const int bk = (int) ((w[e >> 2] >> (8 * (e & 3))) & 0xffu);
-        const float v = __bfloat162float(tile[tid * PITCH + ch * 16 + e]);
-        if (bk != run_bk) {
-          if (run_bk != 255 && run_acc != 0.f) atomicAdd(&hist[run_bk], run_acc);
-          run_acc = 0.f;
-          run_bk = bk;
-        }
-        run_acc += v;
+    for (int o = 1; o < 32; o <<= 1) {                      // inclusive scan of the lane totals
+      const float t = __shfl_up_sync(0xffffffffu, tot, o);
+      if (lane >= o) tot += t;
+    }
+    const float base = tot - v[3];                          // exclusive prefix of this lane
+    const uint32_t next0 = __shfl_down_sync(0xffffffffu, bk4, 1) & 0xffu;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const uint32_t bk = (bk4 >> (8 * e)) & 0xffu;
+      const uint32_t nx = e < 3 ? (bk4 >> (8 * (e + 1))) & 0xffu : (lane < 31 ? next0 : 256u);
+      const float pre = (base + v[e]) * scale;
+      if (nx != bk && pre != 0.f) {
+        if (bk <= (uint32_t) nb) red_add_f32(d_ts_mine + bk, pre);
+        if (nx <= (uint32_t) nb) red_add_f32(d_ts_mine + nx, -pre);
       }
     }
-    if (run_bk != 255 && run_acc != 0.f) atomicAdd(&hist[run_bk], run_acc);
   }
-  __syncthreads();
-  if (tid <= nb && hist[tid] != 0.f) atomicAdd(d_ts_w + tid, hist[tid] * scale);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -985,10 +998,12 @@ int hstu_attn_short_bwd(const grb_hstu_attn_args* a, cudaStream_t st) {
     kern<<<items, SH_THREADS, smem, st>>>(tmQ, tmK, tmV, tmdO, p);
     GRB_LAUNCH_OK();
     timeline_dump("bwd", p.tl, st);
-    // bias gradients from the head-summed dS'^T tiles (dS' = 2N dS), added into copy 0 of d_ts_w / d_pos_w
+    // bias gradients from the head-summed dS'^T tiles (dS' = 2N dS): d_pos_w into copy 0, d_ts_w
+    // spread over the caller's copies
     dim3 grid((unsigned) p.tps, (unsigned) a->B);
     hstu_bias_grad_kernel<<<grid, 256, 0, st>>>(a->offsets, a->index_bits, a->N, NT, a->bucket_cache, p.dbias,
-                                                a->num_buckets, a->d_ts_w, a->d_pos_w, 0.5f / (float) a->N);
+                                                a->num_buckets, a->d_ts_w, a->d_pos_w,
+                                                a->d_bias_copies > 0 ? a->d_bias_copies : 1, 0.5f / (float) a->N);
   } else {
     auto kern = hstu_attn_short_bwd_kernel<false>;
     GRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));

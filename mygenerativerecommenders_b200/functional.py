@@ -222,8 +222,8 @@ class _HstuAttention(torch.autograd.Function):
         if timestamps is not None:
             # every CTA adds into d ts_w / d pos_w; with short sequences that is thousands of CTAs
             # on a handful of cache lines.  Give them private copies (<= 256) and sum after.
-            # (The short-sequence path bins per tile in shared memory first: one copy.)
-            copies = 1 if short else max(1, min(256, (4 << 20) // max(1, pos_w.numel())))
+            # (The short-sequence path bins per tile after summing the heads: 32 copies are plenty.)
+            copies = 32 if short else max(1, min(256, (4 << 20) // max(1, pos_w.numel())))
             n_ts, n_pos = ts_w.numel(), pos_w.numel()
         if short:
             ws = torch.empty(n_acc + copies * (n_ts + n_pos), dtype=torch.float32, device=q.device)
