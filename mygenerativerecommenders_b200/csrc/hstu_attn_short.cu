@@ -120,7 +120,9 @@ __global__ void __launch_bounds__(256) hstu_bias_grad_kernel(
     uint8_t* __restrict__ dbias, int nb, float* __restrict__ d_ts_w, float* __restrict__ d_pos_w, int copies,
     float scale) {
   constexpr int PITCH = 132;                                  // bf16 elements per staged row (8-byte aligned rows)
-  __shared__ __align__(16) __nv_bfloat16 tile[128 * PITCH];
+  extern __shared__ __align__(16) uint8_t bg_smem[];
+  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(bg_smem);            // [128][PITCH]
+  uint8_t* bks = bg_smem + 128 * PITCH * 2;                                    // [128 key rows][128 queries]
   const int b = blockIdx.y, slot = blockIdx.x;
   const int iq = slot == 0 ? 0 : 1, jk = slot == 2 ? 1 : 0;
   const int64_t off0 = load_index(offsets, b, index_bits);
@@ -131,16 +133,29 @@ __global__ void __launch_bounds__(256) hstu_bias_grad_kernel(
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int TPS = NT * (NT + 1) / 2;
   uint8_t* src = dbias + ((int64_t) b * TPS + slot) * 32768;
-  // stage the tile un-swizzled: smem[key row][query 0..127]; the accumulation tile is handed back
-  // zeroed (the caller allocates it once, zero-filled, and every launch leaves it that way)
-  for (int g = tid; g < 2048; g += 256) {
+  const uint8_t* bkt = bcache + ((int64_t) b * TPS + slot) * 32768 + 16384;   // K orientation
+  // stage the tile un-swizzled: smem[key row][query 0..127], and the bucket bytes next to it; all
+  // loads are issued before the first use.  The accumulation tile is handed back zeroed (the caller
+  // allocates it once, zero-filled, and every launch leaves it that way).
+  uint4 tv[8], bv[4];
+#pragma unroll
+  for (int k8 = 0; k8 < 8; ++k8) tv[k8] = ldg_nc_v4(src + (size_t) (tid + 256 * k8) * 16);
+#pragma unroll
+  for (int k4 = 0; k4 < 4; ++k4) bv[k4] = ldg_nc_v4(bkt + (size_t) (tid + 256 * k4) * 16);
+#pragma unroll
+  for (int k8 = 0; k8 < 8; ++k8) {
+    const int g = tid + 256 * k8;
     const int hf = g >> 10, row = (g >> 3) & 127, pos = g & 7;
     const int chunk = pos ^ (row & 7);
-    const uint4 v = *reinterpret_cast<const uint4*>(src + (size_t) g * 16);
     *reinterpret_cast<uint4*>(src + (size_t) g * 16) = make_uint4(0u, 0u, 0u, 0u);
     uint2* d = reinterpret_cast<uint2*>(tile + row * PITCH + hf * 64 + chunk * 8);
-    d[0] = make_uint2(v.x, v.y);
-    d[1] = make_uint2(v.z, v.w);
+    d[0] = make_uint2(tv[k8].x, tv[k8].y);
+    d[1] = make_uint2(tv[k8].z, tv[k8].w);
+  }
+#pragma unroll
+  for (int k4 = 0; k4 < 4; ++k4) {       // global chunk g = (query / 16) * 128 + key row -> smem[key row][16 (query / 16) ..]
+    const int g = tid + 256 * k4;
+    *reinterpret_cast<uint4*>(bks + (g & 127) * 128 + (g >> 7) * 16) = bv[k4];
   }
   __syncthreads();
   // ---- d pos_w: thread t sums the diagonal x = c - r + 127 = t  (c = query column, r = key row) ----
@@ -158,11 +173,10 @@ __global__ void __launch_bounds__(256) hstu_bias_grad_kernel(
   // closes the last run).  A warp takes a row at a time, a lane 4 consecutive columns: no serial
   // walk, no divergence.  Bucket 255 marks masked pairs (their values are exactly 0).
   float* d_ts_mine = d_ts_w + (int64_t) ((blockIdx.x + gridDim.x * blockIdx.y) % (unsigned) copies) * (nb + 1);
-  const uint8_t* bkt = bcache + ((int64_t) b * TPS + slot) * 32768 + 16384;   // K orientation
 #pragma unroll 2
   for (int r = warp; r < 128; r += 8) {
     const uint2 raw = *reinterpret_cast<const uint2*>(tile + r * PITCH + 4 * lane);
-    const uint32_t bk4 = *reinterpret_cast<const uint32_t*>(bkt + ((size_t) (lane >> 2) * 128 + r) * 16 + 4 * (lane & 3));
+    const uint32_t bk4 = *reinterpret_cast<const uint32_t*>(bks + r * 128 + 4 * lane);
     float v[4];
     v[0] = __uint_as_float(raw.x << 16); v[1] = __uint_as_float(raw.x & 0xffff0000u);
     v[2] = __uint_as_float(raw.y << 16); v[3] = __uint_as_float(raw.y & 0xffff0000u);
@@ -1001,7 +1015,9 @@ int hstu_attn_short_bwd(const grb_hstu_attn_args* a, cudaStream_t st) {
     // bias gradients from the head-summed dS'^T tiles (dS' = 2N dS): d_pos_w into copy 0, d_ts_w
     // spread over the caller's copies
     dim3 grid((unsigned) p.tps, (unsigned) a->B);
-    hstu_bias_grad_kernel<<<grid, 256, 0, st>>>(a->offsets, a->index_bits, a->N, NT, a->bucket_cache, p.dbias,
+    const size_t bg_smem = 128 * 132 * 2 + 128 * 128;
+    GRB_CUDA_OK(cudaFuncSetAttribute(hstu_bias_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bg_smem));
+    hstu_bias_grad_kernel<<<grid, 256, bg_smem, st>>>(a->offsets, a->index_bits, a->N, NT, a->bucket_cache, p.dbias,
                                                 a->num_buckets, a->d_ts_w, a->d_pos_w,
                                                 a->d_bias_copies > 0 ? a->d_bias_copies : 1, 0.5f / (float) a->N);
   } else {
