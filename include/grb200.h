@@ -200,6 +200,34 @@ typedef struct grb_hstu_attn_decode_args {
 int grb_hstu_attn_decode(const grb_hstu_attn_decode_args* a, grb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * f1  hstu.py:302-320 (UVQK projection + SiLU) and :404-413 (output projection + bias + residual),
+ *     forward and backward, as ONE tcgen05 GEMM with fused epilogues (csrc/proj_gemm.cu):
+ *        C[M, N] = epilogue(A[M, K] * B[K, N]),  bf16 operands, fp32 accumulation.
+ *     a_mn = 0: A stored (M, K) row-major, row stride lda;  a_mn = 1: A stored (K, M) row-major (a
+ *     transposed operand read in place: the weight gradients contract over the tokens).
+ *     b_mn = 0: B stored (N, K) row-major (nn.Linear weight);  b_mn = 1: B stored (K, N) row-major.
+ *     N % 256 == 0; K % 64 == 0 unless F32_ADD; all pointers / row strides 16-byte aligned.
+ *     Epilogues: PLAIN    out0 (M, N) bf16 = C
+ *                SILU2    out0 = C (bf16), out1 = SiLU(out0) (bf16)
+ *                BIAS_RES out0 = bf16(C + bias[n] + res[m, n])   bias fp32 (N) or NULL, res bf16 or NULL
+ *                F32_ADD  out0 (M, N) fp32 += C   (split-K over the SMs, vector reds; caller zero-fills)
+ *     grb_colsum_bf16: out[W] (fp32) += column sums of a bf16 (rows, W) matrix (bias gradient).
+ * ------------------------------------------------------------------------------------------- */
+enum { GRB_GEMM_EPI_PLAIN = 0, GRB_GEMM_EPI_SILU2 = 1, GRB_GEMM_EPI_BIAS_RES = 2, GRB_GEMM_EPI_F32_ADD = 3 };
+typedef struct grb_proj_gemm_args {
+  int64_t M, N, K;
+  int32_t a_mn, b_mn, epi, reserved;
+  const void* A; int64_t lda;
+  const void* B; int64_t ldb;
+  void* out0; int64_t ldo0;
+  void* out1; int64_t ldo1;
+  const float* bias;
+  const void* res; int64_t ldres;
+} grb_proj_gemm_args;
+int grb_proj_gemm(const grb_proj_gemm_args* a, grb_stream_t stream);
+int grb_colsum_bf16(const void* x, int64_t ldx, int64_t rows, int32_t W, float* out, grb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * a6  hstu.py:304-320  the activation between the UVQK projection and its consumers:
  *     F.silu(batched_mm_output) followed by torch.split into u, v, q, k.
  *     grb_silu_fwd: y = x / (1 + exp(-x)), (rows, W), fp32 math.

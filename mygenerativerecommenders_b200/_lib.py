@@ -56,6 +56,19 @@ class HstuAttnDecodeArgs(C.Structure):
     ]
 
 
+class ProjGemmArgs(C.Structure):
+    _fields_ = [
+        ("M", c_i64), ("N", c_i64), ("K", c_i64),
+        ("a_mn", c_i32), ("b_mn", c_i32), ("epi", c_i32), ("reserved", c_i32),
+        ("A", c_vp), ("lda", c_i64), ("B", c_vp), ("ldb", c_i64),
+        ("out0", c_vp), ("ldo0", c_i64), ("out1", c_vp), ("ldo1", c_i64),
+        ("bias", c_vp), ("res", c_vp), ("ldres", c_i64),
+    ]
+
+
+GEMM_EPI_PLAIN, GEMM_EPI_SILU2, GEMM_EPI_BIAS_RES, GEMM_EPI_F32_ADD = 0, 1, 2, 3
+
+
 class MipsTopkArgs(C.Structure):
     _fields_ = [
         ("B", c_i64), ("X", c_i64), ("D", c_i64),
@@ -128,6 +141,8 @@ SYMBOLS = {
     "grb_adamw_step": (C.c_int, [C.c_int, C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp),
                                  C.POINTER(c_i64)] + [C.c_double] * 7 + [c_vp]),
     "grb_rows_scatter_add": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_i64, c_i64, c_vp]),
+    "grb_proj_gemm": (C.c_int, [C.POINTER(ProjGemmArgs), c_vp]),
+    "grb_colsum_bf16": (C.c_int, [c_vp, c_i64, c_i64, c_i32, c_vp, c_vp]),
     "grb_selftest_umma": (C.c_int, [C.POINTER(C.c_float), C.c_int, c_vp]),
 }
 

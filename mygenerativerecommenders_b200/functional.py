@@ -498,6 +498,170 @@ def linear_bias(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tens
     return torch.nn.functional.linear(x, w, b)
 
 
+# --------------------------------------------------------------------------------------------
+# f1: the layer's projections on the tcgen05 GEMM with fused epilogues (csrc/proj_gemm.cu)
+#     hstu.py:302-320 (UVQK + SiLU + split) and :404-413 (_o + bias + residual)
+# --------------------------------------------------------------------------------------------
+def _proj_gemm(A, B, M, N, K, a_mn, b_mn, epi, out0, out1=None, bias=None, res=None):
+    a = _lib.ProjGemmArgs()
+    a.M, a.N, a.K = M, N, K
+    a.a_mn, a.b_mn, a.epi = int(a_mn), int(b_mn), epi
+    a.A, a.lda = A.data_ptr(), A.stride(0)
+    a.B, a.ldb = B.data_ptr(), B.stride(0)
+    a.out0, a.ldo0 = out0.data_ptr(), out0.stride(0)
+    if out1 is not None:
+        a.out1, a.ldo1 = out1.data_ptr(), out1.stride(0)
+    if bias is not None:
+        a.bias = bias.data_ptr()
+    if res is not None:
+        a.res, a.ldres = res.data_ptr(), res.stride(0)
+    _lib.check(_lib.lib().grb_proj_gemm(C.byref(a), _lib.stream_ptr(A.device)))
+
+
+def _gemm_ok(x: torch.Tensor, K: int, N: int) -> bool:
+    """bf16 rows on the GPU, shapes the 128 x 256 x 64 tiles take.  GRB_NO_PROJ_GEMM=1 keeps the
+    cuBLAS composite (A/B switch)."""
+    import os
+    return (x.is_cuda and x.dim() == 2 and x.dtype == torch.bfloat16 and K % 64 == 0 and N % 256 == 0
+            and x.shape[0] > 0 and os.environ.get("GRB_NO_PROJ_GEMM") != "1")
+
+
+def _al16(t: torch.Tensor) -> torch.Tensor:
+    """Rows contiguous, 16-byte aligned base and row stride (what TMA needs)."""
+    t = _rows_contiguous(t)
+    if t.data_ptr() % 16 or (t.stride(0) * t.element_size()) % 16:
+        t = t.clone(memory_format=torch.contiguous_format)
+    return t
+
+
+def _silu_split_bwd(x_pre: torch.Tensor, grads, sizes) -> torch.Tensor:
+    """d(pre-activation) from the gradients of the column blocks of SiLU(x_pre): one pass."""
+    rows, W = x_pre.shape
+    n = len(sizes)
+    es = x_pre.element_size()
+
+    def prep(g):
+        if g is None:
+            return None
+        g = _rows_contiguous(g if g.dtype == x_pre.dtype else g.to(x_pre.dtype))
+        if g.data_ptr() % 16 or (_ld(g) * es) % 16:      # the kernel reads 16-byte chunks
+            g = g.clone(memory_format=torch.contiguous_format)
+        return g
+
+    keep = [prep(g) for g in grads]
+    dx = torch.empty((rows, W), dtype=x_pre.dtype, device=x_pre.device)
+    ptrs = (C.c_void_p * n)(*[None if g is None else g.data_ptr() for g in keep])
+    lds = (C.c_int64 * n)(*[0 if g is None else _ld(g) for g in keep])
+    widths = (C.c_int32 * n)(*sizes)
+    _lib.check(_lib.lib().grb_silu_split_bwd(
+        x_pre.data_ptr(), _ld(x_pre), n, ptrs, lds, widths, dx.data_ptr(), W, rows,
+        _lib.dtype_code(x_pre.dtype), _lib.stream_ptr(x_pre.device)))
+    return dx
+
+
+class _UvqkProj(torch.autograd.Function):
+    """split(SiLU(xn @ W_uvqk)) (hstu.py:302-320).  Forward: one GEMM whose epilogue writes the
+    pre-activation and its SiLU.  Backward: SiLU' over the four consumers' gradients (one pass), the
+    input gradient and the fp32 weight gradient (split-K over the token dimension) on the same kernel."""
+
+    @staticmethod
+    def forward(ctx, xn, w, *sizes):
+        xn = _al16(xn)
+        T, D = xn.shape
+        Ntot = w.shape[1]
+        wc = (w if w.dtype == xn.dtype else w.to(xn.dtype)).contiguous()       # (K = D, N = Ntot) row-major
+        pre = torch.empty((T, Ntot), dtype=xn.dtype, device=xn.device)
+        act = torch.empty((T, Ntot), dtype=xn.dtype, device=xn.device)
+        with _lib.timed("proj_gemm_uvqk_fwd"):
+            _proj_gemm(xn, wc, T, Ntot, D, False, True, _lib.GEMM_EPI_SILU2, pre, act)
+        ctx.save_for_backward(xn, wc, pre)
+        ctx.sizes = sizes
+        ctx.w_dtype = w.dtype
+        return tuple(act.split(list(sizes), dim=1))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        xn, wc, pre = ctx.saved_tensors
+        T, D = xn.shape
+        Ntot = wc.shape[1]
+        dx = _silu_split_bwd(pre, grads, ctx.sizes)
+        d_xn = dw = None
+        if ctx.needs_input_grad[0]:
+            d_xn = torch.empty((T, D), dtype=xn.dtype, device=xn.device)
+            with _lib.timed("proj_gemm_uvqk_dgrad"):       # dx (T, Ntot) @ W^T: W is (N = D, K = Ntot) row-major
+                _proj_gemm(dx, wc, T, D, Ntot, False, False, _lib.GEMM_EPI_PLAIN, d_xn)
+        if ctx.needs_input_grad[1]:
+            dw32 = torch.zeros((D, Ntot), dtype=torch.float32, device=xn.device)
+            with _lib.timed("proj_gemm_uvqk_wgrad"):       # xn^T (D, T) @ dx (T, Ntot), both read in place
+                _proj_gemm(xn, dx, D, Ntot, T, True, True, _lib.GEMM_EPI_F32_ADD, dw32)
+            dw = dw32 if ctx.w_dtype == torch.float32 else dw32.to(ctx.w_dtype)
+        return (d_xn, dw) + (None,) * len(ctx.sizes)
+
+
+def uvqk_projection(xn: torch.Tensor, w: torch.Tensor, sizes) -> Tuple[torch.Tensor, ...]:
+    """``torch.split(F.silu(xn @ w), sizes, dim=1)`` (hstu.py:302-320), w (D, sum sizes) possibly an
+    fp32 master of a bf16 xn."""
+    _lib.require_cuda(xn, w)
+    sizes = [int(v) for v in sizes]
+    if _gemm_ok(xn, xn.shape[1], w.shape[1]) and xn.shape[1] % 256 == 0 and all(v % 8 == 0 for v in sizes):
+        return _UvqkProj.apply(xn, w, *sizes)
+    return silu_split(master_linear(xn, w, None, w_in_out=True), sizes)
+
+
+class _OutProj(torch.autograd.Function):
+    """F.linear(o_in, W, b) + residual (hstu.py:404-413) with bias and residual in the GEMM epilogue
+    (one rounding to bf16 instead of two).  Backward: input gradient and fp32 weight gradient on the
+    same kernel, bias gradient by a column-sum kernel; the residual's gradient is the incoming one."""
+
+    @staticmethod
+    def forward(ctx, o_in, w, b, res):
+        o_in, res = _al16(o_in), _al16(res)
+        T, Din = o_in.shape
+        Dout = w.shape[0]
+        wc = (w if w.dtype == o_in.dtype else w.to(o_in.dtype)).contiguous()   # (N = Dout, K = Din) row-major
+        bf = None if b is None else (b if b.dtype == torch.float32 else b.float()).contiguous()
+        out = torch.empty((T, Dout), dtype=o_in.dtype, device=o_in.device)
+        with _lib.timed("proj_gemm_o_fwd"):
+            _proj_gemm(o_in, wc, T, Dout, Din, False, False, _lib.GEMM_EPI_BIAS_RES, out, bias=bf, res=res)
+        ctx.save_for_backward(o_in, wc)
+        ctx.w_dtype = w.dtype
+        ctx.b_dtype = None if b is None else b.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        o_in, wc = ctx.saved_tensors
+        g = _al16(g)
+        T, Din = o_in.shape
+        Dout = wc.shape[0]
+        d_in = dw = db = None
+        if ctx.needs_input_grad[0]:
+            d_in = torch.empty((T, Din), dtype=o_in.dtype, device=o_in.device)
+            with _lib.timed("proj_gemm_o_dgrad"):          # g (T, Dout) @ W: W is (K = Dout, N = Din) row-major
+                _proj_gemm(g, wc, T, Din, Dout, False, True, _lib.GEMM_EPI_PLAIN, d_in)
+        if ctx.needs_input_grad[1]:
+            dw32 = torch.zeros((Dout, Din), dtype=torch.float32, device=g.device)
+            with _lib.timed("proj_gemm_o_wgrad"):          # g^T (Dout, T) @ o_in (T, Din)
+                _proj_gemm(g, o_in, Dout, Din, T, True, True, _lib.GEMM_EPI_F32_ADD, dw32)
+            dw = dw32 if ctx.w_dtype == torch.float32 else dw32.to(ctx.w_dtype)
+        if ctx.b_dtype is not None and ctx.needs_input_grad[2]:
+            db32 = torch.zeros(Dout, dtype=torch.float32, device=g.device)
+            _lib.check(_lib.lib().grb_colsum_bf16(g.data_ptr(), g.stride(0), T, Dout, db32.data_ptr(),
+                                                  _lib.stream_ptr(g.device)))
+            db = db32 if ctx.b_dtype == torch.float32 else db32.to(ctx.b_dtype)
+        return d_in, dw, db, (g if ctx.needs_input_grad[3] else None)
+
+
+def output_projection(o_in: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor],
+                      residual: torch.Tensor) -> torch.Tensor:
+    """``F.linear(o_in, w, b) + residual`` (hstu.py:404-413), w / b possibly fp32 masters."""
+    _lib.require_cuda(o_in, w, b, residual)
+    if (_gemm_ok(o_in, o_in.shape[1], w.shape[0]) and w.shape[0] % 256 == 0 and w.shape[1] % 256 == 0
+            and residual.dtype == o_in.dtype and residual.shape == (o_in.shape[0], w.shape[0])):
+        return _OutProj.apply(o_in, w, b, residual)
+    return master_linear(o_in, w, b) + residual
+
+
 class _L2Norm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, eps):

@@ -213,11 +213,12 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
         H, dv, dqk = self._num_heads, self._linear_dim, self._attention_dim
 
         normed_x = self._norm_input(x)
-        mm = GF.master_linear(normed_x, self._uvqk, None, w_in_out=True)
         sizes = [dv * H, dv * H, dqk * H, dqk * H]
         if self._linear_activation == "silu":
-            u, v, q, k = GF.silu_split(mm, sizes)      # F.silu + torch.split, one backward pass
+            # one tcgen05 GEMM with the SiLU in its epilogue (bf16 rows); cuBLAS + silu kernel otherwise
+            u, v, q, k = GF.uvqk_projection(normed_x, self._uvqk, sizes)
         elif self._linear_activation == "none":
+            mm = GF.master_linear(normed_x, self._uvqk, None, w_in_out=True)
             u, v, q, k = torch.split(mm, sizes, dim=1)
         else:
             raise ValueError(f"Unknown linear_activation {self._linear_activation}")
@@ -257,9 +258,9 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
         else:
             o_input = GF.layer_norm_gate(attn_output, u, self._eps)
 
-        new_outputs = GF.master_linear(
+        new_outputs = GF.output_projection(
             F.dropout(o_input, p=self._dropout_ratio, training=self.training),
-            self._o.weight, self._o.bias) + x
+            self._o.weight, self._o.bias, x)
 
         cache_state = None
         if incremental:
