@@ -42,9 +42,11 @@ constexpr int PG_THREADS = 64 + 256;
 
 struct PgSmem {
   static constexpr int ring = 0;
-  static constexpr int bars = ring + PG_STAGES * PG_STAGE_BYTES;
+  static constexpr int stage = ring + PG_STAGES * PG_STAGE_BYTES;   // 8 epilogue warps x [32 rows][128 bytes]
+  static constexpr int bars = stage + 8 * 4096;
   static constexpr int total = bars + 256;
 };
+static_assert(PgSmem::total + 1024 <= 232448, "shared memory budget");
 
 struct PgParams {
   int64_t M, N, K;
@@ -188,9 +190,29 @@ __global__ void __launch_bounds__(PG_THREADS, 1) proj_gemm_kernel(const __grid_c
       const uint32_t ab = tile & 1;
       mbar_wait(bar_acc_full + 8 * ab, (tile >> 1) & 1);
       tc_fence_after();
-      const int64_t row = (int64_t) mt * PG_BM + r;
-      const bool row_ok = row < p.M;
+      // The accumulator arrives with thread = row: stored as it is, one instruction would touch 32
+      // different 128-byte lines (32 LSU wavefronts; the first version of this epilogue spent 16 k
+      // cycles per tile on its stores).  Each 32-column chunk is therefore transposed through a
+      // per-warp staging block (16-byte chunk c of row rr at chunk c ^ ((rr >> 1) & mask): conflict
+      // free both ways) and leaves as row segments of 64 (bf16) or 128 (fp32) contiguous bytes.
+      const int64_t row0 = (int64_t) mt * PG_BM + 32 * wq;          // first row of this warp
       const int64_t col0 = (int64_t) nt * PG_BN + 128 * g;
+      uint8_t* stg = smem + L::stage + (warp - 2) * 4096;
+      // bf16 chunk [32 rows][64 B]: lane -> row 8 i + lane / 4, 16-byte chunk lane % 4   (i = 0..3)
+      auto flush_bf16 = [&](const uint32_t (&w)[16], __nv_bfloat16* base, int64_t ld, int64_t col) {
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(stg + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) =
+              make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = 8 * i + (lane >> 2), c = lane & 3;
+          const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((c ^ ((rr >> 1) & 3)) << 4));
+          if (row0 + rr < p.M) *reinterpret_cast<uint4*>(base + (row0 + rr) * ld + col + 8 * c) = v;
+        }
+      };
 #pragma unroll 1
       for (int c32 = 0; c32 < 4; ++c32) {
         uint32_t acc[32];
@@ -201,61 +223,74 @@ __global__ void __launch_bounds__(PG_THREADS, 1) proj_gemm_kernel(const __grid_c
 #pragma unroll
           for (int i = 0; i < 32; ++i) acc[i] = 0u;
         }
-        if (!row_ok) continue;
         const int64_t col = col0 + 32 * c32;
         if (p.epi == GRB_GEMM_EPI_F32_ADD) {
-          float* o = reinterpret_cast<float*>(p.out0) + row * p.ldo0 + col;
+          // fp32 chunk [32 rows][128 B]: lane -> row 4 i + lane / 8, 16-byte chunk lane % 8   (i = 0..7)
+          __syncwarp();
 #pragma unroll
-          for (int v4 = 0; v4 < 8; ++v4)
-            red_add_v4(o + 4 * v4, __uint_as_float(acc[4 * v4]), __uint_as_float(acc[4 * v4 + 1]),
-                       __uint_as_float(acc[4 * v4 + 2]), __uint_as_float(acc[4 * v4 + 3]));
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                make_uint4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+          __syncwarp();
+          float* o = reinterpret_cast<float*>(p.out0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + (lane >> 3), c = lane & 7;
+            const float4 v = *reinterpret_cast<const float4*>(stg + rr * 128 + ((c ^ (rr & 7)) << 4));
+            if (row0 + rr < p.M) red_add_v4(o + (row0 + rr) * p.ldo0 + col + 4 * c, v.x, v.y, v.z, v.w);
+          }
         } else if (p.epi == GRB_GEMM_EPI_SILU2) {
-          __nv_bfloat16* o0 = reinterpret_cast<__nv_bfloat16*>(p.out0) + row * p.ldo0 + col;
-          __nv_bfloat16* o1 = reinterpret_cast<__nv_bfloat16*>(p.out1) + row * p.ldo1 + col;
+          uint32_t a16[16], s16[16];
 #pragma unroll
-          for (int v8 = 0; v8 < 4; ++v8) {
-            uint32_t a4[4], s4[4];
-#pragma unroll
-            for (int e2 = 0; e2 < 4; ++e2) {
-              const float x0 = __uint_as_float(acc[8 * v8 + 2 * e2]), x1 = __uint_as_float(acc[8 * v8 + 2 * e2 + 1]);
-              a4[e2] = pack_bf16x2(x0, x1);
-              // SiLU of the bf16-rounded pre-activation: what a separate silu pass over the stored
-              // tensor computes, so forward and backward see the same x
-              const float xr0 = __uint_as_float(a4[e2] << 16), xr1 = __uint_as_float(a4[e2] & 0xffff0000u);
-              s4[e2] = pack_bf16x2(silu_fast(xr0), silu_fast(xr1));
-            }
-            *reinterpret_cast<uint4*>(o0 + 8 * v8) = make_uint4(a4[0], a4[1], a4[2], a4[3]);
-            *reinterpret_cast<uint4*>(o1 + 8 * v8) = make_uint4(s4[0], s4[1], s4[2], s4[3]);
+          for (int e2 = 0; e2 < 16; ++e2) {
+            a16[e2] = pack_bf16x2(__uint_as_float(acc[2 * e2]), __uint_as_float(acc[2 * e2 + 1]));
+            // SiLU of the bf16-rounded pre-activation: what a separate silu pass over the stored
+            // tensor computes, so forward and backward see the same x
+            const float xr0 = __uint_as_float(a16[e2] << 16), xr1 = __uint_as_float(a16[e2] & 0xffff0000u);
+            s16[e2] = pack_bf16x2(silu_fast(xr0), silu_fast(xr1));
           }
+          flush_bf16(a16, reinterpret_cast<__nv_bfloat16*>(p.out0), p.ldo0, col);
+          flush_bf16(s16, reinterpret_cast<__nv_bfloat16*>(p.out1), p.ldo1, col);
         } else {
-          __nv_bfloat16* o0 = reinterpret_cast<__nv_bfloat16*>(p.out0) + row * p.ldo0 + col;
           const bool br = p.epi == GRB_GEMM_EPI_BIAS_RES;
+          uint32_t o16[16];
+          if (br && p.res) {
+            // the residual chunk comes in through the same staging block, coalesced
+            __syncwarp();
 #pragma unroll
-          for (int v8 = 0; v8 < 4; ++v8) {
-            float x[8];
+            for (int i = 0; i < 4; ++i) {
+              const int rr = 8 * i + (lane >> 2), c = lane & 3;
+              uint4 v = make_uint4(0u, 0u, 0u, 0u);
+              if (row0 + rr < p.M) v = *reinterpret_cast<const uint4*>(p.res + (row0 + rr) * p.ldres + col + 8 * c);
+              *reinterpret_cast<uint4*>(stg + rr * 64 + ((c ^ ((rr >> 1) & 3)) << 4)) = v;
+            }
+            __syncwarp();
 #pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(acc[8 * v8 + e]);
-            if (br) {
-              if (p.bias) {
-                const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col + 8 * v8);
-                const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 8 * v8 + 4);
-                x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-                x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
-              }
-              if (p.res) {
-                const uint4 rv = *reinterpret_cast<const uint4*>(p.res + row * p.ldres + col + 8 * v8);
-                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+            for (int c = 0; c < 4; ++c) {
+              const uint4 v = *reinterpret_cast<const uint4*>(stg + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4));
+              const uint32_t rw[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                for (int e2 = 0; e2 < 4; ++e2) {
-                  x[2 * e2] += __uint_as_float(rw[e2] << 16);
-                  x[2 * e2 + 1] += __uint_as_float(rw[e2] & 0xffff0000u);
-                }
+              for (int e2 = 0; e2 < 4; ++e2) {
+                acc[8 * c + 2 * e2] = __float_as_uint(__uint_as_float(acc[8 * c + 2 * e2]) + __uint_as_float(rw[e2] << 16));
+                acc[8 * c + 2 * e2 + 1] =
+                    __float_as_uint(__uint_as_float(acc[8 * c + 2 * e2 + 1]) + __uint_as_float(rw[e2] & 0xffff0000u));
               }
             }
-            *reinterpret_cast<uint4*>(o0 + 8 * v8) =
-                make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
-                           pack_bf16x2(x[6], x[7]));
           }
+          if (br && p.bias) {
+#pragma unroll
+            for (int v4 = 0; v4 < 8; ++v4) {
+              const float4 bv = *reinterpret_cast<const float4*>(p.bias + col + 4 * v4);
+              acc[4 * v4] = __float_as_uint(__uint_as_float(acc[4 * v4]) + bv.x);
+              acc[4 * v4 + 1] = __float_as_uint(__uint_as_float(acc[4 * v4 + 1]) + bv.y);
+              acc[4 * v4 + 2] = __float_as_uint(__uint_as_float(acc[4 * v4 + 2]) + bv.z);
+              acc[4 * v4 + 3] = __float_as_uint(__uint_as_float(acc[4 * v4 + 3]) + bv.w);
+            }
+          }
+#pragma unroll
+          for (int e2 = 0; e2 < 16; ++e2)
+            o16[e2] = pack_bf16x2(__uint_as_float(acc[2 * e2]), __uint_as_float(acc[2 * e2 + 1]));
+          flush_bf16(o16, reinterpret_cast<__nv_bfloat16*>(p.out0), p.ldo0, col);
         }
       }
       tc_fence_before();
