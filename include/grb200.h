@@ -131,10 +131,6 @@ typedef struct grb_hstu_attn_args {
    * scratch (no zero fill). */
   const int32_t* short_schedule;
   int32_t bucket_cache_masked;    /* bucket_cache came from grb_hstu_bucket_tiles_masked */
-  /* short-sequence backward with timestamps: grb_hstu_bucket_cache_bytes(B, max_len) bytes, ZERO on
-   * entry and zero again on return: the kernel sums every head's bf16 dS^T tiles into it (bulk
-   * reduce-add), a second kernel bins them into copy 0 of d_ts_w / d_pos_w and clears them. */
-  void* dbias_acc;
 } grb_hstu_attn_args;
 
 /* Host helper: the integer bucketing table the tcgen05 kernels use, from the ascending threshold

@@ -58,8 +58,8 @@ int grb_hstu_attn_bwd(const grb_hstu_attn_args* a, grb_stream_t stream) {
   if (a->short_schedule) {
     GRB_REQUIRE(hstu_attn_short_usable(a, true), GRB_ERR_UNSUPPORTED,
                 "hstu_attn_bwd: short_schedule given but the short-sequence path does not apply (bf16, head "
-                "dims 64, max_len <= 256, 16-byte aligned rows, masked bucket_cache built for max_len, dbias_acc "
-                "with timestamps, dq_accum scratch when max_len > 128)");
+                "dims 64, max_len <= 256, 16-byte aligned rows, masked bucket_cache built for max_len, "
+                "dq_accum scratch when max_len > 128)");
     return hstu_attn_short_bwd(a, st);
   }
   if (!force_cuda_core() && hstu_attn_bwd_sm100_supported(a)) return hstu_attn_bwd_sm100(a, st);

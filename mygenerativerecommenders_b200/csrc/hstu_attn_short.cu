@@ -81,6 +81,12 @@ __device__ __forceinline__ void bulk_reduce_add_bf16(void* dst, uint32_t src_sme
                "r"(src_smem), "r"(bytes)
                : "memory");
 }
+// predicated fire-and-forget fp32 add (no branch around it)
+__device__ __forceinline__ void red_add_f32_pred(float* addr, float v, bool p) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q red.global.add.f32 [%0], %1;\n\t}" ::"l"(addr),
+               "f"(v), "r"((int) p)
+               : "memory");
+}
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   uint4 v;
   asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -99,107 +105,6 @@ __device__ __forceinline__ void add_bf16_pair(float& acc_lo, float& acc_hi, uint
       "add.rn.f32.bf16 %1, hi, %1;\n\t}"
       : "+f"(acc_lo), "+f"(acc_hi)
       : "r"(pair));
-}
-
-// ------------------------------------------------------------------------------------------------
-// bias gradients from the head-summed dS^T tiles
-// ------------------------------------------------------------------------------------------------
-// The backward kernel adds every (sequence, head)'s bf16 dS'^T blocks into one accumulation tile per
-// (sequence, tile) with a bulk reduce-add (the block is already in shared memory as an MMA operand:
-// no epilogue instruction is spent on it).  This kernel then bins each tile once:
-//   d pos_w[N-1+j-i] += sum along the diagonals ; d ts_w[bucket(i,j)] += run-length sums along the
-// key rows (the bucket is a step function of the query position for a fixed key).
-// Tile layout (what the backward wrote): [hf 0..1][key row 128][64 queries] bf16, 16-byte chunk c of
-// a row stored at chunk c ^ (row & 7).
-__device__ __forceinline__ void red_add_f32(float* addr, float v) {
-  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
-}
-
-__global__ void __launch_bounds__(256) hstu_bias_grad_kernel(
-    const void* __restrict__ offsets, int index_bits, int64_t N, int NT, const uint8_t* __restrict__ bcache,
-    uint8_t* __restrict__ dbias, int nb, float* __restrict__ d_ts_w, float* __restrict__ d_pos_w, int copies,
-    float scale) {
-  constexpr int PITCH = 132;                                  // bf16 elements per staged row (8-byte aligned rows)
-  extern __shared__ __align__(16) uint8_t bg_smem[];
-  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(bg_smem);            // [128][PITCH]
-  uint8_t* bks = bg_smem + 128 * PITCH * 2;                                    // [128 key rows][128 queries]
-  const int b = blockIdx.y, slot = blockIdx.x;
-  const int iq = slot == 0 ? 0 : 1, jk = slot == 2 ? 1 : 0;
-  const int64_t off0 = load_index(offsets, b, index_bits);
-  int64_t n64 = load_index(offsets, b + 1, index_bits) - off0;
-  if (n64 > N) n64 = N;
-  const int n = (int) n64;
-  if (iq * 128 >= n) return;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int TPS = NT * (NT + 1) / 2;
-  uint8_t* src = dbias + ((int64_t) b * TPS + slot) * 32768;
-  const uint8_t* bkt = bcache + ((int64_t) b * TPS + slot) * 32768 + 16384;   // K orientation
-  // stage the tile un-swizzled: smem[key row][query 0..127], and the bucket bytes next to it; all
-  // loads are issued before the first use.  The accumulation tile is handed back zeroed (the caller
-  // allocates it once, zero-filled, and every launch leaves it that way).
-  uint4 tv[8], bv[4];
-#pragma unroll
-  for (int k8 = 0; k8 < 8; ++k8) tv[k8] = ldg_nc_v4(src + (size_t) (tid + 256 * k8) * 16);
-#pragma unroll
-  for (int k4 = 0; k4 < 4; ++k4) bv[k4] = ldg_nc_v4(bkt + (size_t) (tid + 256 * k4) * 16);
-#pragma unroll
-  for (int k8 = 0; k8 < 8; ++k8) {
-    const int g = tid + 256 * k8;
-    const int hf = g >> 10, row = (g >> 3) & 127, pos = g & 7;
-    const int chunk = pos ^ (row & 7);
-    *reinterpret_cast<uint4*>(src + (size_t) g * 16) = make_uint4(0u, 0u, 0u, 0u);
-    uint2* d = reinterpret_cast<uint2*>(tile + row * PITCH + hf * 64 + chunk * 8);
-    d[0] = make_uint2(tv[k8].x, tv[k8].y);
-    d[1] = make_uint2(tv[k8].z, tv[k8].w);
-  }
-#pragma unroll
-  for (int k4 = 0; k4 < 4; ++k4) {       // global chunk g = (query / 16) * 128 + key row -> smem[key row][16 (query / 16) ..]
-    const int g = tid + 256 * k4;
-    *reinterpret_cast<uint4*>(bks + (g & 127) * 128 + (g >> 7) * 16) = bv[k4];
-  }
-  __syncthreads();
-  // ---- d pos_w: thread t sums the diagonal x = c - r + 127 = t  (c = query column, r = key row) ----
-  if (tid < 255) {
-    float acc = 0.f;
-    const int rlo = tid < 127 ? 127 - tid : 0, rhi = tid < 127 ? 128 : 255 - tid;
-    for (int r = rlo; r < rhi; ++r) acc += __bfloat162float(tile[r * PITCH + (tid - 127 + r)]);
-    // pos_w index N-1 + j - i = N-1 + (j0 + r) - (i0 + c) = N-1 + j0 - i0 - (tid - 127)
-    const int64_t idx = N - 1 + (int64_t) (jk - iq) * 128 - (tid - 127);
-    if (acc != 0.f && idx >= 0 && idx < 2 * N - 1) red_add_f32(d_pos_w + idx, acc * scale);
-  }
-  // ---- d ts_w: along a key row the bucket is a step function of the query position, so the sum of
-  // a run is a difference of row prefix sums: every position where the bucket changes adds the
-  // prefix to the bucket on its left and subtracts it from the bucket on its right (the row end
-  // closes the last run).  A warp takes a row at a time, a lane 4 consecutive columns: no serial
-  // walk, no divergence.  Bucket 255 marks masked pairs (their values are exactly 0).
-  float* d_ts_mine = d_ts_w + (int64_t) ((blockIdx.x + gridDim.x * blockIdx.y) % (unsigned) copies) * (nb + 1);
-#pragma unroll 2
-  for (int r = warp; r < 128; r += 8) {
-    const uint2 raw = *reinterpret_cast<const uint2*>(tile + r * PITCH + 4 * lane);
-    const uint32_t bk4 = *reinterpret_cast<const uint32_t*>(bks + r * 128 + 4 * lane);
-    float v[4];
-    v[0] = __uint_as_float(raw.x << 16); v[1] = __uint_as_float(raw.x & 0xffff0000u);
-    v[2] = __uint_as_float(raw.y << 16); v[3] = __uint_as_float(raw.y & 0xffff0000u);
-    v[1] += v[0]; v[2] += v[1]; v[3] += v[2];               // inclusive prefix inside the lane
-    float tot = v[3];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {                      // inclusive scan of the lane totals
-      const float t = __shfl_up_sync(0xffffffffu, tot, o);
-      if (lane >= o) tot += t;
-    }
-    const float base = tot - v[3];                          // exclusive prefix of this lane
-    const uint32_t next0 = __shfl_down_sync(0xffffffffu, bk4, 1) & 0xffu;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const uint32_t bk = (bk4 >> (8 * e)) & 0xffu;
-      const uint32_t nx = e < 3 ? (bk4 >> (8 * (e + 1))) & 0xffu : (lane < 31 ? next0 : 256u);
-      const float pre = (base + v[e]) * scale;
-      if (nx != bk && pre != 0.f) {
-        if (bk <= (uint32_t) nb) red_add_f32(d_ts_mine + bk, pre);
-        if (nx <= (uint32_t) nb) red_add_f32(d_ts_mine + nx, -pre);
-      }
-    }
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -541,7 +446,8 @@ struct ShortBwdParams {
   __nv_bfloat16* dk; int64_t lddk;
   __nv_bfloat16* dv; int64_t lddv;
   float* dq_accum;          // (T, H*64) fp32 scratch (no zero fill needed)
-  uint8_t* dbias;           // (B, tps, 32 KiB) bf16 head-summed dS'^T tiles, zero-filled by the caller
+  float* d_ts_w; float* d_pos_w;   // (copies, nb + 1) / (copies, 2N - 1) fp32, accumulated (+=)
+  int d_bias_copies;
 };
 
 struct SbSmem {
@@ -655,8 +561,6 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_bwd_kernel(
         if (u != 1) { mbar_wait_g(bar_kv_full, c_kv & 1); ++c_kv; }
         if (u != 2) { mbar_wait_g(bar_qdo_full, c_qdo & 1); ++c_qdo; }
         if (gu > 0) mbar_wait_g(bar_dq_read, (gu - 1) & 1);    // dQ of the previous unit has left TMEM [64,128)
-        if (HAS_BIAS && gu > 0 && lane == 0) bulk_wait_group_read0();   // the dS^T blocks have been read
-        __syncwarp();
         tc_fence_after();
         // ---- half A scores ----
 #pragma unroll
@@ -669,12 +573,6 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_bwd_kernel(
         mbar_wait_g(bar_half_done, gu & 1);
         if (first_of_kt && gk > 0) mbar_wait_g(bar_dkv_read, (gk - 1) & 1);   // dV / dK of the previous key tile stored
         tc_fence_after();
-        if (HAS_BIAS && lane == 0) {   // head-summed dS'^T for the bias gradients: block A -> global, bf16 add
-          bulk_reduce_add_bf16(p.dbias + (((int64_t) it.seq * p.tps + u) * 2 + 0) * AT_TILE_BYTES,
-                               smem_u32(smem + L::dsT), AT_TILE_BYTES);
-          bulk_commit_group();
-        }
-        __syncwarp();
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)     // dV += P^T_A dO_A : P^T of queries 16 ks .. at TMEM col 32 (ks/2) + 8 (ks%2)
           umma_ts_warp(tmem + 128, tmem + 32 * (ks >> 1) + 8 * (ks & 1), adv(o_desc, ks * 2048), id_kmn,
@@ -696,12 +594,6 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_bwd_kernel(
         umma_commit_warp(bar_s_full + 8);
         mbar_wait_g(bar_half_done + 8, gu & 1);
         tc_fence_after();
-        if (HAS_BIAS && lane == 0) {
-          bulk_reduce_add_bf16(p.dbias + (((int64_t) it.seq * p.tps + u) * 2 + 1) * AT_TILE_BYTES,
-                               smem_u32(smem + L::dsT) + AT_TILE_BYTES, AT_TILE_BYTES);
-          bulk_commit_group();
-        }
-        __syncwarp();
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
           umma_ts_warp(tmem + 128, tmem + 32 * (ks >> 1) + 8 * (ks & 1), adv(o_desc, (4 + ks) * 2048), id_kmn, true);
@@ -715,8 +607,6 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_bwd_kernel(
         if (last_of_kt) { umma_commit_warp(bar_dkv_full); ++gk; }
       }
     }
-    if (HAS_BIAS && lane == 0) bulk_wait_group0();          // shared memory must outlive the reduces
-    __syncwarp();
   } else {
     // ================= epilogue: thread = key row =================
     const int wq = warp & 3;
@@ -728,6 +618,10 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_bwd_kernel(
     const float* tsw_s = reinterpret_cast<const float*>(smem + L::tsw);
     const float* pos_s = reinterpret_cast<const float*>(smem + L::pos);
     uint8_t* dsT_row = smem + L::dsT + r * 128;
+    // bias gradients (fp32, per head, from the unrounded dS'): this CTA's private copies
+    const int64_t copy = cta % p.d_bias_copies;
+    float* d_pos_mine = HAS_BIAS ? p.d_pos_w + copy * (2 * p.N - 1) : nullptr;
+    float* d_ts_mine = HAS_BIAS ? p.d_ts_w + copy * (p.nb + 1) : nullptr;
     ItemIter iter(G, cta, n_items);
     uint32_t gu = 0, gk = 0;
     int k_item = 0;
@@ -754,6 +648,11 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_bwd_kernel(
             bqv[sc] = ldg_nc_v4(bkt + ((size_t) ((cb >> 4) + sc) * 128 + r) * 16);
           mbar_wait_g(bar_s_full + 8 * hf, gu & 1);
           tc_fence_after();
+          // d ts_w: along a key row the bucket is a step function of the query position: the dS' of a
+          // run are summed in a register and leave with one red when the bucket changes (255 = masked
+          // pair, value exactly 0).  The run is closed at the end of the thread's 32 columns.
+          uint32_t run_bk = 255u;
+          float run_acc = 0.f;
 #pragma unroll
           for (int sc = 0; sc < 2; ++sc) {               // 16-column sub-chunks
             const int c16 = cb + 16 * sc;
@@ -761,6 +660,7 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_bwd_kernel(
             // valid columns of this row in the sub-chunk: lo <= e < hi; nothing to do for the warp?
             const int lo = jk - i0 - c16, hi = n - i0 - c16;
             const bool dead = __all_sync(0xffffffffu, lo >= 16 || hi <= 0 || hi <= lo);
+            float am = 0.f, aw = 0.f, bm = 0.f, bw = 0.f;    // d pos_w partial sums of this 32 x 16 block
             if (dead) {
               const uint32_t z4[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
@@ -779,9 +679,11 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_bwd_kernel(
             for (int c8 = 0; c8 < 2; ++c8) {
               const uint32_t bw2[2] = {c8 ? bqv[sc].z : bqv[sc].x, c8 ? bqv[sc].w : bqv[sc].y};
               uint32_t ppk[4], dpk[4];
+              float dsv[8];
 #pragma unroll
               for (int e2 = 0; e2 < 4; ++e2) {
-                float pv2[2], ds2[2];
+                float pv2[2];
+                float* ds2 = dsv + 2 * e2;
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
                   const int cc = 8 * c8 + 2 * e2 + t;
@@ -803,8 +705,41 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_bwd_kernel(
               // dS^T: 16-byte chunk (4 g + 2 sc + c8) of this key row, 128-byte swizzle, block hf
               *reinterpret_cast<uint4*>(dsT_row + hf * AT_TILE_BYTES + ((4 * g + 2 * sc + c8) ^ (r & 7)) * 16) =
                   make_uint4(dpk[0], dpk[1], dpk[2], dpk[3]);
+              if (HAS_BIAS) {
+                // d pos_w: the warp's 32 x 16 block is summed along its diagonals: each packed pair is
+                // rotated to the lane that owns its diagonal (r - c = lane: am / bm, lane - 32: aw / bw)
+#pragma unroll
+                for (int k2 = 0; k2 < 4; ++k2) {
+                  const int src = lane + 8 * c8 + 2 * k2;
+                  const uint32_t got = __shfl_sync(0xffffffffu, dpk[k2], src);
+                  if (src < 32) add_bf16_pair(am, bm, got); else add_bf16_pair(aw, bw, got);
+                }
+                // d ts_w: branch-free run-length walk
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const uint32_t bk = (bw2[e >> 2] >> (8 * (e & 3))) & 0xffu;
+                  const bool chg = bk != run_bk;
+                  red_add_f32_pred(d_ts_mine + run_bk, run_acc * half_inv_n, chg && run_bk != 255u && run_acc != 0.f);
+                  run_acc = (chg ? 0.f : run_acc) + dsv[e];
+                  run_bk = bk;
+                }
+              }
+            }
+            if (HAS_BIAS) {
+              // diagonal totals: b* of lane L+1 belong to the diagonals of lane L
+              const float tbm = __shfl_sync(0xffffffffu, bm, lane + 1);
+              const float tbw = __shfl_sync(0xffffffffu, bw, lane + 1);
+              const float tot_m = am + (lane < 31 ? tbm : 0.f);
+              const float tot_w = aw + tbw + (lane == 31 ? tbm : 0.f);
+              // diagonal r - c = rel  ->  pos_w index N-1 + (j0 + r) - (i0 + c)
+              const int64_t idx_m = p.N - 1 + j0 - i0 + 32 * wq - c16 + lane;
+              red_add_f32_pred(d_pos_mine + idx_m, tot_m * half_inv_n, tot_m != 0.f && idx_m >= 0 && idx_m < 2 * p.N - 1);
+              const int64_t idx_w = idx_m - 32;
+              red_add_f32_pred(d_pos_mine + idx_w, tot_w * half_inv_n, tot_w != 0.f && idx_w >= 0 && idx_w < 2 * p.N - 1);
             }
           }
+          if (HAS_BIAS)
+            red_add_f32_pred(d_ts_mine + run_bk, run_acc * half_inv_n, run_bk != 255u && run_acc != 0.f);
           tmem_st_wait();
           tc_fence_before();
           fence_proxy_async_smem();                  // st.shared -> visible to the MMA / bulk reduce (async proxy)
@@ -911,7 +846,6 @@ bool hstu_attn_short_usable(const grb_hstu_attn_args* a, bool bwd) {
     if (!al16(a->dout) || !al16(a->dq) || !al16(a->dk) || !al16(a->dv_grad) || !al16(a->dq_accum)) return false;
     if ((a->lddo * 2) % 16 || (a->lddq * 2) % 16 || (a->lddk * 2) % 16 || (a->lddv * 2) % 16) return false;
     if (a->max_len > 128 && a->dq_accum == nullptr) return false;
-    if (a->timestamps && (a->dbias_acc == nullptr || !al16(a->dbias_acc))) return false;
   }
   return true;
 }
@@ -1000,7 +934,8 @@ int hstu_attn_short_bwd(const grb_hstu_attn_args* a, cudaStream_t st) {
   p.dk = reinterpret_cast<__nv_bfloat16*>(a->dk); p.lddk = a->lddk;
   p.dv = reinterpret_cast<__nv_bfloat16*>(a->dv_grad); p.lddv = a->lddv;
   p.dq_accum = a->dq_accum;
-  p.dbias = reinterpret_cast<uint8_t*>(a->dbias_acc);
+  p.d_ts_w = a->d_ts_w; p.d_pos_w = a->d_pos_w;
+  p.d_bias_copies = a->d_bias_copies > 0 ? a->d_bias_copies : 1;
   const size_t smem = SbSmem::total + 1024;
   p.tl = timeline_buffer();
   const unsigned items = short_grid(a);
@@ -1010,16 +945,7 @@ int hstu_attn_short_bwd(const grb_hstu_attn_args* a, cudaStream_t st) {
     GRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      (int) cudaSharedmemCarveoutMaxShared));
     kern<<<items, SH_THREADS, smem, st>>>(tmQ, tmK, tmV, tmdO, p);
-    GRB_LAUNCH_OK();
     timeline_dump("bwd", p.tl, st);
-    // bias gradients from the head-summed dS'^T tiles (dS' = 2N dS): d_pos_w into copy 0, d_ts_w
-    // spread over the caller's copies
-    dim3 grid((unsigned) p.tps, (unsigned) a->B);
-    const size_t bg_smem = 128 * 132 * 2 + 128 * 128;
-    GRB_CUDA_OK(cudaFuncSetAttribute(hstu_bias_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bg_smem));
-    hstu_bias_grad_kernel<<<grid, 256, bg_smem, st>>>(a->offsets, a->index_bits, a->N, NT, a->bucket_cache, p.dbias,
-                                                a->num_buckets, a->d_ts_w, a->d_pos_w,
-                                                a->d_bias_copies > 0 ? a->d_bias_copies : 1, 0.5f / (float) a->N);
   } else {
     auto kern = hstu_attn_short_bwd_kernel<false>;
     GRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));

@@ -141,22 +141,6 @@ def short_path_applies(q: torch.Tensor, dqk: int, dv: int, max_len: int) -> bool
             and os.environ.get("GRB_NO_SHORT") != "1")
 
 
-_DBIAS_WS: dict = {}
-
-
-def _dbias_workspace(nbytes: int, device: torch.device) -> torch.Tensor:
-    """Accumulation tiles of the short-sequence backward (head-summed bf16 dS^T).  Allocated once
-    per (device, size) and zero-filled then: every backward call finds it zero and leaves it zero
-    (grb_hstu_attn_bwd clears each tile after binning it), so no per-call memset is needed.  One
-    buffer per stream: calls on the same stream are ordered."""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream, nbytes)
-    ws = _DBIAS_WS.get(key)
-    if ws is None:
-        ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
-        _DBIAS_WS[key] = ws
-    return ws
-
-
 class _HstuAttention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk, dv, max_len,
@@ -222,8 +206,8 @@ class _HstuAttention(torch.autograd.Function):
         if timestamps is not None:
             # every CTA adds into d ts_w / d pos_w; with short sequences that is thousands of CTAs
             # on a handful of cache lines.  Give them private copies (<= 256) and sum after.
-            # (The short-sequence path bins per tile after summing the heads: 32 copies are plenty.)
-            copies = 32 if short else max(1, min(256, (4 << 20) // max(1, pos_w.numel())))
+            # (The short-sequence kernels are persistent: one copy per CTA is 2 x SMs at most.)
+            copies = 64 if short else max(1, min(256, (4 << 20) // max(1, pos_w.numel())))
             n_ts, n_pos = ts_w.numel(), pos_w.numel()
         if short:
             ws = torch.empty(n_acc + copies * (n_ts + n_pos), dtype=torch.float32, device=q.device)
@@ -237,12 +221,6 @@ class _HstuAttention(torch.autograd.Function):
         a.dq, a.dk, a.dv_grad = dq.data_ptr(), dk.data_ptr(), dvv.data_ptr()
         a.lddq, a.lddk, a.lddv = H * dqk, H * dqk, H * dv
         a.dq_accum = dq_acc.data_ptr() if n_acc else None
-        dbias = None
-        if short and timestamps is not None:
-            # head-summed bf16 dS^T tiles (bulk reduce-add target), binned into d ts_w / d pos_w by a
-            # small kernel inside the same C-ABI call, which also clears them again
-            dbias = _dbias_workspace(ctx.cache.numel(), q.device)
-            a.dbias_acc = dbias.data_ptr()
         d_ts = d_pos = None
         if timestamps is not None:
             d_ts = ws[n_acc:n_acc + copies * n_ts].view(copies, n_ts)
