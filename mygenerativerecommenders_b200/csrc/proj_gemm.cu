@@ -21,7 +21,8 @@
 //                  one 64x64 box per 64-wide chunk for an MN-major one)
 //   warp 1 (MMA) : tcgen05.mma M128 N256 K16 x 4 per stage into one of two 256-column TMEM
 //                  accumulators, so the epilogue of tile i overlaps the main loop of tile i + 1
-//   warps 2..9   : epilogue, thread = output row, warpgroup g = columns [128 g, 128 g + 128)
+//   warps 2..17  : epilogue, thread = output row, warpgroup g = columns [64 g, 64 g + 64) (16 warps:
+//                  with 8 the epilogue ran at 27 % issue utilisation, two warps per scheduler)
 // Tiles are ordered n-fastest, so the CTAs running concurrently share A slabs through L2.
 #include "common.cuh"
 #include "sm100_ptx.cuh"
@@ -38,12 +39,13 @@ constexpr int PG_STAGES = 4;
 constexpr int PG_A_BYTES = PG_BM * PG_BK * 2;          // 16 KiB
 constexpr int PG_B_BYTES = PG_BN * PG_BK * 2;          // 32 KiB
 constexpr int PG_STAGE_BYTES = PG_A_BYTES + PG_B_BYTES;
-constexpr int PG_THREADS = 64 + 256;
+constexpr int PG_EPI_WARPS = 16;
+constexpr int PG_THREADS = 64 + 32 * PG_EPI_WARPS;
 
 struct PgSmem {
   static constexpr int ring = 0;
-  static constexpr int stage = ring + PG_STAGES * PG_STAGE_BYTES;   // 8 epilogue warps x [32 rows][128 bytes]
-  static constexpr int bars = stage + 8 * 4096;
+  static constexpr int stage = ring + PG_STAGES * PG_STAGE_BYTES;   // per epilogue warp [32 rows][64 bytes]
+  static constexpr int bars = stage + PG_EPI_WARPS * 2048;
   static constexpr int total = bars + 256;
 };
 static_assert(PgSmem::total + 1024 <= 232448, "shared memory budget");
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) proj_gemm_kernel(const __grid_c
 
   if (tid == 0) {
     for (int s = 0; s < PG_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(bar_acc_full + 8 * s, 1); mbar_init(bar_acc_empty + 8 * s, 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_acc_full + 8 * s, 1); mbar_init(bar_acc_empty + 8 * s, PG_EPI_WARPS); }
     fence_barrier_init();
     prefetch_tensormap(&tmA); prefetch_tensormap(&tmB);
   }
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) proj_gemm_kernel(const __grid_c
   } else {
     // ================= epilogue =================
     const int wq = warp & 3;
-    const int g = (warp - 2) >> 2;                    // columns [128 g, 128 g + 128) of the tile
+    const int g = (warp - 2) >> 2;                    // columns [64 g, 64 g + 64) of the tile
     const int r = (wq << 5) | lane;
     const uint32_t lane_base = (uint32_t) (wq * 32) << 16;
     uint32_t tile = 0;
@@ -196,8 +198,8 @@ __global__ void __launch_bounds__(PG_THREADS, 1) proj_gemm_kernel(const __grid_c
       // per-warp staging block (16-byte chunk c of row rr at chunk c ^ ((rr >> 1) & mask): conflict
       // free both ways) and leaves as row segments of 64 (bf16) or 128 (fp32) contiguous bytes.
       const int64_t row0 = (int64_t) mt * PG_BM + 32 * wq;          // first row of this warp
-      const int64_t col0 = (int64_t) nt * PG_BN + 128 * g;
-      uint8_t* stg = smem + L::stage + (warp - 2) * 4096;
+      const int64_t col0 = (int64_t) nt * PG_BN + 64 * g;
+      uint8_t* stg = smem + L::stage + (warp - 2) * 2048;
       // bf16 chunk [32 rows][64 B]: lane -> row 8 i + lane / 4, 16-byte chunk lane % 4   (i = 0..3)
       auto flush_bf16 = [&](const uint32_t (&w)[16], __nv_bfloat16* base, int64_t ld, int64_t col) {
         __syncwarp();
@@ -214,10 +216,10 @@ __global__ void __launch_bounds__(PG_THREADS, 1) proj_gemm_kernel(const __grid_c
         }
       };
 #pragma unroll 1
-      for (int c32 = 0; c32 < 4; ++c32) {
+      for (int c32 = 0; c32 < 2; ++c32) {
         uint32_t acc[32];
         if (nkb > 0) {
-          tmem_ld32(tmem + lane_base + ab * PG_BN + 128 * g + 32 * c32, acc);
+          tmem_ld32(tmem + lane_base + ab * PG_BN + 64 * g + 32 * c32, acc);
           tmem_ld_wait();
         } else {
 #pragma unroll
@@ -225,32 +227,38 @@ __global__ void __launch_bounds__(PG_THREADS, 1) proj_gemm_kernel(const __grid_c
         }
         const int64_t col = col0 + 32 * c32;
         if (p.epi == GRB_GEMM_EPI_F32_ADD) {
-          // fp32 chunk [32 rows][128 B]: lane -> row 4 i + lane / 8, 16-byte chunk lane % 8   (i = 0..7)
-          __syncwarp();
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
-                make_uint4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
-          __syncwarp();
+          // fp32: two passes of 16 columns = 64 bytes per row through the same staging block
           float* o = reinterpret_cast<float*>(p.out0);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = 4 * i + (lane >> 3), c = lane & 7;
-            const float4 v = *reinterpret_cast<const float4*>(stg + rr * 128 + ((c ^ (rr & 7)) << 4));
-            if (row0 + rr < p.M) red_add_v4(o + (row0 + rr) * p.ldo0 + col + 4 * c, v.x, v.y, v.z, v.w);
+          for (int h16 = 0; h16 < 2; ++h16) {
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              *reinterpret_cast<uint4*>(stg + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) =
+                  make_uint4(acc[16 * h16 + 4 * c], acc[16 * h16 + 4 * c + 1], acc[16 * h16 + 4 * c + 2],
+                             acc[16 * h16 + 4 * c + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = 8 * i + (lane >> 2), c = lane & 3;
+              const float4 v = *reinterpret_cast<const float4*>(stg + rr * 64 + ((c ^ ((rr >> 1) & 3)) << 4));
+              if (row0 + rr < p.M) red_add_v4(o + (row0 + rr) * p.ldo0 + col + 16 * h16 + 4 * c, v.x, v.y, v.z, v.w);
+            }
           }
         } else if (p.epi == GRB_GEMM_EPI_SILU2) {
-          uint32_t a16[16], s16[16];
+          uint32_t a16[16];
+#pragma unroll
+          for (int e2 = 0; e2 < 16; ++e2)
+            a16[e2] = pack_bf16x2(__uint_as_float(acc[2 * e2]), __uint_as_float(acc[2 * e2 + 1]));
+          flush_bf16(a16, reinterpret_cast<__nv_bfloat16*>(p.out0), p.ldo0, col);
 #pragma unroll
           for (int e2 = 0; e2 < 16; ++e2) {
-            a16[e2] = pack_bf16x2(__uint_as_float(acc[2 * e2]), __uint_as_float(acc[2 * e2 + 1]));
             // SiLU of the bf16-rounded pre-activation: what a separate silu pass over the stored
             // tensor computes, so forward and backward see the same x
             const float xr0 = __uint_as_float(a16[e2] << 16), xr1 = __uint_as_float(a16[e2] & 0xffff0000u);
-            s16[e2] = pack_bf16x2(silu_fast(xr0), silu_fast(xr1));
+            a16[e2] = pack_bf16x2(silu_fast(xr0), silu_fast(xr1));
           }
-          flush_bf16(a16, reinterpret_cast<__nv_bfloat16*>(p.out0), p.ldo0, col);
-          flush_bf16(s16, reinterpret_cast<__nv_bfloat16*>(p.out1), p.ldo1, col);
+          flush_bf16(a16, reinterpret_cast<__nv_bfloat16*>(p.out1), p.ldo1, col);
         } else {
           const bool br = p.epi == GRB_GEMM_EPI_BIAS_RES;
           uint32_t o16[16];
