@@ -196,6 +196,39 @@ typedef struct grb_hstu_attn_decode_args {
 int grb_hstu_attn_decode(const grb_hstu_attn_decode_args* a, grb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * f2  the steps either side of the HSTU stack, jagged (csrc/input_path.cu):
+ *     embeddings/embeddings.py:94-97 + preprocessors/learnable_positional_embedding.py:42-58 +
+ *     sequential_encoders/hstu.py:502:
+ *        io[t, :] = dropout_p(table[ids[b, i], :] * scale + pos[i, :]) * (ids[b, i] != 0)
+ *     for the jagged row t = offsets[b] + i, i < n_b; rows >= offsets[B] (row buckets) are zero.
+ *     io (rows, D) in dtype (fp32 | bf16).  Dropout: counter-based (Philox4x32-10) keyed by *seed
+ *     (device int64), counter = element index / 4; p_drop == 0: no dropout, seed may be NULL.
+ *     Backward: io holds d(io); d_table (V, D) and d_pos (N, D) fp32 are accumulated (+=) with
+ *     16-byte vector reds (either may be NULL); the same seed regenerates the mask.
+ *     D % 4 == 0, rows 16-byte aligned.
+ *     grb_l2norm_cast_fwd/bwd: postprocessors.py:47-55 on the encoder's jagged rows in the compute
+ *     dtype: y fp32 = x / max(||x||, eps) with x fp32 | bf16; backward writes dx in x's dtype.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct grb_jagged_input_args {
+  int64_t B, N, V, rows;
+  int32_t D, dtype, index_bits, reserved;
+  const float* table; int64_t ldt;
+  const int64_t* ids;              /* (B, N) */
+  const void* offsets;             /* (B+1) */
+  const float* pos; int64_t ldp;   /* (>= N, D) */
+  float scale, p_drop;
+  const int64_t* seed;
+  void* io; int64_t ldio;
+  float* d_table; float* d_pos;
+} grb_jagged_input_args;
+int grb_jagged_input_fwd(const grb_jagged_input_args* a, grb_stream_t stream);
+int grb_jagged_input_bwd(const grb_jagged_input_args* a, grb_stream_t stream);
+int grb_l2norm_cast_fwd(const void* x, int64_t ldx, int dtype, float* y, int64_t ldy, float* inv, int64_t rows,
+                        int64_t W, float eps, grb_stream_t stream);
+int grb_l2norm_cast_bwd(const float* y, int64_t ldy, const float* dy, int64_t lddy, const float* inv, void* dx,
+                        int64_t lddx, int dtype, int64_t rows, int64_t W, grb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * f1  hstu.py:302-320 (UVQK projection + SiLU) and :404-413 (output projection + bias + residual),
  *     forward and backward, as ONE tcgen05 GEMM with fused epilogues (csrc/proj_gemm.cu):
  *        C[M, N] = epilogue(A[M, K] * B[K, N]),  bf16 operands, fp32 accumulation.

@@ -56,6 +56,17 @@ class HstuAttnDecodeArgs(C.Structure):
     ]
 
 
+class JaggedInputArgs(C.Structure):
+    _fields_ = [
+        ("B", c_i64), ("N", c_i64), ("V", c_i64), ("rows", c_i64),
+        ("D", c_i32), ("dtype", c_i32), ("index_bits", c_i32), ("reserved", c_i32),
+        ("table", c_vp), ("ldt", c_i64), ("ids", c_vp), ("offsets", c_vp),
+        ("pos", c_vp), ("ldp", c_i64),
+        ("scale", C.c_float), ("p_drop", C.c_float), ("seed", c_vp),
+        ("io", c_vp), ("ldio", c_i64), ("d_table", c_vp), ("d_pos", c_vp),
+    ]
+
+
 class ProjGemmArgs(C.Structure):
     _fields_ = [
         ("M", c_i64), ("N", c_i64), ("K", c_i64),
@@ -141,6 +152,10 @@ SYMBOLS = {
     "grb_adamw_step": (C.c_int, [C.c_int, C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp),
                                  C.POINTER(c_i64)] + [C.c_double] * 7 + [c_vp]),
     "grb_rows_scatter_add": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_i64, c_i64, c_vp]),
+    "grb_jagged_input_fwd": (C.c_int, [C.POINTER(JaggedInputArgs), c_vp]),
+    "grb_jagged_input_bwd": (C.c_int, [C.POINTER(JaggedInputArgs), c_vp]),
+    "grb_l2norm_cast_fwd": (C.c_int, [c_vp, c_i64, C.c_int, c_vp, c_i64, c_vp, c_i64, c_i64, C.c_float, c_vp]),
+    "grb_l2norm_cast_bwd": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, C.c_int, c_i64, c_i64, c_vp]),
     "grb_proj_gemm": (C.c_int, [C.POINTER(ProjGemmArgs), c_vp]),
     "grb_colsum_bf16": (C.c_int, [c_vp, c_i64, c_i64, c_i32, c_vp, c_vp]),
     "grb_selftest_umma": (C.c_int, [C.POINTER(C.c_float), C.c_int, c_vp]),

@@ -641,6 +641,8 @@ def output_projection(o_in: torch.Tensor, w: torch.Tensor, b: Optional[torch.Ten
 
 
 class _L2Norm(torch.autograd.Function):
+    """x fp32 or bf16 -> y fp32 (the cast of the compute dtype is folded in); dx in x's dtype."""
+
     @staticmethod
     def forward(ctx, x, eps):
         shape = x.shape
@@ -648,10 +650,11 @@ class _L2Norm(torch.autograd.Function):
         rows, W = x2.shape
         y = torch.empty((rows, W), dtype=torch.float32, device=x.device)
         inv = torch.empty(rows, dtype=torch.float32, device=x.device)
-        _lib.check(_lib.lib().grb_l2norm_fwd(x2.data_ptr(), _ld(x2), y.data_ptr(), W, inv.data_ptr(),
-                                             rows, W, float(eps), _lib.stream_ptr(x.device)))
+        _lib.check(_lib.lib().grb_l2norm_cast_fwd(x2.data_ptr(), _ld(x2), _lib.dtype_code(x2.dtype), y.data_ptr(), W,
+                                                  inv.data_ptr(), rows, W, float(eps), _lib.stream_ptr(x.device)))
         ctx.save_for_backward(y, inv)
         ctx.shape = shape
+        ctx.x_dtype = x2.dtype
         return y.view(shape)
 
     @staticmethod
@@ -662,9 +665,10 @@ class _L2Norm(torch.autograd.Function):
         if dy2.dtype != torch.float32:
             dy2 = dy2.float()
         dy2 = _rows_contiguous(dy2)
-        dx = torch.empty((rows, W), dtype=torch.float32, device=y.device)
-        _lib.check(_lib.lib().grb_l2norm_bwd(y.data_ptr(), W, dy2.data_ptr(), _ld(dy2), inv.data_ptr(),
-                                             dx.data_ptr(), W, rows, W, _lib.stream_ptr(y.device)))
+        dx = torch.empty((rows, W), dtype=ctx.x_dtype, device=y.device)
+        _lib.check(_lib.lib().grb_l2norm_cast_bwd(y.data_ptr(), W, dy2.data_ptr(), _ld(dy2), inv.data_ptr(),
+                                                  dx.data_ptr(), W, _lib.dtype_code(ctx.x_dtype), rows, W,
+                                                  _lib.stream_ptr(y.device)))
         return dx.view(ctx.shape), None
 
 
@@ -672,8 +676,8 @@ def l2_normalize(x: torch.Tensor, eps: float) -> torch.Tensor:
     """x / clamp(||x||_2 over the last dim, min=eps): negative_sampler.py:31-37, postprocessors.py:47-55.
     One kernel forward, one backward (fp32 CUDA); other inputs take the reference's composite."""
     _lib.require_cuda(x)
-    if x.dtype == torch.float32 and x.numel() > 0:
-        return _L2Norm.apply(x, eps)
+    if x.dtype in (torch.float32, torch.bfloat16) and x.numel() > 0:
+        return _L2Norm.apply(x, eps)       # bf16 rows (the encoder's compute dtype) come back as fp32
     return x / torch.clamp(torch.linalg.norm(x, ord=None, dim=-1, keepdim=True), min=eps)
 
 
@@ -713,6 +717,66 @@ def embedding_lookup(weight: torch.Tensor, ids: torch.Tensor,
     if weight.dtype != torch.float32:
         return torch.nn.functional.embedding(ids, weight, padding_idx)
     return _EmbeddingLookup.apply(weight, ids, padding_idx)
+
+
+class _JaggedInput(torch.autograd.Function):
+    """embeddings.py:94-97 + learnable_positional_embedding.py:42-58 + hstu.py:502 in one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, table, pos, ids, offsets, rows, scale, p_drop, seed, out_dtype):
+        _lib.require_cuda(table, pos, ids, offsets)
+        if table.dtype != torch.float32 or pos.dtype != torch.float32:
+            raise NotImplementedError("jagged_input: float32 tables only")
+        table, pos = _rows_contiguous(table), _rows_contiguous(pos)
+        ids, offsets = ids.contiguous(), offsets.contiguous()
+        B, N = ids.shape
+        D = table.shape[1]
+        out = torch.empty((rows, D), dtype=out_dtype, device=table.device)
+        a = _JaggedInput._args(table, pos, ids, offsets, rows, scale, p_drop, seed, out)
+        _lib.check(_lib.lib().grb_jagged_input_fwd(C.byref(a), _lib.stream_ptr(table.device)))
+        ctx.save_for_backward(ids, offsets, seed if seed is not None else ids.new_zeros(1))
+        ctx.cfg = (tuple(table.shape), tuple(pos.shape), rows, scale, p_drop, seed is not None)
+        return out
+
+    @staticmethod
+    def _args(table, pos, ids, offsets, rows, scale, p_drop, seed, io):
+        a = _lib.JaggedInputArgs()
+        a.B, a.N = ids.shape
+        a.V, a.D = table.shape if table is not None else (0, io.shape[1])
+        a.rows = rows
+        a.dtype = _lib.dtype_code(io.dtype)
+        a.index_bits = _lib.index_bits(offsets)
+        if table is not None:
+            a.table, a.ldt = table.data_ptr(), table.stride(0)
+        if pos is not None:
+            a.pos, a.ldp = pos.data_ptr(), pos.stride(0)
+        a.ids, a.offsets = ids.data_ptr(), offsets.data_ptr()
+        a.scale, a.p_drop = float(scale), float(p_drop)
+        a.seed = _lib.ptr(seed)
+        a.io, a.ldio = io.data_ptr(), io.stride(0)
+        return a
+
+    @staticmethod
+    def backward(ctx, g):
+        ids, offsets, seed = ctx.saved_tensors
+        (V, D), (Np, _), rows, scale, p_drop, has_seed = ctx.cfg
+        g = _rows_contiguous(g)
+        d_table = torch.zeros((V, D), dtype=torch.float32, device=g.device) if ctx.needs_input_grad[0] else None
+        d_pos = torch.zeros((Np, D), dtype=torch.float32, device=g.device) if ctx.needs_input_grad[1] else None
+        a = _JaggedInput._args(None, None, ids, offsets, rows, scale, p_drop, seed if has_seed else None, g)
+        a.V = V
+        a.d_table, a.d_pos = _lib.ptr(d_table), _lib.ptr(d_pos)
+        _lib.check(_lib.lib().grb_jagged_input_bwd(C.byref(a), _lib.stream_ptr(g.device)))
+        return d_table, d_pos, None, None, None, None, None, None, None
+
+
+def jagged_input(table: torch.Tensor, pos: torch.Tensor, ids: torch.Tensor, offsets: torch.Tensor,
+                 rows: int, scale: float, p_drop: float = 0.0, seed: Optional[torch.Tensor] = None,
+                 out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """Jagged encoder input (rows, D): ``dropout(table[ids] * scale + pos) * (ids != 0)`` for the valid
+    positions only (embeddings.py:94-97, learnable_positional_embedding.py:42-58, hstu.py:502).
+    ``rows`` >= offsets[-1]; extra rows are zero.  ``seed``: device int64 scalar when p_drop > 0."""
+    return _JaggedInput.apply(table, pos, ids, offsets, int(rows), float(scale), float(p_drop), seed, out_dtype)
 
 
 def layer_norm_gate(x: torch.Tensor, gate: Optional[torch.Tensor], eps: float) -> torch.Tensor:

@@ -328,9 +328,11 @@ class HSTUJagged(torch.nn.Module):
     def forward(self, x: torch.Tensor, x_offsets: torch.Tensor,
                 all_timestamps: Optional[torch.Tensor], invalid_attn_mask: torch.Tensor,
                 delta_x_offsets=None, cache=None, return_cache_states: bool = False,
-                total_length: Optional[int] = None, jagged_output: bool = False):
+                total_length: Optional[int] = None, jagged_output: bool = False,
+                rows_padded: bool = False):
         """x: (B, N, D) padded or (T, D) jagged.  Returns (B, N, D), cache states; with
-        ``jagged_output`` the (>= T, D) jagged rows instead (rows past offsets[-1] are padding)."""
+        ``jagged_output`` the (>= T, D) jagged rows instead (rows past offsets[-1] are padding).
+        ``rows_padded``: a jagged x carries zero rows past offsets[-1] (fixed row buckets)."""
         n = invalid_attn_mask.size(1)
         if (self._graph_rows and x.dim() == 3 and total_length is not None and x.is_cuda
                 and torch.is_grad_enabled() and x.requires_grad and self.training
@@ -357,7 +359,7 @@ class HSTUJagged(torch.nn.Module):
         jagged_x, cache_states = self.jagged_forward(
             x=x, x_offsets=x_offsets, all_timestamps=all_timestamps,
             invalid_attn_mask=invalid_attn_mask, delta_x_offsets=delta_x_offsets, cache=cache,
-            return_cache_states=return_cache_states)
+            return_cache_states=return_cache_states, rows_padded=rows_padded)
         if jagged_output:
             return jagged_x, cache_states
         y = ops.jagged_to_padded_dense(values=jagged_x, offsets=x_offsets,
@@ -499,9 +501,10 @@ class HSTU(torch.nn.Module):
     def forward(self, past_lengths: torch.Tensor, user_embeddings: torch.Tensor,
                 valid_mask: torch.Tensor, past_payloads: Dict[str, torch.Tensor],
                 delta_x_offsets=None, cache=None, return_cache_states: bool = False,
-                total_length: Optional[int] = None, jagged_output: bool = False):
-        """past_lengths (B,) int; user_embeddings (B, N, D); valid_mask unused (as :637);
-        past_payloads["timestamps"] (B, N) int64.  Returns ((B, N, D), cache states);
+                total_length: Optional[int] = None, jagged_output: bool = False,
+                rows_padded: bool = False):
+        """past_lengths (B,) int; user_embeddings (B, N, D) (or jagged (T, D), extension); valid_mask
+        unused (as :637); past_payloads["timestamps"] (B, N) int64.  Returns ((B, N, D), cache states);
         ``jagged_output`` (extension) skips the final jagged -> padded copy."""
         # only the mask's size is read downstream: pass the bool buffer itself instead of
         # materialising 1 - mask in the activation dtype every step (256 MB at N = 8192)
@@ -512,4 +515,4 @@ class HSTU(torch.nn.Module):
             invalid_attn_mask=self._attn_mask,
             delta_x_offsets=delta_x_offsets, cache=cache,
             return_cache_states=return_cache_states, total_length=total_length,
-            jagged_output=jagged_output)
+            jagged_output=jagged_output, rows_padded=rows_padded)

@@ -237,6 +237,38 @@ class InBatchNegativesSampler(*((NegativesSampler, _RefInBatch) if _RefInBatch e
         self._cached_ids = uniq
         self._cached_count = count
 
+    def process_batch_table(self, ids: torch.Tensor, prefix_offsets: torch.Tensor, total: int,
+                            table: torch.Tensor, padded: bool = False) -> bool:
+        """``process_batch`` straight from the embedding table (extension): equal ids carry equal
+        embeddings, so the de-duplicated cache is ``normalize(table[unique(valid ids)])`` -- the
+        (B, N, D) embeddings of the batch (retrieval.py:104-111 looks them up a second time) are not
+        needed at all.  ids (B, N) whose valid entries are the first prefix_offsets[b+1] -
+        prefix_offsets[b] of every row, ``total`` of them (an upper bound when ``padded``).  Static
+        shapes, no device sync.  Needs ``dedup_embeddings`` and a small id space (``max_item_id``);
+        returns False (nothing done) otherwise."""
+        from . import functional as GF
+        from . import ops
+        max_id = getattr(self, "max_item_id", None)
+        if not self._dedup_embeddings or max_id is None or max_id >= (1 << 22) or total <= 0:
+            return False
+        valid_ids = ops.dense_to_jagged(ids.unsqueeze(-1), prefix_offsets, total=total,
+                                        zero_tail=padded).squeeze(-1)
+        n = valid_ids.numel()
+        dev = valid_ids.device
+        if padded:       # rows past the real count are padding: id 0
+            live = torch.arange(n, device=dev) < prefix_offsets[-1]
+            valid_ids = torch.where(live, valid_ids, torch.zeros_like(valid_ids))
+        flags = torch.zeros(max_id + 2, dtype=torch.int64, device=dev)
+        flags.scatter_(0, valid_ids, torch.ones_like(valid_ids))
+        flags[0:1].zero_()                                     # id 0 is padding, never a member
+        count = flags.sum()
+        uniq = torch.nonzero_static(flags, size=n, fill_value=0).view(-1)   # ascending ids, then zeros
+        # slots past the count hold id 0 = the padding row: zero embedding, no gradient, never sampled
+        self._cached_embeddings = self._maybe_l2_norm(GF.embedding_lookup(table, uniq, 0))
+        self._cached_ids = uniq
+        self._cached_count = count
+        return True
+
     def get_all_ids_and_embeddings(self) -> Tuple[torch.Tensor, torch.Tensor]:
         if getattr(self, "_cached_count", None) is not None:     # padded cache: trim (host sync)
             c = int(self._cached_count.item())

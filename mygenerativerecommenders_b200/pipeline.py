@@ -359,10 +359,58 @@ class RetrievalModel(torch.nn.Module):
             return self._loss_impl(*inputs, total_length=t_pad, padded=True)
         return self._loss_impl(*inputs, total_length=total_length, padded=False)
 
+    def _loss_impl_jagged(self, lengths, ids, ts, target_ids, target_ts, total_length: int,
+                          padded: bool) -> Optional[torch.Tensor]:
+        """The same step without any padded (B, N, D) tensor: every consumer of
+        ``input_embeddings`` -- the pre-processor, the in-batch cache, the supervision embeddings -- reads
+        the table rows of the VALID positions directly (the pre-processor fused with the gather, the
+        positional embedding, dropout and the cast to the compute dtype in one kernel).  One fp32
+        table, in-batch sampler with a small id space or the local sampler; None = not applicable."""
+        c = self.cfg
+        table = self.embeddings._item_emb.weight
+        if (self.embeddings._year_emb is not None or not table.is_cuda or table.dtype != torch.float32
+                or c.embedding_dim % 4 or total_length is None):
+            return None
+        sf, target_ids = _features_on_device(lengths, ids, ts, target_ids, target_ts, c.gr_output_length + 1)
+        sf.past_ids.scatter_(dim=1, index=sf.past_lengths.view(-1, 1), src=target_ids.view(-1, 1))
+        sup_ids = sf.past_ids
+        off = ops.asynchronous_complete_cumsum(sf.past_lengths)
+        tot = total_length
+        if isinstance(self.negatives_sampler, InBatchNegativesSampler):
+            if not self.negatives_sampler.process_batch_table(
+                    sup_ids, off + torch.arange(off.numel(), device=off.device, dtype=off.dtype),
+                    tot + sup_ids.size(0), table, padded=padded):
+                return None
+        else:
+            self.negatives_sampler._embeddings_module = self.embeddings
+        p_drop = c.dropout if self.training else 0.0
+        seed = (torch.randint(0, 2 ** 62, (1,), device=table.device, dtype=torch.int64) if p_drop > 0 else None)
+        xj = GF.jagged_input(table, self.preprocessor._pos_emb.weight, sup_ids, off, tot,
+                             c.embedding_dim ** 0.5, p_drop, seed,
+                             out_dtype=c.compute_dtype or torch.float32)
+        enc, _ = self.sequence_encoder(past_lengths=sf.past_lengths, user_embeddings=xj, valid_mask=None,
+                                       past_payloads=sf.past_payloads, total_length=tot,
+                                       jagged_output=True, rows_padded=padded)
+        out_rows = self.postprocessor(enc)
+        sup_ids_j = ops.dense_to_jagged(sup_ids[:, 1:], off, total=tot, zero_tail=padded)
+        jag = dict(
+            output_embeddings=out_rows,
+            supervision_ids=sup_ids_j,
+            supervision_embeddings=GF.embedding_lookup(table, sup_ids_j, 0),
+            supervision_weights=(sup_ids_j != 0).float(),
+        )
+        return self.loss.jagged_forward(negatives_sampler=self.negatives_sampler,
+                                        similarity=self.similarity, **jag)
+
     def _loss_impl(self, lengths, ids, ts, target_ids, target_ts, total_length: Optional[int],
                    padded: bool) -> torch.Tensor:
         """``padded``: ``total_length`` is a row bucket >= sum(lengths); every jagged tensor has that
         many rows, the ones past the real total being zero (and weighing zero in the loss)."""
+        import os
+        if os.environ.get("GRB_NO_FUSED_INPUT") != "1":
+            fused = self._loss_impl_jagged(lengths, ids, ts, target_ids, target_ts, total_length, padded)
+            if fused is not None:
+                return fused
         sf, target_ids = _features_on_device(lengths, ids, ts, target_ids, target_ts,
                                              self.cfg.gr_output_length + 1)
         sf.past_ids.scatter_(dim=1, index=sf.past_lengths.view(-1, 1), src=target_ids.view(-1, 1))
