@@ -334,14 +334,18 @@ class HSTUJagged(torch.nn.Module):
         ``jagged_output`` the (>= T, D) jagged rows instead (rows past offsets[-1] are padding).
         ``rows_padded``: a jagged x carries zero rows past offsets[-1] (fixed row buckets)."""
         n = invalid_attn_mask.size(1)
-        if (self._graph_rows and x.dim() == 3 and total_length is not None and x.is_cuda
-                and torch.is_grad_enabled() and x.requires_grad and self.training
-                and all_timestamps is not None and delta_x_offsets is None and cache is None
-                and not return_cache_states):
+        graphable = (self._graph_rows and x.is_cuda and torch.is_grad_enabled() and x.requires_grad
+                     and self.training and all_timestamps is not None and delta_x_offsets is None
+                     and cache is None and not return_cache_states)
+        if graphable and ((x.dim() == 3 and total_length is not None)
+                          or (x.dim() == 2 and rows_padded and x.shape[0] % self._graph_rows == 0)):
             # CUDA-graph path: jagged rows padded with zero rows up to a fixed bucket, so that one
             # captured (forward, backward) pair serves every batch of that bucket
-            t_pad = -(-max(int(total_length), 1) // self._graph_rows) * self._graph_rows
-            xj = ops.dense_to_jagged(x, x_offsets, total=t_pad, zero_tail=True)
+            if x.dim() == 3:
+                t_pad = -(-max(int(total_length), 1) // self._graph_rows) * self._graph_rows
+                xj = ops.dense_to_jagged(x, x_offsets, total=t_pad, zero_tail=True)
+            else:
+                xj = x                   # already jagged and padded to a bucket by the caller
             run = self._graphed_stack(xj, x_offsets, all_timestamps, invalid_attn_mask,
                                       capture=self._graph_lazy)
             if run is not None:

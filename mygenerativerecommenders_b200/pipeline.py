@@ -385,12 +385,17 @@ class RetrievalModel(torch.nn.Module):
             self.negatives_sampler._embeddings_module = self.embeddings
         p_drop = c.dropout if self.training else 0.0
         seed = (torch.randint(0, 2 ** 62, (1,), device=table.device, dtype=torch.int64) if p_drop > 0 else None)
-        xj = GF.jagged_input(table, self.preprocessor._pos_emb.weight, sup_ids, off, tot,
+        # layer-stack CUDA graphs (enable_cuda_graphs): the encoder wants its rows padded to a bucket
+        g_rows = self.sequence_encoder._hstu._graph_rows
+        enc_rows = tot if (padded or not g_rows or not self.training) else -(-max(tot, 1) // g_rows) * g_rows
+        xj = GF.jagged_input(table, self.preprocessor._pos_emb.weight, sup_ids, off, enc_rows,
                              c.embedding_dim ** 0.5, p_drop, seed,
                              out_dtype=c.compute_dtype or torch.float32)
         enc, _ = self.sequence_encoder(past_lengths=sf.past_lengths, user_embeddings=xj, valid_mask=None,
                                        past_payloads=sf.past_payloads, total_length=tot,
-                                       jagged_output=True, rows_padded=padded)
+                                       jagged_output=True, rows_padded=padded or enc_rows != tot)
+        if enc.size(0) != tot:
+            enc = enc[:tot]            # drop the zero rows of the encoder's row bucket
         out_rows = self.postprocessor(enc)
         sup_ids_j = ops.dense_to_jagged(sup_ids[:, 1:], off, total=tot, zero_tail=padded)
         jag = dict(
