@@ -59,7 +59,7 @@ def peaks() -> dict:
 
 
 class ClockSampler:
-    """SM clock / power / throttle reasons sampled every 50 ms while the timed region runs.
+    """SM clock / power / throttle reasons sampled every 10 ms while the timed region runs.
 
     In-process NVML (nvidia_ml_py): spawning `nvidia-smi -lms 200` next to the timed loop costs the
     training step ~40 % (its NVML session contends with kernel launches); the same counters read
@@ -104,7 +104,7 @@ class ClockSampler:
                 self.samples.append((sm, pw, rs))
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.01)
 
     def __exit__(self, *exc):
         self._stop.set()
@@ -338,36 +338,22 @@ def run_training(args, world, rank, local):
             achieved, peak, unit = amount / (tot_ms / 1e3) / 1e12, pk["bf16_tflops_sustained"], "TFLOP/s"
         else:
             achieved, peak, unit = amount / (tot_ms / 1e3) / 1e9, pk["hbm_gbs_sustained"], "GB/s"
-        traffic = None
-        tf = ROOT / "profiles" / "r1_traffic.json"
+        # `traffic` is by definition a profiler figure (dram bytes of one `ncu --set full` capture of this
+        # kernel at this workload): it cannot be measured inside a timed run, so it carries its source
+        traffic, traffic_src = None, None
+        tf = ROOT / "profiles" / "r2_traffic.json"
         if tf.exists():
             ent = json.loads(tf.read_text()).get(name)
             if ent and ent.get("matches_bench_workload"):
-                traffic = ent["dram_bytes_per_launch"]
+                traffic, traffic_src = ent["dram_bytes_per_launch"], f"profiles/r2_traffic.json <- {ent.get('capture')}"
         r = {"kernel": name, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
-             "frac": achieved / peak, "traffic": traffic,
+             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
              "peak_source": pk["source"] + " (sustained figure: kernel timed inside a long step)",
              "algorithmic_work_per_launch": amount / max(n, 1), "avg_launch_ms": tot_ms / max(n, 1)}
         if name.startswith("hstu_attn"):
-            # at the C2 shape a launch is 128 x 4 sequences of <= 211 tokens: 1-2 tiles per CTA, ~6 % of
-            # the executed 128x128 tile area is useful (causal, short) and every tile pays the whole
-            # epilogue, so the launch is bound by epilogue instruction issue, not by the tensor pipe.  The long-sequence figure of the same kernel
-            # (benchmarks/kbench.py, profiles/r1_kbench.jsonl) is attached for context.
-            r["note"] = ("C2 sequences are <= 211 tokens: every 128x128 tile is a diagonal or ragged tile "
-                         "(~6 % useful area) that still costs a full epilogue pass (10-12 k cycles per tile "
-                         "on the clock64 timeline; a persistent-CTA variant measured no gain, DESIGN.md 4); "
-                         "see long_sequence")
-            kb = ROOT / "profiles" / "r1_kbench.jsonl"
-            if kb.exists():
-                for ln in kb.read_text().splitlines():
-                    try:
-                        e = json.loads(ln)
-                    except ValueError:
-                        continue
-                    if e.get("kernel", "").startswith(name + "[C5-slice"):
-                        r["long_sequence"] = {"shape": "4 x 8192 tokens, H=8 (C5 slice)", "ms": e["ms"],
-                                              "tflops": e["tflops"], "frac_of_burst_peak": e["tensor_frac"],
-                                              "source": "profiles/r1_kbench.jsonl"}
+            r["note"] = ("C2 sequences are <= 211 tokens: the short-sequence kernels (csrc/hstu_attn_short.cu, "
+                         "whole sequence per CTA, two CTAs per SM) run here; ~45 % of the executed tile area is "
+                         "causal / ragged padding.  The long-sequence kernels are timed live in `long_sequence`.")
         if name.startswith("sampled_softmax"):
             # the gather source here is the 11 MB in-batch cache, which stays in L2, so
             # the algorithmic gather bytes are served above the HBM peak; the L2 cap is the real bound
@@ -383,6 +369,134 @@ def run_training(args, world, rank, local):
         out["roofline"] = line(dom)
         out["roofline_others"] = [line(k) for k in present if k != dom]
     return out, cfg, ids, model
+
+
+# --------------------------------------------------------------------------------------------
+# long sequences (C5): the configuration on which "attention >= 60 % of the tensor pipe" is testable
+# --------------------------------------------------------------------------------------------
+def _event_ms(fn, iters: int, warmup: int) -> float:
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def run_long_sequence(local: int) -> dict:
+    """Measured in this run (nothing read from profiles/): (1) the long-sequence attention kernels on a
+    C5 slice, 4 sequences x 8192 tokens, H=8, d=64, forward and backward timed alone (burst peak);
+    (2) one full C5 training step (BASELINE.json configs[4]: N=8192, 8 layers, D=512, 8 heads x 64,
+    bf16, local negatives R=128, AdamW) on one GPU, jagged lengths U[1024, 8181], at the largest batch
+    <= 128 that fits."""
+    from mygenerativerecommenders_b200 import _lib
+    from mygenerativerecommenders_b200 import functional as GF
+    from mygenerativerecommenders_b200 import hstu
+    from mygenerativerecommenders_b200.pipeline import RetrievalModel
+    dev = torch.device("cuda", local)
+    pk = peaks()
+    out = {}
+    # ---- (1) attention slice ---------------------------------------------------------------
+    B, N, H, d = 4, 8192, 8, 64
+    lengths = torch.full((B,), N, dtype=torch.int64)
+    off = torch.zeros(B + 1, dtype=torch.int64)
+    off[1:] = torch.cumsum(lengths, 0)
+    T = int(off[-1])
+    g = torch.Generator(device=dev).manual_seed(0)
+    mk = lambda: (torch.randn(T, H * d, device=dev, generator=g) * 0.5).to(torch.bfloat16).requires_grad_(True)
+    q, k, v = mk(), mk(), mk()
+    ts = (978_300_000 + torch.cumsum(torch.randint(1, 5000, (B, N)), 1)).to(dev)
+    ts_w = (torch.randn(129, device=dev) * 0.02).requires_grad_(True)
+    pos_w = (torch.randn(2 * N - 1, device=dev) * 0.02).requires_grad_(True)
+    thr = hstu.tabulate_bucket_thresholds(hstu._default_bucketization, 128).to(dev)
+    offd = off.to(dev)
+    cache = GF.hstu_bucket_cache(offd, ts, thr, N)
+    pairs = int((lengths * (lengths + 1) // 2).sum())
+    fwd = lambda: GF.hstu_attention(q, k, v, offd, ts, ts_w, pos_w, thr, N, H, d, d, bucket_cache=cache)
+    with torch.no_grad():
+        ms_f = _event_ms(fwd, 10, 3)
+    o = fwd()
+    go = torch.randn_like(o)
+    bwd = lambda: torch.autograd.grad(o, (q, k, v, ts_w, pos_w), go, retain_graph=True)
+    ms_b = _event_ms(bwd, 5, 2)
+    f_f, f_b = pairs * 2 * H * 2 * d, pairs * 2 * H * 5 * d
+    out["attention_slice"] = {
+        "shape": "4 x 8192 tokens, H=8, d=64, bf16, relative time+position bias (C5 slice)",
+        "fwd_ms": ms_f, "fwd_tflops": f_f / ms_f / 1e9, "fwd_frac": f_f / ms_f / 1e9 / pk["bf16_tflops"],
+        "bwd_ms": ms_b, "bwd_tflops": f_b / ms_b / 1e9, "bwd_frac": f_b / ms_b / 1e9 / pk["bf16_tflops"],
+        "peak": pk["bf16_tflops"], "peak_source": pk["source"] + " (burst figure: kernels timed alone)",
+        "measured": "live, CUDA events, 10 / 5 launches after warm-up"}
+    del q, k, v, o, go, cache
+    torch.cuda.empty_cache()
+    # ---- (2) full C5 step ------------------------------------------------------------------
+    cfg = RetrievalConfig(
+        name="C5 long-sequence", num_items=131_262, max_sequence_length=8181, gr_output_length=10,
+        embedding_dim=512, num_blocks=8, num_heads=8, attention_dim=64, linear_dim=64, dropout=0.2,
+        sampler="local", num_negatives=128, temperature=0.05, top_k=200, split_year_embedding=False,
+        compute_dtype=torch.bfloat16)
+    ids = synthetic_item_ids(26_744, cfg.num_items)
+    step_info = None
+    for Bc in (128, 64, 32, 16):
+        model = opt = rows = None
+        try:
+            torch.manual_seed(42)
+            model = RetrievalModel(cfg, ids).to(dev).train()
+            opt = FusedAdamW(model.parameters(), lr=1e-3, betas=(0.9, 0.98), weight_decay=1e-3)
+            rows = [{k_: v_.to(dev) for k_, v_ in synthetic_batch(cfg, ids, Bc, seed=500 + i, min_len=1024).items()}
+                    for i in range(2)]
+            totals = [int(r["history_lengths"].sum()) for r in rows]
+            torch.cuda.reset_peak_memory_stats(dev)
+
+            def step(i):
+                loss = model.training_loss(rows[i % 2], totals[i % 2])
+                opt.zero_grad(set_to_none=True)
+                loss.backward()
+                opt.step()
+                return loss
+            step(0)
+            torch.cuda.synchronize()
+            _lib.profile_start()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_it = 3
+            e0.record()
+            for i in range(n_it):
+                loss = step(i + 1)
+            e1.record()
+            torch.cuda.synchronize()
+            prof = _lib.profile_stop()
+            ms = e0.elapsed_time(e1) / n_it
+            lens = [rows[(i + 1) % 2]["history_lengths"] for i in range(n_it)]
+            pr = sum(attention_pairs(l.cpu() + 1) for l in lens) * cfg.num_blocks
+            Hh, dd = cfg.num_heads, cfg.attention_dim
+            att = {}
+            for name, mult in (("hstu_attn_fwd", 2), ("hstu_attn_bwd", 5)):
+                if name in prof:
+                    n_, tot_ = prof[name]
+                    fl = pr * 2 * Hh * mult * dd
+                    att[name] = {"ms_per_step": tot_ / n_it, "tflops": fl / tot_ / 1e9,
+                                 "frac": fl / tot_ / 1e9 / pk["bf16_tflops_sustained"]}
+            step_info = {
+                "workload": "C5 (BASELINE.json configs[4]) on ONE GPU: N=8192, 8 HSTU layers, D=512, 8 heads x 64, "
+                            "bf16 / fp32 master, local negatives R=128, dropout 0.2, AdamW; jagged lengths "
+                            "U[1024, 8181]; fwd+bwd+optimizer, eager (no graphs)",
+                "batch": Bc, "tokens_per_step": sum(totals) / 2, "ms_per_step": ms,
+                "sequences_per_s": Bc / (ms / 1e3), "tokens_per_s": sum(totals) / 2 / (ms / 1e3),
+                "peak_memory_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+                "attention": att, "attention_peak": pk["bf16_tflops_sustained"],
+                "attention_share_of_step": sum(a["ms_per_step"] for a in att.values()) / ms if att else None,
+                "loss": float(loss), "steps_timed": n_it}
+            break
+        except torch.OutOfMemoryError:
+            step_info = {"error": f"out of memory at batch {Bc}"}
+        finally:
+            del model, opt, rows
+            torch.cuda.empty_cache()
+    out["train_step"] = step_info
+    return out
 
 
 # --------------------------------------------------------------------------------------------
@@ -568,7 +682,7 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-retrieval", action="store_true")

@@ -329,6 +329,18 @@ typedef struct grb_mips_topk_args {
   int64_t sample_stride;        /* every sample_stride-th item tile is sampled (>=1); 0 = auto */
   int64_t cand_cap;             /* candidate capacity per row; 0 = auto */
   int32_t* status;              /* device int32[2]: [0] overflow count, [1] reserved */
+  /* f3 (candidate_index.py:125-158 + metrics/retrieval.py:40-68), fused into the final selection;
+   * all optional (NULL / 0 = plain top-k).  invalid_ids (B, n_invalid) int64, row stride
+   * ld_invalid: ids that must not appear in row b's result.  The thresholds are taken for
+   * k' = min(k + n_invalid, X) exactly as the reference over-selects, the last kernel sorts the
+   * best k' of a row in shared memory, drops the invalid ones and writes the first k (rows left
+   * with fewer than k valid entries are padded with (-inf, -1); the reference raises there).
+   * Requires k + n_invalid <= 2048 and n_invalid <= 1024.
+   * target_ids (B) int64 + out_ranks (B) int32: 1 + position of target_ids[b] in row b's result,
+   * k + 1 when absent: the `ranks` every metric of RetrievalMetrics.compute is a function of. */
+  const int64_t* invalid_ids; int64_t ld_invalid; int32_t n_invalid;
+  const int64_t* target_ids;
+  int32_t* out_ranks;
 } grb_mips_topk_args;
 
 /* Bytes of workspace grb_mips_topk needs for these sizes (fills sample_stride/cand_cap if 0). */

@@ -91,6 +91,8 @@ class MipsTopkArgs(C.Structure):
         ("workspace", c_vp), ("workspace_bytes", c_i64),
         ("sample_stride", c_i64), ("cand_cap", c_i64),
         ("status", c_vp),
+        ("invalid_ids", c_vp), ("ld_invalid", c_i64), ("n_invalid", c_i32),
+        ("target_ids", c_vp), ("out_ranks", c_vp),
     ]
 
 

@@ -29,6 +29,13 @@ def _drop_invalid(ids: torch.Tensor, scores: torch.Tensor, invalid_ids: torch.Te
     return torch.gather(ids, 1, pos), torch.gather(scores, 1, pos)
 
 
+def _fused_filter_ok(top_k_module, k: int, n_invalid: int, num_objects: int) -> bool:
+    """The selection kernel drops invalid ids itself when the list fits its shared memory and the
+    reference's own result would hold k entries per row (k + n_invalid <= X)."""
+    return (n_invalid > 0 and hasattr(top_k_module, "forward_filtered") and n_invalid <= 1024
+            and k + n_invalid <= min(2048, num_objects))
+
+
 class CandidateIndex(torch.nn.Module):
     def __init__(self, k: int, ids: torch.Tensor, top_k_module: TopKModule,
                  embeddings: torch.Tensor = None, invalid_ids: Optional[torch.Tensor] = None,
@@ -66,6 +73,11 @@ class CandidateIndex(torch.nn.Module):
         n_invalid = invalid_ids.size(1) if invalid_ids is not None else 0
         if k is None:
             k = self._k
+        if _fused_filter_ok(self._top_k_module, k, n_invalid, self.num_objects):
+            scores, ids = self._top_k_module.forward_filtered(
+                query_embeddings=query_embeddings, item_embeddings_t=self._embeddings_t,
+                item_ids=self._ids, k=k, invalid_ids=invalid_ids)
+            return ids, scores
         k_prime = min(k + n_invalid, self.num_objects)
         scores, ids = self._top_k_module(
             query_embeddings=query_embeddings, item_embeddings_t=self._embeddings_t,
@@ -121,10 +133,20 @@ class ShardedCandidateIndex(CandidateIndex):
         if k is None:
             k = self._k_total
         k_prime = min(k + n_invalid, self._num_total)
-        k_local = min(k_prime, self._ids.size(1))
-        scores, ids = self._top_k_module(
-            query_embeddings=query_embeddings, item_embeddings_t=self._embeddings_t,
-            item_ids=self._ids, k=k_local, sorted=True)
+        fused = _fused_filter_ok(self._top_k_module, k, n_invalid, self._ids.size(1))
+        if fused:
+            # every shard filters its own result: the global top-k of valid items is contained in
+            # the union of the shards' top-k of valid items, so k (not k') entries are exchanged
+            k_prime, invalid_local, invalid_ids = k, invalid_ids, None
+            scores, ids = self._top_k_module.forward_filtered(
+                query_embeddings=query_embeddings, item_embeddings_t=self._embeddings_t,
+                item_ids=self._ids, k=k, invalid_ids=invalid_local)
+            k_local = k
+        else:
+            k_local = min(k_prime, self._ids.size(1))
+            scores, ids = self._top_k_module(
+                query_embeddings=query_embeddings, item_embeddings_t=self._embeddings_t,
+                item_ids=self._ids, k=k_local, sorted=True)
         if self._world > 1:
             per = -(-self._num_total // self._world)
             k_locals = [min(k_prime, max(0, min((r + 1) * per, self._num_total) - min(r * per, self._num_total)))

@@ -190,11 +190,25 @@ __global__ void __launch_bounds__(256) filter_dense_kernel(const float* __restri
 // ---------------------------------------------------------------------------------------------
 constexpr int SEL_KMAX = 2048;
 
+constexpr int SEL_INVALID_MAX = 1024;
+
+// f3 (candidate_index.py:125-158, metrics/retrieval.py:40-68): what the reference does with the
+// (B, k') result of the top-k module — drop ids listed in invalid_ids[row], keep the first k, find
+// the target's rank — happens here on the sorted shared-memory list, so that only (B, k) leaves.
+struct SelectFilter {
+  const int64_t* invalid;  // (B, n_invalid), row stride ld; NULL = none
+  int64_t ld;
+  int n_invalid;
+  int k_out;               // entries written per row (k_out <= k; k - k_out <= n_invalid)
+  const int64_t* target;   // (B) or NULL
+  int32_t* ranks;          // (B) or NULL
+};
+
 template <typename IdT>
 __global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(
     const float* __restrict__ cs, const IdT* __restrict__ cid, const int32_t* __restrict__ counts,
     int64_t cap, int k, const int64_t* __restrict__ id_map, float* __restrict__ out_scores,
-    int64_t* __restrict__ out_ids, int32_t* __restrict__ status) {
+    int64_t* __restrict__ out_ids, int32_t* __restrict__ status, SelectFilter flt) {
   __shared__ int hist[256];
   __shared__ int sh[3];
   __shared__ uint32_t skey[SEL_KMAX];
@@ -295,17 +309,71 @@ __global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(
     }
   }
   const int filled = (int) (c < k ? c : k);
-  for (int r = tid; r < k; r += SEL_THREADS) {
-    float s = -INFINITY;
-    long long id = -1;
-    if (r < filled) {
-      s = fkey_inv(skey[r]);
-      id = sid[r];
-      if (id_map) id = id_map[id];
+  if (!flt.invalid && !flt.ranks) {
+    for (int r = tid; r < k; r += SEL_THREADS) {
+      float s = -INFINITY;
+      long long id = -1;
+      if (r < filled) {
+        s = fkey_inv(skey[r]);
+        id = sid[r];
+        if (id_map) id = id_map[id];
+      }
+      out_scores[row * k + r] = s;
+      out_ids[row * k + r] = id;
     }
-    out_scores[row * k + r] = s;
-    out_ids[row * k + r] = id;
+    return;
   }
+  // ---- filtered tail: real ids, invalid flags, stable compaction to k_out, target rank --------
+  __shared__ long long sinv[SEL_INVALID_MAX];
+  __shared__ int wsum[SEL_THREADS / 32];
+  __shared__ int rank_sh;
+  const int ko = flt.k_out;
+  const int ninv = flt.invalid ? flt.n_invalid : 0;
+  for (int i = tid; i < ninv; i += SEL_THREADS) sinv[i] = flt.invalid[row * flt.ld + i];
+  if (tid == 0) rank_sh = ko + 1;
+  for (int r = tid; r < filled; r += SEL_THREADS)
+    if (id_map) sid[r] = id_map[sid[r]];
+  __syncthreads();
+  const long long tgt = (flt.ranks && flt.target) ? flt.target[row] : 0;
+  // each thread owns a contiguous run of the sorted list so that the compaction keeps its order
+  const int per = (filled + SEL_THREADS - 1) / SEL_THREADS;
+  const int r0 = tid * per, r1 = (r0 + per < filled) ? r0 + per : filled;
+  unsigned long long keepmask = 0;   // per <= 2048 / 256 = 8
+  int nkeep = 0;
+  for (int r = r0; r < r1; ++r) {
+    const long long id = sid[r];
+    bool bad = false;
+    for (int j = 0; j < ninv; ++j) bad |= (sinv[j] == id);
+    if (!bad) { keepmask |= 1ull << (r - r0); ++nkeep; }
+  }
+  int incl = nkeep;
+  const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) wsum[wid] = incl;
+  __syncthreads();
+  int base = incl - nkeep;
+  for (int w = 0; w < wid; ++w) base += wsum[w];
+  int total = 0;
+  for (int w = 0; w < SEL_THREADS / 32; ++w) total += wsum[w];
+  for (int r = r0; r < r1; ++r) {
+    if (!((keepmask >> (r - r0)) & 1ull)) continue;
+    if (base < ko) {
+      out_scores[row * ko + base] = fkey_inv(skey[r]);
+      out_ids[row * ko + base] = sid[r];
+      if (flt.ranks && sid[r] == tgt) atomicMin(&rank_sh, base + 1);
+    }
+    ++base;
+  }
+  for (int r = (total < ko ? total : ko) + tid; r < ko; r += SEL_THREADS) {
+    out_scores[row * ko + r] = -INFINITY;
+    out_ids[row * ko + r] = -1;
+  }
+  __syncthreads();
+  if (flt.ranks && tid == 0) flt.ranks[row] = rank_sh;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -325,20 +393,30 @@ struct MipsPlan {
 
 static int64_t align256(int64_t x) { return (x + 255) & ~255ll; }
 
+// the selection size: the reference over-selects k' = min(k + #invalid ids, X) (candidate_index.py:132)
+static int64_t mips_ksel(const grb_mips_topk_args* a) {
+  const int64_t ks = (int64_t) a->k + (a->invalid_ids ? a->n_invalid : 0);
+  return ks < a->X ? ks : a->X;
+}
+
 static int plan_mips(const grb_mips_topk_args* a, MipsPlan* P) {
   GRB_REQUIRE(a && a->B >= 0 && a->X > 0 && a->D > 0 && a->k > 0, GRB_ERR_INVALID_ARG,
               "mips_topk: bad sizes");
   GRB_REQUIRE(a->k <= a->X, GRB_ERR_INVALID_ARG, "mips_topk: k=%d exceeds corpus size %lld",
               a->k, (long long) a->X);
-  GRB_REQUIRE(a->k <= SEL_KMAX, GRB_ERR_UNSUPPORTED, "mips_topk: k=%d exceeds %d", a->k,
-              SEL_KMAX);
+  GRB_REQUIRE(a->n_invalid >= 0 && a->n_invalid <= SEL_INVALID_MAX && (a->n_invalid == 0 || a->invalid_ids),
+              GRB_ERR_UNSUPPORTED, "mips_topk: n_invalid=%d (at most %d, with a list)", a->n_invalid,
+              SEL_INVALID_MAX);
+  const int64_t ksel = mips_ksel(a);
+  GRB_REQUIRE(ksel <= SEL_KMAX, GRB_ERR_UNSUPPORTED, "mips_topk: k + n_invalid = %lld exceeds %d",
+              (long long) ksel, SEL_KMAX);
   GRB_REQUIRE(a->X < (1ll << 31), GRB_ERR_UNSUPPORTED, "mips_topk: corpus too large");
   P->n_tiles = ceil_div(a->X, MIPS_TILE_N);
   // Phase 0 scores every (R^levels)-th tile; phase p = 1..levels scores the tiles that are
   // multiples of R^(levels-p) but not of R^(levels-p+1), tightening tau[b] in between.  Each
   // refinement phase is expected to add ~(R-1) k candidates per row ((R-1)x the items seen so far).
   auto ipow = [](int l) { int64_t v = 1; for (int i = 0; i < l; ++i) v *= MIPS_RADIX; return v; };
-  int64_t min_tiles = ceil_div(8 * (int64_t) a->k, MIPS_TILE_N);
+  int64_t min_tiles = ceil_div(8 * ksel, MIPS_TILE_N);
   if (min_tiles < 32) min_tiles = 32;
   int levels = 0;
   if (a->sample_stride > 0) {
@@ -354,16 +432,16 @@ static int plan_mips(const grb_mips_topk_args* a, MipsPlan* P) {
     const int64_t last = (P->n_sample_tiles - 1) * stride;
     const int64_t real = (P->n_sample_tiles - 1) * MIPS_TILE_N +
         (last == P->n_tiles - 1 ? a->X - last * MIPS_TILE_N : MIPS_TILE_N);
-    if (real >= a->k) break;
+    if (real >= ksel) break;
     --levels; stride = ipow(levels); P->n_sample_tiles = ceil_div(P->n_tiles, stride);
   }
   P->levels = levels;
   P->stride = stride;
   P->Xs = P->n_sample_tiles * MIPS_TILE_N;
   int64_t cap = a->cand_cap;
-  if (cap <= 0) cap = (int64_t) a->k * (4 + 2 * (MIPS_RADIX - 1) * levels) + 1024;
+  if (cap <= 0) cap = ksel * (4 + 2 * (MIPS_RADIX - 1) * levels) + 1024;
   if (cap > a->X) cap = a->X;
-  if (cap < a->k) cap = a->k;
+  if (cap < ksel) cap = ksel;
   P->cap = cap;
   int64_t o = 0;
   P->off_tau = o;     o = align256(o + a->B * 4);
@@ -442,8 +520,9 @@ int grb_mips_topk(const grb_mips_topk_args* a, grb_stream_t stream) {
   rc = launch_scores(a, epi, P.n_sample_tiles, st);
   if (rc != GRB_OK) return rc;
 
+  const int ksel = (int) mips_ksel(a);
   row_kth_largest_kernel<<<(unsigned) a->B, SEL_THREADS, 0, st>>>(sample, P.Xs, P.Xs, nullptr,
-                                                                  a->k, tau);
+                                                                  ksel, tau);
   GRB_LAUNCH_OK();
   {
     GRB_REQUIRE(a->B <= 65535, GRB_ERR_UNSUPPORTED, "mips_topk: more than 65535 queries per call");
@@ -464,12 +543,16 @@ int grb_mips_topk(const grb_mips_topk_args* a, grb_stream_t stream) {
     }
     if (ph < P.levels) {
       row_kth_largest_kernel<<<(unsigned) a->B, SEL_THREADS, 0, st>>>(cscores, P.cap, P.cap,
-                                                                      counts, a->k, tau);
+                                                                      counts, ksel, tau);
       GRB_LAUNCH_OK();
     }
   }
+  SelectFilter flt{};
+  flt.invalid = a->n_invalid > 0 ? a->invalid_ids : nullptr;
+  flt.ld = a->ld_invalid; flt.n_invalid = a->n_invalid; flt.k_out = a->k;
+  flt.target = a->target_ids; flt.ranks = a->target_ids ? a->out_ranks : nullptr;
   topk_select_kernel<int32_t><<<(unsigned) a->B, SEL_THREADS, 0, st>>>(
-      cscores, cidx, counts, P.cap, a->k, a->item_ids, a->out_scores, a->out_ids, a->status);
+      cscores, cidx, counts, P.cap, ksel, a->item_ids, a->out_scores, a->out_ids, a->status, flt);
   GRB_LAUNCH_OK();
   return GRB_OK;
 }
@@ -483,7 +566,7 @@ int grb_topk_select(const float* cand_scores, const int64_t* cand_ids, const int
   if (B == 0) return GRB_OK;
   topk_select_kernel<int64_t><<<(unsigned) B, SEL_THREADS, 0,
                                 reinterpret_cast<cudaStream_t>(stream)>>>(
-      cand_scores, cand_ids, counts, cap, k, id_map, out_scores, out_ids, nullptr);
+      cand_scores, cand_ids, counts, cap, k, id_map, out_scores, out_ids, nullptr, SelectFilter{});
   GRB_LAUNCH_OK();
   return GRB_OK;
 }

@@ -681,16 +681,64 @@ def l2_normalize(x: torch.Tensor, eps: float) -> torch.Tensor:
     return x / torch.clamp(torch.linalg.norm(x, ord=None, dim=-1, keepdim=True), min=eps)
 
 
+class _TableSink(torch.autograd.Function):
+    """See TableGradScope: stands between the table parameter and the readers of one step."""
+
+    @staticmethod
+    def forward(ctx, table, scope):
+        ctx.scope = scope
+        return table.new_zeros(1)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.scope.take(), None
+
+
+class TableGradScope:
+    """One dense gradient buffer for ALL readers of an embedding table in a step.
+
+    A train step reads the item table several times (encoder input, in-batch cache, supervision
+    embeddings, local negatives).  With plain autograd every reader's backward zero-fills its own
+    (V, D) fp32 tensor, scatters a few thousand rows into it, and the engine adds the dense tensors
+    together: at C2 (131 263 x 256) that is 3 fills + 2 adds of 134 MB each, 0.16 ms of HBM traffic
+    per step for nothing.  Readers given ``grad_scope=`` take a one-element proxy as their
+    differentiable input instead of the table; their backward scatter-adds into ``buffer()`` (zeroed
+    once, by whichever reader runs first) and hands the proxy a one-element token.  The engine runs
+    ``_TableSink.backward`` after every reader that takes part in this backward pass has finished (its
+    ordinary dependency counting), and that returns the buffer as the table's gradient."""
+
+    def __init__(self, table: torch.Tensor):
+        self.table = table
+        self._buf = None
+        self._tok = None
+        self.proxy = _TableSink.apply(table, self) if (table.requires_grad and torch.is_grad_enabled()) else None
+
+    def buffer(self) -> torch.Tensor:
+        if self._buf is None:
+            self._buf = torch.zeros(self.table.shape, dtype=torch.float32, device=self.table.device)
+        return self._buf
+
+    def token(self) -> torch.Tensor:
+        if self._tok is None:
+            self._tok = torch.zeros(1, dtype=self.table.dtype, device=self.table.device)
+        return self._tok
+
+    def take(self):
+        buf, self._buf = self._buf, None
+        return buf
+
+
 class _EmbeddingLookup(torch.autograd.Function):
     """weight[ids] with a scatter-add backward (one launch) instead of
     aten::embedding_dense_backward (sort + segmented reduce, ~30 launches)."""
 
     @staticmethod
-    def forward(ctx, weight, ids, padding_idx):
+    def forward(ctx, weight, ids, padding_idx, proxy=None, scope=None):
         _lib.require_cuda(weight, ids)
         ctx.save_for_backward(ids)
         ctx.shape = weight.shape
         ctx.padding_idx = -1 if padding_idx is None else int(padding_idx)
+        ctx.scope = scope
         return torch.embedding(weight, ids)
 
     @staticmethod
@@ -703,19 +751,25 @@ class _EmbeddingLookup(torch.autograd.Function):
         flat = ids.reshape(-1)
         if flat.dtype != torch.int64 or not flat.is_contiguous():
             flat = flat.to(torch.int64).contiguous()
-        dw = torch.zeros(V, D, device=g.device, dtype=torch.float32)
+        scope = ctx.scope
+        dw = scope.buffer() if scope is not None else torch.zeros(V, D, device=g.device, dtype=torch.float32)
         _lib.check(_lib.lib().grb_rows_scatter_add(
             g2.data_ptr(), g2.stride(0), flat.data_ptr(), dw.data_ptr(), flat.numel(), D, V,
             ctx.padding_idx, _lib.stream_ptr(g.device)))
-        return dw, None, None
+        if scope is not None:
+            return None, None, None, scope.token(), None
+        return dw, None, None, None, None
 
 
-def embedding_lookup(weight: torch.Tensor, ids: torch.Tensor,
-                     padding_idx: Optional[int] = None) -> torch.Tensor:
+def embedding_lookup(weight: torch.Tensor, ids: torch.Tensor, padding_idx: Optional[int] = None,
+                     grad_scope: Optional[TableGradScope] = None) -> torch.Tensor:
     """F.embedding(ids, weight, padding_idx) for fp32 CUDA tables (models/embeddings/
-    embeddings.py:40-101); rows whose id equals padding_idx get no gradient."""
+    embeddings.py:40-101); rows whose id equals padding_idx get no gradient.  ``grad_scope``: the
+    table's gradient goes into the scope's shared buffer (TableGradScope)."""
     if weight.dtype != torch.float32:
         return torch.nn.functional.embedding(ids, weight, padding_idx)
+    if grad_scope is not None and grad_scope.proxy is not None:
+        return _EmbeddingLookup.apply(weight.detach(), ids, padding_idx, grad_scope.proxy, grad_scope)
     return _EmbeddingLookup.apply(weight, ids, padding_idx)
 
 
@@ -723,8 +777,9 @@ class _JaggedInput(torch.autograd.Function):
     """embeddings.py:94-97 + learnable_positional_embedding.py:42-58 + hstu.py:502 in one kernel each way."""
 
     @staticmethod
-    def forward(ctx, table, pos, ids, offsets, rows, scale, p_drop, seed, out_dtype):
+    def forward(ctx, table, pos, ids, offsets, rows, scale, p_drop, seed, out_dtype, proxy=None, scope=None):
         _lib.require_cuda(table, pos, ids, offsets)
+        ctx.scope = scope
         if table.dtype != torch.float32 or pos.dtype != torch.float32:
             raise NotImplementedError("jagged_input: float32 tables only")
         table, pos = _rows_contiguous(table), _rows_contiguous(pos)
@@ -761,21 +816,31 @@ class _JaggedInput(torch.autograd.Function):
         ids, offsets, seed = ctx.saved_tensors
         (V, D), (Np, _), rows, scale, p_drop, has_seed = ctx.cfg
         g = _rows_contiguous(g)
-        d_table = torch.zeros((V, D), dtype=torch.float32, device=g.device) if ctx.needs_input_grad[0] else None
+        scope = ctx.scope
+        if scope is not None:
+            d_table = scope.buffer() if ctx.needs_input_grad[9] else None
+        else:
+            d_table = torch.zeros((V, D), dtype=torch.float32, device=g.device) if ctx.needs_input_grad[0] else None
         d_pos = torch.zeros((Np, D), dtype=torch.float32, device=g.device) if ctx.needs_input_grad[1] else None
         a = _JaggedInput._args(None, None, ids, offsets, rows, scale, p_drop, seed if has_seed else None, g)
         a.V = V
         a.d_table, a.d_pos = _lib.ptr(d_table), _lib.ptr(d_pos)
         _lib.check(_lib.lib().grb_jagged_input_bwd(C.byref(a), _lib.stream_ptr(g.device)))
-        return d_table, d_pos, None, None, None, None, None, None, None
+        if scope is not None:
+            return (None, d_pos) + (None,) * 7 + (scope.token() if d_table is not None else None, None)
+        return (d_table, d_pos) + (None,) * 9
 
 
 def jagged_input(table: torch.Tensor, pos: torch.Tensor, ids: torch.Tensor, offsets: torch.Tensor,
                  rows: int, scale: float, p_drop: float = 0.0, seed: Optional[torch.Tensor] = None,
-                 out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+                 out_dtype: torch.dtype = torch.float32,
+                 grad_scope: Optional[TableGradScope] = None) -> torch.Tensor:
     """Jagged encoder input (rows, D): ``dropout(table[ids] * scale + pos) * (ids != 0)`` for the valid
     positions only (embeddings.py:94-97, learnable_positional_embedding.py:42-58, hstu.py:502).
     ``rows`` >= offsets[-1]; extra rows are zero.  ``seed``: device int64 scalar when p_drop > 0."""
+    if grad_scope is not None and grad_scope.proxy is not None:
+        return _JaggedInput.apply(table.detach(), pos, ids, offsets, int(rows), float(scale), float(p_drop), seed,
+                                  out_dtype, grad_scope.proxy, grad_scope)
     return _JaggedInput.apply(table, pos, ids, offsets, int(rows), float(scale), float(p_drop), seed, out_dtype)
 
 
@@ -884,13 +949,33 @@ def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
     return ws
 
 
-def mips_topk(queries: torch.Tensor, items: torch.Tensor, item_ids: Optional[torch.Tensor],
-              k: int) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Exact top-k of queries @ items.T, sorted descending, ties -> lowest item index.
+class MipsTopkCall:
+    """One enqueued ``grb_mips_topk``: the outputs exist on the device, ordered on the stream; the
+    overflow flag of the candidate workspace is copied to pinned host memory behind them.
+    ``result()`` is where the host consumes the call: it waits for THIS call's flag only (not for the
+    device), re-runs with the exact capacity when a row overflowed (rare: many equal scores) and
+    returns the tensors.  A serving loop keeps one call in flight and asks for ``result()`` one batch
+    later, where it reads the ids anyway; ``mips_topk`` is ``mips_topk_async(...).result()``."""
 
-    queries (B, D), items (X, D) row-major (same dtype, fp32 or bf16); item_ids (X,) int64 or
-    None.  Returns (scores (B, k) fp32, ids (B, k) int64)."""
-    _lib.require_cuda(queries, items, item_ids)
+    def __init__(self, run, outs, flag, done):
+        self._run, self._outs, self._flag, self._done = run, outs, flag, done
+
+    def result(self):
+        for _attempt in range(3):
+            self._done.synchronize()
+            overflow = int(self._flag[0])
+            if overflow == 0:
+                return self._outs
+            # a row had more candidates than the workspace held: exact re-run
+            self._outs, self._flag, self._done = self._run(overflow + 1024)
+        raise RuntimeError("grb200 mips_topk: candidate workspace overflowed repeatedly")
+
+
+def mips_topk_async(queries: torch.Tensor, items: torch.Tensor, item_ids: Optional[torch.Tensor],
+                    k: int, invalid_ids: Optional[torch.Tensor] = None,
+                    target_ids: Optional[torch.Tensor] = None) -> MipsTopkCall:
+    """Enqueue the fused top-k (arguments as ``mips_topk``) without waiting for it."""
+    _lib.require_cuda(queries, items, item_ids, invalid_ids, target_ids)
     if queries.dtype != items.dtype:
         raise ValueError("mips_topk: queries and items must share a dtype")
     queries, items = _rows_contiguous(queries), _rows_contiguous(items)
@@ -902,10 +987,21 @@ def mips_topk(queries: torch.Tensor, items: torch.Tensor, item_ids: Optional[tor
         item_ids = item_ids.contiguous()
         if item_ids.dtype != torch.int64 or item_ids.numel() != X:
             raise ValueError("mips_topk: item_ids must be int64 with one id per item")
+    if invalid_ids is not None:
+        if invalid_ids.dim() != 2 or invalid_ids.shape[0] != B or invalid_ids.dtype != torch.int64:
+            raise ValueError("mips_topk: invalid_ids must be (B, n) int64")
+        invalid_ids = _rows_contiguous(invalid_ids)
+        if invalid_ids.shape[1] == 0:
+            invalid_ids = None
+    if target_ids is not None:
+        target_ids = target_ids.reshape(-1).contiguous()
+        if target_ids.dtype != torch.int64 or target_ids.numel() != B:
+            raise ValueError("mips_topk: target_ids must be int64 with one id per query")
     dev = queries.device
     out_s = torch.empty((B, k), dtype=torch.float32, device=dev)
     out_i = torch.empty((B, k), dtype=torch.int64, device=dev)
-    status = torch.zeros(2, dtype=torch.int32, device=dev)
+    ranks = torch.empty(B, dtype=torch.int32, device=dev) if target_ids is not None else None
+    outs = (out_s, out_i) if ranks is None else (out_s, out_i, ranks)
     a = _lib.MipsTopkArgs()
     a.B, a.X, a.D, a.k = B, X, D, k
     a.dtype = _lib.dtype_code(queries.dtype)
@@ -913,9 +1009,15 @@ def mips_topk(queries: torch.Tensor, items: torch.Tensor, item_ids: Optional[tor
     a.items, a.ldi = items.data_ptr(), _ld(items)
     a.item_ids = _lib.ptr(item_ids)
     a.out_scores, a.out_ids = out_s.data_ptr(), out_i.data_ptr()
-    a.status = status.data_ptr()
-    cap = 0
-    for _attempt in range(3):
+    if invalid_ids is not None:
+        a.invalid_ids, a.ld_invalid, a.n_invalid = invalid_ids.data_ptr(), _ld(invalid_ids), invalid_ids.shape[1]
+    if target_ids is not None:
+        a.target_ids, a.out_ranks = target_ids.data_ptr(), ranks.data_ptr()
+    keep = (queries, items, item_ids, invalid_ids, target_ids)   # alive until the re-run is ruled out
+
+    def run(cap: int):
+        status = torch.zeros(2, dtype=torch.int32, device=dev)
+        a.status = status.data_ptr()
         a.sample_stride, a.cand_cap = 0, cap
         need = int(_lib.lib().grb_mips_topk_workspace_bytes(C.byref(a)))
         if need < 0:
@@ -924,12 +1026,45 @@ def mips_topk(queries: torch.Tensor, items: torch.Tensor, item_ids: Optional[tor
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         with _lib.timed("mips_topk"):
             _lib.check(_lib.lib().grb_mips_topk(C.byref(a), _lib.stream_ptr(dev)))
-        overflow = int(status[0].item())  # the caller consumes the ids on the host anyway
-        if overflow == 0:
-            return out_s, out_i
-        cap = overflow + 1024  # a row had more candidates than the workspace held: exact re-run
-        status.zero_()
-    raise RuntimeError("grb200 mips_topk: candidate workspace overflowed repeatedly")
+        flag = _pinned_flag()
+        flag.copy_(status, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(dev))
+        return outs, flag, done
+
+    call = MipsTopkCall(run, *run(0))
+    call._keep = keep
+    return call
+
+
+_FLAG_POOL: list = []
+
+
+def _pinned_flag() -> torch.Tensor:
+    """Pinned int32[2] landing pads for the overflow flags, recycled round-robin (a flag is read
+    long before 64 further calls have been enqueued)."""
+    if len(_FLAG_POOL) < 64:
+        _FLAG_POOL.append(torch.zeros(2, dtype=torch.int32).pin_memory())
+        return _FLAG_POOL[-1]
+    f = _FLAG_POOL.pop(0)
+    _FLAG_POOL.append(f)
+    return f
+
+
+def mips_topk(queries: torch.Tensor, items: torch.Tensor, item_ids: Optional[torch.Tensor],
+              k: int, invalid_ids: Optional[torch.Tensor] = None,
+              target_ids: Optional[torch.Tensor] = None):
+    """Exact top-k of queries @ items.T, sorted descending, ties -> lowest item index.
+
+    queries (B, D), items (X, D) row-major (same dtype, fp32 or bf16); item_ids (X,) int64 or
+    None.  Returns (scores (B, k) fp32, ids (B, k) int64).
+
+    invalid_ids (B, n) int64: ids that must not appear in row b's result — the filter of
+    candidate_index.py:125-158 inside the selection kernel (thresholds for k' = k + n, the best k'
+    sorted in shared memory, invalid ones dropped, first k written).  target_ids (B,) int64: a third
+    output ranks (B,) int32 = 1 + position of the target in the row's result, k + 1 when absent
+    (metrics/retrieval.py:45-55)."""
+    return mips_topk_async(queries, items, item_ids, k, invalid_ids, target_ids).result()
 
 
 def topk_merge(cand_scores: torch.Tensor, cand_ids: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -238,7 +238,7 @@ class InBatchNegativesSampler(*((NegativesSampler, _RefInBatch) if _RefInBatch e
         self._cached_count = count
 
     def process_batch_table(self, ids: torch.Tensor, prefix_offsets: torch.Tensor, total: int,
-                            table: torch.Tensor, padded: bool = False) -> bool:
+                            table: torch.Tensor, padded: bool = False, grad_scope=None) -> bool:
         """``process_batch`` straight from the embedding table (extension): equal ids carry equal
         embeddings, so the de-duplicated cache is ``normalize(table[unique(valid ids)])`` -- the
         (B, N, D) embeddings of the batch (retrieval.py:104-111 looks them up a second time) are not
@@ -264,7 +264,7 @@ class InBatchNegativesSampler(*((NegativesSampler, _RefInBatch) if _RefInBatch e
         count = flags.sum()
         uniq = torch.nonzero_static(flags, size=n, fill_value=0).view(-1)   # ascending ids, then zeros
         # slots past the count hold id 0 = the padding row: zero embedding, no gradient, never sampled
-        self._cached_embeddings = self._maybe_l2_norm(GF.embedding_lookup(table, uniq, 0))
+        self._cached_embeddings = self._maybe_l2_norm(GF.embedding_lookup(table, uniq, 0, grad_scope=grad_scope))
         self._cached_ids = uniq
         self._cached_count = count
         return True

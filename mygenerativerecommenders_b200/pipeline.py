@@ -376,10 +376,12 @@ class RetrievalModel(torch.nn.Module):
         sup_ids = sf.past_ids
         off = ops.asynchronous_complete_cumsum(sf.past_lengths)
         tot = total_length
+        # every reader of the table below scatters its gradient into ONE dense buffer (GF.TableGradScope)
+        scope = GF.TableGradScope(table)
         if isinstance(self.negatives_sampler, InBatchNegativesSampler):
             if not self.negatives_sampler.process_batch_table(
                     sup_ids, off + torch.arange(off.numel(), device=off.device, dtype=off.dtype),
-                    tot + sup_ids.size(0), table, padded=padded):
+                    tot + sup_ids.size(0), table, padded=padded, grad_scope=scope):
                 return None
         else:
             self.negatives_sampler._embeddings_module = self.embeddings
@@ -390,7 +392,7 @@ class RetrievalModel(torch.nn.Module):
         enc_rows = tot if (padded or not g_rows or not self.training) else -(-max(tot, 1) // g_rows) * g_rows
         xj = GF.jagged_input(table, self.preprocessor._pos_emb.weight, sup_ids, off, enc_rows,
                              c.embedding_dim ** 0.5, p_drop, seed,
-                             out_dtype=c.compute_dtype or torch.float32)
+                             out_dtype=c.compute_dtype or torch.float32, grad_scope=scope)
         enc, _ = self.sequence_encoder(past_lengths=sf.past_lengths, user_embeddings=xj, valid_mask=None,
                                        past_payloads=sf.past_payloads, total_length=tot,
                                        jagged_output=True, rows_padded=padded or enc_rows != tot)
@@ -401,7 +403,7 @@ class RetrievalModel(torch.nn.Module):
         jag = dict(
             output_embeddings=out_rows,
             supervision_ids=sup_ids_j,
-            supervision_embeddings=GF.embedding_lookup(table, sup_ids_j, 0),
+            supervision_embeddings=GF.embedding_lookup(table, sup_ids_j, 0, grad_scope=scope),
             supervision_weights=(sup_ids_j != 0).float(),
         )
         return self.loss.jagged_forward(negatives_sampler=self.negatives_sampler,

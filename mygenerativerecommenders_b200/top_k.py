@@ -32,3 +32,13 @@ class MIPSBruteForceTopK(TopKModule):
         if scores.dtype != query_embeddings.dtype and query_embeddings.dtype == torch.float32:
             scores = scores.to(query_embeddings.dtype)
         return scores, ids
+
+    def forward_filtered(self, query_embeddings: torch.Tensor, item_embeddings_t: torch.Tensor,
+                         item_ids: torch.Tensor, k: int, invalid_ids: torch.Tensor,
+                         target_ids: torch.Tensor = None):
+        """Top-k with the per-row invalid-id filter of candidate_index.py:125-158 (and, with
+        ``target_ids``, the rank of metrics/retrieval.py:45-55) inside the selection kernel: the
+        caller asks for k, not k + invalid_ids.size(1).  Returns (scores, ids[, ranks])."""
+        items = item_embeddings_t.t()
+        return GF.mips_topk(query_embeddings, items, item_ids.reshape(-1), k,
+                            invalid_ids=invalid_ids, target_ids=target_ids)

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     # sizes implied by the header's field lists (8-byte aligned, LP64)
     assert ctypes.sizeof(_lib.HstuAttnArgs) == 4 * 8 + 6 * 4 + 3 * 8 + 3 * 8 + 5 * 8 + 2 * 8 + 2 * 8 + 3 * 8 + 3 * 8 + 3 * 8 + 8 + 8 + 16 + 16
-    assert ctypes.sizeof(_lib.MipsTopkArgs) == 3 * 8 + 2 * 4 + 4 * 8 + 8 + 2 * 8 + 2 * 8 + 2 * 8 + 8
+    assert ctypes.sizeof(_lib.MipsTopkArgs) == 3 * 8 + 2 * 4 + 4 * 8 + 8 + 2 * 8 + 2 * 8 + 2 * 8 + 8 + (8 + 8 + 8) + 8 + 8
     assert ctypes.sizeof(_lib.SslArgs) == 8 + 6 * 4 + 2 * 4 + 8 * 8 + 4 * 8 + 2 * 8 + 5 * 8
 
 

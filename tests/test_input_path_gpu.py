@@ -95,3 +95,36 @@ def test_l2norm_postprocessor_takes_the_compute_dtype(dtype):
     assert x1.grad.dtype == dtype
     tol = 1e-5 if dtype == torch.float32 else 8e-3
     assert (x1.grad.float() - x2.grad).abs().max().item() <= tol * x2.grad.abs().max().item()
+
+
+def test_table_grad_scope_equals_autograd_accumulation():
+    """GF.TableGradScope: three readers of one table scatter into ONE dense buffer; the gradient equals
+    what autograd's add of three dense gradients gives, an unused reader is skipped, and a table that
+    needs no gradient takes the plain path."""
+    lengths, ids, table, pos = _setup(lengths=[36, 0, 5, 17, 1, 36, 20, 9, 3])
+    off = ops.asynchronous_complete_cumsum(lengths)
+    T = int(lengths.sum())
+    pick = torch.randint(0, 200, (77,), device=DEV)
+    pick2 = torch.randint(1, 200, (5, 11), device=DEV)
+    w = [torch.randn(T, 64, device=DEV), torch.randn(77, 64, device=DEV), torch.randn(5, 11, 64, device=DEV)]
+
+    def run(use_scope, use_third=True):
+        t = table.clone().requires_grad_(True)
+        p = pos.clone().requires_grad_(True)
+        sc = GF.TableGradScope(t) if use_scope else None
+        a = GF.jagged_input(t, p, ids, off, T, 8.0, 0.0, None, grad_scope=sc)
+        b = GF.embedding_lookup(t, pick, 0, grad_scope=sc)
+        c = GF.embedding_lookup(t, pick2, 0, grad_scope=sc)
+        loss = (a * w[0]).sum() + (b * w[1]).sum()
+        if use_third:
+            loss = loss + (c * w[2]).sum()
+        loss.backward()
+        return t.grad, p.grad
+
+    for third in (True, False):
+        (g0, p0), (g1, p1) = run(False, third), run(True, third)
+        assert torch.allclose(g0, g1, rtol=1e-5, atol=1e-5) and torch.equal(p0, p1)
+    with torch.no_grad():
+        sc = GF.TableGradScope(table)
+        assert sc.proxy is None
+        assert torch.equal(GF.embedding_lookup(table, pick, 0, grad_scope=sc), table[pick])

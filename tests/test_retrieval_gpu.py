@@ -91,6 +91,56 @@ def test_adversarial_order_forces_exact_rerun():
     assert torch.equal(i.cpu(), ri)
 
 
+@pytest.mark.parametrize("B,X,D,k,n_inv,dtype", [
+    (128, 3883, 50, 200, 211, torch.float32),      # C1/C2: k' = 411 inside the kernel, 200 written
+    (128, 100_000, 64, 200, 61, torch.bfloat16),   # C3-shaped: past ids (128, 61)
+    (9, 5_000, 32, 10, 3, torch.float32),
+    (4, 900, 16, 100, 700, torch.float32),         # most of the best entries are invalid
+])
+def test_invalid_ids_filtered_inside_the_selection(B, X, D, k, n_inv, dtype):
+    """f3: candidate_index.py:125-158 (over-select k + N, compare (B, k', N), keep the first k) against
+    the fused selection that writes k entries; the target's rank against metrics/retrieval.py:45-55."""
+    gen = torch.Generator().manual_seed(B * 7 + n_inv)
+    items = torch.nn.functional.normalize(torch.randn(X, D, generator=gen), dim=-1).to(dtype)
+    q = torch.nn.functional.normalize(torch.randn(B, D, generator=gen), dim=-1).to(dtype)
+    ids = torch.randperm(4 * X, generator=gen)[:X] + 1
+    ri_full, rs_full = O.candidate_index_topk(q, items, ids, min(k + n_inv, X))
+    # invalid lists drawn mostly from each row's own best ids (so the filter bites), 0 = padding
+    invalid = torch.zeros(B, n_inv, dtype=torch.int64)
+    for b in range(B):
+        pick = torch.randperm(ri_full.shape[1], generator=gen)[: n_inv // 2]
+        invalid[b, : pick.numel()] = ri_full[b, pick]
+        invalid[b, pick.numel(): n_inv - 1] = ids[torch.randint(0, X, (n_inv - 1 - pick.numel(),), generator=gen)]
+    ri, rs = O.candidate_index_topk(q, items, ids, k, invalid_ids=invalid)
+    target = ri[:, min(k - 1, 4)].clone()
+    target[::3] = ids.max() + 7                    # absent -> rank k + 1
+    target[1::3] = invalid[1::3, 0]                # filtered out -> absent as well
+    s, i, ranks = GF.mips_topk(q.to(DEV), items.to(DEV), ids.to(DEV), k, invalid_ids=invalid.to(DEV),
+                               target_ids=target.to(DEV))
+    assert i.shape == (B, k)
+    _check_topk(s, i, rs, ri, 1e-5 if dtype == torch.float32 else 2e-5)
+    assert not (i.cpu().unsqueeze(2) == invalid.unsqueeze(1)).any()
+    # metrics/retrieval.py:45-55 on the kernel's own ids
+    _, rank_idx = torch.max(torch.cat([i.cpu(), target.unsqueeze(1)], dim=1) == target.unsqueeze(1), dim=1)
+    assert torch.equal(ranks.cpu().long(), rank_idx + 1)
+    # the module boundary takes the fused path and returns (ids, scores)
+    ci = CandidateIndex(k=k, ids=ids, top_k_module=MIPSBruteForceTopK(),
+                        embeddings=items.unsqueeze(0)).to(DEV)
+    oi, os_ = ci.get_top_k_outputs(q.to(DEV), invalid_ids=invalid.to(DEV))
+    assert torch.equal(oi, i) and torch.equal(os_.float(), s)
+
+
+def test_async_call_defers_the_overflow_check_to_result():
+    X, D, B, k = 60_000, 8, 4, 50
+    items = torch.zeros(X, D)
+    items[:, 0] = torch.linspace(-1, 1, X)         # adversarial order: the first attempt overflows
+    q = torch.zeros(B, D)
+    q[:, 0] = torch.tensor([1.0, 0.5, -1.0, 2.0])
+    call = GF.mips_topk_async(q.to(DEV), items.to(DEV), None, k)
+    s, i = call.result()
+    assert torch.equal(i.cpu(), O.mips_topk(q, items, None, k)[1])
+
+
 def test_topk_merge_matches_global_topk():
     gen = torch.Generator().manual_seed(8)
     B, G, kl, k = 33, 8, 200, 200
