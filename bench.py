@@ -11,9 +11,15 @@ R=128, AdamW; bf16 activations / fp32 master weights), one full train step per "
 GPU).  The same line carries a ``retrieval`` object with the second half of the metric: top-k
 queries/s on C4 (10 M x 256 bf16 items sharded over the ranks, 4096 queries, k=200).
 
-``--impl reference`` times the reference's CPU path (oracle/ref_step.py — the Python reference
-itself does not exist on the GPU box) on the host cores, on a bounded sample of the same
-workload, and prints the same JSON shape with "impl": "reference".
+The line also carries, all measured in the same run: ``long_sequence`` (the long-sequence attention
+kernels on a C5 slice and one full C5 train step), ``retrieval.small_batch`` / ``retrieval.c3`` (the
+HBM-bound side of the top-k path), ``dropin_eager`` (the step as a reference user gets it: eager, no
+graphs, torch AdamW) and ``loss_check`` (the benchmarked model's loss against the CPU oracle).
+
+``--impl reference`` times the reference's CPU path on the host cores: the reference's own modules
+from the staged copy under oracle/_ref (kind "reference"; oracle/stage_ref.py, run by build() where
+/root/reference exists) or, without it, the restatement oracle/ref_step.py (kind "port"), on a
+bounded sample of the same workload, and prints the same JSON shape with "impl": "reference".
 """
 from __future__ import annotations
 
@@ -296,9 +302,59 @@ def run_training(args, world, rank, local):
         step(resident[i % n_batches], totals[i % n_batches])
     prof = _lib.profile_stop()
     launches = (_lib.launch_count() - launches0) * args.steps // n_attr
-    if use_graphs:
-        model.enable_step_graphs(row_granularity=1024, lazy=(world == 1))
     barrier(world)
+
+    # ---- the drop-in path as a reference user gets it (world == 1): same modules, eager (no CUDA
+    # graphs), no host-provided row count (so the jagged ops read their sizes back from the device,
+    # as every call site of the reference does), torch.optim.AdamW instead of the fused optimizer
+    dropin = None
+    if world == 1:
+        opt_t = torch.optim.AdamW(model.parameters(), lr=1e-3, betas=(0.9, 0.98), weight_decay=1e-3)
+
+        def step_t(row):
+            loss = model.training_loss(row)
+            opt_t.zero_grad(set_to_none=True)
+            loss.backward()
+            opt_t.step()
+            return loss
+        n_d = max(5, min(args.steps, 40))
+        for i in range(3):
+            step_t(resident[i % n_batches])
+        torch.cuda.synchronize()
+        l0 = _lib.launch_count()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for i in range(n_d):
+            row = {k: v.to(dev, non_blocking=True) for k, v in pinned[i % n_batches].items()}
+            last_d = float(step_t(row))                      # blocking loss read, as a logger would
+        d1.record()
+        torch.cuda.synchronize()
+        ms_d = d0.elapsed_time(d1)
+        dropin = {"value": PER_GPU_BATCH * n_d / (ms_d / 1e3), "unit": "sequences/s", "ms_per_step": ms_d / n_d,
+                  "steps": n_d, "our_launches_per_step": (_lib.launch_count() - l0) / n_d,
+                  "what": "end to end (pinned H2D batch, blocking loss read), eager modules behind the reference's "
+                          "module boundary, no CUDA graphs, no host-provided total_length, torch.optim.AdamW"}
+        del opt_t
+
+    # ---- parity probe on the benchmarked model: eval mode (no dropout), fixed negative draws; the CPU
+    # side of the comparison runs in the cpu_baseline leg (oracle/ref_step.py on the same weights)
+    probe = None
+    if world == 1:
+        model.eval()
+        smp = model.negatives_sampler
+        row0 = host[0]
+        tot0 = totals[0]
+        raw = torch.randint(0, 2 ** 40, (tot0, cfg.num_negatives), device=dev,
+                            generator=torch.Generator(device=dev).manual_seed(1))
+        orig_draw = smp._draw
+        smp._draw = lambda positive_ids, n: raw[: positive_ids.size(0)] % (
+            smp._cached_count if smp._cached_count is not None else smp._cached_ids.size(0))
+        with torch.no_grad():
+            l_gpu = float(model.training_loss({k: v.to(dev) for k, v in row0.items()}, total_length=tot0))
+        picked = smp._cached_ids[(raw % smp._cached_count)].cpu()
+        smp._draw = orig_draw
+        model.train()
+        probe = {"row": row0, "picked": picked, "loss_gpu": l_gpu}
 
     seqs = PER_GPU_BATCH * world * args.steps
     out = {
@@ -307,6 +363,7 @@ def run_training(args, world, rank, local):
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "d2h": "loss of every step copied to pinned host memory, consumed by the host one step later"},
         "gpu_launches": int(launches), "clocks": clk.summary(), "final_loss": last,
+        "dropin_eager": dropin, "_probe": probe,
     }
     # ---- roofline of the dominant hand-written kernel, from the live per-kernel events -------
     pk = peaks()
@@ -519,21 +576,29 @@ def run_retrieval(args, world, rank, local, X_total=10_000_000, B=4096, D=256, k
                .to(torch.bfloat16) for _ in range(n_q)]
     pinned_q = [q.cpu().pin_memory() for q in queries]
 
-    def once(q):
-        s, i = GF.mips_topk(q, items, item_ids, k)
+    def finish(call):
+        s, i = call.result()            # waits for this call's overflow flag only; exact re-run if set
         if world > 1:
             s, i = merge_sharded_topk(s, i, k, world, k_locals=[k] * world)   # peer-memory exchange
         return s, i
 
+    def run_resident(n):
+        # one call in flight, as in the end-to-end loop below: the host never waits for the device
+        pending = None
+        for i in range(n):
+            call = GF.mips_topk_async(queries[i % n_q], items, item_ids, k)
+            if pending is not None:
+                finish(pending)
+            pending = call
+        finish(pending)
+
     steps = max(2, min(args.steps, 10))
-    for i in range(2):
-        once(queries[i % n_q])
+    run_resident(2)
     barrier(world)
     _lib.profile_start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(steps):
-        once(queries[i % n_q])
+    run_resident(steps)
     e1.record()
     barrier(world)
     ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
@@ -541,25 +606,34 @@ def run_retrieval(args, world, rank, local, X_total=10_000_000, B=4096, D=256, k
     # results land in pinned host buffers (two, alternating) and are consumed one step later, so the
     # copy of step i overlaps the host work of step i + 1 instead of blocking it
     ids_host = [torch.empty((B, k), dtype=torch.int64).pin_memory() for _ in range(2)]
-    copied = [torch.cuda.Event(), torch.cuda.Event()]
     checksum = 0
+
+    def collect(call, i):
+        s_, ids_ = call.result()                                # exact: re-runs if a row overflowed
+        if world > 1:
+            s_, ids_ = merge_sharded_topk(s_, ids_, k, world, k_locals=[k] * world)
+        ids_host[i % 2].copy_(ids_, non_blocking=False)         # D2H of the result, read by the host
+        return int(ids_host[i % 2][0, 0])
     torch.cuda.synchronize()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
+    # one call in flight: step i is enqueued (its overflow flag travels to pinned memory behind the
+    # ids), then the host collects step i - 1 -- the flag check of MipsTopkCall.result() and the ids
+    pending = None
     for i in range(steps):
         q = pinned_q[i % n_q].to(dev, non_blocking=True)
-        s, ids_ = once(q)
-        ids_host[i % 2].copy_(ids_, non_blocking=True)         # D2H of the result
-        copied[i % 2].record()
-        if i > 0:
-            copied[(i - 1) % 2].synchronize()
-            checksum += int(ids_host[(i - 1) % 2][0, 0])       # the host touches every result
-    copied[(steps - 1) % 2].synchronize()
-    checksum += int(ids_host[(steps - 1) % 2][0, 0])
+        call = GF.mips_topk_async(q, items, item_ids, k)
+        if pending is not None:
+            checksum += collect(*pending)
+        pending = (call, i)
+    checksum += collect(*pending)
     e3.record()
     barrier(world)
     ms_e2e = max_over_ranks(e2.elapsed_time(e3), world, dev)
     pk = peaks()
+    extras = {}
+    if world == 1:
+        extras = retrieval_hbm_regime(dev, items, item_ids, pk)
     n_calls, k_ms = prof.get("mips_topk", (steps, ms))
     flop = 2.0 * B * (hi - lo) * D
     byts = (hi - lo) * D * 2 + B * D * 2 + B * k * 12
@@ -579,21 +653,85 @@ def run_retrieval(args, world, rank, local, X_total=10_000_000, B=4096, D=256, k
                      "unit": "TFLOP/s", "frac": flop / t_kernel / 1e12 / pk["bf16_tflops"],
                      "hbm_frac": byts / t_kernel / 1e9 / pk["hbm_gbs"], "traffic": None,
                      "peak_source": pk["source"]},
+        **extras,
     }
+
+
+def retrieval_hbm_regime(dev, items, item_ids, pk) -> dict:
+    """The HBM-bound side of the top-k path (B below ~250 queries), measured live:
+    (1) the C4 corpus at B=128; (2) C3 (BASELINE.json configs[2]): 128 queries x 700 000 x 64 bf16,
+    k=200 with the users' 61 past ids filtered inside the selection (k' = 261 never leaves the
+    kernel); L2 flushed before every timed call (the 90 MB C3 table would otherwise stay resident)."""
+    from mygenerativerecommenders_b200 import functional as GF
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = {}
+
+    def timed(fn, iters=10):
+        for _ in range(3):
+            fn()
+        tot = 0.0
+        for _ in range(iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / iters
+
+    g = torch.Generator(device=dev).manual_seed(7)
+    X, D, k = items.shape[0], items.shape[1], 200
+    q = torch.nn.functional.normalize(torch.randn(128, D, device=dev, generator=g), dim=-1).to(torch.bfloat16)
+    ms = timed(lambda: GF.mips_topk(q, items, item_ids, k))
+    byts = X * D * 2 + 128 * D * 2 + 128 * k * 12
+    out["small_batch"] = {"workload": f"C4 corpus ({X} x {D} bf16), 128 queries, k={k}", "ms": ms,
+                          "queries_per_s": 128 / (ms / 1e3), "gbs": byts / ms / 1e6,
+                          "hbm_frac": byts / ms / 1e6 / pk["hbm_gbs"],
+                          "tensor_frac": 2.0 * 128 * X * D / ms / 1e9 / pk["bf16_tflops"]}
+    X3, D3, n_inv = 700_000, 64, 61
+    items3 = torch.nn.functional.normalize(torch.randn(X3, D3, device=dev, generator=g), dim=-1).to(torch.bfloat16)
+    ids3 = torch.arange(1, X3 + 1, device=dev, dtype=torch.int64)
+    q3 = torch.nn.functional.normalize(torch.randn(128, D3, device=dev, generator=g), dim=-1).to(torch.bfloat16)
+    inv3 = torch.randint(1, X3 + 1, (128, n_inv), device=dev, generator=g)
+    ms3 = timed(lambda: GF.mips_topk(q3, items3, ids3, k, invalid_ids=inv3))
+    byts3 = X3 * D3 * 2 + 128 * D3 * 2 + 128 * k * 12 + 128 * n_inv * 8
+    out["c3"] = {"workload": f"C3 eval batch: 128 queries x {X3} x {D3} bf16, k={k}, {n_inv} invalid ids per "
+                             "query filtered inside the selection", "ms": ms3,
+                 "queries_per_s": 128 / (ms3 / 1e3), "gbs": byts3 / ms3 / 1e6,
+                 "hbm_frac": byts3 / ms3 / 1e6 / pk["hbm_gbs"], "hbm_peak": pk["hbm_gbs"],
+                 "includes": "host time of the call (workspace lookup, launches, overflow-flag read)"}
+    return out
 
 
 # --------------------------------------------------------------------------------------------
 # CPU baseline (the reference's CPU path, oracle port)
 # --------------------------------------------------------------------------------------------
 def cpu_train_baseline(cfg, ids, sample_batch: int, steps: int, warmup: int, state_dict=None):
-    from oracle.ref_step import RefRetrieval
+    """The reference's CPU path on the host cores.  With the staged package (oracle/_ref, written by
+    oracle/stage_ref.py where /root/reference exists) the reference's OWN modules run, unmodified, with
+    their stock Python fallbacks for the jagged ops -- that is `trainer=cpu` (kind "reference").  Without
+    it: oracle/ref_step.py, the restatement (kind "port", ~4x faster than the reference itself)."""
+    from oracle import ref_verbatim
     from mygenerativerecommenders_b200.pipeline import RetrievalModel
     torch.set_num_threads(os.cpu_count() or 1)
     fp32 = RetrievalConfig(**{**cfg.__dict__, "compute_dtype": None})
-    if state_dict is None:
+    if ref_verbatim.available():
         torch.manual_seed(42)
-        state_dict = RetrievalModel(fp32, ids).state_dict()
-    ref = RefRetrieval.from_state_dict(fp32, ids, state_dict).train()
+        ref = ref_verbatim.ReferenceRetrieval(fp32, ids).train()
+        kind = "reference"
+        how = ("the reference's own modules (staged copy of generative_recommenders_pl, unmodified: HSTU with "
+               "the stock Python fallbacks of the jagged ops, in-batch sampler, SampledSoftmaxLoss) driven by "
+               "the restated Retrieval.training_step")
+    else:
+        from oracle.ref_step import RefRetrieval
+        if state_dict is None:
+            torch.manual_seed(42)
+            state_dict = RetrievalModel(fp32, ids).state_dict()
+        ref = RefRetrieval.from_state_dict(fp32, ids, state_dict).train()
+        kind = "port"
+        how = ("oracle/ref_step.py: the reference formulation restated (padded attention, python-loop jagged "
+               "ops, materialised negatives)")
     opt = torch.optim.AdamW(ref.parameters(), lr=1e-3, betas=(0.9, 0.98), weight_decay=1e-3)
     batches = [synthetic_batch(fp32, ids, sample_batch, seed=77 + i) for i in range(2)]
     times = []
@@ -607,28 +745,58 @@ def cpu_train_baseline(cfg, ids, sample_batch: int, steps: int, warmup: int, sta
             times.append(time.perf_counter() - t0)
     total = sum(times)
     return {"value": sample_batch * len(times) / total, "unit": "sequences/s",
-            "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{len(times)} full train steps (fwd+bwd+AdamW) of the C2 model at "
-                      f"batch {sample_batch} (same shapes, fp32, reference formulation: padded "
-                      f"attention, python-loop jagged ops, materialised negatives); "
-                      f"{total:.1f} s of CPU work", "ms_per_step": 1e3 * total / len(times)}
+            "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{len(times)} full train steps (fwd+bwd+AdamW) of the C2 model at batch {sample_batch} "
+                      f"(same shapes, fp32): {how}; {total:.1f} s of CPU work",
+            "ms_per_step": 1e3 * total / len(times)}
 
 
-def cpu_retrieval_baseline(D=256, k=200, Bq=4096, Xs=2_000_000):   # the real query batch, 1/5 of the corpus
+def cpu_loss_check(cfg, ids, state_dict, probe) -> dict:
+    """The benchmarked model's loss on batch 0 (eval mode, the negative draws the GPU made) recomputed
+    by the CPU oracle (oracle/ref_step.py) from the same weights: DESIGN.md section 2 tolerance 1e-3."""
+    from oracle import reference_port as O
+    from oracle.ref_step import RefRetrieval
+    fp32 = RetrievalConfig(**{**cfg.__dict__, "compute_dtype": None})
+    ref = RefRetrieval.from_state_dict(fp32, ids, state_dict).eval()
+    row = probe["row"]
+    lengths, pids, _ = ref.features(row)
+    pids = pids.scatter(1, lengths.view(-1, 1), row["target_ids"].view(-1, 1))
+    flat = pids.reshape(-1)
+    with torch.no_grad():
+        cid, _ = O.inbatch_process(flat, flat != 0, ref.item_emb(flat), ref.cfg.l2_eps, True)
+        order = torch.argsort(cid)
+        pos = torch.searchsorted(cid[order], probe["picked"])
+        l_cpu = float(ref.training_loss(row, neg_draw=order[pos]))
+    rel = abs(probe["loss_gpu"] - l_cpu) / abs(l_cpu)
+    out = {"loss_gpu_bf16": probe["loss_gpu"], "loss_cpu_oracle_fp32": l_cpu, "rel_err": rel, "tol": 1e-3,
+           "ok": rel <= 1e-3, "what": "C2 batch 0, eval mode, same weights and negative draws"}
+    if not out["ok"]:
+        raise SystemExit(f"bench.py: GPU loss {probe['loss_gpu']} vs CPU oracle {l_cpu}: rel err {rel:.2e} > 1e-3")
+    return out
+
+
+def cpu_retrieval_baseline(D=256, k=200, Bq=4096, Xs=1_000_000):   # the real query batch, 1/10 of the corpus
+    from oracle import ref_verbatim
     from oracle.ref_step import torch_topk_baseline
     torch.set_num_threads(os.cpu_count() or 1)
     g = torch.Generator().manual_seed(0)
     items = torch.nn.functional.normalize(torch.randn(Xs, D, generator=g), dim=-1).to(torch.bfloat16)
     q = torch.nn.functional.normalize(torch.randn(Bq, D, generator=g), dim=-1).to(torch.bfloat16)
-    torch_topk_baseline(q[:8], items[:50_000], k)
+    if ref_verbatim.available():
+        fn, kind = ref_verbatim.reference_topk, "reference"
+        how = "MIPSBruteForceTopK.forward of the staged reference (fp32 mm + torch.topk + id gather, 256 queries per call)"
+    else:
+        fn, kind = torch_topk_baseline, "port"
+        how = "fp32 mm + torch.topk, top_k.py:62-69 restated"
+    fn(q[:8], items[:50_000], k)
     t0 = time.perf_counter()
-    torch_topk_baseline(q, items, k)
+    fn(q, items, k)
     dt = time.perf_counter() - t0
     scale = 10_000_000 / Xs
     return {"value": Bq / (dt * scale), "unit": "queries/s", "cores": torch.get_num_threads(),
-            "kind": "port",
-            "sample": f"{Bq} queries x {Xs} items (fp32 mm + torch.topk, top_k.py:62-69) in "
-                      f"{dt:.2f} s, scaled linearly x{scale:.0f} to the 10 M corpus"}
+            "kind": kind,
+            "sample": f"{Bq} queries x {Xs} items ({how}) in {dt:.2f} s, scaled linearly x{scale:.0f} "
+                      "to the 10 M corpus"}
 
 
 def run_reference_arm(args, world, rank):
@@ -637,7 +805,7 @@ def run_reference_arm(args, world, rank):
     cfg = c2_config(bf16=False)
     ids = synthetic_item_ids(26_744, cfg.num_items)
     sample = PER_GPU_BATCH
-    steps = max(1, min(args.steps, 6))
+    steps = max(1, min(args.steps, 3))
     warm = 1 if args.warmup > 0 else 0
     base = cpu_train_baseline(cfg, ids, sample, steps, warm)
     retr = cpu_retrieval_baseline()
@@ -687,6 +855,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-retrieval", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-long-sequence", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -704,6 +873,8 @@ def main():
     del model
     torch.cuda.empty_cache()
     retrieval = None if args.skip_retrieval else run_retrieval(args, world, rank, local)
+    long_seq = run_long_sequence(local) if (world == 1 and not args.skip_long_sequence) else None
+    probe = train.pop("_probe", None)
     line = {
         "metric": "hstu_train_sequences_per_s", "value": train["value"], "unit": "sequences/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -714,12 +885,15 @@ def main():
         "clocks": train["clocks"], "e2e": train["e2e"], "gpu_launches": train["gpu_launches"],
         "roofline": train.get("roofline"), "roofline_others": train.get("roofline_others"),
         "kernels": train["kernels"], "kernels_timed_in": train.get("kernels_timed_in"),
-        "final_loss": train["final_loss"], "retrieval": retrieval,
+        "final_loss": train["final_loss"], "dropin_eager": train.get("dropin_eager"),
+        "long_sequence": long_seq, "retrieval": retrieval,
     }
     if rank == 0:
         if world == 1 and not args.skip_cpu_baseline:
             fp32 = RetrievalConfig(**{**cfg.__dict__, "compute_dtype": None})
-            line["cpu_baseline"] = cpu_train_baseline(fp32, ids, PER_GPU_BATCH, 6, 1, state)   # ~10 s of CPU work
+            if probe is not None:
+                line["loss_check"] = cpu_loss_check(cfg, ids, state, probe)
+            line["cpu_baseline"] = cpu_train_baseline(fp32, ids, PER_GPU_BATCH, 3, 1, state)   # ~20-30 s of CPU work
             if retrieval is not None:
                 retrieval["cpu_baseline"] = cpu_retrieval_baseline()
         _emit(line, out_fd)

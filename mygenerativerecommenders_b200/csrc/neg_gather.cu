@@ -320,10 +320,10 @@ __global__ void __launch_bounds__(SSL_WARPS * 32) ssl_bwd_vec_kernel(SslP P) {
     *reinterpret_cast<float4*>(P.dq + n * (int64_t) P.D + 128 * v + 4 * lane) = dqa[v];
 }
 
-// single table, D = 128 or 256, everything 16-byte aligned
+// single table, D = 128, 256 or 512, everything 16-byte aligned
 static bool ssl_vec_ok(const SslP& P, bool bwd) {
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  if (P.d1 != 0 || (P.D != 128 && P.D != 256)) return false;
+  if (P.d1 != 0 || (P.D != 128 && P.D != 256 && P.D != 512)) return false;
   if (!al(P.q) || !al(P.p) || !al(P.t0) || P.ldq % 4 || P.ldp % 4 || P.ldt0 % 4) return false;
   if (bwd && (!al(P.dq) || !al(P.dp) || !al(P.dt0))) return false;
   return true;
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(256) p2p_put_table_rows_kernel(const float* __
 static int make(const grb_ssl_args* a, SslP* P, bool bwd) {
   GRB_REQUIRE(a != nullptr, GRB_ERR_INVALID_ARG, "sampled_softmax: null args");
   GRB_REQUIRE(a->dtype == GRB_F32, GRB_ERR_UNSUPPORTED, "sampled_softmax: only fp32 tables");
-  GRB_REQUIRE(a->n_rows >= 0 && a->R > 0 && a->D > 0 && a->D <= 256 && a->d0 > 0 &&
+  GRB_REQUIRE(a->n_rows >= 0 && a->R > 0 && a->D > 0 && (a->D <= 256 || (a->D == 512 && a->d1 == 0)) && a->d0 > 0 &&
                   a->d0 + a->d1 == a->D && a->d1 >= 0,
               GRB_ERR_INVALID_ARG, "sampled_softmax: bad sizes (D=%d d0=%d d1=%d R=%d)", a->D,
               a->d0, a->d1, a->R);
@@ -420,6 +420,9 @@ int grb_sampled_softmax_fwd(const grb_ssl_args* a, grb_stream_t stream) {
     if (P.D == 128) {
       if (P.l2) ssl_fwd_vec_kernel<1, true><<<grid, SSL_WARPS * 32, 0, st>>>(P);
       else ssl_fwd_vec_kernel<1, false><<<grid, SSL_WARPS * 32, 0, st>>>(P);
+    } else if (P.D == 512) {   // C5: D = 512
+      if (P.l2) ssl_fwd_vec_kernel<4, true><<<grid, SSL_WARPS * 32, 0, st>>>(P);
+      else ssl_fwd_vec_kernel<4, false><<<grid, SSL_WARPS * 32, 0, st>>>(P);
     } else {
       if (P.l2) ssl_fwd_vec_kernel<2, true><<<grid, SSL_WARPS * 32, 0, st>>>(P);
       else ssl_fwd_vec_kernel<2, false><<<grid, SSL_WARPS * 32, 0, st>>>(P);
@@ -445,6 +448,9 @@ int grb_sampled_softmax_bwd(const grb_ssl_args* a, grb_stream_t stream) {
     if (P.D == 128) {
       if (P.l2) ssl_bwd_vec_kernel<1, true><<<grid, SSL_WARPS * 32, 0, st>>>(P);
       else ssl_bwd_vec_kernel<1, false><<<grid, SSL_WARPS * 32, 0, st>>>(P);
+    } else if (P.D == 512) {   // C5: D = 512
+      if (P.l2) ssl_bwd_vec_kernel<4, true><<<grid, SSL_WARPS * 32, 0, st>>>(P);
+      else ssl_bwd_vec_kernel<4, false><<<grid, SSL_WARPS * 32, 0, st>>>(P);
     } else {
       if (P.l2) ssl_bwd_vec_kernel<2, true><<<grid, SSL_WARPS * 32, 0, st>>>(P);
       else ssl_bwd_vec_kernel<2, false><<<grid, SSL_WARPS * 32, 0, st>>>(P);

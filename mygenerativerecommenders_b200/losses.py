@@ -65,7 +65,8 @@ class SampledSoftmaxLoss(AutoregressiveLoss):
         fused = None
         if (_is_plain_dot(similarity) and output_embeddings.is_cuda
                 and output_embeddings.dtype == torch.float32 and output_embeddings.dim() == 2
-                and output_embeddings.size(1) <= 256 and supervision_ids.size(0) > 1):
+                and (output_embeddings.size(1) <= 256 or output_embeddings.size(1) == 512)
+                and supervision_ids.size(0) > 1):
                 # a reference sampler (no fused_sample) paired with this loss takes the composite below
             fused_sample = getattr(negatives_sampler, "fused_sample", None)
             fused = fused_sample(supervision_ids, self._num_to_sample) if fused_sample is not None else None

@@ -183,3 +183,54 @@ def test_whole_step_cuda_graph_matches_eager(sampler):
         for k in ge:
             scale = max(ge[k].abs().max().item(), 1e-8)
             assert (ge[k] - gg[k]).abs().max().item() <= 2e-3 * scale, k
+
+
+def test_reference_module_code_runs_on_the_gpu_through_the_installed_operator_layer():
+    """b-1 under the reference's OWN module code: the unmodified ``HSTU`` of the staged reference package
+    (oracle/_ref) on the GPU, its ``ops.<fn>`` call sites (hstu.py:179-204, 502, 512, 661) rebound by
+    ``install_ops()`` to this package's kernels, against the same module on the CPU with the stock Python
+    fallbacks: forward and every gradient (fp32, 1e-4 relative to the largest entry)."""
+    import copy
+    import logging
+    import sys
+    from oracle import ref_verbatim as RV
+    if not RV.available():
+        pytest.skip("oracle/_ref is not staged")
+    sys.path.insert(0, str(RV.REF_ROOT))
+    logging.disable(logging.CRITICAL)
+    from generative_recommenders_pl.models.sequential_encoders.hstu import HSTU as RefHSTU
+    from mygenerativerecommenders_b200 import install
+    try:
+        torch.manual_seed(5)
+        B, L, out_len, D = 6, 40, 5, 32
+        N = L + out_len
+        enc = RefHSTU(max_sequence_len=L, max_output_len=out_len, embedding_dim=D, item_embedding_dim=D,
+                      num_blocks=2, num_heads=2, linear_dim=16, attention_dim=16, normalization="rel_bias",
+                      linear_config="uvqk", linear_activation="silu", linear_dropout_rate=0.0,
+                      attn_dropout_rate=0.0).eval()
+        lengths = torch.tensor([45, 3, 17, 30, 1, 22])
+        ts = 978_300_000 + torch.cumsum(torch.randint(1, 5000, (B, N)), dim=1)
+        valid = torch.arange(N).unsqueeze(0) < lengths.unsqueeze(1)
+        ts = ts * valid
+        x = torch.randn(B, N, D) * valid.unsqueeze(-1)
+        xc = x.clone().requires_grad_(True)
+        yc, _ = enc(past_lengths=lengths, user_embeddings=xc, valid_mask=valid.unsqueeze(-1).float(),
+                    past_payloads={"timestamps": ts})
+        w = torch.randn_like(yc)
+        (yc * w).sum().backward()
+        cpu_grads = {k: p.grad.clone() for k, p in enc.named_parameters()}
+        install.install_ops()
+        encg = copy.deepcopy(enc).to(DEV)
+        encg.zero_grad(set_to_none=True)
+        xg = x.to(DEV).requires_grad_(True)
+        yg, _ = encg(past_lengths=lengths.to(DEV), user_embeddings=xg,
+                     valid_mask=valid.unsqueeze(-1).float().to(DEV), past_payloads={"timestamps": ts.to(DEV)})
+        (yg * w.to(DEV)).sum().backward()
+        assert (yg.cpu() - yc).abs().max().item() <= 1e-4 * yc.abs().max().item()
+        assert (xg.grad.cpu() - xc.grad).abs().max().item() <= 1e-4 * xc.grad.abs().max().item()
+        for k, p in encg.named_parameters():
+            assert (p.grad.cpu() - cpu_grads[k]).abs().max().item() <= 1e-4 * cpu_grads[k].abs().max().item(), k
+    finally:
+        install.uninstall()
+        logging.disable(logging.NOTSET)
+        sys.path.remove(str(RV.REF_ROOT))

@@ -125,7 +125,7 @@ def test_invalid_ids_filtered_inside_the_selection(B, X, D, k, n_inv, dtype):
     assert torch.equal(ranks.cpu().long(), rank_idx + 1)
     # the module boundary takes the fused path and returns (ids, scores)
     ci = CandidateIndex(k=k, ids=ids, top_k_module=MIPSBruteForceTopK(),
-                        embeddings=items.unsqueeze(0)).to(DEV)
+                        embeddings=items.to(DEV).unsqueeze(0)).to(DEV)
     oi, os_ = ci.get_top_k_outputs(q.to(DEV), invalid_ids=invalid.to(DEV))
     assert torch.equal(oi, i) and torch.equal(os_.float(), s)
 
@@ -271,7 +271,8 @@ def test_inbatch_sampler_fused_vs_oracle(golden, monkeypatch):
         assert torch.allclose(src.grad.cpu()[m].sum(0), srcc.grad[m].sum(0), rtol=1e-3, atol=1e-6)
 
 
-@pytest.mark.parametrize("D,R,l2", [(256, 128, False), (256, 40, True), (128, 128, True), (128, 33, False)])
+@pytest.mark.parametrize("D,R,l2", [(256, 128, False), (256, 40, True), (128, 128, True), (128, 33, False),
+                                     (512, 128, True), (512, 20, False)])
 def test_fused_sampled_softmax_vector_path(D, R, l2):
     """Single table with D = 128 / 256 takes the float4 kernels (32 negatives reduced together);
     same oracle as the generic path, incl. collisions and a ragged last batch of negatives."""
