@@ -214,18 +214,26 @@ def run_training(args, world, rank, local):
         if world > 1:
             model.precapture_step_graphs([{k: v.to(dev) for k, v in b.items()} for b in host], totals)
     step_mod = TrainStep(model)
+    reducer = None
     if world > 1:
-        if os.environ.get("GRB_NO_P2P") != "1":
-            # the 134 MB item-table gradient is exchanged over peer memory (touched rows only)
+        if os.environ.get("GRB_DDP") != "1":
+            # gradients are reduced over peer memory by this package's kernels: touched rows of the item
+            # table + a two-shot all-reduce of the dense gradients, two stream barriers per step
             try:
-                ignore = ["model." + n for n in model.enable_peer_table_grads()]
-                torch.nn.parallel.DistributedDataParallel._set_params_and_buffers_to_ignore_for_model(
-                    step_mod, ignore)
-            except Exception as e:   # no symmetric memory between these GPUs: dense all-reduce by DDP
-                print(f"[bench] peer-memory table gradients unavailable ({e!r}); using DDP all-reduce",
-                      file=sys.stderr)
-        step_mod = torch.nn.parallel.DistributedDataParallel(
-            step_mod, device_ids=[local], gradient_as_bucket_view=True, broadcast_buffers=False)
+                reducer = model.enable_peer_gradients()
+            except Exception as e:   # no symmetric memory between these GPUs: DistributedDataParallel
+                print(f"[bench] peer-memory gradient reduction unavailable ({e!r}); using DDP", file=sys.stderr)
+        if reducer is None:
+            if os.environ.get("GRB_NO_P2P") != "1":
+                try:
+                    ignore = ["model." + n for n in model.enable_peer_table_grads()]
+                    torch.nn.parallel.DistributedDataParallel._set_params_and_buffers_to_ignore_for_model(
+                        step_mod, ignore)
+                except Exception as e:
+                    print(f"[bench] peer-memory table gradients unavailable ({e!r}); dense all-reduce by DDP",
+                          file=sys.stderr)
+            step_mod = torch.nn.parallel.DistributedDataParallel(
+                step_mod, device_ids=[local], gradient_as_bucket_view=True, broadcast_buffers=False)
     if os.environ.get("GRB_TORCH_ADAMW") == "1":     # A/B switch: the library optimizer
         opt = torch.optim.AdamW(model.parameters(), lr=1e-3, betas=(0.9, 0.98), weight_decay=1e-3, fused=True)
     else:
@@ -237,6 +245,8 @@ def run_training(args, world, rank, local):
         loss = step_mod(row, total)
         opt.zero_grad(set_to_none=True)
         loss.backward()
+        if reducer is not None:
+            reducer.reduce()
         opt.step()
         return loss
 
@@ -832,7 +842,7 @@ def workload_config(cfg, world):
                     "sampled softmax with in-batch negatives R=128 T=0.05, dropout 0.2, AdamW; "
                     "fwd+bwd+optimizer per step; lengths U[20,200]",
         "global_batch": PER_GPU_BATCH * world, "seq_len": cfg.N,
-        "parallelism": f"dp{world}",
+        "parallelism": f"dp{world}" + ("" if world == 1 else (" (DistributedDataParallel)" if os.environ.get("GRB_DDP") == "1" else " (gradients reduced over peer memory: sparse table rows + two-shot all-reduce kernel)")),
         "l2": "per-step working set (134 MB fp32 embedding table + grads + AdamW state, 8 rotating "
               "batches) exceeds the 126 MB L2; no explicit flush",
     }

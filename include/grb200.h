@@ -419,6 +419,13 @@ int grb_rows_scatter_add(const float* grad, int64_t ld_grad, const int64_t* ids,
                          int64_t n, int32_t D, int64_t num_rows, int64_t skip_id,
                          grb_stream_t stream);
 
+/* table[ids[i], :] *= scale for every i with a real id (!= skip_id, in range); ids must be distinct
+ * (the list of rows a batch touched).  Pre-scales the local rows of a data-parallel table gradient
+ * in place, so that the dense (V, D) tensor autograd produced becomes the reduced gradient once the
+ * peers' rows are added (grb_p2p_put_table_rows + grb_rows_scatter_add): no second dense buffer. */
+int grb_rows_scale(float* table, const int64_t* ids, int64_t n, int32_t D, int64_t num_rows,
+                   int64_t skip_id, float scale, grb_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * AdamW step over a list of fp32 tensors, one launch per 64 tensors (the optimizer of the train
  *     step: torch.optim.AdamW as the reference configures it, configs/model/hstu.yaml +
@@ -442,6 +449,18 @@ int grb_adamw_step(int n, float* const* p, const float* const* g, float* const* 
  * ------------------------------------------------------------------------------------------- */
 int grb_p2p_barrier(void* const* signals, int32_t n_ranks, int32_t rank, int32_t slot, int64_t epoch,
                     grb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Data-parallel all-reduce of the dense gradients over peer memory (new; the reference relies on
+ *     Lightning DDP's NCCL all-reduce, configs/trainer/ddp.yaml:4).  Two-shot, in place: rank r reads
+ *     float range [r, r + 1) * ceil(numel / 4 / n_ranks) * 4 of EVERY rank's buffer, sums in rank order,
+ *     multiplies by scale and stores the result into the same range of EVERY rank's buffer.  bufs:
+ *     host array of n_ranks device pointers (symmetric fp32 buffers of numel elements, numel % 4 == 0,
+ *     16-byte aligned).  The caller orders it with grb_p2p_barrier before (every rank's buffer is
+ *     filled) and after (every range has landed everywhere).
+ * ------------------------------------------------------------------------------------------- */
+int grb_p2p_allreduce(void* const* bufs, int32_t n_ranks, int32_t rank, int64_t numel, float scale,
+                      grb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Data-parallel exchange of an embedding-table gradient over peer memory (new; the reference

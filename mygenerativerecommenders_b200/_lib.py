@@ -145,6 +145,7 @@ SYMBOLS = {
     "grb_l2norm_bwd": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]),
     "grb_p2p_put_rows": (C.c_int, [c_vp, c_i64, C.POINTER(c_vp), c_i32, c_i64, c_i64, c_i64, c_i64, c_vp]),
     "grb_p2p_barrier": (C.c_int, [C.POINTER(c_vp), c_i32, c_i32, c_i32, c_i64, c_vp]),
+    "grb_p2p_allreduce": (C.c_int, [C.POINTER(c_vp), c_i32, c_i32, c_i64, C.c_float, c_vp]),
     "grb_p2p_put_table_rows": (C.c_int, [c_vp, c_vp, c_i64, c_i32, c_i64, c_i64, C.c_float, C.POINTER(c_vp),
                                          C.POINTER(c_vp), c_i32, c_i64, c_vp]),
     "grb_hstu_attn_decode": (C.c_int, [C.POINTER(HstuAttnDecodeArgs), c_vp]),
@@ -154,6 +155,7 @@ SYMBOLS = {
     "grb_adamw_step": (C.c_int, [C.c_int, C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp),
                                  C.POINTER(c_i64)] + [C.c_double] * 7 + [c_vp]),
     "grb_rows_scatter_add": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_i64, c_i64, c_vp]),
+    "grb_rows_scale": (C.c_int, [c_vp, c_vp, c_i64, c_i32, c_i64, c_i64, C.c_float, c_vp]),
     "grb_jagged_input_fwd": (C.c_int, [C.POINTER(JaggedInputArgs), c_vp]),
     "grb_jagged_input_bwd": (C.c_int, [C.POINTER(JaggedInputArgs), c_vp]),
     "grb_l2norm_cast_fwd": (C.c_int, [c_vp, c_i64, C.c_int, c_vp, c_i64, c_vp, c_i64, c_i64, C.c_float, c_vp]),

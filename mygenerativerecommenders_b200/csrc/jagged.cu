@@ -215,11 +215,63 @@ __global__ void __launch_bounds__(32) p2p_barrier_kernel(P2pSig sig, int n_ranks
   }
 }
 
+// two-shot all-reduce over peer memory, in place: rank r owns the float4 chunk range
+// [r * per, (r + 1) * per): it reads that range from EVERY rank's buffer (peer loads over NVLink),
+// sums in rank order (so every rank of a group computes bit-identical results), scales, and stores the
+// result into the same range of EVERY rank's buffer (peer stores).  Nobody reads a range it does not
+// own, so reading and writing the same buffers is safe between the two barriers the caller places
+// around the launch.
+struct P2pBufs { float4* p[P2P_MAX_DST]; };
+__global__ void __launch_bounds__(256) p2p_allreduce_kernel(P2pBufs bufs, int n_ranks, int rank, int64_t n4,
+                                                            float scale) {
+  const int64_t per = (n4 + n_ranks - 1) / n_ranks;
+  const int64_t lo = (int64_t) rank * per;
+  int64_t hi = lo + per;
+  if (hi > n4) hi = n4;
+  for (int64_t i = lo + (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < hi;
+       i += (int64_t) gridDim.x * blockDim.x) {
+    float4 v[P2P_MAX_DST];
+#pragma unroll
+    for (int r = 0; r < P2P_MAX_DST; ++r)
+      if (r < n_ranks) v[r] = bufs.p[r][i];          // all loads in flight before the first add
+    float4 acc = v[0];
+#pragma unroll
+    for (int r = 1; r < P2P_MAX_DST; ++r)
+      if (r < n_ranks) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
+    acc.x *= scale; acc.y *= scale; acc.z *= scale; acc.w *= scale;
+#pragma unroll
+    for (int r = 0; r < P2P_MAX_DST; ++r)
+      if (r < n_ranks) bufs.p[r][i] = acc;
+  }
+}
+
 }  // namespace grb
 
 using namespace grb;
 
 extern "C" {
+
+int grb_p2p_allreduce(void* const* bufs, int32_t n_ranks, int32_t rank, int64_t numel, float scale,
+                      grb_stream_t stream) {
+  GRB_REQUIRE(bufs && n_ranks > 0 && n_ranks <= P2P_MAX_DST && rank >= 0 && rank < n_ranks && numel >= 0 &&
+                  numel % 4 == 0,
+              GRB_ERR_INVALID_ARG, "p2p_allreduce: bad arguments (numel must be a multiple of 4)");
+  if (numel == 0) return GRB_OK;
+  P2pBufs b{};
+  for (int i = 0; i < n_ranks; ++i) {
+    GRB_REQUIRE(bufs[i] != nullptr && (reinterpret_cast<uintptr_t>(bufs[i]) & 15) == 0, GRB_ERR_INVALID_ARG,
+                "p2p_allreduce: null or unaligned buffer");
+    b.p[i] = reinterpret_cast<float4*>(bufs[i]);
+  }
+  const int64_t n4 = numel / 4, per = ceil_div(n4, (int64_t) n_ranks);
+  int64_t blocks = ceil_div(per, (int64_t) 256);
+  if (blocks > 1184) blocks = 1184;
+  if (blocks < 1) blocks = 1;
+  p2p_allreduce_kernel<<<(unsigned) blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(b, n_ranks, rank,
+                                                                                            n4, scale);
+  GRB_LAUNCH_OK();
+  return GRB_OK;
+}
 
 int grb_complete_cumsum(const void* lengths, void* offsets, int64_t B, int index_bits,
                         grb_stream_t stream) {

@@ -354,6 +354,22 @@ __global__ void __launch_bounds__(256) rows_scatter_add_kernel(const float* __re
   }
 }
 
+__global__ void __launch_bounds__(256) rows_scale_kernel(float* __restrict__ table, const int64_t* __restrict__ ids,
+                                                         int64_t n, int D, int64_t num_rows, int64_t skip,
+                                                         float scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t) blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const int64_t id = ids[i];
+  if (id == skip || id < 0 || id >= num_rows) return;
+  float* row = table + id * (int64_t) D;
+  for (int c = 4 * lane; c < D; c += 128) {
+    float4 v = *reinterpret_cast<float4*>(row + c);
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    *reinterpret_cast<float4*>(row + c) = v;
+  }
+}
+
 // sender side of the table-gradient exchange: one warp per (slot, destination), 16-byte stores
 struct RowsDst { float* rows[16]; int64_t* ids[16]; };
 __global__ void __launch_bounds__(256) p2p_put_table_rows_kernel(const float* __restrict__ src,
@@ -479,6 +495,19 @@ int grb_rows_scatter_add(const float* grad, int64_t ld_grad, const int64_t* ids,
                    ((reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(table_grad)) & 15) == 0;
   if (vec) rows_scatter_add_kernel<true><<<grid, 256, 0, st>>>(grad, ld_grad, ids, table_grad, n, D, num_rows, skip_id);
   else rows_scatter_add_kernel<false><<<grid, 256, 0, st>>>(grad, ld_grad, ids, table_grad, n, D, num_rows, skip_id);
+  GRB_LAUNCH_OK();
+  return GRB_OK;
+}
+
+int grb_rows_scale(float* table, const int64_t* ids, int64_t n, int32_t D, int64_t num_rows,
+                   int64_t skip_id, float scale, grb_stream_t stream) {
+  using namespace grb;
+  GRB_REQUIRE(table && ids && n >= 0 && D > 0 && D % 4 == 0 && num_rows > 0 &&
+                  (reinterpret_cast<uintptr_t>(table) & 15) == 0,
+              GRB_ERR_INVALID_ARG, "rows_scale: bad arguments (D must be a multiple of 4)");
+  if (n == 0) return GRB_OK;
+  rows_scale_kernel<<<(unsigned) ceil_div(n, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      table, ids, n, D, num_rows, skip_id, scale);
   GRB_LAUNCH_OK();
   return GRB_OK;
 }

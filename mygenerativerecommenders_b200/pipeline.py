@@ -143,26 +143,30 @@ class PeerTableGrads:
     all-reduce (the reference all-reduces the whole (V, D) table under Lightning DDP; at the ml-20m
     shape that is 134 MB per step although a batch touches ~11 k rows).
 
-    Every rank owns a symmetric staging buffer with one (cap, D) block of rows + ids per source
-    rank.  After backward each rank stores ``local_grad[row] / world`` for the rows its batch
-    touched into its block on EVERY rank (``grb_p2p_put_table_rows``: plain 16-byte stores over
-    NVLink / NVSwitch — remote atomics are several times slower), a stream barrier, then each
-    rank scatter-adds its staging buffer into a zeroed dense gradient with local atomics
-    (``grb_rows_scatter_add``); that becomes ``weight.grad``.  Traffic per rank: touched_rows x D x 4
-    bytes per peer.  Exclude the parameter from DDP — this object does its reduction."""
+    Every rank owns TWO symmetric staging buffers (used by alternate steps), each with one (cap, D)
+    block of rows + ids per source rank.  After backward each rank scales the rows its batch touched by
+    1 / world in place in its own dense gradient (``grb_rows_scale``), stores them into its block on
+    every OTHER rank (``grb_p2p_put_table_rows``: plain 16-byte stores over NVLink / NVSwitch — remote
+    atomics are several times slower), one stream barrier, then adds the peers' rows to its dense
+    gradient with local atomics (``grb_rows_scatter_add``): the tensor autograd produced becomes the
+    averaged gradient, no second (V, D) buffer, no zero fill.  The double buffer makes the second
+    barrier per step unnecessary: a rank that is one step ahead writes the OTHER buffer, and it cannot
+    be two steps ahead because of this step's barrier.  Traffic per rank: touched_rows x D x 4 bytes per
+    peer.  Exclude the parameter from DDP — this object does its reduction."""
 
-    def __init__(self, weight: torch.nn.Parameter, group=None) -> None:
+    def __init__(self, weight: torch.nn.Parameter, group=None, hook: bool = True, sync=None) -> None:
         import torch.distributed as dist
-        from .peer import PeerBarrier, symmetric_empty
+        from .peer import PeerBarrier
         self.weight = weight
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.buf = torch.zeros_like(weight, dtype=torch.float32)   # the reduced gradient (local)
-        self.sync = PeerBarrier(group, weight.device)
+        self.sync = sync if sync is not None else PeerBarrier(group, weight.device)
         self.cap = 0                       # staging rows per source rank, fixed by the first batch
+        self.step = 0
         self.touched: Optional[torch.Tensor] = None
         dist.broadcast(weight.data, src=dist.get_global_rank(self.group, 0), group=group)
-        weight.register_post_accumulate_grad_hook(self._hook)
+        if hook:                           # stand-alone use next to DDP: reduce as soon as the gradient exists
+            weight.register_post_accumulate_grad_hook(self._hook)
 
     @torch.no_grad()
     def note_ids(self, *id_tensors: torch.Tensor) -> None:
@@ -177,36 +181,130 @@ class PeerTableGrads:
         flags[0:1].zero_()
         self.touched = torch.nonzero_static(flags, size=n, fill_value=0).view(-1)
 
+    def _allocate(self, n: int, D: int, device) -> None:
+        import torch.distributed as dist
+        from .peer import pointer_array, symmetric_empty
+        self.cap = n
+        self.stage = []
+        for _ in range(2):
+            rows, hr, _ = symmetric_empty((self.world * n, D), torch.float32, device, self.group)
+            ids, hi, _ = symmetric_empty((self.world * n,), torch.int64, device, self.group)
+            ids.zero_()                    # the own block is never written: id 0 = skipped by the scatter
+            peers = [r for r in range(self.world) if r != self.rank]
+            self.stage.append(dict(
+                rows=rows, ids=ids, handles=(hr, hi),
+                dst_rows=pointer_array([hr.buffer_ptrs[r] for r in peers]),
+                dst_ids=pointer_array([hi.buffer_ptrs[r] for r in peers])))
+        torch.cuda.synchronize(device)
+        dist.barrier(group=self.group)     # nobody stores into a peer's buffer before it is zeroed
+
     def _hook(self, param: torch.nn.Parameter) -> None:
+        self.put(param)
+        self.sync.barrier(0, param.device)     # every rank's block has landed everywhere
+        self.add_peers(param)
+
+    def put(self, param: torch.nn.Parameter) -> None:
+        """Scale the touched rows of the local gradient in place and store them into every peer's
+        staging buffer (stream ordered; needs a cross-rank barrier before ``add_peers``)."""
         from . import _lib
         if self.touched is None or param.grad is None:
             raise RuntimeError("PeerTableGrads: note_ids() was not called for this step")
         g = param.grad
         if g.dtype != torch.float32 or not g.is_contiguous():
             g = g.float().contiguous()
+            param.grad = g
         V, D = g.shape
         n = self.touched.numel()
         if self.cap == 0:
-            from .peer import symmetric_empty
-            self.cap = n
-            self.rows, self._hr, self.dst_rows = symmetric_empty((self.world * n, D), torch.float32,
-                                                                  g.device, self.group)
-            self.ids, self._hi, self.dst_ids = symmetric_empty((self.world * n,), torch.int64,
-                                                                g.device, self.group)
+            self._allocate(n, D, g.device)
         elif n != self.cap:
             raise RuntimeError(f"PeerTableGrads: batch shape changed ({n} id slots, staged for {self.cap})")
         stream = _lib.stream_ptr(g.device)
-        self.sync.barrier(0, g.device)     # every rank has consumed its staging buffer of the last step
-        _lib.check(_lib.lib().grb_p2p_put_table_rows(
-            g.data_ptr(), self.touched.data_ptr(), n, D, V, 0, 1.0 / self.world, self.dst_rows,
-            self.dst_ids, self.world, self.rank * n, stream))
-        self.buf.zero_()
-        self.sync.barrier(1, g.device)     # every rank's block has landed everywhere
+        st = self.stage[self.step & 1]
+        L = _lib.lib()
+        _lib.check(L.grb_rows_scale(g.data_ptr(), self.touched.data_ptr(), n, D, V, 0, 1.0 / self.world, stream))
+        if self.world > 1:
+            _lib.check(L.grb_p2p_put_table_rows(
+                g.data_ptr(), self.touched.data_ptr(), n, D, V, 0, 1.0, st["dst_rows"], st["dst_ids"],
+                self.world - 1, self.rank * n, stream))
+
+    def add_peers(self, param: torch.nn.Parameter) -> None:
+        from . import _lib
+        g = param.grad
+        V, D = g.shape
+        st = self.stage[self.step & 1]
+        self.step += 1
         _lib.check(_lib.lib().grb_rows_scatter_add(
-            self.rows.data_ptr(), D, self.ids.data_ptr(), self.buf.data_ptr(), self.world * n, D, V, 0,
-            stream))
-        param.grad = self.buf
+            st["rows"].data_ptr(), D, st["ids"].data_ptr(), g.data_ptr(), self.world * self.cap, D, V, 0,
+            _lib.stream_ptr(g.device)))
         self.touched = None
+
+
+class PeerGradients:
+    """Data-parallel gradient reduction of a whole model over peer memory (no DistributedDataParallel,
+    no NCCL call on the data path): the reference's `strategy: ddp` (configs/trainer/ddp.yaml:4) as two
+    kernels of this package between two stream barriers per step.
+
+    * item table (in-batch sampler): sparse rows, ``PeerTableGrads.put`` / ``add_peers``;
+    * every other parameter: the gradients are gathered into one symmetric fp32 buffer and
+      all-reduced in place by ``grb_p2p_allreduce`` (two-shot: each rank sums its 1 / world slice of
+      every rank's buffer with peer loads and stores the average into every rank's buffer with peer
+      stores); ``param.grad`` then views that buffer.
+
+    ``reduce()`` goes between ``loss.backward()`` and the optimizer.  Under DDP the all-reduce of a
+    graph-replayed backward cannot overlap anything (the whole backward is one autograd node, every
+    bucket fires at its end) and costs 0.13 ms of launch + ring latency per step for 5 MB; this costs
+    the barriers (the slowest rank's arrival) plus ~20 us.  Sums run in rank order, so all ranks hold
+    bit-identical gradients."""
+
+    def __init__(self, model: "RetrievalModel", group=None) -> None:
+        import torch.distributed as dist
+        from .peer import PeerBarrier, symmetric_empty
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        table = model.embeddings._item_emb.weight
+        dev = table.device
+        self.sync = PeerBarrier(group, dev)
+        self.table = None
+        if isinstance(model.negatives_sampler, InBatchNegativesSampler):
+            self.table = PeerTableGrads(table, group, hook=False, sync=self.sync)
+            object.__setattr__(model, "_peer_grads", self.table)
+        self.dense = [p for p in model.parameters() if p.requires_grad and (self.table is None or p is not table)]
+        src = dist.get_global_rank(self.group, 0)
+        for p in self.dense:
+            dist.broadcast(p.data, src=src, group=group)
+        sizes = [-(-p.numel() // 4) * 4 for p in self.dense]        # every view 16-byte aligned
+        total = sum(sizes)
+        self.flat, self._h, self.ptrs = symmetric_empty((max(total, 4),), torch.float32, dev, self.group)
+        self.flat.zero_()
+        self.views, o = [], 0
+        for p, sz in zip(self.dense, sizes):
+            self.views.append(self.flat[o:o + p.numel()].view(p.shape))
+            o += sz
+        self.numel = total
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=self.group)
+
+    @torch.no_grad()
+    def reduce(self) -> None:
+        from . import _lib
+        dev = self.flat.device
+        if self.table is not None:
+            self.table.put(self.table.weight)
+        have = [(v, p.grad) for v, p in zip(self.views, self.dense) if p.grad is not None]
+        for v, p in zip(self.views, self.dense):
+            if p.grad is None:
+                v.zero_()
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        self.sync.barrier(0, dev)          # peers' table rows have landed; every rank's flat buffer is filled
+        if self.table is not None:
+            self.table.add_peers(self.table.weight)
+        _lib.check(_lib.lib().grb_p2p_allreduce(self.ptrs, self.world, self.rank, self.numel, 1.0 / self.world,
+                                                _lib.stream_ptr(dev)))
+        self.sync.barrier(1, dev)          # every slice has landed everywhere
+        for v, p in zip(self.views, self.dense):
+            p.grad = v
 
 
 class _StepStack(torch.nn.Module):
@@ -303,6 +401,11 @@ class RetrievalModel(torch.nn.Module):
             raise NotImplementedError("enable_peer_table_grads needs the in-batch negatives sampler")
         object.__setattr__(self, "_peer_grads", PeerTableGrads(self.embeddings._item_emb.weight, group))
         return ["embeddings._item_emb.weight"]
+
+    def enable_peer_gradients(self, group=None) -> "PeerGradients":
+        """Multi-GPU training without DistributedDataParallel: returns the reducer whose ``reduce()``
+        goes between ``backward()`` and the optimizer step (PeerGradients)."""
+        return PeerGradients(self, group)
 
     def precapture_step_graphs(self, rows, total_lengths) -> int:
         for row, tot in zip(rows, total_lengths):

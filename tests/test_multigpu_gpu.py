@@ -98,3 +98,56 @@ def test_peer_memory_table_gradient_equals_allreduce(tmp_path):
     world = 2
     mp.spawn(_worker_table_grads, args=(world, 29900 + os.getpid() % 90, str(tmp_path)), nprocs=world,
              join=True)
+
+
+def _worker_all_grads(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from mygenerativerecommenders_b200.pipeline import (RetrievalConfig, RetrievalModel,
+                                                        synthetic_batch, synthetic_item_ids)
+    cfg = RetrievalConfig(name="p", num_items=500, max_sequence_length=40, gr_output_length=5,
+                          embedding_dim=128, num_blocks=2, num_heads=2, attention_dim=64,
+                          linear_dim=64, dropout=0.0, sampler="inbatch", num_negatives=16, top_k=20,
+                          split_year_embedding=False, compute_dtype=torch.bfloat16)
+    ids = synthetic_item_ids(300, cfg.num_items, seed=1)
+    torch.manual_seed(0)
+    m = RetrievalModel(cfg, ids).to(dev).train()
+    row = synthetic_batch(cfg, ids, 6, seed=10 + rank, min_len=2)      # a different batch per rank
+    n_rows = int(row["history_lengths"].sum())
+    raw = torch.randint(0, 2 ** 40, (n_rows, cfg.num_negatives), device=dev)
+    smp = m.negatives_sampler
+    smp._draw = lambda p, n: raw % smp._cached_count
+    # reference: every gradient averaged with NCCL
+    m.training_loss({k: v.clone() for k, v in row.items()}, total_length=n_rows).backward()
+    ref = {}
+    for name, p in m.named_parameters():
+        g = p.grad.clone()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        ref[name] = g / world
+    red = m.enable_peer_gradients()
+    for _ in range(3):          # buffers are reused step after step
+        m.zero_grad(set_to_none=True)
+        m.training_loss({k: v.clone() for k, v in row.items()}, total_length=n_rows).backward()
+        red.reduce()
+        for name, p in m.named_parameters():
+            scale = max(ref[name].abs().max().item(), 1e-30)
+            assert (p.grad - ref[name]).abs().max().item() <= 1e-5 * scale, name
+    # all ranks hold bit-identical dense gradients (sums run in rank order)
+    flat = red.flat.clone()
+    other = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(other, flat)
+    assert all(torch.equal(o, other[0]) for o in other)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_peer_memory_gradient_reduction_equals_allreduce(tmp_path):
+    """PeerGradients (sparse table rows + two-shot all-reduce kernel over peer memory, no DDP) against
+    NCCL averages of the same per-rank gradients."""
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_worker_all_grads, args=(world, 29700 + os.getpid() % 90, str(tmp_path)), nprocs=world, join=True)
