@@ -695,7 +695,11 @@ def retrieval_hbm_regime(dev, items, item_ids, pk) -> dict:
     q = torch.nn.functional.normalize(torch.randn(128, D, device=dev, generator=g), dim=-1).to(torch.bfloat16)
     ms = timed(lambda: GF.mips_topk(q, items, item_ids, k))
     byts = X * D * 2 + 128 * D * 2 + 128 * k * 12
+    gr = GF.MipsTopkGraph(128, items, item_ids, k)
+    ms_g = timed(lambda: gr(q))
+    assert not gr.overflowed()
     out["small_batch"] = {"workload": f"C4 corpus ({X} x {D} bf16), 128 queries, k={k}", "ms": ms,
+                          "graph_ms": ms_g, "graph_hbm_frac": byts / ms_g / 1e6 / pk["hbm_gbs"],
                           "queries_per_s": 128 / (ms / 1e3), "gbs": byts / ms / 1e6,
                           "hbm_frac": byts / ms / 1e6 / pk["hbm_gbs"],
                           "tensor_frac": 2.0 * 128 * X * D / ms / 1e9 / pk["bf16_tflops"]}
@@ -706,8 +710,15 @@ def retrieval_hbm_regime(dev, items, item_ids, pk) -> dict:
     inv3 = torch.randint(1, X3 + 1, (128, n_inv), device=dev, generator=g)
     ms3 = timed(lambda: GF.mips_topk(q3, items3, ids3, k, invalid_ids=inv3))
     byts3 = X3 * D3 * 2 + 128 * D3 * 2 + 128 * k * 12 + 128 * n_inv * 8
+    gr3 = GF.MipsTopkGraph(128, items3, ids3, k, n_invalid=n_inv)
+    ms3_g = timed(lambda: gr3(q3, inv3))
+    assert not gr3.overflowed()
+    assert torch.equal(gr3(q3, inv3)[1], GF.mips_topk(q3, items3, ids3, k, invalid_ids=inv3)[1])
     out["c3"] = {"workload": f"C3 eval batch: 128 queries x {X3} x {D3} bf16, k={k}, {n_inv} invalid ids per "
                              "query filtered inside the selection", "ms": ms3,
+                 "graph_ms": ms3_g, "graph_hbm_frac": byts3 / ms3_g / 1e6 / pk["hbm_gbs"],
+                 "graph": "the same call replayed as one CUDA graph (GF.MipsTopkGraph: static buffers, no Python "
+                          "between the launches)",
                  "queries_per_s": 128 / (ms3 / 1e3), "gbs": byts3 / ms3 / 1e6,
                  "hbm_frac": byts3 / ms3 / 1e6 / pk["hbm_gbs"], "hbm_peak": pk["hbm_gbs"],
                  "includes": "host time of the call (workspace lookup, launches, overflow-flag read)"}

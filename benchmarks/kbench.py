@@ -265,6 +265,10 @@ def main():
         for g in (2, 4, 8):
             bench_mips(f"C4 shard 1/{g}: B4096 X{10_000_000 // g} D256 k200 bf16", 4096, 10_000_000 // g, 256,
                        200, torch.bfloat16)
+    if "mipsshard8" in which:
+        bench_mips("C4 shard 1/8: B4096 X1250000 D256 k200 bf16", 4096, 1_250_000, 256, 200, torch.bfloat16)
+    if "mipsc3" in which:
+        bench_mips("C3 B128 X700k D64 k261 bf16", 128, 700_000, 64, 261, torch.bfloat16)
     if "mipsshard4" in which:
         bench_mips("C4 shard 1/4: B4096 X2500000 D256 k200 bf16", 4096, 2_500_000, 256, 200, torch.bfloat16)
     if "mipsc4" in which:

@@ -1067,6 +1067,74 @@ def mips_topk(queries: torch.Tensor, items: torch.Tensor, item_ids: Optional[tor
     return mips_topk_async(queries, items, item_ids, k, invalid_ids, target_ids).result()
 
 
+class MipsTopkGraph:
+    """Fixed-shape fused top-k replayed as ONE CUDA graph (serving: the same (B, D) query batch shape
+    against the same corpus, call after call).  ``grb_mips_topk`` is a chain of ~11 small stream-ordered
+    launches; at small batches (the HBM-bound regime) their launch latencies and the Python
+    side of the call cost more than the kernels.  The graph owns static query / invalid-id / output
+    buffers and its own workspace; ``__call__`` copies the inputs in, replays, and returns the static
+    outputs (valid until the next call).  The overflow flag stays on the device: ``overflowed()`` reads
+    it (host sync) — when set, fall back to ``mips_topk`` for that batch (exact re-run)."""
+
+    def __init__(self, batch: int, items: torch.Tensor, item_ids: Optional[torch.Tensor], k: int,
+                 n_invalid: int = 0, with_ranks: bool = False) -> None:
+        _lib.require_cuda(items, item_ids)
+        items = _rows_contiguous(items)
+        dev = items.device
+        X, D = items.shape
+        self.items, self.item_ids = items, (item_ids.contiguous() if item_ids is not None else None)
+        self.q = torch.zeros((batch, D), dtype=items.dtype, device=dev)
+        self.invalid = torch.zeros((batch, n_invalid), dtype=torch.int64, device=dev) if n_invalid else None
+        self.target = torch.zeros(batch, dtype=torch.int64, device=dev) if with_ranks else None
+        self.scores = torch.empty((batch, k), dtype=torch.float32, device=dev)
+        self.ids = torch.empty((batch, k), dtype=torch.int64, device=dev)
+        self.ranks = torch.empty(batch, dtype=torch.int32, device=dev) if with_ranks else None
+        self.status = torch.zeros(2, dtype=torch.int32, device=dev)
+        a = _lib.MipsTopkArgs()
+        a.B, a.X, a.D, a.k = batch, X, D, k
+        a.dtype = _lib.dtype_code(items.dtype)
+        a.queries, a.ldq = self.q.data_ptr(), _ld(self.q)
+        a.items, a.ldi = items.data_ptr(), _ld(items)
+        a.item_ids = _lib.ptr(self.item_ids)
+        a.out_scores, a.out_ids = self.scores.data_ptr(), self.ids.data_ptr()
+        a.status = self.status.data_ptr()
+        if self.invalid is not None:
+            a.invalid_ids, a.ld_invalid, a.n_invalid = self.invalid.data_ptr(), _ld(self.invalid), n_invalid
+        if with_ranks:
+            a.target_ids, a.out_ranks = self.target.data_ptr(), self.ranks.data_ptr()
+        a.sample_stride, a.cand_cap = 0, 0
+        need = int(_lib.lib().grb_mips_topk_workspace_bytes(C.byref(a)))
+        if need < 0:
+            _lib.check(need)
+        self.ws = torch.empty(max(need, 16), dtype=torch.uint8, device=dev)
+        a.workspace, a.workspace_bytes = self.ws.data_ptr(), self.ws.numel()
+        self._args = a
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):       # warm-up outside the capture (lazy module loading, attributes)
+            _lib.check(_lib.lib().grb_mips_topk(C.byref(a), _lib.stream_ptr(dev)))
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.status.zero_()
+            _lib.check(_lib.lib().grb_mips_topk(C.byref(a), _lib.stream_ptr(dev)))
+
+    def __call__(self, queries: torch.Tensor, invalid_ids: Optional[torch.Tensor] = None,
+                 target_ids: Optional[torch.Tensor] = None):
+        self.q.copy_(queries, non_blocking=True)
+        if self.invalid is not None:
+            self.invalid.copy_(invalid_ids, non_blocking=True)
+        if self.target is not None:
+            self.target.copy_(target_ids.reshape(-1), non_blocking=True)
+        with _lib.timed("mips_topk"):
+            self.graph.replay()
+        return (self.scores, self.ids) if self.ranks is None else (self.scores, self.ids, self.ranks)
+
+    def overflowed(self) -> bool:
+        return int(self.status[0].item()) != 0
+
+
 def topk_merge(cand_scores: torch.Tensor, cand_ids: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """Exact top-k of per-row candidate lists (B, C): sorted descending, ties -> lowest id.
     This is the merge step after the all-gather of per-shard top-k."""

@@ -344,3 +344,21 @@ def test_inbatch_static_cache_matches_unique_cache(direct):
     hist = torch.bincount(d.view(-1), minlength=c).float()
     expect = d.numel() / c
     assert (hist - expect).abs().max().item() < 6 * expect ** 0.5      # every bin within 6 sigma
+
+
+def test_topk_graph_replay_equals_eager_call():
+    """GF.MipsTopkGraph (one CUDA graph, static buffers) returns what the eager call returns, call after
+    call with different queries; invalid ids and target ranks included."""
+    gen = torch.Generator().manual_seed(11)
+    X, D, B, k, n_inv = 60_000, 64, 40, 50, 7
+    items = torch.nn.functional.normalize(torch.randn(X, D, generator=gen), dim=-1).to(torch.bfloat16).to(DEV)
+    ids = (torch.randperm(2 * X, generator=gen)[:X] + 1).to(DEV)
+    g = GF.MipsTopkGraph(B, items, ids, k, n_invalid=n_inv, with_ranks=True)
+    for rep in range(3):
+        q = torch.nn.functional.normalize(torch.randn(B, D, generator=gen), dim=-1).to(torch.bfloat16).to(DEV)
+        inv = ids[torch.randint(0, X, (B, n_inv), generator=gen).to(DEV)]
+        tgt = ids[torch.randint(0, X, (B,), generator=gen).to(DEV)]
+        s, i, r = g(q, inv, tgt)
+        es, ei, er = GF.mips_topk(q, items, ids, k, invalid_ids=inv, target_ids=tgt)
+        assert not g.overflowed()
+        assert torch.equal(i, ei) and torch.equal(s, es) and torch.equal(r, er)

@@ -48,7 +48,7 @@ def main():
         if k in hdr:
             i = hdr.index(k)
             lines.append(f"{k} = {vals[i]} {units[i]}")
-    src = page(rep, "source")[2:]
+    src = [r for r in page(rep, "source")[2:] if len(r) > 5 and r[4].strip().isdigit() and r[5].strip().isdigit()]
     tot_s = sum(int(r[4]) for r in src) or 1
     tot_i = sum(int(r[5]) for r in src) or 1
     ops = collections.defaultdict(lambda: [0, 0])
