@@ -356,13 +356,12 @@ def run_training(args, world, rank, local):
         tot0 = totals[0]
         raw = torch.randint(0, 2 ** 40, (tot0, cfg.num_negatives), device=dev,
                             generator=torch.Generator(device=dev).manual_seed(1))
-        orig_draw = smp._draw
         smp._draw = lambda positive_ids, n: raw[: positive_ids.size(0)] % (
             smp._cached_count if smp._cached_count is not None else smp._cached_ids.size(0))
         with torch.no_grad():
             l_gpu = float(model.training_loss({k: v.to(dev) for k, v in row0.items()}, total_length=tot0))
         picked = smp._cached_ids[(raw % smp._cached_count)].cpu()
-        smp._draw = orig_draw
+        del smp.__dict__["_draw"]              # back to the class's draw (and its fused kernel)
         model.train()
         probe = {"row": row0, "picked": picked, "loss_gpu": l_gpu}
 

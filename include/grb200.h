@@ -221,6 +221,20 @@ typedef struct grb_jagged_input_args {
   void* io; int64_t ldio;
   float* d_table; float* d_pos;
 } grb_jagged_input_args;
+/* rows [offsets[B], min(rows, offsets[B] + max_tail_rows)) of n_mats (rows, row_bytes) matrices := 0
+ * (row stride ld_bytes, matrices mat_stride_bytes apart; everything 16-byte aligned).  Fixed row buckets:
+ * the padding rows past offsets[B] are the only ones the attention kernels leave unwritten. */
+int grb_zero_tail_rows(void* base, int64_t ld_bytes, int64_t rows, int64_t row_bytes, int32_t n_mats,
+                       int64_t mat_stride_bytes, const void* offsets, int32_t index_bits, int64_t B,
+                       int64_t max_tail_rows, grb_stream_t stream);
+
+/* b5  negatives_samples/negative_sampler.py:208-211  in-batch draw + id gather in one pass:
+ *     offsets[i] = Philox4x32-10(seed, i / 2) (62 bits) mod max(count[0], 1);  ids[i] = cached_ids[offsets[i]].
+ *     seed, count: device int64 scalars (no host read).  Same distribution as randint(0, count), not
+ *     the same stream. */
+int grb_draw_negatives(const int64_t* seed, const int64_t* count, const int64_t* cached_ids, int64_t n,
+                       int64_t* offsets, int64_t* ids, grb_stream_t stream);
+
 int grb_jagged_input_fwd(const grb_jagged_input_args* a, grb_stream_t stream);
 int grb_jagged_input_bwd(const grb_jagged_input_args* a, grb_stream_t stream);
 int grb_l2norm_cast_fwd(const void* x, int64_t ldx, int dtype, float* y, int64_t ldy, float* inv, int64_t rows,

@@ -162,6 +162,46 @@ __global__ void __launch_bounds__(256) l2norm_cast_bwd_kernel(const float* __res
   for (int c = lane; c < W; c += 32) stf(dr + c, iv * (gr[c] - yr[c] * d));
 }
 
+// rows >= offsets[B] of n_mats row-major matrices (same shape, mat_stride bytes apart) := 0.  Fixed row
+// buckets (CUDA-graph mode) carry up to a bucket of padding rows the attention kernels never write;
+// clearing only those replaces a memset of the whole (T_pad, W) output.
+__global__ void __launch_bounds__(256) zero_tail_rows_kernel(unsigned char* __restrict__ base, int64_t ld_bytes,
+                                                             int64_t rows, int64_t row_bytes, int64_t mat_stride,
+                                                             const void* __restrict__ offsets, int index_bits,
+                                                             int B) {
+  const int64_t first = load_index(offsets, B, index_bits);
+  const int64_t r = first + (int64_t) blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  unsigned char* p = base + (int64_t) blockIdx.y * mat_stride + r * ld_bytes;
+  const int lane = threadIdx.x & 31;
+  for (int64_t c = 16 * lane; c < row_bytes; c += 512) *reinterpret_cast<uint4*>(p + c) = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// in-batch negatives draw (negative_sampler.py:208-211: randint(0, X_b) then a gather of the cached
+// ids) as one pass: offset = Philox(seed, i) mod count with the count read on the device, id =
+// cached_ids[offset].  62 random bits per draw: modulo bias < count / 2^62.
+__global__ void __launch_bounds__(256) draw_negatives_kernel(const int64_t* __restrict__ seed,
+                                                             const int64_t* __restrict__ count,
+                                                             const int64_t* __restrict__ cached_ids, int64_t n,
+                                                             int64_t* __restrict__ offsets,
+                                                             int64_t* __restrict__ ids) {
+  const int64_t i2 = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) * 2;   // two draws per Philox call
+  if (i2 >= n) return;
+  const uint64_t sd = (uint64_t) seed[0];
+  const uint64_t ctr = (uint64_t) (i2 >> 1);
+  const uint4 rnd = philox4x32_10((uint32_t) ctr, (uint32_t) (ctr >> 32), (uint32_t) sd, (uint32_t) (sd >> 32));
+  uint64_t cnt = (uint64_t) count[0];
+  if (cnt < 1) cnt = 1;
+  const uint64_t d0 = ((((uint64_t) rnd.x << 32) | rnd.y) >> 2) % cnt;
+  const uint64_t d1 = ((((uint64_t) rnd.z << 32) | rnd.w) >> 2) % cnt;
+  offsets[i2] = (int64_t) d0;
+  ids[i2] = cached_ids[d0];
+  if (i2 + 1 < n) {
+    offsets[i2 + 1] = (int64_t) d1;
+    ids[i2 + 1] = cached_ids[d1];
+  }
+}
+
 }  // namespace
 }  // namespace grb
 
@@ -200,6 +240,34 @@ static int jagged_input_launch(const grb_jagged_input_args* a, bool bwd, grb_str
   auto st = reinterpret_cast<cudaStream_t>(stream);
   if (bwd) jagged_input_kernel<true><<<grid, 256, 0, st>>>(P);
   else jagged_input_kernel<false><<<grid, 256, 0, st>>>(P);
+  GRB_LAUNCH_OK();
+  return GRB_OK;
+}
+
+int grb_zero_tail_rows(void* base, int64_t ld_bytes, int64_t rows, int64_t row_bytes, int32_t n_mats,
+                       int64_t mat_stride_bytes, const void* offsets, int32_t index_bits, int64_t B,
+                       int64_t max_tail_rows, grb_stream_t stream) {
+  GRB_REQUIRE(base && offsets && rows >= 0 && row_bytes > 0 && row_bytes % 16 == 0 && ld_bytes % 16 == 0 &&
+                  (reinterpret_cast<uintptr_t>(base) & 15) == 0 && n_mats > 0 && mat_stride_bytes % 16 == 0 &&
+                  (index_bits == 32 || index_bits == 64) && B >= 0 && max_tail_rows >= 0,
+              GRB_ERR_INVALID_ARG, "zero_tail_rows: bad arguments (16-byte aligned rows)");
+  if (rows == 0 || max_tail_rows == 0) return GRB_OK;
+  const int64_t span = max_tail_rows < rows ? max_tail_rows : rows;
+  zero_tail_rows_kernel<<<dim3((unsigned) ceil_div(span, (int64_t) 8), (unsigned) n_mats), 256, 0,
+                          reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<unsigned char*>(base), ld_bytes, rows, row_bytes, mat_stride_bytes, offsets, index_bits,
+      (int) B);
+  GRB_LAUNCH_OK();
+  return GRB_OK;
+}
+
+int grb_draw_negatives(const int64_t* seed, const int64_t* count, const int64_t* cached_ids, int64_t n,
+                       int64_t* offsets, int64_t* ids, grb_stream_t stream) {
+  GRB_REQUIRE(seed && count && cached_ids && offsets && ids && n >= 0, GRB_ERR_INVALID_ARG,
+              "draw_negatives: bad arguments");
+  if (n == 0) return GRB_OK;
+  draw_negatives_kernel<<<(unsigned) ceil_div(ceil_div(n, (int64_t) 2), (int64_t) 256), 256, 0,
+                          reinterpret_cast<cudaStream_t>(stream)>>>(seed, count, cached_ids, n, offsets, ids);
   GRB_LAUNCH_OK();
   return GRB_OK;
 }

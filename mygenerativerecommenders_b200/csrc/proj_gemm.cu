@@ -312,15 +312,50 @@ __global__ void __launch_bounds__(PG_THREADS, 1) proj_gemm_kernel(const __grid_c
 }
 
 // column sums of a bf16 (rows, W) matrix into fp32 out[W] (+=): the bias gradient of nn.Linear
-// (hstu.py:404-413 backward).  Block = 64 rows x W columns; one red per (block, column).
+// (hstu.py:404-413 backward).  Vector path (W % 8 == 0, aligned): lane = 8 columns (one 16-byte load
+// per row), warp w of the block takes rows r0 + w, r0 + w + 8, ... with all its loads independent, the
+// 8 warps meet in shared memory, one red per (block, column).  One block per ~SM-count slice of rows.
+constexpr int CS_ROWS = 104;
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx,
-                                                          int64_t rows, int W, float* __restrict__ out) {
-  const int64_t r0 = (int64_t) blockIdx.x * 64;
-  for (int c = threadIdx.x; c < W; c += blockDim.x) {
-    float acc = 0.f;
-    const int64_t r1 = r0 + 64 < rows ? r0 + 64 : rows;
-    for (int64_t r = r0; r < r1; ++r) acc += __bfloat162float(x[r * ldx + c]);
-    if (acc != 0.f) atomicAdd(out + c, acc);
+                                                          int64_t rows, int W, float* __restrict__ out, int vec) {
+  const int64_t r0 = (int64_t) blockIdx.x * CS_ROWS;
+  const int64_t r1 = r0 + CS_ROWS < rows ? r0 + CS_ROWS : rows;
+  if (!vec) {
+    for (int c = threadIdx.x; c < W; c += blockDim.x) {
+      float acc = 0.f;
+      for (int64_t r = r0; r < r1; ++r) acc += __bfloat162float(x[r * ldx + c]);
+      if (acc != 0.f) atomicAdd(out + c, acc);
+    }
+    return;
+  }
+  __shared__ float part[8][264];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c0 = 0; c0 < W; c0 += 256) {
+    const int c = c0 + 8 * lane;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (c < W) {
+#pragma unroll 4
+      for (int64_t r = r0 + warp; r < r1; r += 8) {
+        const uint4 v = *reinterpret_cast<const uint4*>(x + r * ldx + c);
+        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          acc[2 * k] += __uint_as_float(w4[k] << 16);
+          acc[2 * k + 1] += __uint_as_float(w4[k] & 0xffff0000u);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) part[warp][8 * lane + k] = acc[k];
+    __syncthreads();
+    const int cc = c0 + threadIdx.x;
+    if (cc < W) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += part[w][threadIdx.x];
+      if (t != 0.f) atomicAdd(out + cc, t);
+    }
+    __syncthreads();
   }
 }
 
@@ -391,8 +426,9 @@ int grb_proj_gemm(const grb_proj_gemm_args* a, grb_stream_t stream) {
 int grb_colsum_bf16(const void* x, int64_t ldx, int64_t rows, int32_t W, float* out, grb_stream_t stream) {
   GRB_REQUIRE(x && out && rows >= 0 && W > 0, GRB_ERR_INVALID_ARG, "colsum_bf16: bad arguments");
   if (rows == 0) return GRB_OK;
-  colsum_bf16_kernel<<<(unsigned) ceil_div(rows, 64), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows, W, out);
+  const int vec = (W % 8 == 0) && (ldx % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  colsum_bf16_kernel<<<(unsigned) ceil_div(rows, (int64_t) CS_ROWS), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows, W, out, vec);
   GRB_LAUNCH_OK();
   return GRB_OK;
 }

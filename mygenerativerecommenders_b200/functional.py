@@ -141,6 +141,19 @@ def short_path_applies(q: torch.Tensor, dqk: int, dv: int, max_len: int) -> bool
             and os.environ.get("GRB_NO_SHORT") != "1")
 
 
+def _zero_tail_rows(t: torch.Tensor, n_mats: int, offsets: torch.Tensor) -> None:
+    """Rows >= offsets[-1] of the n_mats stacked (rows, W) matrices in ``t`` := 0 (fixed row buckets: the
+    padding rows are the only ones the attention kernels leave unwritten)."""
+    rows, W = t.shape[-2], t.shape[-1]
+    row_bytes = W * t.element_size()
+    if row_bytes % 16 or t.data_ptr() % 16:
+        t.zero_()
+        return
+    _lib.check(_lib.lib().grb_zero_tail_rows(
+        t.data_ptr(), row_bytes, rows, row_bytes, n_mats, rows * row_bytes, offsets.data_ptr(),
+        _lib.index_bits(offsets), offsets.numel() - 1, rows, _lib.stream_ptr(t.device)))
+
+
 class _HstuAttention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk, dv, max_len,
@@ -160,8 +173,9 @@ class _HstuAttention(torch.autograd.Function):
                 raise ValueError("hstu_attention: bias table sizes do not match N / num_buckets")
         # rows_padded: q/k/v carry rows past offsets[-1] (fixed-size row buckets); the kernels
         # never write those rows, so they must start as zeros
-        alloc = torch.zeros if rows_padded else torch.empty
-        out = alloc((q.shape[0], H * dv), dtype=q.dtype, device=q.device)
+        out = torch.empty((q.shape[0], H * dv), dtype=q.dtype, device=q.device)
+        if rows_padded:
+            _zero_tail_rows(out, 1, offsets)
         if cache is not None and ((timestamps is None and not cache.grb_masked) or cache.grb_max_len != max_len):
             cache = None
         short = short_path_applies(q, dqk, dv, max_len) and (timestamps is None or thresholds.numel() <= 254)
@@ -190,14 +204,18 @@ class _HstuAttention(torch.autograd.Function):
         T = q.shape[0]
         # one allocation (and, with padded rows, one fill) for the three gradients; one zero-filled
         # fp32 workspace for the dQ accumulator and the privatised bias-gradient copies
-        alloc = torch.zeros if ctx.rows_padded else torch.empty
         if dqk == dv:
-            g3 = alloc((3, T, H * dqk), dtype=q.dtype, device=q.device)
+            g3 = torch.empty((3, T, H * dqk), dtype=q.dtype, device=q.device)
             dq, dk, dvv = g3[0], g3[1], g3[2]
+            if ctx.rows_padded:
+                _zero_tail_rows(g3, 3, offsets)
         else:
-            dq = alloc((T, H * dqk), dtype=q.dtype, device=q.device)
-            dk = alloc((T, H * dqk), dtype=q.dtype, device=q.device)
-            dvv = alloc((T, H * dv), dtype=q.dtype, device=q.device)
+            dq = torch.empty((T, H * dqk), dtype=q.dtype, device=q.device)
+            dk = torch.empty((T, H * dqk), dtype=q.dtype, device=q.device)
+            dvv = torch.empty((T, H * dv), dtype=q.dtype, device=q.device)
+            if ctx.rows_padded:
+                for t in (dq, dk, dvv):
+                    _zero_tail_rows(t, 1, offsets)
         short = ctx.short
         # long-sequence kernels: fp32 dQ accumulator (zero-filled).  Short kernels: plain scratch for
         # the partial dQ of the second query tile, only when a sequence can have one.
@@ -681,17 +699,43 @@ def l2_normalize(x: torch.Tensor, eps: float) -> torch.Tensor:
     return x / torch.clamp(torch.linalg.norm(x, ord=None, dim=-1, keepdim=True), min=eps)
 
 
+class _TableGradState:
+    """What the backward nodes of a TableGradScope share: the dense buffer and the one-element token.
+    It references neither the proxy nor the table, so that no reference cycle keeps an autograd graph
+    (and with it the table's gradient accumulator, pinned to the stream it was created on) alive after
+    the step — a later CUDA-graph capture must not find one from an eager step on the default stream."""
+
+    def __init__(self, shape, dtype, device) -> None:
+        self.shape, self.dtype, self.device = tuple(shape), dtype, device
+        self._buf = None
+        self._tok = None
+
+    def buffer(self) -> torch.Tensor:
+        if self._buf is None:
+            self._buf = torch.zeros(self.shape, dtype=torch.float32, device=self.device)
+        return self._buf
+
+    def token(self) -> torch.Tensor:
+        if self._tok is None:
+            self._tok = torch.zeros(1, dtype=self.dtype, device=self.device)
+        return self._tok
+
+    def take(self):
+        buf, self._buf = self._buf, None
+        return buf
+
+
 class _TableSink(torch.autograd.Function):
     """See TableGradScope: stands between the table parameter and the readers of one step."""
 
     @staticmethod
-    def forward(ctx, table, scope):
-        ctx.scope = scope
+    def forward(ctx, table, state):
+        ctx.state = state
         return table.new_zeros(1)
 
     @staticmethod
     def backward(ctx, g):
-        return ctx.scope.take(), None
+        return ctx.state.take(), None
 
 
 class TableGradScope:
@@ -702,30 +746,15 @@ class TableGradScope:
     (V, D) fp32 tensor, scatters a few thousand rows into it, and the engine adds the dense tensors
     together: at C2 (131 263 x 256) that is 3 fills + 2 adds of 134 MB each, 0.16 ms of HBM traffic
     per step for nothing.  Readers given ``grad_scope=`` take a one-element proxy as their
-    differentiable input instead of the table; their backward scatter-adds into ``buffer()`` (zeroed
-    once, by whichever reader runs first) and hands the proxy a one-element token.  The engine runs
-    ``_TableSink.backward`` after every reader that takes part in this backward pass has finished (its
-    ordinary dependency counting), and that returns the buffer as the table's gradient."""
+    differentiable input instead of the table; their backward scatter-adds into the shared buffer
+    (zeroed once, by whichever reader runs first) and hands the proxy a one-element token.  The engine
+    runs ``_TableSink.backward`` after every reader that takes part in this backward pass has finished
+    (its ordinary dependency counting), and that returns the buffer as the table's gradient."""
 
     def __init__(self, table: torch.Tensor):
-        self.table = table
-        self._buf = None
-        self._tok = None
-        self.proxy = _TableSink.apply(table, self) if (table.requires_grad and torch.is_grad_enabled()) else None
-
-    def buffer(self) -> torch.Tensor:
-        if self._buf is None:
-            self._buf = torch.zeros(self.table.shape, dtype=torch.float32, device=self.table.device)
-        return self._buf
-
-    def token(self) -> torch.Tensor:
-        if self._tok is None:
-            self._tok = torch.zeros(1, dtype=self.table.dtype, device=self.table.device)
-        return self._tok
-
-    def take(self):
-        buf, self._buf = self._buf, None
-        return buf
+        self.state = _TableGradState(table.shape, table.dtype, table.device)
+        self.proxy = (_TableSink.apply(table, self.state)
+                      if (table.requires_grad and torch.is_grad_enabled()) else None)
 
 
 class _EmbeddingLookup(torch.autograd.Function):
@@ -738,7 +767,7 @@ class _EmbeddingLookup(torch.autograd.Function):
         ctx.save_for_backward(ids)
         ctx.shape = weight.shape
         ctx.padding_idx = -1 if padding_idx is None else int(padding_idx)
-        ctx.scope = scope
+        ctx.scope = scope.state if scope is not None else None
         return torch.embedding(weight, ids)
 
     @staticmethod
@@ -779,7 +808,7 @@ class _JaggedInput(torch.autograd.Function):
     @staticmethod
     def forward(ctx, table, pos, ids, offsets, rows, scale, p_drop, seed, out_dtype, proxy=None, scope=None):
         _lib.require_cuda(table, pos, ids, offsets)
-        ctx.scope = scope
+        ctx.scope = scope.state if scope is not None else None
         if table.dtype != torch.float32 or pos.dtype != torch.float32:
             raise NotImplementedError("jagged_input: float32 tables only")
         table, pos = _rows_contiguous(table), _rows_contiguous(pos)

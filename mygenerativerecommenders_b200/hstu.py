@@ -227,9 +227,20 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
             return self._softmax_branch(x, u, v, q, k, x_offsets, all_timestamps, invalid_attn_mask,
                                         return_cache_states)
         bias = self._rel_attn_bias if all_timestamps is not None else None
+        if not incremental and (
+                (bias is not None and not isinstance(bias, RelativeBucketedTimeAndPositionBasedBias))
+                or max(dqk, dv) > (128 if torch.is_grad_enabled() else 256)):
+            # shapes / bias modules the fused kernels do not cover: heads wider than 128 (the reference's
+            # default injection attention_dim = linear_dim = item_embedding_dim gives H = 1, d = D,
+            # generative_recommenders.py:157-160) when a gradient is needed, wider than 256 at all,
+            # or RelativePositionalBias (hstu.py:50-68).  The reference's padded formulation on the
+            # jagged kernels + cuBLAS + ATen, O(B H N^2) memory: functional, not a hot path.
+            attn_output = self._composite_attention(q, k, v, x_offsets, all_timestamps, n)
+            return self._finish_layer(x, u, v, q, k, attn_output, x_offsets, n, False, None, None,
+                                      return_cache_states)
         if bias is not None and not isinstance(bias, RelativeBucketedTimeAndPositionBasedBias):
             raise NotImplementedError(
-                "the fused attention supports RelativeBucketedTimeAndPositionBasedBias only")
+                "the incremental path supports RelativeBucketedTimeAndPositionBasedBias only")
         bias_args = (all_timestamps if bias is not None else None,
                      bias._ts_w if bias is not None else None,
                      bias._pos_w if bias is not None else None,
@@ -252,6 +263,32 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
                 N=n, num_heads=H, attention_dim=dqk, linear_dim=dv, bucket_cache=bucket_cache,
                 rows_padded=rows_padded)
 
+        return self._finish_layer(x, u, v, q, k, attn_output, x_offsets, n, incremental,
+                                  rows if incremental else None,
+                                  (cached_outputs, padded_q, padded_k) if incremental else None,
+                                  return_cache_states)
+
+    def _composite_attention(self, q, k, v, x_offsets, all_timestamps, n: int) -> torch.Tensor:
+        """hstu.py:179-204 as written: pad, (B, H, N, N) scores, + bias, SiLU / N, causal mask, P V, un-pad."""
+        B = x_offsets.numel() - 1
+        H, dv, dqk = self._num_heads, self._linear_dim, self._attention_dim
+        pq = ops.jagged_to_padded_dense(q.contiguous(), x_offsets, n, 0.0).view(B, n, H, dqk)
+        pk = ops.jagged_to_padded_dense(k.contiguous(), x_offsets, n, 0.0).view(B, n, H, dqk)
+        pv = ops.jagged_to_padded_dense(v.contiguous(), x_offsets, n, 0.0).view(B, n, H, dv)
+        qk = torch.einsum("bnhd,bmhd->bhnm", pq, pk)
+        if all_timestamps is not None and self._rel_attn_bias is not None:
+            qk = qk + self._rel_attn_bias(all_timestamps).unsqueeze(1).to(qk.dtype)
+        qk = F.silu(qk) / n
+        qk = qk * torch.ones(n, n, dtype=qk.dtype, device=qk.device).tril_()
+        out = ops.dense_to_jagged(torch.einsum("bhnm,bmhd->bnhd", qk, pv).reshape(B, n, H * dv), x_offsets)
+        if out.size(0) < q.size(0):        # fixed row buckets: the rows past offsets[-1] stay zero
+            out = F.pad(out, (0, 0, 0, q.size(0) - out.size(0)))
+        return out
+
+    def _finish_layer(self, x, u, v, q, k, attn_output, x_offsets, n, incremental, rows, cached,
+                      return_cache_states):
+        if incremental:
+            cached_outputs, padded_q, padded_k = cached
         if self._concat_ua:
             a = self._norm_attn_output(attn_output)
             o_input = torch.cat([u, a, u * a], dim=-1)

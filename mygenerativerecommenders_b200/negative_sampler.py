@@ -291,8 +291,30 @@ class InBatchNegativesSampler(*((NegativesSampler, _RefInBatch) if _RefInBatch e
         offsets = self._draw(positive_ids, num_to_sample)
         return self._cached_ids[offsets], self._cached_embeddings[offsets]
 
+    def _draw_with_ids(self, positive_ids: torch.Tensor, num_to_sample: int):
+        """(offsets, ids) of the static-shape cache in ONE kernel (``grb_draw_negatives``: Philox draw,
+        modulo the device-side count, id gather) instead of randint + remainder + index; falls back to
+        ``_draw`` + a gather when ``_draw`` was replaced (tests inject fixed draws) or the cache is the
+        ``unique`` one."""
+        from . import _lib
+        if (getattr(self, "_cached_count", None) is None or "_draw" in self.__dict__
+                or not positive_ids.is_cuda or self._cached_ids.dtype != torch.int64):
+            offsets = self._draw(positive_ids, num_to_sample)
+            return offsets, self._cached_ids[offsets]
+        dev = positive_ids.device
+        size = tuple(positive_ids.size()) + (num_to_sample,)
+        seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, device=dev)     # torch's generator: graph safe
+        offsets = torch.empty(size, dtype=torch.int64, device=dev)
+        ids = torch.empty(size, dtype=torch.int64, device=dev)
+        count = self._cached_count.reshape(1)
+        if count.dtype != torch.int64:
+            count = count.to(torch.int64)
+        _lib.check(_lib.lib().grb_draw_negatives(seed.data_ptr(), count.data_ptr(), self._cached_ids.data_ptr(),
+                                                 offsets.numel(), offsets.data_ptr(), ids.data_ptr(),
+                                                 _lib.stream_ptr(dev)))
+        return offsets, ids
+
     def fused_sample(self, positive_ids: torch.Tensor, num_to_sample: int) -> Optional[FusedNegatives]:
-        offsets = self._draw(positive_ids, num_to_sample)
+        offsets, ids = self._draw_with_ids(positive_ids, num_to_sample)
         # the cache is already normalised (process_batch), so the kernel must not re-normalise
-        return FusedNegatives(self._cached_ids[offsets], self._cached_embeddings, offsets, None,
-                              None, False, (None, None))
+        return FusedNegatives(ids, self._cached_embeddings, offsets, None, None, False, (None, None))

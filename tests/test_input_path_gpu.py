@@ -128,3 +128,30 @@ def test_table_grad_scope_equals_autograd_accumulation():
         sc = GF.TableGradScope(table)
         assert sc.proxy is None
         assert torch.equal(GF.embedding_lookup(table, pick, 0, grad_scope=sc), table[pick])
+
+
+def test_zero_tail_rows_and_fused_negative_draw():
+    """grb_zero_tail_rows clears exactly the rows past offsets[-1]; grb_draw_negatives draws uniformly over
+    [0, count) with the count read on the device and gathers the cached ids in the same pass."""
+    import ctypes as C
+    from mygenerativerecommenders_b200 import _lib
+    from mygenerativerecommenders_b200.negative_sampler import InBatchNegativesSampler
+    off = torch.tensor([0, 5, 5, 37], dtype=torch.int64, device=DEV)
+    t = torch.full((3, 64, 24), 7.0, dtype=torch.bfloat16, device=DEV)
+    GF._zero_tail_rows(t, 3, off)
+    assert (t[:, :37] == 7).all() and (t[:, 37:] == 0).all()
+    smp = InBatchNegativesSampler(l2_norm=True, l2_norm_eps=1e-6, dedup_embeddings=True)
+    cached = torch.arange(1000, 1000 + 4096, device=DEV)
+    smp._cached_ids, smp._cached_count = cached, torch.tensor(777, device=DEV)
+    smp._cached_embeddings = torch.zeros(4096, 8, device=DEV)
+    pos = torch.zeros(3001, dtype=torch.int64, device=DEV)
+    offs, ids = smp._draw_with_ids(pos, 129)
+    assert offs.shape == (3001, 129) and offs.min() >= 0 and offs.max() == 776
+    assert torch.equal(ids, cached[offs])
+    hist = torch.bincount(offs.view(-1), minlength=777).float()
+    exp = offs.numel() / 777
+    assert ((hist - exp).abs() < 6 * exp ** 0.5).all()              # ~498 per bin, sigma 22
+    offs2, _ = smp._draw_with_ids(pos, 129)
+    assert not torch.equal(offs, offs2)                             # a fresh seed per call
+    smp._draw = lambda p, n: torch.zeros(p.size(0), n, dtype=torch.int64, device=DEV)   # injected draws win
+    assert smp._draw_with_ids(pos, 4)[0].abs().sum() == 0
