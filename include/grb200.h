@@ -269,6 +269,10 @@ typedef struct grb_proj_gemm_args {
 } grb_proj_gemm_args;
 int grb_proj_gemm(const grb_proj_gemm_args* a, grb_stream_t stream);
 int grb_colsum_bf16(const void* x, int64_t ldx, int64_t rows, int32_t W, float* out, grb_stream_t stream);
+/* out_a[wa] / out_b[wb] = column sums of the fp32 matrices a (rows, wa) / b (rows, wb), one launch: sums the
+ * privatised copies of d ts_w and d pos_w that grb_hstu_attn_bwd fills (d_bias_copies of them). */
+int grb_colsum_f32_pair(const float* a, int32_t wa, float* out_a, const float* b, int32_t wb, float* out_b,
+                        int32_t rows, grb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a6  hstu.py:304-320  the activation between the UVQK projection and its consumers:

@@ -164,6 +164,7 @@ SYMBOLS = {
     "grb_l2norm_cast_bwd": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, C.c_int, c_i64, c_i64, c_vp]),
     "grb_proj_gemm": (C.c_int, [C.POINTER(ProjGemmArgs), c_vp]),
     "grb_colsum_bf16": (C.c_int, [c_vp, c_i64, c_i64, c_i32, c_vp, c_vp]),
+    "grb_colsum_f32_pair": (C.c_int, [c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp]),
     "grb_selftest_umma": (C.c_int, [C.POINTER(C.c_float), C.c_int, c_vp]),
 }
 

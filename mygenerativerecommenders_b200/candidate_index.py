@@ -26,7 +26,11 @@ def _drop_invalid(ids: torch.Tensor, scores: torch.Tensor, invalid_ids: torch.Te
     keep &= torch.cumsum(keep.to(torch.int32), dim=1) <= k
     # stable argsort brings the kept positions to the front without reordering them
     pos = torch.argsort((~keep).to(torch.int8), dim=1, stable=True)[:, :k]
-    return torch.gather(ids, 1, pos), torch.gather(scores, 1, pos)
+    out_i, out_s = torch.gather(ids, 1, pos), torch.gather(scores, 1, pos)
+    # rows left with fewer than k valid entries (the reference's .view(-1, k) raises there): pad like the
+    # fused kernel does, (-1, -inf), instead of returning filtered-out ids
+    short = ~torch.gather(keep, 1, pos)
+    return out_i.masked_fill(short, -1), out_s.masked_fill(short, float("-inf"))
 
 
 def _fused_filter_ok(top_k_module, k: int, n_invalid: int, num_objects: int) -> bool:
@@ -85,6 +89,14 @@ class CandidateIndex(torch.nn.Module):
         if invalid_ids is not None:
             ids, scores = _drop_invalid(ids, scores, invalid_ids, k)
         return ids, scores
+
+    def filter_invalid_ids(self, invalid_ids: torch.Tensor) -> "CandidateIndex":
+        """candidate_index.py:52-105 builds a per-row copy of the whole index with the invalid ids removed
+        (and, as written there, constructs ``CandidateIndex`` without its required ``k`` / ``top_k_module``
+        arguments, so the reference's own method raises TypeError).  Per-row filtering is what
+        ``get_top_k_outputs(..., invalid_ids=...)`` does inside the selection kernel."""
+        raise NotImplementedError(
+            "filter_invalid_ids: pass invalid_ids to get_top_k_outputs instead (filtered inside the top-k kernel)")
 
     def apply_object_filter(self) -> "CandidateIndex":
         raise NotImplementedError("not implemented.")

@@ -359,6 +359,34 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
   }
 }
 
+// out_a[wa] = column sums of a (rows, wa), out_b[wb] = column sums of b (rows, wb), fp32, one launch:
+// the privatised copies of d ts_w / d pos_w the attention backward fills (functional._HstuAttention).
+// Block = 32 columns of the concatenated [a | b]; warp w sums rows w, w + 8, ...; shared-memory finish.
+__global__ void __launch_bounds__(256) colsum_f32_pair_kernel(const float* __restrict__ a, int wa,
+                                                              float* __restrict__ out_a,
+                                                              const float* __restrict__ b, int wb,
+                                                              float* __restrict__ out_b, int rows) {
+  __shared__ float part[8][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 32 + lane;
+  const bool in_a = c < wa;
+  const float* src = in_a ? a + c : b + (c - wa);
+  const int ld = in_a ? wa : wb;
+  float acc = 0.f;
+  if (c < wa + wb) {
+#pragma unroll 4
+    for (int r = warp; r < rows; r += 8) acc += src[(int64_t) r * ld];
+  }
+  part[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && c < wa + wb) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += part[w][lane];
+    if (in_a) out_a[c] = t; else out_b[c - wa] = t;
+  }
+}
+
 }  // namespace
 }  // namespace grb
 
@@ -429,6 +457,16 @@ int grb_colsum_bf16(const void* x, int64_t ldx, int64_t rows, int32_t W, float* 
   const int vec = (W % 8 == 0) && (ldx % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   colsum_bf16_kernel<<<(unsigned) ceil_div(rows, (int64_t) CS_ROWS), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows, W, out, vec);
+  GRB_LAUNCH_OK();
+  return GRB_OK;
+}
+
+int grb_colsum_f32_pair(const float* a, int32_t wa, float* out_a, const float* b, int32_t wb, float* out_b,
+                        int32_t rows, grb_stream_t stream) {
+  GRB_REQUIRE(a && out_a && wa > 0 && wb >= 0 && (wb == 0 || (b && out_b)) && rows >= 0, GRB_ERR_INVALID_ARG,
+              "colsum_f32_pair: bad arguments");
+  colsum_f32_pair_kernel<<<(unsigned) ceil_div((int64_t) wa + wb, (int64_t) 32), 256, 0,
+                           reinterpret_cast<cudaStream_t>(stream)>>>(a, wa, out_a, b, wb, out_b, rows);
   GRB_LAUNCH_OK();
   return GRB_OK;
 }

@@ -64,22 +64,20 @@ def _attn_args(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk,
     return a
 
 
-_OCT_CACHE: dict = {}
-
-
 def bucket_octaves(thresholds: torch.Tensor) -> torch.Tensor:
-    """Device copy of grb_bucket_octaves(thresholds), cached per thresholds storage."""
-    key = (thresholds.data_ptr(), thresholds.numel(), thresholds.device)
-    hit = _OCT_CACHE.get(key)
-    if hit is not None:
-        return hit
+    """Device copy of grb_bucket_octaves(thresholds).  The table rides on the thresholds tensor object
+    itself (the module's ``_bucket_thresholds`` buffer), so it lives exactly as long as the thresholds
+    it was computed from: no global cache keyed by a device address that the allocator can hand to
+    another module's table.  The one synchronous ``.cpu()`` happens on the first use of a buffer, i.e.
+    in the warm-up iterations before any CUDA-graph capture."""
+    hit = getattr(thresholds, "_grb_octaves", None)
+    if hit is not None and hit[0] == thresholds._version and hit[1].device == thresholds.device:
+        return hit[1]
     host = thresholds.detach().cpu().contiguous()
     out = torch.empty(130, dtype=torch.int32)
     _lib.check(_lib.lib().grb_bucket_octaves(host.data_ptr(), host.numel(), out.data_ptr()))
     dev = out.to(thresholds.device)
-    if len(_OCT_CACHE) > 64:
-        _OCT_CACHE.clear()
-    _OCT_CACHE[key] = dev
+    thresholds._grb_octaves = (thresholds._version, dev)
     return dev
 
 
@@ -247,8 +245,14 @@ class _HstuAttention(torch.autograd.Function):
         with _lib.timed("hstu_attn_bwd"):
             _lib.check(_lib.lib().grb_hstu_attn_bwd(C.byref(a), _lib.stream_ptr(q.device)))
         if d_pos is not None:
-            d_pos = d_pos.sum(0) if d_pos.shape[0] > 1 else d_pos[0]
-            d_ts = d_ts.sum(0) if d_ts.shape[0] > 1 else d_ts[0]
+            if copies > 1:     # both tables' copies summed by one launch (ATen: two single-block reductions)
+                sums = torch.empty(n_ts + n_pos, dtype=torch.float32, device=q.device)
+                _lib.check(_lib.lib().grb_colsum_f32_pair(
+                    d_ts.data_ptr(), n_ts, sums.data_ptr(), d_pos.data_ptr(), n_pos,
+                    sums.data_ptr() + 4 * n_ts, copies, _lib.stream_ptr(q.device)))
+                d_ts, d_pos = sums[:n_ts], sums[n_ts:]
+            else:
+                d_pos, d_ts = d_pos[0], d_ts[0]
         return dq, dk, dvv, None, None, d_ts, d_pos, None, None, None, None, None, None, None, None
 
 
@@ -455,8 +459,8 @@ class _MasterLinear(torch.autograd.Function):
         ctx.w_in_out = w_in_out
         ctx.w_dtype = w.dtype
         ctx.b_dtype = b.dtype if b is not None else None
-        if w_in_out:
-            return torch.mm(x, wc)
+        if w_in_out or b is None:
+            return torch.mm(x, wc if w_in_out else wc.t())
         bc = b if b.dtype == x.dtype else b.to(x.dtype)
         return torch.addmm(bc, x, wc.t())
 

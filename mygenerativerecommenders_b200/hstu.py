@@ -313,6 +313,26 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
         return new_outputs, cache_state
 
 
+def _require_causal(invalid_attn_mask: torch.Tensor) -> None:
+    """The kernels apply the causal lower triangle HSTU registers as ``_attn_mask`` (hstu.py:595-607, :667)
+    themselves and read only the SIZE of ``invalid_attn_mask``; the reference multiplies by the tensor it is
+    given (hstu.py:194).  Any other mask (full, windowed, target-aware) must not be silently ignored: it is
+    checked once per mask tensor (one host comparison, remembered on the tensor object) and refused."""
+    seen = getattr(invalid_attn_mask, "_grb_causal", None)
+    if seen is not None and seen == invalid_attn_mask._version:
+        return
+    n = invalid_attn_mask.size(-1)
+    m = invalid_attn_mask.reshape(-1, n)[-n:]
+    # two spellings of the same mask: the reference's float `1 - _attn_mask` (non-zero = attend), or this
+    # package's HSTU handing over its boolean `_attn_mask` buffer itself (True = masked, hstu.py:595-607)
+    m = ~m if m.dtype == torch.bool else m != 0
+    if not torch.equal(m, torch.ones(n, n, dtype=torch.bool, device=m.device).tril_()):
+        raise NotImplementedError(
+            "HSTU on the fused kernels supports the causal lower-triangular invalid_attn_mask only; "
+            "got a different mask (the reference would multiply the scores by it, hstu.py:194)")
+    invalid_attn_mask._grb_causal = invalid_attn_mask._version
+
+
 class HSTUJagged(torch.nn.Module):
     """Stack of STU layers over jagged rows (reference hstu.py:426-518)."""
 
@@ -330,6 +350,7 @@ class HSTUJagged(torch.nn.Module):
                        delta_x_offsets=None, cache=None, return_cache_states: bool = False,
                        rows_padded: bool = False):
         cache_states: List[HSTUCacheState] = []
+        _require_causal(invalid_attn_mask)
         in_dtype = x.dtype
         if self._autocast_dtype is not None and x.dtype != self._autocast_dtype:
             x = x.to(self._autocast_dtype)

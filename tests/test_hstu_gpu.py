@@ -577,3 +577,20 @@ def test_wide_heads_and_positional_bias_train_through_the_composite(H, d, bias_k
     _close(xg.grad, xr.grad, 1e-4, what="composite dx")
     for name, p in layer.named_parameters():
         _close(p.grad, sd[name].grad, 2e-4, what=f"composite d{name}")
+
+
+def test_non_causal_mask_is_refused_not_ignored():
+    enc = hstu.HSTU(max_sequence_len=20, max_output_len=4, embedding_dim=64, item_embedding_dim=64, num_blocks=1,
+                    num_heads=1, linear_dim=64, attention_dim=64, normalization="rel_bias", linear_config="uvqk",
+                    linear_activation="silu", linear_dropout_rate=0.0, attn_dropout_rate=0.0).to(DEV).eval()
+    N = 24
+    lengths = torch.tensor([10, 24], device=DEV)
+    x = torch.randn(2, N, 64, device=DEV)
+    ts = torch.zeros(2, N, dtype=torch.int64, device=DEV)
+    enc(past_lengths=lengths, user_embeddings=x, valid_mask=None, past_payloads={"timestamps": ts})   # causal: fine
+    full = torch.ones(N, N, device=DEV)
+    xj = torch.randn(34, 64, device=DEV)
+    off = torch.tensor([0, 10, 34], device=DEV)
+    with pytest.raises(NotImplementedError, match="causal"):
+        enc._hstu.jagged_forward(xj, off, ts, full)
+    enc._hstu.jagged_forward(xj, off, ts, 1.0 - enc._attn_mask.float())      # the reference's spelling: fine
