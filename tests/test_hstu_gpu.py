@@ -174,11 +174,13 @@ def test_hstu_module_bf16_vs_reference_golden(golden):
     y, _ = enc(past_lengths=c["lengths"].to(DEV), user_embeddings=x, valid_mask=None,
                past_payloads={"timestamps": c["ts"].to(DEV)})
     assert y.dtype == torch.float32
-    _close(y, c["y"], 2e-2, 1e-2, what="bf16 y")
+    # bf16 outputs 1e-2 (max) / 5e-3 (rel-L2), gradients 2e-2 / 2e-2.  Measured on the
+    # B200: y 3.8e-3 / 2.4e-3, dx 3.9e-3 / 2.4e-3, parameter gradients <= 1.3e-2 / 1.0e-2 (_ts_w the largest).
+    _close(y, c["y"], 1e-2, 5e-3, what="bf16 y")
     (y * c["w"].to(DEV)).sum().backward()
-    _close(x.grad, c["dx"], 5e-2, 2e-2, what="bf16 dx")
+    _close(x.grad, c["dx"], 2e-2, 2e-2, what="bf16 dx")
     for k, p in enc.named_parameters():
-        _close(p.grad, c["grads"][k], 8e-2, 3e-2, what=f"bf16 grad {k}")
+        _close(p.grad, c["grads"][k], 2e-2, 2e-2, what=f"bf16 grad {k}")
 
 
 def test_training_mode_dropout_only_touches_o_input(golden):
