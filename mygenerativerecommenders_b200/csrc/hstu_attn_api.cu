@@ -17,9 +17,18 @@ bool hstu_attn_short_usable(const grb_hstu_attn_args* a, bool bwd);
 int hstu_attn_short_fwd(const grb_hstu_attn_args* a, cudaStream_t st);
 int hstu_attn_short_bwd(const grb_hstu_attn_args* a, cudaStream_t st);
 
-static bool force_cuda_core() {
-  const char* e = std::getenv("GRB_FORCE_CUDA_CORE");
+// developer switches, read once per process (not on every launch)
+static bool env_flag(const char* name) {
+  const char* e = std::getenv(name);
   return e && e[0] == '1';
+}
+static bool force_cuda_core() {
+  static const bool v = env_flag("GRB_FORCE_CUDA_CORE");
+  return v;
+}
+static bool force_fwd_v1() {
+  static const bool v = env_flag("GRB_FWD_V1");
+  return v;
 }
 }  // namespace grb
 
@@ -43,8 +52,7 @@ int grb_hstu_attn_fwd(const grb_hstu_attn_args* a, grb_stream_t stream) {
   if (!force_cuda_core() && hstu_attn_fwd_sm100_supported(a)) {
     // second-generation kernel when the buckets come from the per-batch cache (or no bias);
     // GRB_FWD_V1=1 keeps the first one (developer switch)
-    const char* v1 = std::getenv("GRB_FWD_V1");
-    if (!(v1 && v1[0] == '1') && hstu_attn_fwd2_sm100_usable(a)) return hstu_attn_fwd2_sm100(a, st);
+    if (!force_fwd_v1() && hstu_attn_fwd2_sm100_usable(a)) return hstu_attn_fwd2_sm100(a, st);
     return hstu_attn_fwd_sm100(a, st);
   }
   return hstu_attn_fwd_simt_dispatch(a, st);

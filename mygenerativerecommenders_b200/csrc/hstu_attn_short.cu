@@ -853,8 +853,8 @@ bool hstu_attn_short_usable(const grb_hstu_attn_args* a, bool bwd) {
 // GRB_SHORT_TIMELINE=1: dump the stamps of the probed CTAs to stderr after the launch (synchronises)
 static long long* timeline_buffer() {
   static long long* buf = nullptr;
-  const char* e = std::getenv("GRB_SHORT_TIMELINE");
-  if (!(e && e[0] == '1')) return nullptr;
+  static const bool on = [] { const char* e = std::getenv("GRB_SHORT_TIMELINE"); return e && e[0] == '1'; }();
+  if (!on) return nullptr;      // (read once per process, not on every launch)
   if (!buf) cudaMalloc(&buf, SH_TL_CTAS * SH_TL_SLOTS * sizeof(long long));
   cudaMemset(buf, 0, SH_TL_CTAS * SH_TL_SLOTS * sizeof(long long));
   return buf;
