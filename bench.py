@@ -336,7 +336,7 @@ def run_training(args, world, rank, local):
         d0.record()
         for i in range(n_d):
             row = {k: v.to(dev, non_blocking=True) for k, v in pinned[i % n_batches].items()}
-            last_d = float(step_t(row))                      # blocking loss read, as a logger would
+            last_d = float(step_t(row).detach())             # blocking loss read, as a logger would
         d1.record()
         torch.cuda.synchronize()
         ms_d = d0.elapsed_time(d1)
@@ -453,12 +453,13 @@ def _event_ms(fn, iters: int, warmup: int) -> float:
     return e0.elapsed_time(e1) / iters
 
 
-def run_long_sequence(local: int) -> dict:
+def run_long_sequence(local: int, world: int = 1, rank: int = 0) -> dict:
     """Measured in this run (nothing read from profiles/): (1) the long-sequence attention kernels on a
     C5 slice, 4 sequences x 8192 tokens, H=8, d=64, forward and backward timed alone (burst peak);
     (2) one full C5 training step (BASELINE.json configs[4]: N=8192, 8 layers, D=512, 8 heads x 64,
-    bf16, local negatives R=128, AdamW) on one GPU, jagged lengths U[1024, 8181], at the largest batch
-    <= 128 that fits."""
+    bf16, local negatives R=128, AdamW), jagged lengths U[1024, 8181], at the largest batch <= 128 per GPU
+    that fits; data parallel over the ranks when launched with torchrun (gradients, the dense 269 MB item
+    table included, reduced by PeerGradients' two-shot all-reduce kernel; max over ranks of the event time)."""
     from mygenerativerecommenders_b200 import _lib
     from mygenerativerecommenders_b200 import functional as GF
     from mygenerativerecommenders_b200 import hstu
@@ -467,37 +468,38 @@ def run_long_sequence(local: int) -> dict:
     pk = peaks()
     out = {}
     # ---- (1) attention slice ---------------------------------------------------------------
-    B, N, H, d = 4, 8192, 8, 64
-    lengths = torch.full((B,), N, dtype=torch.int64)
-    off = torch.zeros(B + 1, dtype=torch.int64)
-    off[1:] = torch.cumsum(lengths, 0)
-    T = int(off[-1])
-    g = torch.Generator(device=dev).manual_seed(0)
-    mk = lambda: (torch.randn(T, H * d, device=dev, generator=g) * 0.5).to(torch.bfloat16).requires_grad_(True)
-    q, k, v = mk(), mk(), mk()
-    ts = (978_300_000 + torch.cumsum(torch.randint(1, 5000, (B, N)), 1)).to(dev)
-    ts_w = (torch.randn(129, device=dev) * 0.02).requires_grad_(True)
-    pos_w = (torch.randn(2 * N - 1, device=dev) * 0.02).requires_grad_(True)
-    thr = hstu.tabulate_bucket_thresholds(hstu._default_bucketization, 128).to(dev)
-    offd = off.to(dev)
-    cache = GF.hstu_bucket_cache(offd, ts, thr, N)
-    pairs = int((lengths * (lengths + 1) // 2).sum())
-    fwd = lambda: GF.hstu_attention(q, k, v, offd, ts, ts_w, pos_w, thr, N, H, d, d, bucket_cache=cache)
-    with torch.no_grad():
-        ms_f = _event_ms(fwd, 10, 3)
-    o = fwd()
-    go = torch.randn_like(o)
-    bwd = lambda: torch.autograd.grad(o, (q, k, v, ts_w, pos_w), go, retain_graph=True)
-    ms_b = _event_ms(bwd, 5, 2)
-    f_f, f_b = pairs * 2 * H * 2 * d, pairs * 2 * H * 5 * d
-    out["attention_slice"] = {
-        "shape": "4 x 8192 tokens, H=8, d=64, bf16, relative time+position bias (C5 slice)",
-        "fwd_ms": ms_f, "fwd_tflops": f_f / ms_f / 1e9, "fwd_frac": f_f / ms_f / 1e9 / pk["bf16_tflops"],
-        "bwd_ms": ms_b, "bwd_tflops": f_b / ms_b / 1e9, "bwd_frac": f_b / ms_b / 1e9 / pk["bf16_tflops"],
-        "peak": pk["bf16_tflops"], "peak_source": pk["source"] + " (burst figure: kernels timed alone)",
-        "measured": "live, CUDA events, 10 / 5 launches after warm-up"}
-    del q, k, v, o, go, cache
-    torch.cuda.empty_cache()
+    if world == 1:
+        B, N, H, d = 4, 8192, 8, 64
+        lengths = torch.full((B,), N, dtype=torch.int64)
+        off = torch.zeros(B + 1, dtype=torch.int64)
+        off[1:] = torch.cumsum(lengths, 0)
+        T = int(off[-1])
+        g = torch.Generator(device=dev).manual_seed(0)
+        mk = lambda: (torch.randn(T, H * d, device=dev, generator=g) * 0.5).to(torch.bfloat16).requires_grad_(True)
+        q, k, v = mk(), mk(), mk()
+        ts = (978_300_000 + torch.cumsum(torch.randint(1, 5000, (B, N)), 1)).to(dev)
+        ts_w = (torch.randn(129, device=dev) * 0.02).requires_grad_(True)
+        pos_w = (torch.randn(2 * N - 1, device=dev) * 0.02).requires_grad_(True)
+        thr = hstu.tabulate_bucket_thresholds(hstu._default_bucketization, 128).to(dev)
+        offd = off.to(dev)
+        cache = GF.hstu_bucket_cache(offd, ts, thr, N)
+        pairs = int((lengths * (lengths + 1) // 2).sum())
+        fwd = lambda: GF.hstu_attention(q, k, v, offd, ts, ts_w, pos_w, thr, N, H, d, d, bucket_cache=cache)
+        with torch.no_grad():
+            ms_f = _event_ms(fwd, 10, 3)
+        o = fwd()
+        go = torch.randn_like(o)
+        bwd = lambda: torch.autograd.grad(o, (q, k, v, ts_w, pos_w), go, retain_graph=True)
+        ms_b = _event_ms(bwd, 5, 2)
+        f_f, f_b = pairs * 2 * H * 2 * d, pairs * 2 * H * 5 * d
+        out["attention_slice"] = {
+            "shape": "4 x 8192 tokens, H=8, d=64, bf16, relative time+position bias (C5 slice)",
+            "fwd_ms": ms_f, "fwd_tflops": f_f / ms_f / 1e9, "fwd_frac": f_f / ms_f / 1e9 / pk["bf16_tflops"],
+            "bwd_ms": ms_b, "bwd_tflops": f_b / ms_b / 1e9, "bwd_frac": f_b / ms_b / 1e9 / pk["bf16_tflops"],
+            "peak": pk["bf16_tflops"], "peak_source": pk["source"] + " (burst figure: kernels timed alone)",
+            "measured": "live, CUDA events, 10 / 5 launches after warm-up"}
+        del q, k, v, o, go, cache
+        torch.cuda.empty_cache()
     # ---- (2) full C5 step ------------------------------------------------------------------
     cfg = RetrievalConfig(
         name="C5 long-sequence", num_items=131_262, max_sequence_length=8181, gr_output_length=10,
@@ -506,13 +508,16 @@ def run_long_sequence(local: int) -> dict:
         compute_dtype=torch.bfloat16)
     ids = synthetic_item_ids(26_744, cfg.num_items)
     step_info = None
-    for Bc in (128, 64, 32, 16):
-        model = opt = rows = None
+    for Bc in ((128, 64, 32, 16) if world == 1 else (128,)):
+        model = opt = rows = reducer = None
         try:
             torch.manual_seed(42)
             model = RetrievalModel(cfg, ids).to(dev).train()
+            if world > 1:
+                reducer = model.enable_peer_gradients()
             opt = FusedAdamW(model.parameters(), lr=1e-3, betas=(0.9, 0.98), weight_decay=1e-3)
-            rows = [{k_: v_.to(dev) for k_, v_ in synthetic_batch(cfg, ids, Bc, seed=500 + i, min_len=1024).items()}
+            rows = [{k_: v_.to(dev) for k_, v_ in
+                     synthetic_batch(cfg, ids, Bc, seed=500 + 10 * rank + i, min_len=1024).items()}
                     for i in range(2)]
             totals = [int(r["history_lengths"].sum()) for r in rows]
             torch.cuda.reset_peak_memory_stats(dev)
@@ -521,10 +526,12 @@ def run_long_sequence(local: int) -> dict:
                 loss = model.training_loss(rows[i % 2], totals[i % 2])
                 opt.zero_grad(set_to_none=True)
                 loss.backward()
+                if reducer is not None:
+                    reducer.reduce()
                 opt.step()
                 return loss
             step(0)
-            torch.cuda.synchronize()
+            barrier(world)
             _lib.profile_start()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             n_it = 3
@@ -532,9 +539,15 @@ def run_long_sequence(local: int) -> dict:
             for i in range(n_it):
                 loss = step(i + 1)
             e1.record()
-            torch.cuda.synchronize()
+            barrier(world)
             prof = _lib.profile_stop()
-            ms = e0.elapsed_time(e1) / n_it
+            ms = max_over_ranks(e0.elapsed_time(e1), world, dev) / n_it
+            tok_all = float(sum(totals)) / 2
+            if world > 1:
+                import torch.distributed as dist
+                tt = torch.tensor([tok_all], device=dev, dtype=torch.float64)
+                dist.all_reduce(tt)
+                tok_all = float(tt.item())
             lens = [rows[(i + 1) % 2]["history_lengths"] for i in range(n_it)]
             pr = sum(attention_pairs(l.cpu() + 1) for l in lens) * cfg.num_blocks
             Hh, dd = cfg.num_heads, cfg.attention_dim
@@ -546,20 +559,21 @@ def run_long_sequence(local: int) -> dict:
                     att[name] = {"ms_per_step": tot_ / n_it, "tflops": fl / tot_ / 1e9,
                                  "frac": fl / tot_ / 1e9 / pk["bf16_tflops_sustained"]}
             step_info = {
-                "workload": "C5 (BASELINE.json configs[4]) on ONE GPU: N=8192, 8 HSTU layers, D=512, 8 heads x 64, "
-                            "bf16 / fp32 master, local negatives R=128, dropout 0.2, AdamW; jagged lengths "
-                            "U[1024, 8181]; fwd+bwd+optimizer, eager (no graphs)",
-                "batch": Bc, "tokens_per_step": sum(totals) / 2, "ms_per_step": ms,
-                "sequences_per_s": Bc / (ms / 1e3), "tokens_per_s": sum(totals) / 2 / (ms / 1e3),
+                "workload": f"C5 (BASELINE.json configs[4]) on {world} GPU(s), data parallel: N=8192, 8 HSTU layers, "
+                            "D=512, 8 heads x 64, bf16 / fp32 master, local negatives R=128, dropout 0.2, AdamW; "
+                            "jagged lengths U[1024, 8181]; fwd+bwd+optimizer, eager (no graphs)",
+                "batch_per_gpu": Bc, "n_gpus": world, "tokens_per_step": tok_all, "ms_per_step": ms,
+                "sequences_per_s": Bc * world / (ms / 1e3), "tokens_per_s": tok_all / (ms / 1e3),
+                "attention_figures": "this rank's kernels",
                 "peak_memory_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
                 "attention": att, "attention_peak": pk["bf16_tflops_sustained"],
                 "attention_share_of_step": sum(a["ms_per_step"] for a in att.values()) / ms if att else None,
-                "loss": float(loss), "steps_timed": n_it}
+                "loss": float(loss.detach()), "steps_timed": n_it}
             break
         except torch.OutOfMemoryError:
             step_info = {"error": f"out of memory at batch {Bc}"}
         finally:
-            del model, opt, rows
+            del model, opt, rows, reducer
             torch.cuda.empty_cache()
     out["train_step"] = step_info
     return out
@@ -893,7 +907,7 @@ def main():
     del model
     torch.cuda.empty_cache()
     retrieval = None if args.skip_retrieval else run_retrieval(args, world, rank, local)
-    long_seq = run_long_sequence(local) if (world == 1 and not args.skip_long_sequence) else None
+    long_seq = None if args.skip_long_sequence else run_long_sequence(local, world, rank)
     probe = train.pop("_probe", None)
     line = {
         "metric": "hstu_train_sequences_per_s", "value": train["value"], "unit": "sequences/s",
