@@ -161,3 +161,55 @@ def test_hstu_layer_options(golden, name):
     assert (x.grad - c["dx"]).abs().max().item() <= 1e-4 * c["dx"].abs().max().item()
     for k, gref in c["grads"].items():
         assert (sd[k].grad - gref).abs().max().item() <= 2e-4 * max(gref.abs().max().item(), 1e-6), k
+
+
+def test_port_agrees_with_the_staged_reference_modules_live():
+    """Beyond the committed fixtures: where the unmodified reference package is staged (oracle/_ref, written
+    by oracle/stage_ref.py in the build container), the port's encoder and its sampled-softmax loss are run
+    against the reference's OWN modules on fresh random weights and inputs (CPU, fp32)."""
+    from oracle import ref_verbatim as RV
+    if not RV.available():
+        pytest.skip("oracle/_ref is not staged")
+    R = RV._import()
+    torch.manual_seed(11)
+    B, L, out_len, D, H, d = 5, 30, 4, 48, 2, 24
+    N = L + out_len
+    enc = R["HSTU"](max_sequence_len=L, max_output_len=out_len, embedding_dim=D, item_embedding_dim=D,
+                    num_blocks=2, num_heads=H, linear_dim=d, attention_dim=d, normalization="rel_bias",
+                    linear_config="uvqk", linear_activation="silu", linear_dropout_rate=0.0,
+                    attn_dropout_rate=0.0).eval()
+    lengths = torch.tensor([34, 2, 17, 30, 9])
+    valid = torch.arange(N).unsqueeze(0) < lengths.unsqueeze(1)
+    ts = (978_300_000 + torch.cumsum(torch.randint(1, 5000, (B, N)), dim=1)) * valid
+    x = torch.randn(B, N, D) * valid.unsqueeze(-1)
+    with torch.no_grad():
+        y_ref, _ = enc(past_lengths=lengths, user_embeddings=x, valid_mask=valid.unsqueeze(-1).float(),
+                       past_payloads={"timestamps": ts})
+        sd = {k: v.detach().clone() for k, v in enc.state_dict().items()}
+        y = O.hstu_forward(lengths, x, ts, sd, 2, H, d, d)
+    assert (y - y_ref).abs().max().item() <= 1e-5 * y_ref.abs().max().item()
+    # sampled softmax: the reference's loss with its local sampler's draw injected into the port
+    V, R_ = 60, 16
+    table = torch.randn(V + 1, D)
+    table[0] = 0
+    emb = torch.nn.Embedding(V + 1, D, padding_idx=0)
+    with torch.no_grad():
+        emb.weight.copy_(table)
+    smp = R["LocalNegativesSampler"](l2_norm=True, l2_norm_eps=1e-6, all_item_ids=list(range(1, V + 1)))
+    smp._item_emb = emb
+    n = 40
+    out_emb = torch.nn.functional.normalize(torch.randn(n, D), dim=-1)
+    sup_ids = torch.randint(1, V + 1, (n,))
+    sup_w = (torch.rand(n) > 0.2).float()
+    loss_fn = R["SampledSoftmaxLoss"](num_to_sample=R_, softmax_temperature=0.05)
+    torch.manual_seed(3)
+    with torch.no_grad():
+        ref_loss = loss_fn.jagged_forward(output_embeddings=out_emb, supervision_ids=sup_ids,
+                                          supervision_embeddings=table[sup_ids], supervision_weights=sup_w,
+                                          negatives_sampler=smp, similarity=R["DotProductSimilarity"]())
+    torch.manual_seed(3)
+    neg_ids = smp._all_item_ids[torch.randint(low=0, high=V, size=(n, R_))] if hasattr(smp, "_all_item_ids") else None
+    if neg_ids is None:
+        pytest.skip("reference sampler layout changed")
+    loss, _ = O.sampled_softmax_loss(out_emb, sup_ids, table[sup_ids], sup_w, neg_ids, table[neg_ids], 0.05, 1e-6)
+    assert abs(loss.item() - ref_loss.item()) <= 1e-5 * abs(ref_loss.item())
