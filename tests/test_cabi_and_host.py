@@ -152,3 +152,30 @@ def test_layer_argument_errors_come_before_any_kernel():
         mk(normalization="softmax_rel_bias")(x, off, None, mask, delta_x_offsets=delta, cache=cache)
     with pytest.raises(RuntimeError, match="no CPU fallback"):         # a valid call reaches the kernels
         mk()(x, off, None, mask)
+
+
+def test_retrieval_metrics_follow_the_reference_formulas():
+    """metrics/retrieval.py:40-68 restated (torchmetrics is not in the image): ranks from (top_k_ids,
+    target_ids), then NDCG / HR / MRR; ``update_ranks`` (the fused kernel's output) gives the same."""
+    from mygenerativerecommenders_b200.metrics import RetrievalMetrics
+    g = torch.Generator().manual_seed(5)
+    B, k = 64, 20
+    top = torch.stack([torch.randperm(500, generator=g)[:k] + 1 for _ in range(B)])
+    tgt = torch.where(torch.rand(B, generator=g) < 0.6, top[torch.arange(B), torch.randint(0, k, (B,), generator=g)],
+                      torch.full((B,), 9999))
+    m = RetrievalMetrics(k=k, at_k_list=[1, 10, 20])
+    m.update(top[:40], tgt[:40].unsqueeze(1))
+    m.update(top[40:], tgt[40:])
+    out = m.compute()
+    # the reference's compute(), line by line
+    _, rank_indices = torch.max(torch.cat([top, tgt.unsqueeze(1)], dim=1) == tgt.unsqueeze(1), dim=1)
+    ranks = rank_indices + 1
+    for at_k in (1, 10, 20):
+        ndcg = torch.where(ranks <= at_k, 1.0 / torch.log2(ranks + 1), torch.zeros(1)).mean()
+        assert torch.equal(out[f"ndcg@{at_k}"], ndcg)
+        assert torch.equal(out[f"hr@{at_k}"], (ranks <= at_k).float().mean())
+    assert torch.equal(out["mrr"], (1.0 / ranks).mean())
+    assert (ranks == k + 1).any() and (ranks <= k).any()
+    m2 = RetrievalMetrics(k=k, at_k_list=[1, 10, 20])
+    m2.update_ranks(ranks.to(torch.int32))
+    assert all(torch.equal(out[key], v) for key, v in m2.compute().items())

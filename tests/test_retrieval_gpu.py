@@ -123,6 +123,11 @@ def test_invalid_ids_filtered_inside_the_selection(B, X, D, k, n_inv, dtype):
     # metrics/retrieval.py:45-55 on the kernel's own ids
     _, rank_idx = torch.max(torch.cat([i.cpu(), target.unsqueeze(1)], dim=1) == target.unsqueeze(1), dim=1)
     assert torch.equal(ranks.cpu().long(), rank_idx + 1)
+    from mygenerativerecommenders_b200.metrics import RetrievalMetrics
+    m_ids, m_rk = RetrievalMetrics(k, [1, 10, min(k, 50)]), RetrievalMetrics(k, [1, 10, min(k, 50)])
+    m_ids.update(i, target.to(DEV).unsqueeze(1))
+    m_rk.update_ranks(ranks)
+    assert all(torch.equal(v, m_rk.compute()[key]) for key, v in m_ids.compute().items())
     # the module boundary takes the fused path and returns (ids, scores)
     ci = CandidateIndex(k=k, ids=ids, top_k_module=MIPSBruteForceTopK(),
                         embeddings=items.to(DEV).unsqueeze(0)).to(DEV)
