@@ -426,6 +426,17 @@ typedef struct grb_ssl_args {
 int grb_sampled_softmax_fwd(const grb_ssl_args* a, grb_stream_t stream);
 int grb_sampled_softmax_bwd(const grb_ssl_args* a, grb_stream_t stream);
 
+/* The same backward for ONE table of already-normalised rows (l2_norm == 0, d1 == 0: the in-batch cache,
+ * negative_sampler.py:192-212), D % 8 == 0, D <= 256, without atomics on the table gradient: the row-wise
+ * half (dq, dp, the coefficients) gathers bf16 copies of the table rows; the (row, negative) pairs are
+ * counting-sorted by table row; one warp per table row then sums coef * q[n] over its list from a bf16
+ * copy of q and stores the row (rows nobody sampled get zeros: dtable0 needs no zero fill and is
+ * OVERWRITTEN, not accumulated).  table_rows = rows of table0 / dtable0.  Gradients see q and the table
+ * rounded to bf16 inside the sums.  Five stream-ordered launches; workspace from the function below. */
+int64_t grb_sampled_softmax_bwd_csr_workspace_bytes(int64_t n_rows, int32_t R, int32_t D, int64_t table_rows);
+int grb_sampled_softmax_bwd_csr(const grb_ssl_args* a, int64_t table_rows, void* workspace,
+                                int64_t workspace_bytes, grb_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Embedding-table gradient: table_grad[ids[i], :] += grad[i, :] for every i with ids[i] != skip_id.
  *     Replaces aten::embedding_dense_backward under the nn.Embedding tables of

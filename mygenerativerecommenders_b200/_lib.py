@@ -141,6 +141,8 @@ SYMBOLS = {
         C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "grb_sampled_softmax_fwd": (C.c_int, [C.POINTER(SslArgs), c_vp]),
     "grb_sampled_softmax_bwd": (C.c_int, [C.POINTER(SslArgs), c_vp]),
+    "grb_sampled_softmax_bwd_csr_workspace_bytes": (c_i64, [c_i64, c_i32, c_i32, c_i64]),
+    "grb_sampled_softmax_bwd_csr": (C.c_int, [C.POINTER(SslArgs), c_i64, c_vp, c_i64, c_vp]),
     "grb_l2norm_fwd": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, C.c_float, c_vp]),
     "grb_l2norm_bwd": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]),
     "grb_p2p_put_rows": (C.c_int, [c_vp, c_i64, C.POINTER(c_vp), c_i32, c_i64, c_i64, c_i64, c_i64, c_vp]),

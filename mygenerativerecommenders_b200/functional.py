@@ -7,6 +7,7 @@ library surface as Python exceptions (ValueError / NotImplementedError / Runtime
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -888,7 +889,8 @@ def layer_norm_gate(x: torch.Tensor, gate: Optional[torch.Tensor], eps: float) -
 # --------------------------------------------------------------------------------------------
 class _SampledSoftmax(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, p, table0, table1, idx0, idx1, pos_ids, neg_ids, l2_norm, eps, temperature):
+    def forward(ctx, q, p, table0, table1, idx0, idx1, pos_ids, neg_ids, l2_norm, eps, temperature,
+                bf16_backward=False):
         _lib.require_cuda(q, p, table0, table1, idx0, idx1, pos_ids, neg_ids)
         for t in (q, p, table0, table1):
             if t is not None and t.dtype != torch.float32:
@@ -910,6 +912,7 @@ class _SampledSoftmax(torch.autograd.Function):
             _lib.check(_lib.lib().grb_sampled_softmax_fwd(C.byref(a), _lib.stream_ptr(q.device)))
         ctx.save_for_backward(q, p, table0, table1, idx0, idx1, pos_ids, neg_ids, probs)
         ctx.cfg = (l2_norm, eps, temperature)
+        ctx.bf16_backward = bool(bf16_backward)
         return loss_rows
 
     @staticmethod
@@ -941,6 +944,22 @@ class _SampledSoftmax(torch.autograd.Function):
         g = g.contiguous().float()
         dq = torch.empty(q.shape, dtype=torch.float32, device=q.device)
         dp = torch.empty(p.shape, dtype=torch.float32, device=q.device)
+        n, D = q.shape
+        R = idx0.shape[1]
+        if (ctx.bf16_backward and table1 is None and not l2_norm and D % 8 == 0 and D <= 256 and n * R < 2 ** 31
+                and os.environ.get("GRB_SSL_BWD_ATOMIC") != "1"):
+            # one table of normalised rows (the in-batch cache): pairs counting-sorted by table row, both
+            # halves of the backward read bf16 rows, no atomics on the table gradient, no zero fill
+            dt0 = torch.empty(table0.shape, dtype=torch.float32, device=q.device)
+            a = _SampledSoftmax._args(q, p, table0, None, idx0, None, pos_ids, neg_ids, l2_norm, eps,
+                                      temperature, probs)
+            a.g, a.dq, a.dp, a.dtable0 = g.data_ptr(), dq.data_ptr(), dp.data_ptr(), dt0.data_ptr()
+            need = int(_lib.lib().grb_sampled_softmax_bwd_csr_workspace_bytes(n, R, D, table0.shape[0]))
+            ws = torch.empty(need, dtype=torch.uint8, device=q.device)
+            with _lib.timed("sampled_softmax_bwd"):
+                _lib.check(_lib.lib().grb_sampled_softmax_bwd_csr(C.byref(a), table0.shape[0], ws.data_ptr(), need,
+                                                                  _lib.stream_ptr(q.device)))
+            return dq, dp, dt0, None, None, None, None, None, None, None, None, None
         dt0 = torch.zeros(table0.shape, dtype=torch.float32, device=q.device)
         dt1 = torch.zeros(table1.shape, dtype=torch.float32, device=q.device) if table1 is not None else None
         a = _SampledSoftmax._args(q, p, table0, table1, idx0, idx1, pos_ids, neg_ids, l2_norm, eps,
@@ -951,20 +970,23 @@ class _SampledSoftmax(torch.autograd.Function):
             a.dtable1 = dt1.data_ptr()
         with _lib.timed("sampled_softmax_bwd"):
             _lib.check(_lib.lib().grb_sampled_softmax_bwd(C.byref(a), _lib.stream_ptr(q.device)))
-        return dq, dp, dt0, dt1, None, None, None, None, None, None, None
+        return dq, dp, dt0, dt1, None, None, None, None, None, None, None, None
 
 
 def sampled_softmax_rows(q: torch.Tensor, p: torch.Tensor, table0: torch.Tensor,
                          table1: Optional[torch.Tensor], idx0: torch.Tensor,
                          idx1: Optional[torch.Tensor], pos_ids: torch.Tensor,
                          neg_ids: torch.Tensor, l2_norm: bool, eps: float,
-                         temperature: float) -> torch.Tensor:
+                         temperature: float, bf16_backward: bool = False) -> torch.Tensor:
     """Per-row sampled-softmax loss -log_softmax([q.p/T, masked q.e_r/T])[0], (N',) fp32.
 
     Negatives e_r = concat(table0[idx0[n, r]], table1[idx1[n, r]]) are gathered, optionally
-    L2-normalised, dotted and reduced inside one kernel; (N', R, D) never exists."""
+    L2-normalised, dotted and reduced inside one kernel; (N', R, D) never exists.
+    ``bf16_backward`` (for models whose activations are bf16 anyway): one table of normalised rows
+    (the in-batch cache) takes the atomics-free backward of csrc/ssl_bwd_csr.cu, whose two sums read
+    bf16 copies of q and of the table rows; the forward / the loss stay fp32."""
     return _SampledSoftmax.apply(q, p, table0, table1, idx0, idx1, pos_ids, neg_ids, l2_norm, eps,
-                                 temperature)
+                                 temperature, bf16_backward)
 
 
 # --------------------------------------------------------------------------------------------

@@ -50,10 +50,14 @@ def _is_plain_dot(similarity) -> bool:
 
 
 class SampledSoftmaxLoss(AutoregressiveLoss):
-    def __init__(self, num_to_sample: int, softmax_temperature: float) -> None:
+    def __init__(self, num_to_sample: int, softmax_temperature: float, bf16_backward: bool = False) -> None:
+        """``bf16_backward`` (extension, default off = the reference's fp32 arithmetic): with the in-batch
+        sampler the backward of the fused loss reads bf16 copies of the output embeddings and of the
+        cache rows (GF.sampled_softmax_rows) — for encoders that compute in bf16 anyway."""
         super().__init__()
         self._num_to_sample: int = num_to_sample
         self._softmax_temperature: float = softmax_temperature
+        self._bf16_backward: bool = bool(bf16_backward)
 
     def jagged_forward(self, output_embeddings: torch.Tensor, supervision_ids: torch.Tensor,
                        supervision_embeddings: torch.Tensor, supervision_weights: torch.Tensor,
@@ -82,7 +86,7 @@ class SampledSoftmaxLoss(AutoregressiveLoss):
             jagged_loss = GF.sampled_softmax_rows(
                 output_embeddings, positive_embeddings, t0, t1, fused.idx0, fused.idx1,
                 supervision_ids, fused.ids, fused.l2_norm, negatives_sampler._l2_norm_eps,
-                self._softmax_temperature)
+                self._softmax_temperature, bf16_backward=self._bf16_backward)
             return (jagged_loss * supervision_weights).sum() / supervision_weights.sum()
 
         # unfused: the reference's sequence on torch ops (autoregressive_losses.py:272-306)

@@ -350,7 +350,8 @@ class RetrievalModel(torch.nn.Module):
             self.negatives_sampler = InBatchNegativesSampler(
                 l2_norm=True, l2_norm_eps=cfg.l2_eps, dedup_embeddings=True)
             self.negatives_sampler.max_item_id = cfg.num_items     # enables the sort-free cache build
-        self.loss = SampledSoftmaxLoss(cfg.num_negatives, cfg.temperature)
+        self.loss = SampledSoftmaxLoss(cfg.num_negatives, cfg.temperature,
+                                       bf16_backward=cfg.compute_dtype == torch.bfloat16)
         index_cls = ShardedCandidateIndex if sharded_index else CandidateIndex
         self.candidate_index = index_cls(k=cfg.top_k, ids=all_item_ids,
                                          top_k_module=MIPSBruteForceTopK())

@@ -276,11 +276,17 @@ def test_inbatch_sampler_fused_vs_oracle(golden, monkeypatch):
         assert torch.allclose(src.grad.cpu()[m].sum(0), srcc.grad[m].sum(0), rtol=1e-3, atol=1e-6)
 
 
-@pytest.mark.parametrize("D,R,l2", [(256, 128, False), (256, 40, True), (128, 128, True), (128, 33, False),
-                                     (512, 128, True), (512, 20, False)])
-def test_fused_sampled_softmax_vector_path(D, R, l2):
-    """Single table with D = 128 / 256 takes the float4 kernels (32 negatives reduced together);
-    same oracle as the generic path, incl. collisions and a ragged last batch of negatives."""
+@pytest.mark.parametrize("D,R,l2,bwd", [(256, 128, False, "csr"), (256, 128, False, "atomic"), (256, 40, True, ""),
+                                         (128, 128, True, ""), (128, 33, False, "csr"), (128, 33, False, "atomic"),
+                                         (512, 128, True, ""), (512, 20, False, ""), (64, 17, False, "csr")])
+def test_fused_sampled_softmax_vector_path(D, R, l2, bwd, monkeypatch):
+    """Single table with D = 128 / 256 / 512 takes the float4 kernels (32 negatives reduced together);
+    same oracle as the generic path, incl. collisions and a ragged last batch of negatives.  A table of
+    already-normalised rows (l2 False: the in-batch cache) takes the atomics-free backward
+    (csrc/ssl_bwd_csr.cu: pairs counting-sorted by table row, bf16 gathers) when asked to (bf16_backward):
+    its gradients carry the bf16 rounding of q and of the table rows inside the sums (4e-3 instead of 2e-4)."""
+    if bwd == "atomic":          # the developer switch wins over the flag
+        monkeypatch.setenv("GRB_SSL_BWD_ATOMIC", "1")
     gen = torch.Generator().manual_seed(D + R)
     n, V = 150, 60
     t0 = torch.randn(V + 1, D, generator=gen) * 0.3
@@ -298,13 +304,15 @@ def test_fused_sampled_softmax_vector_path(D, R, l2):
     ref.backward()
     gq, g0 = (x.to(DEV).requires_grad_(True) for x in (q, t0))
     rows = GF.sampled_softmax_rows(gq, sup.to(DEV), g0, None, neg_ids.to(DEV), None, pos_ids.to(DEV),
-                                   neg_ids.to(DEV), l2, 1e-6, 0.05)
+                                   neg_ids.to(DEV), l2, 1e-6, 0.05, bf16_backward=(bwd == "csr"))
     loss = (rows * w.to(DEV)).sum() / w.sum()
     assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
     loss.backward()
+    tol = 4e-3 if bwd == "csr" else 2e-4
     for got, r, name in ((gq, lq, "dq"), (g0, lt, "dt0")):
         scale = r.grad.abs().max().item()
-        assert (got.grad.cpu().double() - r.grad).abs().max().item() <= 2e-4 * scale, name
+        assert (got.grad.cpu().double() - r.grad).abs().max().item() <= tol * scale, name
+    assert torch.isfinite(g0.grad).all()
 
 
 @pytest.mark.parametrize("direct", [False, True])
