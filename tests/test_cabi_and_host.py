@@ -179,3 +179,42 @@ def test_retrieval_metrics_follow_the_reference_formulas():
     m2 = RetrievalMetrics(k=k, at_k_list=[1, 10, 20])
     m2.update_ranks(ranks.to(torch.int32))
     assert all(torch.equal(out[key], v) for key, v in m2.compute().items())
+
+
+def test_async_topk_handle_reruns_on_overflow_and_gives_up_after_three():
+    """functional.MipsTopkCall: result() waits for the call's own flag, re-runs with the reported capacity
+    + slack when a row overflowed, returns the tensors of the successful attempt (host logic only)."""
+    from mygenerativerecommenders_b200.functional import MipsTopkCall
+
+    class Done:
+        def synchronize(self):
+            pass
+
+    caps = []
+
+    def run(cap):
+        caps.append(cap)
+        flag = [0 if cap >= 5000 else 4000]          # the first attempt (cap 0 = auto) overflows to 4000
+        return ("scores", "ids", cap), flag, Done()
+
+    call = MipsTopkCall(run, *run(0))
+    assert call.result() == ("scores", "ids", 5024) and caps == [0, 5024]
+    always = MipsTopkCall(lambda cap: (None, [7], Done()), None, [7], Done())
+    with pytest.raises(RuntimeError, match="overflowed repeatedly"):
+        always.result()
+
+
+def test_candidate_index_takes_the_fused_filter_only_when_it_is_equivalent():
+    from mygenerativerecommenders_b200.candidate_index import _fused_filter_ok
+    from mygenerativerecommenders_b200.top_k import MIPSBruteForceTopK
+
+    class Foreign:      # a reference-style top-k module without forward_filtered
+        pass
+    ours = MIPSBruteForceTopK()
+    assert _fused_filter_ok(ours, 200, 211, 3706)            # C1 / C2: k' = 411
+    assert _fused_filter_ok(ours, 200, 61, 700_000)          # C3
+    assert not _fused_filter_ok(ours, 200, 0, 3706)          # nothing to filter
+    assert not _fused_filter_ok(Foreign(), 200, 61, 3706)    # foreign module: the reference's composite
+    assert not _fused_filter_ok(ours, 200, 61, 230)          # k + N exceeds the corpus: rows could run short
+    assert not _fused_filter_ok(ours, 1900, 200, 10 ** 6)    # k + N > 2048: beyond the kernel's shared memory
+    assert not _fused_filter_ok(ours, 10, 1025, 10 ** 6)     # invalid list longer than the kernel stages
