@@ -12,7 +12,8 @@
 //             written out; dq[n] = dzpos p[n] + sum_r coef e_r with e_r gathered as 16-byte bf16 chunks;
 //             dp[n] = dzpos q[n]; counts[idx[n, r]] += 1 for every non-zero coefficient.
 //   (exclusive scan of the counts: grb_complete_cumsum)
-//   scatter : pair (n, r) -> its slot in the list of cache row idx[n, r] (counting sort).
+//   scatter : pair (n, r) -> its slot in the list of cache row idx[n, r] (counting sort; the slot inside the
+//             list is the old value of the counter, remembered by `rows`).
 //   cols    : warp per cache row c: d cache[c] = sum over its list of coef * q[n] (bf16 q rows, fp32
 //             accumulation in registers, one plain store per row — rows nobody sampled get zeros, so the
 //             gradient needs no zero fill).
@@ -38,7 +39,7 @@ struct CsrP {
   const float* probs; const float* g;
   float* dq; float* dp; float* dt0;
   __nv_bfloat16* q16; __nv_bfloat16* t16;
-  float* coef; int32_t* counts; int32_t* ptr; int32_t* cursor; int32_t* pairs;
+  float* coef; int32_t* counts; int32_t* ptr; int32_t* slot; int32_t* pairs;
 };
 
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
@@ -65,10 +66,7 @@ __global__ void __launch_bounds__(256) csr_prep_kernel(CsrP P) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.y) : "f"(v.w), "f"(v.z));
     *reinterpret_cast<uint2*>((is_q ? P.q16 : P.t16) + row * P.D + c) = o;
   }
-  for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < P.X0; i += stride) {
-    P.counts[i] = 0;
-    P.cursor[i] = 0;
-  }
+  for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < P.X0; i += stride) P.counts[i] = 0;
 }
 
 __global__ void __launch_bounds__(CSR_WARPS * 32) csr_rows_kernel(CsrP P) {
@@ -106,7 +104,9 @@ __global__ void __launch_bounds__(CSR_WARPS * 32) csr_rows_kernel(CsrP P) {
       my_i = idx[r];
       if (g != 0.f && nid[r] != pid) my_c = g * pr[r + 1] / P.temp;
       cf[r] = my_c;
-      if (my_c != 0.f) atomicAdd(P.counts + my_i, 1);
+      // the counter's old value is this pair's position inside the list of its cache row: the counting
+      // sort below needs no second round of atomics
+      if (my_c != 0.f) P.slot[n * (int64_t) P.R + r] = atomicAdd(P.counts + my_i, 1);
     }
     if (!__any_sync(0xffffffffu, my_c != 0.f)) continue;
 #pragma unroll 2
@@ -143,9 +143,7 @@ __global__ void __launch_bounds__(256) csr_scatter_kernel(CsrP P) {
   const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.n_rows * P.R) return;
   if (P.coef[i] == 0.f) return;
-  const int64_t c = P.idx[i];
-  const int pos = atomicAdd(P.cursor + c, 1);
-  P.pairs[P.ptr[c] + pos] = (int32_t) i;
+  P.pairs[P.ptr[P.idx[i]] + P.slot[i]] = (int32_t) i;
 }
 
 __global__ void __launch_bounds__(CSR_WARPS * 32) csr_cols_kernel(CsrP P) {
@@ -194,7 +192,7 @@ __global__ void __launch_bounds__(CSR_WARPS * 32) csr_cols_kernel(CsrP P) {
 
 int64_t al256(int64_t x) { return (x + 255) & ~255ll; }
 
-struct CsrPlan { int64_t q16, t16, coef, counts, ptr, cursor, pairs, total; };
+struct CsrPlan { int64_t q16, t16, coef, counts, ptr, slot, pairs, total; };
 CsrPlan plan(int64_t n, int R, int D, int64_t X0) {
   CsrPlan L{};
   int64_t o = 0;
@@ -203,7 +201,7 @@ CsrPlan plan(int64_t n, int R, int D, int64_t X0) {
   L.coef = o;   o = al256(o + n * R * 4);
   L.counts = o; o = al256(o + X0 * 4);
   L.ptr = o;    o = al256(o + (X0 + 1) * 4);
-  L.cursor = o; o = al256(o + X0 * 4);
+  L.slot = o;   o = al256(o + n * R * 4);
   L.pairs = o;  o = al256(o + n * R * 4);
   L.total = o;
   return L;
@@ -255,7 +253,7 @@ int grb_sampled_softmax_bwd_csr(const grb_ssl_args* a, int64_t table_rows, void*
   P.dq = a->dq; P.dp = a->dp; P.dt0 = a->dtable0;
   P.q16 = reinterpret_cast<__nv_bfloat16*>(ws + L.q16); P.t16 = reinterpret_cast<__nv_bfloat16*>(ws + L.t16);
   P.coef = reinterpret_cast<float*>(ws + L.coef); P.counts = reinterpret_cast<int32_t*>(ws + L.counts);
-  P.ptr = reinterpret_cast<int32_t*>(ws + L.ptr); P.cursor = reinterpret_cast<int32_t*>(ws + L.cursor);
+  P.ptr = reinterpret_cast<int32_t*>(ws + L.ptr); P.slot = reinterpret_cast<int32_t*>(ws + L.slot);
   P.pairs = reinterpret_cast<int32_t*>(ws + L.pairs);
   csr_prep_kernel<<<1184, 256, 0, st>>>(P);
   GRB_LAUNCH_OK();
