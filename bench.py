@@ -391,6 +391,12 @@ def run_training(args, world, rank, local):
         # 4 loads + 3 stores of fp32 per parameter element (include/grb200.h grb_adamw_step)
         "adamw_step": ("hbm", 28 * sum(p.numel() for p in model.parameters()) * n_attr),
     }
+    # the six projection GEMMs of a layer (csrc/proj_gemm.cu), 2 M N K each, over the padded row bucket
+    t_pads = sum(-(-int(l.sum()) // 1024) * 1024 for l in lengths_used)
+    n_uvqk, n_o = 2 * H * dv + 2 * H * dqk, H * dv
+    for kind in ("fwd", "dgrad", "wgrad"):
+        work[f"proj_gemm_uvqk_{kind}"] = ("tensor", cfg.num_blocks * 2 * t_pads * D * n_uvqk)
+        work[f"proj_gemm_o_{kind}"] = ("tensor", cfg.num_blocks * 2 * t_pads * n_o * D)
     step_ms = ms / args.steps
     kern = {}
     for name, (n, tot_ms) in prof.items():
