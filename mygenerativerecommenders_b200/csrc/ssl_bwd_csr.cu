@@ -18,8 +18,9 @@
 //             accumulation in registers, one plain store per row — rows nobody sampled get zeros, so the
 //             gradient needs no zero fill).
 //
-// Gradients therefore see q and the cache rounded to bf16 inside the two sums (relative 2^-9 per term,
-// independent signs): well inside the 2e-2 gradient tolerance of the bf16 path; the loss and the
+// Gradients therefore see q, the cache and the coefficients rounded to bf16 inside the two sums (the
+// products are mixed-precision FMAs, bf16 x bf16 -> fp32 accumulate; relative 2^-9 per factor, independent
+// signs): well inside the 2e-2 gradient tolerance of the bf16 path; the loss and the
 // probabilities are the forward kernel's, computed from the fp32 values.
 #include "common.cuh"
 
@@ -49,6 +50,23 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
     f[2 * i] = __uint_as_float(w[i] << 16);
     f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
   }
+}
+
+// acc[0..7] += c * (the 8 bf16 values of v), with c given as a bf16 pair (c, c): eight mixed-precision
+// FMAs (bf16 x bf16 -> fp32 accumulate, FHFMA) on the register halves, no unpacking
+__device__ __forceinline__ void fma8_bf16(float (&acc)[8], uint32_t c2, const uint4& v) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    asm("{\n\t.reg .b16 cl, ch, vl, vh;\n\tmov.b32 {cl, ch}, %2;\n\tmov.b32 {vl, vh}, %3;\n\t"
+        "fma.rn.f32.bf16 %0, cl, vl, %0;\n\tfma.rn.f32.bf16 %1, ch, vh, %1;\n\t}"
+        : "+f"(acc[2 * i]), "+f"(acc[2 * i + 1])
+        : "r"(c2), "r"(w[i]));
+}
+__device__ __forceinline__ uint32_t bf16_pair(float c) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %1;" : "=r"(r) : "f"(c));
+  return r;
 }
 
 __global__ void __launch_bounds__(256) csr_prep_kernel(CsrP P) {
@@ -125,10 +143,7 @@ __global__ void __launch_bounds__(CSR_WARPS * 32) csr_rows_kernel(CsrP P) {
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         if (c4[t] == 0.f) continue;    // warp-uniform
-        float e[8];
-        unpack8(e4[t], e);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) dqa[k] = fmaf(c4[t], e[k], dqa[k]);
+        fma8_bf16(dqa, bf16_pair(c4[t]), e4[t]);
       }
     }
   }
@@ -175,12 +190,7 @@ __global__ void __launch_bounds__(CSR_WARPS * 32) csr_cols_kernel(CsrP P) {
                                       : make_uint4(0, 0, 0, 0);
       }
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        float qv[8];
-        unpack8(q4[t], qv);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = fmaf(c4[t], qv[k], acc[k]);
-      }
+      for (int t = 0; t < 4; ++t) fma8_bf16(acc, bf16_pair(c4[t]), q4[t]);
     }
   }
   if (act) {
