@@ -6,7 +6,12 @@ namespace grb {
 
 constexpr int MIPS_TILE_N = 128;  // items per tile: the sampling granule
 
-enum { MIPS_EPI_STORE = 0, MIPS_EPI_FILTER = 1 };
+// GMAX / PRIVATE: the two passes of the small-batch plan (B <= 128, one query block; mips_small.cu)
+enum { MIPS_EPI_STORE = 0, MIPS_EPI_FILTER = 1, MIPS_EPI_GMAX = 2, MIPS_EPI_PRIVATE = 3 };
+
+// candidate of a private sub-list: (score bits, item index)
+struct __align__(8) MipsCand { uint32_t score; int32_t item; };
+constexpr int MIPS_SUB_SPARE = 32;   // spare entries behind a sub-list's capacity (mips_sm100.cu)
 
 struct ScoreEpi {
   int mode;
@@ -24,6 +29,25 @@ struct ScoreEpi {
   float* cscores;
   int32_t* cidx;
   int64_t cap;
+  // GMAX: gmax[row * n_groups + u * (MIPS_TILE_N / group) + g] = max score of `group` consecutive
+  // columns of launch tile u (group in {8, 16, 32, 64}; items >= X count as -inf)
+  float* gmax;
+  int64_t n_groups;
+  int32_t group;
+  // PRIVATE: thread (row, column half) of CTA c owns sub-list s = 2 c + half of row `row`:
+  // sub_cand[(row * n_sub + s) * (sub_cap + MIPS_SUB_SPARE) + slot], slot counter in a register, no
+  // atomics; hits past sub_cap land in the spare tail; sub_counts[row * n_sub + s] = ALL hits
+  MipsCand* sub_cand;
+  int32_t* sub_counts;
+  int32_t n_sub, sub_cap;
+};
+
+// the small-batch plan (mips_small.cu): sizes and workspace offsets; ok == 0: not applicable
+struct MipsSmallPlan {
+  int ok;
+  int64_t stride, n_sample_tiles, n_groups;
+  int group, n_sub, sub_cap;
+  int64_t off_tau, off_gmax, off_counts, off_cand, total;
 };
 
 __device__ __forceinline__ int64_t epi_item_tile(const ScoreEpi& e, int64_t u) {

@@ -47,7 +47,9 @@ struct MipsSmParams {
   ScoreEpi epi;
 };
 
-template <int NQB>
+// SMALL = the small-batch plan's two passes (GMAX, PRIVATE: one query block, NQB = 1); the other
+// instantiations carry STORE and FILTER only, so neither pays for the other's code
+template <int NQB, bool SMALL>
 __global__ void __launch_bounds__(MsCfg<NQB>::threads, 1) mips_scores_sm100_kernel(
     const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmI,
     MipsSmParams p) {
@@ -164,6 +166,90 @@ __global__ void __launch_bounds__(MsCfg<NQB>::threads, 1) mips_scores_sm100_kern
     const int half = ((warp - 2) >> 2) & 1;
     const uint32_t lane_base = (uint32_t) ((warp & 3) * 32) << 16;
     uint32_t tile = 0;
+    if constexpr (SMALL) {
+      // One query block for the whole launch: this thread keeps query row r and the column half
+      // `half` of every tile its CTA scores.  GMAX writes group maxima of the sample tiles;
+      // PRIVATE appends hits to the thread's own sub-list — the slot counter is a register, there
+      // is no atomic and no second pass over the accumulator.
+      const int64_t row = r;
+      const bool row_ok = row < p.B;
+      const bool priv = p.epi.mode == MIPS_EPI_PRIVATE;
+      const float tau = (priv && row_ok) ? p.epi.tau[row] : INFINITY;
+      const int sub = 2 * (int) blockIdx.x + half;
+      const int cap = p.epi.sub_cap;
+      // a sub-list has cap + MIPS_SUB_SPARE entries: the write position is clamped to cap once per 32
+      // columns, not per hit, so a full list takes at most 32 stray writes into its spare tail
+      const uint64_t list = reinterpret_cast<uint64_t>(
+          p.epi.sub_cand + (row * p.epi.n_sub + sub) * (int64_t) (cap + MIPS_SUB_SPARE));
+      const int G = p.epi.group;
+      int slot = 0;
+      for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const int64_t u0 = w * p.chunk;       // n_qb == 1: work item = chunk
+        const int64_t u1 = (u0 + p.chunk < p.n_launch_tiles) ? u0 + p.chunk : p.n_launch_tiles;
+        for (int64_t u = u0; u < u1; ++u, ++tile) {
+          const uint32_t ab = tile % MS_ACC;
+          mbar_wait(bar_acc_full + 8 * ab, (tile / MS_ACC) & 1);
+          tc_fence_after();
+          const int64_t item0 = epi_item_tile(p.epi, u) * MIPS_TILE_N;
+          const bool full = item0 + MIPS_TILE_N <= p.X;
+          const uint32_t acc_addr = tmem + lane_base + ab * MIPS_TILE_N;
+          float* const go = p.epi.gmax + row * p.epi.n_groups + u * (MIPS_TILE_N / G) + half * (64 / G);
+          float m64 = -INFINITY;
+#pragma unroll 1
+          for (int c32 = 2 * half; c32 < 2 * half + 2; ++c32) {
+            uint32_t sv[32];
+            tmem_ld32(acc_addr + c32 * 32, sv);
+            tmem_ld_wait();
+            if (!full) {   // the last item tile only: columns past X never win
+              const int lim = (int) (p.X - (item0 + c32 * 32));
+#pragma unroll
+              for (int c = 0; c < 32; ++c) sv[c] = c < lim ? sv[c] : 0xff800000u;
+            }
+            float m8[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float m = __uint_as_float(sv[8 * k]);
+#pragma unroll
+              for (int c = 1; c < 8; ++c) m = fmaxf(m, __uint_as_float(sv[8 * k + c]));
+              m8[k] = m;
+            }
+            const float m16a = fmaxf(m8[0], m8[1]), m16b = fmaxf(m8[2], m8[3]);
+            const float m32 = fmaxf(m16a, m16b);
+            if (!priv) {
+              if (row_ok) {
+                if (G == 8) *reinterpret_cast<float4*>(go + (c32 & 1) * 4) = make_float4(m8[0], m8[1], m8[2], m8[3]);
+                else if (G == 16) *reinterpret_cast<float2*>(go + (c32 & 1) * 2) = make_float2(m16a, m16b);
+                else if (G == 32) go[c32 & 1] = m32;
+              }
+              m64 = fmaxf(m64, m32);
+            } else if (row_ok && m32 >= tau) {
+              const int32_t ibase = (int32_t) (item0 + c32 * 32);
+              // entry `slot` of this chunk's view of the list: the real one while slot <= cap
+              uint64_t wbase = list + (int64_t) (min(slot, cap) - slot) * (int64_t) sizeof(MipsCand);
+              asm volatile("" : "+l"(wbase));   // kept as one base: a hit is multiply-add, store, increment
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (m8[k] >= tau) {
+#pragma unroll
+                  for (int c = 8 * k; c < 8 * k + 8; ++c) {
+                    if (__uint_as_float(sv[c]) >= tau) {
+                      asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(wbase + (uint64_t) (uint32_t) slot * sizeof(MipsCand)),
+                                   "r"(sv[c]), "r"(ibase + c) : "memory");
+                      ++slot;
+                    }
+                  }
+                }
+              }
+            }
+          }
+          if (!priv && G == 64 && row_ok) go[0] = m64;
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * ab);
+        }
+      }
+      if (priv && row_ok) p.epi.sub_counts[row * p.epi.n_sub + sub] = slot;
+    } else
     for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
       const int64_t chunk = w / p.n_qb, qb = w % p.n_qb;
       const int64_t row = (qb * NQB + qq) * 128 + r;
@@ -293,6 +379,32 @@ bool mips_sm100_supported(const grb_mips_topk_args* a) {
   return true;
 }
 
+// how a launch over n_launch_tiles is cut into work items: ~8 per CTA for balance, at most 128 tiles
+// (8 MiB of items) each; the small-batch plan sizes its private sub-lists from the same grid
+void mips_sm100_work_split(int64_t n_launch_tiles, int64_t n_qb, int64_t* chunk_out, int64_t* n_chunks_out,
+                           unsigned* grid_out) {
+  const int sms = num_sms();
+  int64_t chunk = ceil_div(n_launch_tiles * n_qb, (int64_t) sms * 8);
+  if (chunk < 1) chunk = 1;
+  if (chunk > 128) chunk = 128;
+  const int64_t n_chunks = ceil_div(n_launch_tiles, chunk);
+  const int64_t n_items = n_chunks * n_qb;
+  *chunk_out = chunk;
+  *n_chunks_out = n_chunks;
+  *grid_out = (unsigned) (n_items < sms ? n_items : sms);
+}
+
+template <int NQB, bool SMALL>
+static int launch_ms(const CUtensorMap& tmQ, const CUtensorMap& tmI, const MipsSmParams& p, unsigned grid,
+                     cudaStream_t st) {
+  const size_t smem = MsCfg<NQB>::total + 1024;
+  GRB_CUDA_OK(cudaFuncSetAttribute(mips_scores_sm100_kernel<NQB, SMALL>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  mips_scores_sm100_kernel<NQB, SMALL><<<grid, MsCfg<NQB>::threads, smem, st>>>(tmQ, tmI, p);
+  GRB_LAUNCH_OK();
+  return GRB_OK;
+}
+
 int mips_scores_sm100(const grb_mips_topk_args* a, const ScoreEpi& epi, int64_t n_launch_tiles,
                       cudaStream_t st) {
   CUtensorMap tmQ, tmI;
@@ -304,29 +416,17 @@ int mips_scores_sm100(const grb_mips_topk_args* a, const ScoreEpi& epi, int64_t 
   p.n_launch_tiles = n_launch_tiles;
   const int nqb = a->B > 128 ? 2 : 1;     // query blocks per CTA
   p.n_qb = ceil_div(a->B, 128 * nqb);     // query-block groups
-  const int sms = num_sms();
-  // ~8 work items per CTA for balance; at most 128 tiles (8 MiB of items) per item
-  int64_t chunk = ceil_div(n_launch_tiles * p.n_qb, (int64_t) sms * 8);
-  if (chunk < 1) chunk = 1;
-  if (chunk > 128) chunk = 128;
-  p.chunk = chunk;
-  p.n_chunks = ceil_div(n_launch_tiles, chunk);
+  unsigned grid;
+  mips_sm100_work_split(n_launch_tiles, p.n_qb, &p.chunk, &p.n_chunks, &grid);
   p.epi = epi;
-  const int64_t n_items = p.n_chunks * p.n_qb;
-  const unsigned grid = (unsigned) (n_items < sms ? n_items : sms);
-  if (nqb == 2) {
-    const size_t smem = MsCfg<2>::total + 1024;
-    GRB_CUDA_OK(cudaFuncSetAttribute(mips_scores_sm100_kernel<2>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    mips_scores_sm100_kernel<2><<<grid, MsCfg<2>::threads, smem, st>>>(tmQ, tmI, p);
-  } else {
-    const size_t smem = MsCfg<1>::total + 1024;
-    GRB_CUDA_OK(cudaFuncSetAttribute(mips_scores_sm100_kernel<1>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    mips_scores_sm100_kernel<1><<<grid, MsCfg<1>::threads, smem, st>>>(tmQ, tmI, p);
+  if (epi.mode == MIPS_EPI_GMAX || epi.mode == MIPS_EPI_PRIVATE) {
+    GRB_REQUIRE(nqb == 1 && p.n_qb == 1, GRB_ERR_INVALID_ARG, "mips_topk: small-batch pass with B=%lld",
+                (long long) a->B);
+    GRB_REQUIRE(epi.mode == MIPS_EPI_GMAX || epi.n_sub == 2 * (int) grid, GRB_ERR_INVALID_ARG,
+                "mips_topk: %d sub-lists for a grid of %u", epi.n_sub, grid);
+    return launch_ms<1, true>(tmQ, tmI, p, grid, st);
   }
-  GRB_LAUNCH_OK();
-  return GRB_OK;
+  return nqb == 2 ? launch_ms<2, false>(tmQ, tmI, p, grid, st) : launch_ms<1, false>(tmQ, tmI, p, grid, st);
 }
 
 }  // namespace grb

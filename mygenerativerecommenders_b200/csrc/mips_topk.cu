@@ -18,6 +18,7 @@
 // plugs into the same epilogue contract (ScoreEpi).
 #include "common.cuh"
 #include "mips_epilogue.cuh"
+#include "mips_select.cuh"
 #include <cmath>
 #include <cfloat>
 
@@ -92,15 +93,6 @@ __global__ void __launch_bounds__(SG_THREADS) mips_scores_simt(
 // ---------------------------------------------------------------------------------------------
 // Phase 2: k-th largest of each row (radix select, 4 x 8 bits).  One CTA per row.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t fkey(float f) {
-  const uint32_t u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float fkey_inv(uint32_t k) {
-  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
-}
-
-constexpr int SEL_THREADS = 256;
 
 // Finds the kk-th largest (1-based) key among keys matching (key & mask) == prefix restricted to
 // digit `shift`.  hist must be 256 ints of smem; result broadcast through sh[0..2].
@@ -188,22 +180,6 @@ __global__ void __launch_bounds__(256) filter_dense_kernel(const float* __restri
 // ---------------------------------------------------------------------------------------------
 // Phase 4 / shard merge: exact top-k of a candidate list, sorted, ties -> lowest id.
 // ---------------------------------------------------------------------------------------------
-constexpr int SEL_KMAX = 2048;
-
-constexpr int SEL_INVALID_MAX = 1024;
-
-// f3 (candidate_index.py:125-158, metrics/retrieval.py:40-68): what the reference does with the
-// (B, k') result of the top-k module — drop ids listed in invalid_ids[row], keep the first k, find
-// the target's rank — happens here on the sorted shared-memory list, so that only (B, k) leaves.
-struct SelectFilter {
-  const int64_t* invalid;  // (B, n_invalid), row stride ld; NULL = none
-  int64_t ld;
-  int n_invalid;
-  int k_out;               // entries written per row (k_out <= k; k - k_out <= n_invalid)
-  const int64_t* target;   // (B) or NULL
-  int32_t* ranks;          // (B) or NULL
-};
-
 template <typename IdT>
 __global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(
     const float* __restrict__ cs, const IdT* __restrict__ cid, const int32_t* __restrict__ counts,
@@ -308,72 +284,7 @@ __global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(
       __syncthreads();
     }
   }
-  const int filled = (int) (c < k ? c : k);
-  if (!flt.invalid && !flt.ranks) {
-    for (int r = tid; r < k; r += SEL_THREADS) {
-      float s = -INFINITY;
-      long long id = -1;
-      if (r < filled) {
-        s = fkey_inv(skey[r]);
-        id = sid[r];
-        if (id_map) id = id_map[id];
-      }
-      out_scores[row * k + r] = s;
-      out_ids[row * k + r] = id;
-    }
-    return;
-  }
-  // ---- filtered tail: real ids, invalid flags, stable compaction to k_out, target rank --------
-  __shared__ long long sinv[SEL_INVALID_MAX];
-  __shared__ int wsum[SEL_THREADS / 32];
-  __shared__ int rank_sh;
-  const int ko = flt.k_out;
-  const int ninv = flt.invalid ? flt.n_invalid : 0;
-  for (int i = tid; i < ninv; i += SEL_THREADS) sinv[i] = flt.invalid[row * flt.ld + i];
-  if (tid == 0) rank_sh = ko + 1;
-  for (int r = tid; r < filled; r += SEL_THREADS)
-    if (id_map) sid[r] = id_map[sid[r]];
-  __syncthreads();
-  const long long tgt = (flt.ranks && flt.target) ? flt.target[row] : 0;
-  // each thread owns a contiguous run of the sorted list so that the compaction keeps its order
-  const int per = (filled + SEL_THREADS - 1) / SEL_THREADS;
-  const int r0 = tid * per, r1 = (r0 + per < filled) ? r0 + per : filled;
-  unsigned long long keepmask = 0;   // per <= 2048 / 256 = 8
-  int nkeep = 0;
-  for (int r = r0; r < r1; ++r) {
-    const long long id = sid[r];
-    bool bad = false;
-    for (int j = 0; j < ninv; ++j) bad |= (sinv[j] == id);
-    if (!bad) { keepmask |= 1ull << (r - r0); ++nkeep; }
-  }
-  int incl = nkeep;
-  const int lane = tid & 31, wid = tid >> 5;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane == 31) wsum[wid] = incl;
-  __syncthreads();
-  int base = incl - nkeep;
-  for (int w = 0; w < wid; ++w) base += wsum[w];
-  int total = 0;
-  for (int w = 0; w < SEL_THREADS / 32; ++w) total += wsum[w];
-  for (int r = r0; r < r1; ++r) {
-    if (!((keepmask >> (r - r0)) & 1ull)) continue;
-    if (base < ko) {
-      out_scores[row * ko + base] = fkey_inv(skey[r]);
-      out_ids[row * ko + base] = sid[r];
-      if (flt.ranks && sid[r] == tgt) atomicMin(&rank_sh, base + 1);
-    }
-    ++base;
-  }
-  for (int r = (total < ko ? total : ko) + tid; r < ko; r += SEL_THREADS) {
-    out_scores[row * ko + r] = -INFINITY;
-    out_ids[row * ko + r] = -1;
-  }
-  __syncthreads();
-  if (flt.ranks && tid == 0) flt.ranks[row] = rank_sh;
+  select_write_rows<SEL_THREADS>(row, k, (int) (c < k ? c : k), skey, sid, id_map, out_scores, out_ids, flt);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -387,11 +298,18 @@ constexpr int MIPS_RADIX = 4;
 
 struct MipsPlan {
   int64_t n_tiles, stride, n_sample_tiles, Xs, cap;
+  int64_t auto_cap;     // the capacity the plan picks on its own (cand_cap = 0)
+  MipsSmallPlan small;  // B <= 128, bf16: mips_small.cu; taken unless the caller sized the lists itself
   int levels;  // stride = MIPS_RADIX^levels; refinement phases 1..levels
   int64_t off_tau, off_counts, off_sample, off_cscores, off_cidx, total;
 };
 
 static int64_t align256(int64_t x) { return (x + 255) & ~255ll; }
+
+// implemented in mips_small.cu
+int plan_mips_small(const grb_mips_topk_args* a, int64_t ksel, MipsSmallPlan* S);
+int run_mips_small(const grb_mips_topk_args* a, const MipsSmallPlan& S, int ksel, int32_t overflow_floor,
+                   cudaStream_t st);
 
 // the selection size: the reference over-selects k' = min(k + #invalid ids, X) (candidate_index.py:132)
 static int64_t mips_ksel(const grb_mips_topk_args* a) {
@@ -438,11 +356,9 @@ static int plan_mips(const grb_mips_topk_args* a, MipsPlan* P) {
   P->levels = levels;
   P->stride = stride;
   P->Xs = P->n_sample_tiles * MIPS_TILE_N;
-  int64_t cap = a->cand_cap;
-  if (cap <= 0) cap = ksel * (4 + 2 * (MIPS_RADIX - 1) * levels) + 1024;
-  if (cap > a->X) cap = a->X;
-  if (cap < ksel) cap = ksel;
-  P->cap = cap;
+  auto clamp_cap = [&](int64_t c) { c = c > a->X ? a->X : c; return c < ksel ? ksel : c; };
+  P->auto_cap = clamp_cap(ksel * (4 + 2 * (MIPS_RADIX - 1) * levels) + 1024);
+  P->cap = a->cand_cap > 0 ? clamp_cap(a->cand_cap) : P->auto_cap;
   int64_t o = 0;
   P->off_tau = o;     o = align256(o + a->B * 4);
   P->off_counts = o;  o = align256(o + a->B * 4);
@@ -450,6 +366,13 @@ static int plan_mips(const grb_mips_topk_args* a, MipsPlan* P) {
   P->off_cscores = o; o = align256(o + a->B * P->cap * 4);
   P->off_cidx = o;    o = align256(o + a->B * P->cap * 4);
   P->total = o;
+  // The small-batch plan runs when the capacity is the automatic one; an explicit capacity is the host
+  // wrapper's exact re-run after an overflow (status[0] + 1024 > auto_cap) and takes the phased plan.
+  // Either way the workspace holds both layouts, so the choice never depends on who sized it.
+  int rc = plan_mips_small(a, ksel, &P->small);
+  if (rc != GRB_OK) return rc;
+  if (P->small.ok && (P->cap != P->auto_cap || 4 * P->auto_cap > a->X)) P->small.ok = 0;
+  if (P->small.ok && P->small.total > P->total) P->total = P->small.total;
   return GRB_OK;
 }
 
@@ -511,6 +434,7 @@ int grb_mips_topk(const grb_mips_topk_args* a, grb_stream_t stream) {
   float* sample = reinterpret_cast<float*>(ws + P.off_sample);
   float* cscores = reinterpret_cast<float*>(ws + P.off_cscores);
   int32_t* cidx = reinterpret_cast<int32_t*>(ws + P.off_cidx);
+  if (P.small.ok) return run_mips_small(a, P.small, (int) mips_ksel(a), (int32_t) P.auto_cap, st);
   GRB_CUDA_OK(cudaMemsetAsync(counts, 0, a->B * 4, st));
 
   ScoreEpi epi{};

@@ -1016,7 +1016,7 @@ class MipsTopkCall:
         self._run, self._outs, self._flag, self._done = run, outs, flag, done
 
     def result(self):
-        for _attempt in range(3):
+        for _attempt in range(4):
             self._done.synchronize()
             overflow = int(self._flag[0])
             if overflow == 0:

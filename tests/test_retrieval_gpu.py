@@ -135,6 +135,76 @@ def test_invalid_ids_filtered_inside_the_selection(B, X, D, k, n_inv, dtype):
     assert torch.equal(oi, i) and torch.equal(os_.float(), s)
 
 
+def _launches(fn):
+    from mygenerativerecommenders_b200 import _lib
+    n0 = _lib.launch_count()
+    out = fn()
+    return out, _lib.launch_count() - n0
+
+
+@pytest.mark.parametrize("B,X,D,k,n_inv", [
+    (128, 700_000, 64, 200, 61),       # C3 (BASELINE.json configs[2]) at full size: k' = 261
+    (37, 150_001, 128, 100, 0),        # ragged last item tile, rows 37..127 of the query block unused
+    (128, 1_000_000, 256, 200, 0),     # C4's item width, group maxima per half tile (G = 64)
+    (1, 200_000, 64, 10, 5),
+    (96, 333_333, 192, 411, 211),      # C1/C2's k' = 200 + 211
+])
+def test_small_batch_plan_vs_oracle(B, X, D, k, n_inv):
+    """One query block against a corpus that streams from HBM once (mips_small.cu: group-maxima sample,
+    private sub-lists, register-resident select): exact ids against the oracle, in four launches."""
+    gen = torch.Generator().manual_seed(B + X + k)
+    items = torch.nn.functional.normalize(torch.randn(X, D, generator=gen), dim=-1).to(torch.bfloat16)
+    q = torch.nn.functional.normalize(torch.randn(B, D, generator=gen), dim=-1).to(torch.bfloat16)
+    ids = torch.randperm(2 * X, generator=gen)[:X] + 1
+    invalid = None
+    if n_inv:
+        ri_full, _ = O.candidate_index_topk(q, items, ids, k + n_inv)
+        invalid = torch.zeros(B, n_inv, dtype=torch.int64)
+        for b in range(B):       # half of each list from the row's own best ids, so that the filter bites
+            pick = torch.randperm(ri_full.shape[1], generator=gen)[: n_inv // 2]
+            invalid[b, : pick.numel()] = ri_full[b, pick]
+    ri, rs = O.candidate_index_topk(q, items, ids, k, invalid_ids=invalid)
+    target = ri[:, min(k - 1, 3)].clone()
+    target[::2] = 2 * X + 9                          # absent -> rank k + 1
+    qd, itd, idd = q.to(DEV), items.to(DEV), ids.to(DEV)
+    invd = invalid.to(DEV) if invalid is not None else None
+    GF.mips_topk(qd, itd, idd, k, invalid_ids=invd, target_ids=target.to(DEV))          # workspace warm-up
+    (s, i, ranks), n = _launches(lambda: GF.mips_topk(qd, itd, idd, k, invalid_ids=invd,
+                                                      target_ids=target.to(DEV)))
+    assert n == 4, f"{n} launches: the small-batch plan was not taken"
+    _check_topk(s, i, rs, ri, 2e-5)
+    _, rank_idx = torch.max(torch.cat([i.cpu(), target.unsqueeze(1)], dim=1) == target.unsqueeze(1), dim=1)
+    assert torch.equal(ranks.cpu().long(), rank_idx + 1)
+    if invalid is not None:
+        assert not (i.cpu().unsqueeze(2) == invalid.unsqueeze(1)).any()
+
+
+def test_small_batch_plan_ties_and_overflow_fall_back_exactly():
+    """Equal scores straddling the cut resolve to the lowest index inside the register-resident select;
+    an item order (or a tie class) that overflows the private sub-lists sets the status word and the
+    wrapper's re-run — the phased plan with an explicit capacity — still returns the exact answer."""
+    gen = torch.Generator().manual_seed(5)
+    X, D, B, k = 120_000, 64, 16, 150
+    base = torch.nn.functional.normalize(torch.randn(6_000, D, generator=gen), dim=-1).to(torch.bfloat16)
+    items = base.repeat(20, 1)                       # every item 20 times: k = 150 cuts through a tie class
+    q = base[:B].clone()
+    (s, i), n = _launches(lambda: GF.mips_topk(q.to(DEV), items.to(DEV), None, k))
+    rs, ri = O.mips_topk(q, items, None, k)
+    assert torch.equal(i.cpu(), ri) and torch.allclose(s.cpu(), rs, atol=2e-5)
+    # scores increase with the index: the strided sample under-estimates tau, every sub-list of the last
+    # CTAs overflows
+    items = torch.zeros(X, D)
+    items[:, 0] = torch.linspace(-1, 1, X)
+    items = items.to(torch.bfloat16)
+    q = torch.zeros(4, D)
+    q[:, 0] = torch.tensor([1.0, 0.5, -1.0, 2.0])
+    q = q.to(torch.bfloat16)
+    (s, i), n = _launches(lambda: GF.mips_topk(q.to(DEV), items.to(DEV), None, 50))
+    assert n > 4, "expected the overflow re-run"
+    rs, ri = O.mips_topk(q, items, None, 50)
+    assert torch.equal(i.cpu(), ri)
+
+
 def test_async_call_defers_the_overflow_check_to_result():
     X, D, B, k = 60_000, 8, 4, 50
     items = torch.zeros(X, D)
