@@ -12,6 +12,7 @@ enum { MIPS_EPI_STORE = 0, MIPS_EPI_FILTER = 1, MIPS_EPI_GMAX = 2, MIPS_EPI_PRIV
 // candidate of a private sub-list: (score bits, item index)
 struct __align__(8) MipsCand { uint32_t score; int32_t item; };
 constexpr int MIPS_SUB_SPARE = 32;   // spare entries behind a sub-list's capacity (mips_sm100.cu)
+constexpr int MIPS_SUB_PER_CTA = 4;  // sub-lists per (CTA, row): one per 32-column quarter of a tile
 
 struct ScoreEpi {
   int mode;
@@ -30,11 +31,11 @@ struct ScoreEpi {
   int32_t* cidx;
   int64_t cap;
   // GMAX: gmax[row * n_groups + u * (MIPS_TILE_N / group) + g] = max score of `group` consecutive
-  // columns of launch tile u (group in {8, 16, 32, 64}; items >= X count as -inf)
+  // columns of launch tile u (group in {8, 16, 32}; items >= X count as -inf)
   float* gmax;
   int64_t n_groups;
   int32_t group;
-  // PRIVATE: thread (row, column half) of CTA c owns sub-list s = 2 c + half of row `row`:
+  // PRIVATE: thread (row, column quarter q) of CTA c owns sub-list s = 4 c + q of row `row`:
   // sub_cand[(row * n_sub + s) * (sub_cap + MIPS_SUB_SPARE) + slot], slot counter in a register, no
   // atomics; hits past sub_cap land in the spare tail; sub_counts[row * n_sub + s] = ALL hits
   MipsCand* sub_cand;

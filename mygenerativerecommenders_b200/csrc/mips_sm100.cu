@@ -27,8 +27,8 @@ constexpr int MS_SLAB = 128 * 64 * 2;   // 16 KiB: 128 rows x 64 bf16
 template <int NQB> struct MsCfg {
   // TMA warp, MMA warp, and per query block TWO epilogue warpgroups (64 of the 128 score columns
   // each): with one, a tile's epilogue (TMEM loads, reject tree, the atomic's round trip) takes
-  // longer than its 1024 MMA cycles as soon as candidates are dense (small shards, early phases)
-  static constexpr int threads = 64 + 256 * NQB;
+  // longer than its 1024 MMA cycles as soon as candidates are dense (small shards, early phases);
+  // thread counts: ms_threads<NQB, SMALL>() below
   static constexpr int stages = NQB == 1 ? 8 : 6;
   static constexpr int acc = 4 / NQB;                   // accumulator sets (NQB x 128 columns each)
   static constexpr int q = 0;                           // NQB x 4 slabs
@@ -49,8 +49,14 @@ struct MipsSmParams {
 
 // SMALL = the small-batch plan's two passes (GMAX, PRIVATE: one query block, NQB = 1); the other
 // instantiations carry STORE and FILTER only, so neither pays for the other's code
+// epilogue warps: 8 per query block (two column halves x four TMEM lane quadrants); the small-batch
+// passes run 16 (four 32-column quarters): their epilogue is a chain of dependent steps per tile
+// (TMEM load, max tree, compare walk) that two warps per scheduler cannot overlap
+template <int NQB, bool SMALL> constexpr int ms_epi_warps() { return SMALL ? 16 : 8 * NQB; }
+template <int NQB, bool SMALL> constexpr int ms_threads() { return 64 + 32 * ms_epi_warps<NQB, SMALL>(); }
+
 template <int NQB, bool SMALL>
-__global__ void __launch_bounds__(MsCfg<NQB>::threads, 1) mips_scores_sm100_kernel(
+__global__ void __launch_bounds__(ms_threads<NQB, SMALL>(), 1) mips_scores_sm100_kernel(
     const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmI,
     MipsSmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -69,7 +75,7 @@ __global__ void __launch_bounds__(MsCfg<NQB>::threads, 1) mips_scores_sm100_kern
 
   if (tid == 0) {
     for (int s = 0; s < MS_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    for (int s = 0; s < MS_ACC; ++s) { mbar_init(bar_acc_full + 8 * s, 1); mbar_init(bar_acc_empty + 8 * s, 8 * NQB); }
+    for (int s = 0; s < MS_ACC; ++s) { mbar_init(bar_acc_full + 8 * s, 1); mbar_init(bar_acc_empty + 8 * s, ms_epi_warps<NQB, SMALL>()); }
     mbar_init(bar_q_full, 1);
     mbar_init(bar_q_empty, 1);
     fence_barrier_init();
@@ -167,18 +173,19 @@ __global__ void __launch_bounds__(MsCfg<NQB>::threads, 1) mips_scores_sm100_kern
     const uint32_t lane_base = (uint32_t) ((warp & 3) * 32) << 16;
     uint32_t tile = 0;
     if constexpr (SMALL) {
-      // One query block for the whole launch: this thread keeps query row r and the column half
-      // `half` of every tile its CTA scores.  GMAX writes group maxima of the sample tiles;
+      // One query block for the whole launch: this thread keeps query row r and the 32-column
+      // quarter `cq` of every tile its CTA scores.  GMAX writes group maxima of the sample tiles;
       // PRIVATE appends hits to the thread's own sub-list — the slot counter is a register, there
       // is no atomic and no second pass over the accumulator.
+      const int cq = (warp - 2) >> 2;
       const int64_t row = r;
       const bool row_ok = row < p.B;
       const bool priv = p.epi.mode == MIPS_EPI_PRIVATE;
       const float tau = (priv && row_ok) ? p.epi.tau[row] : INFINITY;
-      const int sub = 2 * (int) blockIdx.x + half;
+      const int sub = MIPS_SUB_PER_CTA * (int) blockIdx.x + cq;
       const int cap = p.epi.sub_cap;
-      // a sub-list has cap + MIPS_SUB_SPARE entries: the write position is clamped to cap once per 32
-      // columns, not per hit, so a full list takes at most 32 stray writes into its spare tail
+      // a sub-list has cap + MIPS_SUB_SPARE entries: the write position is clamped to cap once per
+      // tile, not per hit, so a full list takes at most 32 stray writes into its spare tail
       const uint64_t list = reinterpret_cast<uint64_t>(
           p.epi.sub_cand + (row * p.epi.n_sub + sub) * (int64_t) (cap + MIPS_SUB_SPARE));
       const int G = p.epi.group;
@@ -190,62 +197,58 @@ __global__ void __launch_bounds__(MsCfg<NQB>::threads, 1) mips_scores_sm100_kern
           const uint32_t ab = tile % MS_ACC;
           mbar_wait(bar_acc_full + 8 * ab, (tile / MS_ACC) & 1);
           tc_fence_after();
-          const int64_t item0 = epi_item_tile(p.epi, u) * MIPS_TILE_N;
-          const bool full = item0 + MIPS_TILE_N <= p.X;
-          const uint32_t acc_addr = tmem + lane_base + ab * MIPS_TILE_N;
-          float* const go = p.epi.gmax + row * p.epi.n_groups + u * (MIPS_TILE_N / G) + half * (64 / G);
-          float m64 = -INFINITY;
-#pragma unroll 1
-          for (int c32 = 2 * half; c32 < 2 * half + 2; ++c32) {
-            uint32_t sv[32];
-            tmem_ld32(acc_addr + c32 * 32, sv);
-            tmem_ld_wait();
-            if (!full) {   // the last item tile only: columns past X never win
-              const int lim = (int) (p.X - (item0 + c32 * 32));
+          const int64_t item0 = epi_item_tile(p.epi, u) * MIPS_TILE_N + cq * 32;
+          uint32_t sv[32];
+          tmem_ld32(tmem + lane_base + ab * MIPS_TILE_N + cq * 32, sv);
+          tmem_ld_wait();
+          // the accumulator is in registers: the MMA warp may refill it while this warp walks
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * ab);
+          if (item0 + 32 > p.X) {   // the last item tile only: columns past X never win
+            const int lim = (int) (p.X - item0);
 #pragma unroll
-              for (int c = 0; c < 32; ++c) sv[c] = c < lim ? sv[c] : 0xff800000u;
+            for (int c = 0; c < 32; ++c) sv[c] = c < lim ? sv[c] : 0xff800000u;
+          }
+          float m4[8], m8[4];
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            m4[k] = fmaxf(fmaxf(__uint_as_float(sv[4 * k]), __uint_as_float(sv[4 * k + 1])),
+                          fmaxf(__uint_as_float(sv[4 * k + 2]), __uint_as_float(sv[4 * k + 3])));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) m8[k] = fmaxf(m4[2 * k], m4[2 * k + 1]);
+          const float m16a = fmaxf(m8[0], m8[1]), m16b = fmaxf(m8[2], m8[3]);
+          const float m32 = fmaxf(m16a, m16b);
+          if (!priv) {
+            if (row_ok) {
+              float* const go = p.epi.gmax + row * p.epi.n_groups + u * (MIPS_TILE_N / G) + cq * (32 / G);
+              if (G == 8) *reinterpret_cast<float4*>(go) = make_float4(m8[0], m8[1], m8[2], m8[3]);
+              else if (G == 16) *reinterpret_cast<float2*>(go) = make_float2(m16a, m16b);
+              else go[0] = m32;
             }
-            float m8[4];
+          } else if (__any_sync(0xffffffffu, m32 >= tau)) {   // tau = +inf on rows past B
+            // the two reject levels (32 columns, 4 columns) are warp votes: real branches.  Left to
+            // itself the compiler predicates the whole walk and issues every column's store sequence
+            // on every tile (ncu: 790 instructions per warp and tile); a walked column costs 8
+            // instructions, and with ~0.4 hits per (row, tile) two thirds of the groups are skipped
+            const int32_t ibase = (int32_t) item0;
+            // entry `slot` of this tile's view of the list: the real one while slot <= cap
+            uint64_t wbase = list + (int64_t) (min(slot, cap) - slot) * (int64_t) sizeof(MipsCand);
+            asm volatile("" : "+l"(wbase));   // kept as one base: a hit is multiply-add, store, increment
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              float m = __uint_as_float(sv[8 * k]);
+            for (int k = 0; k < 8; ++k) {
+              if (__any_sync(0xffffffffu, m4[k] >= tau)) {
 #pragma unroll
-              for (int c = 1; c < 8; ++c) m = fmaxf(m, __uint_as_float(sv[8 * k + c]));
-              m8[k] = m;
-            }
-            const float m16a = fmaxf(m8[0], m8[1]), m16b = fmaxf(m8[2], m8[3]);
-            const float m32 = fmaxf(m16a, m16b);
-            if (!priv) {
-              if (row_ok) {
-                if (G == 8) *reinterpret_cast<float4*>(go + (c32 & 1) * 4) = make_float4(m8[0], m8[1], m8[2], m8[3]);
-                else if (G == 16) *reinterpret_cast<float2*>(go + (c32 & 1) * 2) = make_float2(m16a, m16b);
-                else if (G == 32) go[c32 & 1] = m32;
-              }
-              m64 = fmaxf(m64, m32);
-            } else if (row_ok && m32 >= tau) {
-              const int32_t ibase = (int32_t) (item0 + c32 * 32);
-              // entry `slot` of this chunk's view of the list: the real one while slot <= cap
-              uint64_t wbase = list + (int64_t) (min(slot, cap) - slot) * (int64_t) sizeof(MipsCand);
-              asm volatile("" : "+l"(wbase));   // kept as one base: a hit is multiply-add, store, increment
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (m8[k] >= tau) {
-#pragma unroll
-                  for (int c = 8 * k; c < 8 * k + 8; ++c) {
-                    if (__uint_as_float(sv[c]) >= tau) {
-                      asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(wbase + (uint64_t) (uint32_t) slot * sizeof(MipsCand)),
-                                   "r"(sv[c]), "r"(ibase + c) : "memory");
-                      ++slot;
-                    }
+                for (int c = 4 * k; c < 4 * k + 4; ++c) {
+                  if (__uint_as_float(sv[c]) >= tau) {
+                    asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(wbase + (uint64_t) (uint32_t) slot * sizeof(MipsCand)),
+                                 "r"(sv[c]), "r"(ibase + c) : "memory");
+                    ++slot;
                   }
                 }
               }
             }
           }
-          if (!priv && G == 64 && row_ok) go[0] = m64;
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * ab);
         }
       }
       if (priv && row_ok) p.epi.sub_counts[row * p.epi.n_sub + sub] = slot;
@@ -400,7 +403,7 @@ static int launch_ms(const CUtensorMap& tmQ, const CUtensorMap& tmI, const MipsS
   const size_t smem = MsCfg<NQB>::total + 1024;
   GRB_CUDA_OK(cudaFuncSetAttribute(mips_scores_sm100_kernel<NQB, SMALL>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  mips_scores_sm100_kernel<NQB, SMALL><<<grid, MsCfg<NQB>::threads, smem, st>>>(tmQ, tmI, p);
+  mips_scores_sm100_kernel<NQB, SMALL><<<grid, ms_threads<NQB, SMALL>(), smem, st>>>(tmQ, tmI, p);
   GRB_LAUNCH_OK();
   return GRB_OK;
 }
@@ -422,7 +425,7 @@ int mips_scores_sm100(const grb_mips_topk_args* a, const ScoreEpi& epi, int64_t 
   if (epi.mode == MIPS_EPI_GMAX || epi.mode == MIPS_EPI_PRIVATE) {
     GRB_REQUIRE(nqb == 1 && p.n_qb == 1, GRB_ERR_INVALID_ARG, "mips_topk: small-batch pass with B=%lld",
                 (long long) a->B);
-    GRB_REQUIRE(epi.mode == MIPS_EPI_GMAX || epi.n_sub == 2 * (int) grid, GRB_ERR_INVALID_ARG,
+    GRB_REQUIRE(epi.mode == MIPS_EPI_GMAX || epi.n_sub == MIPS_SUB_PER_CTA * (int) grid, GRB_ERR_INVALID_ARG,
                 "mips_topk: %d sub-lists for a grid of %u", epi.n_sub, grid);
     return launch_ms<1, true>(tmQ, tmI, p, grid, st);
   }
