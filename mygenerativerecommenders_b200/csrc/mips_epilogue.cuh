@@ -51,8 +51,13 @@ struct MipsSmallPlan {
   int64_t off_tau, off_gmax, off_counts, off_cand, total;
 };
 
+// (launch tiles number < 2^24, since X < 2^31: the quotient is a 32-bit division — or none at all
+//  for a plain stride — instead of the ~100-instruction 64-bit one, which every epilogue warp paid
+//  per tile: ncu of the one-query-block pass, 246 instructions per warp and tile)
 __device__ __forceinline__ int64_t epi_item_tile(const ScoreEpi& e, int64_t u) {
-  return e.tile_stride * ((int64_t) e.grp * (u / e.per) + (u % e.per) + e.first);
+  const uint32_t uu = (uint32_t) u, per = (uint32_t) e.per;
+  const uint32_t q = per == 1u ? uu : uu / per;
+  return e.tile_stride * (int64_t) ((uint32_t) e.grp * q + (uu - q * per) + (uint32_t) e.first);
 }
 
 __device__ __forceinline__ void append_candidate(const ScoreEpi& e, int64_t row, float s,
