@@ -712,6 +712,12 @@ def retrieval_hbm_regime(dev, items, item_ids, pk) -> dict:
             tot += e0.elapsed_time(e1)
         return tot / iters
 
+    def launches_of(fn):
+        from mygenerativerecommenders_b200 import _lib
+        n0 = _lib.launch_count()
+        fn()
+        return _lib.launch_count() - n0
+
     g = torch.Generator(device=dev).manual_seed(7)
     X, D, k = items.shape[0], items.shape[1], 200
     q = torch.nn.functional.normalize(torch.randn(128, D, device=dev, generator=g), dim=-1).to(torch.bfloat16)
@@ -724,7 +730,10 @@ def retrieval_hbm_regime(dev, items, item_ids, pk) -> dict:
                           "graph_ms": ms_g, "graph_hbm_frac": byts / ms_g / 1e6 / pk["hbm_gbs"],
                           "queries_per_s": 128 / (ms / 1e3), "gbs": byts / ms / 1e6,
                           "hbm_frac": byts / ms / 1e6 / pk["hbm_gbs"],
-                          "tensor_frac": 2.0 * 128 * X * D / ms / 1e9 / pk["bf16_tflops"]}
+                          "tensor_frac": 2.0 * 128 * X * D / ms / 1e9 / pk["bf16_tflops"],
+                          "launches_per_call": launches_of(lambda: GF.mips_topk(q, items, item_ids, k)),
+                          "plan": "4 launches = the one-query-block plan of csrc/mips_small.cu (group-maxima sample, "
+                                  "threshold, private sub-lists, select); 9+ = the phased plan"}
     X3, D3, n_inv = 700_000, 64, 61
     items3 = torch.nn.functional.normalize(torch.randn(X3, D3, device=dev, generator=g), dim=-1).to(torch.bfloat16)
     ids3 = torch.arange(1, X3 + 1, device=dev, dtype=torch.int64)
@@ -743,6 +752,7 @@ def retrieval_hbm_regime(dev, items, item_ids, pk) -> dict:
                           "between the launches)",
                  "queries_per_s": 128 / (ms3 / 1e3), "gbs": byts3 / ms3 / 1e6,
                  "hbm_frac": byts3 / ms3 / 1e6 / pk["hbm_gbs"], "hbm_peak": pk["hbm_gbs"],
+                 "launches_per_call": launches_of(lambda: GF.mips_topk(q3, items3, ids3, k, invalid_ids=inv3)),
                  "includes": "host time of the call (workspace lookup, launches, overflow-flag read)"}
     return out
 

@@ -330,6 +330,14 @@ int grb_l2norm_bwd(const float* y, int64_t ldy, const float* dy, int64_t lddy, c
  *     count if any row overflowed `cand_cap`, else left 0; the host wrapper re-runs with a larger
  *     workspace in that case.  sample_stride: 0 = auto, else 4^L is the largest power of 4 <= it.
  *
+ *     One query block (B <= 128, GRB_BF16, a corpus of >= ~500 tiles, cand_cap left automatic) takes
+ *     the one-query-block plan instead (csrc/mips_small.cu), four launches, the corpus streamed 1 + 1/s
+ *     times (s = 8 or 16):  group maxima of every s-th tile -> tau[b] = k'-th largest group maximum
+ *     (each the score of a distinct item) -> all tiles, hits >= tau[b] appended to per-thread private
+ *     sub-lists (no atomics) -> exact select.  Same outputs, same status word; a capacity passed
+ *     explicitly (cand_cap != the automatic one: the wrapper's re-run after an overflow) selects the
+ *     phased plan.  grb_mips_topk_workspace_bytes covers both layouts.
+ *
  *     queries (B, D) row stride ldq; items (X, D) row stride ldi (the reference keeps the
  *     transposed *view* of this contiguous table, candidate_index.py:29).
  *     dtype GRB_BF16: tcgen05 path (D % 64 == 0, D <= 256);  GRB_F32: CUDA-core path (any D).

@@ -95,16 +95,31 @@ __global__ void __launch_bounds__(SG_THREADS) mips_scores_simt(
 // ---------------------------------------------------------------------------------------------
 
 // Finds the kk-th largest (1-based) key among keys matching (key & mask) == prefix restricted to
-// digit `shift`.  hist must be 256 ints of smem; result broadcast through sh[0..2].
+// digit `shift`.  hist must be 256 ints of smem; result broadcast through sh[0..2] = (digit, rank
+// inside the digit's bin, size of the bin).  Warp 0 walks the bins from 255 down, 8 per lane.
 __device__ __forceinline__ void pick_digit_desc(int* hist, int* sh, int kk) {
-  if (threadIdx.x == 0) {
-    int cum = 0, digit = 0, rem = kk, cnt = 0;
-    for (int b = 255; b >= 0; --b) {
-      const int h = hist[b];
-      if (cum + h >= kk) { digit = b; rem = kk - cum; cnt = h; break; }
-      cum += h;
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int h[8], s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { h[j] = hist[255 - 8 * lane - j]; s += h[j]; }
+    int incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
     }
-    sh[0] = digit; sh[1] = rem; sh[2] = cnt;
+    const int excl = incl - s;
+    if (excl < kk && kk <= incl) {   // the lane whose bins hold the kk-th largest
+      int cum = excl;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (cum < kk && cum + h[j] >= kk) { sh[0] = 255 - 8 * lane - j; sh[1] = kk - cum; sh[2] = h[j]; }
+        cum += h[j];
+      }
+    } else if (lane == 31 && incl < kk) {   // fewer than kk keys: callers rule this out
+      sh[0] = 0; sh[1] = kk; sh[2] = 0;
+    }
   }
   __syncthreads();
 }
