@@ -303,6 +303,32 @@ int grb_ln_gate_bwd(const void* x, int64_t ldx, const void* gate, int64_t ldg, c
                     void* dgate, int64_t lddg, int64_t rows, int64_t W, int dtype,
                     grb_stream_t stream);
 
+/* The same pair with the two elementwise neighbours of the STU layer folded in (struct form):
+ *   p_drop > 0 (forward and backward): dropout on the output, hstu.py:404-408 dropout(u * norm(a)) in front
+ *     of the output projection.  The mask is drawn inside the kernels (Philox4x32-10 keyed by the device
+ *     int64 `seed` the caller draws per step, counter = (row, 8-element chunk, `salt` of the call site)) and
+ *     regenerated in the backward: no mask tensor, no dropout / masked-scale passes.  bf16 rows of 256 /
+ *     512 / 1024 elements only (GRB_ERR_UNSUPPORTED otherwise: apply the dropout outside).
+ *   res (backward): dx = LayerNorm backward + res, the gradient reaching x through the residual branch
+ *     (hstu.py:413 new_outputs = o(...) + x) — the add autograd would launch on its own.
+ * In the backward call `y` / `ldy` carry dy. */
+typedef struct grb_ln_gate_args {
+  const void* x; int64_t ldx;
+  const void* gate; int64_t ldg;         /* NULL: plain LayerNorm */
+  void* y; int64_t ldy;                  /* forward: output; backward: dy (read only) */
+  float* mean; float* rstd;              /* (rows) saved by the forward, read by the backward */
+  int64_t rows, W;
+  float eps;
+  int32_t dtype;
+  float p_drop; int32_t _pad0;
+  const int64_t* seed; int64_t salt;
+  void* dx; int64_t lddx;                /* backward outputs */
+  void* dgate; int64_t lddg;
+  const void* res; int64_t ldres;        /* backward: added to dx; NULL = none */
+} grb_ln_gate_args;
+int grb_ln_gate_fwd_ex(const grb_ln_gate_args* a, grb_stream_t stream);
+int grb_ln_gate_bwd_ex(const grb_ln_gate_args* a, grb_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * b4  negatives_samples/negative_sampler.py:31-37 (_maybe_l2_norm) and postprocessors.py:47-55:
  *     y = x / clamp(||x||_2, min=eps) per row, fp32.  inv (rows) is saved for backward:

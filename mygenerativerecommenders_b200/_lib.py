@@ -96,6 +96,22 @@ class MipsTopkArgs(C.Structure):
     ]
 
 
+class LnGateArgs(C.Structure):
+    _fields_ = [
+        ("x", c_vp), ("ldx", c_i64),
+        ("gate", c_vp), ("ldg", c_i64),
+        ("y", c_vp), ("ldy", c_i64),
+        ("mean", c_vp), ("rstd", c_vp),
+        ("rows", c_i64), ("W", c_i64),
+        ("eps", C.c_float), ("dtype", c_i32),
+        ("p_drop", C.c_float), ("_pad0", c_i32),
+        ("seed", c_vp), ("salt", c_i64),
+        ("dx", c_vp), ("lddx", c_i64),
+        ("dgate", c_vp), ("lddg", c_i64),
+        ("res", c_vp), ("ldres", c_i64),
+    ]
+
+
 class SslArgs(C.Structure):
     _fields_ = [
         ("n_rows", c_i64),
@@ -135,6 +151,8 @@ SYMBOLS = {
     "grb_ln_gate_bwd": (
         C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64,
                   c_i64, c_i64, C.c_int, c_vp]),
+    "grb_ln_gate_fwd_ex": (C.c_int, [C.POINTER(LnGateArgs), c_vp]),
+    "grb_ln_gate_bwd_ex": (C.c_int, [C.POINTER(LnGateArgs), c_vp]),
     "grb_mips_topk_workspace_bytes": (c_i64, [C.POINTER(MipsTopkArgs)]),
     "grb_mips_topk": (C.c_int, [C.POINTER(MipsTopkArgs), c_vp]),
     "grb_topk_select": (

@@ -80,6 +80,20 @@ __device__ __forceinline__ float dsilu_f32(float x) {
   return s * (1.0f + x * (1.0f - s));
 }
 
+// Philox4x32-10 (Salmon et al., the generator behind curand / torch's CUDA RNG): counter (c0, c1, 0, 0)
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
+  uint32_t c2 = 0u, c3 = 0u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
 // number of table entries <= d  (table ascending, n entries) — the reference's bucketization_fn
 // (hstu.py:579-581) tabulated on the host; result in [0, n].
 __device__ __forceinline__ int bucket_of(const int64_t* __restrict__ thr, int n, int64_t d) {

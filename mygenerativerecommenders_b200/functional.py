@@ -328,10 +328,28 @@ def hstu_attention_decode(q: torch.Tensor, k_cache: torch.Tensor, v: torch.Tenso
 # --------------------------------------------------------------------------------------------
 # y = gate * LayerNorm(x)   (hstu.py:258-264, :300, :402)
 # --------------------------------------------------------------------------------------------
+def _ln_args(x, gate, mean, rstd, eps, p_drop, seed, salt):
+    a = _lib.LnGateArgs()
+    a.x, a.ldx = x.data_ptr(), _ld(x)
+    if gate is not None:
+        a.gate, a.ldg = gate.data_ptr(), _ld(gate)
+    a.mean, a.rstd = mean.data_ptr(), rstd.data_ptr()
+    a.rows, a.W = x.shape
+    a.eps, a.dtype = float(eps), _lib.dtype_code(x.dtype)
+    if p_drop > 0.0:
+        a.p_drop, a.seed, a.salt = float(p_drop), seed.data_ptr(), int(salt)
+    return a
+
+
 class _LnGate(torch.autograd.Function):
+    """y = dropout(gate * LN(x)); with ``skip`` a second output aliases x (the residual operand of the
+    layer, hstu.py:413), so that both gradients of x meet in ONE backward call and leave it as one tensor:
+    dx = LN backward + d skip, summed inside the kernel instead of by autograd's own add."""
+
     @staticmethod
-    def forward(ctx, x, gate, eps):
-        _lib.require_cuda(x, gate)
+    def forward(ctx, x, gate, eps, p_drop, seed, salt, skip):
+        _lib.require_cuda(x, gate, seed)
+        ctx.set_materialize_grads(False)     # an unused output's gradient arrives as None, not as zeros
         x = _rows_contiguous(x)
         if gate is not None:
             gate = _rows_contiguous(gate)
@@ -341,25 +359,41 @@ class _LnGate(torch.autograd.Function):
         y = torch.empty((rows, W), dtype=x.dtype, device=x.device)
         mean = torch.empty(rows, dtype=torch.float32, device=x.device)
         rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
-        _lib.check(_lib.lib().grb_ln_gate_fwd(
-            x.data_ptr(), _ld(x), _lib.ptr(gate), _ld(gate) if gate is not None else 0,
-            y.data_ptr(), W, mean.data_ptr(), rstd.data_ptr(), rows, W, float(eps),
-            _lib.dtype_code(x.dtype), _lib.stream_ptr(x.device)))
-        ctx.save_for_backward(x, gate, mean, rstd)
+        a = _ln_args(x, gate, mean, rstd, eps, p_drop, seed, salt)
+        a.y, a.ldy = y.data_ptr(), W
+        _lib.check(_lib.lib().grb_ln_gate_fwd_ex(C.byref(a), _lib.stream_ptr(x.device)))
+        ctx.save_for_backward(x, gate, mean, rstd, seed)
+        ctx.cfg = (float(eps), float(p_drop), int(salt))
+        if skip:
+            return y, x.view_as(x)
         return y
 
     @staticmethod
-    def backward(ctx, dy):
-        x, gate, mean, rstd = ctx.saved_tensors
-        dy = _rows_contiguous(dy)
+    def backward(ctx, dy, dskip=None):
+        x, gate, mean, rstd, seed = ctx.saved_tensors
+        eps, p_drop, salt = ctx.cfg
         rows, W = x.shape
+        if dy is None:                       # only the residual branch carried a gradient
+            return dskip, None, None, None, None, None, None
+        dy = _rows_contiguous(dy)
         dx = torch.empty((rows, W), dtype=x.dtype, device=x.device)
         dgate = torch.empty((rows, W), dtype=x.dtype, device=x.device) if gate is not None else None
-        _lib.check(_lib.lib().grb_ln_gate_bwd(
-            x.data_ptr(), _ld(x), _lib.ptr(gate), _ld(gate) if gate is not None else 0,
-            dy.data_ptr(), _ld(dy), mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(), W,
-            _lib.ptr(dgate), W, rows, W, _lib.dtype_code(x.dtype), _lib.stream_ptr(x.device)))
-        return dx, dgate, None
+        a = _ln_args(x, gate, mean, rstd, eps, p_drop, seed, salt)
+        a.y, a.ldy = dy.data_ptr(), _ld(dy)
+        a.dx, a.lddx = dx.data_ptr(), W
+        if dgate is not None:
+            a.dgate, a.lddg = dgate.data_ptr(), W
+        if dskip is not None:
+            dskip = _rows_contiguous(dskip if dskip.dtype == x.dtype else dskip.to(x.dtype))
+            a.res, a.ldres = dskip.data_ptr(), _ld(dskip)
+        _lib.check(_lib.lib().grb_ln_gate_bwd_ex(C.byref(a), _lib.stream_ptr(x.device)))
+        return dx, dgate, None, None, None, None, None
+
+
+def ln_dropout_fusable(x: torch.Tensor) -> bool:
+    """Whether ``layer_norm_gate`` can draw the dropout mask inside its kernels for rows like x's."""
+    return (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 2 and x.shape[1] in (256, 512, 1024)
+            and x.stride(1) == 1 and x.stride(0) % 8 == 0 and x.data_ptr() % 16 == 0)
 
 
 class _SiluSplit(torch.autograd.Function):
@@ -878,9 +912,22 @@ def jagged_input(table: torch.Tensor, pos: torch.Tensor, ids: torch.Tensor, offs
     return _JaggedInput.apply(table, pos, ids, offsets, int(rows), float(scale), float(p_drop), seed, out_dtype)
 
 
-def layer_norm_gate(x: torch.Tensor, gate: Optional[torch.Tensor], eps: float) -> torch.Tensor:
-    """gate * F.layer_norm(x, [W], eps=eps) without affine; gate=None gives the plain norm."""
-    return _LnGate.apply(x, gate, eps)
+def layer_norm_gate(x: torch.Tensor, gate: Optional[torch.Tensor], eps: float, p_drop: float = 0.0,
+                    seed: Optional[torch.Tensor] = None, salt: int = 0) -> torch.Tensor:
+    """gate * F.layer_norm(x, [W], eps=eps) without affine; gate=None gives the plain norm.
+    p_drop > 0: dropout on the result (hstu.py:404-408), drawn inside the kernel from the device int64
+    ``seed`` (one per step) and ``salt`` (one per call site) when ``ln_dropout_fusable(x)``, by F.dropout
+    otherwise."""
+    if p_drop > 0.0 and not (seed is not None and ln_dropout_fusable(x)
+                             and (gate is None or ln_dropout_fusable(gate))):
+        return torch.nn.functional.dropout(_LnGate.apply(x, gate, eps, 0.0, None, 0, False), p=p_drop, training=True)
+    return _LnGate.apply(x, gate, eps, float(p_drop), seed if p_drop > 0.0 else None, salt, False)
+
+
+def layer_norm_skip(x: torch.Tensor, eps: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(F.layer_norm(x), x): the second output is x itself, routed through the same autograd node, for the
+    layer's residual add (hstu.py:300 and :413) — see ``_LnGate``."""
+    return _LnGate.apply(x, None, eps, 0.0, None, 0, True)
 
 
 # --------------------------------------------------------------------------------------------

@@ -186,7 +186,8 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
                 cache: Optional[HSTUCacheState] = None,
                 return_cache_states: bool = False,
                 bucket_cache: Optional[torch.Tensor] = None,
-                rows_padded: bool = False):
+                rows_padded: bool = False,
+                dropout_seed: Optional[torch.Tensor] = None):
         """x: (sum_i N_i, D); x_offsets: (B+1); all_timestamps: (B, N) int64 or None;
         invalid_attn_mask: (N, N) — only its size is read: the kernel applies the causal
         lower-triangular mask that HSTU registers (hstu.py:595-607,667)."""
@@ -212,7 +213,16 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
         n: int = invalid_attn_mask.size(-1)
         H, dv, dqk = self._num_heads, self._linear_dim, self._attention_dim
 
-        normed_x = self._norm_input(x)
+        # (F.layer_norm(x), x): the residual operand of :413 leaves the same autograd node as the norm, so
+        # that x receives ONE gradient (norm backward + residual, summed in the kernel)
+        normed_x, x = GF.layer_norm_skip(x, self._eps)
+        # training-mode dropout in front of the output projection (:404-408) is drawn inside the
+        # u * norm(a) kernel from a per-step device seed; HSTUJagged hands one seed to all its layers
+        drop = None
+        if self.training and self._dropout_ratio > 0.0:
+            if dropout_seed is None:
+                dropout_seed = torch.randint(0, 2 ** 62, (1,), device=x.device, dtype=torch.int64)
+            drop = (dropout_seed, getattr(self, "_layer_index", 0))
         sizes = [dv * H, dv * H, dqk * H, dqk * H]
         if self._linear_activation == "silu":
             # one tcgen05 GEMM with the SiLU in its epilogue (bf16 rows); cuBLAS + silu kernel otherwise
@@ -237,7 +247,7 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
             # jagged kernels + cuBLAS + ATen, O(B H N^2) memory: functional, not a hot path.
             attn_output = self._composite_attention(q, k, v, x_offsets, all_timestamps, n)
             return self._finish_layer(x, u, v, q, k, attn_output, x_offsets, n, False, None, None,
-                                      return_cache_states)
+                                      return_cache_states, drop)
         if bias is not None and not isinstance(bias, RelativeBucketedTimeAndPositionBasedBias):
             raise NotImplementedError(
                 "the incremental path supports RelativeBucketedTimeAndPositionBasedBias only")
@@ -266,7 +276,7 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
         return self._finish_layer(x, u, v, q, k, attn_output, x_offsets, n, incremental,
                                   rows if incremental else None,
                                   (cached_outputs, padded_q, padded_k) if incremental else None,
-                                  return_cache_states)
+                                  return_cache_states, drop)
 
     def _composite_attention(self, q, k, v, x_offsets, all_timestamps, n: int) -> torch.Tensor:
         """hstu.py:179-204 as written: pad, (B, H, N, N) scores, + bias, SiLU / N, causal mask, P V, un-pad."""
@@ -286,18 +296,19 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
         return out
 
     def _finish_layer(self, x, u, v, q, k, attn_output, x_offsets, n, incremental, rows, cached,
-                      return_cache_states):
+                      return_cache_states, drop=None):
         if incremental:
             cached_outputs, padded_q, padded_k = cached
         if self._concat_ua:
             a = self._norm_attn_output(attn_output)
             o_input = torch.cat([u, a, u * a], dim=-1)
+            o_input = F.dropout(o_input, p=self._dropout_ratio, training=self.training)
+        elif drop is not None:
+            o_input = GF.layer_norm_gate(attn_output, u, self._eps, self._dropout_ratio, *drop)
         else:
             o_input = GF.layer_norm_gate(attn_output, u, self._eps)
 
-        new_outputs = GF.output_projection(
-            F.dropout(o_input, p=self._dropout_ratio, training=self.training),
-            self._o.weight, self._o.bias, x)
+        new_outputs = GF.output_projection(o_input, self._o.weight, self._o.bias, x)
 
         cache_state = None
         if incremental:
@@ -371,12 +382,16 @@ class HSTUJagged(torch.nn.Module):
                 bucket_cache = GF.hstu_bucket_cache(
                     x_offsets, all_timestamps if has_bias else None,
                     first._rel_attn_bias._bucket_thresholds if has_bias else None, n_pad, masked=short)
+        dropout_seed = None
+        if self.training and any(l._dropout_ratio > 0.0 for l in self._attention_layers):
+            dropout_seed = torch.randint(0, 2 ** 62, (1,), device=x.device, dtype=torch.int64)
         for i, layer in enumerate(self._attention_layers):
+            layer._layer_index = i
             x, cs = layer(x=x, x_offsets=x_offsets, all_timestamps=all_timestamps,
                           invalid_attn_mask=invalid_attn_mask, delta_x_offsets=delta_x_offsets,
                           cache=cache[i] if cache is not None else None,
                           return_cache_states=return_cache_states, bucket_cache=bucket_cache,
-                          rows_padded=rows_padded)
+                          rows_padded=rows_padded, dropout_seed=dropout_seed)
             if return_cache_states:
                 cache_states.append(cs)
         if x.dtype != in_dtype:

@@ -35,6 +35,9 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.HstuAttnArgs) == 4 * 8 + 6 * 4 + 3 * 8 + 3 * 8 + 5 * 8 + 2 * 8 + 2 * 8 + 3 * 8 + 3 * 8 + 3 * 8 + 8 + 8 + 16 + 16
     assert ctypes.sizeof(_lib.MipsTopkArgs) == 3 * 8 + 2 * 4 + 4 * 8 + 8 + 2 * 8 + 2 * 8 + 2 * 8 + 8 + (8 + 8 + 8) + 8 + 8
     assert ctypes.sizeof(_lib.SslArgs) == 8 + 6 * 4 + 2 * 4 + 8 * 8 + 4 * 8 + 2 * 8 + 5 * 8
+    # grb_ln_gate_args: 3 x (ptr, ld) + 2 ptr + rows, W + (eps, dtype) + (p_drop, pad) + seed, salt + 3 x (ptr, ld)
+    assert ctypes.sizeof(_lib.LnGateArgs) == 6 * 8 + 2 * 8 + 2 * 8 + 8 + 8 + 2 * 8 + 6 * 8
+    assert _lib.LnGateArgs.seed.offset == 96 and _lib.LnGateArgs.dx.offset == 112
 
 
 def test_invalid_arguments_are_reported_without_a_gpu():

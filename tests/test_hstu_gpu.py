@@ -143,6 +143,69 @@ def test_ln_gate_vs_torch(W, dtype):
     _close(y2, torch.nn.functional.layer_norm(xr.detach(), [W], eps=1e-6), *t, what="ln y")
 
 
+@pytest.mark.parametrize("W", [256, 512, 1024])
+@pytest.mark.parametrize("gated", [True, False])
+def test_ln_gate_fused_dropout_mask_is_consistent_forward_and_backward(W, gated):
+    """hstu.py:404-408 dropout(u * norm(a)) drawn inside the ln_gate kernels: the kept fraction and the scale
+    are those of F.dropout, the same seed gives the same mask, another salt / seed another one, and the
+    backward applies exactly the mask the forward drew (checked against torch autograd with the mask read
+    off the forward's zeros)."""
+    gen = torch.Generator().manual_seed(W)
+    rows, p = 301, 0.2
+    x = (torch.randn(rows, W, generator=gen) * 2 + 0.5).to(DEV).bfloat16().requires_grad_(True)
+    u = (torch.randn(rows, W, generator=gen) + 3.0).to(DEV).bfloat16().requires_grad_(gated)   # u != 0
+    dy = torch.randn(rows, W, generator=gen).to(DEV).bfloat16()
+    seed = torch.tensor([123456789012345], dtype=torch.int64, device=DEV)
+    gate = u if gated else None
+    y0 = GF.layer_norm_gate(x, gate, 1e-6)
+    y = GF.layer_norm_gate(x, gate, 1e-6, p, seed, 3)
+    y.backward(dy)
+    keep = y != 0
+    frac = keep.float().mean().item()
+    assert abs(frac - (1 - p)) < 4 * (p * (1 - p) / keep.numel()) ** 0.5 + 2e-3, frac
+    # kept entries are the undropped ones scaled by 1 / (1 - p) (bf16 rounding of both sides)
+    _close(y[keep].float(), y0[keep].float() / (1 - p), 2e-2, 1e-2, what="kept values")
+    assert not keep.all(dim=0).any() and keep.any(dim=1).all()      # no dead column pattern, no dead row
+    assert torch.equal(y, GF.layer_norm_gate(x, gate, 1e-6, p, seed, 3))
+    assert not torch.equal(y != 0, GF.layer_norm_gate(x, gate, 1e-6, p, seed, 4) != 0)
+    assert not torch.equal(y != 0, GF.layer_norm_gate(x, gate, 1e-6, p, seed + 1, 3) != 0)
+    # reference gradients with the kernel's own mask
+    xr = x.detach().double().requires_grad_(True)
+    ur = u.detach().double().requires_grad_(gated)
+    yr = torch.nn.functional.layer_norm(xr, [W], eps=1e-6) * (ur if gated else 1.0) * keep.double() / (1 - p)
+    yr.backward(dy.double())
+    _close(x.grad, xr.grad, 2e-2, 2e-2, what="dropout dx")
+    if gated:
+        _close(u.grad, ur.grad, 2e-2, 2e-2, what="dropout dgate")
+
+
+@pytest.mark.parametrize("W,dtype", [(256, torch.bfloat16), (512, torch.bfloat16), (50, torch.float32), (96, torch.bfloat16)])
+def test_layer_norm_skip_sums_both_gradients_of_x_in_the_kernel(W, dtype):
+    """(LN(x), x) through one autograd node: dx = LN backward + the residual branch's gradient."""
+    gen = torch.Generator().manual_seed(W + 1)
+    x = torch.randn(77, W, generator=gen).to(DEV).to(dtype).requires_grad_(True)
+    g1 = torch.randn(77, W, generator=gen).to(DEV).to(dtype)
+    g2 = torch.randn(77, W, generator=gen).to(DEV).to(dtype)
+    normed, skip = GF.layer_norm_skip(x, 1e-6)
+    assert skip.data_ptr() == x.data_ptr() and torch.equal(skip, x)
+    (normed * g1 + skip * g2).sum().backward()
+    xr = x.detach().double().requires_grad_(True)
+    (torch.nn.functional.layer_norm(xr, [W], eps=1e-6) * g1.double() + xr * g2.double()).sum().backward()
+    t = (1e-4, None) if dtype == torch.float32 else (2e-2, 2e-2)
+    _close(x.grad, xr.grad, *t, what="ln_skip dx")
+    # one branch only
+    x2 = x.detach().clone().requires_grad_(True)
+    n2, s2 = GF.layer_norm_skip(x2, 1e-6)
+    (s2 * g2).sum().backward()
+    _close(x2.grad, g2, 1e-6, None, what="skip-only dx")
+    x3 = x.detach().clone().requires_grad_(True)
+    n3, s3 = GF.layer_norm_skip(x3, 1e-6)
+    (n3 * g1).sum().backward()
+    x4 = x.detach().clone().requires_grad_(True)
+    (GF.layer_norm_gate(x4, None, 1e-6) * g1).sum().backward()
+    assert torch.equal(x3.grad, x4.grad)
+
+
 def _build(c, compute_dtype=None, normalization="rel_bias", linear_activation="silu", **kw):
     enc = hstu.HSTU(max_sequence_len=c["max_seq"], max_output_len=c["out_len"],
                     embedding_dim=c["D"], item_embedding_dim=c["D"], num_blocks=c["blocks"],
