@@ -504,6 +504,12 @@ int grb_adamw_step(int n, float* const* p, const float* const* g, float* const* 
                    double weight_decay, double bias_correction1, double bias_correction2,
                    grb_stream_t stream);
 
+/* dst[i] (bf16, numel[i]) = src[i] (fp32) for a HOST list of n device tensors, one launch per 64 tensors:
+ * the compute-dtype copies of the fp32 master weights of all STU layers of a forward pass (the per-layer
+ * casts of hstu.py:300-305 / :404-413 under autocast, made once). */
+int grb_cast_f32_bf16_many(int n, const float* const* src, void* const* dst, const int64_t* numel,
+                           grb_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Cross-rank barrier on the stream, over peer memory: every rank adds 1 to word `slot` of each
  *     rank's signal array (system-scope release after its earlier stores / reds), then waits until

@@ -150,3 +150,78 @@ extern "C" int grb_adamw_step(int n, float* const* p, const float* const* g, flo
   }
   return GRB_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------------
+// fp32 -> bf16 copies of a list of tensors in one launch: the compute-dtype shadows of the fp32 master
+// weights of all STU layers (hstu.py:300-305, :404-413 run under bf16 autocast in the reference; here the
+// masters stay fp32 and every projection used to cast its own weight, one launch each, every step).
+// ---------------------------------------------------------------------------------------------------
+namespace grb {
+namespace {
+
+struct CastList {
+  const float* src[ADAMW_MAX_TENSORS];
+  __nv_bfloat16* dst[ADAMW_MAX_TENSORS];
+  int64_t numel[ADAMW_MAX_TENSORS];
+  int32_t first_block[ADAMW_MAX_TENSORS + 1];
+  int32_t n;
+};
+
+__global__ void __launch_bounds__(ADAMW_THREADS) cast_many_kernel(const __grid_constant__ CastList L) {
+  int lo = 0, hi = L.n;
+  const int b = (int) blockIdx.x;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (L.first_block[mid] <= b) lo = mid; else hi = mid;
+  }
+  const int64_t base = (int64_t) (b - L.first_block[lo]) * ADAMW_CHUNK;
+  const int64_t left = L.numel[lo] - base;
+  const float* __restrict__ src = L.src[lo] + base;
+  __nv_bfloat16* __restrict__ dst = L.dst[lo] + base;
+  const bool vec = ((((uintptr_t) src) & 15u) | (((uintptr_t) dst) & 7u)) == 0;
+#pragma unroll
+  for (int j = 0; j < ADAMW_CHUNK / (4 * ADAMW_THREADS); ++j) {
+    const int64_t e = ((int64_t) j * ADAMW_THREADS + threadIdx.x) * 4;
+    if (vec && e + 4 <= left) {
+      const float4 v = *reinterpret_cast<const float4*>(src + e);
+      const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), c = __floats2bfloat162_rn(v.z, v.w);
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&a);
+      o.y = *reinterpret_cast<const uint32_t*>(&c);
+      *reinterpret_cast<uint2*>(dst + e) = o;
+    } else {
+      for (int64_t i = e; i < e + 4 && i < left; ++i) dst[i] = __float2bfloat16_rn(src[i]);
+    }
+  }
+}
+
+}  // namespace
+}  // namespace grb
+
+extern "C" int grb_cast_f32_bf16_many(int n, const float* const* src, void* const* dst, const int64_t* numel,
+                                      grb_stream_t stream) {
+  using namespace grb;
+  GRB_REQUIRE(n >= 0 && (n == 0 || (src && dst && numel)), GRB_ERR_INVALID_ARG, "cast_many: bad arguments");
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  for (int t0 = 0; t0 < n; t0 += ADAMW_MAX_TENSORS) {
+    CastList L{};
+    int64_t blocks = 0;
+    const int cnt = n - t0 < ADAMW_MAX_TENSORS ? n - t0 : ADAMW_MAX_TENSORS;
+    for (int i = 0; i < cnt; ++i) {
+      GRB_REQUIRE(src[t0 + i] && dst[t0 + i] && numel[t0 + i] >= 0, GRB_ERR_INVALID_ARG, "cast_many: tensor %d", t0 + i);
+      L.src[i] = src[t0 + i];
+      L.dst[i] = reinterpret_cast<__nv_bfloat16*>(dst[t0 + i]);
+      L.numel[i] = numel[t0 + i];
+      L.first_block[i] = (int32_t) blocks;
+      blocks += ceil_div(numel[t0 + i], ADAMW_CHUNK);
+      GRB_REQUIRE(blocks < (1ll << 31), GRB_ERR_UNSUPPORTED, "cast_many: too many elements");
+    }
+    L.first_block[cnt] = (int32_t) blocks;
+    L.n = cnt;
+    if (blocks == 0) continue;
+    cast_many_kernel<<<(unsigned) blocks, ADAMW_THREADS, 0, st>>>(L);
+    GRB_LAUNCH_OK();
+  }
+  return GRB_OK;
+}

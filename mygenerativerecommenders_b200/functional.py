@@ -7,6 +7,7 @@ library surface as Python exceptions (ValueError / NotImplementedError / Runtime
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 from typing import Optional, Tuple
 
@@ -594,17 +595,72 @@ def _silu_split_bwd(x_pre: torch.Tensor, grads, sizes) -> torch.Tensor:
     return dx
 
 
+def cast_many_bf16(tensors) -> list:
+    """bf16 copies of a list of fp32 CUDA tensors, one launch (``grb_cast_f32_bf16_many``), carved out of
+    one buffer (every copy 16-byte aligned).  Not differentiable: the copies are operands, the gradients
+    go to the fp32 masters."""
+    tensors = [t.detach() for t in tensors]
+    if not tensors:
+        return []
+    _lib.require_cuda(*tensors)
+    for t in tensors:
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError("cast_many_bf16: contiguous float32 tensors only")
+    offs, total = [], 0
+    for t in tensors:
+        offs.append(total)
+        total += (t.numel() + 7) // 8 * 8
+    flat = torch.empty(total, dtype=torch.bfloat16, device=tensors[0].device)
+    outs = [flat[o:o + t.numel()].view(t.shape) for o, t in zip(offs, tensors)]
+    n = len(tensors)
+    src = (C.c_void_p * n)(*[t.data_ptr() for t in tensors])
+    dst = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+    num = (C.c_int64 * n)(*[t.numel() for t in tensors])
+    _lib.check(_lib.lib().grb_cast_f32_bf16_many(n, src, dst, num, _lib.stream_ptr(flat.device)))
+    return outs
+
+
+def zeros_many(shapes, device) -> list:
+    """fp32 zero tensors of the given shapes carved out of ONE zero-filled buffer (one fill launch; every
+    tensor 256-byte aligned): the split-K weight-gradient accumulators of all layers of a step."""
+    offs, total = [], 0
+    for sh in shapes:
+        offs.append(total)
+        total += (math.prod(sh) + 63) // 64 * 64
+    flat = torch.zeros(total, dtype=torch.float32, device=device)
+    return [flat[o:o + math.prod(sh)].view(sh) for o, sh in zip(offs, shapes)]
+
+
+def _usable_shadow(w: torch.Tensor, w_cast, dtype) -> bool:
+    return (w_cast is not None and w_cast.dtype == dtype and w_cast.shape == w.shape and w_cast.is_contiguous()
+            and w_cast.device == w.device and w_cast.data_ptr() % 16 == 0)
+
+
+def _take_buf(ctx, name: str, shape, device) -> torch.Tensor:
+    """A pre-zeroed accumulator handed in by the caller (used once: a second backward through the same
+    node gets a fresh one), else a new zero tensor."""
+    buf = getattr(ctx, name, None)
+    setattr(ctx, name, None)
+    if buf is not None and tuple(buf.shape) == tuple(shape) and buf.dtype == torch.float32 and buf.device == device:
+        return buf
+    return torch.zeros(shape, dtype=torch.float32, device=device)
+
+
 class _UvqkProj(torch.autograd.Function):
     """split(SiLU(xn @ W_uvqk)) (hstu.py:302-320).  Forward: one GEMM whose epilogue writes the
     pre-activation and its SiLU.  Backward: SiLU' over the four consumers' gradients (one pass), the
     input gradient and the fp32 weight gradient (split-K over the token dimension) on the same kernel."""
 
     @staticmethod
-    def forward(ctx, xn, w, *sizes):
+    def forward(ctx, xn, w, w_cast, dw_buf, *sizes):
         xn = _al16(xn)
         T, D = xn.shape
         Ntot = w.shape[1]
-        wc = (w if w.dtype == xn.dtype else w.to(xn.dtype)).contiguous()       # (K = D, N = Ntot) row-major
+        if _usable_shadow(w, w_cast, xn.dtype):
+            wc = w_cast
+        else:
+            wc = (w if w.dtype == xn.dtype else w.to(xn.dtype)).contiguous()   # (K = D, N = Ntot) row-major
+        ctx.dw_buf = dw_buf
         pre = torch.empty((T, Ntot), dtype=xn.dtype, device=xn.device)
         act = torch.empty((T, Ntot), dtype=xn.dtype, device=xn.device)
         with _lib.timed("proj_gemm_uvqk_fwd"):
@@ -626,20 +682,22 @@ class _UvqkProj(torch.autograd.Function):
             with _lib.timed("proj_gemm_uvqk_dgrad"):       # dx (T, Ntot) @ W^T: W is (N = D, K = Ntot) row-major
                 _proj_gemm(dx, wc, T, D, Ntot, False, False, _lib.GEMM_EPI_PLAIN, d_xn)
         if ctx.needs_input_grad[1]:
-            dw32 = torch.zeros((D, Ntot), dtype=torch.float32, device=xn.device)
+            dw32 = _take_buf(ctx, "dw_buf", (D, Ntot), xn.device)
             with _lib.timed("proj_gemm_uvqk_wgrad"):       # xn^T (D, T) @ dx (T, Ntot), both read in place
                 _proj_gemm(xn, dx, D, Ntot, T, True, True, _lib.GEMM_EPI_F32_ADD, dw32)
             dw = dw32 if ctx.w_dtype == torch.float32 else dw32.to(ctx.w_dtype)
-        return (d_xn, dw) + (None,) * len(ctx.sizes)
+        return (d_xn, dw, None, None) + (None,) * len(ctx.sizes)
 
 
-def uvqk_projection(xn: torch.Tensor, w: torch.Tensor, sizes) -> Tuple[torch.Tensor, ...]:
+def uvqk_projection(xn: torch.Tensor, w: torch.Tensor, sizes, w_cast: Optional[torch.Tensor] = None,
+                    dw_buf: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, ...]:
     """``torch.split(F.silu(xn @ w), sizes, dim=1)`` (hstu.py:302-320), w (D, sum sizes) possibly an
-    fp32 master of a bf16 xn."""
+    fp32 master of a bf16 xn.  ``w_cast``: w already in xn's dtype (``cast_many_bf16``); ``dw_buf``: a
+    zero-filled fp32 tensor of w's shape the weight gradient is accumulated into (``zeros_many``)."""
     _lib.require_cuda(xn, w)
     sizes = [int(v) for v in sizes]
     if _gemm_ok(xn, xn.shape[1], w.shape[1]) and xn.shape[1] % 256 == 0 and all(v % 8 == 0 for v in sizes):
-        return _UvqkProj.apply(xn, w, *sizes)
+        return _UvqkProj.apply(xn, w, w_cast, dw_buf, *sizes)
     return silu_split(master_linear(xn, w, None, w_in_out=True), sizes)
 
 
@@ -649,11 +707,15 @@ class _OutProj(torch.autograd.Function):
     same kernel, bias gradient by a column-sum kernel; the residual's gradient is the incoming one."""
 
     @staticmethod
-    def forward(ctx, o_in, w, b, res):
+    def forward(ctx, o_in, w, b, res, w_cast, dw_buf, db_buf):
         o_in, res = _al16(o_in), _al16(res)
         T, Din = o_in.shape
         Dout = w.shape[0]
-        wc = (w if w.dtype == o_in.dtype else w.to(o_in.dtype)).contiguous()   # (N = Dout, K = Din) row-major
+        if _usable_shadow(w, w_cast, o_in.dtype):
+            wc = w_cast
+        else:
+            wc = (w if w.dtype == o_in.dtype else w.to(o_in.dtype)).contiguous()   # (N = Dout, K = Din) row-major
+        ctx.dw_buf, ctx.db_buf = dw_buf, db_buf
         bf = None if b is None else (b if b.dtype == torch.float32 else b.float()).contiguous()
         out = torch.empty((T, Dout), dtype=o_in.dtype, device=o_in.device)
         with _lib.timed("proj_gemm_o_fwd"):
@@ -675,25 +737,27 @@ class _OutProj(torch.autograd.Function):
             with _lib.timed("proj_gemm_o_dgrad"):          # g (T, Dout) @ W: W is (K = Dout, N = Din) row-major
                 _proj_gemm(g, wc, T, Din, Dout, False, True, _lib.GEMM_EPI_PLAIN, d_in)
         if ctx.needs_input_grad[1]:
-            dw32 = torch.zeros((Dout, Din), dtype=torch.float32, device=g.device)
+            dw32 = _take_buf(ctx, "dw_buf", (Dout, Din), g.device)
             with _lib.timed("proj_gemm_o_wgrad"):          # g^T (Dout, T) @ o_in (T, Din)
                 _proj_gemm(g, o_in, Dout, Din, T, True, True, _lib.GEMM_EPI_F32_ADD, dw32)
             dw = dw32 if ctx.w_dtype == torch.float32 else dw32.to(ctx.w_dtype)
         if ctx.b_dtype is not None and ctx.needs_input_grad[2]:
-            db32 = torch.zeros(Dout, dtype=torch.float32, device=g.device)
+            db32 = _take_buf(ctx, "db_buf", (Dout,), g.device)
             _lib.check(_lib.lib().grb_colsum_bf16(g.data_ptr(), g.stride(0), T, Dout, db32.data_ptr(),
                                                   _lib.stream_ptr(g.device)))
             db = db32 if ctx.b_dtype == torch.float32 else db32.to(ctx.b_dtype)
-        return d_in, dw, db, (g if ctx.needs_input_grad[3] else None)
+        return d_in, dw, db, (g if ctx.needs_input_grad[3] else None), None, None, None
 
 
 def output_projection(o_in: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor],
-                      residual: torch.Tensor) -> torch.Tensor:
-    """``F.linear(o_in, w, b) + residual`` (hstu.py:404-413), w / b possibly fp32 masters."""
+                      residual: torch.Tensor, w_cast: Optional[torch.Tensor] = None,
+                      dw_buf: Optional[torch.Tensor] = None, db_buf: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``F.linear(o_in, w, b) + residual`` (hstu.py:404-413), w / b possibly fp32 masters; ``w_cast`` /
+    ``dw_buf`` / ``db_buf`` as in ``uvqk_projection``."""
     _lib.require_cuda(o_in, w, b, residual)
     if (_gemm_ok(o_in, o_in.shape[1], w.shape[0]) and w.shape[0] % 256 == 0 and w.shape[1] % 256 == 0
             and residual.dtype == o_in.dtype and residual.shape == (o_in.shape[0], w.shape[0])):
-        return _OutProj.apply(o_in, w, b, residual)
+        return _OutProj.apply(o_in, w, b, residual, w_cast, dw_buf, db_buf)
     return master_linear(o_in, w, b) + residual
 
 

@@ -187,7 +187,8 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
                 return_cache_states: bool = False,
                 bucket_cache: Optional[torch.Tensor] = None,
                 rows_padded: bool = False,
-                dropout_seed: Optional[torch.Tensor] = None):
+                dropout_seed: Optional[torch.Tensor] = None,
+                aux: Optional[dict] = None):
         """x: (sum_i N_i, D); x_offsets: (B+1); all_timestamps: (B, N) int64 or None;
         invalid_attn_mask: (N, N) — only its size is read: the kernel applies the causal
         lower-triangular mask that HSTU registers (hstu.py:595-607,667)."""
@@ -226,7 +227,10 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
         sizes = [dv * H, dv * H, dqk * H, dqk * H]
         if self._linear_activation == "silu":
             # one tcgen05 GEMM with the SiLU in its epilogue (bf16 rows); cuBLAS + silu kernel otherwise
-            u, v, q, k = GF.uvqk_projection(normed_x, self._uvqk, sizes)
+            # aux (from HSTUJagged): this layer's weights already in the compute dtype and zero-filled
+            # accumulators for its weight gradients, each made by ONE launch for all layers
+            aux = aux or {}
+            u, v, q, k = GF.uvqk_projection(normed_x, self._uvqk, sizes, aux.get("w_uvqk"), aux.get("dw_uvqk"))
         elif self._linear_activation == "none":
             mm = GF.master_linear(normed_x, self._uvqk, None, w_in_out=True)
             u, v, q, k = torch.split(mm, sizes, dim=1)
@@ -247,7 +251,7 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
             # jagged kernels + cuBLAS + ATen, O(B H N^2) memory: functional, not a hot path.
             attn_output = self._composite_attention(q, k, v, x_offsets, all_timestamps, n)
             return self._finish_layer(x, u, v, q, k, attn_output, x_offsets, n, False, None, None,
-                                      return_cache_states, drop)
+                                      return_cache_states, drop, aux)
         if bias is not None and not isinstance(bias, RelativeBucketedTimeAndPositionBasedBias):
             raise NotImplementedError(
                 "the incremental path supports RelativeBucketedTimeAndPositionBasedBias only")
@@ -276,7 +280,7 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
         return self._finish_layer(x, u, v, q, k, attn_output, x_offsets, n, incremental,
                                   rows if incremental else None,
                                   (cached_outputs, padded_q, padded_k) if incremental else None,
-                                  return_cache_states, drop)
+                                  return_cache_states, drop, aux)
 
     def _composite_attention(self, q, k, v, x_offsets, all_timestamps, n: int) -> torch.Tensor:
         """hstu.py:179-204 as written: pad, (B, H, N, N) scores, + bias, SiLU / N, causal mask, P V, un-pad."""
@@ -296,7 +300,7 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
         return out
 
     def _finish_layer(self, x, u, v, q, k, attn_output, x_offsets, n, incremental, rows, cached,
-                      return_cache_states, drop=None):
+                      return_cache_states, drop=None, aux=None):
         if incremental:
             cached_outputs, padded_q, padded_k = cached
         if self._concat_ua:
@@ -308,7 +312,9 @@ class SequentialTransductionUnitJagged(torch.nn.Module):
         else:
             o_input = GF.layer_norm_gate(attn_output, u, self._eps)
 
-        new_outputs = GF.output_projection(o_input, self._o.weight, self._o.bias, x)
+        aux = aux or {}
+        new_outputs = GF.output_projection(o_input, self._o.weight, self._o.bias, x, aux.get("w_o"),
+                                           aux.get("dw_o"), aux.get("db_o"))
 
         cache_state = None
         if incremental:
@@ -356,6 +362,32 @@ class HSTUJagged(torch.nn.Module):
         self._graph_lazy = True
         object.__setattr__(self, "_graphs", {})
 
+    def _layer_aux(self, x: torch.Tensor) -> Optional[List[dict]]:
+        """Per-layer operands every layer used to make for itself, one launch each: the bf16 copies of the
+        fp32 master weights (uvqk, _o.weight) -> ONE multi-tensor cast; the zero-filled fp32 accumulators of
+        the split-K weight / bias gradients -> ONE zero fill (only when a backward can follow)."""
+        layers = list(self._attention_layers)
+        if not (layers and x.is_cuda and x.dtype == torch.bfloat16):
+            return None
+        if not all(l._linear_activation == "silu" and l._uvqk.dtype == torch.float32 and l._uvqk.is_contiguous()
+                   and l._o.weight.dtype == torch.float32 and l._o.weight.is_contiguous() for l in layers):
+            return None
+        L = len(layers)
+        with torch.no_grad():
+            sh = GF.cast_many_bf16([l._uvqk for l in layers] + [l._o.weight for l in layers])
+        aux = [{"w_uvqk": sh[i], "w_o": sh[L + i]} for i in range(L)]
+        if torch.is_grad_enabled() and any(l._uvqk.requires_grad or l._o.weight.requires_grad for l in layers):
+            shapes = []
+            for l in layers:
+                shapes += [tuple(l._uvqk.shape), tuple(l._o.weight.shape), (l._o.weight.shape[0],)]
+            with torch.no_grad():
+                z = GF.zeros_many(shapes, x.device)
+            for i in range(L):
+                aux[i].update(dw_uvqk=z[3 * i], dw_o=z[3 * i + 1])
+                if layers[i]._o.bias is not None and layers[i]._o.bias.dtype == torch.float32:
+                    aux[i]["db_o"] = z[3 * i + 2]
+        return aux
+
     def jagged_forward(self, x: torch.Tensor, x_offsets: torch.Tensor,
                        all_timestamps: Optional[torch.Tensor], invalid_attn_mask: torch.Tensor,
                        delta_x_offsets=None, cache=None, return_cache_states: bool = False,
@@ -385,13 +417,15 @@ class HSTUJagged(torch.nn.Module):
         dropout_seed = None
         if self.training and any(l._dropout_ratio > 0.0 for l in self._attention_layers):
             dropout_seed = torch.randint(0, 2 ** 62, (1,), device=x.device, dtype=torch.int64)
+        layer_aux = self._layer_aux(x) if delta_x_offsets is None else None
         for i, layer in enumerate(self._attention_layers):
             layer._layer_index = i
             x, cs = layer(x=x, x_offsets=x_offsets, all_timestamps=all_timestamps,
                           invalid_attn_mask=invalid_attn_mask, delta_x_offsets=delta_x_offsets,
                           cache=cache[i] if cache is not None else None,
                           return_cache_states=return_cache_states, bucket_cache=bucket_cache,
-                          rows_padded=rows_padded, dropout_seed=dropout_seed)
+                          rows_padded=rows_padded, dropout_seed=dropout_seed,
+                          aux=layer_aux[i] if layer_aux is not None else None)
             if return_cache_states:
                 cache_states.append(cs)
         if x.dtype != in_dtype:

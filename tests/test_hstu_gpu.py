@@ -246,6 +246,51 @@ def test_hstu_module_bf16_vs_reference_golden(golden):
         _close(p.grad, c["grads"][k], 2e-2, 2e-2, what=f"bf16 grad {k}")
 
 
+def test_shared_weight_copies_and_gradient_buffers_change_nothing(monkeypatch):
+    """HSTUJagged._layer_aux (one multi-tensor cast of all master weights, one zero fill for all weight-gradient
+    accumulators) against every layer casting / zero-filling for itself: same outputs (bitwise: same operands),
+    same gradients (split-K reds: summation order differs, 1e-5)."""
+    torch.manual_seed(4)
+    B, max_seq, out_len, D, H, d, blocks = 5, 120, 9, 256, 4, 64, 2      # D = 256: the tcgen05 projection GEMMs
+    N = max_seq + out_len
+    proto = hstu.HSTU(max_sequence_len=max_seq, max_output_len=out_len, embedding_dim=D, item_embedding_dim=D,
+                      num_blocks=blocks, num_heads=H, linear_dim=d, attention_dim=d, normalization="rel_bias",
+                      linear_config="uvqk", linear_activation="silu", linear_dropout_rate=0.2, attn_dropout_rate=0.0)
+    lengths = torch.tensor([129, 40, 77, 3, 110])
+    ts = 978_300_000 + torch.cumsum(torch.randint(1, 5000, (B, N)), dim=1)
+    xin = torch.randn(B, N, D) * (torch.arange(N).unsqueeze(0) < lengths.unsqueeze(1)).unsqueeze(-1)
+    c = dict(max_seq=max_seq, out_len=out_len, D=D, blocks=blocks, H=H, dv=d, dqk=d, sd=proto.state_dict(), x=xin)
+    args = dict(past_lengths=lengths.to(DEV), valid_mask=None, past_payloads={"timestamps": ts.to(DEV)})
+    res = []
+    for shared in (True, False):
+        enc = _build(c, compute_dtype=torch.bfloat16)
+        if not shared:
+            monkeypatch.setattr(type(enc._hstu), "_layer_aux", lambda self, x: None)
+        else:
+            made = []
+            orig = type(enc._hstu)._layer_aux
+            monkeypatch.setattr(type(enc._hstu), "_layer_aux", lambda self, x: made.append(orig(self, x)) or made[-1])
+        x = c["x"].to(DEV).requires_grad_(True)
+        y, _ = enc(user_embeddings=x, **args)
+        y.float().square().sum().backward()
+        res.append((y.detach(), x.grad, {k: p.grad for k, p in enc.named_parameters() if p.grad is not None}))
+        if shared:
+            assert made and made[0] is not None and "dw_uvqk" in made[0][0] and made[0][0]["w_uvqk"].dtype == torch.bfloat16
+        monkeypatch.undo()
+    (y1, dx1, g1), (y2, dx2, g2) = res
+    assert torch.equal(y1, y2) and torch.equal(dx1, dx2)
+    assert g1.keys() == g2.keys() and len(g1) > 0
+    for k in g1:
+        _close(g1[k], g2[k], 1e-5, what=k)
+    # the two helpers on their own
+    ws = [torch.randn(257, 33, device=DEV), torch.randn(5, device=DEV), torch.randn(64, 1024, device=DEV)]
+    for w, wc in zip(ws, GF.cast_many_bf16(ws)):
+        assert wc.dtype == torch.bfloat16 and wc.data_ptr() % 16 == 0 and torch.equal(wc, w.bfloat16())
+    zs = GF.zeros_many([(3, 5), (7,), (256, 1024)], torch.device(DEV))
+    assert all(z.dtype == torch.float32 and not z.any() and z.data_ptr() % 256 == 0 for z in zs)
+    assert [tuple(z.shape) for z in zs] == [(3, 5), (7,), (256, 1024)]
+
+
 def test_training_mode_dropout_only_touches_o_input(golden):
     c = hstu_case(golden("hstu"), "mh")
     enc = _build(c).train()
