@@ -131,6 +131,11 @@ typedef struct grb_hstu_attn_args {
    * scratch (no zero fill). */
   const int32_t* short_schedule;
   int32_t bucket_cache_masked;    /* bucket_cache came from grb_hstu_bucket_tiles_masked */
+  /* short-sequence kernels only: T counts rows past offsets[B] (a fixed-size row bucket) and the launch
+   * itself writes zeros to those rows of out (forward) / dq, dk, dv_grad (backward) — the kernels never
+   * touch them otherwise, and the row-wise consumers (GEMMs, column sums) read them.  Rows 16-byte
+   * aligned.  0: the caller has zero-filled them. */
+  int32_t zero_tail_rows;
 } grb_hstu_attn_args;
 
 /* Host helper: the integer bucketing table the tcgen05 kernels use, from the ascending threshold

@@ -41,7 +41,7 @@ class HstuAttnArgs(C.Structure):
         ("lddq", c_i64), ("lddk", c_i64), ("lddv", c_i64),
         ("dq_accum", c_vp), ("d_ts_w", c_vp), ("d_pos_w", c_vp), ("d_bias_copies", c_i32),
         ("bucket_octaves", c_vp), ("bucket_cache", c_vp), ("bucket_cache_max_len", c_i64),
-        ("short_schedule", c_vp), ("bucket_cache_masked", c_i32),
+        ("short_schedule", c_vp), ("bucket_cache_masked", c_i32), ("zero_tail_rows", c_i32),
     ]
 
 

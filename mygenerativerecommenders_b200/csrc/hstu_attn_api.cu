@@ -49,6 +49,8 @@ int grb_hstu_attn_fwd(const grb_hstu_attn_args* a, grb_stream_t stream) {
                 "dims 64, max_len <= 256, 16-byte aligned rows, masked bucket_cache built for max_len)");
     return hstu_attn_short_fwd(a, st);
   }
+  GRB_REQUIRE(!a->zero_tail_rows, GRB_ERR_UNSUPPORTED,
+              "hstu_attn_fwd: zero_tail_rows is a service of the short-sequence kernels (zero-fill the rows)");
   if (!force_cuda_core() && hstu_attn_fwd_sm100_supported(a)) {
     // second-generation kernel when the buckets come from the per-batch cache (or no bias);
     // GRB_FWD_V1=1 keeps the first one (developer switch)
@@ -70,6 +72,8 @@ int grb_hstu_attn_bwd(const grb_hstu_attn_args* a, grb_stream_t stream) {
                 "dq_accum scratch when max_len > 128)");
     return hstu_attn_short_bwd(a, st);
   }
+  GRB_REQUIRE(!a->zero_tail_rows, GRB_ERR_UNSUPPORTED,
+              "hstu_attn_bwd: zero_tail_rows is a service of the short-sequence kernels (zero-fill the rows)");
   if (!force_cuda_core() && hstu_attn_bwd_sm100_supported(a)) return hstu_attn_bwd_sm100(a, st);
   return hstu_attn_bwd_simt_dispatch(a, st);
 }

@@ -205,7 +205,21 @@ struct ShortFwdParams {
   int nb;
   __nv_bfloat16* out;
   int64_t ldo;
+  int64_t T;                // rows of out; rows >= offsets[B] are zeroed here when zero_tail is set
+  int zero_tail;
 };
+
+// Rows [offsets[B], T) of a (T, H * 64) bf16 matrix := 0, spread over the whole grid (fixed row buckets:
+// at most one bucket's worth of rows, a few hundred KB).
+__device__ __forceinline__ void zero_tail_rows_of(__nv_bfloat16* m, int64_t ld, int64_t t0, int64_t T, int H) {
+  const int vpr = H * 8;                                  // 16-byte stores per row
+  const int64_t nvec = (T - t0) * vpr;
+  for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t) gridDim.x * blockDim.x) {
+    const int64_t r = t0 + i / vpr;
+    const int c = (int) (i % vpr);
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(m + r * ld) + 16 * c) = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
 
 struct SfSmem {
   static constexpr int ring = 0;                                   // 2 x (Q, K, V)
@@ -222,6 +236,7 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_fwd_kernel(
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   using L = SfSmem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (p.zero_tail) zero_tail_rows_of(p.out, p.ldo, load_index(p.offsets, p.B, p.index_bits), p.T, p.H);
   const int n_items = p.sched[0] * p.H;
   const int G = (int) gridDim.x, cta = (int) blockIdx.x;
   if (cta >= n_items) return;
@@ -448,6 +463,8 @@ struct ShortBwdParams {
   float* dq_accum;          // (T, H*64) fp32 scratch (no zero fill needed)
   float* d_ts_w; float* d_pos_w;   // (copies, nb + 1) / (copies, 2N - 1) fp32, accumulated (+=)
   int d_bias_copies;
+  int64_t T;                // rows of dq / dk / dv; rows >= offsets[B] are zeroed here when zero_tail is set
+  int zero_tail;
 };
 
 struct SbSmem {
@@ -471,6 +488,12 @@ __global__ void __launch_bounds__(SH_THREADS, 2) hstu_attn_short_bwd_kernel(
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   using L = SbSmem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (p.zero_tail) {
+    const int64_t t0 = load_index(p.offsets, p.B, p.index_bits);
+    zero_tail_rows_of(p.dq, p.lddq, t0, p.T, p.H);
+    zero_tail_rows_of(p.dk, p.lddk, t0, p.T, p.H);
+    zero_tail_rows_of(p.dv, p.lddv, t0, p.T, p.H);
+  }
   const int n_items = p.sched[0] * p.H;
   const int G = (int) gridDim.x, cta = (int) blockIdx.x;
   if (cta >= n_items) return;
@@ -900,6 +923,9 @@ int hstu_attn_short_fwd(const grb_hstu_attn_args* a, cudaStream_t st) {
   p.ts_w = a->timestamps ? a->ts_w : nullptr; p.pos_w = a->timestamps ? a->pos_w : nullptr;
   p.nb = a->timestamps ? a->num_buckets : 0;
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out); p.ldo = a->ldo;
+  p.T = a->T; p.zero_tail = a->zero_tail_rows;
+  GRB_REQUIRE(!p.zero_tail || ((reinterpret_cast<uintptr_t>(a->out) | (uintptr_t) (a->ldo * 2)) & 15) == 0,
+              GRB_ERR_INVALID_ARG, "hstu_attn_short_fwd: zero_tail_rows needs 16-byte aligned rows");
   const size_t smem = SfSmem::total + 1024;
   auto kern = hstu_attn_short_fwd_kernel;
   GRB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
@@ -936,6 +962,11 @@ int hstu_attn_short_bwd(const grb_hstu_attn_args* a, cudaStream_t st) {
   p.dq_accum = a->dq_accum;
   p.d_ts_w = a->d_ts_w; p.d_pos_w = a->d_pos_w;
   p.d_bias_copies = a->d_bias_copies > 0 ? a->d_bias_copies : 1;
+  p.T = a->T; p.zero_tail = a->zero_tail_rows;
+  GRB_REQUIRE(!p.zero_tail || ((reinterpret_cast<uintptr_t>(a->dq) | reinterpret_cast<uintptr_t>(a->dk) |
+                                reinterpret_cast<uintptr_t>(a->dv_grad) | (uintptr_t) (a->lddq * 2) |
+                                (uintptr_t) (a->lddk * 2) | (uintptr_t) (a->lddv * 2)) & 15) == 0,
+              GRB_ERR_INVALID_ARG, "hstu_attn_short_bwd: zero_tail_rows needs 16-byte aligned rows");
   const size_t smem = SbSmem::total + 1024;
   p.tl = timeline_buffer();
   const unsigned items = short_grid(a);

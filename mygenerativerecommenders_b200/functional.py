@@ -174,8 +174,6 @@ class _HstuAttention(torch.autograd.Function):
         # rows_padded: q/k/v carry rows past offsets[-1] (fixed-size row buckets); the kernels
         # never write those rows, so they must start as zeros
         out = torch.empty((q.shape[0], H * dv), dtype=q.dtype, device=q.device)
-        if rows_padded:
-            _zero_tail_rows(out, 1, offsets)
         if cache is not None and ((timestamps is None and not cache.grb_masked) or cache.grb_max_len != max_len):
             cache = None
         short = short_path_applies(q, dqk, dv, max_len) and (timestamps is None or thresholds.numel() <= 254)
@@ -187,6 +185,12 @@ class _HstuAttention(torch.autograd.Function):
         a = _attn_args(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds, N, H, dqk, dv, max_len, cache,
                        short)
         a.out, a.ldo = out.data_ptr(), H * dv
+        if rows_padded:
+            # the short-sequence kernels zero the rows past offsets[-1] themselves
+            if short and out.data_ptr() % 16 == 0 and (H * dv * out.element_size()) % 16 == 0:
+                a.zero_tail_rows = 1
+            else:
+                _zero_tail_rows(out, 1, offsets)
         with _lib.timed("hstu_attn_fwd"):
             _lib.check(_lib.lib().grb_hstu_attn_fwd(C.byref(a), _lib.stream_ptr(q.device)))
         ctx.save_for_backward(q, k, v, offsets, timestamps, ts_w, pos_w, thresholds)
@@ -207,12 +211,15 @@ class _HstuAttention(torch.autograd.Function):
         if dqk == dv:
             g3 = torch.empty((3, T, H * dqk), dtype=q.dtype, device=q.device)
             dq, dk, dvv = g3[0], g3[1], g3[2]
-            if ctx.rows_padded:
+            zero_in_kernel = (ctx.rows_padded and ctx.short and g3.data_ptr() % 16 == 0
+                              and (H * dqk * g3.element_size()) % 16 == 0 and (T * H * dqk * g3.element_size()) % 16 == 0)
+            if ctx.rows_padded and not zero_in_kernel:
                 _zero_tail_rows(g3, 3, offsets)
         else:
             dq = torch.empty((T, H * dqk), dtype=q.dtype, device=q.device)
             dk = torch.empty((T, H * dqk), dtype=q.dtype, device=q.device)
             dvv = torch.empty((T, H * dv), dtype=q.dtype, device=q.device)
+            zero_in_kernel = False
             if ctx.rows_padded:
                 for t in (dq, dk, dvv):
                     _zero_tail_rows(t, 1, offsets)
@@ -237,6 +244,7 @@ class _HstuAttention(torch.autograd.Function):
                        ctx.cache, short)
         a.dout, a.lddo = dout.data_ptr(), _ld(dout)
         a.dq, a.dk, a.dv_grad = dq.data_ptr(), dk.data_ptr(), dvv.data_ptr()
+        a.zero_tail_rows = 1 if zero_in_kernel else 0
         a.lddq, a.lddk, a.lddv = H * dqk, H * dqk, H * dv
         a.dq_accum = dq_acc.data_ptr() if n_acc else None
         d_ts = d_pos = None

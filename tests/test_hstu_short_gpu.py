@@ -179,3 +179,29 @@ def test_masked_bucket_tiles_and_item_schedule():
     only = GF.hstu_bucket_cache(off, None, None, N, masked=True).cpu().view(len(lengths), 3, 2, 8, 128, 16)
     tq = only[1, 1, 0].permute(1, 0, 2).reshape(128, 128)                  # sequence of 140, slot (1, 0)
     assert (tq[:12] == 0).all() and (tq[12:] == 255).all()
+
+
+@pytest.mark.parametrize("with_ts", [True, False])
+def test_row_bucket_tail_is_zeroed_by_the_kernels_themselves(with_ts):
+    """Fixed-size row buckets (rows_padded): q / k / v carry rows past offsets[-1]; the short-sequence
+    launches zero those rows of out / dq / dk / dv themselves (grb_hstu_attn_args.zero_tail_rows) — no
+    separate fill.  The allocator is poisoned with NaN first so that an unwritten row shows."""
+    N, H, lengths = 211, 4, [200, 37, 129, 5]
+    c = _case(21, N, H, lengths, with_ts=with_ts)
+    T, pad = c["T"], 300
+    ref_out, ref_leaves = _run(c, N, H)
+    for _ in range(4):                                   # poison blocks of the sizes about to be allocated
+        for rows in (T + pad, 3 * (T + pad)):
+            torch.full((rows, H * D), float("nan"), dtype=torch.bfloat16, device=DEV)
+    q, k, v = (torch.cat([c[n], torch.zeros(pad, H * D)]).to(DEV).to(torch.bfloat16).requires_grad_(True)
+               for n in ("q", "k", "v"))
+    ts_w = c["ts_w"].to(DEV).requires_grad_(True)
+    pos_w = c["pos_w"].to(DEV).requires_grad_(True)
+    out = GF.hstu_attention(q, k, v, c["off"].to(DEV), c["ts"].to(DEV) if with_ts else None,
+                            ts_w if with_ts else None, pos_w if with_ts else None,
+                            _thr() if with_ts else None, N, H, D, D, rows_padded=True)
+    assert out.shape[0] == T + pad and not out[T:].any() and torch.isfinite(out).all()
+    assert torch.equal(out[:T], ref_out)
+    out.backward(torch.cat([c["w"], torch.randn(pad, H * D)]).to(DEV).to(torch.bfloat16))
+    for g, r in zip((q, k, v), ref_leaves[:3]):
+        assert not g.grad[T:].any() and torch.equal(g.grad[:T], r.grad)
