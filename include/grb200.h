@@ -509,6 +509,13 @@ int grb_adamw_step(int n, float* const* p, const float* const* g, float* const* 
                    double weight_decay, double bias_correction1, double bias_correction2,
                    grb_stream_t stream);
 
+/* autoregressive_losses.py:306 (and :172), the loss of the step from its per-position terms:
+ *     out2[0] = sum(x * w) / sum(w),  out2[1] = sum(w)        (x, w fp32 (n); one CTA, fixed order)
+ * and its backward gx[i] = gout[0] * w[i] / out2[1]  (w = supervision_weights carries no gradient). */
+int grb_weighted_mean_fwd(const float* x, const float* w, int64_t n, float* out2, grb_stream_t stream);
+int grb_weighted_mean_bwd(const float* w, const float* out2, const float* gout, int64_t n, float* gx,
+                          grb_stream_t stream);
+
 /* dst[i] (bf16, numel[i]) = src[i] (fp32) for a HOST list of n device tensors, one launch per 64 tensors:
  * the compute-dtype copies of the fp32 master weights of all STU layers of a forward pass (the per-layer
  * casts of hstu.py:300-305 / :404-413 under autocast, made once). */

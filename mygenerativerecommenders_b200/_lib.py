@@ -174,6 +174,8 @@ SYMBOLS = {
                                      c_vp, c_i64, c_i64, c_i32, c_vp]),
     "grb_adamw_step": (C.c_int, [C.c_int, C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp),
                                  C.POINTER(c_i64)] + [C.c_double] * 7 + [c_vp]),
+    "grb_weighted_mean_fwd": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "grb_weighted_mean_bwd": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "grb_cast_f32_bf16_many": (C.c_int, [C.c_int, C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_i64), c_vp]),
     "grb_rows_scatter_add": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_i64, c_i64, c_vp]),
     "grb_rows_scale": (C.c_int, [c_vp, c_vp, c_i64, c_i32, c_i64, c_i64, C.c_float, c_vp]),

@@ -1002,6 +1002,34 @@ def layer_norm_skip(x: torch.Tensor, eps: float) -> Tuple[torch.Tensor, torch.Te
     return _LnGate.apply(x, None, eps, 0.0, None, 0, True)
 
 
+class _WeightedMean(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w):
+        out2 = torch.empty(2, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().grb_weighted_mean_fwd(x.data_ptr(), w.data_ptr(), x.numel(), out2.data_ptr(),
+                                                    _lib.stream_ptr(x.device)))
+        ctx.save_for_backward(w, out2)
+        return out2[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        w, out2 = ctx.saved_tensors
+        g = g.reshape(1).float().contiguous()
+        gx = torch.empty(w.numel(), dtype=torch.float32, device=w.device)
+        _lib.check(_lib.lib().grb_weighted_mean_bwd(w.data_ptr(), out2.data_ptr(), g.data_ptr(), w.numel(),
+                                                    gx.data_ptr(), _lib.stream_ptr(w.device)))
+        return gx, None
+
+
+def weighted_mean(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """``(x * w).sum() / w.sum()`` (autoregressive_losses.py:306) for 1-D float32 CUDA tensors, one launch
+    each way; ``w`` (the supervision weights) receives no gradient.  Anything else takes the torch ops."""
+    if (x.is_cuda and w.is_cuda and x.dtype == torch.float32 and w.dtype == torch.float32 and x.dim() == 1
+            and x.shape == w.shape and x.is_contiguous() and w.is_contiguous() and not w.requires_grad):
+        return _WeightedMean.apply(x, w)
+    return (x * w).sum() / w.sum()
+
+
 # --------------------------------------------------------------------------------------------
 # fused sampled softmax  (negative_sampler.py:31-37,123-131,208-211; dot_product.py:61-64;
 #                         autoregressive_losses.py:279-306)

@@ -87,7 +87,7 @@ class SampledSoftmaxLoss(AutoregressiveLoss):
                 output_embeddings, positive_embeddings, t0, t1, fused.idx0, fused.idx1,
                 supervision_ids, fused.ids, fused.l2_norm, negatives_sampler._l2_norm_eps,
                 self._softmax_temperature, bf16_backward=self._bf16_backward)
-            return (jagged_loss * supervision_weights).sum() / supervision_weights.sum()
+            return GF.weighted_mean(jagged_loss, supervision_weights)
 
         # unfused: the reference's sequence on torch ops (autoregressive_losses.py:272-306)
         sampled_ids, sampled_negative_embeddings = negatives_sampler(

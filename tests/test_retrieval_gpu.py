@@ -445,3 +445,25 @@ def test_topk_graph_replay_equals_eager_call():
         es, ei, er = GF.mips_topk(q, items, ids, k, invalid_ids=inv, target_ids=tgt)
         assert not g.overflowed()
         assert torch.equal(i, ei) and torch.equal(s, es) and torch.equal(r, er)
+
+
+def test_weighted_mean_one_launch_each_way():
+    """autoregressive_losses.py:306, (loss * w).sum() / w.sum(): value and gradient against the torch ops."""
+    from mygenerativerecommenders_b200 import _lib
+    gen = torch.Generator().manual_seed(2)
+    for n in (1, 33, 14_080, 300_001):
+        x = torch.randn(n, generator=gen).to(DEV).requires_grad_(True)
+        w = (torch.rand(n, generator=gen) > 0.3).float().to(DEV)
+        w[0] = 1.0
+        n0 = _lib.launch_count()
+        y = GF.weighted_mean(x, w)
+        (y * 3.0).backward()
+        assert _lib.launch_count() - n0 == 2
+        xr = x.detach().double().requires_grad_(True)
+        yr = (xr * w.double()).sum() / w.double().sum()
+        (yr * 3.0).backward()
+        assert y.dim() == 0 and abs(y.item() - yr.item()) <= 1e-5 * max(1.0, abs(yr.item()))
+        assert torch.allclose(x.grad.double(), xr.grad, rtol=1e-6, atol=1e-9)
+    # anything the kernel does not take falls back to the torch expression
+    xh = torch.randn(8, device=DEV, dtype=torch.bfloat16)
+    assert GF.weighted_mean(xh, torch.ones(8, device=DEV, dtype=torch.bfloat16)).dtype == torch.bfloat16
