@@ -697,6 +697,12 @@ def retrieval_hbm_regime(dev, items, item_ids, pk) -> dict:
     from mygenerativerecommenders_b200 import functional as GF
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     out = {}
+    # These calls are 0.1 - 1 ms long and, at C3, instruction-bound: they follow the SM clock.  The timed C4
+    # loop just before draws > 600 W; measured right behind it the same C3 graph takes 0.115 ms instead of
+    # the 0.087 ms it takes in a process of its own (benchmarks/probes/mips_small_probe.py, same box).  Let
+    # the board settle, and sample the clocks over this region so that the line says under which ones it ran.
+    torch.cuda.synchronize(dev)
+    time.sleep(2.0)
 
     def timed(fn, iters=10):
         for _ in range(3):
@@ -721,6 +727,8 @@ def retrieval_hbm_regime(dev, items, item_ids, pk) -> dict:
     g = torch.Generator(device=dev).manual_seed(7)
     X, D, k = items.shape[0], items.shape[1], 200
     q = torch.nn.functional.normalize(torch.randn(128, D, device=dev, generator=g), dim=-1).to(torch.bfloat16)
+    sampler = ClockSampler(dev.index or 0)
+    sampler.__enter__()
     ms = timed(lambda: GF.mips_topk(q, items, item_ids, k))
     byts = X * D * 2 + 128 * D * 2 + 128 * k * 12
     gr = GF.MipsTopkGraph(128, items, item_ids, k)
@@ -754,6 +762,9 @@ def retrieval_hbm_regime(dev, items, item_ids, pk) -> dict:
                  "hbm_frac": byts3 / ms3 / 1e6 / pk["hbm_gbs"], "hbm_peak": pk["hbm_gbs"],
                  "launches_per_call": launches_of(lambda: GF.mips_topk(q3, items3, ids3, k, invalid_ids=inv3)),
                  "includes": "host time of the call (workspace lookup, launches, overflow-flag read)"}
+    sampler.__exit__()
+    out["clocks"] = dict(sampler.summary(), what="SM clocks over the small_batch and c3 measurements (after a 2 s idle "
+                                               "behind the timed C4 loop)")
     return out
 
 

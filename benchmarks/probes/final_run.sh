@@ -1,0 +1,17 @@
+# round-end sequence on one GPU: all GPU tests, the bench line, the reference arm, the train step's launch list
+set -x
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/final_tests.txt 2>&1
+tail -3 gpurun_out/final_tests.txt | cut -c1-200
+timeout 900 python bench.py > gpurun_out/r2_bench_1gpu.json 2> gpurun_out/r2_bench_1gpu.err || { tail -20 gpurun_out/r2_bench_1gpu.err; exit 1; }
+python - <<'P'
+import json
+d=json.loads(open('gpurun_out/r2_bench_1gpu.json').read().strip().splitlines()[-1])
+print('train', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], 'roof', d['roofline']['kernel'], d['roofline']['frac'])
+r=d['retrieval']; print('C4', r['value'], r['roofline']['frac'], 'small', r['small_batch']['graph_ms'], r['small_batch']['graph_hbm_frac'], r['small_batch'].get('launches_per_call'), 'c3', r['c3']['ms'], r['c3']['graph_ms'], r['c3']['graph_hbm_frac'], r['c3'].get('launches_per_call'))
+ls=d['long_sequence']; print('C5 slice', ls['attention_slice']['fwd_frac'], ls['attention_slice']['bwd_frac'], 'step', ls['train_step']['ms_per_step'])
+print('dropin', d['dropin_eager']['value'], 'loss_check', d['loss_check']['ok'], 'clocks', d['clocks'])
+P
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_bench_ref_1gpu.json 2> gpurun_out/r2_bench_ref_1gpu.err; tail -c 400 gpurun_out/r2_bench_ref_1gpu.json
+CMD="python bench.py --steps 2 --warmup 3 --skip-retrieval --skip-cpu-baseline --skip-long-sequence"
+$CMD > /dev/null 2>&1 && timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/r2_launches_bench_train.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+python tools/step_breakdown.py gpurun_out/r2_launches_bench_train.csv | head -30

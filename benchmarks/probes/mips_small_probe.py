@@ -19,10 +19,11 @@ def run(tag, B, X, D, k, n_inv):
     items = torch.nn.functional.normalize(torch.randn(X, D, device=DEV, generator=g), dim=-1).to(torch.bfloat16)
     q = torch.nn.functional.normalize(torch.randn(B, D, device=DEV, generator=g), dim=-1).to(torch.bfloat16)
     inv = torch.randint(1, X, (B, n_inv), device=DEV, generator=g) if n_inv else None
-    graph = GF.MipsTopkGraph(B, items, None, k, n_invalid=n_inv)
+    ids = torch.arange(1, X + 1, device=DEV, dtype=torch.int64) if os.environ.get("PROBE_IDS") == "1" else None
+    graph = GF.MipsTopkGraph(B, items, ids, k, n_invalid=n_inv)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
     res = {}
-    for name, fn in (("eager", lambda: GF.mips_topk(q, items, None, k, invalid_ids=inv)),
+    for name, fn in (("eager", lambda: GF.mips_topk(q, items, ids, k, invalid_ids=inv)),
                      ("graph", lambda: graph(q, inv))):
         for _ in range(3):
             fn()
@@ -33,12 +34,14 @@ def run(tag, B, X, D, k, n_inv):
             e0.record(); fn(); e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
+        res[name + "_mean"] = sum(ts) / len(ts)
         ts.sort()
         res[name] = ts[len(ts) // 2]
     assert not graph.overflowed()
     byts = X * D * 2
     print(f"{tag} small={os.environ.get('GRB_MIPS_SMALL', '1')} stride={os.environ.get('GRB_MIPS_SMALL_STRIDE', 'auto')}: "
-          f"eager {res['eager']:.4f} ms, graph {res['graph']:.4f} ms = {byts / res['graph'] / 1e6:.0f} GB/s", flush=True)
+          f"eager {res['eager']:.4f} ms (mean {res['eager_mean']:.4f}), graph {res['graph']:.4f} ms (mean {res['graph_mean']:.4f}) "
+          f"= {byts / res['graph'] / 1e6:.0f} GB/s, ids={'yes' if ids is not None else 'no'}", flush=True)
 
 
 if __name__ == "__main__":

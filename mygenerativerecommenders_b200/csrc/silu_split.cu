@@ -63,6 +63,20 @@ struct SplitGrads {          // up to four column blocks [begin_i, begin_{i+1}) 
   int n;
 };
 
+// (row, first element) of 16-byte chunk i of a (rows, cpr chunks) matrix.  Chunk counts below 2^31 (every
+// real shape) take a 32-bit division: the 64-bit one is ~100 instructions, paid per chunk, and made these
+// streaming kernels instruction-bound.
+__device__ __forceinline__ void chunk_row_col(int64_t i, int cpr, bool small, int64_t& r, int& c) {
+  if (small) {
+    const uint32_t q = (uint32_t) i / (uint32_t) cpr;
+    r = q;
+    c = (int) ((uint32_t) i - q * (uint32_t) cpr);
+  } else {
+    r = i / cpr;
+    c = (int) (i - r * cpr);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) silu_fwd_kernel(const T* __restrict__ x, int64_t ldx, T* __restrict__ y,
                                                        int64_t ldy, int64_t rows, int W) {
@@ -78,8 +92,10 @@ __global__ void __launch_bounds__(256) silu_fwd_kernel(const T* __restrict__ x, 
     const int64_t i = base + u * 256;
     off_y[u] = -1;
     if (i < total) {
-      const int64_t r = i / cpr;
-      const int c = (int) (i - r * cpr) * E;
+      int64_t r;
+      int c;
+      chunk_row_col(i, cpr, total < (1ll << 31), r, c);
+      c *= E;
       Vec16<T>::load(x + r * ldx + c, f[u]);
       off_y[u] = r * ldy + c;
     }
@@ -111,8 +127,10 @@ __global__ void __launch_bounds__(256) silu_split_bwd_kernel(const T* __restrict
     off_d[u] = -1;
     has[u] = false;
     if (i < total) {
-      const int64_t r = i / cpr;
-      const int c = (int) (i - r * cpr) * E;
+      int64_t r;
+      int c;
+      chunk_row_col(i, cpr, total < (1ll << 31), r, c);
+      c *= E;
       int blk = 0;
 #pragma unroll
       for (int b = 1; b < 4; ++b) blk += (b < sg.n && c >= sg.begin[b]) ? 1 : 0;
