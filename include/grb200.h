@@ -240,6 +240,18 @@ int grb_zero_tail_rows(void* base, int64_t ld_bytes, int64_t rows, int64_t row_b
 int grb_draw_negatives(const int64_t* seed, const int64_t* count, const int64_t* cached_ids, int64_t n,
                        int64_t* offsets, int64_t* ids, grb_stream_t stream);
 
+/* b5  negatives_samples/negative_sampler.py:187-196: the de-duplicated id list of the in-batch cache,
+ *     torch.unique(ids[presences]) (ascending: the draw of :208-211 indexes it), for a small id space, in two
+ *     launches and without a device sync.  ids (B, N) int64; the valid ids of row b are its first
+ *     offsets[b+1] - offsets[b] + rows_extra entries (id 0 = padding; ids >= n_flags are skipped).
+ *     flags: persistent int32[n_flags + ceil(n_flags / 1024)] (membership table + one counter per 1024
+ *     ids), zero-initialised ONCE by the caller and never cleared by it (entries are stamped with epoch[0],
+ *     a device int32 starting at 1 that this call increments; the counters are left at zero).  n_flags <= 2^22.
+ *     uniq[0 .. count) = the distinct ids ascending, uniq[count .. n_out) = 0, count[0] = their number. */
+int grb_inbatch_distinct_ids(const int64_t* ids, int64_t B, int64_t N, const void* offsets, int32_t index_bits,
+                             int32_t rows_extra, int32_t* flags, int64_t n_flags, int32_t* epoch, int64_t* uniq,
+                             int64_t n_out, int64_t* count, grb_stream_t stream);
+
 int grb_jagged_input_fwd(const grb_jagged_input_args* a, grb_stream_t stream);
 int grb_jagged_input_bwd(const grb_jagged_input_args* a, grb_stream_t stream);
 int grb_l2norm_cast_fwd(const void* x, int64_t ldx, int dtype, float* y, int64_t ldy, float* inv, int64_t rows,

@@ -181,6 +181,8 @@ SYMBOLS = {
     "grb_rows_scale": (C.c_int, [c_vp, c_vp, c_i64, c_i32, c_i64, c_i64, C.c_float, c_vp]),
     "grb_zero_tail_rows": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_i32, c_i64, c_vp, c_i32, c_i64, c_i64, c_vp]),
     "grb_draw_negatives": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "grb_inbatch_distinct_ids": (C.c_int, [c_vp, c_i64, c_i64, c_vp, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp,
+                                           c_i64, c_vp, c_vp]),
     "grb_jagged_input_fwd": (C.c_int, [C.POINTER(JaggedInputArgs), c_vp]),
     "grb_jagged_input_bwd": (C.c_int, [C.POINTER(JaggedInputArgs), c_vp]),
     "grb_l2norm_cast_fwd": (C.c_int, [c_vp, c_i64, C.c_int, c_vp, c_i64, c_vp, c_i64, c_i64, C.c_float, c_vp]),

@@ -20,6 +20,130 @@
 namespace grb {
 namespace {
 
+// ---------------------------------------------------------------------------------------------
+// b5  in-batch cache: the distinct ids of a batch, ascending, in two launches and without a sync.
+// negative_sampler.py:187-196 keeps `torch.unique(ids[presences])` (sorted ascending; the draw of :208-211
+// indexes it, so the order is part of the contract).  With a small id space that is a membership table
+// and a compaction.  The table is persistent and stamped with an epoch instead of being cleared:
+//   mark     for the first cnt_b = offsets[b+1] - offsets[b] + rows_extra ids of row b (id 0 = padding, ids
+//            past the table are skipped): old = exch(flags[id], epoch); the first marker of an id also
+//            counts it in chunk_cnt[id / 1024]
+//   compact  one CTA: exclusive scan of the chunk counts; every warp walks its chunks (32 coalesced loads,
+//            32 ballots: lane l holds the membership mask of ids [1024 c + 32 l, + 32)) and writes the ids
+//            in ascending order to uniq[0 .. count); uniq[count .. n_out) = 0, count stored, chunk counts
+//            cleared for the next call, epoch += 1.
+// (Replaces dense_to_jagged + arange + compare + where + zeros + scatter_ + zero_ + sum + the four kernels
+//  of nonzero_static: 12 launches of the train step.)
+// ---------------------------------------------------------------------------------------------
+constexpr int IBC_CHUNK = 1024;
+constexpr int IBC_MAX_CHUNKS = 4096;      // ids < 2^22
+__global__ void __launch_bounds__(256) inbatch_mark_kernel(const int64_t* __restrict__ ids, int64_t N,
+                                                           const void* __restrict__ offsets, int index_bits,
+                                                           int rows_extra, int64_t n_flags,
+                                                           int32_t* __restrict__ flags, int32_t* __restrict__ chunk_cnt,
+                                                           const int32_t* __restrict__ epoch) {
+  const int64_t b = blockIdx.y;
+  int64_t cnt = load_index(offsets, b + 1, index_bits) - load_index(offsets, b, index_bits) + rows_extra;
+  if (cnt > N) cnt = N;
+  const int32_t e = epoch[0];
+  for (int64_t j = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; j < cnt; j += (int64_t) gridDim.x * blockDim.x) {
+    const int64_t id = ids[b * N + j];
+    if (id > 0 && id < n_flags && atomicExch(flags + id, e) != e) atomicAdd(chunk_cnt + (id / IBC_CHUNK), 1);
+  }
+}
+
+constexpr int IBC_THREADS = 1024;
+__global__ void __launch_bounds__(IBC_THREADS) inbatch_compact_kernel(const int32_t* __restrict__ flags,
+                                                                      int64_t n_flags, int32_t* __restrict__ chunk_cnt,
+                                                                      int32_t* __restrict__ epoch,
+                                                                      int64_t* __restrict__ uniq, int64_t n_out,
+                                                                      int64_t* __restrict__ count) {
+  __shared__ int chunk_base[IBC_MAX_CHUNKS];
+  __shared__ int wtot[32];
+  __shared__ int total_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int32_t e = epoch[0];
+  const int n_chunks = (int) ((n_flags + IBC_CHUNK - 1) / IBC_CHUNK);
+  // exclusive scan of the chunk counts: thread t owns chunks [t * per, (t + 1) * per)
+  const int per = (n_chunks + IBC_THREADS - 1) / IBC_THREADS;      // <= 4
+  int cc[4], c = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int ch = tid * per + k;
+    cc[k] = (k < per && ch < n_chunks) ? chunk_cnt[ch] : 0;
+    c += cc[k];
+  }
+  int incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) wtot[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int w = wtot[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += v;
+    }
+    wtot[lane] = w;                       // inclusive warp totals
+    if (lane == 31) total_s = w;
+  }
+  __syncthreads();
+  int run = (wid > 0 ? wtot[wid - 1] : 0) + incl - c;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int ch = tid * per + k;
+    if (k < per && ch < n_chunks) {
+      chunk_base[ch] = run;
+      run += cc[k];
+      chunk_cnt[ch] = 0;                  // clean for the next call
+    }
+  }
+  __syncthreads();
+  // chunks with members, round-robin over the warps
+  for (int ch = wid; ch < n_chunks; ch += 32) {
+    const int have = (ch + 1 < n_chunks ? chunk_base[ch + 1] : total_s) - chunk_base[ch];
+    if (have == 0) continue;              // warp-uniform
+    int32_t v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {        // all loads before the first ballot
+      const int64_t i = (int64_t) ch * IBC_CHUNK + 32 * k + lane;
+      v[k] = i < n_flags ? flags[i] : 0;  // e >= 1: 0 is never a member
+    }
+    uint32_t m = 0u;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const uint32_t word = __ballot_sync(0xffffffffu, v[k] == e);
+      if (lane == k) m = word;
+    }
+    if (ch == 0) m &= lane == 0 ? ~1u : ~0u;     // id 0 is padding (never marked; belt and braces)
+    const int cw = __popc(m);
+    int inw = cw;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inw, o);
+      if (lane >= o) inw += t;
+    }
+    int64_t pos = chunk_base[ch] + inw - cw;
+    const int64_t id0 = (int64_t) ch * IBC_CHUNK + 32 * lane;
+    while (m) {
+      const int bit = __ffs(m) - 1;
+      m &= m - 1;
+      if (pos < n_out) uniq[pos] = id0 + bit;
+      ++pos;
+    }
+  }
+  const int total = total_s;
+  for (int64_t i = total + tid; i < n_out; i += IBC_THREADS) uniq[i] = 0;
+  if (tid == 0) {
+    count[0] = total < n_out ? total : n_out;
+    epoch[0] = e == 0x7fffffff ? 1 : e + 1;   // (a wrap would need a cleared table: 2^31 steps away)
+  }
+}
+
 // jagged row t -> (sequence b, position i); offsets ascending, off[B] = valid rows.  Warp-uniform.
 __device__ __forceinline__ bool locate_row(const void* __restrict__ offsets, int index_bits, int B, int64_t t,
                                            int& b, int64_t& i) {
@@ -255,6 +379,24 @@ int grb_draw_negatives(const int64_t* seed, const int64_t* count, const int64_t*
   if (n == 0) return GRB_OK;
   draw_negatives_kernel<<<(unsigned) ceil_div(ceil_div(n, (int64_t) 2), (int64_t) 256), 256, 0,
                           reinterpret_cast<cudaStream_t>(stream)>>>(seed, count, cached_ids, n, offsets, ids);
+  GRB_LAUNCH_OK();
+  return GRB_OK;
+}
+
+int grb_inbatch_distinct_ids(const int64_t* ids, int64_t B, int64_t N, const void* offsets, int32_t index_bits,
+                             int32_t rows_extra, int32_t* flags, int64_t n_flags, int32_t* epoch, int64_t* uniq,
+                             int64_t n_out, int64_t* count, grb_stream_t stream) {
+  GRB_REQUIRE(ids && offsets && flags && epoch && uniq && count && B >= 0 && N > 0 && n_flags > 1 && n_out >= 0 &&
+                  B <= 65535 && n_flags <= (int64_t) IBC_MAX_CHUNKS * IBC_CHUNK && (index_bits == 32 || index_bits == 64),
+              GRB_ERR_INVALID_ARG, "inbatch_distinct_ids: bad arguments");
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  int32_t* chunk_cnt = flags + n_flags;       // the table's tail: one counter per 1024 ids
+  if (B > 0) {
+    inbatch_mark_kernel<<<dim3((unsigned) ceil_div(N, (int64_t) 256), (unsigned) B), 256, 0, st>>>(
+        ids, N, offsets, index_bits, rows_extra, n_flags, flags, chunk_cnt, epoch);
+    GRB_LAUNCH_OK();
+  }
+  inbatch_compact_kernel<<<1, IBC_THREADS, 0, st>>>(flags, n_flags, chunk_cnt, epoch, uniq, n_out, count);
   GRB_LAUNCH_OK();
   return GRB_OK;
 }

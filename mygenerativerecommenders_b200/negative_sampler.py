@@ -238,19 +238,33 @@ class InBatchNegativesSampler(*((NegativesSampler, _RefInBatch) if _RefInBatch e
         self._cached_count = count
 
     def process_batch_table(self, ids: torch.Tensor, prefix_offsets: torch.Tensor, total: int,
-                            table: torch.Tensor, padded: bool = False, grad_scope=None) -> bool:
+                            table: torch.Tensor, padded: bool = False, grad_scope=None,
+                            rows_extra: int = 0) -> bool:
         """``process_batch`` straight from the embedding table (extension): equal ids carry equal
         embeddings, so the de-duplicated cache is ``normalize(table[unique(valid ids)])`` -- the
         (B, N, D) embeddings of the batch (retrieval.py:104-111 looks them up a second time) are not
         needed at all.  ids (B, N) whose valid entries are the first prefix_offsets[b+1] -
         prefix_offsets[b] of every row, ``total`` of them (an upper bound when ``padded``).  Static
         shapes, no device sync.  Needs ``dedup_embeddings`` and a small id space (``max_item_id``);
-        returns False (nothing done) otherwise."""
+        returns False (nothing done) otherwise.  ``rows_extra``: the valid count of row b is
+        prefix_offsets[b+1] - prefix_offsets[b] + rows_extra (the caller's jagged offsets + the target)."""
         from . import functional as GF
         from . import ops
         max_id = getattr(self, "max_item_id", None)
         if not self._dedup_embeddings or max_id is None or max_id >= (1 << 22) or total <= 0:
             return False
+        if ids.is_cuda and ids.dtype == torch.int64 and ids.dim() == 2 and ids.is_contiguous() \
+                and prefix_offsets.dtype in (torch.int32, torch.int64) and ids.size(0) <= 65535:
+            # membership table stamped with a device-side epoch + one compaction: two launches
+            # (grb_inbatch_distinct_ids) instead of the twelve of the torch formulation below
+            uniq, count = self._distinct_ids(ids, prefix_offsets.contiguous(), int(total), int(rows_extra), max_id + 2)
+            self._cached_embeddings = self._maybe_l2_norm(GF.embedding_lookup(table, uniq, 0, grad_scope=grad_scope))
+            self._cached_ids = uniq
+            self._cached_count = count
+            return True
+        if rows_extra:
+            prefix_offsets = prefix_offsets + rows_extra * torch.arange(
+                prefix_offsets.numel(), device=prefix_offsets.device, dtype=prefix_offsets.dtype)
         valid_ids = ops.dense_to_jagged(ids.unsqueeze(-1), prefix_offsets, total=total,
                                         zero_tail=padded).squeeze(-1)
         n = valid_ids.numel()
@@ -268,6 +282,26 @@ class InBatchNegativesSampler(*((NegativesSampler, _RefInBatch) if _RefInBatch e
         self._cached_ids = uniq
         self._cached_count = count
         return True
+
+    def _distinct_ids(self, ids: torch.Tensor, offsets: torch.Tensor, n_out: int, rows_extra: int,
+                      n_flags: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        from . import _lib
+        dev = ids.device
+        tab = self.__dict__.get("_flag_table")
+        n_tab = n_flags + (n_flags + 1023) // 1024      # membership flags + one counter per 1024 ids
+        if tab is None or tab[0].device != dev or tab[0].numel() != n_tab:
+            # persistent: zero-filled once, entries are stamped with the epoch, never cleared
+            tab = (torch.zeros(n_tab, dtype=torch.int32, device=dev),
+                   torch.ones(1, dtype=torch.int32, device=dev))
+            self.__dict__["_flag_table"] = tab
+        flags, epoch = tab
+        uniq = torch.empty(n_out, dtype=torch.int64, device=dev)
+        count = torch.empty(1, dtype=torch.int64, device=dev)
+        _lib.check(_lib.lib().grb_inbatch_distinct_ids(
+            ids.data_ptr(), ids.size(0), ids.size(1), offsets.data_ptr(), _lib.index_bits(offsets), rows_extra,
+            flags.data_ptr(), n_flags, epoch.data_ptr(), uniq.data_ptr(), n_out, count.data_ptr(),
+            _lib.stream_ptr(dev)))
+        return uniq, count[0]
 
     def get_all_ids_and_embeddings(self) -> Tuple[torch.Tensor, torch.Tensor]:
         if getattr(self, "_cached_count", None) is not None:     # padded cache: trim (host sync)

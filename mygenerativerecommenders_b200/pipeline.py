@@ -483,9 +483,9 @@ class RetrievalModel(torch.nn.Module):
         # every reader of the table below scatters its gradient into ONE dense buffer (GF.TableGradScope)
         scope = GF.TableGradScope(table)
         if isinstance(self.negatives_sampler, InBatchNegativesSampler):
+            # the valid ids of row b are its first length + 1 entries (history + target)
             if not self.negatives_sampler.process_batch_table(
-                    sup_ids, off + torch.arange(off.numel(), device=off.device, dtype=off.dtype),
-                    tot + sup_ids.size(0), table, padded=padded, grad_scope=scope):
+                    sup_ids, off, tot + sup_ids.size(0), table, padded=padded, grad_scope=scope, rows_extra=1):
                 return None
         else:
             self.negatives_sampler._embeddings_module = self.embeddings

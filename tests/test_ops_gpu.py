@@ -205,3 +205,14 @@ def test_l2_normalize_matches_reference_composite(W):
     ya.backward(go)
     yb.backward(go)
     torch.testing.assert_close(a.grad, b.grad, rtol=2e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("dtype", [torch.int32, torch.int64])
+def test_complete_cumsum_across_tile_boundaries(dtype):
+    """a1 at sizes around the kernel's tiles (16 lengths per thread, 16 384 per tile, running carry)."""
+    gen = torch.Generator().manual_seed(1)
+    for n in (0, 1, 15, 16, 17, 1023, 1024, 16383, 16384, 16385, 50_001):
+        x = torch.randint(0, 300, (n,), generator=gen).to(dtype)
+        want = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(x.long(), 0)]).to(dtype)
+        got = ops.asynchronous_complete_cumsum(x.to(DEV))
+        assert got.dtype == dtype and torch.equal(got.cpu(), want), n

@@ -467,3 +467,35 @@ def test_weighted_mean_one_launch_each_way():
     # anything the kernel does not take falls back to the torch expression
     xh = torch.randn(8, device=DEV, dtype=torch.bfloat16)
     assert GF.weighted_mean(xh, torch.ones(8, device=DEV, dtype=torch.bfloat16)).dtype == torch.bfloat16
+
+
+@pytest.mark.parametrize("off_dtype", [torch.int64, torch.int32])
+def test_inbatch_cache_from_the_table_is_the_sorted_distinct_id_list(off_dtype):
+    """process_batch_table (grb_inbatch_distinct_ids: epoch-stamped membership table + one compaction) against
+    torch.unique of the valid ids (negative_sampler.py:187-196), batch after batch on the same table — ids of
+    an earlier batch must not reappear — with the caller's jagged offsets + rows_extra and a padded total."""
+    from mygenerativerecommenders_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    B, N, D, V = 37, 61, 32, 5000
+    table = torch.randn(V + 1, D, generator=g).to(DEV)
+    table[0].zero_()
+    smp = InBatchNegativesSampler(True, 1e-6, True)
+    smp.max_item_id = V
+    for rep in range(4):
+        lengths = torch.randint(0, N - 1, (B,), generator=g)
+        if rep == 2:
+            lengths[:] = 0                                   # targets only
+        ids = torch.zeros(B, N, dtype=torch.int64)
+        for b in range(B):
+            ids[b, : lengths[b] + 1] = torch.randint(1, V + 1 if rep % 2 else 200, (int(lengths[b]) + 1,), generator=g)
+            ids[b, lengths[b] + 1:] = torch.randint(1, V + 1, (N - int(lengths[b]) - 1,), generator=g)   # junk past the prefix
+        off = ops.asynchronous_complete_cumsum(lengths.to(DEV)).to(off_dtype)
+        total = int(lengths.sum()) + B + (53 if rep % 2 else 0)          # an upper bound when padded
+        assert smp.process_batch_table(ids.to(DEV), off, total, table, padded=bool(rep % 2), rows_extra=1)
+        valid = torch.cat([ids[b, : lengths[b] + 1] for b in range(B)])
+        want = torch.unique(valid)
+        c = int(smp._cached_count.item())
+        assert c == want.numel() and smp._cached_ids.numel() == total
+        assert torch.equal(smp._cached_ids[:c].cpu(), want) and not smp._cached_ids[c:].any()
+        ref = torch.nn.functional.normalize(table[want.to(DEV)], dim=-1, eps=1e-6)
+        assert torch.allclose(smp._cached_embeddings[:c], ref, atol=1e-6) and not smp._cached_embeddings[c:].any()
