@@ -51,6 +51,43 @@ def test_invalid_arguments_are_reported_without_a_gpu():
     assert L.grb_mips_topk_workspace_bytes(ctypes.byref(a)) == _lib.GRB_ERR_INVALID_ARG
 
 
+def _mips_ws(B, X, D, k, dtype, n_invalid=0, cand_cap=0):
+    a = _lib.MipsTopkArgs()
+    a.B, a.X, a.D, a.k, a.dtype = B, X, D, k, dtype
+    a.ldq = a.ldi = D
+    a.n_invalid, a.cand_cap = n_invalid, cand_cap
+    if n_invalid:
+        a.invalid_ids = 16          # any non-null address: the planner only looks at the count
+    need = int(_lib.lib().grb_mips_topk_workspace_bytes(ctypes.byref(a)))
+    return need, int(a.cand_cap), int(a.sample_stride)
+
+
+def test_topk_planner_picks_the_one_query_block_plan_where_it_applies():
+    """Host logic of grb_mips_topk_workspace_bytes (no GPU): one bf16 query block against a corpus of several
+    hundred tiles gets the workspace of the one-query-block plan (csrc/mips_small.cu: private sub-lists, much
+    larger than the phased plan's candidate lists); more queries, fp32 tables, tiny corpora, or an explicit
+    candidate capacity (the wrapper's exact re-run after an overflow) get the phased plan's."""
+    BF16, F32 = _lib.GRB_BF16, _lib.GRB_F32
+    c3, cap, stride = _mips_ws(128, 700_000, 64, 200, BF16, n_invalid=61)
+    assert stride == 64 and cap == 261 * (4 + 2 * 3 * 3) + 1024       # the phased plan's own sizes are still reported
+    rerun, cap2, _ = _mips_ws(128, 700_000, 64, 200, BF16, n_invalid=61, cand_cap=cap + 1024)
+    assert cap2 == cap + 1024
+    phased_c3 = 128 * (4 + 4 + 11008 * 4 + 2 * 4 * cap)               # tau, counts, sample, candidate lists
+    assert rerun < 2 * phased_c3 + 128 * 2 * 4 * 1024 and c3 > 2 * rerun   # sub-lists: 128 x 592 x (24 + 32) x 8 B
+    assert abs(c3 - 128 * 592 * 56 * 8) < 8 << 20
+    two_blocks, _, _ = _mips_ws(129, 700_000, 64, 200, BF16, n_invalid=61)
+    fp32, _, _ = _mips_ws(128, 700_000, 64, 200, F32, n_invalid=61)
+    assert two_blocks < c3 / 2 and fp32 < c3 / 2
+    small_corpus, cap_s, _ = _mips_ws(128, 20_000, 64, 200, BF16)      # 157 tiles: too few groups for the estimate
+    assert cap_s == 200 * (4 + 2 * 3 * 1) + 1024 and small_corpus < 128 * (8 + 40 * 128 * 4 + 8 * cap_s) + 4096
+    # k' too large for the 8192-key select of the plan: phased
+    big_k, _, _ = _mips_ws(128, 700_000, 64, 1500, BF16)
+    assert big_k < 128 * 2 * 4 * (1500 * 22 + 1024) + (16 << 20)
+    # C4 corpus at one query block: sample stride 16, still the one-query-block plan
+    c4, _, _ = _mips_ws(128, 10_000_000, 256, 200, BF16)
+    assert c4 > 128 * 592 * 40 * 8
+
+
 def test_no_cpu_fallback():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.asynchronous_complete_cumsum(torch.tensor([1, 2]))
