@@ -12,8 +12,12 @@
 //               L2 -> smem item slab feeds NQB x 128 queries (L2 traffic, not the tensor pipe, is
 //               the first limit at B = 4096: 32 query blocks x 5.12 GB with one block per CTA).
 //               2 TMEM accumulator sets of NQB x 128 columns.
-//   epilogue  : NQB warpgroups, thread = query row: tcgen05.ld the 128 scores of the tile and
-//               either store them (sample pass) or append (score, index) >= tau[row].
+//   epilogue  : 2 x NQB warpgroups (two 64-column halves per query block), thread = query row:
+//               tcgen05.ld the scores of the tile and either store them (sample pass) or append
+//               (score, index) >= tau[row] to the row's candidate list (one atomic per tile half).
+//               One query block for the whole launch (B <= 128, instantiation <1, SMALL>, the two
+//               passes of mips_small.cu): 16 epilogue warps (32-column quarters), group maxima of
+//               the sample tiles (GMAX) or hits appended to the thread's private sub-list (PRIVATE).
 #include "common.cuh"
 #include "mips_epilogue.cuh"
 #include "sm100_ptx.cuh"
